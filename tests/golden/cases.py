@@ -1,0 +1,64 @@
+"""Seeded inputs shared by tests/golden/make_golden.py and the parity tests.
+
+No dependency on /root/reference: the GPU box regenerates the same arrays from the same
+seeds and checks their SHA against the one stored next to the golden outputs.
+"""
+import hashlib
+
+import numpy as np
+
+from tetraear_b200 import synth
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def process_cases():
+    """(name, sample_rate, freq_offset, iq) — every input is reproducible from its seed."""
+    cases = []
+    cap = synth.make_capture(131072 * 2, 130, seed=1234)
+    cases.append(("c1_chunk0", 2.4e6, 0.0, cap[:131072]))
+    cases.append(("c1_chunk1", 2.4e6, 0.0, cap[131072:]))
+    n = 131072
+    sh = (cap[:n] * np.exp(2j * np.pi * 1234.5 * np.arange(n) / 2.4e6)).astype(np.complex64)
+    cases.append(("c1_afc", 2.4e6, 1234.5, sh))
+    rng = np.random.default_rng(5)
+    noise = (0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    cases.append(("noise", 2.4e6, 0.0, noise))
+    cases.append(("noise_afc", 2.4e6, -3210.0, noise))
+    wide = synth.make_capture(1 << 20, 83 * 13, seed=21)
+    cases.append(("wide_q83", 20e6, 0.0, wide))
+    cases.append(("wide_q83_afc", 20e6, 700.0, wide))
+    cases.append(("rate_1p8M", 1.8e6, 0.0, synth.make_capture(98000, 98, seed=3)))
+    cases.append(("rate_240k_nodecim", 240000.0, 0.0, synth.make_capture(20000, 13, seed=4)))
+    cases.append(("c128_input", 2.4e6, 0.0, cap[:40000].astype(np.complex128)))
+    cases.append(("ragged_40001", 2.4e6, 250.0, cap[:40001]))
+    for m in (1, 2, 16, 27, 28, 29, 100, 150, 160, 161, 290, 500):
+        cases.append((f"short_{m}", 2.4e6, 0.0, cap[1000:1000 + m]))
+    cases.append(("zeros", 2.4e6, 0.0, np.zeros(5000, np.complex64)))
+    return cases
+
+
+
+
+def psd_chunks():
+    """8 chunks of 131072 samples @2.4 MS/s: modem at -20 dBFS + CW spur at +7.3 kHz (C2),
+    a near-silent chunk and a strong tone."""
+    fs = 2.4e6
+    n = 131072
+    cap = synth.make_capture(n * 6, 130, seed=1234, amplitude=0.1, sigma=0.002)
+    spur = (0.03 * np.exp(2j * np.pi * 7300.0 * np.arange(len(cap)) / fs)).astype(np.complex64)
+    x = (cap + spur).astype(np.complex64)
+    rng = np.random.default_rng(8)
+    quiet = (1e-4 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    tone = (0.5 * np.exp(2j * np.pi * 3000.0 * np.arange(n) / fs)).astype(np.complex64) + quiet
+    chunks = [x[i * n:(i + 1) * n] for i in range(6)] + [quiet, tone]
+    return chunks
+
+
+def burst_batch(n=3000, seed=99):
+    d = synth.make_burst_batch(n, seed=seed)
+    d[0] = 0   # degenerate rows the reference special-cases (all-zero / all-one data)
+    d[1] = 3
+    return d

@@ -1,0 +1,181 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+Usage (from the repo root, in the container that has /root/reference):
+    python tests/golden/make_golden.py
+
+Inputs are regenerated from seeds by ``tetraear_b200.synth`` (committed), so only the
+reference's OUTPUTS (and a checksum of each input) are stored.  The reference classes are
+imported read-only through ``oracle/ref_bridge.py`` (bitstring stand-in, no bytecode).
+The PSD/AFC block is inline code inside a QThread method of ``tetraear/ui/modern.py``
+(PyQt6 is absent, the module cannot be imported), so its source LINES are read from the
+file, dedented and exec'd against a stub ``self`` — the arithmetic executed is still the
+reference's own text, not a restatement.
+"""
+import hashlib
+import logging
+import os
+import sys
+import textwrap
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+logging.disable(logging.CRITICAL)
+
+from oracle import ref_bridge  # noqa: E402
+from tetraear_b200 import synth  # noqa: E402
+from tests.golden.cases import process_cases, psd_chunks, burst_batch  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SP, TD, TP = ref_bridge.load()
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def save(name, **kw):
+    np.savez_compressed(os.path.join(HERE, name), **kw)
+    print("wrote", name, len(kw), "arrays")
+
+
+# ----------------------------------------------------------------------------- inputs
+def gen_process():
+    out = {}
+    names = []
+    for name, fs, f, iq in process_cases():
+        sp = SP(fs)
+        d = sp.process(iq, f)
+        names.append(name)
+        out[name + "/fs"] = np.float64(fs)
+        out[name + "/f"] = np.float64(f)
+        out[name + "/in_sha"] = np.array(sha(iq))
+        out[name + "/dibits"] = np.asarray(d, dtype=np.uint8)
+        out[name + "/symbols"] = np.asarray(sp.symbols)
+    out["names"] = np.array(names)
+    save("process.npz", **out)
+    return out
+
+
+def frame_summary(frames):
+    """[sync-independent] per-frame tuple: number, type, encrypted(final), burst_crc, header enc bits."""
+    rows = []
+    for fr in frames:
+        bits = np.asarray(fr["bits"])
+        rows.append([fr["number"], fr["type"], int(bits[2]) * 2 + int(bits[3]),
+                     int(bool(fr.get("burst_crc", False))), int("mac_pdu" in fr)])
+    return np.array(rows, dtype=np.int64).reshape(-1, 5)
+
+
+def gen_decode(proc):
+    out = {}
+    names = []
+    rng = np.random.default_rng(77)
+    streams = {}
+    for n in ("c1_chunk0", "c1_chunk1", "c1_afc", "noise", "wide_q83", "rate_1p8M", "ragged_40001"):
+        streams[n] = proc[n + "/dibits"]
+    # long clean stream with every burst kind, transmitted dibits directly (no modem)
+    rb = np.random.default_rng(11)
+    bits = np.concatenate([synth.make_burst(rb, k) for k in
+                           ["pass", "near", "random", "pass", "pass", "random", "near", "pass"] * 3])
+    for shift in (0, 1, 2, 3, 215, 216, 217):
+        streams[f"tx_shift{shift}"] = synth.bits_to_dibits(
+            np.concatenate([rb.integers(0, 2, shift, dtype=np.uint8), bits])[: (len(bits) + shift) // 2 * 2])
+    # corrupted training sequences: exercises the 0.85 / 0.80 / adaptive cascade
+    for nerr in (2, 3, 4, 5, 6):
+        b = bits[: 510 * 4].copy()
+        for k in range(4):
+            idx = rb.choice(22, nerr, replace=False)
+            b[510 * k + 216 + idx] ^= 1
+        streams[f"ts_err{nerr}"] = synth.bits_to_dibits(b)
+    for i in range(6):
+        streams[f"random_{i}"] = rng.integers(0, 4, 1007 + i, dtype=np.uint8)
+    streams["psk8"] = rng.integers(0, 8, 1500, dtype=np.uint8)
+    streams["tiny_10"] = rng.integers(0, 4, 10, dtype=np.uint8)
+    streams["tiny_254"] = synth.bits_to_dibits(bits[:508])
+    streams["exact_255"] = synth.bits_to_dibits(bits[:510])
+    streams["exact_256"] = synth.bits_to_dibits(bits[:512])
+    for name, d in streams.items():
+        dec = TD(auto_decrypt=False)
+        b, mapped = dec.symbols_to_bits(d)
+        frames = dec.decode(d)
+        names.append(name)
+        out[name + "/dibits"] = np.asarray(d, dtype=np.uint8)
+        out[name + "/bits"] = np.asarray(b, dtype=np.uint8)
+        out[name + "/mapped"] = np.asarray(mapped, dtype=np.uint8)
+        for thr in (0.90, 0.85, 0.80, 0.7727):
+            pos, mc = dec.find_sync(b, threshold=thr, return_max_corr=True)
+            out[name + f"/sync_{thr}"] = np.asarray(pos, dtype=np.int64)
+            out[name + f"/maxcorr_{thr}"] = np.float64(mc)
+        out[name + "/frames"] = frame_summary(frames)
+        out[name + "/frame_bits"] = (np.stack([np.asarray(f["bits"], dtype=np.uint8) for f in frames])
+                                     if frames else np.zeros((0, 510), np.uint8))
+        st = dec.protocol_parser.stats
+        out[name + "/stats"] = np.array([st["total_bursts"], st["crc_pass"], st["crc_fail"]], dtype=np.int64)
+    out["names"] = np.array(names)
+    save("decode.npz", **out)
+
+
+def gen_bursts():
+    d = burst_batch()
+    p = TP()
+    bt, ok, nd, mac = [], [], [], []
+    data = np.zeros((len(d), 510), np.uint8)
+    ts = np.zeros((len(d), 22), np.uint8)
+    for i, row in enumerate(d):
+        b = p.parse_burst(row, slot_number=i % 4)
+        bt.append(b.burst_type.value)
+        ok.append(int(bool(b.crc_ok)))
+        nd.append(len(b.data_bits))
+        data[i, :len(b.data_bits)] = b.data_bits
+        ts[i, :len(b.training_sequence)] = b.training_sequence
+        mac.append(int(TP().parse_mac_pdu(b.data_bits) is not None))
+    st = p.stats
+    crcs = np.array([int("".join(str(int(x)) for x in p._calculate_crc16(row_bits)), 2)
+                     for row_bits in data[:64, :200]], dtype=np.int64)
+    save("bursts.npz", in_sha=np.array(sha(d)), burst_type=np.array(bt, np.uint8), crc_ok=np.array(ok, np.uint8),
+         n_data=np.array(nd, np.int32), data_bits=np.packbits(data, axis=1), training=ts,
+         mac_ok=np.array(mac, np.uint8), crc16_first64=crcs,
+         stats=np.array([st["total_bursts"], st["crc_pass"], st["crc_fail"]], np.int64))
+
+
+# ------------------------------------------------------------------------------- PSD
+def _lines(path, lo, hi):
+    with open(path) as f:
+        src = f.readlines()[lo - 1:hi]
+    return textwrap.dedent("".join(src))
+
+
+def gen_psd():
+    modern = os.path.join(ref_bridge.REFERENCE_ROOT, "tetraear", "ui", "modern.py")
+    spec_src = _lines(modern, 1928, 1944)          # n_fft .. freqs_actual
+    stat_src = _lines(modern, 1953, 2010)          # signal_present .. is_signal_strong
+    ema_src = _lines(modern, 929, 937)             # denoiser EMA
+    assert "np.hanning" in spec_src and "is_signal_strong" in stat_src and "avg_factor" in ema_src
+    fs = 2.4e6
+    chunks = psd_chunks()
+    powers, stats = [], []
+    widget = types.SimpleNamespace(denoiser_enabled=True, avg_factor=0.15, smoothed_fft=None, current_fft=None)
+    smoothed = []
+    for samples in chunks:
+        ns = {"np": np, "samples": samples, "current_time": 0.0,
+              "self": types.SimpleNamespace(sample_rate=fs, frequency=390e6, last_signal_time=0.0)}
+        exec(spec_src, ns)
+        exec(stat_src, ns)
+        powers.append(ns["power"])
+        stats.append([ns["signal_power"], ns["peak_power"], ns["peak_idx"], ns["peak_freq_offset"],
+                      ns["noise_floor"], ns["snr"], float(ns["signal_present"])])
+        ens = {"np": np, "self": widget, "powers": ns["power"]}
+        exec(ema_src, ens)
+        smoothed.append(np.array(widget.current_fft))
+    save("psd.npz", in_sha=np.array(sha(np.concatenate(chunks))), power=np.stack(powers), stats=np.array(stats),
+         smoothed=np.stack(smoothed), freqs=ns["freqs"])
+
+
+if __name__ == "__main__":
+    proc = gen_process()
+    gen_decode(proc)
+    gen_bursts()
+    gen_psd()

@@ -1,0 +1,102 @@
+"""Pin the oracle (oracle/) against the golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.golden.cases import sha, psd_chunks, burst_batch
+
+
+def test_inputs_reproduce(golden_process, process_inputs):
+    for name in golden_process["names"]:
+        fs, f, iq = process_inputs[str(name)]
+        assert sha(iq) == str(golden_process[f"{name}/in_sha"]), name
+
+
+def test_process_matches_reference(golden_process, process_inputs):
+    for name in golden_process["names"]:
+        name = str(name)
+        fs, f, iq = process_inputs[name]
+        d, sym, _ = oracle.process(iq, fs, f)
+        gd, gs = golden_process[name + "/dibits"], golden_process[name + "/symbols"]
+        assert d.dtype == np.uint8 and np.array_equal(d, gd), name
+        assert len(sym) == len(gs), name
+        if len(gs):
+            scale = max(np.abs(gs).max(), 1e-30)
+            assert np.abs(np.asarray(sym) - gs).max() <= 1e-12 * scale, name
+
+
+def test_bits_sync_decode_match_reference(golden_decode):
+    g = golden_decode
+    for name in g["names"]:
+        name = str(name)
+        d = g[name + "/dibits"]
+        bits, mapped = oracle.symbols_to_bits(d)
+        assert np.array_equal(bits, g[name + "/bits"]), name
+        assert np.array_equal(mapped, g[name + "/mapped"]), name
+        for thr in (0.90, 0.85, 0.80, 0.7727):
+            pos, mc = oracle.find_sync(bits, thr)
+            assert pos == list(g[name + f"/sync_{thr}"]), (name, thr)
+            assert mc == float(g[name + f"/maxcorr_{thr}"]), (name, thr)
+        frames, stats = oracle.decode(d)
+        gf = g[name + "/frames"]
+        assert len(frames) == len(gf), name
+        for fr, row, fb in zip(frames, gf, g[name + "/frame_bits"]):
+            assert [fr["number"], fr["type"], fr["enc_mode"], int(fr["burst_crc"]), int(fr["mac_ok"])] == list(row), name
+            assert np.array_equal(fr["bits"], fb), name
+        assert [stats["total_bursts"], stats["crc_pass"], stats["crc_fail"]] == list(g[name + "/stats"]), name
+
+
+def test_parse_bursts_match_reference(golden_bursts):
+    g = golden_bursts
+    d = burst_batch()
+    assert sha(d) == str(g["in_sha"])
+    r = oracle.parse_bursts(d)
+    assert np.array_equal(r["burst_type"], g["burst_type"])
+    assert np.array_equal(r["crc_ok"], g["crc_ok"])
+    assert np.array_equal(r["n_data"], g["n_data"])
+    gbits = np.unpackbits(g["data_bits"], axis=1)[:, :510]
+    assert np.array_equal(r["data_bits"], gbits)
+    mac = np.array([oracle.mac_pdu_valid(r["data_bits"][i, :r["n_data"][i]]) for i in range(len(d))], np.uint8)
+    assert np.array_equal(mac, g["mac_ok"])
+    crcs = [oracle.crc16(gbits[i, :200]) for i in range(64)]
+    assert crcs == list(g["crc16_first64"])
+    assert [len(d), int(r["crc_ok"].sum()), int(len(d) - r["crc_ok"].sum())] == list(g["stats"])
+    # the batch must exercise every verdict
+    assert 0 < r["crc_ok"].sum() < len(d) and (r["burst_type"] == 5).any() and (g["mac_ok"] == 0).any()
+
+
+def test_psd_matches_reference(golden_psd):
+    g = golden_psd
+    chunks = psd_chunks()
+    assert sha(np.concatenate(chunks)) == str(g["in_sha"])
+    powers = []
+    for i, c in enumerate(chunks):
+        freqs, p = oracle.psd_frame(c, 2.4e6, 2048)
+        powers.append(p)
+        assert np.array_equal(freqs, g["freqs"])
+        assert np.abs(p - g["power"][i]).max() <= 1e-9
+        st = oracle.band_stats(p, 2.4e6)
+        row = g["stats"][i]
+        got = [st["signal_power"], st["peak_power"], st["peak_idx"], st["peak_freq_offset"], st["noise_floor"],
+               st["snr"], float(st["signal_present"])]
+        assert np.allclose(got, row, rtol=0, atol=1e-9), i
+    sm = oracle.ema_denoise(np.stack(powers))
+    assert np.abs(sm - g["smoothed"]).max() <= 1e-9
+    assert g["stats"][:, 6].any() and not g["stats"][:, 6].all()  # both gate outcomes covered
+
+
+def test_known_answers_from_reference_tests():
+    """The few known-answer facts the reference's own tests hold."""
+    # tests/unit/test_tetra_protocol.py:53-65: continuous-downlink pattern is a sync, zeros are not
+    row = np.zeros(255, np.uint8)
+    assert oracle.parse_bursts(row)["burst_type"][0] == 2
+    bits = np.zeros(510, np.uint8)
+    bits[255:277] = [1, 1, 0, 1, 0, 0, 0, 0, 1, 1, 1, 0, 1, 0, 0, 1, 1, 1, 0, 1, 0, 0]
+    assert oracle.parse_bursts((bits[0::2] << 1) | bits[1::2])["burst_type"][0] == 5
+    # tests/unit/test_tetra_decoder.py:49-54: < 22 bits -> no sync
+    assert oracle.find_sync(np.zeros(10, np.uint8)) == ([], 0.0)
+    # tests/unit/test_signal_processor.py:36-41, 72-86, 97-102: empty / single sample
+    assert len(oracle.process(np.array([], np.complex64), 2.4e6)[0]) == 0
+    assert len(oracle.demodulate_dqpsk(np.array([1 + 1j]))) == 0
+    assert oracle.FRAME_LENGTH == 510
