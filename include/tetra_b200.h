@@ -1,0 +1,195 @@
+/*
+ * tetra_b200.h — C-ABI of libtetra_b200.so, the B200 (sm_100a) implementation of TetraEar's
+ * IQ -> bursts receive path.
+ *
+ * The reference (WizzardDr/TetraEar-BladeRF) is pure Python and has no FFI of its own; the
+ * boundary this library replaces is the Python class API its callers import
+ * (tetraear/ui/modern.py:194-195, tetraear/signal/scanner.py:16-17).  Each entry point below
+ * names the reference method(s) whose arithmetic it performs.  The ctypes binding a
+ * maintainer adds on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, < 0 on error (TB200_E_*); the message of the last
+ *     error on the calling thread is tb200_last_error().  Nothing throws or aborts.
+ *   - pointers named d_* are DEVICE pointers owned by the caller (e.g. torch tensors'
+ *     data_ptr()); pointers named h_* are HOST pointers.  `stream` is a cudaStream_t passed
+ *     as void* (NULL = legacy default stream).  Calls are asynchronous on `stream` unless the
+ *     name ends in _host (those synchronise `stream` before returning).
+ *   - all scratch memory is allocated by tb200_create for the declared capacity; no entry
+ *     point allocates afterwards.  One handle per thread of execution; distinct handles are
+ *     independent (the reference builds fresh instances per thread, scanner.py:164-171).
+ *   - complex samples are interleaved (re, im); complex64 = 2 x float, complex128 = 2 x double.
+ */
+#ifndef TETRA_B200_H
+#define TETRA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB200_OK 0
+#define TB200_E_ARG (-1)      /* bad argument / exceeds handle capacity */
+#define TB200_E_CUDA (-2)     /* CUDA runtime error (message has the detail) */
+#define TB200_E_NODEV (-3)    /* no CUDA device: there is no CPU fallback */
+#define TB200_E_ALLOC (-4)
+
+#define TB200_DTYPE_C64 0
+#define TB200_DTYPE_C128 1
+
+/* decimator arithmetic: EXACT = scipy's float32 op order, sequential per (chunk, I/Q) lane,
+ * bit-identical to the reference; FAST = time-tiled, same filter, float32/float64 mixed,
+ * soft symbols within 1e-4 of full scale */
+#define TB200_MODE_EXACT 0
+#define TB200_MODE_FAST 1
+
+#define TB200_MAX_PHASES 32
+#define TB200_FRAME_BITS 510
+#define TB200_BURST_SYMS 255
+
+typedef struct tb200_handle_s *tb200_handle;
+
+typedef struct tb200_config {
+    double sample_rate;   /* SignalProcessor(sample_rate), processor.py:21-33 */
+    int32_t max_chunks;   /* capacity: chunks per tb200_process_batch call */
+    int32_t max_chunk_len;/* capacity: samples per chunk */
+    int32_t mode;         /* TB200_MODE_* */
+    int32_t device;       /* CUDA device ordinal */
+    int32_t max_fft;      /* capacity of the PSD path (0 -> 4096) */
+    int32_t max_bursts;   /* capacity of tb200_burst_batch_host staging (0 -> none) */
+    int32_t max_stream_len; /* capacity: dibits per stream of the decoder entry points (0 -> derived) */
+} tb200_config;
+
+/* What process() will do for (sample_rate, chunk_len): mirrors the control flow of
+ * SignalProcessor.process, processor.py:239-273 (decimate only if fs > 480 kHz and
+ * len > 27; filter only if len > 15; sps = int(rate/18000); phase step = max(1, sps/8)). */
+typedef struct tb200_plan {
+    int32_t q;            /* decimation factor actually applied (1 = none) */
+    int32_t n_dec;        /* samples after decimation */
+    int32_t filtered;     /* 1 if the Butterworth filtfilt runs */
+    int32_t sps;          /* int(rate / 18000) */
+    int32_t phase_step;   /* max(1, sps / 8) */
+    int32_t max_symbols;  /* upper bound of symbols per chunk (phase 0) */
+    double rate;          /* sample rate after decimation */
+} tb200_plan;
+
+/* one kept frame of TetraDecoder.decode (core/decoder.py:861-888 + decode_frame :890-992) */
+typedef struct tb200_frame {
+    int32_t sync_pos;     /* bit position of the training sequence */
+    int32_t start_pos;    /* sync_pos - 216 */
+    int32_t number;       /* start_pos / 510 (frame['number']); timeslot = number % 4 */
+    uint8_t type;         /* bits[0:2]  (frame['type'], decoder.py:906) */
+    uint8_t enc_mode;     /* bits[2:4]  (decoder.py:909) */
+    uint8_t burst_type;   /* BurstType value: 2 NormalDownlink, 5 Synchronization (protocol.py:34-41) */
+    uint8_t crc_ok;       /* TetraBurst.crc_ok, protocol.py:292-329 */
+    uint8_t mac_ok;       /* parse_mac_pdu() would return a PDU (protocol.py:349-596) */
+    uint8_t kept;         /* 1 unless dropped by decoder.py:1092-1100 (mac None and CRC bad) */
+    uint8_t pad[2];
+    uint8_t bits[64];     /* the 510 frame bits (frame['bits']), MSB-first packed */
+    uint8_t data[64];     /* TetraBurst.data_bits packed: 216 (normal) or 510 (sync) bits */
+} tb200_frame;
+
+/* ---- library ------------------------------------------------------------------------- */
+const char *tb200_last_error(void);
+int tb200_version(void);
+int tb200_device_count(void);   /* 0 when no usable CUDA device */
+
+/* ---- filter design: host only, no device needed -------------------------------------- */
+/* scipy.signal.decimate's filter for factor q as the reference gets it (processor.py:254):
+ * cheby1(8, 0.05, 0.8/q) SOS rows [b0 b1 b2 1 a1 a2] and sosfilt_zi, in float64 and in the
+ * float32 (complex64 arithmetic) form used for complex64 IQ. */
+int tb200_design_decimator(int q, double sos64[24], double zi64[8], float sos32[24], float zi32[8]);
+/* butter(4, clip((bw/2)/(fs/2), .01, .99)) and lfilter_zi, processor.py:70-79 */
+int tb200_design_channel_filter(double bandwidth, double fs, double b[5], double a[5], double zi[4]);
+int tb200_plan_process(double sample_rate, int chunk_len, tb200_plan *plan);
+
+/* ---- handle -------------------------------------------------------------------------- */
+int tb200_create(const tb200_config *cfg, tb200_handle *out);
+int tb200_destroy(tb200_handle h);
+int tb200_set_sample_rate(tb200_handle h, double sample_rate); /* attr is mutated live, modern.py:1857 */
+size_t tb200_workspace_bytes(tb200_handle h);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t tb200_launch_count(tb200_handle h);
+
+/* ---- SignalProcessor.process over a batch of equal-length chunks (processor.py:221-273) -
+ * d_iq        [n_chunks][chunk_stride] complex samples (dtype: TB200_DTYPE_*)
+ * d_freq_off  [n_chunks] double, Hz, or NULL for 0 (freq_offset; NCO skipped where == 0)
+ * d_dibits    [n_chunks][out_stride] uint8   demodulated symbols 0..3
+ * d_symbols   [n_chunks][out_stride] complex128 (self.symbols) or NULL
+ * d_n_dibits  [n_chunks] int32  dibits produced per chunk (symbols = dibits + 1 when > 0)
+ * d_phase     [n_chunks] int32  timing phase picked (may be NULL)                          */
+int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, int n_chunks, int chunk_len,
+                        int64_t chunk_stride, const double *d_freq_off, uint8_t *d_dibits,
+                        void *d_symbols, int out_stride, int32_t *d_n_dibits, int32_t *d_phase,
+                        void *stream);
+/* same, HOST buffers in and out: H2D of the IQ, the kernels, D2H of dibits / counts / symbols,
+ * all on `stream`, synchronised before return. */
+int tb200_process_batch_host(tb200_handle h, const void *h_iq, int dtype, int n_chunks, int chunk_len,
+                             const double *h_freq_off, uint8_t *h_dibits, void *h_symbols,
+                             int out_stride, int32_t *h_n_dibits, int32_t *h_phase, void *stream);
+
+/* ---- stage-level entry points (one array each; the per-method Python API and parity tests) */
+/* scipy.signal.decimate(x, q) (processor.py:254).  out: ceil(n/q) samples of the same dtype. */
+int tb200_decimate(tb200_handle h, const void *d_x, int dtype, int n, int q, void *d_out, void *stream);
+/* frequency_shift (processor.py:85-100): out complex128[n] = x * exp(-j 2 pi f k / fs) */
+int tb200_freq_shift(tb200_handle h, const void *d_x, int dtype, int n, double freq_offset, double fs,
+                     void *d_out_c128, void *stream);
+/* filter_signal (processor.py:51-83): Butterworth(4) filtfilt, complex128 out. n must be > 15. */
+int tb200_filter(tb200_handle h, const void *d_x, int dtype, int n, double bandwidth, double fs,
+                 void *d_out_c128, void *stream);
+/* extract_symbols (processor.py:168-219): d_n_out <- count, d_phase <- best phase */
+int tb200_extract_symbols(tb200_handle h, const void *d_x_c128, int n, double fs, void *d_out_c128,
+                          int32_t *d_n_out, int32_t *d_phase, void *stream);
+/* demodulate_dqpsk (processor.py:102-166): n complex128 symbols -> n-1 dibits */
+int tb200_demod_dqpsk(tb200_handle h, const void *d_sym_c128, int n, uint8_t *d_dibits, void *stream);
+
+/* ---- TetraDecoder (core/decoder.py) -------------------------------------------------- */
+/* symbols_to_bits (:140-169): n symbols (0..3, or 0..7 -> 8-PSK map) -> 2n bits, n mapped */
+int tb200_symbols_to_bits(tb200_handle h, const uint8_t *d_symbols, int n, uint8_t *d_bits,
+                          uint8_t *d_mapped, void *stream);
+/* find_sync (:171-295) on one bit stream: positions (<= max_pos) and count, max correlation
+ * as the match COUNT out of 22 over the positions the reference visits. */
+int tb200_find_sync(tb200_handle h, const uint8_t *d_bits, int n_bits, double threshold,
+                    int32_t *d_pos, int max_pos, int32_t *d_count, int32_t *d_max_match, void *stream);
+/* decode (:835-888) over a batch of dibit streams: threshold cascade, frame windows, header
+ * bits, parse_burst, CRC, MAC validity, drop rule.
+ * d_dibits [n_streams][stride]; d_n_dibits [n_streams] (device) ;
+ * d_frames [n_streams][max_frames] ; d_n_frames [n_streams] = sync positions examined
+ * (records with kept == 0 were dropped by the reference and must be skipped) ;
+ * d_stats  int64[3] += (total_bursts, crc_pass, crc_fail)  (protocol.py:228-232) */
+int tb200_decode_batch(tb200_handle h, const uint8_t *d_dibits, int n_streams, int stride,
+                       const int32_t *d_n_dibits, tb200_frame *d_frames, int max_frames,
+                       int32_t *d_n_frames, int64_t *d_stats, void *stream);
+
+/* ---- TetraProtocolParser.parse_burst integer path over a batch (core/protocol.py:192-347)
+ * d_dibits [n][255] ; d_rec [n][32] bytes:
+ *   [0..26] first 216 data bits packed MSB-first (normal burst: bits 0..107 ++ 122..229)
+ *   [27] burst_type (2 / 5)   [28] crc_ok   [29] mac_ok   [30] (type << 2) | enc_mode
+ *   [31] number of 1-bits in the 22-bit window compared with the sync patterns (max match)
+ * d_full [n][64] or NULL: all 510 burst bits packed (data_bits of a Synchronization burst)
+ * d_stats int64[3] += (total_bursts, crc_pass, crc_fail) or NULL */
+int tb200_burst_batch(tb200_handle h, const uint8_t *d_dibits, int64_t n, uint8_t *d_rec,
+                      uint8_t *d_full, int64_t *d_stats, void *stream);
+int tb200_burst_batch_host(tb200_handle h, const uint8_t *h_dibits, int64_t n, uint8_t *h_rec,
+                           uint8_t *h_full, int64_t *h_stats, void *stream);
+/* _calculate_crc16 (protocol.py:331-347) of n_rows bit rows of n_bits each -> uint16 */
+int tb200_crc16_rows(tb200_handle h, const uint8_t *d_bits, int n_rows, int n_bits, int row_stride,
+                     uint16_t *d_crc, void *stream);
+
+/* ---- waterfall PSD + AFC statistics (tetraear/ui/modern.py:1926-2029, :923-947) ---------
+ * frame i = Hann(n_fft) * iq[i*frame_stride : +n_fft]; power = 20 log10(|fftshift FFT|/n_fft + 1e-20)
+ * d_power    [n_frames][n_fft] float32 dB (or NULL)
+ * d_smoothed [n_frames][n_fft] float32: EMA in the dB domain, S = S(1-a) + P a (or NULL)
+ * d_ema_state [n_fft] double, carried across calls; *first* != 0 -> first frame initialises it
+ * d_stats    [n_frames][8] double: signal_power, peak_power, peak_idx, peak_freq_offset,
+ *            noise_floor, snr, signal_present, afc_offset   (modern.py:1956-2028) */
+int tb200_psd_batch(tb200_handle h, const void *d_iq_c64, int64_t n_frames, int64_t frame_stride,
+                    int n_fft, double sample_rate, double ema_alpha, int first, float *d_power,
+                    float *d_smoothed, double *d_ema_state, double *d_stats, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TETRA_B200_H */

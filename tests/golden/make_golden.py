@@ -65,8 +65,8 @@ def frame_summary(frames):
     for fr in frames:
         bits = np.asarray(fr["bits"])
         rows.append([fr["number"], fr["type"], int(bits[2]) * 2 + int(bits[3]),
-                     int(bool(fr.get("burst_crc", False))), int("mac_pdu" in fr)])
-    return np.array(rows, dtype=np.int64).reshape(-1, 5)
+                     int(bool(fr.get("burst_crc", False))), int("mac_pdu" in fr), int(bool(fr["encrypted"]))])
+    return np.array(rows, dtype=np.int64).reshape(-1, 6)
 
 
 def gen_decode(proc):

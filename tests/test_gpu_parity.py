@@ -1,0 +1,185 @@
+"""Parity of the CUDA path (through the C-ABI) against the golden vectors of the UNMODIFIED
+reference (tests/golden) and against the oracle on seeded inputs.  Needs a B200."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.golden.cases import burst_batch, psd_chunks
+
+pytestmark = pytest.mark.gpu
+
+SOFT_TOL = 1e-9      # EXACT mode: relative to max |symbol|; (north_star tolerance is 1e-4)
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import __graft_entry__ as entry
+    entry.build()
+    from tetraear_b200 import signal, core, pipeline, _lib
+    return signal, core, pipeline, _lib
+
+
+def test_process_matches_reference_golden(mods, golden_process, process_inputs):
+    signal = mods[0]
+    for name in golden_process["names"]:
+        name = str(name)
+        fs, f, iq = process_inputs[name]
+        sp = signal.SignalProcessor(fs)
+        d = sp.process(iq, f)
+        gd, gs = golden_process[name + "/dibits"], golden_process[name + "/symbols"]
+        assert d.dtype == np.uint8 and np.array_equal(d, gd), name
+        assert len(sp.symbols) == len(gs), name
+        if len(gs):
+            scale = max(np.abs(gs).max(), 1e-30)
+            assert np.abs(sp.symbols - gs).max() <= SOFT_TOL * scale, (name, np.abs(sp.symbols - gs).max() / scale)
+
+
+def test_stage_level_entry_points(mods, process_inputs):
+    signal = mods[0]
+    fs, f, iq = process_inputs["c1_chunk0"]
+    sp = signal.SignalProcessor(fs)
+    dec = sp.decimate(iq, 10)
+    ref = oracle.decimate(iq, 10)
+    assert dec.dtype == np.complex64 and np.array_equal(dec.view(np.uint32), ref.view(np.uint32))   # bit-exact float32
+    wide = process_inputs["wide_q83"][2][:200000]
+    assert np.array_equal(sp.decimate(wide, 83).view(np.uint32), oracle.decimate(wide, 83).view(np.uint32))
+    sh = sp.frequency_shift(ref, 1234.5, 240000.0)
+    assert np.abs(sh - oracle.frequency_shift(ref, 1234.5, 240000.0)).max() <= 1e-13
+    flt = sp.filter_signal(ref, 25000, 240000.0)
+    assert np.abs(flt - oracle.filter_signal(ref, 25000, 240000.0)).max() <= 1e-12
+    flt128 = sp.filter_signal(sh, 25000, 240000.0)
+    assert np.abs(flt128 - oracle.filter_signal(sh, 25000, 240000.0)).max() <= 1e-12
+    sym = sp.extract_symbols(flt, 240000.0)
+    osym, _ = oracle.extract_symbols(oracle.filter_signal(ref, 25000, 240000.0), 240000.0)
+    assert len(sym) == len(osym) and np.abs(sym - osym).max() <= 1e-12
+    assert np.array_equal(sp.demodulate_dqpsk(osym), oracle.demodulate_dqpsk(osym))
+    # reference edge cases: empty / single-sample inputs (tests/unit/test_signal_processor.py:36-41, 72-102)
+    assert len(sp.filter_signal(np.array([]))) == 0
+    assert len(sp.demodulate_dqpsk(np.array([1 + 1j]))) == 0
+    assert len(sp.extract_symbols(np.array([]))) == 0
+    custom = sp.extract_symbols(flt, sample_rate=1.0e6)
+    ocustom, _ = oracle.extract_symbols(flt, 1.0e6)
+    assert len(custom) == len(ocustom) and np.abs(custom - ocustom).max() <= 1e-12
+
+
+def test_bits_sync_decode_match_reference_golden(mods, golden_decode):
+    core = mods[1]
+    g = golden_decode
+    for name in g["names"]:
+        name = str(name)
+        d = g[name + "/dibits"]
+        dec = core.TetraDecoder(auto_decrypt=False)
+        bits, mapped = dec.symbols_to_bits(d)
+        assert np.array_equal(bits, g[name + "/bits"]), name
+        assert np.array_equal(mapped, g[name + "/mapped"]), name
+        for thr in (0.90, 0.85, 0.80, 0.7727):
+            pos, mc = dec.find_sync(bits, threshold=thr, return_max_corr=True)
+            assert pos == list(g[name + f"/sync_{thr}"]), (name, thr)
+            assert mc == float(g[name + f"/maxcorr_{thr}"]), (name, thr)
+        frames = dec.decode(d)
+        gf = g[name + "/frames"]
+        assert len(frames) == len(gf), name
+        for fr, row, fb in zip(frames, gf, g[name + "/frame_bits"]):
+            got = [fr["number"], fr["type"], int(fr["bits"][2]) * 2 + int(fr["bits"][3]), int(fr["burst_crc"]),
+                   int("mac_pdu" in fr)]
+            assert got == list(row[:5]), name
+            assert np.array_equal(np.asarray(fr["bits"]), fb), name
+            if len(row) > 5:
+                assert int(bool(fr["encrypted"])) == row[5], name
+        st = dec.protocol_parser.stats
+        assert [st["total_bursts"], st["crc_pass"], st["crc_fail"]] == list(g[name + "/stats"]), name
+
+
+def test_parse_bursts_match_reference_golden(mods, golden_bursts):
+    core = mods[1]
+    g = golden_bursts
+    d = burst_batch()
+    p = core.TetraProtocolParser()
+    r = p.parse_burst_batch(d)
+    assert np.array_equal(r["burst_type"], g["burst_type"])
+    assert np.array_equal(r["crc_ok"], g["crc_ok"])
+    assert np.array_equal(r["n_data"], g["n_data"])
+    gbits = np.unpackbits(g["data_bits"], axis=1)[:, :510]
+    assert np.array_equal(r["data_bits"], gbits)
+    assert np.array_equal(r["mac_ok"], g["mac_ok"])
+    assert [p.stats["total_bursts"], p.stats["crc_pass"], p.stats["crc_fail"]] == list(g["stats"])
+    # single-burst API, TetraBurst fields
+    for i in (0, 1, 2, 3, 50, 51, int(np.argmax(g["burst_type"] == 5))):
+        b = core.TetraProtocolParser().parse_burst(d[i], slot_number=i % 4)
+        assert b.burst_type.value == g["burst_type"][i] and bool(b.crc_ok) == bool(g["crc_ok"][i])
+        nd = int(g["n_data"][i])
+        assert np.array_equal(b.data_bits, gbits[i, :nd])
+        nt = 22 if g["burst_type"][i] == 5 else 14
+        assert np.array_equal(b.training_sequence, g["training"][i, :nt])
+    assert core.TetraProtocolParser().parse_burst(np.zeros(100, np.uint8)) is None
+    for i in range(8):
+        crc_bits = p._calculate_crc16(gbits[i, :200])
+        assert int("".join(str(int(x)) for x in crc_bits), 2) == int(g["crc16_first64"][i])
+        nd = int(g["n_data"][i])
+        assert p._check_crc(gbits[i, :nd]) == bool(g["crc_ok"][i])
+    # known answers from the reference's own tests (tests/unit/test_tetra_protocol.py:53-65)
+    assert p._check_sync_pattern(np.array(p.SYNC_CONTINUOUS_DOWNLINK)) is True
+    assert p._check_sync_pattern(np.zeros(22, dtype=int)) is False
+
+
+def test_psd_matches_reference_golden(mods, golden_psd):
+    signal = mods[0]
+    g = golden_psd
+    chunks = psd_chunks()
+    an = signal.SpectrumAnalyzer(2.4e6, 2048, ema_alpha=0.15)
+    x = np.concatenate(chunks)
+    r = an.run(x, frame_stride=131072, denoise=True)      # reference mode: first 2048 of every chunk
+    assert r["power"].shape == g["power"].shape
+    mask = g["power"] > -120.0
+    assert np.abs(r["power"] - g["power"])[mask].max() <= 1e-3      # dB, float32 output
+    assert np.abs(r["smoothed"] - g["smoothed"])[mask].max() <= 1e-3
+    assert np.array_equal(r["freqs"], g["freqs"])
+    for i, st in enumerate(r["stats"]):
+        row = g["stats"][i]
+        assert st["peak_idx"] == int(row[2]) and st["signal_present"] == bool(row[6]), i
+        got = [st["signal_power"], st["peak_power"], st["peak_freq_offset"], st["noise_floor"], st["snr"]]
+        assert np.allclose(got, row[[0, 1, 3, 4, 5]], rtol=0, atol=1e-6), i
+    f, p, st = signal.compute_spectrum(chunks[0], 2.4e6, center_freq=390e6)
+    assert np.abs(p - g["power"][0])[mask[0]].max() <= 1e-3 and f[1024] == 390e6
+    assert signal.compute_spectrum(chunks[0][:100], 2.4e6)[0] is None
+    # config mode: N = 4096 dense frames, against the numpy restatement
+    an2 = signal.SpectrumAnalyzer(2.4e6, 4096)
+    r2 = an2.run(chunks[0][:4096 * 8], denoise=True)
+    ref = np.stack([oracle.psd_frame(chunks[0][i * 4096:(i + 1) * 4096], 2.4e6, 4096)[1] for i in range(8)])
+    assert np.abs(r2["power"] - ref).max() <= 1e-3
+    assert np.abs(r2["smoothed"] - oracle.ema_denoise(ref)).max() <= 1e-3
+    for i in range(8):
+        o = oracle.band_stats(ref[i], 2.4e6)
+        assert r2["stats"][i]["peak_idx"] == o["peak_idx"] and abs(r2["stats"][i]["snr"] - o["snr"]) <= 1e-6
+
+
+def test_batched_pipeline_matches_oracle(mods):
+    pipeline, _lib = mods[2], mods[3]
+    from tetraear_b200 import synth
+    n_chunks, L = 6, 131072
+    cap = synth.make_capture(n_chunks * L, 130, seed=4321, mix=(0.6, 0.2, 0.2))
+    freq = np.array([0.0, 0.0, 500.0, 0.0, -750.25, 0.0])
+    x = cap.reshape(n_chunks, L).copy()
+    for c in range(n_chunks):
+        if freq[c]:
+            x[c] = (x[c] * np.exp(2j * np.pi * freq[c] * np.arange(L) / 2.4e6)).astype(np.complex64)
+    pipe = pipeline.ReceivePipeline(2.4e6, L, max_chunks=8, keep_symbols=True)
+    nfr, frames, stats = pipe.run_host(x, freq_off=freq)
+    ndib = pipe.n_dibits.cpu().numpy()
+    dib = pipe.dibits.cpu().numpy()
+    sym = pipe.symbols.cpu().numpy().view(np.complex128)[..., 0]
+    tot = [0, 0, 0]
+    for c in range(n_chunks):
+        od, osym, _ = oracle.process(x[c], 2.4e6, freq[c])
+        assert ndib[c] == len(od) and np.array_equal(dib[c, :ndib[c]], od), c
+        assert np.abs(sym[c, :len(osym)] - osym).max() <= SOFT_TOL * np.abs(osym).max(), c
+        ofr, ost = oracle.decode(od)
+        kept = [r for r in frames[c, :nfr[c]] if r["kept"]]
+        assert [(int(r["number"]), int(r["type"]), bool(r["crc_ok"])) for r in kept] == \
+               [(f["number"], f["type"], f["burst_crc"]) for f in ofr], c
+        for r, f in zip(kept, ofr):
+            assert np.array_equal(np.unpackbits(r["bits"])[:510], f["bits"])
+        for k, key in enumerate(("total_bursts", "crc_pass", "crc_fail")):
+            tot[k] += ost[key]
+    assert list(stats) == tot and tot[1] > 0
+    assert pipe.h.launches > 0

@@ -42,7 +42,7 @@ def test_bits_sync_decode_match_reference(golden_decode):
         gf = g[name + "/frames"]
         assert len(frames) == len(gf), name
         for fr, row, fb in zip(frames, gf, g[name + "/frame_bits"]):
-            assert [fr["number"], fr["type"], fr["enc_mode"], int(fr["burst_crc"]), int(fr["mac_ok"])] == list(row), name
+            assert [fr["number"], fr["type"], fr["enc_mode"], int(fr["burst_crc"]), int(fr["mac_ok"])] == list(row[:5]), name
             assert np.array_equal(fr["bits"], fb), name
         assert [stats["total_bursts"], stats["crc_pass"], stats["crc_fail"]] == list(g[name + "/stats"]), name
 

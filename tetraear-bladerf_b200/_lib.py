@@ -1,0 +1,133 @@
+"""ctypes binding of libtetra_b200.so (include/tetra_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a) into
+``tetraear-bladerf_b200/lib/``.  There is no CPU fallback: a missing library or a missing
+CUDA device raises ``RuntimeError`` from the first compute call.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtetra_b200.so")
+
+DTYPE_C64, DTYPE_C128 = 0, 1
+MODE_EXACT, MODE_FAST = 0, 1
+
+
+class Config(C.Structure):
+    _fields_ = [("sample_rate", C.c_double), ("max_chunks", C.c_int32), ("max_chunk_len", C.c_int32),
+                ("mode", C.c_int32), ("device", C.c_int32), ("max_fft", C.c_int32), ("max_bursts", C.c_int32),
+                ("max_stream_len", C.c_int32)]
+
+
+class Plan(C.Structure):
+    _fields_ = [("q", C.c_int32), ("n_dec", C.c_int32), ("filtered", C.c_int32), ("sps", C.c_int32),
+                ("phase_step", C.c_int32), ("max_symbols", C.c_int32), ("rate", C.c_double)]
+
+
+FRAME_DTYPE = np.dtype([("sync_pos", "<i4"), ("start_pos", "<i4"), ("number", "<i4"), ("type", "u1"),
+                        ("enc_mode", "u1"), ("burst_type", "u1"), ("crc_ok", "u1"), ("mac_ok", "u1"),
+                        ("kept", "u1"), ("pad", "u1", (2,)), ("bits", "u1", (64,)), ("data", "u1", (64,))])
+assert FRAME_DTYPE.itemsize == 148
+
+_vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+_PROTOS = {
+    "tb200_last_error": (C.c_char_p, []),
+    "tb200_version": (_i, []),
+    "tb200_device_count": (_i, []),
+    "tb200_design_decimator": (_i, [_i, _vp, _vp, _vp, _vp]),
+    "tb200_design_channel_filter": (_i, [_d, _d, _vp, _vp, _vp]),
+    "tb200_plan_process": (_i, [_d, _i, C.POINTER(Plan)]),
+    "tb200_create": (_i, [C.POINTER(Config), C.POINTER(_vp)]),
+    "tb200_destroy": (_i, [_vp]),
+    "tb200_set_sample_rate": (_i, [_vp, _d]),
+    "tb200_workspace_bytes": (C.c_size_t, [_vp]),
+    "tb200_launch_count": (_i64, [_vp]),
+    "tb200_process_batch": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "tb200_process_batch_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "tb200_decimate": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "tb200_freq_shift": (_i, [_vp, _vp, _i, _i, _d, _d, _vp, _vp]),
+    "tb200_filter": (_i, [_vp, _vp, _i, _i, _d, _d, _vp, _vp]),
+    "tb200_extract_symbols": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp, _vp]),
+    "tb200_demod_dqpsk": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "tb200_symbols_to_bits": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "tb200_find_sync": (_i, [_vp, _vp, _i, _d, _vp, _i, _vp, _vp, _vp]),
+    "tb200_decode_batch": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "tb200_burst_batch": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "tb200_burst_batch_host": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "tb200_crc16_rows": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "tb200_psd_batch": (_i, [_vp, _vp, _i64, _i64, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
+}
+EXPORTS = tuple(_PROTOS)
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no device needed for this step)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(nvcc, sm_100a). tetraear_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().tb200_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(f"libtetra_b200 error {rc}: {last_error()}")
+
+
+def require_device():
+    lib = load()
+    if lib.tb200_device_count() <= 0:
+        raise RuntimeError("tetraear_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return lib
+
+
+def plan(sample_rate, chunk_len):
+    p = Plan()
+    check(load().tb200_plan_process(float(sample_rate), int(chunk_len), C.byref(p)))
+    return p
+
+
+class Handle:
+    """RAII wrapper of tb200_handle."""
+
+    def __init__(self, sample_rate=2.4e6, max_chunks=1, max_chunk_len=131072, mode=MODE_EXACT, device=0,
+                 max_fft=4096, max_bursts=0, max_stream_len=0):
+        self.lib = require_device()
+        self.cfg = Config(float(sample_rate), int(max_chunks), int(max_chunk_len), int(mode), int(device),
+                          int(max_fft), int(max_bursts), int(max_stream_len))
+        self.h = _vp()
+        check(self.lib.tb200_create(C.byref(self.cfg), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.tb200_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.lib.tb200_launch_count(self.h))
+
+    @property
+    def workspace_bytes(self):
+        return int(self.lib.tb200_workspace_bytes(self.h))

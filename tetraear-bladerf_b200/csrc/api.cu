@@ -1,0 +1,422 @@
+// api.cu — the C-ABI of libtetra_b200 (include/tetra_b200.h): handle, workspace, entry points.
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include "common.h"
+#include "kernels.h"
+
+namespace tb200 {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int ensure_crc_tables(int device);
+int launch_decimate_fast(tb200_handle h, const void *x, int n_chunks, long n, long chunk_stride, int q,
+                         const DecimDesign &d, void *dec_out, long n_dec, cudaStream_t st);
+
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct Carver {
+    char *base;
+    size_t off;
+    template <typename T> T *take(size_t bytes)
+    {
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += align_up(bytes);
+        return p;
+    }
+};
+
+// lay out (or, with base == nullptr, just size) the workspace of a handle
+static size_t carve(tb200_handle h, char *base)
+{
+    Carver c{base, 0};
+    const tb200_config &cfg = h->cfg;
+    const size_t C = (size_t)cfg.max_chunks, L = (size_t)cfg.max_chunk_len;
+    const tb200_plan &P = h->plan;
+    const size_t ND = (size_t)P.n_dec;
+    if (C && L) {
+        h->fwd_bytes = C * 2 * (L + 54) * sizeof(float);
+        h->fwd = c.take<char>(h->fwd_bytes);
+        h->dec_bytes = C * (L / 2 + 2) * 16;
+        h->dec_out = c.take<char>(h->dec_bytes);
+        h->chan_bytes = C * 2 * (ND + 30) * sizeof(double);
+        h->chan_fwd = c.take<double>(h->chan_bytes);
+        h->filt_bytes = C * ND * 16;
+        h->filtered = c.take<double>(h->filt_bytes);
+        h->n_sym = c.take<int32_t>(C * sizeof(int32_t));
+    } else {
+        h->fwd = h->dec_out = nullptr; h->chan_fwd = h->filtered = nullptr; h->n_sym = nullptr;
+        h->fwd_bytes = h->dec_bytes = h->chan_bytes = h->filt_bytes = 0;
+    }
+    // decode: per stream a bit row of bits_stride bytes
+    size_t S = (size_t)h->max_streams, B = (size_t)h->bits_stride;
+    h->bits = c.take<uint8_t>(S * B);
+    h->mapped = c.take<uint8_t>(S * B / 2);
+    h->m1 = c.take<uint8_t>(S * B);
+    h->m2 = c.take<uint8_t>(S * B);
+    h->sync_pos = c.take<int32_t>(S * (size_t)h->max_frames * sizeof(int32_t));
+    h->sync_cnt = c.take<int32_t>(64);
+    size_t nf = (size_t)cfg.max_fft;
+    h->psd_tables = c.take<double>((nf + 2 * (nf / 2 + nf / 4 + 1)) * sizeof(double));
+    // staging for *_host
+    h->stage_in_bytes = C * L * 8;
+    h->stage_in = c.take<char>(h->stage_in_bytes);
+    h->stage_out_stride = (size_t)P.max_symbols + 8;
+    h->stage_dibits = c.take<uint8_t>(C * h->stage_out_stride);
+    h->stage_symbols = c.take<char>(C * h->stage_out_stride * 16);
+    h->stage_counts = c.take<int32_t>(2 * C * sizeof(int32_t) + 64);
+    h->stage_freq = c.take<double>(C * sizeof(double) + 64);
+    size_t NB = (size_t)cfg.max_bursts;
+    h->stage_burst_in = c.take<uint8_t>(NB * 255);
+    h->stage_burst_rec = c.take<uint8_t>(NB * 32);
+    h->stage_burst_full = c.take<uint8_t>(NB * 64);
+    h->stage_stats = c.take<int64_t>(64);
+    return c.off;
+}
+
+static int refresh_designs(tb200_handle h)
+{
+    int rc = tb200_plan_process(h->cfg.sample_rate, h->cfg.max_chunk_len, &h->plan);
+    if (rc) return rc;
+    h->dec_q = 0;
+    h->chan_rate = h->chan_bw = -1.0;
+    return TB200_OK;
+}
+
+static int get_decim(tb200_handle h, int q)
+{
+    if (h->dec_q == q) return TB200_OK;
+    int rc = tb200_design_decimator(q, h->dec.sos64, h->dec.zi64, h->dec.sos32, h->dec.zi32);
+    if (rc) return rc;
+    h->dec_q = q;
+    return TB200_OK;
+}
+
+static int get_chan(tb200_handle h, double bw, double rate)
+{
+    if (h->chan_rate == rate && h->chan_bw == bw) return TB200_OK;
+    int rc = tb200_design_channel_filter(bw, rate, h->chan.b, h->chan.a, h->chan.zi);
+    if (rc) return rc;
+    h->chan_rate = rate; h->chan_bw = bw;
+    return TB200_OK;
+}
+
+}  // namespace tb200
+
+using namespace tb200;
+
+extern "C" const char *tb200_last_error(void) { return g_err; }
+extern "C" int tb200_version(void) { return 100; }
+
+extern "C" int tb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int tb200_create(const tb200_config *cfg, tb200_handle *out)
+{
+    if (!cfg || !out) return fail(TB200_E_ARG, "tb200_create: null argument");
+    if (cfg->max_chunks < 0 || cfg->max_chunk_len < 0 || !(cfg->sample_rate > 0))
+        return fail(TB200_E_ARG, "tb200_create: bad capacity / sample rate");
+    int ndev = tb200_device_count();
+    if (ndev <= 0) return fail(TB200_E_NODEV, "tb200_create: no CUDA device visible (there is no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(TB200_E_ARG, "tb200_create: device %d of %d", cfg->device, ndev);
+    TB_CUDA(cudaSetDevice(cfg->device));
+    tb200_handle h = new (std::nothrow) tb200_handle_s();
+    if (!h) return fail(TB200_E_ALLOC, "tb200_create: out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    if (h->cfg.max_fft <= 0) h->cfg.max_fft = 4096;
+    int rc = refresh_designs(h);
+    if (rc) { delete h; return rc; }
+    h->max_streams = cfg->max_chunks > 0 ? cfg->max_chunks : 1;
+    long per_stream = h->plan.max_symbols + 8;
+    if (per_stream < 4096) per_stream = 4096;
+    if (cfg->max_stream_len > per_stream) per_stream = cfg->max_stream_len;
+    h->bits_stride = 2 * ((per_stream + 127) / 128 * 128);
+    h->max_frames = (int)(h->bits_stride / 250 + 2);
+    h->psd_tables_n = 0;
+    h->ws_bytes = carve(h, nullptr);
+    cudaError_t e = cudaMalloc(&h->ws, h->ws_bytes);
+    if (e != cudaSuccess) {
+        size_t want = h->ws_bytes;
+        delete h;
+        return fail(TB200_E_ALLOC, "tb200_create: cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    }
+    carve(h, (char *)h->ws);
+    rc = ensure_crc_tables(cfg->device);
+    if (rc) { cudaFree(h->ws); delete h; return rc; }
+    *out = h;
+    return TB200_OK;
+}
+
+extern "C" int tb200_destroy(tb200_handle h)
+{
+    if (!h) return TB200_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->ws) cudaFree(h->ws);
+    delete h;
+    return TB200_OK;
+}
+
+extern "C" int tb200_set_sample_rate(tb200_handle h, double sample_rate)
+{
+    if (!h || !(sample_rate > 0)) return fail(TB200_E_ARG, "tb200_set_sample_rate: bad argument");
+    tb200_handle_s probe = *h;
+    probe.cfg.sample_rate = sample_rate;
+    int rc = refresh_designs(&probe);
+    if (rc) return rc;
+    probe.bits_stride = h->bits_stride; probe.max_frames = h->max_frames; probe.max_streams = h->max_streams;
+    if (probe.plan.max_symbols + 8 > h->bits_stride / 2 || carve(&probe, nullptr) > h->ws_bytes)
+        return fail(TB200_E_ARG, "tb200_set_sample_rate: %g Hz needs a larger workspace; create a new handle", sample_rate);
+    probe.ws = h->ws; probe.ws_bytes = h->ws_bytes; probe.launches = h->launches; probe.psd_tables_n = 0;
+    carve(&probe, (char *)h->ws);
+    *h = probe;
+    return TB200_OK;
+}
+
+extern "C" size_t tb200_workspace_bytes(tb200_handle h) { return h ? h->ws_bytes : 0; }
+extern "C" int64_t tb200_launch_count(tb200_handle h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------- process
+extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, int n_chunks, int chunk_len,
+                                   int64_t chunk_stride, const double *d_freq_off, uint8_t *d_dibits,
+                                   void *d_symbols, int out_stride, int32_t *d_n_dibits, int32_t *d_phase,
+                                   void *stream)
+{
+    if (!h || !d_n_dibits || n_chunks < 0 || chunk_len < 0) return fail(TB200_E_ARG, "tb200_process_batch: bad argument");
+    if (dtype != TB200_DTYPE_C64 && dtype != TB200_DTYPE_C128) return fail(TB200_E_ARG, "tb200_process_batch: dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_chunks == 0) return TB200_OK;
+    if (n_chunks > h->cfg.max_chunks || chunk_len > h->cfg.max_chunk_len)
+        return fail(TB200_E_ARG, "tb200_process_batch: %d x %d exceeds the handle capacity %d x %d", n_chunks, chunk_len,
+                    h->cfg.max_chunks, h->cfg.max_chunk_len);
+    if (chunk_len == 0) {                                            // processor.py:239-241
+        TB_CUDA(cudaMemsetAsync(d_n_dibits, 0, sizeof(int32_t) * n_chunks, st));
+        if (d_phase) TB_CUDA(cudaMemsetAsync(d_phase, 0, sizeof(int32_t) * n_chunks, st));
+        return TB200_OK;
+    }
+    if (!d_iq || !d_dibits) return fail(TB200_E_ARG, "tb200_process_batch: null buffer");
+    if (chunk_stride < chunk_len) return fail(TB200_E_ARG, "tb200_process_batch: chunk_stride < chunk_len");
+    tb200_plan P;
+    int rc = tb200_plan_process(h->cfg.sample_rate, chunk_len, &P);
+    if (rc) return rc;
+    if (out_stride < P.max_symbols) return fail(TB200_E_ARG, "tb200_process_batch: out_stride %d < %d symbols", out_stride, P.max_symbols);
+    const size_t esz = dtype == TB200_DTYPE_C64 ? 4 : 8;
+    const void *x = d_iq;
+    long in_stride = (long)chunk_stride;
+    int cur_dtype = dtype;
+    if (P.q > 1) {
+        rc = get_decim(h, P.q);
+        if (rc) return rc;
+        if ((size_t)n_chunks * P.n_dec * 2 * esz > h->dec_bytes)
+            return fail(TB200_E_ARG, "tb200_process_batch: decimated batch exceeds workspace");
+        if (h->cfg.mode == TB200_MODE_FAST && dtype == TB200_DTYPE_C64) {
+            rc = launch_decimate_fast(h, d_iq, n_chunks, chunk_len, (long)chunk_stride, P.q, h->dec, h->dec_out, P.n_dec, st);
+        } else {
+            if ((size_t)n_chunks * 2 * (chunk_len + 54) * esz > h->fwd_bytes)
+                return fail(TB200_E_ARG, "tb200_process_batch: batch exceeds the decimator scratch (complex128 input needs 2x)");
+            rc = launch_decimate_exact(h, d_iq, dtype, n_chunks, chunk_len, (long)chunk_stride, P.q, h->dec, h->fwd,
+                                       h->dec_out, P.n_dec, st);
+        }
+        if (rc) return rc;
+        x = h->dec_out;
+        in_stride = P.n_dec;
+    }
+    if ((size_t)n_chunks * 2 * (P.n_dec + 30) * sizeof(double) > h->chan_bytes || (size_t)n_chunks * P.n_dec * 16 > h->filt_bytes)
+        return fail(TB200_E_ARG, "tb200_process_batch: batch exceeds the channel-filter workspace");
+    rc = get_chan(h, 25000.0, P.rate);
+    if (rc) return rc;
+    rc = launch_channel_exact(h, x, cur_dtype, n_chunks, P.n_dec, in_stride, d_freq_off, P.rate, h->chan, P.filtered,
+                              h->chan_fwd, h->filtered, P.n_dec, st);
+    if (rc) return rc;
+    return launch_symbols(h, h->filtered, n_chunks, P.n_dec, P.n_dec, P.sps, P.phase_step, (double *)d_symbols, d_dibits,
+                          out_stride, d_n_dibits, nullptr, d_phase, st);
+}
+
+extern "C" int tb200_process_batch_host(tb200_handle h, const void *h_iq, int dtype, int n_chunks, int chunk_len,
+                                        const double *h_freq_off, uint8_t *h_dibits, void *h_symbols, int out_stride,
+                                        int32_t *h_n_dibits, int32_t *h_phase, void *stream)
+{
+    if (!h || !h_n_dibits) return fail(TB200_E_ARG, "tb200_process_batch_host: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_chunks <= 0) return TB200_OK;
+    if (n_chunks > h->cfg.max_chunks || chunk_len > h->cfg.max_chunk_len)
+        return fail(TB200_E_ARG, "tb200_process_batch_host: exceeds the handle capacity");
+    const size_t esz = dtype == TB200_DTYPE_C64 ? 8 : 16;
+    size_t in_bytes = (size_t)n_chunks * chunk_len * esz;
+    if (in_bytes > h->stage_in_bytes) return fail(TB200_E_ARG, "tb200_process_batch_host: input exceeds staging (complex128 needs 2x)");
+    if ((size_t)out_stride > h->stage_out_stride) return fail(TB200_E_ARG, "tb200_process_batch_host: out_stride too large");
+    if (in_bytes) TB_CUDA(cudaMemcpyAsync(h->stage_in, h_iq, in_bytes, cudaMemcpyHostToDevice, st));
+    double *d_f = nullptr;
+    if (h_freq_off) {
+        TB_CUDA(cudaMemcpyAsync(h->stage_freq, h_freq_off, sizeof(double) * n_chunks, cudaMemcpyHostToDevice, st));
+        d_f = h->stage_freq;
+    }
+    int32_t *d_cnt = h->stage_counts, *d_ph = h->stage_counts + n_chunks;
+    int rc = tb200_process_batch(h, h->stage_in, dtype, n_chunks, chunk_len, chunk_len, d_f, h->stage_dibits,
+                                 h_symbols ? h->stage_symbols : nullptr, out_stride, d_cnt, d_ph, stream);
+    if (rc) return rc;
+    if (h_dibits) TB_CUDA(cudaMemcpyAsync(h_dibits, h->stage_dibits, (size_t)n_chunks * out_stride, cudaMemcpyDeviceToHost, st));
+    if (h_symbols) TB_CUDA(cudaMemcpyAsync(h_symbols, h->stage_symbols, (size_t)n_chunks * out_stride * 16, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaMemcpyAsync(h_n_dibits, d_cnt, sizeof(int32_t) * n_chunks, cudaMemcpyDeviceToHost, st));
+    if (h_phase) TB_CUDA(cudaMemcpyAsync(h_phase, d_ph, sizeof(int32_t) * n_chunks, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    return TB200_OK;
+}
+
+// ------------------------------------------------------------------------- stage level
+extern "C" int tb200_decimate(tb200_handle h, const void *d_x, int dtype, int n, int q, void *d_out, void *stream)
+{
+    if (!h || !d_x || !d_out || q < 2) return fail(TB200_E_ARG, "tb200_decimate: bad argument");
+    if (n <= 27) return fail(TB200_E_ARG, "The length of the input vector x must be greater than padlen, which is 27.");
+    const size_t esz = dtype == TB200_DTYPE_C64 ? 4 : 8;
+    if ((size_t)2 * (n + 54) * esz > h->fwd_bytes) return fail(TB200_E_ARG, "tb200_decimate: n exceeds the handle capacity");
+    int rc = get_decim(h, q);
+    if (rc) return rc;
+    long n_dec = (n + q - 1) / q;
+    return launch_decimate_exact(h, d_x, dtype, 1, n, n, q, h->dec, h->fwd, d_out, n_dec, (cudaStream_t)stream);
+}
+
+extern "C" int tb200_freq_shift(tb200_handle h, const void *d_x, int dtype, int n, double freq_offset, double fs,
+                                void *d_out_c128, void *stream)
+{
+    if (!h || n < 0 || (n && (!d_x || !d_out_c128))) return fail(TB200_E_ARG, "tb200_freq_shift: bad argument");
+    return launch_freq_shift(h, d_x, dtype, n, freq_offset, fs, (double *)d_out_c128, (cudaStream_t)stream);
+}
+
+extern "C" int tb200_filter(tb200_handle h, const void *d_x, int dtype, int n, double bandwidth, double fs,
+                            void *d_out_c128, void *stream)
+{
+    if (!h || !d_x || !d_out_c128) return fail(TB200_E_ARG, "tb200_filter: bad argument");
+    if (n <= 15) return fail(TB200_E_ARG, "The length of the input vector x must be greater than padlen, which is 15.");
+    if ((size_t)2 * (n + 30) * sizeof(double) > h->chan_bytes) return fail(TB200_E_ARG, "tb200_filter: n exceeds the handle capacity");
+    int rc = get_chan(h, bandwidth, fs);
+    if (rc) return rc;
+    return launch_channel_exact(h, d_x, dtype, 1, n, n, nullptr, fs, h->chan, 1, h->chan_fwd, (double *)d_out_c128, n,
+                                (cudaStream_t)stream);
+}
+
+extern "C" int tb200_extract_symbols(tb200_handle h, const void *d_x_c128, int n, double fs, void *d_out_c128,
+                                     int32_t *d_n_out, int32_t *d_phase, void *stream)
+{
+    if (!h || n < 0 || !d_n_out) return fail(TB200_E_ARG, "tb200_extract_symbols: bad argument");
+    int sps = (int)(fs / 18000);
+    int step = sps / 8 > 1 ? sps / 8 : 1;
+    long cap = sps > 1 ? n / sps + 1 : n;
+    return launch_symbols(h, (const double *)d_x_c128, 1, n, n, sps, step, (double *)d_out_c128, nullptr, cap, nullptr,
+                          d_n_out, d_phase, (cudaStream_t)stream);
+}
+
+extern "C" int tb200_demod_dqpsk(tb200_handle h, const void *d_sym_c128, int n, uint8_t *d_dibits, void *stream)
+{
+    if (!h || n < 0) return fail(TB200_E_ARG, "tb200_demod_dqpsk: bad argument");
+    return launch_slicer(h, (const double *)d_sym_c128, n, d_dibits, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------- decoder
+extern "C" int tb200_symbols_to_bits(tb200_handle h, const uint8_t *d_symbols, int n, uint8_t *d_bits, uint8_t *d_mapped,
+                                     void *stream)
+{
+    if (!h || n < 0 || (n && (!d_symbols || !d_bits))) return fail(TB200_E_ARG, "tb200_symbols_to_bits: bad argument");
+    if (n == 0) return TB200_OK;
+    // mapped is written at bits_stride/2 pitch: with one stream the pitch is irrelevant
+    return launch_symbols_to_bits(h, d_symbols, 1, n, nullptr, n, d_bits, d_mapped, 2L * n, (cudaStream_t)stream);
+}
+
+extern "C" int tb200_find_sync(tb200_handle h, const uint8_t *d_bits, int n_bits, double threshold, int32_t *d_pos,
+                               int max_pos, int32_t *d_count, int32_t *d_max_match, void *stream)
+{
+    if (!h || n_bits < 0 || !d_count || !d_max_match) return fail(TB200_E_ARG, "tb200_find_sync: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_bits < 22) {                                               // decoder.py:201-204
+        TB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int32_t), st));
+        TB_CUDA(cudaMemsetAsync(d_max_match, 0, sizeof(int32_t), st));
+        return TB200_OK;
+    }
+    if ((long)n_bits > h->bits_stride * h->max_streams) return fail(TB200_E_ARG, "tb200_find_sync: n_bits exceeds the handle capacity");
+    int rc = launch_sync_corr(h, d_bits, 1, n_bits, nullptr, n_bits, h->m1, h->m2, st);
+    if (rc) return rc;
+    return launch_find_sync(h, h->m1, h->m2, n_bits, threshold, d_pos, max_pos, d_count, d_max_match, st);
+}
+
+extern "C" int tb200_decode_batch(tb200_handle h, const uint8_t *d_dibits, int n_streams, int stride,
+                                  const int32_t *d_n_dibits, tb200_frame *d_frames, int max_frames, int32_t *d_n_frames,
+                                  int64_t *d_stats, void *stream)
+{
+    if (!h || n_streams < 0 || stride < 0 || !d_n_dibits || !d_frames || !d_n_frames)
+        return fail(TB200_E_ARG, "tb200_decode_batch: bad argument");
+    if (n_streams == 0) return TB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long bstride = 2L * stride;
+    if ((size_t)n_streams * bstride > (size_t)h->max_streams * h->bits_stride)
+        return fail(TB200_E_ARG, "tb200_decode_batch: %d x %d dibits exceed the handle capacity", n_streams, stride);
+    if ((size_t)n_streams * max_frames > (size_t)h->max_streams * h->max_frames)
+        return fail(TB200_E_ARG, "tb200_decode_batch: max_frames too large for the handle");
+    if (stride == 0) { TB_CUDA(cudaMemsetAsync(d_n_frames, 0, sizeof(int32_t) * n_streams, st)); return TB200_OK; }
+    int rc = launch_symbols_to_bits(h, d_dibits, n_streams, stride, d_n_dibits, 0, h->bits, h->mapped, bstride, st);
+    if (rc) return rc;
+    rc = launch_sync_corr(h, h->bits, n_streams, bstride, d_n_dibits, 0, h->m1, h->m2, st);
+    if (rc) return rc;
+    return launch_decode(h, h->bits, h->mapped, h->m1, h->m2, n_streams, bstride, d_n_dibits, d_frames, max_frames,
+                         d_n_frames, d_stats, st);
+}
+
+extern "C" int tb200_burst_batch(tb200_handle h, const uint8_t *d_dibits, int64_t n, uint8_t *d_rec, uint8_t *d_full,
+                                 int64_t *d_stats, void *stream)
+{
+    if (!h || n < 0 || (n && (!d_dibits || !d_rec))) return fail(TB200_E_ARG, "tb200_burst_batch: bad argument");
+    return launch_burst_batch(h, d_dibits, n, d_rec, d_full, d_stats, (cudaStream_t)stream);
+}
+
+extern "C" int tb200_burst_batch_host(tb200_handle h, const uint8_t *h_dibits, int64_t n, uint8_t *h_rec, uint8_t *h_full,
+                                      int64_t *h_stats, void *stream)
+{
+    if (!h || n < 0 || (n && (!h_dibits || !h_rec))) return fail(TB200_E_ARG, "tb200_burst_batch_host: bad argument");
+    if (n > h->cfg.max_bursts) return fail(TB200_E_ARG, "tb200_burst_batch_host: %lld bursts exceed max_bursts %d", (long long)n, h->cfg.max_bursts);
+    if (n == 0) return TB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    TB_CUDA(cudaMemcpyAsync(h->stage_burst_in, h_dibits, (size_t)n * 255, cudaMemcpyHostToDevice, st));
+    if (h_stats) TB_CUDA(cudaMemsetAsync(h->stage_stats, 0, 3 * sizeof(int64_t), st));
+    int rc = launch_burst_batch(h, h->stage_burst_in, n, h->stage_burst_rec, h_full ? h->stage_burst_full : nullptr,
+                                h_stats ? h->stage_stats : nullptr, st);
+    if (rc) return rc;
+    TB_CUDA(cudaMemcpyAsync(h_rec, h->stage_burst_rec, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    if (h_full) TB_CUDA(cudaMemcpyAsync(h_full, h->stage_burst_full, (size_t)n * 64, cudaMemcpyDeviceToHost, st));
+    int64_t tmp[3];
+    if (h_stats) TB_CUDA(cudaMemcpyAsync(tmp, h->stage_stats, sizeof(tmp), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    if (h_stats) for (int i = 0; i < 3; ++i) h_stats[i] += tmp[i];
+    return TB200_OK;
+}
+
+extern "C" int tb200_crc16_rows(tb200_handle h, const uint8_t *d_bits, int n_rows, int n_bits, int row_stride,
+                                uint16_t *d_crc, void *stream)
+{
+    if (!h || n_rows < 0 || n_bits < 0 || !d_crc) return fail(TB200_E_ARG, "tb200_crc16_rows: bad argument");
+    return launch_crc16_rows(h, d_bits, n_rows, n_bits, row_stride, d_crc, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------- PSD
+extern "C" int tb200_psd_batch(tb200_handle h, const void *d_iq_c64, int64_t n_frames, int64_t frame_stride, int n_fft,
+                               double sample_rate, double ema_alpha, int first, float *d_power, float *d_smoothed,
+                               double *d_ema_state, double *d_stats, void *stream)
+{
+    if (!h || n_frames < 0 || !d_iq_c64) return fail(TB200_E_ARG, "tb200_psd_batch: bad argument");
+    if (n_fft < 16 || (n_fft & (n_fft - 1)) || n_fft > h->cfg.max_fft)
+        return fail(TB200_E_ARG, "tb200_psd_batch: n_fft must be a power of two in [16, %d]", h->cfg.max_fft);
+    if (d_smoothed && (!d_power || !d_ema_state)) return fail(TB200_E_ARG, "tb200_psd_batch: smoothing needs d_power and d_ema_state");
+    return launch_psd(h, (const float *)d_iq_c64, n_frames, frame_stride, n_fft, sample_rate, ema_alpha, first, d_power,
+                      d_smoothed, d_ema_state, d_stats, h->psd_tables, (cudaStream_t)stream);
+}

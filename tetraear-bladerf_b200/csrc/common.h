@@ -1,0 +1,72 @@
+// common.h — shared host-side declarations of libtetra_b200 (internal).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../include/tetra_b200.h"
+
+namespace tb200 {
+
+int fail(int code, const char *fmt, ...);
+
+#define TB_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return tb200::fail(TB200_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                               __FILE__, __LINE__);                                            \
+    } while (0)
+
+#define TB_LAUNCH_CHECK(h)                                                                     \
+    do {                                                                                       \
+        (h)->launches++;                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess)                                                                 \
+            return tb200::fail(TB200_E_CUDA, "kernel launch failed: %s (%s:%d)",               \
+                               cudaGetErrorString(_e), __FILE__, __LINE__);                    \
+    } while (0)
+
+// Filter constants for one (sample_rate) setting, as kernels take them (by value).
+struct DecimDesign {
+    float sos32[24];
+    float zi32[8];
+    double sos64[24];
+    double zi64[8];
+};
+struct ChanDesign {
+    double b[5];
+    double a[5];
+    double zi[4];
+};
+
+}  // namespace tb200
+
+struct tb200_handle_s {
+    tb200_config cfg;
+    int64_t launches;
+    tb200_plan plan;             // for (cfg.sample_rate, cfg.max_chunk_len)
+    // cached designs
+    int dec_q;                   // q the decimator design below is for (0 = none)
+    tb200::DecimDesign dec;
+    double chan_rate, chan_bw;   // (rate, bandwidth) the channel design below is for
+    tb200::ChanDesign chan;
+    // workspace: one device allocation, carved
+    void *ws;
+    size_t ws_bytes;
+    void *fwd;        size_t fwd_bytes;       // decimator forward scratch [time][lane]
+    void *dec_out;    size_t dec_bytes;       // decimated chunks (complex f32 / f64)
+    double *chan_fwd; size_t chan_bytes;      // channel-filter forward scratch [time][lane]
+    double *filtered; size_t filt_bytes;      // complex128 [chunk][n_dec]
+    int32_t *n_sym;                           // [chunks] symbols per chunk
+    // decode
+    int max_streams; long bits_stride; int max_frames;
+    uint8_t *bits, *mapped, *m1, *m2;
+    int32_t *sync_pos, *sync_cnt;             // [streams][max_frames], [2]
+    // psd
+    double *psd_tables; int psd_tables_n;
+    // staging for the *_host entry points
+    void *stage_in;   size_t stage_in_bytes;
+    uint8_t *stage_dibits; void *stage_symbols; int32_t *stage_counts; double *stage_freq;
+    size_t stage_out_stride;
+    uint8_t *stage_burst_in, *stage_burst_rec, *stage_burst_full; int64_t *stage_stats;
+};

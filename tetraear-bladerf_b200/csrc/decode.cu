@@ -1,0 +1,504 @@
+// decode.cu — the integer half of the path: TetraDecoder.symbols_to_bits / find_sync / decode
+// (/root/reference/tetraear/core/decoder.py:140-295, :835-992) and
+// TetraProtocolParser.parse_burst with its CRC (/root/reference/tetraear/core/protocol.py:192-347).
+//
+// Design: byte work, HBM bound.  A burst is 255 dibits = 255 bytes: one warp takes one burst,
+// each lane loads 8 consecutive dibits (a coalesced 255-byte row per warp) and keeps its 16
+// bits in one register; every later step (pattern match, data-bit gather, CRC, header
+// fields) is a warp-shuffle exchange on those registers, nothing goes back to memory until
+// the 32-byte record is written.  The CRC-16 is linear over GF(2), so instead of a 200-step
+// serial shift register each lane XORs the precomputed contribution of its own 1-bits and
+// the warp XOR-reduces (5 shuffles) — forward and bit-reversed payload in the same pass.
+#include "common.h"
+#include "kernels.h"
+
+namespace tb200 {
+
+__constant__ uint8_t c_ts1[22] = {1,1,0,1,0,0,0,0,1,1,1,0,1,0,0,1,1,1,0,1,0,0};   // decoder.py:197
+__constant__ uint8_t c_ts2[22] = {0,1,1,1,1,0,1,0,0,1,0,0,0,0,1,1,0,1,1,1,0,0};   // decoder.py:198
+// protocol.py:162-163 as 22-bit words, first bit = MSB
+#define SYNC_CONT_W 0x343A74u  /* 1101000011101001110100 */
+#define SYNC_DISC_W 0x0E90D3u  /* 0011101001000011010011 */
+
+// crc_tab[k] = state reached from e15 after k register steps (k = 1..511); crc_init[n] is
+// folded in by the kernels (M^n * 0xFFFF) for the two payload lengths in use.
+__device__ uint16_t g_crc_tab[512];
+__device__ uint16_t g_crc_init[512];
+static bool g_crc_ready[64] = {false};
+
+static void build_crc_tables(uint16_t *tab, uint16_t *init)
+{
+    // one register step without input: M(s)
+    auto stepf = [](uint16_t s) -> uint16_t { return (s & 0x8000) ? (uint16_t)((s << 1) ^ 0x1021) : (uint16_t)(s << 1); };
+    // contribution of a 1-bit whose own step is the first of k steps: M^k applied to e15 ... the bit is
+    // XORed in BEFORE the shift (protocol.py:337-343), so k steps act on 0x8000.
+    uint16_t s = 0x8000;
+    tab[0] = 0;
+    for (int k = 1; k < 512; ++k) { s = stepf(s); tab[k] = s; }
+    uint16_t r = 0xFFFF;
+    init[0] = r;
+    for (int n = 1; n < 512; ++n) { r = stepf(r); init[n] = r; }
+}
+
+int ensure_crc_tables(int device)
+{
+    if (device < 0 || device >= 64) return fail(TB200_E_ARG, "device ordinal out of range");
+    if (g_crc_ready[device]) return TB200_OK;
+    uint16_t tab[512], init[512];
+    build_crc_tables(tab, init);
+    TB_CUDA(cudaMemcpyToSymbol(g_crc_tab, tab, sizeof(tab)));
+    TB_CUDA(cudaMemcpyToSymbol(g_crc_init, init, sizeof(init)));
+    g_crc_ready[device] = true;
+    return TB200_OK;
+}
+
+// ------------------------------------------------------------------ symbols_to_bits
+__global__ void symbols_to_bits_kernel(const uint8_t *__restrict__ sym, long stride, const int32_t *__restrict__ n_sym,
+                                       int n_fixed, uint8_t *__restrict__ bits, uint8_t *__restrict__ mapped,
+                                       long bits_stride)
+{
+    __shared__ int s_max;
+    int s = blockIdx.x;
+    long n = n_sym ? n_sym[s] : n_fixed;
+    const uint8_t *in = sym + (long)s * stride;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    int mx = 0;
+    for (long i = threadIdx.x; i < n; i += blockDim.x) mx = max(mx, (int)in[i]);
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_max, mx);
+    __syncthreads();
+    bool dqpsk = s_max <= 3;                              // decoder.py:149-150
+    uint8_t *b = bits + (long)s * bits_stride;
+    uint8_t *m = mapped ? mapped + (long)s * (bits_stride / 2) : nullptr;
+    for (long i = threadIdx.x; i < n; i += blockDim.x) {
+        int v = in[i];
+        if (dqpsk) v &= 3;
+        else v = (v <= 2) ? 0 : (v <= 4) ? 1 : (v == 5) ? 3 : (v <= 7) ? 2 : 0;   // decoder.py:160-164
+        if (m) m[i] = (uint8_t)v;
+        b[2 * i] = (uint8_t)(v >> 1);
+        b[2 * i + 1] = (uint8_t)(v & 1);
+    }
+}
+
+// ------------------------------------------------------------------ 22-bit Hamming correlation
+__global__ void sync_corr_kernel(const uint8_t *__restrict__ bits, long bits_stride, const int32_t *__restrict__ n_sym,
+                                 int n_bits_fixed, uint8_t *__restrict__ m1, uint8_t *__restrict__ m2)
+{
+    int s = blockIdx.y;
+    long nb = n_sym ? 2L * n_sym[s] : n_bits_fixed;
+    long nwin = nb - 21;
+    long pos = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (pos >= nwin) return;
+    const uint8_t *b = bits + (long)s * bits_stride + pos;
+    int a1 = 0, a2 = 0;
+#pragma unroll
+    for (int k = 0; k < 22; ++k) { int v = b[k]; a1 += (v == c_ts1[k]); a2 += (v == c_ts2[k]); }
+    m1[(long)s * bits_stride + pos] = (uint8_t)a1;
+    m2[(long)s * bits_stride + pos] = (uint8_t)a2;
+}
+
+// smallest match count m with (double)m / 22 >= thr  (decoder.py:240,245)
+__device__ __forceinline__ int need_matches(double thr)
+{
+    int m = 0;
+    while (m <= 22 && !((double)m / 22.0 >= thr)) ++m;
+    return m;
+}
+
+// find_sync executed by one full warp over precomputed match counts (decoder.py:226-281).
+// Returns the number of positions written (same on every lane); *max_match = best count
+// among the (pattern, position) pairs the reference evaluates.
+__device__ int warp_find_sync(const uint8_t *__restrict__ m1, const uint8_t *__restrict__ m2, long nwin, double thr,
+                              int32_t *__restrict__ pos_out, int max_pos, int *max_match)
+{
+    const int lane = threadIdx.x & 31;
+    int found = 0, mmax = 0;
+    if (nwin <= 0) { *max_match = 0; return 0; }
+    const int need = need_matches(thr);
+    long i = 0;
+    while (i < nwin) {
+        long p = i + lane;
+        int a1 = 0, a2 = 0;
+        if (p < nwin) { a1 = m1[p]; a2 = m2[p]; }
+        bool hit = (p < nwin) && (a1 >= need || a2 >= need);
+        unsigned ball = __ballot_sync(0xffffffffu, hit);
+        int first = ball ? (__ffs(ball) - 1) : 32;
+        // visited: lanes < first evaluate both patterns; the hit lane stops after TS1 if TS1 hits
+        int v = 0;
+        if (p < nwin) {
+            if (lane < first) v = max(a1, a2);
+            else if (lane == first) v = (a1 >= need) ? a1 : max(a1, a2);
+        }
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        mmax = max(mmax, v);
+        if (ball) {
+            if (lane == 0 && found < max_pos) pos_out[found] = (int32_t)(i + first);
+            ++found;
+            i = i + first + 250;                         // decoder.py:256
+        } else {
+            i += 32;
+        }
+    }
+    if (found == 0) {
+        double max_corr = (double)mmax / 22.0;
+        if (max_corr > 0.75 && max_corr >= (thr - 0.15)) {       // decoder.py:265
+            double ad = fmax(0.75, max_corr - 0.02);
+            if (ad < thr) {
+                const int need_ad = need_matches(ad);
+                i = 0;
+                while (i < nwin) {
+                    long p = i + lane;
+                    bool hit = (p < nwin) && (max((int)m1[p < nwin ? p : 0], (int)m2[p < nwin ? p : 0]) >= need_ad);
+                    unsigned ball = __ballot_sync(0xffffffffu, hit);
+                    if (ball) {
+                        int first = __ffs(ball) - 1;
+                        if (lane == 0 && found < max_pos) pos_out[found] = (int32_t)(i + first);
+                        ++found;
+                        i = i + first + 250;             // seen_positions window, decoder.py:278
+                    } else {
+                        i += 32;
+                    }
+                }
+            }
+        }
+    }
+    *max_match = mmax;
+    return found;
+}
+
+__global__ void find_sync_kernel(const uint8_t *__restrict__ m1, const uint8_t *__restrict__ m2, int n_bits, double thr,
+                                 int32_t *__restrict__ pos, int max_pos, int32_t *__restrict__ count,
+                                 int32_t *__restrict__ max_match)
+{
+    int mm;
+    int c = warp_find_sync(m1, m2, (long)n_bits - 21, thr, pos, max_pos, &mm);
+    if (threadIdx.x == 0) { *count = c; *max_match = mm; }
+}
+
+// ------------------------------------------------------------------ burst parsing, warp-resident
+struct BurstOut {
+    uint32_t burst_type, crc_ok, mac_ok, hdr, sync_match;
+};
+
+__device__ __forceinline__ unsigned warp_xor(unsigned v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_isum(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// bits i .. i+nb-1 (nb <= 16) of the 510-bit burst held as one 16-bit word per lane (bit 15 first)
+__device__ __forceinline__ unsigned burst_field(unsigned w, int i, int nb)
+{
+    int l0 = i >> 4, o0 = i & 15;
+    unsigned hi = __shfl_sync(0xffffffffu, w, l0 & 31);
+    unsigned lo = __shfl_sync(0xffffffffu, w, (l0 + 1) & 31);
+    unsigned both = (hi << 16) | lo;                       // 32 bits starting at bit 16*l0
+    return (both >> (32 - o0 - nb)) & ((1u << nb) - 1u);
+}
+
+// packed byte `byte` (8 data bits, MSB first) of TetraBurst.data_bits (protocol.py:277-290):
+// normal burst = burst bits [0,108) ++ [122,230) (216 bits), sync burst = all 510 bits; zero padded.
+// Every lane of the warp must call this (it shuffles).
+__device__ __forceinline__ unsigned data_byte(unsigned w, bool is_sync, int byte)
+{
+    int d0 = byte * 8;
+    unsigned gap = (burst_field(w, 104, 4) << 4) | burst_field(w, 122, 4);   // byte 13 straddles the TS gap
+    int src = is_sync ? d0 : (d0 < 104 ? d0 : d0 + 14);
+    bool valid = is_sync ? (d0 < 512) : (d0 < 216);
+    unsigned plain = burst_field(w, (valid && src <= 504) ? src : 0, 8);
+    if (!valid) return 0u;
+    if (!is_sync && d0 == 104) return gap;
+    return plain;
+}
+
+// Parse one burst held in `w` (lane L has burst bits 16L..16L+15; bits >= 510 are zero).
+// crc tables in shared memory.  rec (32 B) / full (64 B) may be null.
+__device__ void warp_parse_burst(unsigned w, const uint16_t *__restrict__ tab, const uint16_t *__restrict__ initv,
+                                 uint8_t *__restrict__ rec, uint8_t *__restrict__ full, BurstOut &out)
+{
+    const int lane = threadIdx.x & 31;
+    // _detect_burst_type: bits[255:277] vs both patterns, max/22 > 0.8 (protocol.py:246-265)
+    unsigned win = (burst_field(w, 255, 11) << 11) | burst_field(w, 266, 11);
+    int mc = 22 - __popc(win ^ SYNC_CONT_W), md = 22 - __popc(win ^ SYNC_DISC_W);
+    int mx = max(mc, md);
+    bool is_sync = ((double)mx / 22.0) > 0.8;
+    // per-lane view of the data bits: normal = [0,108) ++ [122,230), sync = all 510
+    int ones = 0;
+    unsigned cf = 0, cr = 0;           // forward / reversed-payload CRC contributions
+    const int n_data = is_sync ? 510 : 216;
+    const int n_pay = n_data - 16;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        int bi = lane * 16 + k;                            // burst bit index
+        unsigned bit = (w >> (15 - k)) & 1u;
+        int d;                                             // data-bit index or -1
+        if (is_sync) d = (bi < 510) ? bi : -1;
+        else d = (bi < 108) ? bi : (bi >= 122 && bi < 230) ? bi - 14 : -1;
+        if (d >= 0 && bit) {
+            ++ones;
+            if (d < n_pay) { cf ^= tab[n_pay - d]; cr ^= tab[d + 1]; }
+        }
+    }
+    ones = warp_isum(ones);
+    cf = warp_xor(cf) ^ initv[n_pay];
+    cr = warp_xor(cr) ^ initv[n_pay];
+    unsigned rx = is_sync ? burst_field(w, 494, 16) : burst_field(w, 214, 16);
+    bool crc_ok = false;
+    if (ones != 0 && ones != n_data) {                     // protocol.py:301-304
+        crc_ok = (__popc(cf ^ rx) <= 2) || (__popc(cr ^ rx) <= 2);   // :311-325
+    }
+    // MAC header validity (parse_mac_pdu returns None?) protocol.py:369-526 — data bits 0..34 = burst bits 0..34
+    unsigned f0 = burst_field(w, 0, 16), f1 = burst_field(w, 16, 16), f2 = burst_field(w, 32, 16);
+    unsigned long long head = ((unsigned long long)f0 << 32) | ((unsigned long long)f1 << 16) | f2;   // 48 bits
+    auto fld = [&](int lo, int nb) -> unsigned { return (unsigned)((head >> (48 - lo - nb)) & ((1ull << nb) - 1ull)); };
+    unsigned type = fld(0, 2), enc = fld(2, 2);
+    bool mac_ok;
+    if (type == 0) { unsigned len = fld(29, 6); mac_ok = !((int)(len * 8) > n_data - 35 + 16); }
+    else if (type == 1) mac_ok = true;
+    else if (type == 2) {
+        mac_ok = true;
+        if (enc == 0) { unsigned mcc = fld(4, 10), mnc = fld(14, 14); mac_ok = !(mcc < 200 || mcc > 799 || mnc > 999); }
+    } else { unsigned len = fld(5, 6); mac_ok = !((int)(len * 8) > n_data - 11 + 16); }
+    out.burst_type = is_sync ? 5u : 2u;
+    out.crc_ok = crc_ok;
+    out.mac_ok = mac_ok;
+    out.hdr = (type << 2) | enc;
+    out.sync_match = (unsigned)mx;
+    if (rec) {
+        // bytes 0..26: first 216 data bits packed
+        unsigned byte = data_byte(w, is_sync, lane);
+        if (lane < 27) rec[lane] = (uint8_t)byte;
+        if (lane == 27) rec[27] = (uint8_t)out.burst_type;
+        if (lane == 28) rec[28] = (uint8_t)out.crc_ok;
+        if (lane == 29) rec[29] = (uint8_t)out.mac_ok;
+        if (lane == 30) rec[30] = (uint8_t)out.hdr;
+        if (lane == 31) rec[31] = (uint8_t)out.sync_match;
+    }
+    if (full) {
+        full[2 * lane] = (uint8_t)(w >> 8);
+        full[2 * lane + 1] = (uint8_t)(w & 0xff);
+    }
+}
+
+// lane's 16 bits of a burst given its 255 dibits (each dibit -> (s>>1)&1, s&1: protocol.py:211-214)
+__device__ __forceinline__ unsigned load_burst_word(const uint8_t *__restrict__ dib)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned w = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int idx = lane * 8 + k;
+        unsigned s = (idx < 255) ? dib[idx] : 0u;
+        w = (w << 2) | (s & 3u);
+    }
+    return w;
+}
+
+__global__ void burst_batch_kernel(const uint8_t *__restrict__ dibits, long n, uint8_t *__restrict__ rec,
+                                   uint8_t *__restrict__ full, unsigned long long *__restrict__ stats)
+{
+    __shared__ uint16_t tab[512];
+    __shared__ uint16_t initv[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { tab[i] = g_crc_tab[i]; initv[i] = g_crc_init[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    unsigned pass = 0, total = 0;
+    for (long b = warp; b < n; b += nwarps) {
+        unsigned w = load_burst_word(dibits + b * 255);
+        BurstOut o;
+        warp_parse_burst(w, tab, initv, rec ? rec + b * 32 : nullptr, full ? full + b * 64 : nullptr, o);
+        ++total;
+        pass += o.crc_ok;
+    }
+    if (stats && lane == 0 && total) {
+        atomicAdd(&stats[0], (unsigned long long)total);
+        atomicAdd(&stats[1], (unsigned long long)pass);
+        atomicAdd(&stats[2], (unsigned long long)(total - pass));
+    }
+}
+
+// ------------------------------------------------------------------ TetraDecoder.decode, one warp per stream
+__global__ void decode_kernel(const uint8_t *__restrict__ bits, const uint8_t *__restrict__ mapped,
+                              const uint8_t *__restrict__ m1, const uint8_t *__restrict__ m2, int n_streams,
+                              long bits_stride, const int32_t *__restrict__ n_sym, tb200_frame *__restrict__ frames,
+                              int max_frames, int32_t *__restrict__ n_frames, unsigned long long *__restrict__ stats,
+                              int32_t *__restrict__ pos_scratch)
+{
+    __shared__ uint16_t tab[512];
+    __shared__ uint16_t initv[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { tab[i] = g_crc_tab[i]; initv[i] = g_crc_init[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= n_streams) return;
+    long nsym = n_sym[s];
+    long nb = 2 * nsym;
+    long nwin = nb - 21;
+    const uint8_t *b = bits + (long)s * bits_stride;
+    const uint8_t *mp = mapped + (long)s * (bits_stride / 2);
+    const uint8_t *c1 = m1 + (long)s * bits_stride, *c2 = m2 + (long)s * bits_stride;
+    int32_t *pos = pos_scratch + (long)s * max_frames;
+    // threshold cascade, decoder.py:845-856
+    int mm;
+    int cnt = warp_find_sync(c1, c2, nwin, 0.90, pos, max_frames, &mm);
+    if (cnt == 0) {
+        cnt = warp_find_sync(c1, c2, nwin, 0.85, pos, max_frames, &mm);
+        if (cnt == 0) {
+            cnt = warp_find_sync(c1, c2, nwin, 0.80, pos, max_frames, &mm);
+            double mc = (double)mm / 22.0;
+            if (cnt == 0 && mc >= 0.75) cnt = warp_find_sync(c1, c2, nwin, fmax(0.75, mc - 0.02), pos, max_frames, &mm);
+        }
+    }
+    if (cnt > max_frames) cnt = max_frames;
+    __syncwarp();
+    unsigned total = 0, pass = 0;
+    tb200_frame *fo = frames + (long)s * max_frames;
+    for (int f = 0; f < cnt; ++f) {
+        int p = pos[f];
+        long start_pos = (long)p - 216;
+        long start_sym = start_pos >= 0 ? start_pos / 2 : 0;
+        // decoder.py:867-871 bounds, and decode_frame's len(bits) < 510 -> None (:894)
+        bool ok = start_pos >= 0 && (start_sym + 255 <= nsym) && (start_pos + 510 <= nb);
+        tb200_frame *fr = fo + f;
+        BurstOut o = {0, 0, 0, 0, 0};
+        unsigned fw = 0;
+        if (ok) {
+            // frame bits come from the BIT stream at start_pos, burst symbols from the SYMBOL stream at
+            // start_pos // 2 — they differ by one bit when start_pos is odd (decoder.py:870-877); keep that.
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                long bi = start_pos + lane * 16 + k;
+                unsigned bit = (lane * 16 + k < 510) ? b[bi] : 0u;
+                fw = (fw << 1) | (bit & 1u);
+            }
+            unsigned w = load_burst_word(mp + start_sym);
+            warp_parse_burst(w, tab, initv, nullptr, nullptr, o);
+            // TetraBurst.data_bits packed into fr->data (216 or 510 bits)
+            bool is_sync = o.burst_type == 5;
+            for (int r = 0; r < 2; ++r) fr->data[r * 32 + lane] = (uint8_t)data_byte(w, is_sync, r * 32 + lane);
+            fr->bits[2 * lane] = (uint8_t)(fw >> 8);
+            fr->bits[2 * lane + 1] = (uint8_t)(fw & 0xff);
+            ++total;
+            pass += o.crc_ok;
+        }
+        if (lane == 0) {
+            fr->sync_pos = p;
+            fr->start_pos = (int32_t)start_pos;
+            fr->number = ok ? (int32_t)(start_pos / 510) : 0;
+            fr->type = (uint8_t)((fw >> 14) & 3u);          // frame bits [0:2], decoder.py:906
+            fr->enc_mode = (uint8_t)((fw >> 12) & 3u);      // frame bits [2:4], decoder.py:909
+            fr->burst_type = (uint8_t)o.burst_type;
+            fr->crc_ok = (uint8_t)o.crc_ok;
+            fr->mac_ok = (uint8_t)o.mac_ok;
+            fr->kept = (uint8_t)(ok && (o.crc_ok || o.mac_ok));   // decoder.py:1092-1100
+            fr->pad[0] = fr->pad[1] = 0;
+        }
+    }
+    if (lane == 0) {
+        n_frames[s] = cnt;
+        if (stats && total) {
+            atomicAdd(&stats[0], (unsigned long long)total);
+            atomicAdd(&stats[1], (unsigned long long)pass);
+            atomicAdd(&stats[2], (unsigned long long)(total - pass));
+        }
+    }
+}
+
+// _calculate_crc16 of bit rows (one byte per bit), one warp per row
+__global__ void crc16_rows_kernel(const uint8_t *__restrict__ bits, int n_rows, int n_bits, int row_stride,
+                                  uint16_t *__restrict__ crc)
+{
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const uint8_t *b = bits + (long)row * row_stride;
+    // general length: serial shift register per row chunk is fine here (stage-level API, not the hot path)
+    unsigned c = 0xFFFF;
+    if (lane == 0) {
+        for (int i = 0; i < n_bits; ++i) {
+            c ^= ((unsigned)(b[i] & 1)) << 15;
+            c = (c & 0x8000) ? ((c << 1) ^ 0x1021) : (c << 1);
+            c &= 0xFFFF;
+        }
+        crc[row] = (uint16_t)c;
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+int launch_symbols_to_bits(tb200_handle h, const uint8_t *sym, int n_streams, long stride, const int32_t *n_sym,
+                           int n_fixed, uint8_t *bits, uint8_t *mapped, long bits_stride, cudaStream_t st)
+{
+    if (n_streams <= 0) return TB200_OK;
+    symbols_to_bits_kernel<<<n_streams, 256, 0, st>>>(sym, stride, n_sym, n_fixed, bits, mapped, bits_stride);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+int launch_sync_corr(tb200_handle h, const uint8_t *bits, int n_streams, long bits_stride, const int32_t *n_sym,
+                     int n_bits_fixed, uint8_t *m1, uint8_t *m2, cudaStream_t st)
+{
+    long maxwin = bits_stride;   // upper bound of windows per stream
+    if (n_streams <= 0 || maxwin <= 0) return TB200_OK;
+    dim3 grid((unsigned)((maxwin + 255) / 256), (unsigned)n_streams);
+    sync_corr_kernel<<<grid, 256, 0, st>>>(bits, bits_stride, n_sym, n_bits_fixed, m1, m2);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+int launch_find_sync(tb200_handle h, const uint8_t *m1, const uint8_t *m2, int n_bits, double thr, int32_t *pos,
+                     int max_pos, int32_t *count, int32_t *max_match, cudaStream_t st)
+{
+    find_sync_kernel<<<1, 32, 0, st>>>(m1, m2, n_bits, thr, pos, max_pos, count, max_match);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+int launch_decode(tb200_handle h, const uint8_t *bits, const uint8_t *mapped, const uint8_t *m1, const uint8_t *m2,
+                  int n_streams, long bits_stride, const int32_t *n_sym, tb200_frame *frames, int max_frames,
+                  int32_t *n_frames, int64_t *stats, cudaStream_t st)
+{
+    if (n_streams <= 0) return TB200_OK;
+    int threads = 128;
+    int blocks = (n_streams * 32 + threads - 1) / threads;
+    decode_kernel<<<blocks, threads, 0, st>>>(bits, mapped, m1, m2, n_streams, bits_stride, n_sym, frames, max_frames,
+                                              n_frames, (unsigned long long *)stats, h->sync_pos);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+int launch_burst_batch(tb200_handle h, const uint8_t *dibits, int64_t n, uint8_t *rec, uint8_t *full, int64_t *stats,
+                       cudaStream_t st)
+{
+    if (n <= 0) return TB200_OK;
+    int threads = 256;
+    long warps_needed = n;
+    long blocks = (warps_needed * 32 + threads - 1) / threads;
+    long cap = 148L * 8 * 4;                  // persistent-ish: 8 CTAs/SM x 4 waves
+    if (blocks > cap) blocks = cap;
+    burst_batch_kernel<<<(unsigned)blocks, threads, 0, st>>>(dibits, n, rec, full, (unsigned long long *)stats);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+int launch_crc16_rows(tb200_handle h, const uint8_t *bits, int n_rows, int n_bits, int row_stride, uint16_t *crc,
+                      cudaStream_t st)
+{
+    if (n_rows <= 0) return TB200_OK;
+    int threads = 128;
+    int blocks = (n_rows * 32 + threads - 1) / threads;
+    crc16_rows_kernel<<<blocks, threads, 0, st>>>(bits, n_rows, n_bits, row_stride, crc);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+}  // namespace tb200

@@ -1,0 +1,35 @@
+// kernels.h — internal launcher prototypes (one per kernel family).
+#pragma once
+#include "common.h"
+
+namespace tb200 {
+
+int launch_decimate_exact(tb200_handle h, const void *x, int dtype, int n_chunks, long n, long chunk_stride,
+                          int q, const DecimDesign &d, void *scratch, void *dec_out, long n_dec, cudaStream_t st);
+int launch_channel_exact(tb200_handle h, const void *x, int dtype, int n_chunks, long n, long in_stride,
+                         const double *freq_off, double fs, const ChanDesign &cd, int filtered_flag,
+                         double *scratch, double *filtered, long out_stride, cudaStream_t st);
+int launch_symbols(tb200_handle h, const double *filtered, int n_chunks, long n, long in_stride, int sps,
+                   int phase_step, double *symbols, uint8_t *dibits, long out_stride, int32_t *n_dibits,
+                   int32_t *n_symbols, int32_t *phase, cudaStream_t st);
+int launch_slicer(tb200_handle h, const double *symbols, long n, uint8_t *dibits, cudaStream_t st);
+
+int launch_symbols_to_bits(tb200_handle h, const uint8_t *sym, int n_streams, long stride, const int32_t *n_sym,
+                           int n_fixed, uint8_t *bits, uint8_t *mapped, long bits_stride, cudaStream_t st);
+int launch_sync_corr(tb200_handle h, const uint8_t *bits, int n_streams, long bits_stride, const int32_t *n_sym,
+                     int n_bits_fixed, uint8_t *m1, uint8_t *m2, cudaStream_t st);
+int launch_find_sync(tb200_handle h, const uint8_t *m1, const uint8_t *m2, int n_bits, double thr, int32_t *pos,
+                     int max_pos, int32_t *count, int32_t *max_match, cudaStream_t st);
+int launch_decode(tb200_handle h, const uint8_t *bits, const uint8_t *mapped, const uint8_t *m1, const uint8_t *m2,
+                  int n_streams, long bits_stride, const int32_t *n_sym, tb200_frame *frames, int max_frames,
+                  int32_t *n_frames, int64_t *stats, cudaStream_t st);
+int launch_burst_batch(tb200_handle h, const uint8_t *dibits, int64_t n, uint8_t *rec, uint8_t *full,
+                       int64_t *stats, cudaStream_t st);
+int launch_crc16_rows(tb200_handle h, const uint8_t *bits, int n_rows, int n_bits, int row_stride, uint16_t *crc,
+                      cudaStream_t st);
+int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_stride, int n_fft, double fs,
+               double alpha, int first, float *power, float *smoothed, double *ema_state, double *stats,
+               double *scratch_db, cudaStream_t st);
+int launch_freq_shift(tb200_handle h, const void *x, int dtype, long n, double f, double fs, double *out, cudaStream_t st);
+
+}  // namespace tb200

@@ -1,0 +1,204 @@
+// psd.cu — waterfall PSD, dB-domain EMA "denoise" and the AFC / signal-gate statistics
+// (inline block of CaptureThread.run, /root/reference/tetraear/ui/modern.py:1926-2029, and
+// WaterfallWidget.update_spectrum :923-947).
+//
+// One CTA per frame: the Hann-windowed frame is staged in shared memory (complex128 like
+// numpy, which promotes complex64 * float64), transformed by an in-place shared-memory
+// radix-4 (+ one radix-2 stage when log2 N is odd) decimation-in-time FFT with a twiddle
+// table, then turned into dBFS, fft-shifted, written as float32, and reduced to the 8
+// band statistics the AFC loop reads — all without leaving the SM.
+#include "common.h"
+#include "kernels.h"
+
+namespace tb200 {
+
+__global__ void psd_tables_kernel(int n_fft, double *__restrict__ window, double2 *__restrict__ twiddle)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_fft) {
+        // np.hanning(M): 0.5 + 0.5 cos(pi n / (M-1)), n = 1-M, 3-M, ...
+        window[i] = 0.5 + 0.5 * cospi((double)(2 * i + 1 - n_fft) / (double)(n_fft - 1));
+    }
+    if (i < n_fft / 2 + n_fft / 4 + 1) {
+        double s, c;
+        sincospi(-2.0 * (double)i / (double)n_fft, &s, &c);   // exp(-2 pi j i / N)
+        twiddle[i] = make_double2(c, s);
+    }
+}
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+{
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+struct BandParams {
+    int start, end;          // in-channel bins  [start, end)
+    int n_lo, n_hi0;         // noise bins [0, n_lo) and [n_hi0, N)
+    double freq_step;        // 1 / (N * (1/fs))
+};
+
+extern __shared__ double2 psd_smem[];
+
+__global__ void psd_kernel(const float2 *__restrict__ iq, long frame_stride, int n_fft, int log2n,
+                           const double *__restrict__ window, const double2 *__restrict__ tw, BandParams bp,
+                           float *__restrict__ power, double *__restrict__ stats)
+{
+    double2 *x = psd_smem;
+    __shared__ double red[3][32];
+    __shared__ int redi[32];
+    const long frame = blockIdx.x;
+    const float2 *in = iq + frame * frame_stride;
+    const int N = n_fft;
+    // load, window, bit-reverse (radix-2 ordering)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        float2 v = in[i];
+        double w = window[i];
+        int r = __brev((unsigned)i) >> (32 - log2n);
+        x[r] = make_double2((double)v.x * w, (double)v.y * w);
+    }
+    __syncthreads();
+    // first stage radix-2 when log2n is odd, then radix-4 stages (two radix-2 levels fused)
+    int len = 1;                 // current sub-transform length
+    if (log2n & 1) {
+        for (int i = threadIdx.x; i < N / 2; i += blockDim.x) {
+            double2 a = x[2 * i], b = x[2 * i + 1];
+            x[2 * i] = make_double2(a.x + b.x, a.y + b.y);
+            x[2 * i + 1] = make_double2(a.x - b.x, a.y - b.y);
+        }
+        len = 2;
+        __syncthreads();
+    }
+    while (len < N) {
+        // combine 4 sub-transforms of length len into one of 4*len (bit-reversed input order:
+        // blocks are  E0=[even-even], E1=[even-odd], O0, O1  -> radix-2 twice)
+        const int L4 = 4 * len;
+        const int tstep1 = N / (2 * len);      // twiddle stride for the length-2len level
+        const int tstep2 = N / L4;             // for the length-4len level
+        for (int i = threadIdx.x; i < N / 4; i += blockDim.x) {
+            int blk = i / len, k = i - blk * len;
+            int base = blk * L4 + k;
+            double2 a = x[base], b = x[base + len], c = x[base + 2 * len], d = x[base + 3 * len];
+            double2 w1 = tw[k * tstep1];
+            double2 bt = cmul(b, w1), dt = cmul(d, w1);
+            double2 e0 = make_double2(a.x + bt.x, a.y + bt.y), e1 = make_double2(a.x - bt.x, a.y - bt.y);
+            double2 o0 = make_double2(c.x + dt.x, c.y + dt.y), o1 = make_double2(c.x - dt.x, c.y - dt.y);
+            double2 w2a = tw[k * tstep2], w2b = tw[(k + len) * tstep2];
+            double2 p0 = cmul(o0, w2a), p1 = cmul(o1, w2b);
+            x[base] = make_double2(e0.x + p0.x, e0.y + p0.y);
+            x[base + 2 * len] = make_double2(e0.x - p0.x, e0.y - p0.y);
+            x[base + len] = make_double2(e1.x + p1.x, e1.y + p1.y);
+            x[base + 3 * len] = make_double2(e1.x - p1.x, e1.y - p1.y);
+        }
+        len = L4;
+        __syncthreads();
+    }
+    // dBFS, fftshift, band statistics
+    const double invN = 1.0 / (double)N;   // |X| / n_fft : power-of-two N, the product is exact
+    double sig = 0.0, noise = 0.0, pk = -1e300;
+    int pki = 0x7fffffff;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        double2 v = x[(j + N / 2) & (N - 1)];
+        double p = 20.0 * log10(hypot(v.x, v.y) * invN + 1e-20);
+        if (power) power[frame * N + j] = (float)p;
+        if (j >= bp.start && j < bp.end) {
+            sig += p;
+            if (p > pk) { pk = p; pki = j; }
+        }
+        if (j < bp.n_lo || j >= bp.n_hi0) noise += p;
+    }
+    if (!stats) return;
+    // block reductions (sum, sum, max + first argmax)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) {
+        sig += __shfl_down_sync(0xffffffffu, sig, o);
+        noise += __shfl_down_sync(0xffffffffu, noise, o);
+        double opk = __shfl_down_sync(0xffffffffu, pk, o);
+        int oi = __shfl_down_sync(0xffffffffu, pki, o);
+        if (opk > pk || (opk == pk && oi < pki)) { pk = opk; pki = oi; }
+    }
+    if (lane == 0) { red[0][w] = sig; red[1][w] = noise; red[2][w] = pk; redi[w] = pki; }
+    __syncthreads();
+    if (w == 0) {
+        sig = lane < nw ? red[0][lane] : 0.0;
+        noise = lane < nw ? red[1][lane] : 0.0;
+        pk = lane < nw ? red[2][lane] : -1e300;
+        pki = lane < nw ? redi[lane] : 0x7fffffff;
+        for (int o = 16; o > 0; o >>= 1) {
+            sig += __shfl_down_sync(0xffffffffu, sig, o);
+            noise += __shfl_down_sync(0xffffffffu, noise, o);
+            double opk = __shfl_down_sync(0xffffffffu, pk, o);
+            int oi = __shfl_down_sync(0xffffffffu, pki, o);
+            if (opk > pk || (opk == pk && oi < pki)) { pk = opk; pki = oi; }
+        }
+        if (lane == 0) {
+            double *s = stats + frame * 8;
+            int nband = bp.end - bp.start;
+            int nnoise = bp.n_lo + (N - bp.n_hi0);
+            if (nband <= 0) { for (int k = 0; k < 8; ++k) s[k] = 0.0; return; }
+            double signal_power = sig / (double)nband;
+            double noise_floor = nnoise > 0 ? noise / (double)nnoise : -100.0;     // modern.py:1989-1992
+            double snr = signal_power - noise_floor;
+            double off = (double)(pki - N / 2) * bp.freq_step;                      // freqs[peak_idx]
+            bool present = (snr > 15.0) && (pk > -70.0) && ((pk - signal_power) > 3.0);   // :2006
+            s[0] = signal_power; s[1] = pk; s[2] = (double)pki; s[3] = off; s[4] = noise_floor; s[5] = snr;
+            s[6] = present ? 1.0 : 0.0;
+            s[7] = (present && pk > -70.0) ? off : 0.0;                             // :2028
+        }
+    }
+}
+
+// EMA across frames, dB domain: S = S (1 - a) + P a ; first frame S = P  (modern.py:929-935)
+__global__ void psd_ema_kernel(const float *__restrict__ power, long n_frames, int n_fft, double alpha, int first,
+                               double *__restrict__ state, float *__restrict__ smoothed)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_fft) return;
+    double S = first ? 0.0 : state[j];
+    for (long f = 0; f < n_frames; ++f) {
+        double p = (double)power[f * n_fft + j];
+        S = (first && f == 0) ? p : __dadd_rn(__dmul_rn(S, 1.0 - alpha), __dmul_rn(p, alpha));
+        smoothed[f * n_fft + j] = (float)S;
+    }
+    state[j] = S;
+}
+
+int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_stride, int n_fft, double fs,
+               double alpha, int first, float *power, float *smoothed, double *ema_state, double *stats,
+               double *tables, cudaStream_t st)
+{
+    if (n_frames <= 0) return TB200_OK;
+    int log2n = 0;
+    while ((1 << log2n) < n_fft) ++log2n;
+    double *window = tables;
+    double2 *tw = reinterpret_cast<double2 *>(tables + n_fft);
+    if (h->psd_tables_n != n_fft) {
+        psd_tables_kernel<<<(n_fft + 255) / 256, 256, 0, st>>>(n_fft, window, tw);
+        TB_LAUNCH_CHECK(h);
+        h->psd_tables_n = n_fft;
+    }
+    BandParams bp;
+    int center = n_fft / 2;
+    double freq_resolution = fs / n_fft;
+    int bins = (int)(25000 / freq_resolution);
+    bp.start = center - bins / 2 > 0 ? center - bins / 2 : 0;
+    bp.end = center + bins / 2 < n_fft ? center + bins / 2 : n_fft;
+    bp.n_lo = bp.start - 10 > 0 ? bp.start - 10 : 0;
+    bp.n_hi0 = bp.end + 10 < n_fft ? bp.end + 10 : n_fft;
+    bp.freq_step = 1.0 / ((double)n_fft * (1.0 / fs));
+    size_t smem = sizeof(double2) * (size_t)n_fft;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(psd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(psd_kernel): %s", cudaGetErrorString(e));
+    }
+    int threads = n_fft >= 2048 ? 512 : (n_fft >= 512 ? 128 : 64);
+    psd_kernel<<<(unsigned)n_frames, threads, smem, st>>>((const float2 *)iq, frame_stride, n_fft, log2n, window, tw, bp,
+                                                         power, stats);
+    TB_LAUNCH_CHECK(h);
+    if (smoothed) {
+        psd_ema_kernel<<<(n_fft + 127) / 128, 128, 0, st>>>(power, n_frames, n_fft, alpha, first, ema_state, smoothed);
+        TB_LAUNCH_CHECK(h);
+    }
+    return TB200_OK;
+}
+
+}  // namespace tb200
