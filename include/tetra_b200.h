@@ -189,6 +189,10 @@ int tb200_psd_batch(tb200_handle h, const void *d_iq_c64, int64_t n_frames, int6
                     int n_fft, double sample_rate, double ema_alpha, int first, float *d_power,
                     float *d_smoothed, double *d_ema_state, double *d_stats, void *stream);
 
+/* ---- debugging aid: synchronous copy of an internal workspace region to the host ---------
+ * region 0 = decimated chunks, 1 = channel-filtered complex128, 2 / 3 = forward-pass scratches */
+int tb200_debug_read(tb200_handle h, int region, void *h_dst, size_t nbytes);
+
 #ifdef __cplusplus
 }
 #endif

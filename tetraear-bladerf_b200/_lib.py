@@ -58,6 +58,7 @@ _PROTOS = {
     "tb200_burst_batch": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "tb200_burst_batch_host": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "tb200_crc16_rows": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "tb200_debug_read": (_i, [_vp, _i, _vp, C.c_size_t]),
     "tb200_psd_batch": (_i, [_vp, _vp, _i64, _i64, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 EXPORTS = tuple(_PROTOS)

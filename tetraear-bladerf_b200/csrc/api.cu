@@ -420,3 +420,22 @@ extern "C" int tb200_psd_batch(tb200_handle h, const void *d_iq_c64, int64_t n_f
     return launch_psd(h, (const float *)d_iq_c64, n_frames, frame_stride, n_fft, sample_rate, ema_alpha, first, d_power,
                       d_smoothed, d_ema_state, d_stats, h->psd_tables, (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------------- debugging aid
+extern "C" int tb200_debug_read(tb200_handle h, int region, void *h_dst, size_t nbytes)
+{
+    if (!h || !h_dst) return fail(TB200_E_ARG, "tb200_debug_read: bad argument");
+    const void *src = nullptr;
+    size_t cap = 0;
+    switch (region) {
+    case 0: src = h->dec_out; cap = h->dec_bytes; break;
+    case 1: src = h->filtered; cap = h->filt_bytes; break;
+    case 2: src = h->fwd; cap = h->fwd_bytes; break;
+    case 3: src = h->chan_fwd; cap = h->chan_bytes; break;
+    default: return fail(TB200_E_ARG, "tb200_debug_read: unknown region %d", region);
+    }
+    if (nbytes > cap) return fail(TB200_E_ARG, "tb200_debug_read: %zu bytes > region size %zu", nbytes, cap);
+    TB_CUDA(cudaDeviceSynchronize());
+    TB_CUDA(cudaMemcpy(h_dst, src, nbytes, cudaMemcpyDeviceToHost));
+    return TB200_OK;
+}

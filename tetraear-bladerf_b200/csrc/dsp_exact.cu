@@ -120,7 +120,7 @@ __global__ void decim_exact_bwd(const T *__restrict__ scratch, long n, int q, in
         T v = (j < m) ? in[(m - 1 - j) * n_lanes] : T(0);
         T o = (j < 3 || j >= m) ? f.template step<true>(K.c, v, j, m) : f.template step<false>(K.c, v, j, m);
         long pos = m - 1 - (j - 3);
-        if (j >= 3 && pos == next_keep) {
+        if (j >= 3 && pos == next_keep && pos >= edge) {
             out[2 * ((pos - edge) / q)] = o;
             next_keep -= q;
         }

@@ -60,7 +60,6 @@ __global__ void symbols_kernel(const double *__restrict__ filtered, long n, long
                                int32_t *__restrict__ phase_out)
 {
     __shared__ double sh[32];
-    __shared__ int s_best;
     int chunk = blockIdx.x;
     const double *x = filtered + (long)chunk * in_stride * 2;
     int best = 0;
@@ -83,7 +82,6 @@ __global__ void symbols_kernel(const double *__restrict__ filtered, long n, long
         num = (n - best) / sps;
         stride_s = sps;
     }
-    if (threadIdx.x == 0) s_best = best;
     // gather symbols, max |x|
     double mx = 0.0;
     double *so = symbols ? symbols + (long)chunk * out_stride * 2 : nullptr;

@@ -48,10 +48,10 @@ class SignalProcessor:
             if self._h is not None:
                 self._h.close()
             # complex128 input needs twice the float32 scratch: size for it
-            cap = max(2 * int(n), 1 << 16)
+            cap = max(2 * int(n) + 128, 1 << 16)
             self._h = _lib.Handle(sample_rate=fs, max_chunks=1, max_chunk_len=cap, mode=_MODES[self.mode],
                                   device=self.device)
-            self._cap = (cap // 2, fs)
+            self._cap = ((cap - 128) // 2, fs)
         return self._h
 
     # ------------------------------------------------------------------ public API
