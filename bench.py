@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — IQ Msamples/s (and CRC-pass bursts/s) of the IQ->bursts receive path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c3|c2]
+                    [--mode exact|fast]
+
+Workload c1 (default, BASELINE.json configs[0]): one synthetic TETRA-like downlink carrier, 10 s of
+complex64 IQ at 2.4 MS/s = 183 whole chunks of 131072 samples (the ragged 0.1-chunk tail is
+dropped, like a capture loop that stops on a chunk boundary), processed exactly as the
+reference's receive loop does per chunk: SignalProcessor.process -> TetraDecoder.decode.
+A "step" is one pass of the hot path over that 192 MB batch (larger than the 126 MB L2, so
+no L2 flush is needed between steps).
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput, `e2e` = the same
+through the host-buffer API with H2D/D2H inside the timed region, `roofline` = the dominant
+stage (decimator) against the measured HBM peak, `cpu_baseline` = the oracle port on the
+box's host cores over a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CHUNK = 131072
+FS = 2.4e6
+C1_CHUNKS = 183          # floor(24e6 / 131072)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------ workload
+def make_c1(seed=1234, n_chunks=C1_CHUNKS):
+    from tetraear_b200 import synth
+    iq = synth.make_capture(n_chunks * CHUNK, 130, seed=seed)
+    return iq.reshape(n_chunks, CHUNK)
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    """process + decode of a list of chunks with the oracle port; returns (samples, crc_pass, seconds)."""
+    from oracle import oracle
+    chunks, fs = args
+    t0 = time.perf_counter()
+    crc = 0
+    n = 0
+    for ch in chunks:
+        d, _, _ = oracle.process(ch, fs, 0.0)
+        _, st = oracle.decode(d)
+        crc += st["crc_pass"]
+        n += len(ch)
+    return n, crc, time.perf_counter() - t0
+
+
+def cpu_run(x, cores, reps=1):
+    """Oracle port over the chunks of x with `cores` worker processes.  Returns (Msamples/s, bursts/s, wall s)."""
+    import multiprocessing as mp
+    from oracle import oracle
+    oracle.lib()                              # compile the C part before forking
+    parts = [list(x[i::cores]) for i in range(cores)]
+    parts = [p for p in parts if p]
+    best = None
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(parts)) as pool:
+        pool.map(_cpu_worker, [([p[0][:4096]], FS) for p in parts])      # warm the workers
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, [(p, FS) for p in parts])
+            wall = time.perf_counter() - t0
+            n = sum(r[0] for r in res)
+            crc = sum(r[1] for r in res)
+            if best is None or wall < best[2]:
+                best = (n / wall / 1e6, crc / wall, wall)
+    return best
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            # "under load": the upper half of the samples (idle samples before/after are excluded)
+            top = sorted(sm)[len(sm) // 2:]
+            out = {"sm_mhz": float(np.median(top)), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.set_device(local_rank)
+    from tetraear_b200 import pipeline, _lib
+
+    # every rank owns one independent 10 s capture (weak scaling: shard = capture segment per GPU)
+    x = make_c1(seed=1234 + rank)
+    n_chunks = x.shape[0]
+    samples_per_step = n_chunks * CHUNK
+    pipe = pipeline.ReceivePipeline(FS, CHUNK, max_chunks=n_chunks, mode=args.mode, device=local_rank)
+    host = torch.from_numpy(x.view(np.float32).reshape(n_chunks, CHUNK, 2)).pin_memory()
+    dev = host.to(f"cuda:{local_rank}")
+    stream = torch.cuda.current_stream()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident: warm-up, then K timed steps
+    for _ in range(args.warmup):
+        pipe.run_device(dev)
+    sync_all()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    l0 = pipe.h.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pipe.stats.zero_()
+    e0.record(stream)
+    for _ in range(args.steps):
+        pipe.run_device(dev)
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = pipe.h.launches - l0
+    stats = pipe.stats.cpu().numpy().copy()
+
+    # ---- end to end: pinned host IQ -> H2D -> kernels -> D2H of frame records, every step
+    for _ in range(max(1, min(args.warmup, 2))):
+        pipe.run_host(host)
+    sync_all()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(args.steps):
+        nfr, frames, st_e2e = pipe.run_host(host)
+    t1.record(stream)
+    sync_all()
+    ms_e2e = t0.elapsed_time(t1)
+    clk = clocks.stop() if clocks else None
+
+    # ---- per-stage device time for the roofline (separate pass so the events do not sit in `value`)
+    pipe.h.profile(True)
+    for _ in range(args.steps):
+        pipe.run_device(dev)
+    torch.cuda.synchronize()
+    prof = pipe.h.profile_read()
+    pipe.h.profile(False)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        s = torch.tensor(stats, dtype=torch.int64, device=f"cuda:{local_rank}")
+        dist.all_reduce(s)
+        stats = s.cpu().numpy()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_samples = samples_per_step * world * args.steps
+    value = total_samples / (ms / 1e3) / 1e6
+    e2e = total_samples / (ms_e2e / 1e3) / 1e6
+    bursts_per_s = float(stats[1]) / (ms / 1e3)
+
+    # roofline of the dominant stage: algorithmic bytes = 8 B per input complex64 sample + 8/q per decimated output
+    peak, peak_src = measured_peaks()
+    dec_ms, dec_calls = prof["decimator"]
+    q = pipe.plan.q
+    alg_bytes = samples_per_step * 8.0 + n_chunks * pipe.plan.n_dec * 8.0
+    dec_launch_ms = dec_ms / max(dec_calls, 1)
+    achieved = alg_bytes / (dec_launch_ms / 1e3) / 1e9
+    stage_ms = {k: round(v[0] / max(v[1], 1), 4) for k, v in prof.items() if v[1]}
+    # whole process() path against the same roofline: 8 B in + 1 B/dibit out per sample
+    path_bytes = samples_per_step * 8.0 + n_chunks * (pipe.plan.max_symbols) * 1.0
+    step_ms = ms / args.steps
+
+    # ---- CPU baseline: oracle port on a bounded sample, rank 0 only at N=1
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = host_cores()
+        sample_chunks = n_chunks
+        one = cpu_run(x[:8], 1)
+        many = cpu_run(x[:sample_chunks], cores)
+        cpu = {"value": round(many[0], 3), "unit": "Msamples/s", "cores": cores, "kind": "port",
+               "sample": f"{sample_chunks} of {n_chunks} chunks (131072 samples each) of the same capture through "
+                         f"oracle.process + oracle.decode, {cores} worker processes; 1-core: {one[0]:.3f} Msamples/s over 8 chunks",
+               "one_core_value": round(one[0], 3), "bursts_per_s": round(many[1], 1)}
+
+    line = {
+        "metric": "iq_msamples_per_s", "value": round(value, 3), "unit": "Msamples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c1: single synthetic TETRA downlink carrier, 10 s complex64 IQ @2.4 MS/s, "
+                               f"{n_chunks} chunks x 131072 samples per GPU, process+decode per chunk (reference mode, "
+                               f"decimator arithmetic '{args.mode}')",
+                   "l2": "input 192 MB per step > 126 MB L2, no flush needed", "parallelism": f"capture segment per GPU x{world}"},
+        "crc_pass_bursts_per_s": round(bursts_per_s, 1), "crc_pass_per_step": int(stats[1] // max(args.steps, 1)),
+        "gpu_launches": int(launches),
+        "e2e": {"value": round(e2e, 3), "unit": "Msamples/s", "h2d_bytes_per_step": pipe.h2d_bytes(n_chunks),
+                "d2h_bytes_per_step": pipe.d2h_bytes(n_chunks), "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "roofline": {"bound": "hbm", "kernel": "decimator stage (cheby1 zero-phase IIR + ::q)", "achieved": round(achieved, 2),
+                     "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "ms_per_launch": round(dec_launch_ms, 4),
+                     "path_achieved_gbs": round(path_bytes / (step_ms / 1e3) / 1e9, 2),
+                     "path_frac": round(path_bytes / (step_ms / 1e3) / 1e9 / peak, 5), "stage_ms": stage_ms},
+        "clocks": clk,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's CPU implementation of the path (oracle port: the reference is pure Python and
+    /root/reference does not exist on the GPU box) on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as entry
+    from oracle import build as ob
+    ob.build()
+    cores = host_cores()
+    sample_chunks = C1_CHUNKS
+    x = make_c1(n_chunks=sample_chunks)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_run(x[:cores], cores)
+    walls, crcs = [], 0.0
+    for _ in range(args.steps):
+        v, b, wall = cpu_run(x, cores)
+        walls.append(wall)
+        crcs += b * wall
+    total = sample_chunks * CHUNK * args.steps
+    value = total / sum(walls) / 1e6
+    line = {
+        "impl": "reference", "metric": "iq_msamples_per_s", "value": round(value, 3), "unit": "Msamples/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1e3 * sum(walls) / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c1: single synthetic TETRA downlink carrier @2.4 MS/s, process+decode per 131072-sample chunk",
+                   "sample": f"{sample_chunks} chunks per step"},
+        "crc_pass_bursts_per_s": round(crcs / sum(walls), 1),
+        "cpu_baseline": {"value": round(value, 3), "unit": "Msamples/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_chunks} chunks x 131072 samples per step, {cores} worker processes, "
+                                   "oracle.process + oracle.decode (C + numpy restatement of the Python reference)"},
+        "e2e": {"value": round(value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("TB200_BENCH_MODE", "exact"), choices=["exact", "fast"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

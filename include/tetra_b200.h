@@ -189,6 +189,14 @@ int tb200_psd_batch(tb200_handle h, const void *d_iq_c64, int64_t n_frames, int6
                     int n_fft, double sample_rate, double ema_alpha, int first, float *d_power,
                     float *d_smoothed, double *d_ema_state, double *d_stats, void *stream);
 
+/* ---- per-stage device timing (bench.py's roofline): when enabled every entry point brackets
+ * its stages with CUDA events on the launching stream; tb200_profile_read synchronises them,
+ * sums the elapsed milliseconds per stage and clears the list.
+ * stages: 0 decimator, 1 channel filter (NCO + Butterworth), 2 timing pick + slicer,
+ *         3 bits + sync correlation, 4 sync select + frame/burst/CRC, 5 burst batch, 6 PSD, 7 etsi */
+int tb200_profile_enable(tb200_handle h, int on);
+int tb200_profile_read(tb200_handle h, double ms[8], int64_t calls[8]);
+
 /* ---- debugging aid: synchronous copy of an internal workspace region to the host ---------
  * region 0 = decimated chunks, 1 = channel-filtered complex128, 2 / 3 = forward-pass scratches */
 int tb200_debug_read(tb200_handle h, int region, void *h_dst, size_t nbytes);

@@ -58,6 +58,8 @@ _PROTOS = {
     "tb200_burst_batch": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "tb200_burst_batch_host": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "tb200_crc16_rows": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "tb200_profile_enable": (_i, [_vp, _i]),
+    "tb200_profile_read": (_i, [_vp, _vp, _vp]),
     "tb200_debug_read": (_i, [_vp, _i, _vp, C.c_size_t]),
     "tb200_psd_batch": (_i, [_vp, _vp, _i64, _i64, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
 }
@@ -124,6 +126,17 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+    def profile(self, on=True):
+        check(self.lib.tb200_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """{stage name: (total ms, calls)} since the last read."""
+        ms = (C.c_double * 8)()
+        calls = (C.c_int64 * 8)()
+        check(self.lib.tb200_profile_read(self.h, ms, calls))
+        names = ("decimator", "channel_filter", "symbols", "bits_sync", "decode", "burst_batch", "psd", "etsi")
+        return {n: (float(ms[i]), int(calls[i])) for i, n in enumerate(names)}
 
     @property
     def launches(self):

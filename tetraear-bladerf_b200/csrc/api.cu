@@ -21,6 +21,7 @@ int fail(int code, const char *fmt, ...)
 int ensure_crc_tables(int device);
 int launch_decimate_fast(tb200_handle h, const void *x, int n_chunks, long n, long chunk_stride, int q,
                          const DecimDesign &d, void *dec_out, long n_dec, cudaStream_t st);
+int fast_decimator_supported(int q);
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -110,9 +111,49 @@ static int get_chan(tb200_handle h, double bw, double rate)
     return TB200_OK;
 }
 
+// RAII stage timer: records an event pair around a stage when profiling is on
+struct StageTimer {
+    tb200_handle h; cudaStream_t st; bool on;
+    StageTimer(tb200_handle h_, int stage, cudaStream_t st_) : h(h_), st(st_), on(h_->profiling != 0)
+    {
+        if (!on) return;
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { on = false; return; }
+        h->prof_ev->push_back(a); h->prof_ev->push_back(b); h->prof_stage->push_back(stage);
+        cudaEventRecord(a, st);
+    }
+    ~StageTimer() { if (on) cudaEventRecord(h->prof_ev->back(), st); }
+};
+
 }  // namespace tb200
 
 using namespace tb200;
+
+extern "C" int tb200_profile_enable(tb200_handle h, int on)
+{
+    if (!h) return fail(TB200_E_ARG, "tb200_profile_enable: null handle");
+    if (!h->prof_ev) { h->prof_ev = new std::vector<cudaEvent_t>(); h->prof_stage = new std::vector<int>(); }
+    h->profiling = on;
+    return TB200_OK;
+}
+
+extern "C" int tb200_profile_read(tb200_handle h, double ms[TB200_N_STAGES], int64_t calls[TB200_N_STAGES])
+{
+    if (!h || !ms || !calls) return fail(TB200_E_ARG, "tb200_profile_read: bad argument");
+    for (int i = 0; i < TB200_N_STAGES; ++i) { ms[i] = 0.0; calls[i] = 0; }
+    if (!h->prof_ev) return TB200_OK;
+    for (size_t k = 0; k < h->prof_stage->size(); ++k) {
+        cudaEvent_t a = (*h->prof_ev)[2 * k], b = (*h->prof_ev)[2 * k + 1];
+        TB_CUDA(cudaEventSynchronize(b));
+        float t = 0.f;
+        TB_CUDA(cudaEventElapsedTime(&t, a, b));
+        int sgi = (*h->prof_stage)[k];
+        ms[sgi] += t; calls[sgi] += 1;
+        cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+    h->prof_ev->clear(); h->prof_stage->clear();
+    return TB200_OK;
+}
 
 extern "C" const char *tb200_last_error(void) { return g_err; }
 extern "C" int tb200_version(void) { return 100; }
@@ -166,6 +207,10 @@ extern "C" int tb200_destroy(tb200_handle h)
     if (!h) return TB200_OK;
     cudaSetDevice(h->cfg.device);
     if (h->ws) cudaFree(h->ws);
+    if (h->prof_ev) {
+        for (cudaEvent_t e : *h->prof_ev) cudaEventDestroy(e);
+        delete h->prof_ev; delete h->prof_stage;
+    }
     delete h;
     return TB200_OK;
 }
@@ -222,7 +267,8 @@ extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, 
         if (rc) return rc;
         if ((size_t)n_chunks * P.n_dec * 2 * esz > h->dec_bytes)
             return fail(TB200_E_ARG, "tb200_process_batch: decimated batch exceeds workspace");
-        if (h->cfg.mode == TB200_MODE_FAST && dtype == TB200_DTYPE_C64) {
+        StageTimer tm(h, TB_STAGE_DECIM, st);
+        if (h->cfg.mode == TB200_MODE_FAST && dtype == TB200_DTYPE_C64 && fast_decimator_supported(P.q)) {
             rc = launch_decimate_fast(h, d_iq, n_chunks, chunk_len, (long)chunk_stride, P.q, h->dec, h->dec_out, P.n_dec, st);
         } else {
             if ((size_t)n_chunks * 2 * (chunk_len + 54) * esz > h->fwd_bytes)
@@ -238,9 +284,13 @@ extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, 
         return fail(TB200_E_ARG, "tb200_process_batch: batch exceeds the channel-filter workspace");
     rc = get_chan(h, 25000.0, P.rate);
     if (rc) return rc;
-    rc = launch_channel_exact(h, x, cur_dtype, n_chunks, P.n_dec, in_stride, d_freq_off, P.rate, h->chan, P.filtered,
-                              h->chan_fwd, h->filtered, P.n_dec, st);
+    {
+        StageTimer tm(h, TB_STAGE_CHAN, st);
+        rc = launch_channel_exact(h, x, cur_dtype, n_chunks, P.n_dec, in_stride, d_freq_off, P.rate, h->chan, P.filtered,
+                                  h->chan_fwd, h->filtered, P.n_dec, st);
+    }
     if (rc) return rc;
+    StageTimer tm(h, TB_STAGE_SYMBOLS, st);
     return launch_symbols(h, h->filtered, n_chunks, P.n_dec, P.n_dec, P.sps, P.phase_step, (double *)d_symbols, d_dibits,
                           out_stride, d_n_dibits, nullptr, d_phase, st);
 }
@@ -286,6 +336,8 @@ extern "C" int tb200_decimate(tb200_handle h, const void *d_x, int dtype, int n,
     int rc = get_decim(h, q);
     if (rc) return rc;
     long n_dec = (n + q - 1) / q;
+    if (h->cfg.mode == TB200_MODE_FAST && dtype == TB200_DTYPE_C64 && fast_decimator_supported(q))
+        return launch_decimate_fast(h, d_x, 1, n, n, q, h->dec, d_out, n_dec, (cudaStream_t)stream);
     return launch_decimate_exact(h, d_x, dtype, 1, n, n, q, h->dec, h->fwd, d_out, n_dec, (cudaStream_t)stream);
 }
 
@@ -365,10 +417,15 @@ extern "C" int tb200_decode_batch(tb200_handle h, const uint8_t *d_dibits, int n
     if ((size_t)n_streams * max_frames > (size_t)h->max_streams * h->max_frames)
         return fail(TB200_E_ARG, "tb200_decode_batch: max_frames too large for the handle");
     if (stride == 0) { TB_CUDA(cudaMemsetAsync(d_n_frames, 0, sizeof(int32_t) * n_streams, st)); return TB200_OK; }
-    int rc = launch_symbols_to_bits(h, d_dibits, n_streams, stride, d_n_dibits, 0, h->bits, h->mapped, bstride, st);
-    if (rc) return rc;
-    rc = launch_sync_corr(h, h->bits, n_streams, bstride, d_n_dibits, 0, h->m1, h->m2, st);
-    if (rc) return rc;
+    int rc;
+    {
+        StageTimer tm(h, TB_STAGE_BITS_SYNC, st);
+        rc = launch_symbols_to_bits(h, d_dibits, n_streams, stride, d_n_dibits, 0, h->bits, h->mapped, bstride, st);
+        if (rc) return rc;
+        rc = launch_sync_corr(h, h->bits, n_streams, bstride, d_n_dibits, 0, h->m1, h->m2, st);
+        if (rc) return rc;
+    }
+    StageTimer tm(h, TB_STAGE_DECODE, st);
     return launch_decode(h, h->bits, h->mapped, h->m1, h->m2, n_streams, bstride, d_n_dibits, d_frames, max_frames,
                          d_n_frames, d_stats, st);
 }
@@ -377,6 +434,7 @@ extern "C" int tb200_burst_batch(tb200_handle h, const uint8_t *d_dibits, int64_
                                  int64_t *d_stats, void *stream)
 {
     if (!h || n < 0 || (n && (!d_dibits || !d_rec))) return fail(TB200_E_ARG, "tb200_burst_batch: bad argument");
+    StageTimer tm(h, TB_STAGE_BURST, (cudaStream_t)stream);
     return launch_burst_batch(h, d_dibits, n, d_rec, d_full, d_stats, (cudaStream_t)stream);
 }
 
@@ -417,6 +475,7 @@ extern "C" int tb200_psd_batch(tb200_handle h, const void *d_iq_c64, int64_t n_f
     if (n_fft < 16 || (n_fft & (n_fft - 1)) || n_fft > h->cfg.max_fft)
         return fail(TB200_E_ARG, "tb200_psd_batch: n_fft must be a power of two in [16, %d]", h->cfg.max_fft);
     if (d_smoothed && (!d_power || !d_ema_state)) return fail(TB200_E_ARG, "tb200_psd_batch: smoothing needs d_power and d_ema_state");
+    StageTimer tm(h, TB_STAGE_PSD, (cudaStream_t)stream);
     return launch_psd(h, (const float *)d_iq_c64, n_frames, frame_stride, n_fft, sample_rate, ema_alpha, first, d_power,
                       d_smoothed, d_ema_state, d_stats, h->psd_tables, (cudaStream_t)stream);
 }

@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <vector>
 #include "../../include/tetra_b200.h"
 
 namespace tb200 {
@@ -41,9 +42,17 @@ struct ChanDesign {
 
 }  // namespace tb200
 
+#define TB200_N_STAGES 8
+enum { TB_STAGE_DECIM = 0, TB_STAGE_CHAN = 1, TB_STAGE_SYMBOLS = 2, TB_STAGE_BITS_SYNC = 3, TB_STAGE_DECODE = 4,
+       TB_STAGE_BURST = 5, TB_STAGE_PSD = 6, TB_STAGE_ETSI = 7 };
+
 struct tb200_handle_s {
     tb200_config cfg;
     int64_t launches;
+    // optional per-stage CUDA-event timing (tb200_profile_*): pairs recorded on the launching stream
+    int profiling;
+    std::vector<cudaEvent_t> *prof_ev;      // flat: start, stop, start, stop ...
+    std::vector<int> *prof_stage;
     tb200_plan plan;             // for (cfg.sample_rate, cfg.max_chunk_len)
     // cached designs
     int dec_q;                   // q the decimator design below is for (0 = none)

@@ -1,11 +1,407 @@
-// dsp_fast.cu — time-tiled ("FAST" mode) decimator.  Placeholder until the tiled kernel lands.
+// dsp_fast.cu — time-parallel ("FAST" mode) zero-phase decimator for scipy.signal.decimate(x, q)
+// as called by SignalProcessor.process (/root/reference/tetraear/signal/processor.py:254).
+//
+// Same filter as the reference (the float32-rounded cheby1 biquads, odd extension, steady-state
+// initial conditions, forward + backward pass, keep every q-th sample) but evaluated in a form
+// that has no long recurrence:
+//
+//   H(z) H(1/z) over the padded chunk  ==  sum over the 4 conjugate pole pairs p_i of
+//        2 Re{ alpha_i ( F_i[n] + p_i B_i[n+1] ) }  -  (right-edge transient),
+//   F_i[n] = sum_{k>=0} p_i^k x[n-k]   (causal one-pole),  B_i[n] = sum_{k>=0} p_i^k x[n+k].
+//
+// Only every q-th output is needed, so per kept output k the work is two q-tap complex FIRs
+//   U_i[k] = sum_{j<q} p_i^j x[n_k - j],   V_i[k] = sum_{j<q} p_i^j x[n_k + 1 + j]
+// plus the decimated-rate recurrences F[k] = lambda F[k-1] + U[k], Bq[k] = V[k] + lambda Bq[k+1]
+// with lambda = p^q (|lambda| <= 0.834 for q = 10).  A pass of 96 outputs forgets its past to
+// 0.834^96 = 3e-8, so each warp works on one 96-output pass from a zero state and receives the
+// end state of its neighbour warp as carry; warp-level Kogge-Stone scans (shuffles) resolve
+// the recurrence inside the pass.  The residues alpha_i are ~1e-2, so float32 is ample: the
+// result is within 2e-7 of the exact-arithmetic filter (the reference's own float32 recursion
+// is 3e-5 away from it; DESIGN.md "FAST mode accuracy").
+//
+// Data layout: a CTA stages its tile of the padded chunk in shared memory as separate I and Q
+// planes, one row of q samples per output with an odd row pitch (q+1 for even q), so that the
+// 32 lanes of a warp — each owning R=3 consecutive rows — read conflict-free.
+#include <complex>
 #include "common.h"
 #include "kernels.h"
+
 namespace tb200 {
+
+constexpr int FD_R = 3;              // outputs per lane
+constexpr int FD_P = 32 * FD_R;      // outputs per warp pass
+constexpr int FD_W = 8;              // warps per CTA: 1 left-halo + 6 storing + 1 right-halo
+constexpr int FD_QMAX = 16;
+constexpr int FD_EDGE_W = 1316;      // warm-up length of the edge kernel (0.982^1316 = 4e-11)
+
+struct FastDecimParams {
+    float tap[FD_QMAX][4][2];        // p_i^j
+    float lam[4][2];                 // lambda_i = p_i^q
+    float lampow[5][4][2];           // (lambda^R)^(2^s), Kogge-Stone multipliers
+    float a0[4][2];                  // alpha_i
+    float ap[4][2];                  // alpha_i p_i
+    float aF[FD_R][4][2];            // alpha_i lambda^(r+1)
+    float aB[FD_R][4][2];            // alpha_i p_i lambda^(R-r)
+    // edge kernel (right-end transient), complex as (re, im)
+    float p[4][2];                   // p_i
+    float inv1mp[4][2];              // 1 / (1 - p_i)
+    float ka[4][2];                  // kappa_i = ka_i * xc + sum_j kM[i][j] F_j + kMc[i][j] conj(F_j)
+    float kM[4][4][2];
+    float kMc[4][4][2];
+    float pc[4][2];                  // p_i^(M - n_last)
+};
+
+struct cf { float x, y; };
+__device__ __forceinline__ cf cmulf(cf a, cf b) { return cf{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cf cfma(cf a, cf b, cf c) { return cf{fmaf(a.x, b.x, fmaf(-a.y, b.y, c.x)), fmaf(a.x, b.y, fmaf(a.y, b.x, c.y))}; }
+__device__ __forceinline__ cf cshfl_up(cf v, int d) { return cf{__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d)}; }
+__device__ __forceinline__ cf cshfl_down(cf v, int d) { return cf{__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d)}; }
+__device__ __forceinline__ cf cshfl(cf v, int l) { return cf{__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l)}; }
+__device__ __forceinline__ cf ld2(const float c[2]) { return cf{c[0], c[1]}; }
+
+// sample t of the padded signal (ext coordinates, scipy odd_ext with edge 27) continued by the
+// constants the steady-state initial conditions stand for: ext[0] to the left, ext[M-1] to the right
+__device__ __forceinline__ float2 padded_sample(const float2 *__restrict__ x, long n, long t)
+{
+    const long edge = 27;
+    if (t >= edge && t < edge + n) return x[t - edge];
+    float2 e, v;
+    if (t < edge) { e = x[0]; v = x[t < 0 ? edge : edge - t]; }
+    else { long u = t - edge - n; e = x[n - 1]; v = x[u < edge ? n - 2 - u : n - 1 - edge]; }
+    return make_float2(__fsub_rn(__fmul_rn(2.0f, e.x), v.x), __fsub_rn(__fmul_rn(2.0f, e.y), v.y));
+}
+
+template <int Q>
+__global__ void __launch_bounds__(FD_W * 32, 2)
+decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int tiles_per_chunk, long n_dec,
+                  FastDecimParams K, float2 *__restrict__ dec_out)
+{
+    constexpr int PITCH = (Q & 1) ? Q : Q + 1;
+    constexpr int ROWS = FD_W * FD_P + 1;
+    extern __shared__ float fd_smem[];
+    float *sI = fd_smem;
+    float *sQ = fd_smem + ROWS * PITCH;
+    __shared__ cf carryF[FD_W][2][4];
+    __shared__ cf carryB[FD_W][2][4];
+
+    const int chunk = blockIdx.x / tiles_per_chunk;
+    const int tile = blockIdx.x - chunk * tiles_per_chunk;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float2 *xc = x + (long)chunk * chunk_stride;
+    // first output of warp 0 (the left-halo pass) and the padded-signal position of tile row 0, col 0
+    const long k_tile0 = (long)tile * (FD_W - 2) * FD_P - FD_P;
+    const long t0 = 27 + (long)Q * k_tile0 - (Q - 1);
+
+    // ---- stage the tile: coalesced float2 loads -> I/Q planes with odd pitch
+    for (int s = threadIdx.x; s < ROWS * Q; s += blockDim.x) {
+        float2 v = padded_sample(xc, n, t0 + s);
+        int row = s / Q, col = s - row * Q;
+        sI[row * PITCH + col] = v.x;
+        sQ[row * PITCH + col] = v.y;
+    }
+    __syncthreads();
+
+    const bool do_F = w < FD_W - 1, do_B = w > 0, store = w > 0 && w < FD_W - 1;
+    const int row0 = w * FD_P + lane * FD_R;
+    float yI[FD_R], yQ[FD_R];
+#pragma unroll
+    for (int r = 0; r < FD_R; ++r) yI[r] = yQ[r] = 0.f;
+
+    // ---- forward (causal) part
+    if (do_F) {
+        cf UI[FD_R][4], UQ[FD_R][4];
+#pragma unroll
+        for (int r = 0; r < FD_R; ++r) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) UI[r][m] = UQ[r][m] = cf{0.f, 0.f};
+            const float *pi = sI + (row0 + r) * PITCH, *pq = sQ + (row0 + r) * PITCH;
+#pragma unroll
+            for (int c = 0; c < Q; ++c) {
+                float xi = pi[c], xq = pq[c];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    float tr = K.tap[Q - 1 - c][m][0], ti = K.tap[Q - 1 - c][m][1];
+                    UI[r][m].x = fmaf(tr, xi, UI[r][m].x); UI[r][m].y = fmaf(ti, xi, UI[r][m].y);
+                    UQ[r][m].x = fmaf(tr, xq, UQ[r][m].x); UQ[r][m].y = fmaf(ti, xq, UQ[r][m].y);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const cf lam = ld2(K.lam[m]);
+            // zero-state recurrence inside the lane
+#pragma unroll
+            for (int r = 1; r < FD_R; ++r) { UI[r][m] = cfma(lam, UI[r - 1][m], UI[r][m]); UQ[r][m] = cfma(lam, UQ[r - 1][m], UQ[r][m]); }
+            // inclusive scan of lane aggregates (multiplier lambda^R per lane)
+            cf aI = UI[FD_R - 1][m], aQ = UQ[FD_R - 1][m];
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                cf oI = cshfl_up(aI, 1 << s), oQ = cshfl_up(aQ, 1 << s);
+                if (lane >= (1 << s)) { cf g = ld2(K.lampow[s][m]); aI = cfma(g, oI, aI); aQ = cfma(g, oQ, aQ); }
+            }
+            cf cI = cshfl_up(aI, 1), cQ = cshfl_up(aQ, 1);
+            if (lane == 0) cI = cQ = cf{0.f, 0.f};
+            if (lane == 31) { carryF[w][0][m] = aI; carryF[w][1][m] = aQ; }
+            const cf a0 = ld2(K.a0[m]);
+#pragma unroll
+            for (int r = 0; r < FD_R; ++r) {
+                const cf af = ld2(K.aF[r][m]);
+                // Re(alpha Fz[r]) + Re(alpha lambda^(r+1) cin)
+                yI[r] += a0.x * UI[r][m].x - a0.y * UI[r][m].y + af.x * cI.x - af.y * cI.y;
+                yQ[r] += a0.x * UQ[r][m].x - a0.y * UQ[r][m].y + af.x * cQ.x - af.y * cQ.y;
+            }
+        }
+    }
+    // ---- backward (anti-causal) part: V uses the NEXT row, taps in ascending order
+    if (do_B) {
+        cf VI[FD_R][4], VQ[FD_R][4];
+#pragma unroll
+        for (int r = 0; r < FD_R; ++r) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) VI[r][m] = VQ[r][m] = cf{0.f, 0.f};
+            const float *pi = sI + (row0 + r + 1) * PITCH, *pq = sQ + (row0 + r + 1) * PITCH;
+#pragma unroll
+            for (int c = 0; c < Q; ++c) {
+                float xi = pi[c], xq = pq[c];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    float tr = K.tap[c][m][0], ti = K.tap[c][m][1];
+                    VI[r][m].x = fmaf(tr, xi, VI[r][m].x); VI[r][m].y = fmaf(ti, xi, VI[r][m].y);
+                    VQ[r][m].x = fmaf(tr, xq, VQ[r][m].x); VQ[r][m].y = fmaf(ti, xq, VQ[r][m].y);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const cf lam = ld2(K.lam[m]);
+#pragma unroll
+            for (int r = FD_R - 2; r >= 0; --r) { VI[r][m] = cfma(lam, VI[r + 1][m], VI[r][m]); VQ[r][m] = cfma(lam, VQ[r + 1][m], VQ[r][m]); }
+            cf aI = VI[0][m], aQ = VQ[0][m];
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                cf oI = cshfl_down(aI, 1 << s), oQ = cshfl_down(aQ, 1 << s);
+                if (lane + (1 << s) < 32) { cf g = ld2(K.lampow[s][m]); aI = cfma(g, oI, aI); aQ = cfma(g, oQ, aQ); }
+            }
+            cf cI = cshfl_down(aI, 1), cQ = cshfl_down(aQ, 1);
+            if (lane == 31) cI = cQ = cf{0.f, 0.f};
+            if (lane == 0) { carryB[w][0][m] = aI; carryB[w][1][m] = aQ; }
+            const cf ap = ld2(K.ap[m]);
+#pragma unroll
+            for (int r = 0; r < FD_R; ++r) {
+                const cf ab = ld2(K.aB[r][m]);
+                yI[r] += ap.x * VI[r][m].x - ap.y * VI[r][m].y + ab.x * cI.x - ab.y * cI.y;
+                yQ[r] += ap.x * VQ[r][m].x - ap.y * VQ[r][m].y + ab.x * cQ.x - ab.y * cQ.y;
+            }
+        }
+    }
+    __syncthreads();
+    if (!store) return;
+    // ---- carries from the neighbour passes: lambda^(lane R) cF on the left, lambda^((31-lane) R) cB on the right
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        cf LF = cf{1.f, 0.f}, LB = cf{1.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            cf g = ld2(K.lampow[s][m]);
+            if (lane & (1 << s)) LF = cmulf(LF, g);
+            if ((31 - lane) & (1 << s)) LB = cmulf(LB, g);
+        }
+        cf gFI = cmulf(LF, carryF[w - 1][0][m]), gFQ = cmulf(LF, carryF[w - 1][1][m]);
+        cf gBI = cmulf(LB, carryB[w + 1][0][m]), gBQ = cmulf(LB, carryB[w + 1][1][m]);
+#pragma unroll
+        for (int r = 0; r < FD_R; ++r) {
+            const cf af = ld2(K.aF[r][m]), ab = ld2(K.aB[r][m]);
+            yI[r] += af.x * gFI.x - af.y * gFI.y + ab.x * gBI.x - ab.y * gBI.y;
+            yQ[r] += af.x * gFQ.x - af.y * gFQ.y + ab.x * gBQ.x - ab.y * gBQ.y;
+        }
+    }
+    float2 *out = dec_out + (long)chunk * n_dec;
+    const long k0 = k_tile0 + row0;
+#pragma unroll
+    for (int r = 0; r < FD_R; ++r) {
+        long k = k0 + r;
+        if (k >= 0 && k < n_dec) out[k] = make_float2(2.0f * yI[r], 2.0f * yQ[r]);
+    }
+}
+
+// Right-end transient: the backward pass of filtfilt starts from the steady state of the LAST
+// forward output, not from the forward filter's continuation; the difference is a decaying sum of
+// the 4 modes, kappa_i p_i^(M-n).  One warp per chunk: lanes 0..7 run the (mode, I/Q) one-pole
+// recurrences over the last FD_EDGE_W padded samples to get F_i[M-1], then every lane corrects
+// its share of the last outputs.
+__global__ void decim_fast_edge_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_chunks, int q,
+                                       long n_dec, FastDecimParams K, float2 *__restrict__ dec_out)
+{
+    const int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (chunk >= n_chunks) return;
+    const float2 *xc = x + (long)chunk * chunk_stride;
+    const long M = n + 54;
+    const int m = lane & 3, comp = (lane >> 2) & 1;
+    const cf p = ld2(K.p[m]);
+    long tstart = M - FD_EDGE_W;
+    cf s = cf{0.f, 0.f};
+    if (tstart <= 0) {                       // short chunk: exact steady state of the left constant
+        tstart = 0;
+        float2 e = padded_sample(xc, n, -1);
+        cf i1 = ld2(K.inv1mp[m]);
+        float v = comp ? e.y : e.x;
+        s = cf{i1.x * v, i1.y * v};
+    }
+    if (lane < 8) {
+        for (long t = tstart; t < M; ++t) {
+            float2 e = padded_sample(xc, n, t);
+            float v = comp ? e.y : e.x;
+            cf ns = cmulf(p, s);
+            s = cf{ns.x + v, ns.y};
+        }
+    }
+    // kappa for (mode mi, comp ci) on lanes 0..7 : gather the four F_j of the same comp
+    float2 last = padded_sample(xc, n, M - 1);
+    float xlast = comp ? last.y : last.x;
+    cf kap = cf{K.ka[m][0] * xlast, K.ka[m][1] * xlast};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        cf Fj = cshfl(s, comp * 4 + j);
+        kap = cfma(ld2(K.kM[m][j]), Fj, kap);
+        kap = cfma(ld2(K.kMc[m][j]), cf{Fj.x, -Fj.y}, kap);
+    }
+    // every lane needs all 8 kappas
+    cf kI[4], kQ[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { kI[j] = cshfl(kap, j); kQ[j] = cshfl(kap, 4 + j); }
+    // outputs k = n_dec-1-mm, mm = lane, lane+32, ... : corr = 2 Re sum_i kappa_i pc_i lambda_i^mm
+    float2 *out = dec_out + (long)chunk * n_dec;
+    const int n_fix = 160;
+    cf lp[4], l32[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        cf lam = ld2(K.lam[j]);
+        cf a = cf{1.f, 0.f}, b = lam;
+        for (int bit = 0; bit < 5; ++bit) { if (lane & (1 << bit)) a = cmulf(a, b); b = cmulf(b, b); }
+        lp[j] = cmulf(a, ld2(K.pc[j]));      // pc lambda^lane
+        l32[j] = b;                           // lambda^32
+    }
+    for (int mm = lane; mm < n_fix; mm += 32) {
+        long k = n_dec - 1 - mm;
+        float cI = 0.f, cQ = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cI += kI[j].x * lp[j].x - kI[j].y * lp[j].y;
+            cQ += kQ[j].x * lp[j].x - kQ[j].y * lp[j].y;
+            lp[j] = cmulf(lp[j], l32[j]);
+        }
+        if (k >= 0) { float2 v = out[k]; out[k] = make_float2(v.x - 2.0f * cI, v.y - 2.0f * cQ); }
+    }
+    (void)q;
+}
+
+// ---- host: modal design from the float32-rounded biquads (double precision) -----------------
+typedef std::complex<double> cd;
+
+static void put(float dst[2], cd v) { dst[0] = (float)v.real(); dst[1] = (float)v.imag(); }
+
+static int make_fast_params(const DecimDesign &d, int q, long n, long n_dec, FastDecimParams &K)
+{
+    cd p8[8], r8[8];
+    const double g = (double)d.sos32[0];
+    for (int s = 0; s < 4; ++s) {
+        double a1 = (double)d.sos32[6 * s + 4], a2 = (double)d.sos32[6 * s + 5];
+        double disc = a1 * a1 - 4 * a2;
+        if (!(disc < 0)) return fail(TB200_E_ARG, "fast decimator: real pole pair in section %d", s);
+        p8[s] = cd(-a1 / 2, std::sqrt(-disc) / 2);
+        p8[s + 4] = std::conj(p8[s]);
+    }
+    cd prodp(1.0, 0.0);
+    for (int i = 0; i < 8; ++i) prodp *= p8[i];
+    const double dd = g / prodp.real();
+    for (int i = 0; i < 8; ++i) {
+        cd num = g * std::pow(1.0 + 1.0 / p8[i], 8), den(1.0, 0.0);
+        for (int j = 0; j < 8; ++j) if (j != i) den *= (1.0 - p8[j] / p8[i]);
+        r8[i] = num / den;
+    }
+    cd alpha[4], lam[4];
+    for (int j = 0; j < 4; ++j) {
+        cd acc(dd, 0.0);
+        for (int i = 0; i < 8; ++i) acc += r8[i] / (1.0 - p8[i] * p8[j]);
+        alpha[j] = r8[j] * acc;
+        lam[j] = std::pow(p8[j], q);
+    }
+    memset(&K, 0, sizeof(K));
+    for (int j = 0; j < 4; ++j) {
+        cd pw(1.0, 0.0);
+        for (int t = 0; t < q; ++t) { put(K.tap[t][j], pw); pw *= p8[j]; }
+        put(K.lam[j], lam[j]);
+        cd lr = std::pow(lam[j], FD_R);
+        for (int s = 0; s < 5; ++s) { put(K.lampow[s][j], lr); lr *= lr; }
+        put(K.a0[j], alpha[j]);
+        put(K.ap[j], alpha[j] * p8[j]);
+        for (int r = 0; r < FD_R; ++r) {
+            put(K.aF[r][j], alpha[j] * std::pow(lam[j], r + 1));
+            put(K.aB[r][j], alpha[j] * p8[j] * std::pow(lam[j], FD_R - r));
+        }
+        put(K.p[j], p8[j]);
+        put(K.inv1mp[j], 1.0 / (1.0 - p8[j]));
+    }
+    // kappa_i = r_i E_i,  E_i = (G - wlast)/(1-p_i) + sum_j r_j delta_j p_j / (1 - p_i p_j),
+    // G = xc H(1), wlast = d xc + sum_j r_j F_j, delta_j = F_j - xc/(1-p_j)   (j over all 8 poles)
+    cd H1(dd, 0.0);
+    for (int j = 0; j < 8; ++j) H1 += r8[j] / (1.0 - p8[j]);
+    const long M = n + 54;
+    const long n_last = 27 + (long)q * (n_dec - 1);
+    for (int i = 0; i < 4; ++i) {
+        cd ka = (H1 - dd) / (1.0 - p8[i]);
+        cd kM[8];
+        for (int j = 0; j < 8; ++j) {
+            ka -= r8[j] * p8[j] / ((1.0 - p8[i] * p8[j]) * (1.0 - p8[j]));
+            kM[j] = -r8[j] / (1.0 - p8[i]) + r8[j] * p8[j] / (1.0 - p8[i] * p8[j]);
+        }
+        put(K.ka[i], r8[i] * ka);
+        for (int j = 0; j < 4; ++j) { put(K.kM[i][j], r8[i] * kM[j]); put(K.kMc[i][j], r8[i] * kM[j + 4]); }
+        put(K.pc[i], std::pow(p8[i], (double)(M - n_last)));
+    }
+    return TB200_OK;
+}
+
+int fast_decimator_supported(int q) { return q == 10 || q == 7 || q == 8; }
+
+template <int Q>
+static int launch_q(tb200_handle h, const void *x, int n_chunks, long n, long chunk_stride, long n_dec,
+                    const FastDecimParams &K, void *dec_out, cudaStream_t st)
+{
+    constexpr int PITCH = (Q & 1) ? Q : Q + 1;
+    constexpr int ROWS = FD_W * FD_P + 1;
+    const size_t smem = sizeof(float) * 2 * ROWS * PITCH;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(decim_fast_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(decim_fast): %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int per_tile = (FD_W - 2) * FD_P;
+    const int tiles = (int)((n_dec + per_tile - 1) / per_tile);
+    decim_fast_kernel<Q><<<n_chunks * tiles, FD_W * 32, smem, st>>>((const float2 *)x, n, chunk_stride, tiles, n_dec, K,
+                                                                  (float2 *)dec_out);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
 int launch_decimate_fast(tb200_handle h, const void *x, int n_chunks, long n, long chunk_stride, int q,
                          const DecimDesign &d, void *dec_out, long n_dec, cudaStream_t st)
 {
-    (void)h; (void)x; (void)n_chunks; (void)n; (void)chunk_stride; (void)q; (void)d; (void)dec_out; (void)n_dec; (void)st;
-    return fail(TB200_E_ARG, "TB200_MODE_FAST is not available in this build");
+    if (!fast_decimator_supported(q)) return fail(TB200_E_ARG, "fast decimator: q=%d not instantiated", q);
+    FastDecimParams K;
+    int rc = make_fast_params(d, q, n, n_dec, K);
+    if (rc) return rc;
+    if (q == 10) rc = launch_q<10>(h, x, n_chunks, n, chunk_stride, n_dec, K, dec_out, st);
+    else if (q == 7) rc = launch_q<7>(h, x, n_chunks, n, chunk_stride, n_dec, K, dec_out, st);
+    else rc = launch_q<8>(h, x, n_chunks, n, chunk_stride, n_dec, K, dec_out, st);
+    if (rc) return rc;
+    int threads = 128, blocks = (n_chunks * 32 + threads - 1) / threads;
+    decim_fast_edge_kernel<<<blocks, threads, 0, st>>>((const float2 *)x, n, chunk_stride, n_chunks, q, n_dec, K,
+                                                      (float2 *)dec_out);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
 }
+
 }  // namespace tb200
