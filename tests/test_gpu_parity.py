@@ -229,6 +229,13 @@ def test_fast_mode_within_tolerance(mods, golden_process, process_inputs):
         truth = sg.sosfiltfilt(sos32.astype(np.float64), iq.astype(np.complex128))[::q]
         assert np.abs(got - ref).max() <= 1e-4, (n, q, np.abs(got - ref).max())
         assert np.abs(got - truth).max() <= 2e-6, (n, q, np.abs(got - truth).max())
+    # channel filter (FAST = float64 modal form): agrees with scipy's filtfilt to ~1e-13
+    dec = oracle.decimate(process_inputs["c1_chunk0"][2], 10)
+    for sl in (slice(None), slice(0, 16), slice(0, 100), slice(0, 2000)):
+        got = sp.filter_signal(dec[sl], 25000, 240000.0)
+        assert np.abs(got - oracle.filter_signal(dec[sl], 25000, 240000.0)).max() <= 1e-11, sl
+    sh = oracle.frequency_shift(dec, 777.0, 240000.0)
+    assert np.abs(sp.filter_signal(sh, 25000, 240000.0) - oracle.filter_signal(sh, 25000, 240000.0)).max() <= 1e-11
     # q = 83 falls back to the exact kernel in FAST mode: bit-identical
     fs, f, iq = process_inputs["wide_q83"]
     spw = signal.SignalProcessor(fs, mode="fast")

@@ -22,6 +22,9 @@ int ensure_crc_tables(int device);
 int launch_decimate_fast(tb200_handle h, const void *x, int n_chunks, long n, long chunk_stride, int q,
                          const DecimDesign &d, void *dec_out, long n_dec, cudaStream_t st);
 int fast_decimator_supported(int q);
+int launch_channel_fast(tb200_handle h, const void *x, int dtype, int n_chunks, long n, long in_stride,
+                        const double *freq_off, double fs, double bandwidth, double *filtered, long out_stride,
+                        cudaStream_t st);
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -286,8 +289,12 @@ extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, 
     if (rc) return rc;
     {
         StageTimer tm(h, TB_STAGE_CHAN, st);
-        rc = launch_channel_exact(h, x, cur_dtype, n_chunks, P.n_dec, in_stride, d_freq_off, P.rate, h->chan, P.filtered,
-                                  h->chan_fwd, h->filtered, P.n_dec, st);
+        if (h->cfg.mode == TB200_MODE_FAST && P.filtered)
+            rc = launch_channel_fast(h, x, (P.q > 1) ? cur_dtype : dtype, n_chunks, P.n_dec, in_stride, d_freq_off, P.rate,
+                                     25000.0, h->filtered, P.n_dec, st);
+        else
+            rc = launch_channel_exact(h, x, cur_dtype, n_chunks, P.n_dec, in_stride, d_freq_off, P.rate, h->chan, P.filtered,
+                                      h->chan_fwd, h->filtered, P.n_dec, st);
     }
     if (rc) return rc;
     StageTimer tm(h, TB_STAGE_SYMBOLS, st);
@@ -354,6 +361,8 @@ extern "C" int tb200_filter(tb200_handle h, const void *d_x, int dtype, int n, d
     if (!h || !d_x || !d_out_c128) return fail(TB200_E_ARG, "tb200_filter: bad argument");
     if (n <= 15) return fail(TB200_E_ARG, "The length of the input vector x must be greater than padlen, which is 15.");
     if ((size_t)2 * (n + 30) * sizeof(double) > h->chan_bytes) return fail(TB200_E_ARG, "tb200_filter: n exceeds the handle capacity");
+    if (h->cfg.mode == TB200_MODE_FAST)
+        return launch_channel_fast(h, d_x, dtype, 1, n, n, nullptr, fs, bandwidth, (double *)d_out_c128, n, (cudaStream_t)stream);
     int rc = get_chan(h, bandwidth, fs);
     if (rc) return rc;
     return launch_channel_exact(h, d_x, dtype, 1, n, n, nullptr, fs, h->chan, 1, h->chan_fwd, (double *)d_out_c128, n,

@@ -1,0 +1,337 @@
+// chan_fast.cu — time-parallel NCO + zero-phase Butterworth channel filter ("FAST" mode) for
+// SignalProcessor.frequency_shift / filter_signal as chained by process()
+// (/root/reference/tetraear/signal/processor.py:85-100, :51-83, :260-264).
+//
+// Same arithmetic model as the reference — float64, butter(4) run forward and backward over the
+// odd-extended chunk with steady-state initial conditions (scipy filtfilt) — evaluated in the
+// two-sided one-pole form (see dsp_fast.cu): with F_i[n] = sum_k p_i^k x[n-k] and
+// B_i[n] = sum_k p_i^k x[n+k] over the padded signal,
+//     y[n] = (c0 - 2 sum Re a_i) x[n] + 2 Re sum_i a_i (F_i[n] + B_i[n]) - right-edge transient.
+// Each lane owns R = 8 consecutive samples, runs both one-pole recurrences from a zero state,
+// warp Kogge-Stone scans give the in-pass carries and the neighbour warp's end state the
+// cross-pass carry (|p|max^256 < 1e-15).  All float64: agrees with scipy to ~1e-13.
+#include <complex>
+#include "common.h"
+#include "kernels.h"
+
+namespace tb200 {
+
+constexpr int CF_R = 8;
+constexpr int CF_P = 32 * CF_R;
+constexpr int CF_W = 8;            // warps per CTA: halo + 6 storing + halo
+constexpr int CF_EDGE_W = 320;     // edge-kernel warm-up (0.88^320 ~ 2e-18)
+constexpr int CF_FIX = 320;        // outputs corrected at the right end
+
+struct ChanFastParams {
+    double p[2][2];
+    double ppow[5][2][2];          // (p^R)^(2^s)
+    double c0p;                    // c0 - 2 sum Re(alpha)
+    double a[2][2];                // alpha_i
+    double aF[CF_R][2][2];         // alpha_i p^(r+1)
+    double aB[CF_R][2][2];         // alpha_i p^(R-r)
+    double inv1mp[2][2];
+    double ka[2][2], kM[2][2][2], kMc[2][2][2];
+    double pc[2][2];               // p^16 : exponent of the last output (M - n_last)
+};
+
+struct cdd { double x, y; };
+__device__ __forceinline__ cdd cmuld(cdd a, cdd b) { return cdd{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cdd cfmad(cdd a, cdd b, cdd c) { return cdd{fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y))}; }
+__device__ __forceinline__ cdd dshfl_up(cdd v, int d) { return cdd{__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d)}; }
+__device__ __forceinline__ cdd dshfl_down(cdd v, int d) { return cdd{__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d)}; }
+__device__ __forceinline__ cdd dshfl(cdd v, int l) { return cdd{__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l)}; }
+__device__ __forceinline__ cdd ldd(const double c[2]) { return cdd{c[0], c[1]}; }
+
+// sample i of the chunk after the optional NCO, complex128
+template <typename TI>
+__device__ __forceinline__ cdd nco_sample(const TI *__restrict__ x, long i, double W, double fs)
+{
+    double xr = (double)x[2 * i], xi = (double)x[2 * i + 1];
+    if (W == 0.0) return cdd{xr, xi};
+    double t = (double)i / fs, s, c;
+    sincos(__dmul_rn(W, t), &s, &c);
+    return cdd{__dsub_rn(__dmul_rn(xr, c), __dmul_rn(xi, s)), __dadd_rn(__dmul_rn(xr, s), __dmul_rn(xi, c))};
+}
+
+// padded signal at ext position t (edge 15), constants beyond both ends
+template <typename TI>
+__device__ __forceinline__ cdd chan_padded(const TI *__restrict__ x, long n, long t, double W, double fs)
+{
+    const long edge = 15;
+    if (t >= edge && t < edge + n) return nco_sample<TI>(x, t - edge, W, fs);
+    long ie, ii;
+    if (t < edge) { ie = 0; ii = t < 0 ? edge : edge - t; }
+    else { long u = t - edge - n; ie = n - 1; ii = u < edge ? n - 2 - u : n - 1 - edge; }
+    if (W == 0.0 && sizeof(TI) == 4) {      // complex64 reaches filtfilt un-promoted: odd_ext rounds in float32
+        float er = (float)x[2 * ie], ei = (float)x[2 * ie + 1], vr = (float)x[2 * ii], vi = (float)x[2 * ii + 1];
+        return cdd{(double)__fsub_rn(__fmul_rn(2.0f, er), vr), (double)__fsub_rn(__fmul_rn(2.0f, ei), vi)};
+    }
+    cdd e = nco_sample<TI>(x, ie, W, fs), v = nco_sample<TI>(x, ii, W, fs);
+    return cdd{__dsub_rn(__dmul_rn(2.0, e.x), v.x), __dsub_rn(__dmul_rn(2.0, e.y), v.y)};
+}
+
+template <typename TI>
+__global__ void __launch_bounds__(CF_W * 32)
+chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per_chunk,
+                 const double *__restrict__ freq_off, double fs, ChanFastParams K,
+                 double *__restrict__ filtered, long out_stride)
+{
+    __shared__ cdd carryF[CF_W][2][2];
+    __shared__ cdd carryB[CF_W][2][2];
+    const int chunk = blockIdx.x / tiles_per_chunk;
+    const int tile = blockIdx.x - chunk * tiles_per_chunk;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TI *xc = x + (long)chunk * in_stride * 2;
+    const double f = freq_off ? freq_off[chunk] : 0.0;
+    const double W = (f != 0.0) ? __dmul_rn(-6.283185307179586, f) : 0.0;
+    // output index (0-based, un-padded) of this lane's first sample; ext position = 15 + m
+    const long m0 = (long)tile * (CF_W - 2) * CF_P - CF_P + (long)w * CF_P + (long)lane * CF_R;
+    const bool do_F = w < CF_W - 1, do_B = w > 0, store = w > 0 && w < CF_W - 1;
+
+    cdd xs[CF_R];
+#pragma unroll
+    for (int r = 0; r < CF_R; ++r) xs[r] = chan_padded<TI>(xc, n, 15 + m0 + r, W, fs);
+    double yI[CF_R], yQ[CF_R];
+#pragma unroll
+    for (int r = 0; r < CF_R; ++r) { yI[r] = K.c0p * xs[r].x; yQ[r] = K.c0p * xs[r].y; }
+
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const cdd p = ldd(K.p[m]), a = ldd(K.a[m]);
+        if (do_F) {
+            cdd sI = cdd{0.0, 0.0}, sQ = cdd{0.0, 0.0};
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) {
+                sI = cmuld(p, sI); sI.x += xs[r].x;
+                sQ = cmuld(p, sQ); sQ.x += xs[r].y;
+                yI[r] += 2.0 * (a.x * sI.x - a.y * sI.y);
+                yQ[r] += 2.0 * (a.x * sQ.x - a.y * sQ.y);
+            }
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                cdd oI = dshfl_up(sI, 1 << s), oQ = dshfl_up(sQ, 1 << s);
+                if (lane >= (1 << s)) { cdd g = ldd(K.ppow[s][m]); sI = cfmad(g, oI, sI); sQ = cfmad(g, oQ, sQ); }
+            }
+            cdd cI = dshfl_up(sI, 1), cQ = dshfl_up(sQ, 1);
+            if (lane == 0) cI = cQ = cdd{0.0, 0.0};
+            if (lane == 31) { carryF[w][0][m] = sI; carryF[w][1][m] = sQ; }
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) {
+                const cdd af = ldd(K.aF[r][m]);
+                yI[r] += 2.0 * (af.x * cI.x - af.y * cI.y);
+                yQ[r] += 2.0 * (af.x * cQ.x - af.y * cQ.y);
+            }
+        }
+        if (do_B) {
+            cdd sI = cdd{0.0, 0.0}, sQ = cdd{0.0, 0.0};
+#pragma unroll
+            for (int r = CF_R - 1; r >= 0; --r) {
+                sI = cmuld(p, sI); sI.x += xs[r].x;
+                sQ = cmuld(p, sQ); sQ.x += xs[r].y;
+                yI[r] += 2.0 * (a.x * sI.x - a.y * sI.y);
+                yQ[r] += 2.0 * (a.x * sQ.x - a.y * sQ.y);
+            }
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                cdd oI = dshfl_down(sI, 1 << s), oQ = dshfl_down(sQ, 1 << s);
+                if (lane + (1 << s) < 32) { cdd g = ldd(K.ppow[s][m]); sI = cfmad(g, oI, sI); sQ = cfmad(g, oQ, sQ); }
+            }
+            cdd cI = dshfl_down(sI, 1), cQ = dshfl_down(sQ, 1);
+            if (lane == 31) cI = cQ = cdd{0.0, 0.0};
+            if (lane == 0) { carryB[w][0][m] = sI; carryB[w][1][m] = sQ; }
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) {
+                const cdd ab = ldd(K.aB[r][m]);
+                yI[r] += 2.0 * (ab.x * cI.x - ab.y * cI.y);
+                yQ[r] += 2.0 * (ab.x * cQ.x - ab.y * cQ.y);
+            }
+        }
+    }
+    __syncthreads();
+    if (!store) return;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        cdd LF = cdd{1.0, 0.0}, LB = cdd{1.0, 0.0};
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            cdd g = ldd(K.ppow[s][m]);
+            if (lane & (1 << s)) LF = cmuld(LF, g);
+            if ((31 - lane) & (1 << s)) LB = cmuld(LB, g);
+        }
+        cdd gFI = cmuld(LF, carryF[w - 1][0][m]), gFQ = cmuld(LF, carryF[w - 1][1][m]);
+        cdd gBI = cmuld(LB, carryB[w + 1][0][m]), gBQ = cmuld(LB, carryB[w + 1][1][m]);
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) {
+            const cdd af = ldd(K.aF[r][m]), ab = ldd(K.aB[r][m]);
+            yI[r] += 2.0 * (af.x * gFI.x - af.y * gFI.y + ab.x * gBI.x - ab.y * gBI.y);
+            yQ[r] += 2.0 * (af.x * gFQ.x - af.y * gFQ.y + ab.x * gBQ.x - ab.y * gBQ.y);
+        }
+    }
+    double2 *out = reinterpret_cast<double2 *>(filtered) + (long)chunk * out_stride;
+#pragma unroll
+    for (int r = 0; r < CF_R; ++r) {
+        long m = m0 + r;
+        if (m >= 0 && m < n) out[m] = make_double2(yI[r], yQ[r]);
+    }
+}
+
+// right-end transient (see dsp_fast.cu): one warp per chunk
+template <typename TI>
+__global__ void chan_fast_edge_kernel(const TI *__restrict__ x, long n, long in_stride, int n_chunks,
+                                      const double *__restrict__ freq_off, double fs, ChanFastParams K,
+                                      double *__restrict__ filtered, long out_stride)
+{
+    const int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (chunk >= n_chunks) return;
+    const TI *xc = x + (long)chunk * in_stride * 2;
+    const double f = freq_off ? freq_off[chunk] : 0.0;
+    const double W = (f != 0.0) ? __dmul_rn(-6.283185307179586, f) : 0.0;
+    const long M = n + 30;
+    const int m = lane & 1, comp = (lane >> 1) & 1;
+    const cdd p = ldd(K.p[m]);
+    long tstart = M - CF_EDGE_W;
+    cdd s = cdd{0.0, 0.0};
+    if (tstart <= 0) {
+        tstart = 0;
+        cdd e = chan_padded<TI>(xc, n, -1, W, fs);
+        cdd i1 = ldd(K.inv1mp[m]);
+        double v = comp ? e.y : e.x;
+        s = cdd{i1.x * v, i1.y * v};
+    }
+    if (lane < 4) {
+        for (long t = tstart; t < M; ++t) {
+            cdd e = chan_padded<TI>(xc, n, t, W, fs);
+            s = cmuld(p, s);
+            s.x += comp ? e.y : e.x;
+        }
+    }
+    cdd last = chan_padded<TI>(xc, n, M - 1, W, fs);
+    double xlast = comp ? last.y : last.x;
+    cdd kap = cdd{K.ka[m][0] * xlast, K.ka[m][1] * xlast};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        cdd Fj = dshfl(s, comp * 2 + j);
+        kap = cfmad(ldd(K.kM[m][j]), Fj, kap);
+        kap = cfmad(ldd(K.kMc[m][j]), cdd{Fj.x, -Fj.y}, kap);
+    }
+    cdd kI[2], kQ[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { kI[j] = dshfl(kap, j); kQ[j] = dshfl(kap, 2 + j); }
+    cdd lp[2], l32[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        cdd a = cdd{1.0, 0.0}, b = ldd(K.p[j]);
+        for (int bit = 0; bit < 5; ++bit) { if (lane & (1 << bit)) a = cmuld(a, b); b = cmuld(b, b); }
+        lp[j] = cmuld(a, ldd(K.pc[j]));
+        l32[j] = b;
+    }
+    double2 *out = reinterpret_cast<double2 *>(filtered) + (long)chunk * out_stride;
+    for (int mm = lane; mm < CF_FIX; mm += 32) {
+        long k = n - 1 - mm;
+        double cI = 0.0, cQ = 0.0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            cI += kI[j].x * lp[j].x - kI[j].y * lp[j].y;
+            cQ += kQ[j].x * lp[j].x - kQ[j].y * lp[j].y;
+            lp[j] = cmuld(lp[j], l32[j]);
+        }
+        if (k >= 0) { double2 v = out[k]; out[k] = make_double2(v.x - 2.0 * cI, v.y - 2.0 * cQ); }
+    }
+}
+
+// ---- host: modal constants from the Butterworth poles ---------------------------------------
+typedef std::complex<double> cd;
+static void putd(double dst[2], cd v) { dst[0] = v.real(); dst[1] = v.imag(); }
+
+int channel_filter_poles(double bandwidth, double fs, std::complex<double> poles[4], double *gain);
+
+static int make_chan_params(double bandwidth, double fs, ChanFastParams &K)
+{
+    cd pz[4];
+    double k;
+    int rc = channel_filter_poles(bandwidth, fs, pz, &k);
+    if (rc) return rc;
+    // order: the two poles with positive imaginary part first, then their conjugates
+    cd p4[4];
+    int np = 0;
+    for (int i = 0; i < 4; ++i) if (pz[i].imag() > 0) p4[np++] = pz[i];
+    if (np != 2) return fail(TB200_E_ARG, "fast channel filter: expected two complex pole pairs");
+    p4[2] = std::conj(p4[0]); p4[3] = std::conj(p4[1]);
+    cd r4[4];
+    cd prodp(1.0, 0.0);
+    for (int i = 0; i < 4; ++i) prodp *= p4[i];
+    const double dd = k / prodp.real();
+    for (int i = 0; i < 4; ++i) {
+        cd num = k * std::pow(1.0 + 1.0 / p4[i], 4), den(1.0, 0.0);
+        for (int j = 0; j < 4; ++j) if (j != i) den *= (1.0 - p4[j] / p4[i]);
+        r4[i] = num / den;
+    }
+    cd alpha[2];
+    cd sumr(0.0, 0.0);
+    for (int i = 0; i < 4; ++i) sumr += r4[i];
+    double c0 = (dd * dd + dd * sumr).real();
+    double sum_re_alpha = 0.0;
+    for (int j = 0; j < 2; ++j) {
+        cd acc(dd, 0.0);
+        for (int i = 0; i < 4; ++i) acc += r4[i] / (1.0 - p4[i] * p4[j]);
+        alpha[j] = r4[j] * acc;
+        sum_re_alpha += alpha[j].real();
+    }
+    memset(&K, 0, sizeof(K));
+    K.c0p = c0 - 2.0 * sum_re_alpha;
+    for (int j = 0; j < 2; ++j) {
+        putd(K.p[j], p4[j]);
+        cd pr = std::pow(p4[j], CF_R);
+        for (int s = 0; s < 5; ++s) { putd(K.ppow[s][j], pr); pr *= pr; }
+        putd(K.a[j], alpha[j]);
+        for (int r = 0; r < CF_R; ++r) {
+            putd(K.aF[r][j], alpha[j] * std::pow(p4[j], r + 1));
+            putd(K.aB[r][j], alpha[j] * std::pow(p4[j], CF_R - r));
+        }
+        putd(K.inv1mp[j], 1.0 / (1.0 - p4[j]));
+        putd(K.pc[j], std::pow(p4[j], 16));
+    }
+    cd H1(dd, 0.0);
+    for (int j = 0; j < 4; ++j) H1 += r4[j] / (1.0 - p4[j]);
+    for (int i = 0; i < 2; ++i) {
+        cd ka = (H1 - dd) / (1.0 - p4[i]);
+        cd kM[4];
+        for (int j = 0; j < 4; ++j) {
+            ka -= r4[j] * p4[j] / ((1.0 - p4[i] * p4[j]) * (1.0 - p4[j]));
+            kM[j] = -r4[j] / (1.0 - p4[i]) + r4[j] * p4[j] / (1.0 - p4[i] * p4[j]);
+        }
+        putd(K.ka[i], r4[i] * ka);
+        for (int j = 0; j < 2; ++j) { putd(K.kM[i][j], r4[i] * kM[j]); putd(K.kMc[i][j], r4[i] * kM[j + 2]); }
+    }
+    return TB200_OK;
+}
+
+template <typename TI>
+static int launch_t(tb200_handle h, const void *x, int n_chunks, long n, long in_stride, const double *freq_off,
+                    double fs, const ChanFastParams &K, double *filtered, long out_stride, cudaStream_t st)
+{
+    const int per_tile = (CF_W - 2) * CF_P;
+    const int tiles = (int)((n + per_tile - 1) / per_tile);
+    chan_fast_kernel<TI><<<n_chunks * tiles, CF_W * 32, 0, st>>>((const TI *)x, n, in_stride, tiles, freq_off, fs, K,
+                                                               filtered, out_stride);
+    TB_LAUNCH_CHECK(h);
+    int threads = 128, blocks = (n_chunks * 32 + threads - 1) / threads;
+    chan_fast_edge_kernel<TI><<<blocks, threads, 0, st>>>((const TI *)x, n, in_stride, n_chunks, freq_off, fs, K,
+                                                         filtered, out_stride);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+int launch_channel_fast(tb200_handle h, const void *x, int dtype, int n_chunks, long n, long in_stride,
+                        const double *freq_off, double fs, double bandwidth, double *filtered, long out_stride,
+                        cudaStream_t st)
+{
+    ChanFastParams K;
+    int rc = make_chan_params(bandwidth, fs, K);
+    if (rc) return rc;
+    if (dtype == TB200_DTYPE_C64) return launch_t<float>(h, x, n_chunks, n, in_stride, freq_off, fs, K, filtered, out_stride, st);
+    return launch_t<double>(h, x, n_chunks, n, in_stride, freq_off, fs, K, filtered, out_stride, st);
+}
+
+}  // namespace tb200

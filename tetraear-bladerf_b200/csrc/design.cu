@@ -131,9 +131,11 @@ extern "C" int tb200_design_decimator(int q, double sos64[24], double zi64[8], f
     return TB200_OK;
 }
 
-extern "C" int tb200_design_channel_filter(double bandwidth, double fs, double b[5], double a[5], double zi[4])
+namespace tb200 {
+// digital poles and gain of butter(4, clip((bw/2)/(fs/2))) (zeros: four at -1)
+int channel_filter_poles(double bandwidth, double fs, std::complex<double> poles[4], double *gain)
 {
-    if (!(fs > 0)) return tb200::fail(TB200_E_ARG, "tb200_design_channel_filter: fs must be > 0");
+    if (!(fs > 0)) return fail(TB200_E_ARG, "channel filter: fs must be > 0");
     double cutoff = (bandwidth / 2) / (fs / 2);
     cutoff = std::min(0.99, std::max(0.01, cutoff));
     const int N = 4;
@@ -146,6 +148,23 @@ extern "C" int tb200_design_channel_filter(double bandwidth, double fs, double b
     }
     double k = 1.0;
     analog_to_digital(p, k, cutoff);
+    for (int i = 0; i < N; ++i) poles[i] = p[i];
+    *gain = k;
+    return TB200_OK;
+}
+}  // namespace tb200
+
+extern "C" int tb200_design_channel_filter(double bandwidth, double fs, double b[5], double a[5], double zi[4])
+{
+    const int N = 4;
+    std::vector<cd> p(N);
+    double k = 1.0;
+    {
+        cd pz[4];
+        int rc = tb200::channel_filter_poles(bandwidth, fs, pz, &k);
+        if (rc) return rc;
+        for (int i = 0; i < N; ++i) p[i] = pz[i];
+    }
     // a = real(np.poly(p)): sequential convolution with [1, -root]
     cd acc[N + 1];
     acc[0] = cd(1.0, 0.0);
