@@ -24,7 +24,8 @@ int launch_decimate_fast(tb200_handle h, const void *x, int n_chunks, long n, lo
 int fast_decimator_supported(int q);
 int launch_channel_fast(tb200_handle h, const void *x, int dtype, int n_chunks, long n, long in_stride,
                         const double *freq_off, double fs, double bandwidth, double *filtered, long out_stride,
-                        cudaStream_t st);
+                        double *phase_partial, double *phase_tail, int sps, int step, cudaStream_t st);
+int chan_fast_tiles(long n);
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -57,8 +58,11 @@ static size_t carve(tb200_handle h, char *base)
         h->filt_bytes = C * ND * 16;
         h->filtered = c.take<double>(h->filt_bytes);
         h->n_sym = c.take<int32_t>(C * sizeof(int32_t));
+        h->phase_bytes = C * (size_t)(ND / 1536 + 3) * TB200_MAX_PHASES * sizeof(double);
+        h->phase_pw = c.take<double>(h->phase_bytes);
     } else {
         h->fwd = h->dec_out = nullptr; h->chan_fwd = h->filtered = nullptr; h->n_sym = nullptr;
+        h->phase_pw = nullptr; h->phase_bytes = 0;
         h->fwd_bytes = h->dec_bytes = h->chan_bytes = h->filt_bytes = 0;
     }
     // decode: per stream a bit row of bits_stride bytes
@@ -287,11 +291,21 @@ extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, 
         return fail(TB200_E_ARG, "tb200_process_batch: batch exceeds the channel-filter workspace");
     rc = get_chan(h, 25000.0, P.rate);
     if (rc) return rc;
+    double *ph_partial = nullptr, *ph_tail = nullptr;
+    int ph_tiles = 0;
     {
         StageTimer tm(h, TB_STAGE_CHAN, st);
-        if (h->cfg.mode == TB200_MODE_FAST && P.filtered)
+        if (h->cfg.mode == TB200_MODE_FAST && P.filtered) {
+            int tiles = chan_fast_tiles(P.n_dec);
+            if (P.sps > 1 && P.sps <= TB200_MAX_PHASES &&
+                (size_t)n_chunks * (tiles + 1) * TB200_MAX_PHASES * sizeof(double) <= h->phase_bytes) {
+                ph_partial = h->phase_pw;
+                ph_tail = h->phase_pw + (size_t)n_chunks * tiles * TB200_MAX_PHASES;
+                ph_tiles = tiles;
+            }
             rc = launch_channel_fast(h, x, (P.q > 1) ? cur_dtype : dtype, n_chunks, P.n_dec, in_stride, d_freq_off, P.rate,
-                                     25000.0, h->filtered, P.n_dec, st);
+                                     25000.0, h->filtered, P.n_dec, ph_partial, ph_tail, P.sps, P.phase_step, st);
+        }
         else
             rc = launch_channel_exact(h, x, cur_dtype, n_chunks, P.n_dec, in_stride, d_freq_off, P.rate, h->chan, P.filtered,
                                       h->chan_fwd, h->filtered, P.n_dec, st);
@@ -299,7 +313,7 @@ extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, 
     if (rc) return rc;
     StageTimer tm(h, TB_STAGE_SYMBOLS, st);
     return launch_symbols(h, h->filtered, n_chunks, P.n_dec, P.n_dec, P.sps, P.phase_step, (double *)d_symbols, d_dibits,
-                          out_stride, d_n_dibits, nullptr, d_phase, st);
+                          out_stride, d_n_dibits, nullptr, d_phase, st, ph_partial, ph_tail, ph_tiles);
 }
 
 extern "C" int tb200_process_batch_host(tb200_handle h, const void *h_iq, int dtype, int n_chunks, int chunk_len,
@@ -362,7 +376,8 @@ extern "C" int tb200_filter(tb200_handle h, const void *d_x, int dtype, int n, d
     if (n <= 15) return fail(TB200_E_ARG, "The length of the input vector x must be greater than padlen, which is 15.");
     if ((size_t)2 * (n + 30) * sizeof(double) > h->chan_bytes) return fail(TB200_E_ARG, "tb200_filter: n exceeds the handle capacity");
     if (h->cfg.mode == TB200_MODE_FAST)
-        return launch_channel_fast(h, d_x, dtype, 1, n, n, nullptr, fs, bandwidth, (double *)d_out_c128, n, (cudaStream_t)stream);
+        return launch_channel_fast(h, d_x, dtype, 1, n, n, nullptr, fs, bandwidth, (double *)d_out_c128, n, nullptr, nullptr,
+                                   0, 1, (cudaStream_t)stream);
     int rc = get_chan(h, bandwidth, fs);
     if (rc) return rc;
     return launch_channel_exact(h, d_x, dtype, 1, n, n, nullptr, fs, h->chan, 1, h->chan_fwd, (double *)d_out_c128, n,

@@ -19,7 +19,7 @@ namespace tb200 {
 constexpr int CF_R = 8;
 constexpr int CF_P = 32 * CF_R;
 constexpr int CF_W = 8;            // warps per CTA: halo + 6 storing + halo
-constexpr int CF_EDGE_W = 320;     // edge-kernel warm-up (0.88^320 ~ 2e-18)
+constexpr int CF_EDGE_S = 10;      // edge kernel: samples per lane (32 x 10 = 320; 0.88^320 ~ 2e-18)
 constexpr int CF_FIX = 320;        // outputs corrected at the right end
 
 struct ChanFastParams {
@@ -32,6 +32,7 @@ struct ChanFastParams {
     double inv1mp[2][2];
     double ka[2][2], kM[2][2][2], kMc[2][2][2];
     double pc[2][2];               // p^16 : exponent of the last output (M - n_last)
+    double pS[5][2][2];            // (p^S)^(2^s)
 };
 
 struct cdd { double x, y; };
@@ -74,10 +75,11 @@ template <typename TI>
 __global__ void __launch_bounds__(CF_W * 32)
 chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per_chunk,
                  const double *__restrict__ freq_off, double fs, ChanFastParams K,
-                 double *__restrict__ filtered, long out_stride)
+                 double *__restrict__ filtered, long out_stride, double *__restrict__ phase_partial, int sps, int step)
 {
     __shared__ cdd carryF[CF_W][2][2];
     __shared__ cdd carryB[CF_W][2][2];
+    __shared__ double phacc[CF_W][TB200_MAX_PHASES];
     const int chunk = blockIdx.x / tiles_per_chunk;
     const int tile = blockIdx.x - chunk * tiles_per_chunk;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -148,7 +150,7 @@ chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per
         }
     }
     __syncthreads();
-    if (!store) return;
+    if (store) {
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
         cdd LF = cdd{1.0, 0.0}, LB = cdd{1.0, 0.0};
@@ -173,13 +175,51 @@ chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per
         long m = m0 + r;
         if (m >= 0 && m < n) out[m] = make_double2(yI[r], yQ[r]);
     }
+    }
+    // ---- per-phase power partial sums for the timing pick (extract_symbols, processor.py:196-210):
+    // deterministic order — lanes by shuffle tree, warps then tiles in index order.  The outputs of
+    // the last CF_FIX samples of a chunk still lack the right-edge term; the edge kernel adds the
+    // difference of their powers.
+    if (phase_partial) {
+        if (store) {
+            // phase class of each owned sample, -1 when it does not count (32-bit arithmetic, once per sample)
+            int phr[CF_R];
+            double pw[CF_R];
+            const int ni = (int)n;
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) {
+                long m = m0 + r;
+                phr[r] = -1;
+                pw[r] = yI[r] * yI[r] + yQ[r] * yQ[r];
+                if (m >= 0 && m < n - CF_FIX) {
+                    int mi = (int)m, k = mi / sps, ph = mi - k * sps;
+                    if ((ph % step) == 0 && k < (ni - ph) / sps) phr[r] = ph;
+                }
+            }
+            for (int ph = 0; ph < sps; ph += step) {
+                double v = 0.0;
+#pragma unroll
+                for (int r = 0; r < CF_R; ++r) v += (phr[r] == ph) ? pw[r] : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) phacc[w][ph] = v;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < sps && (threadIdx.x % step) == 0) {
+            double t = 0.0;
+            for (int ww = 1; ww < CF_W - 1; ++ww) t += phacc[ww][threadIdx.x];
+            phase_partial[((long)chunk * tiles_per_chunk + tile) * TB200_MAX_PHASES + threadIdx.x] = t;
+        }
+    }
 }
 
 // right-end transient (see dsp_fast.cu): one warp per chunk
 template <typename TI>
 __global__ void chan_fast_edge_kernel(const TI *__restrict__ x, long n, long in_stride, int n_chunks,
                                       const double *__restrict__ freq_off, double fs, ChanFastParams K,
-                                      double *__restrict__ filtered, long out_stride)
+                                      double *__restrict__ filtered, long out_stride,
+                                      double *__restrict__ phase_tail, int sps, int step)
 {
     const int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -189,23 +229,30 @@ __global__ void chan_fast_edge_kernel(const TI *__restrict__ x, long n, long in_
     const double W = (f != 0.0) ? __dmul_rn(-6.283185307179586, f) : 0.0;
     const long M = n + 30;
     const int m = lane & 1, comp = (lane >> 1) & 1;
-    const cdd p = ldd(K.p[m]);
-    long tstart = M - CF_EDGE_W;
-    cdd s = cdd{0.0, 0.0};
-    if (tstart <= 0) {
-        tstart = 0;
-        cdd e = chan_padded<TI>(xc, n, -1, W, fs);
-        cdd i1 = ldd(K.inv1mp[m]);
-        double v = comp ? e.y : e.x;
-        s = cdd{i1.x * v, i1.y * v};
-    }
-    if (lane < 4) {
-        for (long t = tstart; t < M; ++t) {
-            cdd e = chan_padded<TI>(xc, n, t, W, fs);
-            s = cmuld(p, s);
-            s.x += comp ? e.y : e.x;
+    cdd sI[2], sQ[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) sI[j] = sQ[j] = cdd{0.0, 0.0};
+    const long tbeg = M - 32L * CF_EDGE_S + (long)lane * CF_EDGE_S;
+    for (int i = 0; i < CF_EDGE_S; ++i) {
+        cdd e = chan_padded<TI>(xc, n, tbeg + i, W, fs);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            cdd pj = ldd(K.p[j]);
+            sI[j] = cmuld(pj, sI[j]); sI[j].x += e.x;
+            sQ[j] = cmuld(pj, sQ[j]); sQ[j].x += e.y;
         }
     }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int st = 0; st < 5; ++st) {
+            cdd oI = dshfl_up(sI[j], 1 << st), oQ = dshfl_up(sQ[j], 1 << st);
+            if (lane >= (1 << st)) { cdd g = ldd(K.pS[st][j]); sI[j] = cfmad(g, oI, sI[j]); sQ[j] = cfmad(g, oQ, sQ[j]); }
+        }
+        sI[j] = dshfl(sI[j], 31);
+        sQ[j] = dshfl(sQ[j], 31);
+    }
+    cdd s = comp ? (m ? sQ[1] : sQ[0]) : (m ? sI[1] : sI[0]);
     cdd last = chan_padded<TI>(xc, n, M - 1, W, fs);
     double xlast = comp ? last.y : last.x;
     cdd kap = cdd{K.ka[m][0] * xlast, K.ka[m][1] * xlast};
@@ -237,6 +284,21 @@ __global__ void chan_fast_edge_kernel(const TI *__restrict__ x, long n, long in_
             lp[j] = cmuld(lp[j], l32[j]);
         }
         if (k >= 0) { double2 v = out[k]; out[k] = make_double2(v.x - 2.0 * cI, v.y - 2.0 * cQ); }
+    }
+    if (phase_tail) {
+        // power of the final (corrected) last CF_FIX samples, per phase, in a fixed order
+        __syncwarp();
+        for (int ph = 0; ph < sps; ph += step) {
+            long cnt = (n - ph >= 0) ? (n - ph) / sps : 0;
+            double v = 0.0;
+            for (int mm = lane; mm < CF_FIX; mm += 32) {
+                long k = n - 1 - mm;
+                if (k >= 0 && (k % sps) == ph && (k - ph) < cnt * sps) { double2 y = out[k]; v += y.x * y.x + y.y * y.y; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) phase_tail[(long)chunk * TB200_MAX_PHASES + ph] = v;
+        }
     }
 }
 
@@ -291,6 +353,8 @@ static int make_chan_params(double bandwidth, double fs, ChanFastParams &K)
         }
         putd(K.inv1mp[j], 1.0 / (1.0 - p4[j]));
         putd(K.pc[j], std::pow(p4[j], 16));
+        cd ps = std::pow(p4[j], CF_EDGE_S);
+        for (int st = 0; st < 5; ++st) { putd(K.pS[st][j], ps); ps *= ps; }
     }
     cd H1(dd, 0.0);
     for (int j = 0; j < 4; ++j) H1 += r4[j] / (1.0 - p4[j]);
@@ -307,31 +371,39 @@ static int make_chan_params(double bandwidth, double fs, ChanFastParams &K)
     return TB200_OK;
 }
 
-template <typename TI>
-static int launch_t(tb200_handle h, const void *x, int n_chunks, long n, long in_stride, const double *freq_off,
-                    double fs, const ChanFastParams &K, double *filtered, long out_stride, cudaStream_t st)
+int chan_fast_tiles(long n)
 {
     const int per_tile = (CF_W - 2) * CF_P;
-    const int tiles = (int)((n + per_tile - 1) / per_tile);
+    return (int)((n + per_tile - 1) / per_tile);
+}
+
+template <typename TI>
+static int launch_t(tb200_handle h, const void *x, int n_chunks, long n, long in_stride, const double *freq_off,
+                    double fs, const ChanFastParams &K, double *filtered, long out_stride, double *phase_partial,
+                    double *phase_tail, int sps, int step, cudaStream_t st)
+{
+    const int tiles = chan_fast_tiles(n);
     chan_fast_kernel<TI><<<n_chunks * tiles, CF_W * 32, 0, st>>>((const TI *)x, n, in_stride, tiles, freq_off, fs, K,
-                                                               filtered, out_stride);
+                                                               filtered, out_stride, phase_partial, sps, step);
     TB_LAUNCH_CHECK(h);
     int threads = 128, blocks = (n_chunks * 32 + threads - 1) / threads;
     chan_fast_edge_kernel<TI><<<blocks, threads, 0, st>>>((const TI *)x, n, in_stride, n_chunks, freq_off, fs, K,
-                                                         filtered, out_stride);
+                                                         filtered, out_stride, phase_tail, sps, step);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
 }
 
 int launch_channel_fast(tb200_handle h, const void *x, int dtype, int n_chunks, long n, long in_stride,
                         const double *freq_off, double fs, double bandwidth, double *filtered, long out_stride,
-                        cudaStream_t st)
+                        double *phase_partial, double *phase_tail, int sps, int step, cudaStream_t st)
 {
     ChanFastParams K;
     int rc = make_chan_params(bandwidth, fs, K);
     if (rc) return rc;
-    if (dtype == TB200_DTYPE_C64) return launch_t<float>(h, x, n_chunks, n, in_stride, freq_off, fs, K, filtered, out_stride, st);
-    return launch_t<double>(h, x, n_chunks, n, in_stride, freq_off, fs, K, filtered, out_stride, st);
+    if (sps > TB200_MAX_PHASES || sps <= 1) phase_partial = phase_tail = nullptr;
+    if (dtype == TB200_DTYPE_C64)
+        return launch_t<float>(h, x, n_chunks, n, in_stride, freq_off, fs, K, filtered, out_stride, phase_partial, phase_tail, sps, step, st);
+    return launch_t<double>(h, x, n_chunks, n, in_stride, freq_off, fs, K, filtered, out_stride, phase_partial, phase_tail, sps, step, st);
 }
 
 }  // namespace tb200

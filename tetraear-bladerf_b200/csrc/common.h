@@ -67,6 +67,7 @@ struct tb200_handle_s {
     double *chan_fwd; size_t chan_bytes;      // channel-filter forward scratch [time][lane]
     double *filtered; size_t filt_bytes;      // complex128 [chunk][n_dec]
     int32_t *n_sym;                           // [chunks] symbols per chunk
+    double *phase_pw; size_t phase_bytes;     // per-(chunk, tile) phase power partial sums (FAST mode)
     // decode
     int max_streams; long bits_stride; int max_frames;
     uint8_t *bits, *mapped, *m1, *m2;

@@ -32,7 +32,7 @@ constexpr int FD_R = 3;              // outputs per lane
 constexpr int FD_P = 32 * FD_R;      // outputs per warp pass
 constexpr int FD_W = 8;              // warps per CTA: 1 left-halo + 6 storing + 1 right-halo
 constexpr int FD_QMAX = 16;
-constexpr int FD_EDGE_W = 1316;      // warm-up length of the edge kernel (0.982^1316 = 4e-11)
+constexpr int FD_EDGE_S = 42;        // edge kernel: samples per lane (32 x 42 = 1344; 0.982^1344 = 3e-11)
 
 struct FastDecimParams {
     float tap[FD_QMAX][4][2];        // p_i^j
@@ -49,6 +49,7 @@ struct FastDecimParams {
     float kM[4][4][2];
     float kMc[4][4][2];
     float pc[4][2];                  // p_i^(M - n_last)
+    float pS[5][4][2];               // (p_i^S)^(2^s): lane-combine multipliers of the edge kernel
 };
 
 struct cf { float x, y; };
@@ -238,24 +239,38 @@ __global__ void decim_fast_edge_kernel(const float2 *__restrict__ x, long n, lon
     const float2 *xc = x + (long)chunk * chunk_stride;
     const long M = n + 54;
     const int m = lane & 3, comp = (lane >> 2) & 1;
-    const cf p = ld2(K.p[m]);
-    long tstart = M - FD_EDGE_W;
-    cf s = cf{0.f, 0.f};
-    if (tstart <= 0) {                       // short chunk: exact steady state of the left constant
-        tstart = 0;
-        float2 e = padded_sample(xc, n, -1);
-        cf i1 = ld2(K.inv1mp[m]);
-        float v = comp ? e.y : e.x;
-        s = cf{i1.x * v, i1.y * v};
-    }
-    if (lane < 8) {
-        for (long t = tstart; t < M; ++t) {
-            float2 e = padded_sample(xc, n, t);
-            float v = comp ? e.y : e.x;
-            cf ns = cmulf(p, s);
-            s = cf{ns.x + v, ns.y};
+    // F_i[M-1] = sum_k p_i^k ext[M-1-k] over the last 32*S samples: lane l runs the 8 (mode, I/Q)
+    // one-pole recurrences over its own S samples from zero, an inclusive shuffle scan with
+    // multipliers (p^S)^(2^s) assembles the total on lane 31.
+    cf sI[4], sQ[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sI[j] = sQ[j] = cf{0.f, 0.f};
+    const long tbeg = M - 32L * FD_EDGE_S + (long)lane * FD_EDGE_S;
+#pragma unroll 2
+    for (int i = 0; i < FD_EDGE_S; ++i) {
+        float2 e = padded_sample(xc, n, tbeg + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cf pj = ld2(K.p[j]);
+            cf a = cmulf(pj, sI[j]), b = cmulf(pj, sQ[j]);
+            sI[j] = cf{a.x + e.x, a.y};
+            sQ[j] = cf{b.x + e.y, b.y};
         }
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int st = 0; st < 5; ++st) {
+            cf oI = cshfl_up(sI[j], 1 << st), oQ = cshfl_up(sQ[j], 1 << st);
+            if (lane >= (1 << st)) { cf g = ld2(K.pS[st][j]); sI[j] = cfma(g, oI, sI[j]); sQ[j] = cfma(g, oQ, sQ[j]); }
+        }
+        sI[j] = cshfl(sI[j], 31);
+        sQ[j] = cshfl(sQ[j], 31);
+    }
+    // lane (m, comp) of the first eight picks its own F
+    cf s = comp ? sQ[0] : sI[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) if (m == j) s = comp ? sQ[j] : sI[j];
     // kappa for (mode mi, comp ci) on lanes 0..7 : gather the four F_j of the same comp
     float2 last = padded_sample(xc, n, M - 1);
     float xlast = comp ? last.y : last.x;
@@ -342,6 +357,8 @@ static int make_fast_params(const DecimDesign &d, int q, long n, long n_dec, Fas
         }
         put(K.p[j], p8[j]);
         put(K.inv1mp[j], 1.0 / (1.0 - p8[j]));
+        cd ps = std::pow(p8[j], FD_EDGE_S);
+        for (int st = 0; st < 5; ++st) { put(K.pS[st][j], ps); ps *= ps; }
     }
     // kappa_i = r_i E_i,  E_i = (G - wlast)/(1-p_i) + sum_j r_j delta_j p_j / (1 - p_i p_j),
     // G = xc H(1), wlast = d xc + sum_j r_j F_j, delta_j = F_j - xc/(1-p_j)   (j over all 8 poles)

@@ -11,7 +11,8 @@ int launch_channel_exact(tb200_handle h, const void *x, int dtype, int n_chunks,
                          double *scratch, double *filtered, long out_stride, cudaStream_t st);
 int launch_symbols(tb200_handle h, const double *filtered, int n_chunks, long n, long in_stride, int sps,
                    int phase_step, double *symbols, uint8_t *dibits, long out_stride, int32_t *n_dibits,
-                   int32_t *n_symbols, int32_t *phase, cudaStream_t st);
+                   int32_t *n_symbols, int32_t *phase, cudaStream_t st, const double *phase_partial = nullptr,
+                   const double *phase_tail = nullptr, int n_tiles = 0);
 int launch_slicer(tb200_handle h, const double *symbols, long n, uint8_t *dibits, cudaStream_t st);
 
 int launch_symbols_to_bits(tb200_handle h, const uint8_t *sym, int n_streams, long stride, const int32_t *n_sym,

@@ -57,7 +57,8 @@ __device__ __forceinline__ uint8_t slice_dqpsk(double ar, double ai, double pr, 
 __global__ void symbols_kernel(const double *__restrict__ filtered, long n, long in_stride, int sps, int step,
                                double *__restrict__ symbols, uint8_t *__restrict__ dibits, long out_stride,
                                int32_t *__restrict__ n_dibits, int32_t *__restrict__ n_symbols,
-                               int32_t *__restrict__ phase_out)
+                               int32_t *__restrict__ phase_out, const double *__restrict__ phase_partial,
+                               const double *__restrict__ phase_tail, int n_tiles)
 {
     __shared__ double sh[32];
     int chunk = blockIdx.x;
@@ -70,12 +71,20 @@ __global__ void symbols_kernel(const double *__restrict__ filtered, long n, long
         for (int p = 0; p < sps; p += step) {
             long cnt = (n - p >= 0) ? (n - p) / sps : -1;
             if (cnt <= 0) continue;
-            double acc = 0.0;
-            for (long k = threadIdx.x; k < cnt; k += blockDim.x) {
-                double a = hypot(x[2 * (p + k * sps)], x[2 * (p + k * sps) + 1]);
-                acc += a * a;
+            double tot;
+            if (phase_partial) {
+                // sums produced by the channel-filter kernel: tiles in index order, then the tail
+                tot = 0.0;
+                for (int t = 0; t < n_tiles; ++t) tot += phase_partial[((long)chunk * n_tiles + t) * TB200_MAX_PHASES + p];
+                tot += phase_tail[(long)chunk * TB200_MAX_PHASES + p];
+            } else {
+                double acc = 0.0;
+                for (long k = threadIdx.x; k < cnt; k += blockDim.x) {
+                    double a = hypot(x[2 * (p + k * sps)], x[2 * (p + k * sps) + 1]);
+                    acc += a * a;
+                }
+                tot = block_reduce<false>(acc, sh);
             }
-            double tot = block_reduce<false>(acc, sh);
             double power = tot / (double)cnt;
             if (power > max_power) { max_power = power; best = p; }
         }
@@ -125,11 +134,12 @@ __global__ void slicer_kernel(const double *__restrict__ s, long n, uint8_t *__r
 
 int launch_symbols(tb200_handle h, const double *filtered, int n_chunks, long n, long in_stride, int sps,
                    int phase_step, double *symbols, uint8_t *dibits, long out_stride, int32_t *n_dibits,
-                   int32_t *n_symbols, int32_t *phase, cudaStream_t st)
+                   int32_t *n_symbols, int32_t *phase, cudaStream_t st, const double *phase_partial,
+                   const double *phase_tail, int n_tiles)
 {
     if (n_chunks <= 0) return TB200_OK;
     symbols_kernel<<<n_chunks, 256, 0, st>>>(filtered, n, in_stride, sps, phase_step, symbols, dibits, out_stride,
-                                             n_dibits, n_symbols, phase);
+                                             n_dibits, n_symbols, phase, phase_partial, phase_tail, n_tiles);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
 }
