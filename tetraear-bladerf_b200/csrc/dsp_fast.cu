@@ -72,16 +72,80 @@ __device__ __forceinline__ float2 padded_sample(const float2 *__restrict__ x, lo
     return make_float2(__fsub_rn(__fmul_rn(2.0f, e.x), v.x), __fsub_rn(__fmul_rn(2.0f, e.y), v.y));
 }
 
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+
+// one direction (causal: row0.., taps reversed; anti-causal: next row, taps ascending) for two of the
+// four modes; accumulates Re(alpha * .) into yI/yQ and leaves the pass-end state in `carry`.
+template <int Q, int PITCH, bool FWD>
+__device__ __forceinline__ void fd_half(const float2 *__restrict__ tile, int row0, int lane, int m0,
+                                        const FastDecimParams &K, float yI[FD_R], float yQ[FD_R], cf (*carry)[4])
+{
+    cf UI[FD_R][2], UQ[FD_R][2];
+#pragma unroll
+    for (int r = 0; r < FD_R; ++r) {
+#pragma unroll
+        for (int mm = 0; mm < 2; ++mm) UI[r][mm] = UQ[r][mm] = cf{0.f, 0.f};
+        const float2 *row = tile + (row0 + r + (FWD ? 0 : 1)) * PITCH;
+#pragma unroll
+        for (int c = 0; c < Q; ++c) {
+            const float2 v = row[c];
+#pragma unroll
+            for (int mm = 0; mm < 2; ++mm) {
+                const int tp = FWD ? Q - 1 - c : c;
+                const float tr = K.tap[tp][m0 + mm][0], ti = K.tap[tp][m0 + mm][1];
+                UI[r][mm].x = fmaf(tr, v.x, UI[r][mm].x); UI[r][mm].y = fmaf(ti, v.x, UI[r][mm].y);
+                UQ[r][mm].x = fmaf(tr, v.y, UQ[r][mm].x); UQ[r][mm].y = fmaf(ti, v.y, UQ[r][mm].y);
+            }
+        }
+    }
+#pragma unroll
+    for (int mm = 0; mm < 2; ++mm) {
+        const int m = m0 + mm;
+        const cf lam = ld2(K.lam[m]);
+        // zero-state recurrence inside the lane, then an inclusive scan of the lane aggregates
+        if (FWD) {
+#pragma unroll
+            for (int r = 1; r < FD_R; ++r) { UI[r][mm] = cfma(lam, UI[r - 1][mm], UI[r][mm]); UQ[r][mm] = cfma(lam, UQ[r - 1][mm], UQ[r][mm]); }
+        } else {
+#pragma unroll
+            for (int r = FD_R - 2; r >= 0; --r) { UI[r][mm] = cfma(lam, UI[r + 1][mm], UI[r][mm]); UQ[r][mm] = cfma(lam, UQ[r + 1][mm], UQ[r][mm]); }
+        }
+        cf aI = UI[FWD ? FD_R - 1 : 0][mm], aQ = UQ[FWD ? FD_R - 1 : 0][mm];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            cf oI = FWD ? cshfl_up(aI, 1 << s) : cshfl_down(aI, 1 << s);
+            cf oQ = FWD ? cshfl_up(aQ, 1 << s) : cshfl_down(aQ, 1 << s);
+            const bool take = FWD ? (lane >= (1 << s)) : (lane + (1 << s) < 32);
+            if (take) { cf g = ld2(K.lampow[s][m]); aI = cfma(g, oI, aI); aQ = cfma(g, oQ, aQ); }
+        }
+        cf cI = FWD ? cshfl_up(aI, 1) : cshfl_down(aI, 1);
+        cf cQ = FWD ? cshfl_up(aQ, 1) : cshfl_down(aQ, 1);
+        if (lane == (FWD ? 0 : 31)) cI = cQ = cf{0.f, 0.f};
+        if (lane == (FWD ? 31 : 0)) { carry[0][m] = aI; carry[1][m] = aQ; }
+        const cf a0 = FWD ? ld2(K.a0[m]) : ld2(K.ap[m]);
+#pragma unroll
+        for (int r = 0; r < FD_R; ++r) {
+            const cf af = FWD ? ld2(K.aF[r][m]) : ld2(K.aB[r][m]);
+            yI[r] += a0.x * UI[r][mm].x - a0.y * UI[r][mm].y + af.x * cI.x - af.y * cI.y;
+            yQ[r] += a0.x * UQ[r][mm].x - a0.y * UQ[r][mm].y + af.x * cQ.x - af.y * cQ.y;
+        }
+    }
+}
+
 template <int Q>
 __global__ void __launch_bounds__(FD_W * 32, 2)
 decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int tiles_per_chunk, long n_dec,
                   FastDecimParams K, float2 *__restrict__ dec_out)
 {
+    // interleaved (I,Q) rows of Q samples, row pitch PITCH float2 with R*PITCH odd mod 16: the 16 lanes of a
+    // half-warp, R rows apart, hit 16 different 8-byte banks
     constexpr int PITCH = (Q & 1) ? Q : Q + 1;
     constexpr int ROWS = FD_W * FD_P + 1;
-    extern __shared__ float fd_smem[];
-    float *sI = fd_smem;
-    float *sQ = fd_smem + ROWS * PITCH;
+    extern __shared__ float2 fd_tile[];
     __shared__ cf carryF[FD_W][2][4];
     __shared__ cf carryB[FD_W][2][4];
 
@@ -93,12 +157,21 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
     const long k_tile0 = (long)tile * (FD_W - 2) * FD_P - FD_P;
     const long t0 = 27 + (long)Q * k_tile0 - (Q - 1);
 
-    // ---- stage the tile: coalesced float2 loads -> I/Q planes with odd pitch
-    for (int s = threadIdx.x; s < ROWS * Q; s += blockDim.x) {
-        float2 v = padded_sample(xc, n, t0 + s);
-        int row = s / Q, col = s - row * Q;
-        sI[row * PITCH + col] = v.x;
-        sQ[row * PITCH + col] = v.y;
+    // ---- stage the tile.  Interior tiles: asynchronous 8-byte global->shared copies (no registers, all
+    // in flight at once); tiles touching a chunk end synthesise the odd extension sample by sample.
+    if (t0 >= 27 && t0 + (long)ROWS * Q <= 27 + n) {
+        const float2 *src = xc + (t0 - 27);
+        for (int s = threadIdx.x; s < ROWS * Q; s += blockDim.x) {
+            int row = s / Q, col = s - row * Q;
+            cp_async8(&fd_tile[row * PITCH + col], src + s);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    } else {
+        for (int s = threadIdx.x; s < ROWS * Q; s += blockDim.x) {
+            int row = s / Q, col = s - row * Q;
+            fd_tile[row * PITCH + col] = padded_sample(xc, n, t0 + s);
+        }
     }
     __syncthreads();
 
@@ -107,93 +180,13 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
     float yI[FD_R], yQ[FD_R];
 #pragma unroll
     for (int r = 0; r < FD_R; ++r) yI[r] = yQ[r] = 0.f;
-
-    // ---- forward (causal) part
     if (do_F) {
-        cf UI[FD_R][4], UQ[FD_R][4];
-#pragma unroll
-        for (int r = 0; r < FD_R; ++r) {
-#pragma unroll
-            for (int m = 0; m < 4; ++m) UI[r][m] = UQ[r][m] = cf{0.f, 0.f};
-            const float *pi = sI + (row0 + r) * PITCH, *pq = sQ + (row0 + r) * PITCH;
-#pragma unroll
-            for (int c = 0; c < Q; ++c) {
-                float xi = pi[c], xq = pq[c];
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    float tr = K.tap[Q - 1 - c][m][0], ti = K.tap[Q - 1 - c][m][1];
-                    UI[r][m].x = fmaf(tr, xi, UI[r][m].x); UI[r][m].y = fmaf(ti, xi, UI[r][m].y);
-                    UQ[r][m].x = fmaf(tr, xq, UQ[r][m].x); UQ[r][m].y = fmaf(ti, xq, UQ[r][m].y);
-                }
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const cf lam = ld2(K.lam[m]);
-            // zero-state recurrence inside the lane
-#pragma unroll
-            for (int r = 1; r < FD_R; ++r) { UI[r][m] = cfma(lam, UI[r - 1][m], UI[r][m]); UQ[r][m] = cfma(lam, UQ[r - 1][m], UQ[r][m]); }
-            // inclusive scan of lane aggregates (multiplier lambda^R per lane)
-            cf aI = UI[FD_R - 1][m], aQ = UQ[FD_R - 1][m];
-#pragma unroll
-            for (int s = 0; s < 5; ++s) {
-                cf oI = cshfl_up(aI, 1 << s), oQ = cshfl_up(aQ, 1 << s);
-                if (lane >= (1 << s)) { cf g = ld2(K.lampow[s][m]); aI = cfma(g, oI, aI); aQ = cfma(g, oQ, aQ); }
-            }
-            cf cI = cshfl_up(aI, 1), cQ = cshfl_up(aQ, 1);
-            if (lane == 0) cI = cQ = cf{0.f, 0.f};
-            if (lane == 31) { carryF[w][0][m] = aI; carryF[w][1][m] = aQ; }
-            const cf a0 = ld2(K.a0[m]);
-#pragma unroll
-            for (int r = 0; r < FD_R; ++r) {
-                const cf af = ld2(K.aF[r][m]);
-                // Re(alpha Fz[r]) + Re(alpha lambda^(r+1) cin)
-                yI[r] += a0.x * UI[r][m].x - a0.y * UI[r][m].y + af.x * cI.x - af.y * cI.y;
-                yQ[r] += a0.x * UQ[r][m].x - a0.y * UQ[r][m].y + af.x * cQ.x - af.y * cQ.y;
-            }
-        }
+        fd_half<Q, PITCH, true>(fd_tile, row0, lane, 0, K, yI, yQ, carryF[w]);
+        fd_half<Q, PITCH, true>(fd_tile, row0, lane, 2, K, yI, yQ, carryF[w]);
     }
-    // ---- backward (anti-causal) part: V uses the NEXT row, taps in ascending order
     if (do_B) {
-        cf VI[FD_R][4], VQ[FD_R][4];
-#pragma unroll
-        for (int r = 0; r < FD_R; ++r) {
-#pragma unroll
-            for (int m = 0; m < 4; ++m) VI[r][m] = VQ[r][m] = cf{0.f, 0.f};
-            const float *pi = sI + (row0 + r + 1) * PITCH, *pq = sQ + (row0 + r + 1) * PITCH;
-#pragma unroll
-            for (int c = 0; c < Q; ++c) {
-                float xi = pi[c], xq = pq[c];
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    float tr = K.tap[c][m][0], ti = K.tap[c][m][1];
-                    VI[r][m].x = fmaf(tr, xi, VI[r][m].x); VI[r][m].y = fmaf(ti, xi, VI[r][m].y);
-                    VQ[r][m].x = fmaf(tr, xq, VQ[r][m].x); VQ[r][m].y = fmaf(ti, xq, VQ[r][m].y);
-                }
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const cf lam = ld2(K.lam[m]);
-#pragma unroll
-            for (int r = FD_R - 2; r >= 0; --r) { VI[r][m] = cfma(lam, VI[r + 1][m], VI[r][m]); VQ[r][m] = cfma(lam, VQ[r + 1][m], VQ[r][m]); }
-            cf aI = VI[0][m], aQ = VQ[0][m];
-#pragma unroll
-            for (int s = 0; s < 5; ++s) {
-                cf oI = cshfl_down(aI, 1 << s), oQ = cshfl_down(aQ, 1 << s);
-                if (lane + (1 << s) < 32) { cf g = ld2(K.lampow[s][m]); aI = cfma(g, oI, aI); aQ = cfma(g, oQ, aQ); }
-            }
-            cf cI = cshfl_down(aI, 1), cQ = cshfl_down(aQ, 1);
-            if (lane == 31) cI = cQ = cf{0.f, 0.f};
-            if (lane == 0) { carryB[w][0][m] = aI; carryB[w][1][m] = aQ; }
-            const cf ap = ld2(K.ap[m]);
-#pragma unroll
-            for (int r = 0; r < FD_R; ++r) {
-                const cf ab = ld2(K.aB[r][m]);
-                yI[r] += ap.x * VI[r][m].x - ap.y * VI[r][m].y + ab.x * cI.x - ab.y * cI.y;
-                yQ[r] += ap.x * VQ[r][m].x - ap.y * VQ[r][m].y + ab.x * cQ.x - ab.y * cQ.y;
-            }
-        }
+        fd_half<Q, PITCH, false>(fd_tile, row0, lane, 0, K, yI, yQ, carryB[w]);
+        fd_half<Q, PITCH, false>(fd_tile, row0, lane, 2, K, yI, yQ, carryB[w]);
     }
     __syncthreads();
     if (!store) return;
@@ -388,7 +381,7 @@ static int launch_q(tb200_handle h, const void *x, int n_chunks, long n, long ch
 {
     constexpr int PITCH = (Q & 1) ? Q : Q + 1;
     constexpr int ROWS = FD_W * FD_P + 1;
-    const size_t smem = sizeof(float) * 2 * ROWS * PITCH;
+    const size_t smem = sizeof(float2) * ROWS * PITCH;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(decim_fast_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
