@@ -178,6 +178,15 @@ int tb200_burst_batch_host(tb200_handle h, const uint8_t *h_dibits, int64_t n, u
 int tb200_crc16_rows(tb200_handle h, const uint8_t *d_bits, int n_rows, int n_bits, int row_stride,
                      uint16_t *d_crc, void *stream);
 
+/* ---- `etsi` mode: ETSI EN 300 392-2 clause 8 channel decoding over a batch of bursts.
+ * NOT in the reference (core/protocol.py:300 "we do not do full channel decoding"): parity unpinned,
+ * validated by encode -> decode round trips (tests/test_etsi_*.py).
+ * d_soft [n][K3] int8 soft type-5 bits (+ = 1); channel 0 SCH/HD (124->216), 1 SCH/F (268->432),
+ * 2 BSCH (60->120); scramb_init = ((colour | mnc<<6 | mcc<<20) << 2) | 3.
+ * d_bits [n][40]: decoded type-1 bits packed MSB-first; d_crc_ok [n]; d_metric [n] final path metric. */
+int tb200_etsi_decode_batch(tb200_handle h, const int8_t *d_soft, int64_t n, int channel, uint32_t scramb_init,
+                            uint8_t *d_bits, uint8_t *d_crc_ok, int32_t *d_metric, void *stream);
+
 /* ---- waterfall PSD + AFC statistics (tetraear/ui/modern.py:1926-2029, :923-947) ---------
  * frame i = Hann(n_fft) * iq[i*frame_stride : +n_fft]; power = 20 log10(|fftshift FFT|/n_fft + 1e-20)
  * d_power    [n_frames][n_fft] float32 dB (or NULL)

@@ -490,6 +490,16 @@ extern "C" int tb200_crc16_rows(tb200_handle h, const uint8_t *d_bits, int n_row
     return launch_crc16_rows(h, d_bits, n_rows, n_bits, row_stride, d_crc, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------------- etsi mode
+extern "C" int tb200_etsi_decode_batch(tb200_handle h, const int8_t *d_soft, int64_t n, int channel, uint32_t scramb_init,
+                                       uint8_t *d_bits, uint8_t *d_crc_ok, int32_t *d_metric, void *stream)
+{
+    if (!h || n < 0 || (n && (!d_soft || !d_bits || !d_crc_ok || !d_metric)))
+        return fail(TB200_E_ARG, "tb200_etsi_decode_batch: bad argument");
+    StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
+    return launch_etsi_decode(h, d_soft, n, channel, scramb_init, d_bits, d_crc_ok, d_metric, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------- PSD
 extern "C" int tb200_psd_batch(tb200_handle h, const void *d_iq_c64, int64_t n_frames, int64_t frame_stride, int n_fft,
                                double sample_rate, double ema_alpha, int first, float *d_power, float *d_smoothed,
