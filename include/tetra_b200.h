@@ -187,6 +187,22 @@ int tb200_crc16_rows(tb200_handle h, const uint8_t *d_bits, int n_rows, int n_bi
 int tb200_etsi_decode_batch(tb200_handle h, const int8_t *d_soft, int64_t n, int channel, uint32_t scramb_init,
                             uint8_t *d_bits, uint8_t *d_crc_ok, int32_t *d_metric, void *stream);
 
+/* `etsi` mode physical layer (parity unpinned): per stream (one 25 kHz channel at
+ * fs in [36, 72] kHz, i.e. 2..4 samples/symbol): RRC(0.35) matched filter + closed-loop timing
+ * (Gardner + PI) + pi/4-DQPSK differential soft bits.  d_soft [n_streams][soft_stride] float, two per
+ * symbol, + = 1, normalised by the running symbol power; d_n_soft = soft bits produced. */
+int tb200_etsi_demod_batch(tb200_handle h, const void *d_iq_c64, int n_streams, int64_t n_samples, int64_t stride,
+                           double fs, void *d_sym_c64, float *d_soft, int64_t soft_stride, int32_t *d_n_soft,
+                           void *stream);
+/* normal-burst training-sequence search on the soft bits: d_metric [n_streams][soft_stride/2] scratch
+ * (normalised correlation per symbol position, sign = which of the two normal sequences); for every
+ * burst found the two 216-bit blocks BKN1 | BKN2 are quantised to int8 into d_blocks
+ * [n_streams][max_bursts][432] (input of tb200_etsi_decode_batch, channel 0) and its first bit
+ * position into d_burst_pos. */
+int tb200_etsi_find_bursts(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,
+                           const int32_t *d_n_soft, double threshold, float *d_metric, int8_t *d_blocks,
+                           int32_t *d_burst_pos, int32_t *d_n_bursts, int max_bursts, void *stream);
+
 /* ---- waterfall PSD + AFC statistics (tetraear/ui/modern.py:1926-2029, :923-947) ---------
  * frame i = Hann(n_fft) * iq[i*frame_stride : +n_fft]; power = 20 log10(|fftshift FFT|/n_fft + 1e-20)
  * d_power    [n_frames][n_fft] float32 dB (or NULL)

@@ -75,6 +75,7 @@ static size_t carve(tb200_handle h, char *base)
     h->sync_cnt = c.take<int32_t>(64);
     size_t nf = (size_t)cfg.max_fft;
     h->psd_tables = c.take<double>((nf + 2 * (nf / 2 + nf / 4 + 1)) * sizeof(double));
+    h->etsi_taps = c.take<float>(32 * 32 * sizeof(float));
     // staging for *_host
     h->stage_in_bytes = C * L * 8;
     h->stage_in = c.take<char>(h->stage_in_bytes);
@@ -498,6 +499,28 @@ extern "C" int tb200_etsi_decode_batch(tb200_handle h, const int8_t *d_soft, int
         return fail(TB200_E_ARG, "tb200_etsi_decode_batch: bad argument");
     StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
     return launch_etsi_decode(h, d_soft, n, channel, scramb_init, d_bits, d_crc_ok, d_metric, (cudaStream_t)stream);
+}
+
+extern "C" int tb200_etsi_demod_batch(tb200_handle h, const void *d_iq_c64, int n_streams, int64_t n_samples, int64_t stride,
+                                      double fs, void *d_sym_c64, float *d_soft, int64_t soft_stride, int32_t *d_n_soft,
+                                      void *stream)
+{
+    if (!h || n_streams < 0 || n_samples < 0 || !d_iq_c64 || !d_soft || !d_n_soft || soft_stride < 2)
+        return fail(TB200_E_ARG, "tb200_etsi_demod_batch: bad argument");
+    StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
+    return launch_etsi_demod(h, (const float2 *)d_iq_c64, n_streams, n_samples, stride, fs, h->etsi_taps, (float2 *)d_sym_c64,
+                             d_soft, soft_stride, d_n_soft, (cudaStream_t)stream);
+}
+
+extern "C" int tb200_etsi_find_bursts(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,
+                                      const int32_t *d_n_soft, double threshold, float *d_metric, int8_t *d_blocks,
+                                      int32_t *d_burst_pos, int32_t *d_n_bursts, int max_bursts, void *stream)
+{
+    if (!h || n_streams < 0 || !d_soft || !d_n_soft || !d_metric || !d_blocks || !d_burst_pos || !d_n_bursts || max_bursts <= 0)
+        return fail(TB200_E_ARG, "tb200_etsi_find_bursts: bad argument");
+    StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
+    return launch_etsi_find_bursts(h, d_soft, n_streams, soft_stride, d_n_soft, (float)threshold, d_metric, d_blocks, d_burst_pos,
+                                   d_n_bursts, max_bursts, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------- PSD

@@ -116,15 +116,25 @@ __global__ void decim_exact_bwd(const T *__restrict__ scratch, long n, int q, in
     // j-th fed sample is ext position m-1-j; the output of step j belongs to position m-1-(j-3)
     long last_kept = ((n - 1) / q) * (long)q;          // largest kept index in [0, n)
     long next_keep = edge + last_kept;                  // ext position of the next sample to keep
-    for (long j = 0; j < m + 3; ++j) {
-        T v = (j < m) ? in[(m - 1 - j) * n_lanes] : T(0);
-        T o = (j < 3 || j >= m) ? f.template step<true>(K.c, v, j, m) : f.template step<false>(K.c, v, j, m);
+    auto emit = [&](long j, T o) {
         long pos = m - 1 - (j - 3);
         if (j >= 3 && pos == next_keep && pos >= edge) {
             out[2 * ((pos - edge) / q)] = o;
             next_keep -= q;
         }
+    };
+    long j = 0;
+    for (; j < 3; ++j) emit(j, f.template step<true>(K.c, in[(m - 1 - j) * n_lanes], j, m));
+    // body: 8 loads in flight ahead of the recurrence (the scratch rows are 4*n_lanes bytes apart)
+    for (; j + 8 <= m; j += 8) {
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = in[(m - 1 - (j + u)) * n_lanes];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) emit(j + u, f.template step<false>(K.c, v[u], j + u, m));
     }
+    for (; j < m; ++j) emit(j, f.template step<false>(K.c, in[(m - 1 - j) * n_lanes], j, m));
+    for (; j < m + 3; ++j) emit(j, f.template step<true>(K.c, T(0), j, m));
 }
 
 // ---- channel filter: NCO (processor.py:97-100) + butter(4) filtfilt in float64 (:74-79) --
@@ -199,7 +209,19 @@ __global__ void chan_exact_bwd(const double *__restrict__ scratch, long n, int n
 #pragma unroll
     for (int k = 0; k < 4; ++k) Z[k] = xmul(K.zi[k], first);
     double *out = filtered + (long)(lane >> 1) * out_stride * 2 + (lane & 1);
-    for (long t = m - 1; t >= 0; --t) {
+    long t = m - 1;
+    for (; t >= 7; t -= 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = scratch[(t - u) * n_lanes + lane];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            double y = df2t4(K, Z, v[u]);
+            long tt = t - u;
+            if (tt >= edge && tt < edge + n) out[2 * (tt - edge)] = y;
+        }
+    }
+    for (; t >= 0; --t) {
         double y = df2t4(K, Z, scratch[t * n_lanes + lane]);
         if (t >= edge && t < edge + n) out[2 * (t - edge)] = y;
     }

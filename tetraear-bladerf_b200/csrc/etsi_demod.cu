@@ -1,0 +1,199 @@
+// etsi_demod.cu — `etsi` mode physical layer per 25 kHz channel: RRC (alpha 0.35) matched filter,
+// closed-loop symbol timing at 18 ksym/s (Gardner detector + PI loop, fractional-delay polyphase
+// matched-filter bank), pi/4-DQPSK differential detection with SOFT bit output, and the
+// normal-burst training-sequence search on the soft bits.
+//
+// None of this exists in the reference (it uses a Butterworth low-pass, an
+// open-loop 13-phase power pick at 18 461.5 sym/s, a hard slicer with mis-centred decision
+// regions and a hard-bit Hamming scan) — parity unpinned; validated end to end by
+// modulator -> demod -> TS search -> channel decoder round trips (tests/test_etsi_phy.py).
+//
+// One warp per stream: the feedback state (timing phase, loop integrator, power estimate) is
+// warp-uniform and register resident; the 32 lanes are the 32 taps of the interpolating matched
+// filter, reduced with shuffles, for the on-time and the half-symbol sample of every symbol.
+#include <cmath>
+#include "common.h"
+#include "kernels.h"
+
+namespace tb200 {
+
+constexpr int ED_TAPS = 32;
+constexpr int ED_PH = 32;
+
+__device__ __forceinline__ float2 warp_sum2(float2 v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o); }
+    return v;
+}
+
+// matched-filter output at continuous sample time tau (window i-15 .. i+16 around i = floor(tau))
+__device__ __forceinline__ float2 mf_at(const float2 *__restrict__ x, long n, const float *__restrict__ taps, float tau, int lane)
+{
+    float fl = floorf(tau);
+    long i = (long)fl;
+    int ph = (int)((tau - fl) * ED_PH);
+    ph = ph < 0 ? 0 : (ph >= ED_PH ? ED_PH - 1 : ph);
+    long idx = i + lane - 15;
+    float2 v = (idx >= 0 && idx < n) ? x[idx] : make_float2(0.f, 0.f);
+    float g = taps[ph * ED_TAPS + lane];
+    return warp_sum2(make_float2(v.x * g, v.y * g));
+}
+
+__global__ void etsi_demod_kernel(const float2 *__restrict__ iq, int n_streams, long n, long stride, float sps, float kp,
+                                  float ki, const float *__restrict__ taps_g, float2 *__restrict__ sym_out,
+                                  float *__restrict__ soft_out, long soft_stride, int32_t *__restrict__ n_soft)
+{
+    __shared__ float taps[ED_PH * ED_TAPS];
+    for (int i = threadIdx.x; i < ED_PH * ED_TAPS; i += blockDim.x) taps[i] = taps_g[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= n_streams) return;
+    const float2 *x = iq + (long)s * stride;
+    float tau = 16.0f + sps;                 // first symbol instant with a full filter window
+    float integ = 0.f, pavg = 0.f;
+    float2 prev = make_float2(0.f, 0.f);
+    long k = 0;
+    const long max_sym = soft_stride / 2;
+    float2 *so = sym_out ? sym_out + (long)s * max_sym : nullptr;
+    float *sb = soft_out + (long)s * soft_stride;
+    while (tau + 17.0f < (float)n && k < max_sym) {
+        float2 on = mf_at(x, n, taps, tau, lane);
+        float2 mid = mf_at(x, n, taps, tau - 0.5f * sps, lane);
+        float p = on.x * on.x + on.y * on.y;
+        pavg = (k == 0) ? p : 0.98f * pavg + 0.02f * p;
+        float inv = 1.0f / (pavg + 1e-20f);
+        // Gardner: e = Re{(y[k] - y[k-1]) conj(y[k-1/2])}; e > 0 <=> sampling late
+        float e = ((on.x - prev.x) * mid.x + (on.y - prev.y) * mid.y) * inv;
+        e = fminf(fmaxf(e, -1.0f), 1.0f);
+        // differential detection: d = y[k] conj(y[k-1]); b1 = [Im d < 0], b2 = [Re d < 0]; soft = -(.)/P
+        float dre = on.x * prev.x + on.y * prev.y, dim = on.y * prev.x - on.x * prev.y;
+        if (lane == 0) {
+            if (so) so[k] = on;
+            if (k > 0) { sb[2 * (k - 1)] = -dim * inv; sb[2 * (k - 1) + 1] = -dre * inv; }
+        }
+        prev = on;
+        if (k > 0) { integ += ki * e; tau += sps - kp * e - integ; }
+        else tau += sps;
+        ++k;
+    }
+    if (lane == 0) n_soft[s] = (int32_t)(k > 0 ? 2 * (k - 1) : 0);
+}
+
+// training sequences (EN 300 392-2 cl. 9.4.4.3): normal n, p, and the extended/tail q
+__constant__ int8_t c_ts_pm[3][22] = {
+    {1, 1, -1, 1, -1, -1, -1, -1, 1, 1, 1, -1, 1, -1, -1, 1, 1, 1, -1, 1, -1, -1},
+    {-1, 1, 1, 1, 1, -1, 1, -1, -1, 1, -1, -1, -1, -1, 1, 1, -1, 1, 1, 1, 1, -1},
+    {1, -1, 1, 1, -1, 1, 1, 1, -1, -1, -1, -1, -1, 1, 1, -1, 1, -1, 1, 1, -1, 1}};
+
+// normalised soft correlation with the two normal training sequences at every (even) bit position
+__global__ void etsi_ts_corr_kernel(const float *__restrict__ soft, long soft_stride, const int32_t *__restrict__ n_soft,
+                                    float *__restrict__ metric)
+{
+    int s = blockIdx.y;
+    long nb = n_soft[s];
+    long p = 2 * (blockIdx.x * (long)blockDim.x + threadIdx.x);      // bursts start on symbol boundaries
+    if (p + 22 > nb) return;
+    const float *b = soft + (long)s * soft_stride + p;
+    float c0 = 0.f, c1 = 0.f, en = 0.f;
+#pragma unroll
+    for (int i = 0; i < 22; ++i) { float v = b[i]; c0 += v * c_ts_pm[0][i]; c1 += v * c_ts_pm[1][i]; en += fabsf(v); }
+    float best = fmaxf(c0, c1) / (en + 1e-20f);
+    metric[(long)s * (soft_stride / 2) + p / 2] = (c1 > c0) ? -best : best;     // sign carries the sequence id
+}
+
+// one warp per stream: first position over threshold, refine to the local maximum of the next 4
+// symbol positions, emit the burst (TS at bit 244), skip ahead one burst.
+__global__ void etsi_find_bursts_kernel(const float *__restrict__ soft, long soft_stride, const int32_t *__restrict__ n_soft,
+                                        const float *__restrict__ metric, int n_streams, float thr,
+                                        int8_t *__restrict__ blocks, int32_t *__restrict__ burst_pos,
+                                        int32_t *__restrict__ n_bursts, int max_bursts, float quant)
+{
+    const int lane = threadIdx.x & 31;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= n_streams) return;
+    const long nb = n_soft[s];
+    const long npos = (nb >= 22) ? (nb - 22) / 2 + 1 : 0;
+    const float *m = metric + (long)s * (soft_stride / 2);
+    const float *b = soft + (long)s * soft_stride;
+    int found = 0;
+    long i = 0;
+    while (i < npos && found < max_bursts) {
+        long p = i + lane;
+        float v = (p < npos) ? fabsf(m[p]) : 0.f;
+        unsigned ball = __ballot_sync(0xffffffffu, v >= thr);
+        if (!ball) { i += 32; continue; }
+        long first = i + (__ffs(ball) - 1);
+        // local maximum over first .. first+3
+        long best = first;
+        float bv = fabsf(m[first]);
+        for (int d = 1; d < 4; ++d) if (first + d < npos && fabsf(m[first + d]) > bv) { bv = fabsf(m[first + d]); best = first + d; }
+        long ts_bit = 2 * best;
+        long start = ts_bit - 244;
+        if (start >= 0 && start + 510 <= nb) {
+            int8_t *o = blocks + ((long)s * max_bursts + found) * 432;
+            for (int j = lane; j < 432; j += 32) {
+                long src = start + (j < 216 ? 14 + j : 282 + (j - 216));
+                float q = rintf(b[src] * quant);
+                o[j] = (int8_t)fminf(fmaxf(q, -127.f), 127.f);
+            }
+            if (lane == 0) burst_pos[(long)s * max_bursts + found] = (int32_t)start;
+            ++found;
+        }
+        i = best + 200;          // next training sequence is 255 symbols later
+    }
+    if (lane == 0) n_bursts[s] = found;
+}
+
+void make_mf_taps(double sps, float *taps)
+{
+    const double alpha = 0.35;
+    for (int ph = 0; ph < ED_PH; ++ph) {
+        for (int j = 0; j < ED_TAPS; ++j) {
+            double t = ((double)ph / ED_PH - (double)(j - 15)) / sps;      // in symbols
+            double v;
+            double at = std::fabs(t);
+            if (at < 1e-9) v = 1 - alpha + 4 * alpha / M_PI;
+            else if (std::fabs(at - 1 / (4 * alpha)) < 1e-9)
+                v = alpha / std::sqrt(2.0) * ((1 + 2 / M_PI) * std::sin(M_PI / (4 * alpha)) + (1 - 2 / M_PI) * std::cos(M_PI / (4 * alpha)));
+            else
+                v = (std::sin(M_PI * t * (1 - alpha)) + 4 * alpha * t * std::cos(M_PI * t * (1 + alpha))) /
+                    (M_PI * t * (1 - (4 * alpha * t) * (4 * alpha * t)));
+            taps[ph * ED_TAPS + j] = (float)(v / sps);
+        }
+    }
+}
+
+int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, long stride, double fs, float *taps_dev,
+                      float2 *sym, float *soft, long soft_stride, int32_t *n_soft, cudaStream_t st)
+{
+    if (n_streams <= 0) return TB200_OK;
+    double sps = fs / 18000.0;
+    if (sps < 2.0 || sps > 4.01) return fail(TB200_E_ARG, "tb200_etsi_demod_batch: %.3f samples/symbol outside [2, 4]", sps);
+    float taps[ED_PH * ED_TAPS];
+    make_mf_taps(sps, taps);
+    TB_CUDA(cudaMemcpyAsync(taps_dev, taps, sizeof(taps), cudaMemcpyHostToDevice, st));
+    int threads = 128, blocks = (n_streams * 32 + threads - 1) / threads;
+    etsi_demod_kernel<<<blocks, threads, 0, st>>>(iq, n_streams, n, stride, (float)sps, (float)(0.05 * sps), (float)(0.0005 * sps),
+                                                  taps_dev, sym, soft, soft_stride, n_soft);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+int launch_etsi_find_bursts(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft,
+                            float thr, float *metric, int8_t *blocks, int32_t *burst_pos, int32_t *n_bursts, int max_bursts,
+                            cudaStream_t st)
+{
+    if (n_streams <= 0) return TB200_OK;
+    dim3 grid((unsigned)((soft_stride / 2 + 255) / 256), (unsigned)n_streams);
+    etsi_ts_corr_kernel<<<grid, 256, 0, st>>>(soft, soft_stride, n_soft, metric);
+    TB_LAUNCH_CHECK(h);
+    int threads = 128, blocks_n = (n_streams * 32 + threads - 1) / threads;
+    etsi_find_bursts_kernel<<<blocks_n, threads, 0, st>>>(soft, soft_stride, n_soft, metric, n_streams, thr, blocks, burst_pos,
+                                                         n_bursts, max_bursts, 45.0f);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+}  // namespace tb200

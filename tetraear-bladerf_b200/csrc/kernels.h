@@ -33,6 +33,11 @@ int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_
                double *scratch_db, cudaStream_t st);
 int launch_etsi_decode(tb200_handle h, const int8_t *soft, long n, int channel, uint32_t scramb_init, uint8_t *bits,
                        uint8_t *crc_ok, int32_t *metric, cudaStream_t st);
+int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, long stride, double fs, float *taps_dev,
+                      float2 *sym, float *soft, long soft_stride, int32_t *n_soft, cudaStream_t st);
+int launch_etsi_find_bursts(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft,
+                            float thr, float *metric, int8_t *blocks, int32_t *burst_pos, int32_t *n_bursts, int max_bursts,
+                            cudaStream_t st);
 int launch_freq_shift(tb200_handle h, const void *x, int dtype, long n, double f, double fs, double *out, cudaStream_t st);
 
 }  // namespace tb200

@@ -126,3 +126,148 @@ class ChannelDecoder:
         bits, ok, met = self.decode_device(d, scramb_init)
         b = np.unpackbits(bits.cpu().numpy(), axis=1)[:, :self.K1]
         return b, ok.cpu().numpy().astype(bool), met.cpu().numpy()
+
+
+# ======================================================================================
+# ETSI physical layer: burst building + pi/4-DQPSK RRC modulator (workload generator) and the
+# host API of the CUDA demodulator (RRC matched filter, closed-loop timing, soft bits, TS search)
+# ======================================================================================
+TS_N = np.array([1, 1, 0, 1, 0, 0, 0, 0, 1, 1, 1, 0, 1, 0, 0, 1, 1, 1, 0, 1, 0, 0], dtype=np.uint8)   # normal 1
+TS_P = np.array([0, 1, 1, 1, 1, 0, 1, 0, 0, 1, 0, 0, 0, 0, 1, 1, 0, 1, 1, 1, 1, 0], dtype=np.uint8)   # normal 2
+TS_Q = np.array([1, 0, 1, 1, 0, 1, 1, 1, 0, 0, 0, 0, 0, 1, 1, 0, 1, 0, 1, 1, 0, 1], dtype=np.uint8)   # tail/extended
+# normal continuous downlink burst, bit offsets (EN 300 392-2 cl. 9.4.4.3.2)
+NDB = {"q_tail": (0, 12), "pa": (12, 14), "bkn1": (14, 230), "bb1": (230, 244), "ts": (244, 266),
+       "bb2": (266, 282), "bkn2": (282, 498), "pb": (498, 500), "q_head": (500, 510)}
+# dibit (b1, b2) -> differential phase
+DQPSK_DPHI = {(0, 0): np.pi / 4, (0, 1): 3 * np.pi / 4, (1, 1): -3 * np.pi / 4, (1, 0): -np.pi / 4}
+
+
+def rrc_pulse(t, alpha=0.35):
+    """Root-raised-cosine impulse response at times t (in symbols), unit energy per symbol."""
+    t = np.asarray(t, dtype=np.float64)
+    out = np.empty_like(t)
+    eps = 1e-9
+    z = np.abs(t) < eps
+    s = np.abs(np.abs(t) - 1 / (4 * alpha)) < eps
+    r = ~(z | s)
+    out[z] = 1 - alpha + 4 * alpha / np.pi
+    out[s] = alpha / np.sqrt(2) * ((1 + 2 / np.pi) * np.sin(np.pi / (4 * alpha)) + (1 - 2 / np.pi) * np.cos(np.pi / (4 * alpha)))
+    tr = t[r]
+    out[r] = (np.sin(np.pi * tr * (1 - alpha)) + 4 * alpha * tr * np.cos(np.pi * tr * (1 + alpha))) / \
+             (np.pi * tr * (1 - (4 * alpha * tr) ** 2))
+    return out
+
+
+def build_normal_burst(bkn1, bkn2, rng=None, ts=TS_N):
+    """510-bit normal continuous downlink burst around two 216-bit (type-5) blocks."""
+    rng = np.random.default_rng(0) if rng is None else rng
+    b = rng.integers(0, 2, 510, dtype=np.uint8)
+    b[0:12] = TS_Q[10:22]
+    b[14:230] = bkn1
+    b[244:266] = ts
+    b[282:498] = bkn2
+    b[500:510] = TS_Q[0:10]
+    return b
+
+
+def make_etsi_stream(n_bursts, seed=0, scramb_init=None, ts=TS_N):
+    """Back-to-back normal bursts carrying random SCH/HD blocks.  Returns (bits, type1 [n,2,124])."""
+    rng = np.random.default_rng(seed)
+    init = scrambling_init(262, 42, 17) if scramb_init is None else scramb_init
+    t1 = rng.integers(0, 2, (n_bursts, 2, 124), dtype=np.uint8)
+    t5 = encode(t1.reshape(-1, 124), "SCH/HD", init).reshape(n_bursts, 2, 216)
+    bits = np.concatenate([build_normal_burst(t5[i, 0], t5[i, 1], rng, ts) for i in range(n_bursts)])
+    return bits, t1, init
+
+
+def modulate_dqpsk(bits, fs, symbol_rate=18000.0, sigma=0.0, freq=0.0, t_offset=0.0, amplitude=1.0, seed=0,
+                   n_samples=None, span=6):
+    """pi/4-DQPSK with RRC(0.35) pulse shaping at an arbitrary (non-integer) samples-per-symbol ratio,
+    mixed to `freq` Hz; complex64."""
+    bits = np.asarray(bits, dtype=np.uint8)
+    dib = bits.reshape(-1, 2)
+    dphi = np.array([DQPSK_DPHI[(int(a), int(b))] for a, b in dib])
+    sym = amplitude * np.exp(1j * np.concatenate([[0.0], np.cumsum(dphi)]))
+    sps = fs / symbol_rate
+    n = int(np.ceil((len(sym) + 2 * span) * sps)) if n_samples is None else n_samples
+    t = (np.arange(n) / sps) - span - t_offset                   # time in symbols, symbol k at t = k
+    k0 = np.floor(t).astype(np.int64)
+    x = np.zeros(n, dtype=np.complex128)
+    for d in range(-span + 1, span + 1):
+        k = k0 + d
+        ok = (k >= 0) & (k < len(sym))
+        x[ok] += sym[k[ok]] * rrc_pulse(t[ok] - k[ok])
+    if freq:
+        x *= np.exp(2j * np.pi * freq * np.arange(n) / fs)
+    if sigma > 0:
+        rng = np.random.default_rng(seed + 1000)
+        x += sigma * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    return x.astype(np.complex64)
+
+
+class EtsiReceiver:
+    """`etsi` mode receive chain for a batch of 25 kHz channels, all on the GPU:
+    RRC matched filter + closed-loop timing + soft pi/4-DQPSK bits (tb200_etsi_demod_batch) ->
+    training-sequence search + block extraction (tb200_etsi_find_bursts) ->
+    descramble / de-interleave / Viterbi / CRC of both SCH/HD blocks (tb200_etsi_decode_batch)."""
+
+    def __init__(self, fs, max_streams, max_samples, device=0, max_bursts_per_stream=None):
+        import torch
+        from . import _dev
+        self.fs = float(fs)
+        self.device = device
+        self.max_streams, self.max_samples = int(max_streams), int(max_samples)
+        sps = self.fs / 18000.0
+        self.max_sym = int(max_samples / sps) + 8
+        self.soft_stride = 2 * self.max_sym
+        self.max_bursts = max_bursts_per_stream or (self.max_sym // 255 + 2)
+        self._h = _lib.Handle(max_chunks=0, max_chunk_len=0, device=device)
+        S = self.max_streams
+        self.soft = _dev.zeros((S, self.soft_stride), torch.float32, device)
+        self.n_soft = _dev.zeros((S,), torch.int32, device)
+        self.metric = _dev.zeros((S, self.max_sym), torch.float32, device)
+        self.blocks = _dev.zeros((S, self.max_bursts, 432), torch.int8, device)
+        self.burst_pos = _dev.zeros((S, self.max_bursts), torch.int32, device)
+        self.n_bursts = _dev.zeros((S,), torch.int32, device)
+        self.bits = _dev.zeros((S * self.max_bursts * 2, 40), torch.uint8, device)
+        self.crc_ok = _dev.zeros((S * self.max_bursts * 2,), torch.uint8, device)
+        self.path_metric = _dev.zeros((S * self.max_bursts * 2,), torch.int32, device)
+        self.symbols = None
+
+    def run_device(self, iq, n_samples, scramb_init, threshold=0.8, keep_symbols=False):
+        """iq: CUDA float32 tensor [n_streams, stride, 2].  Asynchronous; results stay on the device."""
+        import torch
+        from . import _dev
+        n_streams, stride = iq.shape[0], iq.shape[1]
+        h, lib = self._h, self._h.lib
+        st = _dev.stream_ptr(self.device)
+        if keep_symbols and self.symbols is None:
+            self.symbols = _dev.zeros((self.max_streams, self.max_sym, 2), torch.float32, self.device)
+        self.metric.zero_()
+        _lib.check(lib.tb200_etsi_demod_batch(h.h, iq.data_ptr(), n_streams, int(n_samples), int(stride), self.fs,
+                                              self.symbols.data_ptr() if keep_symbols else None, self.soft.data_ptr(),
+                                              self.soft_stride, self.n_soft.data_ptr(), st))
+        _lib.check(lib.tb200_etsi_find_bursts(h.h, self.soft.data_ptr(), n_streams, self.soft_stride, self.n_soft.data_ptr(),
+                                              float(threshold), self.metric.data_ptr(), self.blocks.data_ptr(),
+                                              self.burst_pos.data_ptr(), self.n_bursts.data_ptr(), self.max_bursts, st))
+        nblk = n_streams * self.max_bursts * 2
+        _lib.check(lib.tb200_etsi_decode_batch(h.h, self.blocks.data_ptr(), nblk, 0, int(scramb_init) & 0xFFFFFFFF,
+                                               self.bits.data_ptr(), self.crc_ok.data_ptr(), self.path_metric.data_ptr(), st))
+        return n_streams
+
+    def run(self, iq, scramb_init, threshold=0.8):
+        """numpy complex64 [n_streams, n] -> list per stream of dicts(start, blocks [2,124] bits, crc_ok [2])."""
+        from . import _dev
+        x = np.ascontiguousarray(iq, dtype=np.complex64)
+        if x.ndim == 1:
+            x = x[None, :]
+        d = _dev.to_dev(x.view(np.float32).reshape(x.shape[0], x.shape[1], 2), self.device)
+        S = self.run_device(d, x.shape[1], scramb_init, threshold)
+        nb = self.n_bursts.cpu().numpy()[:S]
+        pos = self.burst_pos.cpu().numpy()[:S]
+        bits = np.unpackbits(self.bits.cpu().numpy(), axis=1)[:, :124].reshape(self.max_streams, self.max_bursts, 2, 124)
+        ok = self.crc_ok.cpu().numpy().reshape(self.max_streams, self.max_bursts, 2).astype(bool)
+        out = []
+        for s in range(S):
+            out.append([{"start": int(pos[s, i]), "blocks": bits[s, i], "crc_ok": ok[s, i]} for i in range(int(nb[s]))])
+        return out
