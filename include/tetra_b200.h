@@ -60,6 +60,7 @@ typedef struct tb200_config {
     int32_t max_fft;      /* capacity of the PSD path (0 -> 4096) */
     int32_t max_bursts;   /* capacity of tb200_burst_batch_host staging (0 -> none) */
     int32_t max_stream_len; /* capacity: dibits per stream of the decoder entry points (0 -> derived) */
+    int32_t max_channels; /* capacity of tb200_channelize (0 -> no channelizer workspace) */
 } tb200_config;
 
 /* What process() will do for (sample_rate, chunk_len): mirrors the control flow of
@@ -186,6 +187,14 @@ int tb200_crc16_rows(tb200_handle h, const uint8_t *d_bits, int n_rows, int n_bi
  * d_bits [n][40]: decoded type-1 bits packed MSB-first; d_crc_ok [n]; d_metric [n] final path metric. */
 int tb200_etsi_decode_batch(tb200_handle h, const int8_t *d_soft, int64_t n, int channel, uint32_t scramb_init,
                             uint8_t *d_bits, uint8_t *d_crc_ok, int32_t *d_metric, void *stream);
+
+/* `etsi` mode polyphase FIR channelizer (parity unpinned, SURVEY.md G1/G9: the reference has none):
+ * wideband complex64 at fs = n_channels x 25 kHz -> n_channels rows at 50 kHz (2x oversampled);
+ * row k is centred on k x 25 kHz (k >= n_channels/2 are the negative frequencies);
+ * frame m = sum_n x[n] h[m D - n] exp(-j 2 pi k n / M), D = M/2, h = Kaiser-windowed sinc of 6 M taps.
+ * d_out [n_channels][out_stride] complex64, n_frames <= out_stride frames written per row. */
+int tb200_channelize(tb200_handle h, const void *d_iq_c64, int64_t n_samples, int n_channels, void *d_out_c64,
+                     int64_t out_stride, int64_t n_frames, void *stream);
 
 /* `etsi` mode physical layer (parity unpinned): per stream (one 25 kHz channel at
  * fs in [36, 72] kHz, i.e. 2..4 samples/symbol): RRC(0.35) matched filter + closed-loop timing

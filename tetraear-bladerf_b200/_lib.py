@@ -19,7 +19,7 @@ MODE_EXACT, MODE_FAST = 0, 1
 class Config(C.Structure):
     _fields_ = [("sample_rate", C.c_double), ("max_chunks", C.c_int32), ("max_chunk_len", C.c_int32),
                 ("mode", C.c_int32), ("device", C.c_int32), ("max_fft", C.c_int32), ("max_bursts", C.c_int32),
-                ("max_stream_len", C.c_int32)]
+                ("max_stream_len", C.c_int32), ("max_channels", C.c_int32)]
 
 
 class Plan(C.Structure):
@@ -61,6 +61,7 @@ _PROTOS = {
     "tb200_etsi_decode_batch": (_i, [_vp, _vp, _i64, _i, C.c_uint32, _vp, _vp, _vp, _vp]),
     "tb200_etsi_demod_batch": (_i, [_vp, _vp, _i, _i64, _i64, _d, _vp, _vp, _i64, _vp, _vp]),
     "tb200_etsi_find_bursts": (_i, [_vp, _vp, _i, _i64, _vp, _d, _vp, _vp, _vp, _vp, _i, _vp]),
+    "tb200_channelize": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _i64, _vp]),
     "tb200_profile_enable": (_i, [_vp, _i]),
     "tb200_profile_read": (_i, [_vp, _vp, _vp]),
     "tb200_debug_read": (_i, [_vp, _i, _vp, C.c_size_t]),
@@ -112,10 +113,10 @@ class Handle:
     """RAII wrapper of tb200_handle."""
 
     def __init__(self, sample_rate=2.4e6, max_chunks=1, max_chunk_len=131072, mode=MODE_EXACT, device=0,
-                 max_fft=4096, max_bursts=0, max_stream_len=0):
+                 max_fft=4096, max_bursts=0, max_stream_len=0, max_channels=0):
         self.lib = require_device()
         self.cfg = Config(float(sample_rate), int(max_chunks), int(max_chunk_len), int(mode), int(device),
-                          int(max_fft), int(max_bursts), int(max_stream_len))
+                          int(max_fft), int(max_bursts), int(max_stream_len), int(max_channels))
         self.h = _vp()
         check(self.lib.tb200_create(C.byref(self.cfg), C.byref(self.h)))
 

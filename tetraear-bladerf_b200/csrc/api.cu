@@ -76,6 +76,9 @@ static size_t carve(tb200_handle h, char *base)
     size_t nf = (size_t)cfg.max_fft;
     h->psd_tables = c.take<double>((nf + 2 * (nf / 2 + nf / 4 + 1)) * sizeof(double));
     h->etsi_taps = c.take<float>(32 * 32 * sizeof(float));
+    size_t MC = (size_t)cfg.max_channels;
+    h->chan_proto = c.take<float>(MC * 6 * sizeof(float));
+    h->chan_tw = c.take<float>((MC + 256) * 2 * sizeof(float));
     // staging for *_host
     h->stage_in_bytes = C * L * 8;
     h->stage_in = c.take<char>(h->stage_in_bytes);
@@ -196,6 +199,7 @@ extern "C" int tb200_create(const tb200_config *cfg, tb200_handle *out)
     h->bits_stride = 2 * ((per_stream + 127) / 128 * 128);
     h->max_frames = (int)(h->bits_stride / 250 + 2);
     h->psd_tables_n = 0;
+    h->chan_M = 0;
     h->ws_bytes = carve(h, nullptr);
     cudaError_t e = cudaMalloc(&h->ws, h->ws_bytes);
     if (e != cudaSuccess) {
@@ -521,6 +525,17 @@ extern "C" int tb200_etsi_find_bursts(tb200_handle h, const float *d_soft, int n
     StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
     return launch_etsi_find_bursts(h, d_soft, n_streams, soft_stride, d_n_soft, (float)threshold, d_metric, d_blocks, d_burst_pos,
                                    d_n_bursts, max_bursts, (cudaStream_t)stream);
+}
+
+extern "C" int tb200_channelize(tb200_handle h, const void *d_iq_c64, int64_t n_samples, int n_channels, void *d_out_c64,
+                                int64_t out_stride, int64_t n_frames, void *stream)
+{
+    if (!h || !d_iq_c64 || !d_out_c64 || n_samples < 0 || n_channels < 2 || (n_channels & 1) || n_channels > h->cfg.max_channels)
+        return fail(TB200_E_ARG, "tb200_channelize: bad argument (n_channels must be even and <= the handle's max_channels)");
+    if (n_frames < 0 || n_frames > out_stride) return fail(TB200_E_ARG, "tb200_channelize: n_frames exceeds out_stride");
+    StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
+    return launch_channelizer(h, (const float2 *)d_iq_c64, n_samples, n_channels, h->chan_proto, (float2 *)h->chan_tw,
+                              (float2 *)d_out_c64, out_stride, n_frames, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------- PSD

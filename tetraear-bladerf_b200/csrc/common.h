@@ -74,6 +74,7 @@ struct tb200_handle_s {
     int32_t *sync_pos, *sync_cnt;             // [streams][max_frames], [2]
     // psd
     double *psd_tables; int psd_tables_n;
+    float *chan_proto, *chan_tw; int chan_M;   // channelizer prototype [6 M], twiddles, M they are for
     float *etsi_taps;                         // [32 phases][32 taps] interpolating matched filter
     // staging for the *_host entry points
     void *stage_in;   size_t stage_in_bytes;

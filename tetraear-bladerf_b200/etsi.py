@@ -271,3 +271,47 @@ class EtsiReceiver:
         for s in range(S):
             out.append([{"start": int(pos[s, i]), "blocks": bits[s, i], "crc_ok": ok[s, i]} for i in range(int(nb[s]))])
         return out
+
+
+CHANNEL_SPACING = 25000.0
+CHANNELIZER_TAPS_PER_BRANCH = 6
+
+
+def channelizer_prototype(M, beta=8.0):
+    """The prototype low-pass of tb200_channelize (Kaiser-windowed sinc, cutoff 25 kHz, 6 M taps, unit DC gain)."""
+    L = CHANNELIZER_TAPS_PER_BRANCH * M
+    t = np.arange(L) - (L - 1) / 2.0
+    h = 2.0 / M * np.sinc(2.0 / M * t) * np.kaiser(L, beta)
+    return h / h.sum()
+
+
+class Channelizer:
+    """Polyphase FIR channelizer: wideband complex64 at fs = M x 25 kHz -> [M, n_frames] at 50 kHz."""
+
+    def __init__(self, n_channels, device=0):
+        self.M = int(n_channels)
+        self.device = device
+        self.fs_in = self.M * CHANNEL_SPACING
+        self.fs_out = 2 * CHANNEL_SPACING
+        self._h = _lib.Handle(max_chunks=0, max_chunk_len=0, device=device, max_channels=self.M)
+
+    def n_frames(self, n_samples):
+        return (int(n_samples) - 1) // (self.M // 2) + 1 if n_samples > 0 else 0
+
+    def run_device(self, iq, n_samples, out=None):
+        """iq: CUDA float32 tensor [n_samples, 2]; returns CUDA float32 [M, n_frames, 2]."""
+        import torch
+        from . import _dev
+        nf = self.n_frames(n_samples)
+        if out is None:
+            out = _dev.empty((self.M, nf, 2), torch.float32, self.device)
+        h = self._h
+        _lib.check(h.lib.tb200_channelize(h.h, iq.data_ptr(), int(n_samples), self.M, out.data_ptr(), int(out.shape[1]), nf,
+                                          _dev.stream_ptr(self.device)))
+        return out
+
+    def run(self, x):
+        from . import _dev
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        d = _dev.to_dev(x.view(np.float32).reshape(-1, 2), self.device)
+        return self.run_device(d, len(x)).cpu().numpy().view(np.complex64)[..., 0]
