@@ -24,6 +24,9 @@ __constant__ uint8_t c_ts2[22] = {0,1,1,1,1,0,1,0,0,1,0,0,0,0,1,1,0,1,1,1,0,0}; 
 // folded in by the kernels (M^n * 0xFFFF) for the two payload lengths in use.
 __device__ uint16_t g_crc_tab[512];
 __device__ uint16_t g_crc_init[512];
+// CRC contribution of every 4-bit group of BURST bits, per burst type (0 normal, 1 sync) and payload
+// direction (0 forward, 1 reversed): g_crc_nib[type][dir][nibble 0..127][value 0..15]
+__device__ uint16_t g_crc_nib[2][2][128][16];
 static bool g_crc_ready[64] = {false};
 
 static void build_crc_tables(uint16_t *tab, uint16_t *init)
@@ -48,6 +51,22 @@ int ensure_crc_tables(int device)
     build_crc_tables(tab, init);
     TB_CUDA(cudaMemcpyToSymbol(g_crc_tab, tab, sizeof(tab)));
     TB_CUDA(cudaMemcpyToSymbol(g_crc_init, init, sizeof(init)));
+    static uint16_t nib[2][2][128][16];
+    for (int type = 0; type < 2; ++type) {
+        const int n_pay = type ? 494 : 200;
+        for (int j = 0; j < 128; ++j)
+            for (int v = 0; v < 16; ++v) {
+                uint16_t f = 0, r = 0;
+                for (int b = 0; b < 4; ++b) {
+                    if (!((v >> (3 - b)) & 1)) continue;
+                    int bi = 4 * j + b;                                    // burst bit index
+                    int d = type ? (bi < 510 ? bi : -1) : (bi < 108 ? bi : (bi >= 122 && bi < 230) ? bi - 14 : -1);
+                    if (d >= 0 && d < n_pay) { f ^= tab[n_pay - d]; r ^= tab[d + 1]; }
+                }
+                nib[type][0][j][v] = f; nib[type][1][j][v] = r;
+            }
+    }
+    TB_CUDA(cudaMemcpyToSymbol(g_crc_nib, nib, sizeof(nib)));
     g_crc_ready[device] = true;
     return TB200_OK;
 }
@@ -302,21 +321,130 @@ __device__ __forceinline__ unsigned load_burst_word(const uint8_t *__restrict__ 
     return w;
 }
 
-__global__ void burst_batch_kernel(const uint8_t *__restrict__ dibits, long n, uint8_t *__restrict__ rec,
-                                   uint8_t *__restrict__ full, unsigned long long *__restrict__ stats)
+// same for a row known to live in a buffer padded to a multiple of 8 bytes: two aligned 64-bit loads and
+// a funnel shift instead of eight byte loads
+__device__ __forceinline__ unsigned load_burst_word_fast(const uint8_t *__restrict__ base, long row_byte0, long total_bytes)
 {
-    __shared__ uint16_t tab[512];
+    const int lane = threadIdx.x & 31;
+    long a = row_byte0 + lane * 8;
+    long a0 = a & ~7L;
+    int sh = (int)(a & 7) * 8;
+    unsigned long long v;
+    if (a0 + 16 <= total_bytes) {
+        const unsigned long long *p = reinterpret_cast<const unsigned long long *>(base + a0);
+        unsigned long long lo = p[0], hi = p[1];
+        v = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;                     // bytes a .. a+7, little endian
+    } else {                                                                // last words of the buffer: stay in bounds
+        v = 0;
+        for (int k = 0; k < 8; ++k) if (a + k < total_bytes) v |= (unsigned long long)base[a + k] << (8 * k);
+    }
+    if (lane == 31) v &= 0x00FFFFFFFFFFFFFFull;                            // dibit 255 does not exist
+    v &= 0x0303030303030303ull;
+    // byte k (dibit k) -> bits 15-2k..14-2k
+    unsigned w = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w |= (unsigned)((v >> (8 * k)) & 3ull) << (14 - 2 * k);
+    return w;
+}
+
+// Leaner burst parse for the batch kernel: nibble CRC tables, hardware warp reductions, direct shuffles.
+__device__ __forceinline__ void warp_parse_burst_v2(unsigned w, const uint16_t (*__restrict__ nibtab)[2][128][16],
+                                                    const uint16_t *__restrict__ initv, uint8_t *__restrict__ rec,
+                                                    uint8_t *__restrict__ full, BurstOut &out)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    // bits 255..276: lane 15 bit 0, lane 16 all, lane 17 top 5
+    unsigned w15 = __shfl_sync(FULL, w, 15), w16 = __shfl_sync(FULL, w, 16), w17 = __shfl_sync(FULL, w, 17);
+    unsigned win = ((w15 & 1u) << 21) | (w16 << 5) | (w17 >> 11);
+    int mx = max(22 - __popc(win ^ SYNC_CONT_W), 22 - __popc(win ^ SYNC_DISC_W));
+    const bool is_sync = ((double)mx / 22.0) > 0.8;
+    const int type = is_sync ? 1 : 0;
+    const int n_data = is_sync ? 510 : 216, n_pay = n_data - 16;
+    // data-bit mask of this lane's 16 burst bits (normal: [0,108) ++ [122,230); sync: [0,510))
+    unsigned dmask;
+    {
+        int lo = lane * 16;
+        if (is_sync) dmask = (lane == 31) ? 0xFFFCu : 0xFFFFu;
+        else {
+            dmask = 0;
+            if (lo + 16 <= 108) dmask = 0xFFFFu;
+            else if (lo < 108) dmask = (0xFFFFu << (lo + 16 - 108)) & 0xFFFFu;         // lane 6: bits 96..107
+            if (lo >= 122 && lo + 16 <= 230) dmask = 0xFFFFu;
+            else if (lo < 122 && lo + 16 > 122) dmask |= 0xFFFFu >> (122 - lo);          // lane 7: bits 122..127
+            else if (lo < 230 && lo + 16 > 230) dmask = (0xFFFFu << (lo + 16 - 230)) & 0xFFFFu;   // lane 14: 224..229
+        }
+    }
+    int ones = __reduce_add_sync(FULL, __popc(w & dmask));
+    unsigned c = 0;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+        unsigned v = (w >> (12 - 4 * q4)) & 15u;
+        int j = lane * 4 + q4;
+        c ^= (unsigned)nibtab[type][0][j][v] | ((unsigned)nibtab[type][1][j][v] << 16);
+    }
+    c = __reduce_xor_sync(FULL, c);
+    unsigned cf = (c & 0xFFFFu) ^ initv[n_pay], cr = (c >> 16) ^ initv[n_pay];
+    unsigned w13 = __shfl_sync(FULL, w, 13), w14 = __shfl_sync(FULL, w, 14);
+    unsigned w30 = __shfl_sync(FULL, w, 30), w31 = __shfl_sync(FULL, w, 31);
+    unsigned rx = is_sync ? (((w30 & 3u) << 14) | (w31 >> 2)) : (((w13 & 0x3FFu) << 6) | (w14 >> 10));
+    bool crc_ok = false;
+    if (ones != 0 && ones != n_data) crc_ok = (__popc(cf ^ rx) <= 2) || (__popc(cr ^ rx) <= 2);
+    unsigned f0 = __shfl_sync(FULL, w, 0), f1 = __shfl_sync(FULL, w, 1), f2 = __shfl_sync(FULL, w, 2);
+    unsigned long long head = ((unsigned long long)f0 << 32) | ((unsigned long long)f1 << 16) | f2;
+    auto fld = [&](int lo, int nb) -> unsigned { return (unsigned)((head >> (48 - lo - nb)) & ((1ull << nb) - 1ull)); };
+    unsigned type2 = fld(0, 2), enc = fld(2, 2);
+    bool mac_ok;
+    if (type2 == 0) mac_ok = !((int)(fld(29, 6) * 8) > n_data - 35 + 16);
+    else if (type2 == 1) mac_ok = true;
+    else if (type2 == 2) { mac_ok = true; if (enc == 0) { unsigned mcc = fld(4, 10), mnc = fld(14, 14); mac_ok = !(mcc < 200 || mcc > 799 || mnc > 999); } }
+    else mac_ok = !((int)(fld(5, 6) * 8) > n_data - 11 + 16);
+    out.burst_type = is_sync ? 5u : 2u; out.crc_ok = crc_ok; out.mac_ok = mac_ok; out.hdr = (type2 << 2) | enc;
+    out.sync_match = (unsigned)mx;
+    // record: 27 packed data bytes + 5 flag bytes, one byte per lane -> the warp writes 32 contiguous bytes
+    unsigned byte;
+    {
+        int d0 = lane * 8;
+        int src = is_sync ? d0 : (d0 < 104 ? d0 : d0 + 14);
+        src = (lane < 27) ? src : 0;
+        unsigned hi = __shfl_sync(FULL, w, (src >> 4) & 31), lo = __shfl_sync(FULL, w, ((src >> 4) + 1) & 31);
+        unsigned both = (hi << 16) | lo;
+        byte = (both >> (24 - (src & 15))) & 0xFFu;
+        unsigned w6 = __shfl_sync(FULL, w, 6), w7 = __shfl_sync(FULL, w, 7);
+        if (!is_sync && lane == 13) byte = (((w6 >> 4) & 0xFu) << 4) | ((w7 >> 2) & 0xFu);   // bits 104..107 ++ 122..125
+        if (lane == 27) byte = out.burst_type;
+        if (lane == 28) byte = out.crc_ok;
+        if (lane == 29) byte = out.mac_ok;
+        if (lane == 30) byte = out.hdr;
+        if (lane == 31) byte = out.sync_match;
+    }
+    rec[lane] = (uint8_t)byte;
+    if (full) { full[2 * lane] = (uint8_t)(w >> 8); full[2 * lane + 1] = (uint8_t)(w & 0xff); }
+}
+
+__global__ void __launch_bounds__(256)
+burst_batch_kernel(const uint8_t *__restrict__ dibits, long n, uint8_t *__restrict__ rec,
+                   uint8_t *__restrict__ full, unsigned long long *__restrict__ stats)
+{
+    __shared__ uint16_t nibtab[2][2][128][16];
     __shared__ uint16_t initv[512];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) { tab[i] = g_crc_tab[i]; initv[i] = g_crc_init[i]; }
+    {
+        const uint16_t *src = &g_crc_nib[0][0][0][0];
+        uint16_t *dst = &nibtab[0][0][0][0];
+        for (int i = threadIdx.x; i < 2 * 2 * 128 * 16; i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) initv[i] = g_crc_init[i];
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
     long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
     unsigned pass = 0, total = 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dibits) & 7) == 0);
+    const long total_bytes = n * 255;
     for (long b = warp; b < n; b += nwarps) {
-        unsigned w = load_burst_word(dibits + b * 255);
+        unsigned w = aligned ? load_burst_word_fast(dibits, b * 255, total_bytes) : load_burst_word(dibits + b * 255);
         BurstOut o;
-        warp_parse_burst(w, tab, initv, rec ? rec + b * 32 : nullptr, full ? full + b * 64 : nullptr, o);
+        warp_parse_burst_v2(w, nibtab, initv, rec + b * 32, full ? full + b * 64 : nullptr, o);
         ++total;
         pass += o.crc_ok;
     }

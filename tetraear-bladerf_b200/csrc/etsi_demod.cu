@@ -98,7 +98,8 @@ __global__ void etsi_ts_corr_kernel(const float *__restrict__ soft, long soft_st
     const float *b = soft + (long)s * soft_stride + p;
     float c0 = 0.f, c1 = 0.f, en = 0.f;
 #pragma unroll
-    for (int i = 0; i < 22; ++i) { float v = b[i]; c0 += v * c_ts_pm[0][i]; c1 += v * c_ts_pm[1][i]; en += fabsf(v); }
+    // soft bits are normalised to ~0.7: clip so that a few large noise products cannot fake a match
+    for (int i = 0; i < 22; ++i) { float v = fminf(fmaxf(b[i], -1.0f), 1.0f); c0 += v * c_ts_pm[0][i]; c1 += v * c_ts_pm[1][i]; en += fabsf(v); }
     float best = fmaxf(c0, c1) / (en + 1e-20f);
     metric[(long)s * (soft_stride / 2) + p / 2] = (c1 > c0) ? -best : best;     // sign carries the sequence id
 }
