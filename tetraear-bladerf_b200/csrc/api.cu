@@ -447,6 +447,10 @@ extern "C" int tb200_decode_batch(tb200_handle h, const uint8_t *d_dibits, int n
         return fail(TB200_E_ARG, "tb200_decode_batch: max_frames too large for the handle");
     if (stride == 0) { TB_CUDA(cudaMemsetAsync(d_n_frames, 0, sizeof(int32_t) * n_streams, st)); return TB200_OK; }
     int rc;
+    if (stride <= 6000 && max_frames <= 64) {          // one chunk's worth: fused single-launch path (42 KB smem)
+        StageTimer tm(h, TB_STAGE_DECODE, st);
+        return launch_decode_fused(h, d_dibits, n_streams, stride, d_n_dibits, d_frames, max_frames, d_n_frames, d_stats, st);
+    }
     {
         StageTimer tm(h, TB_STAGE_BITS_SYNC, st);
         rc = launch_symbols_to_bits(h, d_dibits, n_streams, stride, d_n_dibits, 0, h->bits, h->mapped, bstride, st);

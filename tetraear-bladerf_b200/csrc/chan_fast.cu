@@ -97,26 +97,30 @@ chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per
 #pragma unroll
     for (int r = 0; r < CF_R; ++r) { yI[r] = K.c0p * xs[r].x; yQ[r] = K.c0p * xs[r].y; }
 
+    // both modes and both components advance together: four independent recurrences per direction
+    const cdd p0 = ldd(K.p[0]), p1 = ldd(K.p[1]), a0 = ldd(K.a[0]), a1 = ldd(K.a[1]);
+    if (do_F) {
+        cdd sI0 = cdd{0.0, 0.0}, sQ0 = sI0, sI1 = sI0, sQ1 = sI0;
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
-        const cdd p = ldd(K.p[m]), a = ldd(K.a[m]);
-        if (do_F) {
-            cdd sI = cdd{0.0, 0.0}, sQ = cdd{0.0, 0.0};
+        for (int r = 0; r < CF_R; ++r) {
+            sI0 = cmuld(p0, sI0); sI0.x += xs[r].x;
+            sQ0 = cmuld(p0, sQ0); sQ0.x += xs[r].y;
+            sI1 = cmuld(p1, sI1); sI1.x += xs[r].x;
+            sQ1 = cmuld(p1, sQ1); sQ1.x += xs[r].y;
+            yI[r] += 2.0 * (a0.x * sI0.x - a0.y * sI0.y + a1.x * sI1.x - a1.y * sI1.y);
+            yQ[r] += 2.0 * (a0.x * sQ0.x - a0.y * sQ0.y + a1.x * sQ1.x - a1.y * sQ1.y);
+        }
+        cdd sI[2] = {sI0, sI1}, sQ[2] = {sQ0, sQ1};
 #pragma unroll
-            for (int r = 0; r < CF_R; ++r) {
-                sI = cmuld(p, sI); sI.x += xs[r].x;
-                sQ = cmuld(p, sQ); sQ.x += xs[r].y;
-                yI[r] += 2.0 * (a.x * sI.x - a.y * sI.y);
-                yQ[r] += 2.0 * (a.x * sQ.x - a.y * sQ.y);
-            }
+        for (int m = 0; m < 2; ++m) {
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
-                cdd oI = dshfl_up(sI, 1 << s), oQ = dshfl_up(sQ, 1 << s);
-                if (lane >= (1 << s)) { cdd g = ldd(K.ppow[s][m]); sI = cfmad(g, oI, sI); sQ = cfmad(g, oQ, sQ); }
+                cdd oI = dshfl_up(sI[m], 1 << s), oQ = dshfl_up(sQ[m], 1 << s);
+                if (lane >= (1 << s)) { cdd g = ldd(K.ppow[s][m]); sI[m] = cfmad(g, oI, sI[m]); sQ[m] = cfmad(g, oQ, sQ[m]); }
             }
-            cdd cI = dshfl_up(sI, 1), cQ = dshfl_up(sQ, 1);
+            cdd cI = dshfl_up(sI[m], 1), cQ = dshfl_up(sQ[m], 1);
             if (lane == 0) cI = cQ = cdd{0.0, 0.0};
-            if (lane == 31) { carryF[w][0][m] = sI; carryF[w][1][m] = sQ; }
+            if (lane == 31) { carryF[w][0][m] = sI[m]; carryF[w][1][m] = sQ[m]; }
 #pragma unroll
             for (int r = 0; r < CF_R; ++r) {
                 const cdd af = ldd(K.aF[r][m]);
@@ -124,23 +128,29 @@ chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per
                 yQ[r] += 2.0 * (af.x * cQ.x - af.y * cQ.y);
             }
         }
-        if (do_B) {
-            cdd sI = cdd{0.0, 0.0}, sQ = cdd{0.0, 0.0};
+    }
+    if (do_B) {
+        cdd sI0 = cdd{0.0, 0.0}, sQ0 = sI0, sI1 = sI0, sQ1 = sI0;
 #pragma unroll
-            for (int r = CF_R - 1; r >= 0; --r) {
-                sI = cmuld(p, sI); sI.x += xs[r].x;
-                sQ = cmuld(p, sQ); sQ.x += xs[r].y;
-                yI[r] += 2.0 * (a.x * sI.x - a.y * sI.y);
-                yQ[r] += 2.0 * (a.x * sQ.x - a.y * sQ.y);
-            }
+        for (int r = CF_R - 1; r >= 0; --r) {
+            sI0 = cmuld(p0, sI0); sI0.x += xs[r].x;
+            sQ0 = cmuld(p0, sQ0); sQ0.x += xs[r].y;
+            sI1 = cmuld(p1, sI1); sI1.x += xs[r].x;
+            sQ1 = cmuld(p1, sQ1); sQ1.x += xs[r].y;
+            yI[r] += 2.0 * (a0.x * sI0.x - a0.y * sI0.y + a1.x * sI1.x - a1.y * sI1.y);
+            yQ[r] += 2.0 * (a0.x * sQ0.x - a0.y * sQ0.y + a1.x * sQ1.x - a1.y * sQ1.y);
+        }
+        cdd sI[2] = {sI0, sI1}, sQ[2] = {sQ0, sQ1};
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
-                cdd oI = dshfl_down(sI, 1 << s), oQ = dshfl_down(sQ, 1 << s);
-                if (lane + (1 << s) < 32) { cdd g = ldd(K.ppow[s][m]); sI = cfmad(g, oI, sI); sQ = cfmad(g, oQ, sQ); }
+                cdd oI = dshfl_down(sI[m], 1 << s), oQ = dshfl_down(sQ[m], 1 << s);
+                if (lane + (1 << s) < 32) { cdd g = ldd(K.ppow[s][m]); sI[m] = cfmad(g, oI, sI[m]); sQ[m] = cfmad(g, oQ, sQ[m]); }
             }
-            cdd cI = dshfl_down(sI, 1), cQ = dshfl_down(sQ, 1);
+            cdd cI = dshfl_down(sI[m], 1), cQ = dshfl_down(sQ[m], 1);
             if (lane == 31) cI = cQ = cdd{0.0, 0.0};
-            if (lane == 0) { carryB[w][0][m] = sI; carryB[w][1][m] = sQ; }
+            if (lane == 0) { carryB[w][0][m] = sI[m]; carryB[w][1][m] = sQ[m]; }
 #pragma unroll
             for (int r = 0; r < CF_R; ++r) {
                 const cdd ab = ldd(K.aB[r][m]);
@@ -233,8 +243,12 @@ __global__ void chan_fast_edge_kernel(const TI *__restrict__ x, long n, long in_
 #pragma unroll
     for (int j = 0; j < 2; ++j) sI[j] = sQ[j] = cdd{0.0, 0.0};
     const long tbeg = M - 32L * CF_EDGE_S + (long)lane * CF_EDGE_S;
+    cdd ev[CF_EDGE_S];
+#pragma unroll
+    for (int i = 0; i < CF_EDGE_S; ++i) ev[i] = chan_padded<TI>(xc, n, tbeg + i, W, fs);
+#pragma unroll
     for (int i = 0; i < CF_EDGE_S; ++i) {
-        cdd e = chan_padded<TI>(xc, n, tbeg + i, W, fs);
+        const cdd e = ev[i];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             cdd pj = ldd(K.p[j]);
@@ -274,8 +288,20 @@ __global__ void chan_fast_edge_kernel(const TI *__restrict__ x, long n, long in_
         l32[j] = b;
     }
     double2 *out = reinterpret_cast<double2 *>(filtered) + (long)chunk * out_stride;
-    for (int mm = lane; mm < CF_FIX; mm += 32) {
-        long k = n - 1 - mm;
+    constexpr int NIT = CF_FIX / 32;
+    // read-modify-write of this lane's tail outputs: all loads first, then the corrections; the corrected
+    // powers stay in registers for the per-phase tail sums
+    double2 yv[NIT];
+    int phv[NIT];
+    const int ni = (int)n;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        long k = n - 1 - (lane + 32 * it);
+        yv[it] = (k >= 0) ? out[k] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        long k = n - 1 - (lane + 32 * it);
         double cI = 0.0, cQ = 0.0;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -283,18 +309,21 @@ __global__ void chan_fast_edge_kernel(const TI *__restrict__ x, long n, long in_
             cQ += kQ[j].x * lp[j].x - kQ[j].y * lp[j].y;
             lp[j] = cmuld(lp[j], l32[j]);
         }
-        if (k >= 0) { double2 v = out[k]; out[k] = make_double2(v.x - 2.0 * cI, v.y - 2.0 * cQ); }
+        yv[it].x -= 2.0 * cI; yv[it].y -= 2.0 * cQ;
+        phv[it] = -1;
+        if (k >= 0) {
+            out[k] = yv[it];
+            if (phase_tail) {
+                int ki = (int)k, kk = ki / sps, ph = ki - kk * sps;
+                if ((ph % step) == 0 && kk < (ni - ph) / sps) phv[it] = ph;
+            }
+        }
     }
     if (phase_tail) {
-        // power of the final (corrected) last CF_FIX samples, per phase, in a fixed order
-        __syncwarp();
         for (int ph = 0; ph < sps; ph += step) {
-            long cnt = (n - ph >= 0) ? (n - ph) / sps : 0;
             double v = 0.0;
-            for (int mm = lane; mm < CF_FIX; mm += 32) {
-                long k = n - 1 - mm;
-                if (k >= 0 && (k % sps) == ph && (k - ph) < cnt * sps) { double2 y = out[k]; v += y.x * y.x + y.y * y.y; }
-            }
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) v += (phv[it] == ph) ? (yv[it].x * yv[it].x + yv[it].y * yv[it].y) : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0) phase_tail[(long)chunk * TB200_MAX_PHASES + ph] = v;

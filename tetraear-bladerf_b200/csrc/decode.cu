@@ -456,26 +456,15 @@ burst_batch_kernel(const uint8_t *__restrict__ dibits, long n, uint8_t *__restri
 }
 
 // ------------------------------------------------------------------ TetraDecoder.decode, one warp per stream
-__global__ void decode_kernel(const uint8_t *__restrict__ bits, const uint8_t *__restrict__ mapped,
-                              const uint8_t *__restrict__ m1, const uint8_t *__restrict__ m2, int n_streams,
-                              long bits_stride, const int32_t *__restrict__ n_sym, tb200_frame *__restrict__ frames,
-                              int max_frames, int32_t *__restrict__ n_frames, unsigned long long *__restrict__ stats,
-                              int32_t *__restrict__ pos_scratch)
+// decode() of ONE stream by one full warp: b = bit row, mp = mapped symbols, c1/c2 = match counts
+// (global or shared memory), pos = scratch for max_frames sync positions.
+__device__ void decode_stream_warp(const uint8_t *b, const uint8_t *mp, const uint8_t *c1, const uint8_t *c2, long nsym,
+                                   const uint16_t *tab, const uint16_t *initv, tb200_frame *__restrict__ fo, int max_frames,
+                                   int32_t *__restrict__ n_frames_out, unsigned long long *__restrict__ stats, int32_t *pos)
 {
-    __shared__ uint16_t tab[512];
-    __shared__ uint16_t initv[512];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) { tab[i] = g_crc_tab[i]; initv[i] = g_crc_init[i]; }
-    __syncthreads();
     const int lane = threadIdx.x & 31;
-    int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (s >= n_streams) return;
-    long nsym = n_sym[s];
     long nb = 2 * nsym;
     long nwin = nb - 21;
-    const uint8_t *b = bits + (long)s * bits_stride;
-    const uint8_t *mp = mapped + (long)s * (bits_stride / 2);
-    const uint8_t *c1 = m1 + (long)s * bits_stride, *c2 = m2 + (long)s * bits_stride;
-    int32_t *pos = pos_scratch + (long)s * max_frames;
     // threshold cascade, decoder.py:845-856
     int mm;
     int cnt = warp_find_sync(c1, c2, nwin, 0.90, pos, max_frames, &mm);
@@ -490,7 +479,6 @@ __global__ void decode_kernel(const uint8_t *__restrict__ bits, const uint8_t *_
     if (cnt > max_frames) cnt = max_frames;
     __syncwarp();
     unsigned total = 0, pass = 0;
-    tb200_frame *fo = frames + (long)s * max_frames;
     for (int f = 0; f < cnt; ++f) {
         int p = pos[f];
         long start_pos = (long)p - 216;
@@ -533,13 +521,80 @@ __global__ void decode_kernel(const uint8_t *__restrict__ bits, const uint8_t *_
         }
     }
     if (lane == 0) {
-        n_frames[s] = cnt;
+        *n_frames_out = cnt;
         if (stats && total) {
             atomicAdd(&stats[0], (unsigned long long)total);
             atomicAdd(&stats[1], (unsigned long long)pass);
             atomicAdd(&stats[2], (unsigned long long)(total - pass));
         }
     }
+}
+
+__global__ void decode_kernel(const uint8_t *__restrict__ bits, const uint8_t *__restrict__ mapped,
+                              const uint8_t *__restrict__ m1, const uint8_t *__restrict__ m2, int n_streams,
+                              long bits_stride, const int32_t *__restrict__ n_sym, tb200_frame *__restrict__ frames,
+                              int max_frames, int32_t *__restrict__ n_frames, unsigned long long *__restrict__ stats,
+                              int32_t *__restrict__ pos_scratch)
+{
+    __shared__ uint16_t tab[512];
+    __shared__ uint16_t initv[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { tab[i] = g_crc_tab[i]; initv[i] = g_crc_init[i]; }
+    __syncthreads();
+    int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= n_streams) return;
+    decode_stream_warp(bits + (long)s * bits_stride, mapped + (long)s * (bits_stride / 2), m1 + (long)s * bits_stride,
+                       m2 + (long)s * bits_stride, n_sym[s], tab, initv, frames + (long)s * max_frames, max_frames,
+                       n_frames + s, stats, pos_scratch + (long)s * max_frames);
+}
+
+// Fused variant for short streams (one chunk of process() output): symbols_to_bits, both 22-bit
+// correlations and decode() in ONE launch, every intermediate in shared memory.  One CTA per stream.
+__global__ void __launch_bounds__(128)
+decode_fused_kernel(const uint8_t *__restrict__ dibits, int n_streams, long stride, const int32_t *__restrict__ n_sym,
+                    tb200_frame *__restrict__ frames, int max_frames, int32_t *__restrict__ n_frames,
+                    unsigned long long *__restrict__ stats)
+{
+    extern __shared__ uint8_t dsm[];
+    __shared__ uint16_t tab[512];
+    __shared__ uint16_t initv[512];
+    __shared__ int s_max;
+    __shared__ int32_t pos_sm[64];
+    const int s = blockIdx.x;
+    const long n = n_sym[s];
+    uint8_t *mp = dsm;                       // [stride]
+    uint8_t *b = mp + stride;                // [2 stride]
+    uint8_t *c1 = b + 2 * stride;            // [2 stride]
+    uint8_t *c2 = c1 + 2 * stride;           // [2 stride]
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { tab[i] = g_crc_tab[i]; initv[i] = g_crc_init[i]; }
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    const uint8_t *in = dibits + (long)s * stride;
+    int mx = 0;
+    for (long i = threadIdx.x; i < n; i += blockDim.x) { int v = in[i]; mp[i] = (uint8_t)v; mx = max(mx, v); }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_max, mx);
+    __syncthreads();
+    const bool dqpsk = s_max <= 3;
+    for (long i = threadIdx.x; i < n; i += blockDim.x) {
+        int v = mp[i];
+        if (dqpsk) v &= 3;
+        else v = (v <= 2) ? 0 : (v <= 4) ? 1 : (v == 5) ? 3 : (v <= 7) ? 2 : 0;
+        mp[i] = (uint8_t)v;
+        b[2 * i] = (uint8_t)(v >> 1);
+        b[2 * i + 1] = (uint8_t)(v & 1);
+    }
+    __syncthreads();
+    const long nwin = 2 * n - 21;
+    for (long p = threadIdx.x; p < nwin; p += blockDim.x) {
+        int a1 = 0, a2 = 0;
+#pragma unroll
+        for (int k = 0; k < 22; ++k) { int v = b[p + k]; a1 += (v == c_ts1[k]); a2 += (v == c_ts2[k]); }
+        c1[p] = (uint8_t)a1; c2[p] = (uint8_t)a2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32)
+        decode_stream_warp(b, mp, c1, c2, n, tab, initv, frames + (long)s * max_frames, max_frames < 64 ? max_frames : 64,
+                           n_frames + s, stats, pos_sm);
 }
 
 // _calculate_crc16 of bit rows (one byte per bit), one warp per row
@@ -600,6 +655,17 @@ int launch_decode(tb200_handle h, const uint8_t *bits, const uint8_t *mapped, co
     int blocks = (n_streams * 32 + threads - 1) / threads;
     decode_kernel<<<blocks, threads, 0, st>>>(bits, mapped, m1, m2, n_streams, bits_stride, n_sym, frames, max_frames,
                                               n_frames, (unsigned long long *)stats, h->sync_pos);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+int launch_decode_fused(tb200_handle h, const uint8_t *dibits, int n_streams, long stride, const int32_t *n_sym,
+                        tb200_frame *frames, int max_frames, int32_t *n_frames, int64_t *stats, cudaStream_t st)
+{
+    if (n_streams <= 0) return TB200_OK;
+    size_t smem = 7 * (size_t)stride;
+    decode_fused_kernel<<<n_streams, 128, smem, st>>>(dibits, n_streams, stride, n_sym, frames, max_frames, n_frames,
+                                                     (unsigned long long *)stats);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
 }

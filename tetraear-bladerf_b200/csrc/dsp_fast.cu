@@ -50,6 +50,7 @@ struct FastDecimParams {
     float kMc[4][4][2];
     float pc[4][2];                  // p_i^(M - n_last)
     float pS[5][4][2];               // (p_i^S)^(2^s): lane-combine multipliers of the edge kernel
+    float lanepow[32][4][2];         // lambda_i^(R lane): cross-pass carry weights
 };
 
 struct cf { float x, y; };
@@ -148,6 +149,8 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
     extern __shared__ float2 fd_tile[];
     __shared__ cf carryF[FD_W][2][4];
     __shared__ cf carryB[FD_W][2][4];
+    __shared__ cf lanepow[32][4];
+    if (threadIdx.x < 128) lanepow[threadIdx.x >> 2][threadIdx.x & 3] = ld2(K.lanepow[threadIdx.x >> 2][threadIdx.x & 3]);
 
     const int chunk = blockIdx.x / tiles_per_chunk;
     const int tile = blockIdx.x - chunk * tiles_per_chunk;
@@ -160,10 +163,13 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
     // ---- stage the tile.  Interior tiles: asynchronous 8-byte global->shared copies (no registers, all
     // in flight at once); tiles touching a chunk end synthesise the odd extension sample by sample.
     if (t0 >= 27 && t0 + (long)ROWS * Q <= 27 + n) {
-        const float2 *src = xc + (t0 - 27);
-        for (int s = threadIdx.x; s < ROWS * Q; s += blockDim.x) {
-            int row = s / Q, col = s - row * Q;
-            cp_async8(&fd_tile[row * PITCH + col], src + s);
+        // thread -> fixed column, rows RPS apart: one address add per copy, no divisions in the loop
+        constexpr int RPS = (FD_W * 32) / Q;
+        const int row_first = threadIdx.x / Q, col = threadIdx.x - row_first * Q;
+        if (row_first < RPS) {
+            const float2 *src = xc + (t0 - 27) + col;
+            float2 *dst = fd_tile + col;
+            for (int row = row_first; row < ROWS; row += RPS) cp_async8(dst + row * PITCH, src + row * Q);
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -193,13 +199,7 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
     // ---- carries from the neighbour passes: lambda^(lane R) cF on the left, lambda^((31-lane) R) cB on the right
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-        cf LF = cf{1.f, 0.f}, LB = cf{1.f, 0.f};
-#pragma unroll
-        for (int s = 0; s < 5; ++s) {
-            cf g = ld2(K.lampow[s][m]);
-            if (lane & (1 << s)) LF = cmulf(LF, g);
-            if ((31 - lane) & (1 << s)) LB = cmulf(LB, g);
-        }
+        const cf LF = lanepow[lane][m], LB = lanepow[31 - lane][m];
         cf gFI = cmulf(LF, carryF[w - 1][0][m]), gFQ = cmulf(LF, carryF[w - 1][1][m]);
         cf gBI = cmulf(LB, carryB[w + 1][0][m]), gBQ = cmulf(LB, carryB[w + 1][1][m]);
 #pragma unroll
@@ -239,9 +239,12 @@ __global__ void decim_fast_edge_kernel(const float2 *__restrict__ x, long n, lon
 #pragma unroll
     for (int j = 0; j < 4; ++j) sI[j] = sQ[j] = cf{0.f, 0.f};
     const long tbeg = M - 32L * FD_EDGE_S + (long)lane * FD_EDGE_S;
-#pragma unroll 2
+    float2 ev[FD_EDGE_S];
+#pragma unroll
+    for (int i = 0; i < FD_EDGE_S; ++i) ev[i] = padded_sample(xc, n, tbeg + i);
+#pragma unroll
     for (int i = 0; i < FD_EDGE_S; ++i) {
-        float2 e = padded_sample(xc, n, tbeg + i);
+        const float2 e = ev[i];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             cf pj = ld2(K.p[j]);
@@ -290,8 +293,12 @@ __global__ void decim_fast_edge_kernel(const float2 *__restrict__ x, long n, lon
         lp[j] = cmulf(a, ld2(K.pc[j]));      // pc lambda^lane
         l32[j] = b;                           // lambda^32
     }
-    for (int mm = lane; mm < n_fix; mm += 32) {
-        long k = n_dec - 1 - mm;
+    float2 ov[5];
+#pragma unroll
+    for (int it = 0; it < 5; ++it) { long k = n_dec - 1 - (lane + 32 * it); ov[it] = (k >= 0) ? out[k] : make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+        long k = n_dec - 1 - (lane + 32 * it);
         float cI = 0.f, cQ = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -299,8 +306,10 @@ __global__ void decim_fast_edge_kernel(const float2 *__restrict__ x, long n, lon
             cQ += kQ[j].x * lp[j].x - kQ[j].y * lp[j].y;
             lp[j] = cmulf(lp[j], l32[j]);
         }
-        if (k >= 0) { float2 v = out[k]; out[k] = make_float2(v.x - 2.0f * cI, v.y - 2.0f * cQ); }
+        if (k >= 0) out[k] = make_float2(ov[it].x - 2.0f * cI, ov[it].y - 2.0f * cQ);
     }
+    static_assert(5 * 32 == 160, "n_fix");
+    (void)n_fix;
     (void)q;
 }
 
@@ -350,6 +359,7 @@ static int make_fast_params(const DecimDesign &d, int q, long n, long n_dec, Fas
         }
         put(K.p[j], p8[j]);
         put(K.inv1mp[j], 1.0 / (1.0 - p8[j]));
+        for (int l = 0; l < 32; ++l) put(K.lanepow[l][j], std::pow(lam[j], FD_R * l));
         cd ps = std::pow(p8[j], FD_EDGE_S);
         for (int st = 0; st < 5; ++st) { put(K.pS[st][j], ps); ps *= ps; }
     }

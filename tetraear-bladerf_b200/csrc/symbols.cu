@@ -66,7 +66,34 @@ __global__ void symbols_kernel(const double *__restrict__ filtered, long n, long
     int best = 0;
     long num = n;
     long stride_s = 1;
-    if (n > 0 && sps > 1) {
+    __shared__ double s_pw[TB200_MAX_PHASES];
+    __shared__ int s_best;
+    if (n > 0 && sps > 1 && phase_partial) {
+        // phase powers already summed per (chunk, tile) by the channel-filter kernel: thread p adds its phase
+        if (threadIdx.x < sps) {
+            int p = threadIdx.x;
+            long cnt = (n - p >= 0) ? (n - p) / sps : -1;
+            double tot = -2.0;                                   // phases that do not count never win
+            if ((p % step) == 0 && cnt > 0) {
+                tot = 0.0;
+                for (int t = 0; t < n_tiles; ++t) tot += phase_partial[((long)chunk * n_tiles + t) * TB200_MAX_PHASES + p];
+                tot += phase_tail[(long)chunk * TB200_MAX_PHASES + p];
+                tot = tot / (double)cnt;
+            }
+            s_pw[p] = tot;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double max_power = -1.0;
+            int bb = 0;
+            for (int p = 0; p < sps; p += step) if (s_pw[p] > max_power) { max_power = s_pw[p]; bb = p; }   // first strict max
+            s_best = bb;
+        }
+        __syncthreads();
+        best = s_best;
+        num = (n - best) / sps;
+        stride_s = sps;
+    } else if (n > 0 && sps > 1) {
         double max_power = -1.0;
         for (int p = 0; p < sps; p += step) {
             long cnt = (n - p >= 0) ? (n - p) / sps : -1;
