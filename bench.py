@@ -273,7 +273,10 @@ def run_b200(args):
         "e2e": {"value": round(e2e, 3), "unit": "Msamples/s", "h2d_bytes_per_step": pipe.h2d_bytes(n_chunks),
                 "d2h_bytes_per_step": pipe.d2h_bytes(n_chunks), "ms_per_step": round(ms_e2e / args.steps, 4)},
         "roofline": {"bound": "hbm", "kernel": "decimator stage (cheby1 zero-phase IIR + ::q)", "achieved": round(achieved, 2),
-                     "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": None,
+                     "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
+                     # dram__bytes_read.sum + dram__bytes_write.sum of decim_fast_kernel<10>, one launch, ncu --set full
+                     # (profiles/r01_ncu_kernels_final.md); valid for the fast mode on this workload only
+                     "traffic": 208214272 if args.mode == "fast" else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "ms_per_launch": round(dec_launch_ms, 4),
                      "path_achieved_gbs": round(path_bytes / (step_ms / 1e3) / 1e9, 2),
