@@ -15,7 +15,7 @@ from . import _lib
 
 class ReceivePipeline:
     def __init__(self, sample_rate=2.4e6, chunk_len=131072, max_chunks=184, mode="exact", device=0,
-                 keep_symbols=False):
+                 keep_symbols=False, n_lanes=1):
         self.sample_rate = float(sample_rate)
         self.chunk_len = int(chunk_len)
         self.max_chunks = int(max_chunks)
@@ -23,8 +23,17 @@ class ReceivePipeline:
         self.dev = torch.device(f"cuda:{device}")
         self.mode = mode
         self.plan = _lib.plan(self.sample_rate, self.chunk_len)
-        self.h = _lib.Handle(sample_rate=self.sample_rate, max_chunks=self.max_chunks, max_chunk_len=self.chunk_len,
-                             mode={"exact": _lib.MODE_EXACT, "fast": _lib.MODE_FAST}[mode], device=device)
+        # n_lanes > 1: the batch is cut into n_lanes contiguous sub-batches, each with its own handle
+        # (workspace) and CUDA stream, so the latency-bound tail kernels of one sub-batch (edge fix,
+        # timing pick, sync search) overlap the bandwidth/FMA-bound kernels of the next.
+        self.n_lanes = max(1, int(n_lanes))
+        per = (self.max_chunks + self.n_lanes - 1) // self.n_lanes
+        self.lane_chunks = per
+        m = {"exact": _lib.MODE_EXACT, "fast": _lib.MODE_FAST}[mode]
+        self.handles = [_lib.Handle(sample_rate=self.sample_rate, max_chunks=per, max_chunk_len=self.chunk_len, mode=m,
+                                    device=device) for _ in range(self.n_lanes)]
+        self.h = self.handles[0]
+        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.n_lanes - 1)]
         C = self.max_chunks
         self.stride = int(self.plan.max_symbols) + 8
         self.max_frames = (2 * self.stride) // 250 + 2
@@ -42,18 +51,42 @@ class ReceivePipeline:
         """iq: CUDA tensor, float32 [n_chunks, chunk_len, 2] (interleaved complex64).  Asynchronous."""
         n_chunks = iq.shape[0]
         assert iq.is_cuda and iq.dtype == torch.float32 and iq.shape[1] == self.chunk_len and iq.is_contiguous()
-        stream = torch.cuda.current_stream(self.dev).cuda_stream
-        lib, h = self.h.lib, self.h.h
-        _lib.check(lib.tb200_process_batch(
-            h, iq.data_ptr(), _lib.DTYPE_C64, n_chunks, self.chunk_len, self.chunk_len,
-            freq_off.data_ptr() if freq_off is not None else None, self.dibits.data_ptr(),
-            self.symbols.data_ptr() if self.symbols is not None else None, self.stride,
-            self.n_dibits.data_ptr(), self.phase.data_ptr(), stream))
-        if decode:
-            _lib.check(lib.tb200_decode_batch(h, self.dibits.data_ptr(), n_chunks, self.stride, self.n_dibits.data_ptr(),
-                                              self.frames.data_ptr(), self.max_frames, self.n_frames.data_ptr(),
-                                              self.stats.data_ptr(), stream))
+        main = torch.cuda.current_stream(self.dev)
+        if self.n_lanes == 1 or n_chunks <= self.n_lanes:
+            self._run_slice(self.handles[0], main.cuda_stream, iq, freq_off, 0, n_chunks, decode)
+            return n_chunks
+        per = (n_chunks + self.n_lanes - 1) // self.n_lanes
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for li in range(self.n_lanes):
+            lo, hi = li * per, min(n_chunks, (li + 1) * per)
+            if lo >= hi:
+                break
+            st = main if li == 0 else self.streams[li - 1]
+            if li:
+                st.wait_event(fork)
+            self._run_slice(self.handles[li], st.cuda_stream, iq, freq_off, lo, hi, decode)
+            if li:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                main.wait_event(ev)
         return n_chunks
+
+    def _run_slice(self, handle, stream, iq, freq_off, lo, hi, decode):
+        lib, h = handle.lib, handle.h
+        n = hi - lo
+        esz = self.chunk_len * 8
+        sym_ptr = self.symbols.data_ptr() + lo * self.stride * 16 if self.symbols is not None else None
+        _lib.check(lib.tb200_process_batch(
+            h, iq.data_ptr() + lo * esz, _lib.DTYPE_C64, n, self.chunk_len, self.chunk_len,
+            freq_off.data_ptr() + lo * 8 if freq_off is not None else None, self.dibits.data_ptr() + lo * self.stride,
+            sym_ptr, self.stride, self.n_dibits.data_ptr() + lo * 4, self.phase.data_ptr() + lo * 4, stream))
+        if decode:
+            fsz = self.max_frames * _lib.FRAME_DTYPE.itemsize
+            _lib.check(lib.tb200_decode_batch(h, self.dibits.data_ptr() + lo * self.stride, n, self.stride,
+                                              self.n_dibits.data_ptr() + lo * 4, self.frames.data_ptr() + lo * fsz,
+                                              self.max_frames, self.n_frames.data_ptr() + lo * 4,
+                                              self.stats.data_ptr(), stream))
 
     # ---------------------------------------------------------------- host-buffer path (end to end)
     def run_host(self, iq_host, freq_off=None, decode=True):
@@ -70,16 +103,35 @@ class ReceivePipeline:
             self._host_frames = torch.empty(self.frames.shape, dtype=torch.uint8).pin_memory()
             self._host_ndib = torch.empty((self.max_chunks,), dtype=torch.int32).pin_memory()
         dev_iq = self._staging[:n_chunks]
-        dev_iq.copy_(iq_host, non_blocking=True)
         f = None
         if freq_off is not None:
             f = torch.as_tensor(np.asarray(freq_off, dtype=np.float64)).to(self.dev, non_blocking=True)
         self.stats.zero_()
-        self.run_device(dev_iq, f, decode=decode)
-        self._host_ndib[:n_chunks].copy_(self.n_dibits[:n_chunks], non_blocking=True)
+        main = torch.cuda.current_stream(self.dev)
+        lanes = self.n_lanes if n_chunks > self.n_lanes else 1
+        per = (n_chunks + lanes - 1) // lanes
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for li in range(lanes):
+            lo, hi = li * per, min(n_chunks, (li + 1) * per)
+            if lo >= hi:
+                break
+            st = main if li == 0 else self.streams[li - 1]
+            with torch.cuda.stream(st):
+                if li:
+                    st.wait_event(fork)
+                # H2D of this lane's chunks, its kernels, D2H of its results: lane i+1's copy overlaps lane i's kernels
+                dev_iq[lo:hi].copy_(iq_host[lo:hi], non_blocking=True)
+                self._run_slice(self.handles[li], st.cuda_stream, dev_iq, f, lo, hi, decode)
+                self._host_ndib[lo:hi].copy_(self.n_dibits[lo:hi], non_blocking=True)
+                if decode:
+                    self._host_nfr[lo:hi].copy_(self.n_frames[lo:hi], non_blocking=True)
+                    self._host_frames[lo:hi].copy_(self.frames[lo:hi], non_blocking=True)
+                if li:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    main.wait_event(ev)
         if decode:
-            self._host_nfr[:n_chunks].copy_(self.n_frames[:n_chunks], non_blocking=True)
-            self._host_frames[:n_chunks].copy_(self.frames[:n_chunks], non_blocking=True)
             self._host_stats.copy_(self.stats, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
         if not decode:
@@ -87,6 +139,22 @@ class ReceivePipeline:
         return (self._host_nfr[:n_chunks].numpy(),
                 self._host_frames[:n_chunks].numpy().view(_lib.FRAME_DTYPE).reshape(n_chunks, self.max_frames),
                 self._host_stats.numpy())
+
+    @property
+    def launches(self):
+        return sum(h.launches for h in self.handles)
+
+    def profile(self, on=True):
+        for h in self.handles:
+            h.profile(on)
+
+    def profile_read(self):
+        tot = {}
+        for h in self.handles:
+            for k, (ms, calls) in h.profile_read().items():
+                a = tot.get(k, (0.0, 0))
+                tot[k] = (a[0] + ms, a[1] + calls)
+        return tot
 
     def h2d_bytes(self, n_chunks):
         return n_chunks * self.chunk_len * 8
