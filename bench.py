@@ -279,7 +279,7 @@ def run_b200(args):
                      "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
                      # dram__bytes_read.sum + dram__bytes_write.sum of decim_fast_kernel<10>, one launch, ncu --set full
                      # (profiles/r01_ncu_kernels_final.md); valid for the fast mode on this workload only
-                     "traffic": 208214272 if args.mode == "fast" else None,
+                     "traffic": 208214272 if args.mode.startswith("fast") else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "ms_per_launch": round(dec_launch_ms, 4),
                      "path_achieved_gbs": round(path_bytes / (step_ms / 1e3) / 1e9, 2),
@@ -444,7 +444,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("TB200_BENCH_LANES", "2")),
                     help="sub-batches processed on concurrent streams (overlaps the latency-bound tail kernels)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("TB200_BENCH_MODE", "fast"), choices=["exact", "fast"])
+    ap.add_argument("--mode", default=os.environ.get("TB200_BENCH_MODE", "fast"), choices=["exact", "fast", "fast32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the other-workload kernel figures")
     args = ap.parse_args()

@@ -110,6 +110,12 @@ int tb200_plan_process(double sample_rate, int chunk_len, tb200_plan *plan);
 int tb200_create(const tb200_config *cfg, tb200_handle *out);
 int tb200_destroy(tb200_handle h);
 int tb200_set_sample_rate(tb200_handle h, double sample_rate); /* attr is mutated live, modern.py:1857 */
+/* options: TB200_OPT_CHAN_F32 = 1: in FAST mode evaluate the Butterworth channel filter's recurrences in
+ * float32 instead of float64 (soft symbols then agree with the reference to ~1e-6 of full scale instead
+ * of ~1e-13 for that stage; the 1e-4 budget of FAST mode is dominated by the reference's own float32
+ * decimator either way).  Default 0. */
+#define TB200_OPT_CHAN_F32 1
+int tb200_set_option(tb200_handle h, int option, int value);
 size_t tb200_workspace_bytes(tb200_handle h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t tb200_launch_count(tb200_handle h);

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtetra_b200.so")
 
 DTYPE_C64, DTYPE_C128 = 0, 1
 MODE_EXACT, MODE_FAST = 0, 1
+OPT_CHAN_F32 = 1
 
 
 class Config(C.Structure):
@@ -43,6 +44,7 @@ _PROTOS = {
     "tb200_create": (_i, [C.POINTER(Config), C.POINTER(_vp)]),
     "tb200_destroy": (_i, [_vp]),
     "tb200_set_sample_rate": (_i, [_vp, _d]),
+    "tb200_set_option": (_i, [_vp, _i, _i]),
     "tb200_workspace_bytes": (C.c_size_t, [_vp]),
     "tb200_launch_count": (_i64, [_vp]),
     "tb200_process_batch": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
@@ -130,6 +132,9 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+    def set_option(self, option, value):
+        check(self.lib.tb200_set_option(self.h, int(option), int(value)))
 
     def profile(self, on=True):
         check(self.lib.tb200_profile_enable(self.h, int(on)))

@@ -243,6 +243,15 @@ extern "C" int tb200_set_sample_rate(tb200_handle h, double sample_rate)
     return TB200_OK;
 }
 
+extern "C" int tb200_set_option(tb200_handle h, int option, int value)
+{
+    if (!h) return fail(TB200_E_ARG, "tb200_set_option: null handle");
+    switch (option) {
+    case TB200_OPT_CHAN_F32: h->chan_f32 = value ? 1 : 0; return TB200_OK;
+    default: return fail(TB200_E_ARG, "tb200_set_option: unknown option %d", option);
+    }
+}
+
 extern "C" size_t tb200_workspace_bytes(tb200_handle h) { return h ? h->ws_bytes : 0; }
 extern "C" int64_t tb200_launch_count(tb200_handle h) { return h ? h->launches : 0; }
 

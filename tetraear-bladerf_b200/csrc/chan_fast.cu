@@ -43,6 +43,14 @@ __device__ __forceinline__ cdd dshfl_down(cdd v, int d) { return cdd{__shfl_down
 __device__ __forceinline__ cdd dshfl(cdd v, int l) { return cdd{__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l)}; }
 __device__ __forceinline__ cdd ldd(const double c[2]) { return cdd{c[0], c[1]}; }
 
+// working precision of the main kernel: double (default) or float (TB200 "fast32" channel filter)
+template <typename T> struct cx { T x, y; };
+template <typename T> __device__ __forceinline__ cx<T> cxmul(cx<T> a, cx<T> b) { return cx<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+template <typename T> __device__ __forceinline__ cx<T> cxfma(cx<T> a, cx<T> b, cx<T> c) { return cx<T>{a.x * b.x - a.y * b.y + c.x, a.x * b.y + a.y * b.x + c.y}; }
+template <typename T> __device__ __forceinline__ cx<T> cxup(cx<T> v, int d) { return cx<T>{__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d)}; }
+template <typename T> __device__ __forceinline__ cx<T> cxdown(cx<T> v, int d) { return cx<T>{__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d)}; }
+template <typename T> __device__ __forceinline__ cx<T> cxld(const double c[2]) { return cx<T>{(T)c[0], (T)c[1]}; }
+
 // sample i of the chunk after the optional NCO, complex128
 template <typename TI>
 __device__ __forceinline__ cdd nco_sample(const TI *__restrict__ x, long i, double W, double fs)
@@ -71,14 +79,15 @@ __device__ __forceinline__ cdd chan_padded(const TI *__restrict__ x, long n, lon
     return cdd{__dsub_rn(__dmul_rn(2.0, e.x), v.x), __dsub_rn(__dmul_rn(2.0, e.y), v.y)};
 }
 
-template <typename TI>
+template <typename TI, typename T>
 __global__ void __launch_bounds__(CF_W * 32)
 chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per_chunk,
                  const double *__restrict__ freq_off, double fs, ChanFastParams K,
                  double *__restrict__ filtered, long out_stride, double *__restrict__ phase_partial, int sps, int step)
 {
-    __shared__ cdd carryF[CF_W][2][2];
-    __shared__ cdd carryB[CF_W][2][2];
+    typedef cx<T> C;
+    __shared__ C carryF[CF_W][2][2];
+    __shared__ C carryB[CF_W][2][2];
     __shared__ double phacc[CF_W][TB200_MAX_PHASES];
     const int chunk = blockIdx.x / tiles_per_chunk;
     const int tile = blockIdx.x - chunk * tiles_per_chunk;
@@ -90,72 +99,73 @@ chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per
     const long m0 = (long)tile * (CF_W - 2) * CF_P - CF_P + (long)w * CF_P + (long)lane * CF_R;
     const bool do_F = w < CF_W - 1, do_B = w > 0, store = w > 0 && w < CF_W - 1;
 
-    cdd xs[CF_R];
+    C xs[CF_R];
 #pragma unroll
-    for (int r = 0; r < CF_R; ++r) xs[r] = chan_padded<TI>(xc, n, 15 + m0 + r, W, fs);
-    double yI[CF_R], yQ[CF_R];
+    for (int r = 0; r < CF_R; ++r) { cdd v = chan_padded<TI>(xc, n, 15 + m0 + r, W, fs); xs[r] = C{(T)v.x, (T)v.y}; }
+    T yI[CF_R], yQ[CF_R];
+    const T c0p = (T)K.c0p;
 #pragma unroll
-    for (int r = 0; r < CF_R; ++r) { yI[r] = K.c0p * xs[r].x; yQ[r] = K.c0p * xs[r].y; }
+    for (int r = 0; r < CF_R; ++r) { yI[r] = c0p * xs[r].x; yQ[r] = c0p * xs[r].y; }
 
     // both modes and both components advance together: four independent recurrences per direction
-    const cdd p0 = ldd(K.p[0]), p1 = ldd(K.p[1]), a0 = ldd(K.a[0]), a1 = ldd(K.a[1]);
+    const C p0 = cxld<T>(K.p[0]), p1 = cxld<T>(K.p[1]), a0 = cxld<T>(K.a[0]), a1 = cxld<T>(K.a[1]);
     if (do_F) {
-        cdd sI0 = cdd{0.0, 0.0}, sQ0 = sI0, sI1 = sI0, sQ1 = sI0;
+        C sI0 = C{T(0), T(0)}, sQ0 = sI0, sI1 = sI0, sQ1 = sI0;
 #pragma unroll
         for (int r = 0; r < CF_R; ++r) {
-            sI0 = cmuld(p0, sI0); sI0.x += xs[r].x;
-            sQ0 = cmuld(p0, sQ0); sQ0.x += xs[r].y;
-            sI1 = cmuld(p1, sI1); sI1.x += xs[r].x;
-            sQ1 = cmuld(p1, sQ1); sQ1.x += xs[r].y;
-            yI[r] += 2.0 * (a0.x * sI0.x - a0.y * sI0.y + a1.x * sI1.x - a1.y * sI1.y);
-            yQ[r] += 2.0 * (a0.x * sQ0.x - a0.y * sQ0.y + a1.x * sQ1.x - a1.y * sQ1.y);
+            sI0 = cxmul<T>(p0, sI0); sI0.x += xs[r].x;
+            sQ0 = cxmul<T>(p0, sQ0); sQ0.x += xs[r].y;
+            sI1 = cxmul<T>(p1, sI1); sI1.x += xs[r].x;
+            sQ1 = cxmul<T>(p1, sQ1); sQ1.x += xs[r].y;
+            yI[r] += T(2) * (a0.x * sI0.x - a0.y * sI0.y + a1.x * sI1.x - a1.y * sI1.y);
+            yQ[r] += T(2) * (a0.x * sQ0.x - a0.y * sQ0.y + a1.x * sQ1.x - a1.y * sQ1.y);
         }
-        cdd sI[2] = {sI0, sI1}, sQ[2] = {sQ0, sQ1};
+        C sI[2] = {sI0, sI1}, sQ[2] = {sQ0, sQ1};
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
-                cdd oI = dshfl_up(sI[m], 1 << s), oQ = dshfl_up(sQ[m], 1 << s);
-                if (lane >= (1 << s)) { cdd g = ldd(K.ppow[s][m]); sI[m] = cfmad(g, oI, sI[m]); sQ[m] = cfmad(g, oQ, sQ[m]); }
+                C oI = cxup<T>(sI[m], 1 << s), oQ = cxup<T>(sQ[m], 1 << s);
+                if (lane >= (1 << s)) { C g = cxld<T>(K.ppow[s][m]); sI[m] = cxfma<T>(g, oI, sI[m]); sQ[m] = cxfma<T>(g, oQ, sQ[m]); }
             }
-            cdd cI = dshfl_up(sI[m], 1), cQ = dshfl_up(sQ[m], 1);
-            if (lane == 0) cI = cQ = cdd{0.0, 0.0};
+            C cI = cxup<T>(sI[m], 1), cQ = cxup<T>(sQ[m], 1);
+            if (lane == 0) cI = cQ = C{T(0), T(0)};
             if (lane == 31) { carryF[w][0][m] = sI[m]; carryF[w][1][m] = sQ[m]; }
 #pragma unroll
             for (int r = 0; r < CF_R; ++r) {
-                const cdd af = ldd(K.aF[r][m]);
-                yI[r] += 2.0 * (af.x * cI.x - af.y * cI.y);
-                yQ[r] += 2.0 * (af.x * cQ.x - af.y * cQ.y);
+                const C af = cxld<T>(K.aF[r][m]);
+                yI[r] += T(2) * (af.x * cI.x - af.y * cI.y);
+                yQ[r] += T(2) * (af.x * cQ.x - af.y * cQ.y);
             }
         }
     }
     if (do_B) {
-        cdd sI0 = cdd{0.0, 0.0}, sQ0 = sI0, sI1 = sI0, sQ1 = sI0;
+        C sI0 = C{T(0), T(0)}, sQ0 = sI0, sI1 = sI0, sQ1 = sI0;
 #pragma unroll
         for (int r = CF_R - 1; r >= 0; --r) {
-            sI0 = cmuld(p0, sI0); sI0.x += xs[r].x;
-            sQ0 = cmuld(p0, sQ0); sQ0.x += xs[r].y;
-            sI1 = cmuld(p1, sI1); sI1.x += xs[r].x;
-            sQ1 = cmuld(p1, sQ1); sQ1.x += xs[r].y;
-            yI[r] += 2.0 * (a0.x * sI0.x - a0.y * sI0.y + a1.x * sI1.x - a1.y * sI1.y);
-            yQ[r] += 2.0 * (a0.x * sQ0.x - a0.y * sQ0.y + a1.x * sQ1.x - a1.y * sQ1.y);
+            sI0 = cxmul<T>(p0, sI0); sI0.x += xs[r].x;
+            sQ0 = cxmul<T>(p0, sQ0); sQ0.x += xs[r].y;
+            sI1 = cxmul<T>(p1, sI1); sI1.x += xs[r].x;
+            sQ1 = cxmul<T>(p1, sQ1); sQ1.x += xs[r].y;
+            yI[r] += T(2) * (a0.x * sI0.x - a0.y * sI0.y + a1.x * sI1.x - a1.y * sI1.y);
+            yQ[r] += T(2) * (a0.x * sQ0.x - a0.y * sQ0.y + a1.x * sQ1.x - a1.y * sQ1.y);
         }
-        cdd sI[2] = {sI0, sI1}, sQ[2] = {sQ0, sQ1};
+        C sI[2] = {sI0, sI1}, sQ[2] = {sQ0, sQ1};
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
-                cdd oI = dshfl_down(sI[m], 1 << s), oQ = dshfl_down(sQ[m], 1 << s);
-                if (lane + (1 << s) < 32) { cdd g = ldd(K.ppow[s][m]); sI[m] = cfmad(g, oI, sI[m]); sQ[m] = cfmad(g, oQ, sQ[m]); }
+                C oI = cxdown<T>(sI[m], 1 << s), oQ = cxdown<T>(sQ[m], 1 << s);
+                if (lane + (1 << s) < 32) { C g = cxld<T>(K.ppow[s][m]); sI[m] = cxfma<T>(g, oI, sI[m]); sQ[m] = cxfma<T>(g, oQ, sQ[m]); }
             }
-            cdd cI = dshfl_down(sI[m], 1), cQ = dshfl_down(sQ[m], 1);
-            if (lane == 31) cI = cQ = cdd{0.0, 0.0};
+            C cI = cxdown<T>(sI[m], 1), cQ = cxdown<T>(sQ[m], 1);
+            if (lane == 31) cI = cQ = C{T(0), T(0)};
             if (lane == 0) { carryB[w][0][m] = sI[m]; carryB[w][1][m] = sQ[m]; }
 #pragma unroll
             for (int r = 0; r < CF_R; ++r) {
-                const cdd ab = ldd(K.aB[r][m]);
-                yI[r] += 2.0 * (ab.x * cI.x - ab.y * cI.y);
-                yQ[r] += 2.0 * (ab.x * cQ.x - ab.y * cQ.y);
+                const C ab = cxld<T>(K.aB[r][m]);
+                yI[r] += T(2) * (ab.x * cI.x - ab.y * cI.y);
+                yQ[r] += T(2) * (ab.x * cQ.x - ab.y * cQ.y);
             }
         }
     }
@@ -163,27 +173,27 @@ chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per
     if (store) {
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
-        cdd LF = cdd{1.0, 0.0}, LB = cdd{1.0, 0.0};
+        C LF = C{T(1), T(0)}, LB = C{T(1), T(0)};
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
-            cdd g = ldd(K.ppow[s][m]);
-            if (lane & (1 << s)) LF = cmuld(LF, g);
-            if ((31 - lane) & (1 << s)) LB = cmuld(LB, g);
+            C g = cxld<T>(K.ppow[s][m]);
+            if (lane & (1 << s)) LF = cxmul<T>(LF, g);
+            if ((31 - lane) & (1 << s)) LB = cxmul<T>(LB, g);
         }
-        cdd gFI = cmuld(LF, carryF[w - 1][0][m]), gFQ = cmuld(LF, carryF[w - 1][1][m]);
-        cdd gBI = cmuld(LB, carryB[w + 1][0][m]), gBQ = cmuld(LB, carryB[w + 1][1][m]);
+        C gFI = cxmul<T>(LF, carryF[w - 1][0][m]), gFQ = cxmul<T>(LF, carryF[w - 1][1][m]);
+        C gBI = cxmul<T>(LB, carryB[w + 1][0][m]), gBQ = cxmul<T>(LB, carryB[w + 1][1][m]);
 #pragma unroll
         for (int r = 0; r < CF_R; ++r) {
-            const cdd af = ldd(K.aF[r][m]), ab = ldd(K.aB[r][m]);
-            yI[r] += 2.0 * (af.x * gFI.x - af.y * gFI.y + ab.x * gBI.x - ab.y * gBI.y);
-            yQ[r] += 2.0 * (af.x * gFQ.x - af.y * gFQ.y + ab.x * gBQ.x - ab.y * gBQ.y);
+            const C af = cxld<T>(K.aF[r][m]), ab = cxld<T>(K.aB[r][m]);
+            yI[r] += T(2) * (af.x * gFI.x - af.y * gFI.y + ab.x * gBI.x - ab.y * gBI.y);
+            yQ[r] += T(2) * (af.x * gFQ.x - af.y * gFQ.y + ab.x * gBQ.x - ab.y * gBQ.y);
         }
     }
     double2 *out = reinterpret_cast<double2 *>(filtered) + (long)chunk * out_stride;
 #pragma unroll
     for (int r = 0; r < CF_R; ++r) {
         long m = m0 + r;
-        if (m >= 0 && m < n) out[m] = make_double2(yI[r], yQ[r]);
+        if (m >= 0 && m < n) out[m] = make_double2((double)yI[r], (double)yQ[r]);
     }
     }
     // ---- per-phase power partial sums for the timing pick (extract_symbols, processor.py:196-210):
@@ -200,7 +210,7 @@ chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per
             for (int r = 0; r < CF_R; ++r) {
                 long m = m0 + r;
                 phr[r] = -1;
-                pw[r] = yI[r] * yI[r] + yQ[r] * yQ[r];
+                pw[r] = (double)yI[r] * (double)yI[r] + (double)yQ[r] * (double)yQ[r];
                 if (m >= 0 && m < n - CF_FIX) {
                     int mi = (int)m, k = mi / sps, ph = mi - k * sps;
                     if ((ph % step) == 0 && k < (ni - ph) / sps) phr[r] = ph;
@@ -412,8 +422,12 @@ static int launch_t(tb200_handle h, const void *x, int n_chunks, long n, long in
                     double *phase_tail, int sps, int step, cudaStream_t st)
 {
     const int tiles = chan_fast_tiles(n);
-    chan_fast_kernel<TI><<<n_chunks * tiles, CF_W * 32, 0, st>>>((const TI *)x, n, in_stride, tiles, freq_off, fs, K,
-                                                               filtered, out_stride, phase_partial, sps, step);
+    if (h->chan_f32)
+        chan_fast_kernel<TI, float><<<n_chunks * tiles, CF_W * 32, 0, st>>>((const TI *)x, n, in_stride, tiles, freq_off, fs, K,
+                                                                          filtered, out_stride, phase_partial, sps, step);
+    else
+        chan_fast_kernel<TI, double><<<n_chunks * tiles, CF_W * 32, 0, st>>>((const TI *)x, n, in_stride, tiles, freq_off, fs, K,
+                                                                           filtered, out_stride, phase_partial, sps, step);
     TB_LAUNCH_CHECK(h);
     int threads = 128, blocks = (n_chunks * 32 + threads - 1) / threads;
     chan_fast_edge_kernel<TI><<<blocks, threads, 0, st>>>((const TI *)x, n, in_stride, n_chunks, freq_off, fs, K,

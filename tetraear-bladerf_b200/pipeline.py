@@ -29,9 +29,12 @@ class ReceivePipeline:
         self.n_lanes = max(1, int(n_lanes))
         per = (self.max_chunks + self.n_lanes - 1) // self.n_lanes
         self.lane_chunks = per
-        m = {"exact": _lib.MODE_EXACT, "fast": _lib.MODE_FAST}[mode]
+        m = {"exact": _lib.MODE_EXACT, "fast": _lib.MODE_FAST, "fast32": _lib.MODE_FAST}[mode]
         self.handles = [_lib.Handle(sample_rate=self.sample_rate, max_chunks=per, max_chunk_len=self.chunk_len, mode=m,
                                     device=device) for _ in range(self.n_lanes)]
+        if mode == "fast32":
+            for hh in self.handles:
+                hh.set_option(_lib.OPT_CHAN_F32, 1)
         self.h = self.handles[0]
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.n_lanes - 1)]
         C = self.max_chunks

@@ -15,7 +15,7 @@ from .. import _lib
 
 logger = logging.getLogger(__name__)
 
-_MODES = {"exact": _lib.MODE_EXACT, "fast": _lib.MODE_FAST}
+_MODES = {"exact": _lib.MODE_EXACT, "fast": _lib.MODE_FAST, "fast32": _lib.MODE_FAST}
 
 
 def _as_complex(samples):
@@ -51,6 +51,8 @@ class SignalProcessor:
             cap = max(2 * int(n) + 128, 1 << 16)
             self._h = _lib.Handle(sample_rate=fs, max_chunks=1, max_chunk_len=cap, mode=_MODES[self.mode],
                                   device=self.device)
+            if self.mode == "fast32":
+                self._h.set_option(_lib.OPT_CHAN_F32, 1)
             self._cap = ((cap - 128) // 2, fs)
         return self._h
 
