@@ -73,10 +73,26 @@ __device__ __forceinline__ float2 padded_sample(const float2 *__restrict__ x, lo
     return make_float2(__fsub_rn(__fmul_rn(2.0f, e.x), v.x), __fsub_rn(__fmul_rn(2.0f, e.y), v.y));
 }
 
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+// ---- TMA (bulk async copy) of one contiguous tile: global -> shared, completion on an mbarrier ----
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, unsigned bytes, uint64_t *bar)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem), ba = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(ba), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(sa), "l"(gmem), "r"(bytes), "r"(ba) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(a), "r"(parity) : "memory");
 }
 
 // one direction (causal: row0.., taps reversed; anti-causal: next row, taps ascending) for two of the
@@ -142,11 +158,17 @@ __global__ void __launch_bounds__(FD_W * 32, 2)
 decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int tiles_per_chunk, long n_dec,
                   FastDecimParams K, float2 *__restrict__ dec_out)
 {
-    // interleaved (I,Q) rows of Q samples, row pitch PITCH float2 with R*PITCH odd mod 16: the 16 lanes of a
-    // half-warp, R rows apart, hit 16 different 8-byte banks
-    constexpr int PITCH = (Q & 1) ? Q : Q + 1;
+    // The tile is the CONTIGUOUS run of ROWS*Q input samples (interleaved I,Q) behind the CTA's outputs,
+    // laid out densely (row pitch Q) so that one TMA bulk copy stages it; lanes are R rows = R*Q float2
+    // apart (30 for q = 10: a 2-way bank conflict on the 8-byte loads, cheaper than a padded layout that
+    // TMA cannot write).  One extra leading sample keeps the global source 16-byte aligned.
+    constexpr int PITCH = Q;
     constexpr int ROWS = FD_W * FD_P + 1;
-    extern __shared__ float2 fd_tile[];
+    constexpr int TILE = ROWS * Q;
+    constexpr unsigned TMA_BYTES = (unsigned)(((TILE + 1) * 8 + 15) & ~15);
+    extern __shared__ __align__(128) float2 fd_raw[];
+    __shared__ __align__(8) uint64_t tile_bar;
+    float2 *fd_tile = fd_raw + 1;
     __shared__ cf carryF[FD_W][2][4];
     __shared__ cf carryB[FD_W][2][4];
     __shared__ cf lanepow[32][4];
@@ -160,26 +182,22 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
     const long k_tile0 = (long)tile * (FD_W - 2) * FD_P - FD_P;
     const long t0 = 27 + (long)Q * k_tile0 - (Q - 1);
 
-    // ---- stage the tile.  Interior tiles: asynchronous 8-byte global->shared copies (no registers, all
-    // in flight at once); tiles touching a chunk end synthesise the odd extension sample by sample.
-    if (t0 >= 27 && t0 + (long)ROWS * Q <= 27 + n) {
-        // thread -> fixed column, rows RPS apart: one address add per copy, no divisions in the loop
-        constexpr int RPS = (FD_W * 32) / Q;
-        const int row_first = threadIdx.x / Q, col = threadIdx.x - row_first * Q;
-        if (row_first < RPS) {
-            const float2 *src = xc + (t0 - 27) + col;
-            float2 *dst = fd_tile + col;
-            for (int row = row_first; row < ROWS; row += RPS) cp_async8(dst + row * PITCH, src + row * Q);
+    // ---- stage the tile.  Interior tiles: ONE TMA bulk copy issued by thread 0, everybody waits on the
+    // mbarrier; tiles touching a chunk end synthesise the odd extension sample by sample.
+    const float2 *src = xc + (t0 - 28);                       // one sample early: 16-byte aligned (see above)
+    const bool interior = (t0 >= 28) && (t0 - 28 + (long)(TMA_BYTES / 8) <= n) &&
+                          ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (interior) {
+        if (threadIdx.x == 0) {
+            mbar_init(&tile_bar, 1);
+            tma_load_1d(fd_raw, src, TMA_BYTES, &tile_bar);
         }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();                                       // barrier initialised before anybody polls it
+        mbar_wait(&tile_bar, 0);
     } else {
-        for (int s = threadIdx.x; s < ROWS * Q; s += blockDim.x) {
-            int row = s / Q, col = s - row * Q;
-            fd_tile[row * PITCH + col] = padded_sample(xc, n, t0 + s);
-        }
+        for (int s = threadIdx.x; s < TILE; s += blockDim.x) fd_tile[s] = padded_sample(xc, n, t0 + s);
+        __syncthreads();
     }
-    __syncthreads();
 
     const bool do_F = w < FD_W - 1, do_B = w > 0, store = w > 0 && w < FD_W - 1;
     const int row0 = w * FD_P + lane * FD_R;
@@ -389,9 +407,8 @@ template <int Q>
 static int launch_q(tb200_handle h, const void *x, int n_chunks, long n, long chunk_stride, long n_dec,
                     const FastDecimParams &K, void *dec_out, cudaStream_t st)
 {
-    constexpr int PITCH = (Q & 1) ? Q : Q + 1;
     constexpr int ROWS = FD_W * FD_P + 1;
-    const size_t smem = sizeof(float2) * ROWS * PITCH;
+    const size_t smem = ((size_t)(ROWS * Q + 1) * sizeof(float2) + 15 + 16) & ~(size_t)15;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(decim_fast_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
