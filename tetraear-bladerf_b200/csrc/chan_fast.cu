@@ -100,8 +100,19 @@ chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per
     const bool do_F = w < CF_W - 1, do_B = w > 0, store = w > 0 && w < CF_W - 1;
 
     C xs[CF_R];
+    if (sizeof(TI) == 4 && W == 0.0 && m0 >= 0 && m0 + CF_R <= n && ((reinterpret_cast<uintptr_t>(xc) & 15) == 0)) {
+        // interior lane, complex64, no NCO: 8 samples = 64 contiguous bytes = four 16-byte loads
+        const float4 *v4 = reinterpret_cast<const float4 *>(xc + 2 * m0);     // m0 is a multiple of 8: 16-byte aligned
 #pragma unroll
-    for (int r = 0; r < CF_R; ++r) { cdd v = chan_padded<TI>(xc, n, 15 + m0 + r, W, fs); xs[r] = C{(T)v.x, (T)v.y}; }
+        for (int r = 0; r < CF_R / 2; ++r) {
+            float4 v = v4[r];
+            xs[2 * r] = C{(T)v.x, (T)v.y};
+            xs[2 * r + 1] = C{(T)v.z, (T)v.w};
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) { cdd v = chan_padded<TI>(xc, n, 15 + m0 + r, W, fs); xs[r] = C{(T)v.x, (T)v.y}; }
+    }
     T yI[CF_R], yQ[CF_R];
     const T c0p = (T)K.c0p;
 #pragma unroll
