@@ -27,15 +27,47 @@ __device__ __forceinline__ float2 warp_sum2(float2 v)
     return v;
 }
 
+// Register-resident sliding window of the stream: lane l holds x[base + l] (cur), x[base + 32 + l] (nxt)
+// and the prefetched x[base + 64 + l] (pre); the matched filter reads its 32 taps with shuffles, so the
+// only global loads are coalesced 256-byte prefetches issued a whole window ahead of their use.
+struct Window {
+    float2 cur, nxt, pre;
+    long base;
+    __device__ __forceinline__ float2 ld(const float2 *__restrict__ x, long n, long i) const
+    {
+        return (i >= 0 && i < n) ? x[i] : make_float2(0.f, 0.f);
+    }
+    __device__ __forceinline__ void init(const float2 *__restrict__ x, long n, long b, int lane)
+    {
+        base = b;
+        cur = ld(x, n, b + lane); nxt = ld(x, n, b + 32 + lane); pre = ld(x, n, b + 64 + lane);
+    }
+    // make sure [first, first + 48) lies inside [base, base + 64)
+    __device__ __forceinline__ void advance_to(const float2 *__restrict__ x, long n, long first, int lane)
+    {
+        while (first >= base + 16) {
+            if (first >= base + 32) { cur = nxt; nxt = pre; base += 32; pre = ld(x, n, base + 64 + lane); }
+            else break;
+        }
+    }
+    __device__ __forceinline__ float2 at(long j) const       // j in [base, base + 64), per lane
+    {
+        int rel = (int)(j - base);
+        int src = rel & 31;
+        float cx = __shfl_sync(0xffffffffu, cur.x, src), cy = __shfl_sync(0xffffffffu, cur.y, src);
+        float nx = __shfl_sync(0xffffffffu, nxt.x, src), ny = __shfl_sync(0xffffffffu, nxt.y, src);
+        return (rel & 32) ? make_float2(nx, ny) : make_float2(cx, cy);
+    }
+};
+
 // matched-filter output at continuous sample time tau (window i-15 .. i+16 around i = floor(tau))
-__device__ __forceinline__ float2 mf_at(const float2 *__restrict__ x, long n, const float *__restrict__ taps, float tau, int lane)
+__device__ __forceinline__ float2 mf_at(const Window &wdw, const float *__restrict__ taps, float tau, int lane)
 {
     float fl = floorf(tau);
     long i = (long)fl;
     int ph = (int)((tau - fl) * ED_PH);
     ph = ph < 0 ? 0 : (ph >= ED_PH ? ED_PH - 1 : ph);
-    long idx = i + lane - 15;
-    float2 v = (idx >= 0 && idx < n) ? x[idx] : make_float2(0.f, 0.f);
+    float2 v = wdw.at(i + lane - 15);
     float g = taps[ph * ED_TAPS + lane];
     return warp_sum2(make_float2(v.x * g, v.y * g));
 }
@@ -58,9 +90,14 @@ __global__ void etsi_demod_kernel(const float2 *__restrict__ iq, int n_streams, 
     const long max_sym = soft_stride / 2;
     float2 *so = sym_out ? sym_out + (long)s * max_sym : nullptr;
     float *sb = soft_out + (long)s * soft_stride;
+    Window wdw;
+    wdw.init(x, n, 0, lane);
     while (tau + 17.0f < (float)n && k < max_sym) {
-        float2 on = mf_at(x, n, taps, tau, lane);
-        float2 mid = mf_at(x, n, taps, tau - 0.5f * sps, lane);
+        // earliest sample touched this symbol: the half-symbol point's window start
+        long first = (long)floorf(tau - 0.5f * sps) - 15;
+        wdw.advance_to(x, n, first < 0 ? 0 : first, lane);
+        float2 on = mf_at(wdw, taps, tau, lane);
+        float2 mid = mf_at(wdw, taps, tau - 0.5f * sps, lane);
         float p = on.x * on.x + on.y * on.y;
         pavg = (k == 0) ? p : 0.98f * pavg + 0.02f * p;
         float inv = 1.0f / (pavg + 1e-20f);
