@@ -115,6 +115,10 @@ int tb200_set_sample_rate(tb200_handle h, double sample_rate); /* attr is mutate
  * of ~1e-13 for that stage; the 1e-4 budget of FAST mode is dominated by the reference's own float32
  * decimator either way).  Default 0. */
 #define TB200_OPT_CHAN_F32 1
+/* TB200_OPT_PSD_F32 = 2: PSD frames with a float32 FFT and float32 dB conversion (amplitude error ~1e-7 of the
+ * frame peak, i.e. far inside the 1e-4-of-full-scale budget; dB values of bins > 100 dB below the frame peak lose
+ * digits).  Default 0 = float64 like numpy. */
+#define TB200_OPT_PSD_F32 2
 int tb200_set_option(tb200_handle h, int option, int value);
 size_t tb200_workspace_bytes(tb200_handle h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */

@@ -1,5 +1,5 @@
 import sys, numpy as np, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 from tetraear_b200 import etsi, _lib, _dev
 from tetraear_b200.replay import ArchiveReplay
 M, n = 800, 4_000_000

@@ -1,6 +1,6 @@
 # small end-to-end run of every entry point for compute-sanitizer memcheck
 import sys, numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 import __graft_entry__ as g; g.build()
 from tetraear_b200 import synth, etsi, pipeline
 from tetraear_b200.signal import SignalProcessor, SpectrumAnalyzer

@@ -151,6 +151,17 @@ def test_psd_matches_reference_golden(mods, golden_psd):
     for i in range(8):
         o = oracle.band_stats(ref[i], 2.4e6)
         assert r2["stats"][i]["peak_idx"] == o["peak_idx"] and abs(r2["stats"][i]["snr"] - o["snr"]) <= 1e-6
+    # float32 variant (dense config mode): amplitude within 1e-4 of full scale (north_star), dB within 0.01 dB
+    # wherever the bin is less than 80 dB below the frame's peak
+    an3 = signal.SpectrumAnalyzer(2.4e6, 4096, precision="f32")
+    for src in (chunks[0], chunks[7]):
+        r3 = an3.run(src[:4096 * 8], denoise=False)
+        ref3 = np.stack([oracle.psd_frame(src[i * 4096:(i + 1) * 4096], 2.4e6, 4096)[1] for i in range(8)])
+        assert np.abs(10 ** (r3["power"] / 20) - 10 ** (ref3 / 20)).max() <= 1e-6
+        strong = ref3 > ref3.max(axis=1, keepdims=True) - 80
+        assert np.abs(r3["power"] - ref3)[strong].max() <= 1e-2
+        for i in range(8):
+            assert r3["stats"][i]["peak_idx"] == oracle.band_stats(ref3[i], 2.4e6)["peak_idx"]
 
 
 @pytest.mark.parametrize("lanes", [1, 3])

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtetra_b200.so")
 DTYPE_C64, DTYPE_C128 = 0, 1
 MODE_EXACT, MODE_FAST = 0, 1
 OPT_CHAN_F32 = 1
+OPT_PSD_F32 = 2
 
 
 class Config(C.Structure):

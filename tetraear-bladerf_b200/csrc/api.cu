@@ -74,7 +74,7 @@ static size_t carve(tb200_handle h, char *base)
     h->sync_pos = c.take<int32_t>(S * (size_t)h->max_frames * sizeof(int32_t));
     h->sync_cnt = c.take<int32_t>(64);
     size_t nf = (size_t)cfg.max_fft;
-    h->psd_tables = c.take<double>((nf + 2 * (nf / 2 + nf / 4 + 1)) * sizeof(double));
+    h->psd_tables = c.take<double>((2 * nf + 2 * (nf / 2 + nf / 4 + 1)) * sizeof(double));
     h->etsi_taps = c.take<float>(32 * 32 * sizeof(float));
     size_t MC = (size_t)cfg.max_channels;
     h->chan_proto = c.take<float>(MC * 6 * sizeof(float));
@@ -248,6 +248,7 @@ extern "C" int tb200_set_option(tb200_handle h, int option, int value)
     if (!h) return fail(TB200_E_ARG, "tb200_set_option: null handle");
     switch (option) {
     case TB200_OPT_CHAN_F32: h->chan_f32 = value ? 1 : 0; return TB200_OK;
+    case TB200_OPT_PSD_F32: h->psd_f32 = value ? 1 : 0; return TB200_OK;
     default: return fail(TB200_E_ARG, "tb200_set_option: unknown option %d", option);
     }
 }
@@ -562,7 +563,7 @@ extern "C" int tb200_psd_batch(tb200_handle h, const void *d_iq_c64, int64_t n_f
     if (d_smoothed && (!d_power || !d_ema_state)) return fail(TB200_E_ARG, "tb200_psd_batch: smoothing needs d_power and d_ema_state");
     StageTimer tm(h, TB_STAGE_PSD, (cudaStream_t)stream);
     return launch_psd(h, (const float *)d_iq_c64, n_frames, frame_stride, n_fft, sample_rate, ema_alpha, first, d_power,
-                      d_smoothed, d_ema_state, d_stats, h->psd_tables, (cudaStream_t)stream);
+                      d_smoothed, d_ema_state, d_stats, h->psd_tables, (cudaStream_t)stream, h->psd_f32);
 }
 
 // ------------------------------------------------------------------------- debugging aid

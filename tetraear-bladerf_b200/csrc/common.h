@@ -50,6 +50,7 @@ struct tb200_handle_s {
     tb200_config cfg;
     int64_t launches;
     // optional per-stage CUDA-event timing (tb200_profile_*): pairs recorded on the launching stream
+    int psd_f32;                 // PSD: float32 FFT + dB (dense config mode) instead of float64
     int chan_f32;                // FAST mode: run the channel filter's recurrences in float32 (tb200_set_option)
     int profiling;
     std::vector<cudaEvent_t> *prof_ev;      // flat: start, stop, start, stop ...

@@ -26,10 +26,16 @@ __global__ void psd_tables_kernel(int n_fft, double *__restrict__ window, double
     }
 }
 
-__device__ __forceinline__ double2 cmul(double2 a, double2 b)
-{
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
+template <typename T> struct V2;
+template <> struct V2<double> { typedef double2 type; };
+template <> struct V2<float> { typedef float2 type; };
+__device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) { return mk2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double db20(double mag) { return 20.0 * log10(mag + 1e-20); }
+__device__ __forceinline__ float db20(float mag) { return 20.0f * log10f(mag + 1e-20f); }
+__device__ __forceinline__ double mag2(double2 v) { return hypot(v.x, v.y); }
+__device__ __forceinline__ float mag2(float2 v) { return sqrtf(v.x * v.x + v.y * v.y); }
 
 struct BandParams {
     int start, end;          // in-channel bins  [start, end)
@@ -37,13 +43,17 @@ struct BandParams {
     double freq_step;        // 1 / (N * (1/fs))
 };
 
-extern __shared__ double2 psd_smem[];
+extern __shared__ __align__(16) unsigned char psd_smem_raw[];
 
+// T = double: numpy's arithmetic (complex128 FFT, float64 dB) — used for the reference's 2048-point frames.
+// T = float : the dense "config" mode (tolerance: <= 1e-4 of full scale in amplitude, north_star).
+template <typename T>
 __global__ void psd_kernel(const float2 *__restrict__ iq, long frame_stride, int n_fft, int log2n,
                            const double *__restrict__ window, const double2 *__restrict__ tw, BandParams bp,
                            float *__restrict__ power, double *__restrict__ stats)
 {
-    double2 *x = psd_smem;
+    typedef typename V2<T>::type C;
+    C *x = reinterpret_cast<C *>(psd_smem_raw);
     __shared__ double red[3][32];
     __shared__ int redi[32];
     const long frame = blockIdx.x;
@@ -52,18 +62,18 @@ __global__ void psd_kernel(const float2 *__restrict__ iq, long frame_stride, int
     // load, window, bit-reverse (radix-2 ordering)
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         float2 v = in[i];
-        double w = window[i];
+        T w = (T)window[i];
         int r = __brev((unsigned)i) >> (32 - log2n);
-        x[r] = make_double2((double)v.x * w, (double)v.y * w);
+        x[r] = mk2((T)v.x * w, (T)v.y * w);
     }
     __syncthreads();
     // first stage radix-2 when log2n is odd, then radix-4 stages (two radix-2 levels fused)
     int len = 1;                 // current sub-transform length
     if (log2n & 1) {
         for (int i = threadIdx.x; i < N / 2; i += blockDim.x) {
-            double2 a = x[2 * i], b = x[2 * i + 1];
-            x[2 * i] = make_double2(a.x + b.x, a.y + b.y);
-            x[2 * i + 1] = make_double2(a.x - b.x, a.y - b.y);
+            C a = x[2 * i], b = x[2 * i + 1];
+            x[2 * i] = mk2(a.x + b.x, a.y + b.y);
+            x[2 * i + 1] = mk2(a.x - b.x, a.y - b.y);
         }
         len = 2;
         __syncthreads();
@@ -77,28 +87,28 @@ __global__ void psd_kernel(const float2 *__restrict__ iq, long frame_stride, int
         for (int i = threadIdx.x; i < N / 4; i += blockDim.x) {
             int blk = i / len, k = i - blk * len;
             int base = blk * L4 + k;
-            double2 a = x[base], b = x[base + len], c = x[base + 2 * len], d = x[base + 3 * len];
-            double2 w1 = tw[k * tstep1];
-            double2 bt = cmul(b, w1), dt = cmul(d, w1);
-            double2 e0 = make_double2(a.x + bt.x, a.y + bt.y), e1 = make_double2(a.x - bt.x, a.y - bt.y);
-            double2 o0 = make_double2(c.x + dt.x, c.y + dt.y), o1 = make_double2(c.x - dt.x, c.y - dt.y);
-            double2 w2a = tw[k * tstep2], w2b = tw[(k + len) * tstep2];
-            double2 p0 = cmul(o0, w2a), p1 = cmul(o1, w2b);
-            x[base] = make_double2(e0.x + p0.x, e0.y + p0.y);
-            x[base + 2 * len] = make_double2(e0.x - p0.x, e0.y - p0.y);
-            x[base + len] = make_double2(e1.x + p1.x, e1.y + p1.y);
-            x[base + 3 * len] = make_double2(e1.x - p1.x, e1.y - p1.y);
+            C a = x[base], b = x[base + len], c = x[base + 2 * len], d = x[base + 3 * len];
+            double2 t1 = tw[k * tstep1], t2a = tw[k * tstep2], t2b = tw[(k + len) * tstep2];
+            C w1 = mk2((T)t1.x, (T)t1.y), w2a = mk2((T)t2a.x, (T)t2a.y), w2b = mk2((T)t2b.x, (T)t2b.y);
+            C bt = cmul(b, w1), dt = cmul(d, w1);
+            C e0 = mk2(a.x + bt.x, a.y + bt.y), e1 = mk2(a.x - bt.x, a.y - bt.y);
+            C o0 = mk2(c.x + dt.x, c.y + dt.y), o1 = mk2(c.x - dt.x, c.y - dt.y);
+            C p0 = cmul(o0, w2a), p1 = cmul(o1, w2b);
+            x[base] = mk2(e0.x + p0.x, e0.y + p0.y);
+            x[base + 2 * len] = mk2(e0.x - p0.x, e0.y - p0.y);
+            x[base + len] = mk2(e1.x + p1.x, e1.y + p1.y);
+            x[base + 3 * len] = mk2(e1.x - p1.x, e1.y - p1.y);
         }
         len = L4;
         __syncthreads();
     }
     // dBFS, fftshift, band statistics
-    const double invN = 1.0 / (double)N;   // |X| / n_fft : power-of-two N, the product is exact
+    const T invN = (T)1 / (T)N;   // |X| / n_fft : power-of-two N, the product is exact
     double sig = 0.0, noise = 0.0, pk = -1e300;
     int pki = 0x7fffffff;
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        double2 v = x[(j + N / 2) & (N - 1)];
-        double p = 20.0 * log10(hypot(v.x, v.y) * invN + 1e-20);
+        C v = x[(j + N / 2) & (N - 1)];
+        double p = (double)db20(mag2(v) * invN);
         if (power) power[frame * N + j] = (float)p;
         if (j >= bp.start && j < bp.end) {
             sig += p;
@@ -147,24 +157,44 @@ __global__ void psd_kernel(const float2 *__restrict__ iq, long frame_stride, int
     }
 }
 
-// EMA across frames, dB domain: S = S (1 - a) + P a ; first frame S = P  (modern.py:929-935)
+// EMA across frames, dB domain: S = S (1 - a) + P a ; first frame S = P  (modern.py:929-935).
+// The recurrence forgets its past as (1-a)^k, so the frame axis is cut into groups of EMA_G frames and each
+// group re-runs the EMA_W frames before it as warm-up (exact when that reaches frame 0, otherwise the
+// truncated history is below (1-a)^EMA_W of a dB difference: 9e-10 for a = 0.15).  Parallelism:
+// groups x bins threads instead of one thread per bin walking every frame.
+constexpr int EMA_G = 128;
+constexpr int EMA_W = 128;
+
 __global__ void psd_ema_kernel(const float *__restrict__ power, long n_frames, int n_fft, double alpha, int first,
-                               double *__restrict__ state, float *__restrict__ smoothed)
+                               const double *__restrict__ state_in, double *__restrict__ state_out,
+                               float *__restrict__ smoothed)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_fft) return;
-    double S = first ? 0.0 : state[j];
-    for (long f = 0; f < n_frames; ++f) {
-        double p = (double)power[f * n_fft + j];
-        S = (first && f == 0) ? p : __dadd_rn(__dmul_rn(S, 1.0 - alpha), __dmul_rn(p, alpha));
-        smoothed[f * n_fft + j] = (float)S;
+    const long g0 = (long)blockIdx.y * EMA_G;
+    const long g1 = g0 + EMA_G < n_frames ? g0 + EMA_G : n_frames;
+    long f = g0 - EMA_W;
+    double S;
+    if (f <= 0) {
+        f = 0;
+        if (first) { S = (double)power[j]; if (g0 == 0) smoothed[j] = (float)S; f = 1; }
+        else S = state_in[j];
+    } else {
+        S = (double)power[f * n_fft + j];      // any start value: its weight at g0 is (1-a)^EMA_W
+        ++f;
     }
-    state[j] = S;
+    const double om = 1.0 - alpha;
+    for (; f < g1; ++f) {
+        double p = (double)power[f * n_fft + j];
+        S = __dadd_rn(__dmul_rn(S, om), __dmul_rn(p, alpha));
+        if (f >= g0) smoothed[f * n_fft + j] = (float)S;
+    }
+    if (g1 == n_frames) state_out[j] = S;
 }
 
 int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_stride, int n_fft, double fs,
                double alpha, int first, float *power, float *smoothed, double *ema_state, double *stats,
-               double *tables, cudaStream_t st)
+               double *tables, cudaStream_t st, int use_f32)
 {
     if (n_frames <= 0) return TB200_OK;
     int log2n = 0;
@@ -185,17 +215,30 @@ int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_
     bp.n_lo = bp.start - 10 > 0 ? bp.start - 10 : 0;
     bp.n_hi0 = bp.end + 10 < n_fft ? bp.end + 10 : n_fft;
     bp.freq_step = 1.0 / ((double)n_fft * (1.0 / fs));
-    size_t smem = sizeof(double2) * (size_t)n_fft;
+    size_t smem = (use_f32 ? sizeof(float2) : sizeof(double2)) * (size_t)n_fft;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(psd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = use_f32 ? cudaFuncSetAttribute(psd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                : cudaFuncSetAttribute(psd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(psd_kernel): %s", cudaGetErrorString(e));
     }
     int threads = n_fft >= 2048 ? 512 : (n_fft >= 512 ? 128 : 64);
-    psd_kernel<<<(unsigned)n_frames, threads, smem, st>>>((const float2 *)iq, frame_stride, n_fft, log2n, window, tw, bp,
-                                                         power, stats);
+    if (use_f32)
+        psd_kernel<float><<<(unsigned)n_frames, threads, smem, st>>>((const float2 *)iq, frame_stride, n_fft, log2n, window, tw, bp,
+                                                                    power, stats);
+    else
+        psd_kernel<double><<<(unsigned)n_frames, threads, smem, st>>>((const float2 *)iq, frame_stride, n_fft, log2n, window, tw, bp,
+                                                                     power, stats);
     TB_LAUNCH_CHECK(h);
     if (smoothed) {
-        psd_ema_kernel<<<(n_fft + 127) / 128, 128, 0, st>>>(power, n_frames, n_fft, alpha, first, ema_state, smoothed);
+        // state_in and state_out may alias only when a single group runs; otherwise read a snapshot
+        double *state_in = ema_state;
+        long groups = (n_frames + EMA_G - 1) / EMA_G;
+        if (groups > 1 && !first) {
+            state_in = tables + n_fft + 2 * (n_fft / 2 + n_fft / 4 + 1);       // spare n_fft doubles behind the tables
+            TB_CUDA(cudaMemcpyAsync(state_in, ema_state, sizeof(double) * n_fft, cudaMemcpyDeviceToDevice, st));
+        }
+        dim3 grid((n_fft + 127) / 128, (unsigned)groups);
+        psd_ema_kernel<<<grid, 128, 0, st>>>(power, n_frames, n_fft, alpha, first, state_in, ema_state, smoothed);
         TB_LAUNCH_CHECK(h);
     }
     return TB200_OK;

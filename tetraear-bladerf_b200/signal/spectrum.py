@@ -28,13 +28,16 @@ class SpectrumAnalyzer:
     config mode    : any power-of-two n_fft (e.g. 4096), frame_stride = n_fft (dense).
     """
 
-    def __init__(self, sample_rate=2.4e6, n_fft=2048, ema_alpha=0.15, device=0):
+    def __init__(self, sample_rate=2.4e6, n_fft=2048, ema_alpha=0.15, device=0, precision="f64"):
         self.sample_rate = float(sample_rate)
         self.n_fft = int(n_fft)
         self.ema_alpha = float(ema_alpha)
         self.device = device
         self._h = _lib.Handle(sample_rate=self.sample_rate, max_chunks=0, max_chunk_len=0, device=device,
                               max_fft=max(self.n_fft, 4096))
+        if precision == "f32":
+            self._h.set_option(_lib.OPT_PSD_F32, 1)
+        self.precision = precision
         self._state = None
         self._first = True
         self.freqs = _freq_axis(self.n_fft, self.sample_rate)
