@@ -95,17 +95,47 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
                  "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(a), "r"(parity) : "memory");
 }
 
+// ---- packed float2 arithmetic: the I and Q components of a sample share every coefficient, so each
+// quantity is kept as a float2 (I, Q) and updated with ONE fma.rn.f32x2 (SASS FFMA2) instead of two FFMAs.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 splat(float s) { return make_float2(s, s); }
+// complex value per component: re = (re_I, re_Q), im = (im_I, im_Q)
+struct cp { float2 re, im; };
+// c + g * a  for a scalar complex g and packed complex a, c
+__device__ __forceinline__ cp cpfma(cf g, cp a, cp c)
+{
+    cp o;
+    o.re = ffma2(splat(g.x), a.re, ffma2(splat(-g.y), a.im, c.re));
+    o.im = ffma2(splat(g.x), a.im, ffma2(splat(g.y), a.re, c.im));
+    return o;
+}
+__device__ __forceinline__ cp cpmul(cf g, cp a)
+{
+    cp z; z.re = z.im = make_float2(0.f, 0.f);
+    return cpfma(g, a, z);
+}
+__device__ __forceinline__ float2 shfl2_up(float2 v, int d) { return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d)); }
+__device__ __forceinline__ float2 shfl2_down(float2 v, int d) { return make_float2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d)); }
+// y += Re(g * a)
+__device__ __forceinline__ float2 re_acc(cf g, cp a, float2 y) { return ffma2(splat(g.x), a.re, ffma2(splat(-g.y), a.im, y)); }
+
 // one direction (causal: row0.., taps reversed; anti-causal: next row, taps ascending) for two of the
-// four modes; accumulates Re(alpha * .) into yI/yQ and leaves the pass-end state in `carry`.
+// four modes; accumulates Re(alpha * .) into y (I, Q packed) and leaves the pass-end state in `carry`.
 template <int Q, int PITCH, bool FWD>
 __device__ __forceinline__ void fd_half(const float2 *__restrict__ tile, int row0, int lane, int m0,
-                                        const FastDecimParams &K, float yI[FD_R], float yQ[FD_R], cf (*carry)[4])
+                                        const FastDecimParams &K, float2 y[FD_R], cp *carry)
 {
-    cf UI[FD_R][2], UQ[FD_R][2];
+    cp U[FD_R][2];
 #pragma unroll
     for (int r = 0; r < FD_R; ++r) {
 #pragma unroll
-        for (int mm = 0; mm < 2; ++mm) UI[r][mm] = UQ[r][mm] = cf{0.f, 0.f};
+        for (int mm = 0; mm < 2; ++mm) U[r][mm].re = U[r][mm].im = make_float2(0.f, 0.f);
         const float2 *row = tile + (row0 + r + (FWD ? 0 : 1)) * PITCH;
 #pragma unroll
         for (int c = 0; c < Q; ++c) {
@@ -113,9 +143,8 @@ __device__ __forceinline__ void fd_half(const float2 *__restrict__ tile, int row
 #pragma unroll
             for (int mm = 0; mm < 2; ++mm) {
                 const int tp = FWD ? Q - 1 - c : c;
-                const float tr = K.tap[tp][m0 + mm][0], ti = K.tap[tp][m0 + mm][1];
-                UI[r][mm].x = fmaf(tr, v.x, UI[r][mm].x); UI[r][mm].y = fmaf(ti, v.x, UI[r][mm].y);
-                UQ[r][mm].x = fmaf(tr, v.y, UQ[r][mm].x); UQ[r][mm].y = fmaf(ti, v.y, UQ[r][mm].y);
+                U[r][mm].re = ffma2(splat(K.tap[tp][m0 + mm][0]), v, U[r][mm].re);
+                U[r][mm].im = ffma2(splat(K.tap[tp][m0 + mm][1]), v, U[r][mm].im);
             }
         }
     }
@@ -126,29 +155,30 @@ __device__ __forceinline__ void fd_half(const float2 *__restrict__ tile, int row
         // zero-state recurrence inside the lane, then an inclusive scan of the lane aggregates
         if (FWD) {
 #pragma unroll
-            for (int r = 1; r < FD_R; ++r) { UI[r][mm] = cfma(lam, UI[r - 1][mm], UI[r][mm]); UQ[r][mm] = cfma(lam, UQ[r - 1][mm], UQ[r][mm]); }
+            for (int r = 1; r < FD_R; ++r) U[r][mm] = cpfma(lam, U[r - 1][mm], U[r][mm]);
         } else {
 #pragma unroll
-            for (int r = FD_R - 2; r >= 0; --r) { UI[r][mm] = cfma(lam, UI[r + 1][mm], UI[r][mm]); UQ[r][mm] = cfma(lam, UQ[r + 1][mm], UQ[r][mm]); }
+            for (int r = FD_R - 2; r >= 0; --r) U[r][mm] = cpfma(lam, U[r + 1][mm], U[r][mm]);
         }
-        cf aI = UI[FWD ? FD_R - 1 : 0][mm], aQ = UQ[FWD ? FD_R - 1 : 0][mm];
+        cp a = U[FWD ? FD_R - 1 : 0][mm];
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
-            cf oI = FWD ? cshfl_up(aI, 1 << s) : cshfl_down(aI, 1 << s);
-            cf oQ = FWD ? cshfl_up(aQ, 1 << s) : cshfl_down(aQ, 1 << s);
+            cp o;
+            o.re = FWD ? shfl2_up(a.re, 1 << s) : shfl2_down(a.re, 1 << s);
+            o.im = FWD ? shfl2_up(a.im, 1 << s) : shfl2_down(a.im, 1 << s);
             const bool take = FWD ? (lane >= (1 << s)) : (lane + (1 << s) < 32);
-            if (take) { cf g = ld2(K.lampow[s][m]); aI = cfma(g, oI, aI); aQ = cfma(g, oQ, aQ); }
+            if (take) a = cpfma(ld2(K.lampow[s][m]), o, a);
         }
-        cf cI = FWD ? cshfl_up(aI, 1) : cshfl_down(aI, 1);
-        cf cQ = FWD ? cshfl_up(aQ, 1) : cshfl_down(aQ, 1);
-        if (lane == (FWD ? 0 : 31)) cI = cQ = cf{0.f, 0.f};
-        if (lane == (FWD ? 31 : 0)) { carry[0][m] = aI; carry[1][m] = aQ; }
+        cp cin;
+        cin.re = FWD ? shfl2_up(a.re, 1) : shfl2_down(a.re, 1);
+        cin.im = FWD ? shfl2_up(a.im, 1) : shfl2_down(a.im, 1);
+        if (lane == (FWD ? 0 : 31)) cin.re = cin.im = make_float2(0.f, 0.f);
+        if (lane == (FWD ? 31 : 0)) carry[m] = a;
         const cf a0 = FWD ? ld2(K.a0[m]) : ld2(K.ap[m]);
 #pragma unroll
         for (int r = 0; r < FD_R; ++r) {
             const cf af = FWD ? ld2(K.aF[r][m]) : ld2(K.aB[r][m]);
-            yI[r] += a0.x * UI[r][mm].x - a0.y * UI[r][mm].y + af.x * cI.x - af.y * cI.y;
-            yQ[r] += a0.x * UQ[r][mm].x - a0.y * UQ[r][mm].y + af.x * cQ.x - af.y * cQ.y;
+            y[r] = re_acc(af, cin, re_acc(a0, U[r][mm], y[r]));
         }
     }
 }
@@ -169,8 +199,8 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
     extern __shared__ __align__(128) float2 fd_raw[];
     __shared__ __align__(8) uint64_t tile_bar;
     float2 *fd_tile = fd_raw + 1;
-    __shared__ cf carryF[FD_W][2][4];
-    __shared__ cf carryB[FD_W][2][4];
+    __shared__ cp carryF[FD_W][4];
+    __shared__ cp carryB[FD_W][4];
     __shared__ cf lanepow[32][4];
     if (threadIdx.x < 128) lanepow[threadIdx.x >> 2][threadIdx.x & 3] = ld2(K.lanepow[threadIdx.x >> 2][threadIdx.x & 3]);
 
@@ -201,38 +231,33 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
 
     const bool do_F = w < FD_W - 1, do_B = w > 0, store = w > 0 && w < FD_W - 1;
     const int row0 = w * FD_P + lane * FD_R;
-    float yI[FD_R], yQ[FD_R];
+    float2 y[FD_R];
 #pragma unroll
-    for (int r = 0; r < FD_R; ++r) yI[r] = yQ[r] = 0.f;
+    for (int r = 0; r < FD_R; ++r) y[r] = make_float2(0.f, 0.f);
     if (do_F) {
-        fd_half<Q, PITCH, true>(fd_tile, row0, lane, 0, K, yI, yQ, carryF[w]);
-        fd_half<Q, PITCH, true>(fd_tile, row0, lane, 2, K, yI, yQ, carryF[w]);
+        fd_half<Q, PITCH, true>(fd_tile, row0, lane, 0, K, y, carryF[w]);
+        fd_half<Q, PITCH, true>(fd_tile, row0, lane, 2, K, y, carryF[w]);
     }
     if (do_B) {
-        fd_half<Q, PITCH, false>(fd_tile, row0, lane, 0, K, yI, yQ, carryB[w]);
-        fd_half<Q, PITCH, false>(fd_tile, row0, lane, 2, K, yI, yQ, carryB[w]);
+        fd_half<Q, PITCH, false>(fd_tile, row0, lane, 0, K, y, carryB[w]);
+        fd_half<Q, PITCH, false>(fd_tile, row0, lane, 2, K, y, carryB[w]);
     }
     __syncthreads();
     if (!store) return;
     // ---- carries from the neighbour passes: lambda^(lane R) cF on the left, lambda^((31-lane) R) cB on the right
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-        const cf LF = lanepow[lane][m], LB = lanepow[31 - lane][m];
-        cf gFI = cmulf(LF, carryF[w - 1][0][m]), gFQ = cmulf(LF, carryF[w - 1][1][m]);
-        cf gBI = cmulf(LB, carryB[w + 1][0][m]), gBQ = cmulf(LB, carryB[w + 1][1][m]);
+        const cp gF = cpmul(lanepow[lane][m], carryF[w - 1][m]);
+        const cp gB = cpmul(lanepow[31 - lane][m], carryB[w + 1][m]);
 #pragma unroll
-        for (int r = 0; r < FD_R; ++r) {
-            const cf af = ld2(K.aF[r][m]), ab = ld2(K.aB[r][m]);
-            yI[r] += af.x * gFI.x - af.y * gFI.y + ab.x * gBI.x - ab.y * gBI.y;
-            yQ[r] += af.x * gFQ.x - af.y * gFQ.y + ab.x * gBQ.x - ab.y * gBQ.y;
-        }
+        for (int r = 0; r < FD_R; ++r) y[r] = re_acc(ld2(K.aB[r][m]), gB, re_acc(ld2(K.aF[r][m]), gF, y[r]));
     }
     float2 *out = dec_out + (long)chunk * n_dec;
     const long k0 = k_tile0 + row0;
 #pragma unroll
     for (int r = 0; r < FD_R; ++r) {
         long k = k0 + r;
-        if (k >= 0 && k < n_dec) out[k] = make_float2(2.0f * yI[r], 2.0f * yQ[r]);
+        if (k >= 0 && k < n_dec) out[k] = make_float2(2.0f * y[r].x, 2.0f * y[r].y);
     }
 }
 
