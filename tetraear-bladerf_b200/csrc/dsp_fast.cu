@@ -32,6 +32,7 @@ constexpr int FD_R = 3;              // outputs per lane
 constexpr int FD_P = 32 * FD_R;      // outputs per warp pass
 constexpr int FD_W = 8;              // warps per CTA: 1 left-halo + 6 storing + 1 right-halo
 constexpr int FD_QMAX = 16;
+constexpr int FD_NM = 4;              // modes per FIR sweep (4 = one pass over the tile rows, 2 = two passes, fewer registers)
 constexpr int FD_EDGE_S = 42;        // edge kernel: samples per lane (32 x 42 = 1344; 0.982^1344 = 3e-11)
 
 struct FastDecimParams {
@@ -127,21 +128,21 @@ __device__ __forceinline__ float2 re_acc(cf g, cp a, float2 y) { return ffma2(sp
 
 // one direction (causal: row0.., taps reversed; anti-causal: next row, taps ascending) for two of the
 // four modes; accumulates Re(alpha * .) into y (I, Q packed) and leaves the pass-end state in `carry`.
-template <int Q, int PITCH, bool FWD>
+template <int Q, int PITCH, bool FWD, int NM>
 __device__ __forceinline__ void fd_half(const float2 *__restrict__ tile, int row0, int lane, int m0,
                                         const FastDecimParams &K, float2 y[FD_R], cp *carry)
 {
-    cp U[FD_R][2];
+    cp U[FD_R][NM];
 #pragma unroll
     for (int r = 0; r < FD_R; ++r) {
 #pragma unroll
-        for (int mm = 0; mm < 2; ++mm) U[r][mm].re = U[r][mm].im = make_float2(0.f, 0.f);
+        for (int mm = 0; mm < NM; ++mm) U[r][mm].re = U[r][mm].im = make_float2(0.f, 0.f);
         const float2 *row = tile + (row0 + r + (FWD ? 0 : 1)) * PITCH;
 #pragma unroll
         for (int c = 0; c < Q; ++c) {
             const float2 v = row[c];
 #pragma unroll
-            for (int mm = 0; mm < 2; ++mm) {
+            for (int mm = 0; mm < NM; ++mm) {
                 const int tp = FWD ? Q - 1 - c : c;
                 U[r][mm].re = ffma2(splat(K.tap[tp][m0 + mm][0]), v, U[r][mm].re);
                 U[r][mm].im = ffma2(splat(K.tap[tp][m0 + mm][1]), v, U[r][mm].im);
@@ -149,7 +150,7 @@ __device__ __forceinline__ void fd_half(const float2 *__restrict__ tile, int row
         }
     }
 #pragma unroll
-    for (int mm = 0; mm < 2; ++mm) {
+    for (int mm = 0; mm < NM; ++mm) {
         const int m = m0 + mm;
         const cf lam = ld2(K.lam[m]);
         // zero-state recurrence inside the lane, then an inclusive scan of the lane aggregates
@@ -184,7 +185,7 @@ __device__ __forceinline__ void fd_half(const float2 *__restrict__ tile, int row
 }
 
 template <int Q>
-__global__ void __launch_bounds__(FD_W * 32, 2)
+__global__ void __launch_bounds__(FD_W * 32, 3)
 decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int tiles_per_chunk, long n_dec,
                   FastDecimParams K, float2 *__restrict__ dec_out)
 {
@@ -235,12 +236,12 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
 #pragma unroll
     for (int r = 0; r < FD_R; ++r) y[r] = make_float2(0.f, 0.f);
     if (do_F) {
-        fd_half<Q, PITCH, true>(fd_tile, row0, lane, 0, K, y, carryF[w]);
-        fd_half<Q, PITCH, true>(fd_tile, row0, lane, 2, K, y, carryF[w]);
+        fd_half<Q, PITCH, true, FD_NM>(fd_tile, row0, lane, 0, K, y, carryF[w]);
+        if (FD_NM == 2) fd_half<Q, PITCH, true, FD_NM>(fd_tile, row0, lane, 2, K, y, carryF[w]);
     }
     if (do_B) {
-        fd_half<Q, PITCH, false>(fd_tile, row0, lane, 0, K, y, carryB[w]);
-        fd_half<Q, PITCH, false>(fd_tile, row0, lane, 2, K, y, carryB[w]);
+        fd_half<Q, PITCH, false, FD_NM>(fd_tile, row0, lane, 0, K, y, carryB[w]);
+        if (FD_NM == 2) fd_half<Q, PITCH, false, FD_NM>(fd_tile, row0, lane, 2, K, y, carryB[w]);
     }
     __syncthreads();
     if (!store) return;
