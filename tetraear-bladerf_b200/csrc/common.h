@@ -77,6 +77,7 @@ struct tb200_handle_s {
     // psd
     double *psd_tables; int psd_tables_n;
     float *chan_proto, *chan_tw; int chan_M;   // channelizer prototype [6 M], twiddles, M they are for
+    double etsi_taps_fs;                      // fs the tap table below was built for (0 = none)
     float *etsi_taps;                         // [32 phases][32 taps] interpolating matched filter
     // staging for the *_host entry points
     void *stage_in;   size_t stage_in_bytes;

@@ -209,9 +209,13 @@ int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, l
     if (n_streams <= 0) return TB200_OK;
     double sps = fs / 18000.0;
     if (sps < 2.0 || sps > 4.01) return fail(TB200_E_ARG, "tb200_etsi_demod_batch: %.3f samples/symbol outside [2, 4]", sps);
-    float taps[ED_PH * ED_TAPS];
-    make_mf_taps(sps, taps);
-    TB_CUDA(cudaMemcpyAsync(taps_dev, taps, sizeof(taps), cudaMemcpyHostToDevice, st));
+    if (h->etsi_taps_fs != fs) {                 // the tap table depends on fs only: upload once per handle
+        float taps[ED_PH * ED_TAPS];
+        make_mf_taps(sps, taps);
+        TB_CUDA(cudaMemcpyAsync(taps_dev, taps, sizeof(taps), cudaMemcpyHostToDevice, st));
+        TB_CUDA(cudaStreamSynchronize(st));      // `taps` is a stack buffer
+        h->etsi_taps_fs = fs;
+    }
     int threads = 128, blocks = (n_streams * 32 + threads - 1) / threads;
     etsi_demod_kernel<<<blocks, threads, 0, st>>>(iq, n_streams, n, stride, (float)sps, (float)(0.05 * sps), (float)(0.0005 * sps),
                                                   taps_dev, sym, soft, soft_stride, n_soft);

@@ -236,15 +236,20 @@ class EtsiReceiver:
 
     def run_device(self, iq, n_samples, scramb_init, threshold=0.8, keep_symbols=False):
         """iq: CUDA float32 tensor [n_streams, stride, 2].  Asynchronous; results stay on the device."""
+        return self.run_device_strided(iq.data_ptr(), iq.shape[0], n_samples, iq.shape[1], scramb_init, threshold,
+                                       keep_symbols)
+
+    def run_device_strided(self, iq_ptr, n_streams, n_samples, stride, scramb_init, threshold=0.8, keep_symbols=False):
+        """Same on a raw device pointer: stream s starts `stride` complex samples after stream s-1 (the streams may
+        be windows into longer rows)."""
         import torch
         from . import _dev
-        n_streams, stride = iq.shape[0], iq.shape[1]
         h, lib = self._h, self._h.lib
         st = _dev.stream_ptr(self.device)
         if keep_symbols and self.symbols is None:
             self.symbols = _dev.zeros((self.max_streams, self.max_sym, 2), torch.float32, self.device)
         self.metric.zero_()
-        _lib.check(lib.tb200_etsi_demod_batch(h.h, iq.data_ptr(), n_streams, int(n_samples), int(stride), self.fs,
+        _lib.check(lib.tb200_etsi_demod_batch(h.h, int(iq_ptr), n_streams, int(n_samples), int(stride), self.fs,
                                               self.symbols.data_ptr() if keep_symbols else None, self.soft.data_ptr(),
                                               self.soft_stride, self.n_soft.data_ptr(), st))
         _lib.check(lib.tb200_etsi_find_bursts(h.h, self.soft.data_ptr(), n_streams, self.soft_stride, self.n_soft.data_ptr(),
