@@ -38,6 +38,9 @@ extern "C" {
 
 #define TB200_DTYPE_C64 0
 #define TB200_DTYPE_C128 1
+/* interleaved int16 (I, Q) as the bladeRF delivers it (SC16Q11); converted on the device exactly like
+ * BladeRFCapture.read_samples does on the host: complex64(I, Q) / 32768  (signal/capture.py:255-269) */
+#define TB200_DTYPE_SC16 2
 
 /* decimator arithmetic: EXACT = scipy's float32 op order, sequential per (chunk, I/Q) lane,
  * bit-identical to the reference; FAST = time-tiled, same filter, float32/float64 mixed,

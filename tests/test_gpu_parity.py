@@ -254,3 +254,27 @@ def test_fast_mode_within_tolerance(mods, golden_process, process_inputs, fmode)
     fs, f, iq = process_inputs["wide_q83"]
     spw = signal.SignalProcessor(fs, mode=fmode)
     assert np.array_equal(spw.process(iq, f), golden_process["wide_q83/dibits"])
+
+
+def test_sc16_input_is_bit_identical(mods):
+    """N2: int16 SC16Q11 input converted on the device == process(complex64(I, Q) / 32768) of the reference's
+    capture layer (signal/capture.py:255-269)."""
+    signal, pipeline = mods[0], mods[2]
+    from tetraear_b200 import synth
+    cap = synth.make_capture(3 * 131072, 130, seed=77, amplitude=0.7)
+    raw = np.clip(np.rint(cap.view(np.float32) * 32768.0), -32768, 32767).astype(np.int16).reshape(-1, 2)
+    as_c64 = (raw[:, 0].astype(np.float32) + 1j * raw[:, 1].astype(np.float32)).astype(np.complex64) / 32768.0
+    for mode in ("exact", "fast"):
+        sp = signal.SignalProcessor(2.4e6, mode=mode)
+        a = sp.process_sc16(raw[:131072], 250.0)
+        sa = sp.symbols
+        b = sp.process(as_c64[:131072], 250.0)
+        assert np.array_equal(a, b) and np.array_equal(sa, sp.symbols)
+    od, _, _ = oracle.process(as_c64[:131072], 2.4e6, 250.0)
+    assert np.array_equal(b, od)
+    pipe = pipeline.ReceivePipeline(2.4e6, 131072, max_chunks=3, mode="fast", n_lanes=2)
+    n1, f1, s1 = pipe.run_host(raw.reshape(3, 131072, 2))
+    n1, f1, s1 = n1.copy(), f1.copy(), s1.copy()
+    n2, f2, s2 = pipe.run_host(as_c64.reshape(3, 131072))
+    assert np.array_equal(n1, n2) and np.array_equal(s1, s2) and s1[1] > 0
+    assert all(np.array_equal(f1[c, :n1[c]], f2[c, :n2[c]]) for c in range(3))

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libtetra_b200.so")
 
-DTYPE_C64, DTYPE_C128 = 0, 1
+DTYPE_C64, DTYPE_C128, DTYPE_SC16 = 0, 1, 2
 MODE_EXACT, MODE_FAST = 0, 1
 OPT_CHAN_F32 = 1
 OPT_PSD_F32 = 2

@@ -82,6 +82,7 @@ static size_t carve(tb200_handle h, char *base)
     // staging for *_host
     h->stage_in_bytes = C * L * 8;
     h->stage_in = c.take<char>(h->stage_in_bytes);
+    h->stage_sc16 = c.take<char>(h->stage_in_bytes / 2);
     h->stage_out_stride = (size_t)P.max_symbols + 8;
     h->stage_dibits = c.take<uint8_t>(C * h->stage_out_stride);
     h->stage_symbols = c.take<char>(C * h->stage_out_stride * 16);
@@ -263,8 +264,19 @@ extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, 
                                    void *stream)
 {
     if (!h || !d_n_dibits || n_chunks < 0 || chunk_len < 0) return fail(TB200_E_ARG, "tb200_process_batch: bad argument");
-    if (dtype != TB200_DTYPE_C64 && dtype != TB200_DTYPE_C128) return fail(TB200_E_ARG, "tb200_process_batch: dtype");
+    if (dtype != TB200_DTYPE_C64 && dtype != TB200_DTYPE_C128 && dtype != TB200_DTYPE_SC16)
+        return fail(TB200_E_ARG, "tb200_process_batch: dtype");
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TB200_DTYPE_SC16 && n_chunks > 0 && chunk_len > 0) {
+        // int16 IQ: convert into the complex64 staging area, then this is the ordinary complex64 path
+        if (!d_iq) return fail(TB200_E_ARG, "tb200_process_batch: null buffer");
+        if (n_chunks > h->cfg.max_chunks || chunk_len > h->cfg.max_chunk_len || chunk_stride != chunk_len)
+            return fail(TB200_E_ARG, "tb200_process_batch: SC16 input must be dense and within the handle capacity");
+        int rc = launch_sc16_to_c64(h, d_iq, (long)n_chunks * chunk_len, h->stage_in, st);
+        if (rc) return rc;
+        d_iq = h->stage_in;
+        dtype = TB200_DTYPE_C64;
+    }
     if (n_chunks == 0) return TB200_OK;
     if (n_chunks > h->cfg.max_chunks || chunk_len > h->cfg.max_chunk_len)
         return fail(TB200_E_ARG, "tb200_process_batch: %d x %d exceeds the handle capacity %d x %d", n_chunks, chunk_len,
@@ -340,18 +352,20 @@ extern "C" int tb200_process_batch_host(tb200_handle h, const void *h_iq, int dt
     if (n_chunks <= 0) return TB200_OK;
     if (n_chunks > h->cfg.max_chunks || chunk_len > h->cfg.max_chunk_len)
         return fail(TB200_E_ARG, "tb200_process_batch_host: exceeds the handle capacity");
-    const size_t esz = dtype == TB200_DTYPE_C64 ? 8 : 16;
+    const size_t esz = dtype == TB200_DTYPE_C64 ? 8 : (dtype == TB200_DTYPE_SC16 ? 4 : 16);
     size_t in_bytes = (size_t)n_chunks * chunk_len * esz;
-    if (in_bytes > h->stage_in_bytes) return fail(TB200_E_ARG, "tb200_process_batch_host: input exceeds staging (complex128 needs 2x)");
+    void *stage = dtype == TB200_DTYPE_SC16 ? h->stage_sc16 : h->stage_in;
+    if (in_bytes > (dtype == TB200_DTYPE_SC16 ? h->stage_in_bytes / 2 : h->stage_in_bytes))
+        return fail(TB200_E_ARG, "tb200_process_batch_host: input exceeds staging (complex128 needs 2x)");
     if ((size_t)out_stride > h->stage_out_stride) return fail(TB200_E_ARG, "tb200_process_batch_host: out_stride too large");
-    if (in_bytes) TB_CUDA(cudaMemcpyAsync(h->stage_in, h_iq, in_bytes, cudaMemcpyHostToDevice, st));
+    if (in_bytes) TB_CUDA(cudaMemcpyAsync(stage, h_iq, in_bytes, cudaMemcpyHostToDevice, st));
     double *d_f = nullptr;
     if (h_freq_off) {
         TB_CUDA(cudaMemcpyAsync(h->stage_freq, h_freq_off, sizeof(double) * n_chunks, cudaMemcpyHostToDevice, st));
         d_f = h->stage_freq;
     }
     int32_t *d_cnt = h->stage_counts, *d_ph = h->stage_counts + n_chunks;
-    int rc = tb200_process_batch(h, h->stage_in, dtype, n_chunks, chunk_len, chunk_len, d_f, h->stage_dibits,
+    int rc = tb200_process_batch(h, stage, dtype, n_chunks, chunk_len, chunk_len, d_f, h->stage_dibits,
                                  h_symbols ? h->stage_symbols : nullptr, out_stride, d_cnt, d_ph, stream);
     if (rc) return rc;
     if (h_dibits) TB_CUDA(cudaMemcpyAsync(h_dibits, h->stage_dibits, (size_t)n_chunks * out_stride, cudaMemcpyDeviceToHost, st));

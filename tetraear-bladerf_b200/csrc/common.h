@@ -81,6 +81,7 @@ struct tb200_handle_s {
     float *etsi_taps;                         // [32 phases][32 taps] interpolating matched filter
     // staging for the *_host entry points
     void *stage_in;   size_t stage_in_bytes;
+    void *stage_sc16;                         // int16 IQ staging of the host entry point
     uint8_t *stage_dibits; void *stage_symbols; int32_t *stage_counts; double *stage_freq;
     size_t stage_out_stride;
     uint8_t *stage_burst_in, *stage_burst_rec, *stage_burst_full; int64_t *stage_stats;

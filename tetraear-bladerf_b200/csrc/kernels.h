@@ -42,6 +42,7 @@ int launch_etsi_find_bursts(tb200_handle h, const float *soft, int n_streams, lo
                             cudaStream_t st);
 int launch_channelizer(tb200_handle h, const float2 *x, long n, int M, float *proto_dev, float2 *tw_dev, float2 *out,
                        long out_stride, long n_frames, cudaStream_t st);
+int launch_sc16_to_c64(tb200_handle h, const void *in, long n, void *out, cudaStream_t st);
 int launch_freq_shift(tb200_handle h, const void *x, int dtype, long n, double f, double fs, double *out, cudaStream_t st);
 
 }  // namespace tb200

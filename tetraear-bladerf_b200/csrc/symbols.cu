@@ -179,6 +179,24 @@ int launch_slicer(tb200_handle h, const double *symbols, long n, uint8_t *dibits
     return TB200_OK;
 }
 
+// SC16Q11 -> complex64: complex64(I, Q) / 32768 (capture.py:255-269; the quotient by 2^15 is exact)
+__global__ void sc16_to_c64_kernel(const short2 *__restrict__ in, long n, float2 *__restrict__ out)
+{
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    long stride = (long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) { short2 v = in[i]; out[i] = make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f)); }
+}
+
+int launch_sc16_to_c64(tb200_handle h, const void *in, long n, void *out, cudaStream_t st)
+{
+    if (n <= 0) return TB200_OK;
+    long blocks = (n + 255) / 256;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    sc16_to_c64_kernel<<<(unsigned)blocks, 256, 0, st>>>((const short2 *)in, n, (float2 *)out);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
 // frequency_shift as a stand-alone stage (processor.py:85-100)
 template <typename TI>
 __global__ void freq_shift_kernel(const TI *__restrict__ x, long n, double W, double fs, double *__restrict__ out)

@@ -53,7 +53,7 @@ class ReceivePipeline:
     def run_device(self, iq, freq_off=None, decode=True):
         """iq: CUDA tensor, float32 [n_chunks, chunk_len, 2] (interleaved complex64).  Asynchronous."""
         n_chunks = iq.shape[0]
-        assert iq.is_cuda and iq.dtype == torch.float32 and iq.shape[1] == self.chunk_len and iq.is_contiguous()
+        assert iq.is_cuda and iq.dtype in (torch.float32, torch.int16) and iq.shape[1] == self.chunk_len and iq.is_contiguous()
         main = torch.cuda.current_stream(self.dev)
         if self.n_lanes == 1 or n_chunks <= self.n_lanes:
             self._run_slice(self.handles[0], main.cuda_stream, iq, freq_off, 0, n_chunks, decode)
@@ -78,10 +78,11 @@ class ReceivePipeline:
     def _run_slice(self, handle, stream, iq, freq_off, lo, hi, decode):
         lib, h = handle.lib, handle.h
         n = hi - lo
-        esz = self.chunk_len * 8
+        sc16 = iq.dtype == torch.int16
+        esz = self.chunk_len * (4 if sc16 else 8)
         sym_ptr = self.symbols.data_ptr() + lo * self.stride * 16 if self.symbols is not None else None
         _lib.check(lib.tb200_process_batch(
-            h, iq.data_ptr() + lo * esz, _lib.DTYPE_C64, n, self.chunk_len, self.chunk_len,
+            h, iq.data_ptr() + lo * esz, _lib.DTYPE_SC16 if sc16 else _lib.DTYPE_C64, n, self.chunk_len, self.chunk_len,
             freq_off.data_ptr() + lo * 8 if freq_off is not None else None, self.dibits.data_ptr() + lo * self.stride,
             sym_ptr, self.stride, self.n_dibits.data_ptr() + lo * 4, self.phase.data_ptr() + lo * 4, stream))
         if decode:
@@ -97,10 +98,13 @@ class ReceivePipeline:
         H2D -> kernels -> D2H of (n_dibits, n_frames, stats, frame records).  Synchronous.
         Returns (n_frames per chunk, frame records, stats) as numpy."""
         if isinstance(iq_host, np.ndarray):
-            iq_host = torch.from_numpy(iq_host.view(np.float32).reshape(iq_host.shape[0], -1, 2))
+            if iq_host.dtype == np.int16:              # SC16Q11: [n_chunks, chunk_len, 2] int16, converted on the device
+                iq_host = torch.from_numpy(np.ascontiguousarray(iq_host).reshape(iq_host.shape[0], -1, 2))
+            else:
+                iq_host = torch.from_numpy(iq_host.view(np.float32).reshape(iq_host.shape[0], -1, 2))
         n_chunks = iq_host.shape[0]
-        if self._staging is None or self._staging.shape[0] < n_chunks:
-            self._staging = torch.empty((self.max_chunks, self.chunk_len, 2), dtype=torch.float32, device=self.dev)
+        if self._staging is None or self._staging.shape[0] < n_chunks or self._staging.dtype != iq_host.dtype:
+            self._staging = torch.empty((self.max_chunks, self.chunk_len, 2), dtype=iq_host.dtype, device=self.dev)
             self._host_nfr = torch.empty((self.max_chunks,), dtype=torch.int32).pin_memory()
             self._host_stats = torch.empty((3,), dtype=torch.int64).pin_memory()
             self._host_frames = torch.empty(self.frames.shape, dtype=torch.uint8).pin_memory()
@@ -159,8 +163,8 @@ class ReceivePipeline:
                 tot[k] = (a[0] + ms, a[1] + calls)
         return tot
 
-    def h2d_bytes(self, n_chunks):
-        return n_chunks * self.chunk_len * 8
+    def h2d_bytes(self, n_chunks, sc16=False):
+        return n_chunks * self.chunk_len * (4 if sc16 else 8)
 
     def d2h_bytes(self, n_chunks):
         return n_chunks * (4 + 4 + self.max_frames * _lib.FRAME_DTYPE.itemsize) + 24

@@ -86,6 +86,30 @@ class SignalProcessor:
         self.best_phase = int(phase[0])
         return dibits[:nd].copy()
 
+    def process_sc16(self, iq_int16, freq_offset=0):
+        """process() for the bladeRF's native SC16Q11 buffer (interleaved int16 I, Q): the conversion
+        ``complex64(I, Q) / 32768`` of BladeRFCapture.read_samples (signal/capture.py:255-269) runs on the
+        device, so only 4 bytes per sample cross PCIe.  Bit-identical to process(complex64(I, Q) / 32768)."""
+        raw = np.ascontiguousarray(iq_int16, dtype=np.int16).reshape(-1, 2)
+        n = raw.shape[0]
+        if n == 0:
+            self.symbols = np.array([], dtype=complex)
+            return np.array([], dtype=np.uint8)
+        h = self._handle(n)
+        p = _lib.plan(self.sample_rate, n)
+        stride = max(int(p.max_symbols), 1)
+        dibits = np.empty(stride, dtype=np.uint8)
+        symbols = np.empty(stride, dtype=np.complex128)
+        cnt = np.zeros(1, dtype=np.int32)
+        phase = np.zeros(1, dtype=np.int32)
+        f = np.array([float(freq_offset)], dtype=np.float64)
+        _lib.check(h.lib.tb200_process_batch_host(h.h, raw.ctypes.data, _lib.DTYPE_SC16, 1, n, f.ctypes.data,
+                                                  dibits.ctypes.data, symbols.ctypes.data, stride, cnt.ctypes.data,
+                                                  phase.ctypes.data, None))
+        self.symbols = symbols[:self._n_symbols(p, int(phase[0]))].copy()
+        self.best_phase = int(phase[0])
+        return dibits[:int(cnt[0])].copy()
+
     @staticmethod
     def _n_symbols(p, best):
         if p.n_dec <= 0:
