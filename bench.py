@@ -340,6 +340,22 @@ def other_workloads(device, peak):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
+    # ---- drop-in per-call latency: one 131072-sample chunk through the mirrored Python API, host numpy in/out
+    from tetraear_b200.signal import SignalProcessor
+    from tetraear_b200.core import TetraDecoder
+    chunk = synth.make_capture(CHUNK, 130, seed=1234)
+    sp, dec = SignalProcessor(FS, mode="fast"), TetraDecoder(auto_decrypt=False)
+    for _ in range(3):
+        frames = dec.decode(sp.process(chunk, 0.0))
+    t0 = time.perf_counter()
+    for _ in range(20):
+        frames = dec.decode(sp.process(chunk, 0.0))
+    lat = (time.perf_counter() - t0) / 20
+    out["per_call_latency_one_chunk"] = {"ms": round(lat * 1e3, 3), "frames": len(frames),
+                                         "note": "SignalProcessor.process + TetraDecoder.decode, wall clock incl. H2D/D2H and the "
+                                                 "host MAC header walk; the chunk lasts 54.6 ms at 2.4 MS/s (reference: ~60 ms per chunk)"}
+    del sp, dec
+
     # ---- c2: 60 s @2.4 MS/s, N = 4096 dense frames, power + EMA-smoothed output (float32)
     n = 144_000_000
     nfr = n // 4096

@@ -79,7 +79,8 @@ typedef struct tb200_plan {
     double rate;          /* sample rate after decimation */
 } tb200_plan;
 
-/* one kept frame of TetraDecoder.decode (core/decoder.py:861-888 + decode_frame :890-992) */
+/* one frame candidate of TetraDecoder.decode (core/decoder.py:861-888 + decode_frame :890-992) with the
+ * fixed-offset MAC header fields of parse_mac_pdu — 152 bytes */
 typedef struct tb200_frame {
     int32_t sync_pos;     /* bit position of the training sequence */
     int32_t start_pos;    /* sync_pos - 216 */
@@ -90,7 +91,9 @@ typedef struct tb200_frame {
     uint8_t crc_ok;       /* TetraBurst.crc_ok, protocol.py:292-329 */
     uint8_t mac_ok;       /* parse_mac_pdu() would return a PDU (protocol.py:349-596) */
     uint8_t kept;         /* 1 unless dropped by decoder.py:1092-1100 (mac None and CRC bad) */
-    uint8_t pad[2];
+    uint8_t mac_fill;     /* MAC header fill-bit indicator, data bit 4 (protocol.py:402, :454, :510) */
+    uint8_t mac_length;   /* length field: data bits 29..34 (MAC-RESOURCE, :418-421) or 5..10 (MAC-END, :514-517), else 0 */
+    uint32_t mac_address; /* 24-bit address, data bits 5..28, MAC-RESOURCE only (:410-413), else 0 */
     uint8_t bits[64];     /* the 510 frame bits (frame['bits']), MSB-first packed */
     uint8_t data[64];     /* TetraBurst.data_bits packed: 216 (normal) or 510 (sync) bits */
 } tb200_frame;

@@ -46,8 +46,16 @@ def test_decode_fuzz(mods):
                  bool(r["crc_ok"]), bool(r["mac_ok"])) for r in kept] == \
                [(f["sync_pos"], f["number"], f["type"], f["enc_mode"], f["burst_type"], f["burst_crc"], f["mac_ok"])
                 for f in ofr], case
+        host = core.TetraProtocolParser()
         for r, f in zip(kept, ofr):
             assert np.array_equal(np.unpackbits(r["bits"])[:510], f["bits"]), case
+            # N1: the fixed-offset MAC header fields on the record equal the host header walk
+            nd = 510 if int(r["burst_type"]) == 5 else 216
+            pdu = host.parse_mac_pdu(np.unpackbits(r["data"])[:nd])
+            if pdu is not None and pdu.pdu_type.name in ("MAC_RESOURCE", "MAC_END"):
+                assert int(r["mac_length"]) == pdu.length and int(r["mac_fill"]) == pdu.fill_bits, case
+                if pdu.pdu_type.name == "MAC_RESOURCE":
+                    assert int(r["mac_address"]) == pdu.address, case
         st = dec.protocol_parser.stats
         assert (st["total_bursts"], st["crc_pass"], st["crc_fail"]) == (ost["total_bursts"], ost["crc_pass"], ost["crc_fail"]), case
         n_frames_total += len(ofr)

@@ -31,8 +31,9 @@ class Plan(C.Structure):
 
 FRAME_DTYPE = np.dtype([("sync_pos", "<i4"), ("start_pos", "<i4"), ("number", "<i4"), ("type", "u1"),
                         ("enc_mode", "u1"), ("burst_type", "u1"), ("crc_ok", "u1"), ("mac_ok", "u1"),
-                        ("kept", "u1"), ("pad", "u1", (2,)), ("bits", "u1", (64,)), ("data", "u1", (64,))])
-assert FRAME_DTYPE.itemsize == 148
+                        ("kept", "u1"), ("mac_fill", "u1"), ("mac_length", "u1"), ("mac_address", "<u4"),
+                        ("bits", "u1", (64,)), ("data", "u1", (64,))])
+assert FRAME_DTYPE.itemsize == 152
 
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 _PROTOS = {

@@ -198,6 +198,7 @@ __global__ void find_sync_kernel(const uint8_t *__restrict__ m1, const uint8_t *
 // ------------------------------------------------------------------ burst parsing, warp-resident
 struct BurstOut {
     uint32_t burst_type, crc_ok, mac_ok, hdr, sync_match;
+    uint32_t mac_fill, mac_length, mac_address;     // fixed-offset MAC header fields (protocol.py:399-421, :510-517)
 };
 
 __device__ __forceinline__ unsigned warp_xor(unsigned v)
@@ -291,6 +292,9 @@ __device__ void warp_parse_burst(unsigned w, const uint16_t *__restrict__ tab, c
     out.mac_ok = mac_ok;
     out.hdr = (type << 2) | enc;
     out.sync_match = (unsigned)mx;
+    out.mac_fill = (type != 2) ? fld(4, 1) : 0u;
+    out.mac_address = (type == 0) ? fld(5, 24) : 0u;
+    out.mac_length = (type == 0) ? fld(29, 6) : (type == 3) ? fld(5, 6) : 0u;
     if (rec) {
         // bytes 0..26: first 216 data bits packed
         unsigned byte = data_byte(w, is_sync, lane);
@@ -401,6 +405,9 @@ __device__ __forceinline__ void warp_parse_burst_v2(unsigned w, const uint16_t (
     else mac_ok = !((int)(fld(5, 6) * 8) > n_data - 11 + 16);
     out.burst_type = is_sync ? 5u : 2u; out.crc_ok = crc_ok; out.mac_ok = mac_ok; out.hdr = (type2 << 2) | enc;
     out.sync_match = (unsigned)mx;
+    out.mac_fill = (type2 != 2) ? fld(4, 1) : 0u;
+    out.mac_address = (type2 == 0) ? fld(5, 24) : 0u;
+    out.mac_length = (type2 == 0) ? fld(29, 6) : (type2 == 3) ? fld(5, 6) : 0u;
     // record: 27 packed data bytes + 5 flag bytes, one byte per lane -> the warp writes 32 contiguous bytes
     unsigned byte;
     {
@@ -486,7 +493,7 @@ __device__ void decode_stream_warp(const uint8_t *b, const uint8_t *mp, const ui
         // decoder.py:867-871 bounds, and decode_frame's len(bits) < 510 -> None (:894)
         bool ok = start_pos >= 0 && (start_sym + 255 <= nsym) && (start_pos + 510 <= nb);
         tb200_frame *fr = fo + f;
-        BurstOut o = {0, 0, 0, 0, 0};
+        BurstOut o = {0, 0, 0, 0, 0, 0, 0, 0};
         unsigned fw = 0;
         if (ok) {
             // frame bits come from the BIT stream at start_pos, burst symbols from the SYMBOL stream at
@@ -517,7 +524,9 @@ __device__ void decode_stream_warp(const uint8_t *b, const uint8_t *mp, const ui
             fr->crc_ok = (uint8_t)o.crc_ok;
             fr->mac_ok = (uint8_t)o.mac_ok;
             fr->kept = (uint8_t)(ok && (o.crc_ok || o.mac_ok));   // decoder.py:1092-1100
-            fr->pad[0] = fr->pad[1] = 0;
+            fr->mac_fill = (uint8_t)o.mac_fill;
+            fr->mac_length = (uint8_t)o.mac_length;
+            fr->mac_address = o.mac_address;
         }
     }
     if (lane == 0) {
