@@ -148,6 +148,9 @@ int tb200_process_batch_host(tb200_handle h, const void *h_iq, int dtype, int n_
                              int out_stride, int32_t *h_n_dibits, int32_t *h_phase, void *stream);
 
 /* ---- stage-level entry points (one array each; the per-method Python API and parity tests) */
+/* resample (processor.py:35-49) = scipy.signal.resample(x, num) for complex input: num complex samples of the
+ * input dtype.  O(n * min(n, num)) direct DFT in float64 — not on the receive path (no caller uses it). */
+int tb200_resample(tb200_handle h, const void *d_x, int dtype, int n, int num, void *d_out, void *stream);
 /* scipy.signal.decimate(x, q) (processor.py:254).  out: ceil(n/q) samples of the same dtype. */
 int tb200_decimate(tb200_handle h, const void *d_x, int dtype, int n, int q, void *d_out, void *stream);
 /* frequency_shift (processor.py:85-100): out complex128[n] = x * exp(-j 2 pi f k / fs) */

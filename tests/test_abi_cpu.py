@@ -85,6 +85,8 @@ def test_no_cpu_fallback(lib):
         _lib.Handle()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         SignalProcessor().process(np.ones(1000, np.complex64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        SignalProcessor().resample(np.ones(100, np.complex64), 1.2e6)
     # empty input needs no device, exactly like the reference (processor.py:239-241)
     sp = SignalProcessor()
     assert len(sp.process(np.array([], np.complex64))) == 0 and len(sp.symbols) == 0

@@ -278,3 +278,25 @@ def test_sc16_input_is_bit_identical(mods):
     n2, f2, s2 = pipe.run_host(as_c64.reshape(3, 131072))
     assert np.array_equal(n1, n2) and np.array_equal(s1, s2) and s1[1] > 0
     assert all(np.array_equal(f1[c, :n1[c]], f2[c, :n2[c]]) for c in range(3))
+
+
+def test_resample_matches_scipy(mods, process_inputs):
+    """a8: SignalProcessor.resample == scipy.signal.resample (the reference's processor.py:46-48), incl. the
+    unpaired-bin rule for even lengths, up- and down-sampling, and the reference's own test call
+    (tests/unit/test_signal_processor.py:27-34: 24000 samples at 2.4 MS/s -> 1.2 MS/s)."""
+    import scipy.signal as sg
+    signal = mods[0]
+    sp = signal.SignalProcessor(2.4e6)
+    rng = np.random.default_rng(3)
+    for n, target in ((24000, 1.2e6), (1000, 1.8e6), (999, 0.7e6), (512, 4.8e6), (301, 3.3e6), (64, 2.4e6)):
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex128)
+        got = sp.resample(x, target)
+        ref = sg.resample(x, int(n * target / 2.4e6))
+        assert got.shape == ref.shape and np.iscomplexobj(got)
+        assert np.abs(got - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max()), (n, target)
+    x32 = process_inputs["c1_chunk0"][2][:6000]
+    got = sp.resample(x32, 1.0e6)
+    ref = sg.resample(x32.astype(np.complex128), int(6000 * 1.0e6 / 2.4e6))
+    assert got.dtype == np.complex64 and np.abs(got - ref).max() <= 1e-5
+    xr = rng.standard_normal(500)
+    assert np.abs(sp.resample(xr, 1.2e6) - sg.resample(xr, 250)).max() <= 1e-10

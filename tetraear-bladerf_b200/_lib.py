@@ -51,6 +51,7 @@ _PROTOS = {
     "tb200_launch_count": (_i64, [_vp]),
     "tb200_process_batch": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "tb200_process_batch_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "tb200_resample": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "tb200_decimate": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "tb200_freq_shift": (_i, [_vp, _vp, _i, _i, _d, _d, _vp, _vp]),
     "tb200_filter": (_i, [_vp, _vp, _i, _i, _d, _d, _vp, _vp]),

@@ -413,6 +413,16 @@ extern "C" int tb200_filter(tb200_handle h, const void *d_x, int dtype, int n, d
                                 (cudaStream_t)stream);
 }
 
+extern "C" int tb200_resample(tb200_handle h, const void *d_x, int dtype, int n, int num, void *d_out, void *stream)
+{
+    if (!h || n < 0 || num < 0 || (n && num && (!d_x || !d_out))) return fail(TB200_E_ARG, "tb200_resample: bad argument");
+    if (dtype != TB200_DTYPE_C64 && dtype != TB200_DTYPE_C128) return fail(TB200_E_ARG, "tb200_resample: dtype");
+    // scratch: the decimator workspaces (forward scratch + decimated chunks, carved back to back) are idle here
+    if (!h->fwd) return fail(TB200_E_ARG, "tb200_resample: handle has no process workspace");
+    size_t avail = (size_t)(((char *)h->dec_out + h->dec_bytes) - (char *)h->fwd);
+    return launch_resample(h, d_x, dtype, n, num, d_out, (double *)h->fwd, avail, (cudaStream_t)stream);
+}
+
 extern "C" int tb200_extract_symbols(tb200_handle h, const void *d_x_c128, int n, double fs, void *d_out_c128,
                                      int32_t *d_n_out, int32_t *d_phase, void *stream)
 {

@@ -43,6 +43,8 @@ int launch_etsi_find_bursts(tb200_handle h, const float *soft, int n_streams, lo
 int launch_channelizer(tb200_handle h, const float2 *x, long n, int M, float *proto_dev, float2 *tw_dev, float2 *out,
                        long out_stride, long n_frames, cudaStream_t st);
 int launch_sc16_to_c64(tb200_handle h, const void *in, long n, void *out, cudaStream_t st);
+int launch_resample(tb200_handle h, const void *x, int dtype, long n, long num, void *y, double *scratch, size_t scratch_bytes,
+                    cudaStream_t st);
 int launch_freq_shift(tb200_handle h, const void *x, int dtype, long n, double f, double fs, double *out, cudaStream_t st);
 
 }  // namespace tb200

@@ -58,9 +58,24 @@ class SignalProcessor:
 
     # ------------------------------------------------------------------ public API
     def resample(self, samples, target_rate):
-        """processor.py:35-49 (scipy FFT resampler).  No caller on the receive path uses it and it
-        has no GPU implementation yet; refusing is better than a silent CPU path."""
-        raise NotImplementedError("SignalProcessor.resample is not on the IQ->bursts path; not implemented on B200")
+        """processor.py:35-49: scipy.signal.resample(samples, int(n * target_rate / sample_rate)) on the GPU
+        (direct DFT; no caller on the receive path uses it).  Real input comes back real, like scipy's."""
+        x_in = np.asarray(samples)
+        n = len(x_in)
+        num = int(n * target_rate / self.sample_rate)
+        if n == 0 or num <= 0:
+            return np.zeros(max(num, 0), dtype=x_in.dtype if x_in.dtype.kind in "fc" else np.float64)
+        x, dt = _as_complex(x_in)
+        import torch
+        from .. import _dev
+        # scratch = the decimator workspace (~32 bytes per sample of capacity): room for the two twiddle tables + bins
+        h = self._handle(n + 2 * num + 64)
+        real = np.float32 if dt == _lib.DTYPE_C64 else np.float64
+        dx = _dev.to_dev(x.view(real), self.device)
+        out = _dev.empty((2 * num,), torch.float32 if dt == _lib.DTYPE_C64 else torch.float64, self.device)
+        _lib.check(h.lib.tb200_resample(h.h, dx.data_ptr(), dt, n, num, out.data_ptr(), _dev.stream_ptr(self.device)))
+        y = out.cpu().numpy().view(np.complex64 if dt == _lib.DTYPE_C64 else np.complex128)
+        return y if np.iscomplexobj(x_in) else y.real.astype(x_in.dtype if x_in.dtype.kind == "f" else np.float64)
 
     def process(self, samples, freq_offset=0):
         """processor.py:221-273: decimate -> NCO -> Butterworth -> timing pick -> DQPSK slicer."""
