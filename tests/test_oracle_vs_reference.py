@@ -1,0 +1,79 @@
+"""Live cross-check of the oracle against the UNMODIFIED reference on fresh seeds (beyond the committed
+golden vectors).  Runs only where /root/reference exists (the build container); skipped on the GPU box."""
+import logging
+
+import numpy as np
+import pytest
+
+from oracle import oracle, ref_bridge
+from tetraear_b200 import synth
+
+pytestmark = pytest.mark.skipif(not ref_bridge.available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    logging.disable(logging.CRITICAL)
+    yield ref_bridge.load()
+    logging.disable(logging.NOTSET)
+
+
+def test_process_and_decode_live(ref):
+    SP, TD, TP = ref
+    rng = np.random.default_rng(20260101)
+    for case in range(6):
+        fs, sps_total = [(2.4e6, 130), (1.8e6, 98), (2.4e6, 130)][case % 3]
+        n = int(rng.integers(20000, 140000))
+        f = float(rng.choice([0.0, rng.uniform(-2000, 2000)]))
+        iq = synth.make_capture(n, sps_total, seed=900 + case, sigma=0.04, mix=(0.6, 0.2, 0.2))
+        if f:
+            iq = (iq * np.exp(2j * np.pi * f * np.arange(n) / fs)).astype(np.complex64)
+        sp = SP(fs)
+        d_ref = sp.process(iq, f)
+        d, sym, _ = oracle.process(iq, fs, f)
+        assert np.array_equal(d, d_ref), case
+        assert np.abs(sym - sp.symbols).max() <= 1e-12 * max(1.0, np.abs(sp.symbols).max()), case
+        dec = TD(auto_decrypt=False)
+        fr_ref = dec.decode(d_ref)
+        fr, st = oracle.decode(d)
+        assert [(f_["number"], f_["type"], bool(f_.get("burst_crc"))) for f_ in fr_ref] == \
+               [(f_["number"], f_["type"], f_["burst_crc"]) for f_ in fr], case
+        rs = dec.protocol_parser.stats
+        assert (rs["total_bursts"], rs["crc_pass"], rs["crc_fail"]) == (st["total_bursts"], st["crc_pass"], st["crc_fail"])
+
+
+def test_parse_burst_and_mac_validity_live(ref):
+    SP, TD, TP = ref
+    rows = synth.make_burst_batch(400, seed=31337)
+    o = oracle.parse_bursts(rows)
+    for i, row in enumerate(rows):
+        b = TP().parse_burst(row)
+        assert b.burst_type.value == o["burst_type"][i] and bool(b.crc_ok) == bool(o["crc_ok"][i])
+        nd = int(o["n_data"][i])
+        assert np.array_equal(np.asarray(b.data_bits), o["data_bits"][i, :nd])
+        assert (TP().parse_mac_pdu(b.data_bits) is not None) == oracle.mac_pdu_valid(o["data_bits"][i, :nd])
+
+
+def test_host_mac_header_walk_matches_reference(ref):
+    """The host-side parse_mac_pdu kept in tetraear_b200.core (frame drop rule, fragment state) against the
+    reference's, PDU by PDU in sequence (fragment buffer state carried)."""
+    SP, TD, TP = ref
+    from tetraear_b200.core.protocol import TetraProtocolParser as Mine
+    rng = np.random.default_rng(5)
+    r, m = TP(), Mine.__new__(Mine)
+    Mine.__init__(m)
+    for i in range(600):
+        n = int(rng.choice([216, 510, 40, 7, 12]))
+        bits = rng.integers(0, 2, n)
+        if rng.random() < 0.5:
+            bits[0:2] = rng.choice([[0, 0], [0, 1], [1, 0], [1, 1]])
+            if rng.random() < 0.5 and n > 40:
+                bits[29:35] = [0, 0, 0, 1, 0, 1]
+        a, b = r.parse_mac_pdu(bits), m.parse_mac_pdu(bits)
+        assert (a is None) == (b is None), i
+        if a is not None:
+            assert (a.pdu_type.name, a.encrypted, a.address, a.length, a.data, a.fill_bits, a.encryption_mode,
+                    a.reassembled_data) == (b.pdu_type.name, b.encrypted, b.address, b.length, b.data, b.fill_bits,
+                                            b.encryption_mode, b.reassembled_data), i
+    assert {k: r.stats[k] for k in ("clear_mode_frames", "encrypted_frames")} == \
+           {k: m.stats[k] for k in ("clear_mode_frames", "encrypted_frames")}
