@@ -38,7 +38,7 @@ constexpr int FD_EDGE_S = 42;        // edge kernel: samples per lane (32 x 42 =
 struct FastDecimParams {
     float tap[FD_QMAX][4][2];        // p_i^j
     float lam[4][2];                 // lambda_i = p_i^q
-    float lampow[5][4][2];           // (lambda^R)^(2^s), Kogge-Stone multipliers
+    float lampow[6][4][2];           // (lambda^R)^(2^s), Kogge-Stone multipliers (s = 5 only for the edge term)
     float a0[4][2];                  // alpha_i
     float ap[4][2];                  // alpha_i p_i
     float aF[FD_R][4][2];            // alpha_i lambda^(r+1)
@@ -184,6 +184,53 @@ __device__ __forceinline__ void fd_half(const float2 *__restrict__ tile, int row
     }
 }
 
+constexpr int FD_NFIX = 160;           // outputs that receive the right-edge term (0.982^1600 ~ 2e-13)
+
+// kappa_i (packed over I, Q) of one chunk from the staged tile; s_end = tile index of ext[M-1].  One warp.
+__device__ __forceinline__ void fd_kappa(const float2 *__restrict__ tile, int s_end, int lane, const FastDecimParams &K, cp *kappa)
+{
+    cp S[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S[j].re = S[j].im = make_float2(0.f, 0.f);
+    const int s0 = s_end - 32 * FD_EDGE_S + 1 + lane * FD_EDGE_S;
+    for (int i = 0; i < FD_EDGE_S; ++i) {
+        const int si = s0 + i;
+        const float2 e = si >= 0 ? tile[si] : tile[0];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cp nx = cpmul(ld2(K.p[j]), S[j]);
+            nx.re.x += e.x; nx.re.y += e.y;
+            S[j] = nx;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int st = 0; st < 5; ++st) {
+            cp o;
+            o.re = shfl2_up(S[j].re, 1 << st); o.im = shfl2_up(S[j].im, 1 << st);
+            if (lane >= (1 << st)) S[j] = cpfma(ld2(K.pS[st][j]), o, S[j]);
+        }
+    }
+    // lane 31 holds F_j[M-1]; kappa_i = ka_i x_last + sum_j kM_ij F_j + kMc_ij conj(F_j)
+    if (lane == 31) {
+        const float2 xl = tile[s_end];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            cp k;
+            k.re = make_float2(K.ka[i][0] * xl.x, K.ka[i][0] * xl.y);
+            k.im = make_float2(K.ka[i][1] * xl.x, K.ka[i][1] * xl.y);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                k = cpfma(ld2(K.kM[i][j]), S[j], k);
+                cp cj; cj.re = S[j].re; cj.im = make_float2(-S[j].im.x, -S[j].im.y);
+                k = cpfma(ld2(K.kMc[i][j]), cj, k);
+            }
+            kappa[i] = k;
+        }
+    }
+}
+
 template <int Q>
 __global__ void __launch_bounds__(FD_W * 32, 3)
 decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int tiles_per_chunk, long n_dec,
@@ -203,6 +250,7 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
     __shared__ cp carryF[FD_W][4];
     __shared__ cp carryB[FD_W][4];
     __shared__ cf lanepow[32][4];
+    __shared__ cp kappa[4];
     if (threadIdx.x < 128) lanepow[threadIdx.x >> 2][threadIdx.x & 3] = ld2(K.lanepow[threadIdx.x >> 2][threadIdx.x & 3]);
 
     const int chunk = blockIdx.x / tiles_per_chunk;
@@ -210,7 +258,10 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float2 *xc = x + (long)chunk * chunk_stride;
     // first output of warp 0 (the left-halo pass) and the padded-signal position of tile row 0, col 0
-    const long k_tile0 = (long)tile * (FD_W - 2) * FD_P - FD_P;
+    // Tiles are aligned to the END of the chunk (the first one may be partial): the last (FD_W-2)*FD_P outputs and
+    // the whole right extension then live in ONE tile, which also computes and applies the right-edge term.
+    const bool last_tile = tile == tiles_per_chunk - 1;
+    const long k_tile0 = n_dec - (long)(tiles_per_chunk - tile) * (FD_W - 2) * FD_P - FD_P;
     const long t0 = 27 + (long)Q * k_tile0 - (Q - 1);
 
     // ---- stage the tile.  Interior tiles: ONE TMA bulk copy issued by thread 0, everybody waits on the
@@ -243,6 +294,9 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
         fd_half<Q, PITCH, false, FD_NM>(fd_tile, row0, lane, 0, K, y, carryB[w]);
         if (FD_NM == 2) fd_half<Q, PITCH, false, FD_NM>(fd_tile, row0, lane, 2, K, y, carryB[w]);
     }
+    // Right-edge transient (see the header): the right-halo warp of the chunk's last tile, which has only
+    // half a pass of work, derives kappa_i from F_i[M-1] = sum_k p_i^k ext[M-1-k] over the tile in smem.
+    if (last_tile && w == FD_W - 1) fd_kappa(fd_tile, (int)((n + 53) - t0), lane, K, kappa);
     __syncthreads();
     if (!store) return;
     // ---- carries from the neighbour passes: lambda^(lane R) cF on the left, lambda^((31-lane) R) cB on the right
@@ -255,6 +309,24 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
     }
     float2 *out = dec_out + (long)chunk * n_dec;
     const long k0 = k_tile0 + row0;
+    if (last_tile && n_dec - 1 - k0 < FD_NFIX + FD_R) {
+        // y[k] -= Re sum_i kappa_i pc_i lambda_i^mm,  mm = n_dec-1-k  (only the last FD_NFIX outputs matter)
+#pragma unroll
+        for (int r = 0; r < FD_R; ++r) {
+            const long mm = n_dec - 1 - (k0 + r);
+            if (mm < 0 || mm >= FD_NFIX) continue;
+            const int a = (int)(mm / FD_R), b = (int)(mm - (long)a * FD_R);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                cf g = ld2(K.pc[m]);
+#pragma unroll
+                for (int sft = 0; sft < 6; ++sft) if (a & (1 << sft)) g = cmulf(g, ld2(K.lampow[sft][m]));
+                const cf lam = ld2(K.lam[m]);
+                for (int i = 0; i < b; ++i) g = cmulf(g, lam);
+                y[r] = re_acc(cf{-g.x, -g.y}, kappa[m], y[r]);
+            }
+        }
+    }
 #pragma unroll
     for (int r = 0; r < FD_R; ++r) {
         long k = k0 + r;
@@ -394,7 +466,7 @@ static int make_fast_params(const DecimDesign &d, int q, long n, long n_dec, Fas
         for (int t = 0; t < q; ++t) { put(K.tap[t][j], pw); pw *= p8[j]; }
         put(K.lam[j], lam[j]);
         cd lr = std::pow(lam[j], FD_R);
-        for (int s = 0; s < 5; ++s) { put(K.lampow[s][j], lr); lr *= lr; }
+        for (int s = 0; s < 6; ++s) { put(K.lampow[s][j], lr); lr *= lr; }
         put(K.a0[j], alpha[j]);
         put(K.ap[j], alpha[j] * p8[j]);
         for (int r = 0; r < FD_R; ++r) {
@@ -459,12 +531,7 @@ int launch_decimate_fast(tb200_handle h, const void *x, int n_chunks, long n, lo
     if (q == 10) rc = launch_q<10>(h, x, n_chunks, n, chunk_stride, n_dec, K, dec_out, st);
     else if (q == 7) rc = launch_q<7>(h, x, n_chunks, n, chunk_stride, n_dec, K, dec_out, st);
     else rc = launch_q<8>(h, x, n_chunks, n, chunk_stride, n_dec, K, dec_out, st);
-    if (rc) return rc;
-    int threads = 128, blocks = (n_chunks * 32 + threads - 1) / threads;
-    decim_fast_edge_kernel<<<blocks, threads, 0, st>>>((const float2 *)x, n, chunk_stride, n_chunks, q, n_dec, K,
-                                                      (float2 *)dec_out);
-    TB_LAUNCH_CHECK(h);
-    return TB200_OK;
+    return rc;
 }
 
 }  // namespace tb200
