@@ -327,7 +327,7 @@ extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, 
             if (P.sps > 1 && P.sps <= TB200_MAX_PHASES &&
                 (size_t)n_chunks * (tiles + 1) * TB200_MAX_PHASES * sizeof(double) <= h->phase_bytes) {
                 ph_partial = h->phase_pw;
-                ph_tail = h->phase_pw + (size_t)n_chunks * tiles * TB200_MAX_PHASES;
+                ph_tail = nullptr;          // the channel filter applies its right-edge term itself: no separate tail sums
                 ph_tiles = tiles;
             }
             rc = launch_channel_fast(h, x, (P.q > 1) ? cur_dtype : dtype, n_chunks, P.n_dec, in_stride, d_freq_off, P.rate,

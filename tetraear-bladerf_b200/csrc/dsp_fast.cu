@@ -33,7 +33,7 @@ constexpr int FD_P = 32 * FD_R;      // outputs per warp pass
 constexpr int FD_W = 8;              // warps per CTA: 1 left-halo + 6 storing + 1 right-halo
 constexpr int FD_QMAX = 16;
 constexpr int FD_NM = 4;              // modes per FIR sweep (4 = one pass over the tile rows, 2 = two passes, fewer registers)
-constexpr int FD_EDGE_S = 42;        // edge kernel: samples per lane (32 x 42 = 1344; 0.982^1344 = 3e-11)
+constexpr int FD_EDGE_S = 42;        // right-edge term: samples per lane (32 x 42 = 1344; 0.982^1344 = 3e-11)
 
 struct FastDecimParams {
     float tap[FD_QMAX][4][2];        // p_i^j
@@ -332,101 +332,6 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
         long k = k0 + r;
         if (k >= 0 && k < n_dec) out[k] = make_float2(2.0f * y[r].x, 2.0f * y[r].y);
     }
-}
-
-// Right-end transient: the backward pass of filtfilt starts from the steady state of the LAST
-// forward output, not from the forward filter's continuation; the difference is a decaying sum of
-// the 4 modes, kappa_i p_i^(M-n).  One warp per chunk: lanes 0..7 run the (mode, I/Q) one-pole
-// recurrences over the last FD_EDGE_W padded samples to get F_i[M-1], then every lane corrects
-// its share of the last outputs.
-__global__ void decim_fast_edge_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_chunks, int q,
-                                       long n_dec, FastDecimParams K, float2 *__restrict__ dec_out)
-{
-    const int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (chunk >= n_chunks) return;
-    const float2 *xc = x + (long)chunk * chunk_stride;
-    const long M = n + 54;
-    const int m = lane & 3, comp = (lane >> 2) & 1;
-    // F_i[M-1] = sum_k p_i^k ext[M-1-k] over the last 32*S samples: lane l runs the 8 (mode, I/Q)
-    // one-pole recurrences over its own S samples from zero, an inclusive shuffle scan with
-    // multipliers (p^S)^(2^s) assembles the total on lane 31.
-    cf sI[4], sQ[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) sI[j] = sQ[j] = cf{0.f, 0.f};
-    const long tbeg = M - 32L * FD_EDGE_S + (long)lane * FD_EDGE_S;
-    float2 ev[FD_EDGE_S];
-#pragma unroll
-    for (int i = 0; i < FD_EDGE_S; ++i) ev[i] = padded_sample(xc, n, tbeg + i);
-#pragma unroll
-    for (int i = 0; i < FD_EDGE_S; ++i) {
-        const float2 e = ev[i];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cf pj = ld2(K.p[j]);
-            cf a = cmulf(pj, sI[j]), b = cmulf(pj, sQ[j]);
-            sI[j] = cf{a.x + e.x, a.y};
-            sQ[j] = cf{b.x + e.y, b.y};
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-#pragma unroll
-        for (int st = 0; st < 5; ++st) {
-            cf oI = cshfl_up(sI[j], 1 << st), oQ = cshfl_up(sQ[j], 1 << st);
-            if (lane >= (1 << st)) { cf g = ld2(K.pS[st][j]); sI[j] = cfma(g, oI, sI[j]); sQ[j] = cfma(g, oQ, sQ[j]); }
-        }
-        sI[j] = cshfl(sI[j], 31);
-        sQ[j] = cshfl(sQ[j], 31);
-    }
-    // lane (m, comp) of the first eight picks its own F
-    cf s = comp ? sQ[0] : sI[0];
-#pragma unroll
-    for (int j = 1; j < 4; ++j) if (m == j) s = comp ? sQ[j] : sI[j];
-    // kappa for (mode mi, comp ci) on lanes 0..7 : gather the four F_j of the same comp
-    float2 last = padded_sample(xc, n, M - 1);
-    float xlast = comp ? last.y : last.x;
-    cf kap = cf{K.ka[m][0] * xlast, K.ka[m][1] * xlast};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        cf Fj = cshfl(s, comp * 4 + j);
-        kap = cfma(ld2(K.kM[m][j]), Fj, kap);
-        kap = cfma(ld2(K.kMc[m][j]), cf{Fj.x, -Fj.y}, kap);
-    }
-    // every lane needs all 8 kappas
-    cf kI[4], kQ[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { kI[j] = cshfl(kap, j); kQ[j] = cshfl(kap, 4 + j); }
-    // outputs k = n_dec-1-mm, mm = lane, lane+32, ... : corr = 2 Re sum_i kappa_i pc_i lambda_i^mm
-    float2 *out = dec_out + (long)chunk * n_dec;
-    const int n_fix = 160;
-    cf lp[4], l32[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        cf lam = ld2(K.lam[j]);
-        cf a = cf{1.f, 0.f}, b = lam;
-        for (int bit = 0; bit < 5; ++bit) { if (lane & (1 << bit)) a = cmulf(a, b); b = cmulf(b, b); }
-        lp[j] = cmulf(a, ld2(K.pc[j]));      // pc lambda^lane
-        l32[j] = b;                           // lambda^32
-    }
-    float2 ov[5];
-#pragma unroll
-    for (int it = 0; it < 5; ++it) { long k = n_dec - 1 - (lane + 32 * it); ov[it] = (k >= 0) ? out[k] : make_float2(0.f, 0.f); }
-#pragma unroll
-    for (int it = 0; it < 5; ++it) {
-        long k = n_dec - 1 - (lane + 32 * it);
-        float cI = 0.f, cQ = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cI += kI[j].x * lp[j].x - kI[j].y * lp[j].y;
-            cQ += kQ[j].x * lp[j].x - kQ[j].y * lp[j].y;
-            lp[j] = cmulf(lp[j], l32[j]);
-        }
-        if (k >= 0) out[k] = make_float2(ov[it].x - 2.0f * cI, ov[it].y - 2.0f * cQ);
-    }
-    static_assert(5 * 32 == 160, "n_fix");
-    (void)n_fix;
-    (void)q;
 }
 
 // ---- host: modal design from the float32-rounded biquads (double precision) -----------------

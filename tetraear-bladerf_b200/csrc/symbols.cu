@@ -77,7 +77,7 @@ __global__ void symbols_kernel(const double *__restrict__ filtered, long n, long
             if ((p % step) == 0 && cnt > 0) {
                 tot = 0.0;
                 for (int t = 0; t < n_tiles; ++t) tot += phase_partial[((long)chunk * n_tiles + t) * TB200_MAX_PHASES + p];
-                tot += phase_tail[(long)chunk * TB200_MAX_PHASES + p];
+                if (phase_tail) tot += phase_tail[(long)chunk * TB200_MAX_PHASES + p];
                 tot = tot / (double)cnt;
             }
             s_pw[p] = tot;
