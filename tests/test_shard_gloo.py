@@ -53,7 +53,9 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_gather_world_size_2(tmp_path):
+def test_gather_world_size_2(tmp_path, monkeypatch):
+    # spawned children unpickle `_worker` by module name: the repo root must be importable there
+    monkeypatch.setenv("PYTHONPATH", ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert int(np.load(tmp_path / "n.npy")[0]) == 20
