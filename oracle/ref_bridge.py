@@ -27,7 +27,7 @@ def load():
         mod.BitArray = _bitstring_standin.BitArray
         sys.modules["bitstring"] = mod
     if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.append(REFERENCE_ROOT)      # at the END: the reference also has a top-level `tests` package
     from tetraear.signal.processor import SignalProcessor
     from tetraear.core.decoder import TetraDecoder
     from tetraear.core.protocol import TetraProtocolParser
