@@ -190,7 +190,8 @@ def run_b200(args):
     pipe.stats.zero_()
     e0.record(stream)
     for _ in range(args.steps):
-        pipe.run_device(dev)
+        pipe.run_device(dev, join=False)     # batches pipeline through the lane streams, each lane in order
+    pipe.join()                              # ... and all of them are complete before the stop event
     e1.record(stream)
     sync_all()
     ms = e0.elapsed_time(e1)

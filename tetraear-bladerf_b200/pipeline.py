@@ -36,7 +36,8 @@ class ReceivePipeline:
             for hh in self.handles:
                 hh.set_option(_lib.OPT_CHAN_F32, 1)
         self.h = self.handles[0]
-        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.n_lanes - 1)]
+        self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.n_lanes)]
+        self._pending = []
         C = self.max_chunks
         self.stride = int(self.plan.max_symbols) + 8
         self.max_frames = (2 * self.stride) // 250 + 2
@@ -50,8 +51,11 @@ class ReceivePipeline:
         self._staging = None
 
     # ---------------------------------------------------------------- device-resident path
-    def run_device(self, iq, freq_off=None, decode=True):
-        """iq: CUDA tensor, float32 [n_chunks, chunk_len, 2] (interleaved complex64).  Asynchronous."""
+    def run_device(self, iq, freq_off=None, decode=True, join=True):
+        """iq: CUDA tensor, float32 [n_chunks, chunk_len, 2] (interleaved complex64) or int16 (SC16Q11).
+        Asynchronous.  With join=False the current stream does NOT wait for the lanes: consecutive batches then
+        pipeline through the lane streams (each lane processes its sub-batches in order); call join() before
+        reading the outputs or timing."""
         n_chunks = iq.shape[0]
         assert iq.is_cuda and iq.dtype in (torch.float32, torch.int16) and iq.shape[1] == self.chunk_len and iq.is_contiguous()
         main = torch.cuda.current_stream(self.dev)
@@ -60,20 +64,27 @@ class ReceivePipeline:
             return n_chunks
         per = (n_chunks + self.n_lanes - 1) // self.n_lanes
         fork = torch.cuda.Event()
-        fork.record(main)
+        fork.record(main)                       # the batch (input, previous consumers) is ready at this point of `main`
         for li in range(self.n_lanes):
             lo, hi = li * per, min(n_chunks, (li + 1) * per)
             if lo >= hi:
                 break
-            st = main if li == 0 else self.streams[li - 1]
-            if li:
-                st.wait_event(fork)
+            st = self.streams[li]
+            st.wait_event(fork)
             self._run_slice(self.handles[li], st.cuda_stream, iq, freq_off, lo, hi, decode)
-            if li:
-                ev = torch.cuda.Event()
-                ev.record(st)
-                main.wait_event(ev)
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self._pending.append(ev)
+        if join:
+            self.join()
         return n_chunks
+
+    def join(self):
+        """Make the current stream wait for every lane's outstanding work."""
+        main = torch.cuda.current_stream(self.dev)
+        for ev in self._pending:
+            main.wait_event(ev)
+        self._pending = []
 
     def _run_slice(self, handle, stream, iq, freq_off, lo, hi, decode):
         lib, h = handle.lib, handle.h
@@ -123,9 +134,9 @@ class ReceivePipeline:
             lo, hi = li * per, min(n_chunks, (li + 1) * per)
             if lo >= hi:
                 break
-            st = main if li == 0 else self.streams[li - 1]
+            st = self.streams[li] if lanes > 1 else main
             with torch.cuda.stream(st):
-                if li:
+                if lanes > 1:
                     st.wait_event(fork)
                 # H2D of this lane's chunks, its kernels, D2H of its results: lane i+1's copy overlaps lane i's kernels
                 dev_iq[lo:hi].copy_(iq_host[lo:hi], non_blocking=True)
@@ -134,7 +145,7 @@ class ReceivePipeline:
                 if decode:
                     self._host_nfr[lo:hi].copy_(self.n_frames[lo:hi], non_blocking=True)
                     self._host_frames[lo:hi].copy_(self.frames[lo:hi], non_blocking=True)
-                if li:
+                if lanes > 1:
                     ev = torch.cuda.Event()
                     ev.record(st)
                     main.wait_event(ev)
