@@ -428,6 +428,37 @@ def other_workloads(device, peak):
                                    "receiver_ms": round(ms_rx, 3), "total_msamples_per_s": round(n / (ms_ch + ms_rx) / 1e3, 1),
                                    "bursts_found": found, "crc_ok_blocks_on_4_carriers": okb,
                                    "channelizer_frac_of_hbm_peak": round((n * 8 + M * nf * 8) / ms_ch / 1e6 / peak, 4)}
+    del wide, y, rx, ch
+    torch.cuda.empty_cache()
+
+    # ---- N3: scanner heuristics, 64 dwells x 262144 samples (one per scanned frequency), device-resident
+    from tetraear_b200.signal import TetraSignalDetector
+    nd, nsd = 64, 262144
+    dw = 0.05 * torch.randn((nd, nsd, 2), generator=g, device=dev, dtype=torch.float32)
+    det = TetraSignalDetector(FS, device=device)
+    det.stats_batch(dw, 5)
+    hd = det._handle(nd * nsd)
+    rec = torch.empty((nd, _lib.DETECT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    ms = timed(lambda: _lib.check(hd.lib.tb200_detect_batch(hd.h, dw.data_ptr(), _lib.DTYPE_C64, nd, nsd, nsd, FS, 5,
+                                                            rec.data_ptr(), stream)))
+    out["n3_detector_64x262144"] = {"msamples_per_s": round(nd * nsd / ms / 1e3, 1), "ms": round(ms, 4),
+                                    "achieved_gbs": round(nd * nsd * 16 / ms / 1e6, 1),
+                                    "frac_of_hbm_peak": round(nd * nsd * 16 / ms / 1e6 / peak, 4),
+                                    "note": "power/windows + modulation steps + sync-bit search; the dwell is read twice (max|x| first)"}
+    del dw
+
+    # ---- N4: codec frames, 1M frames gathered from bit rows
+    from tetraear_b200.voice import VoiceBlockBuilder
+    nv = 1_000_000
+    vb = VoiceBlockBuilder(device=device)
+    vrows = torch.randint(0, 2, (nv, 432), generator=g, device=dev, dtype=torch.uint8)
+    blocks = torch.empty((nv, 690), dtype=torch.int16, device=dev)
+    vld = torch.empty((nv,), dtype=torch.uint8, device=dev)
+    ms = timed(lambda: _lib.check(vb._h.lib.tb200_voice_blocks(vb._h.h, _lib.VOICE_BITS, vrows.data_ptr(), 432, None, None, None,
+                                                                nv, 127.0, blocks.data_ptr(), vld.data_ptr(), stream)))
+    out["n4_voice_blocks_1M"] = {"frames_per_s": round(nv / ms * 1e3, 0), "ms": round(ms, 4),
+                                 "achieved_gbs": round(nv * (432 + 1380) / ms / 1e6, 1),
+                                 "frac_of_hbm_peak": round(nv * (432 + 1380) / ms / 1e6 / peak, 4)}
     return out
 
 

@@ -254,6 +254,48 @@ int tb200_profile_read(tb200_handle h, double ms[8], int64_t calls[8]);
  * region 0 = decimated chunks, 1 = channel-filtered complex128, 2 / 3 = forward-pass scratches */
 int tb200_debug_read(tb200_handle h, int region, void *h_dst, size_t nbytes);
 
+/* ---- scanner heuristics, batched over dwells ----------------------------------------------
+ * Replaces the per-sample Python loops of TetraSignalDetector.calculate_power / detect_tetra_modulation /
+ * detect_sync_pattern / check_power_stability (tetraear/signal/scanner.py:42-55, :57-98, :100-147, :204-233).
+ * The device returns the sums and integer counts of each dwell; the caller finishes the scalar formulas
+ * (10 log10(sum/n + 1e-10), matches/n_steps > 0.4, sync_best/31 > 0.75, std(window dB) < 10). */
+typedef struct tb200_detect_stats {
+    double power_sum;        /* sum |x|^2 over the dwell */
+    double window_sum[8];    /* sum |x|^2 over window w = samples [w*window_size, (w+1)*window_size) */
+    double max_abs;          /* max |x| */
+    int64_t n;               /* samples per dwell */
+    int32_t window_size;     /* n / num_windows */
+    int32_t n_steps;         /* phase steps examined by detect_tetra_modulation (0 when n < 1000) */
+    int32_t matches;         /* ... of which within pi/8 of a multiple of pi/4 in [-pi, 3pi/4] */
+    int32_t n_sync_bits;     /* bits of detect_sync_pattern's stream (0 when fewer than 100 "symbols") */
+    int32_t sync_best;       /* best match count against the 31-bit pattern over range(n_sync_bits - 31) */
+    int32_t reserved;
+} tb200_detect_stats;        /* 112 bytes */
+
+/* d_iq: [n_dwells][stride] complex (dtype C64 or C128, arithmetic follows the dtype like numpy's), n samples used
+ * per dwell, fs = the detector's sample_rate (sets the sync stride int(fs/18000/10)), num_windows 0..8.
+ * d_out: device array of n_dwells records.  Needs a handle with max_chunks*max_chunk_len >= n_dwells*n. */
+int tb200_detect_batch(tb200_handle h, const void *d_iq, int dtype, int n_dwells, int64_t n, int64_t stride, double fs,
+                       int num_windows, tb200_detect_stats *d_out, void *stream);
+
+/* ---- codec-frame builder -------------------------------------------------------------------
+ * 690 int16 per frame: [0] = 0x6B21, 432 soft values in 1..114, 116..229, 231..344, 346..435.
+ *  TB200_VOICE_SYMBOLS  ui/modern.py:2309-2423 (_extract_voice_slot_from_symbols): d_src = dibit streams
+ *                       [n_streams][src_stride] with d_n_src[stream] valid dibits, frame f lives in stream
+ *                       d_frame_stream[f] (NULL = stream 0) at bit position d_frame_pos[f]; slot = dibits[pos/3 .. +255)
+ *  TB200_VOICE_BITS     continuous_capture.py:100-124: d_src = bit rows [n_frames][src_stride], d_n_src[f] = row length
+ *                       (NULL = src_stride); the first 432 bits -> +-127
+ *  TB200_VOICE_PARAMS   ui/modern.py:2143-2200 (fallback parameter packing), same source as BITS
+ *  TB200_VOICE_SOFT     d_src = float rows [n_frames][src_stride] of soft bits (+ = 1): clamp(rint(scale * s), +-127)
+ * d_valid[f] = 0 (and an all-zero block) where the reference produces no frame. */
+#define TB200_VOICE_SYMBOLS 0
+#define TB200_VOICE_BITS 1
+#define TB200_VOICE_PARAMS 2
+#define TB200_VOICE_SOFT 3
+int tb200_voice_blocks(tb200_handle h, int mode, const void *d_src, int64_t src_stride, const int32_t *d_n_src,
+                       const int32_t *d_frame_stream, const int32_t *d_frame_pos, int64_t n_frames, double scale,
+                       int16_t *d_blocks, uint8_t *d_valid, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

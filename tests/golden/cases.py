@@ -62,3 +62,29 @@ def burst_batch(n=3000, seed=99):
     d[0] = 0   # degenerate rows the reference special-cases (all-zero / all-one data)
     d[1] = 3
     return d
+
+
+def scanner_cases():
+    """(name, sample_rate, samples) dwells for the scanner heuristics."""
+    cap = synth.make_capture(262144, 130, seed=1234)
+    rng = np.random.default_rng(17)
+    n = 60000
+    noise = (0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    tone = (0.4 * np.exp(2j * np.pi * 4500.0 * np.arange(n) / 2.4e6)).astype(np.complex64) + noise * 0.01
+    cases = [("capture_256k", 2.4e6, cap), ("capture_c128", 2.4e6, cap[:60000].astype(np.complex128)),
+             ("noise", 2.4e6, noise), ("tone", 2.4e6, tone.astype(np.complex64)),
+             ("gap", 2.4e6, np.concatenate([cap[:30000], np.zeros(30000, np.complex64)])),
+             ("burst_then_quiet", 2.4e6, np.concatenate([cap[:20000], (1e-4 * noise[:40000]).astype(np.complex64)])),
+             ("short_900", 2.4e6, cap[:900]), ("short_1300", 2.4e6, cap[:1300]), ("short_4999", 2.4e6, cap[:4999]),
+             ("rate_1p8M", 1.8e6, synth.make_capture(98000, 98, seed=3)),
+             ("zeros", 2.4e6, np.zeros(12000, np.complex64))]
+    return cases
+
+
+def voice_cases():
+    """(dibit stream, bit positions) for the codec-frame builder."""
+    rng = np.random.default_rng(23)
+    dibits = rng.integers(0, 4, 1007, dtype=np.uint8)
+    pos = [0, 1, 2, 3, 300, 510, 1019, 2255, 2256, 2258, 2259, 3020, 5000]
+    bits = [rng.integers(0, 2, m, dtype=np.uint8) for m in (510, 432, 431, 600, 0, 510)]
+    return dibits, pos, bits

@@ -26,7 +26,7 @@ logging.disable(logging.CRITICAL)
 
 from oracle import ref_bridge  # noqa: E402
 from tetraear_b200 import synth  # noqa: E402
-from tests.golden.cases import process_cases, psd_chunks, burst_batch  # noqa: E402
+from tests.golden.cases import process_cases, psd_chunks, burst_batch, scanner_cases, voice_cases  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SP, TD, TP = ref_bridge.load()
@@ -174,8 +174,56 @@ def gen_psd():
          smoothed=np.stack(smoothed), freqs=ns["freqs"])
 
 
+# --------------------------------------------------------------- scanner heuristics (N3)
+def gen_scanner():
+    from tetraear.signal.scanner import TetraSignalDetector
+    out, names = {}, []
+    keys = ["power_db", "is_tetra", "confidence", "modulation_confidence", "sync_detected", "sync_correlation",
+            "frames_validated", "crc_pass_rate", "power_stable", "signal_present"]
+    for name, fs, x in scanner_cases():
+        det = TetraSignalDetector(sample_rate=fs)
+        r = det.analyze_signal(x)
+        names.append(name)
+        out[name + "/in_sha"] = np.array(sha(x))
+        out[name + "/fs"] = np.float64(fs)
+        out[name + "/analysis"] = np.array([float(r[k]) for k in keys], dtype=np.float64)
+        out[name + "/power_dtype"] = np.array(type(r["power_db"]).__name__)
+        out[name + "/power"] = np.float64(det.calculate_power(x))
+        out[name + "/mod"] = np.array(det.detect_tetra_modulation(x), dtype=np.float64)
+        out[name + "/sync"] = np.array(det.detect_sync_pattern(x), dtype=np.float64)
+        out[name + "/stable"] = np.array([det.check_power_stability(x), det.check_power_stability(x, 3)], dtype=np.float64)
+    out["names"] = np.array(names)
+    out["keys"] = np.array(keys)
+    save("scanner.npz", **out)
+
+
+# --------------------------------------------------------------- codec-frame builder (N4)
+def gen_voice():
+    """_extract_voice_slot_from_symbols is a method of a PyQt6 class (module not importable here): its source
+    LINES are read from the file, dedented and exec'd as a plain function — the reference's own text."""
+    modern = os.path.join(ref_bridge.REFERENCE_ROOT, "tetraear", "ui", "modern.py")
+    src = _lines(modern, 2309, 2423)
+    assert src.startswith("def _extract_voice_slot_from_symbols") and "0x6B21" in src
+    ns = {"logger": logging.getLogger("golden")}
+    exec(src, ns)
+    fn = ns["_extract_voice_slot_from_symbols"]
+    dibits, pos, _ = voice_cases()
+    blocks = np.zeros((len(pos), 690), np.int16)
+    valid = np.zeros(len(pos), np.uint8)
+    for i, p in enumerate(pos):
+        b = fn(None, {"position": p}, dibits, 13)
+        if b is not None:
+            blocks[i] = np.frombuffer(b, dtype="<i2")
+            valid[i] = 1
+    none_pos = fn(None, {}, dibits, 13)
+    assert none_pos is None
+    save("voice.npz", in_sha=np.array(sha(dibits)), blocks=blocks, valid=valid)
+
+
 if __name__ == "__main__":
     proc = gen_process()
     gen_decode(proc)
     gen_bursts()
     gen_psd()
+    gen_scanner()
+    gen_voice()

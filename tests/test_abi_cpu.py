@@ -36,6 +36,7 @@ def test_struct_sizes():
     assert _lib.FRAME_DTYPE.itemsize == 152
     assert ctypes.sizeof(_lib.Config) == 40       # 8 + 8 x int32
     assert ctypes.sizeof(_lib.Plan) == 32
+    assert _lib.DETECT_DTYPE.itemsize == 112     # tb200_detect_stats
 
 
 def test_decimator_design_is_scipys(lib):
@@ -87,6 +88,15 @@ def test_no_cpu_fallback(lib):
         SignalProcessor().process(np.ones(1000, np.complex64))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         SignalProcessor().resample(np.ones(100, np.complex64), 1.2e6)
+    from tetraear_b200.signal import TetraSignalDetector
+    from tetraear_b200.voice import VoiceBlockBuilder
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        TetraSignalDetector().detect_tetra_modulation(np.ones(2000, np.complex64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        VoiceBlockBuilder()
+    # below the reference's own length gates nothing is computed (scanner.py:66-67, :217-218)
+    assert TetraSignalDetector().detect_tetra_modulation(np.ones(10, np.complex64)) == (False, 0.0)
+    assert TetraSignalDetector().check_power_stability(np.ones(10, np.complex64)) is False
     # empty input needs no device, exactly like the reference (processor.py:239-241)
     sp = SignalProcessor()
     assert len(sp.process(np.array([], np.complex64))) == 0 and len(sp.symbols) == 0

@@ -77,3 +77,22 @@ def test_host_mac_header_walk_matches_reference(ref):
                                             b.encryption_mode, b.reassembled_data), i
     assert {k: r.stats[k] for k in ("clear_mode_frames", "encrypted_frames")} == \
            {k: m.stats[k] for k in ("clear_mode_frames", "encrypted_frames")}
+
+
+def test_scanner_heuristics_live(ref):
+    """oracle/scanner.py against the live TetraSignalDetector on fresh seeds (scanner.py:42-289)."""
+    from oracle import scanner as osc
+    from tetraear.signal.scanner import TetraSignalDetector
+    rng = np.random.default_rng(4242)
+    for case in range(5):
+        n = int(rng.integers(12000, 50000))
+        if case % 2:
+            x = (rng.uniform(0.01, 0.5) * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+        else:
+            x = synth.make_capture(n, 130, seed=300 + case, sigma=0.05)
+        if case == 3:
+            x = x.astype(np.complex128)
+        want = TetraSignalDetector(2.4e6).analyze_signal(x)
+        got = osc.analyze_signal(x, 2.4e6)
+        for k in want:
+            assert got[k] == want[k], (case, k, got[k], want[k])

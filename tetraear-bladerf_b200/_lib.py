@@ -34,6 +34,11 @@ FRAME_DTYPE = np.dtype([("sync_pos", "<i4"), ("start_pos", "<i4"), ("number", "<
                         ("kept", "u1"), ("mac_fill", "u1"), ("mac_length", "u1"), ("mac_address", "<u4"),
                         ("bits", "u1", (64,)), ("data", "u1", (64,))])
 assert FRAME_DTYPE.itemsize == 152
+DETECT_DTYPE = np.dtype([("power_sum", "<f8"), ("window_sum", "<f8", (8,)), ("max_abs", "<f8"), ("n", "<i8"),
+                         ("window_size", "<i4"), ("n_steps", "<i4"), ("matches", "<i4"), ("n_sync_bits", "<i4"),
+                         ("sync_best", "<i4"), ("reserved", "<i4")])
+assert DETECT_DTYPE.itemsize == 112
+VOICE_SYMBOLS, VOICE_BITS, VOICE_PARAMS, VOICE_SOFT = 0, 1, 2, 3
 
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 _PROTOS = {
@@ -71,6 +76,8 @@ _PROTOS = {
     "tb200_profile_read": (_i, [_vp, _vp, _vp]),
     "tb200_debug_read": (_i, [_vp, _i, _vp, C.c_size_t]),
     "tb200_psd_batch": (_i, [_vp, _vp, _i64, _i64, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
+    "tb200_detect_batch": (_i, [_vp, _vp, _i, _i, _i64, _i64, _d, _i, _vp, _vp]),
+    "tb200_voice_blocks": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i64, _d, _vp, _vp, _vp]),
 }
 EXPORTS = tuple(_PROTOS)
 

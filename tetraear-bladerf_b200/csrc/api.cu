@@ -533,6 +533,28 @@ extern "C" int tb200_crc16_rows(tb200_handle h, const uint8_t *d_bits, int n_row
     return launch_crc16_rows(h, d_bits, n_rows, n_bits, row_stride, d_crc, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------------- scanner heuristics / codec frames
+extern "C" int tb200_detect_batch(tb200_handle h, const void *d_iq, int dtype, int n_dwells, int64_t n, int64_t stride, double fs,
+                                  int num_windows, tb200_detect_stats *d_out, void *stream)
+{
+    if (!h || n_dwells < 0 || n < 0 || stride < n || !(fs > 0) || (n_dwells && (!d_iq || !d_out)) ||
+        (dtype != TB200_DTYPE_C64 && dtype != TB200_DTYPE_C128))
+        return fail(TB200_E_ARG, "tb200_detect_batch: bad argument");
+    // scratch: the decimator's forward scratch is idle here
+    return launch_detect(h, d_iq, dtype, n_dwells, n, stride, fs, num_windows, d_out, h->fwd, h->fwd_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int tb200_voice_blocks(tb200_handle h, int mode, const void *d_src, int64_t src_stride, const int32_t *d_n_src,
+                                  const int32_t *d_frame_stream, const int32_t *d_frame_pos, int64_t n_frames, double scale,
+                                  int16_t *d_blocks, uint8_t *d_valid, void *stream)
+{
+    if (!h || n_frames < 0 || mode < TB200_VOICE_SYMBOLS || mode > TB200_VOICE_SOFT || src_stride < 0 ||
+        (n_frames && (!d_src || !d_blocks)) || (n_frames && mode == TB200_VOICE_SYMBOLS && !d_frame_pos))
+        return fail(TB200_E_ARG, "tb200_voice_blocks: bad argument");
+    return launch_voice_blocks(h, mode, d_src, src_stride, d_n_src, d_frame_stream, d_frame_pos, n_frames, (float)scale, d_blocks,
+                               d_valid, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------- etsi mode
 extern "C" int tb200_etsi_decode_batch(tb200_handle h, const int8_t *d_soft, int64_t n, int channel, uint32_t scramb_init,
                                        uint8_t *d_bits, uint8_t *d_crc_ok, int32_t *d_metric, void *stream)

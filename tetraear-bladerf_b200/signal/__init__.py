@@ -1,9 +1,10 @@
 """Mirror of ``tetraear.signal`` for the IQ->bursts path (reference: tetraear/signal/__init__.py:11-28).
 
-Only the classes on the path are provided; device capture and the scanner stay with the
-reference.
+Only the classes on the path are provided (plus the scanner's per-dwell detector);
+device capture and the scan loop stay with the reference.
 """
 from .processor import SignalProcessor
 from .spectrum import SpectrumAnalyzer, compute_spectrum, find_peak_near
+from .scanner import TetraSignalDetector
 
-__all__ = ["SignalProcessor", "SpectrumAnalyzer", "compute_spectrum", "find_peak_near"]
+__all__ = ["SignalProcessor", "SpectrumAnalyzer", "compute_spectrum", "find_peak_near", "TetraSignalDetector"]
