@@ -13,6 +13,7 @@
 #include <complex>
 #include "common.h"
 #include "kernels.h"
+#include "packed.h"
 
 namespace tb200 {
 
@@ -296,6 +297,206 @@ chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// float32 packed variant (TB200_OPT_CHAN_F32, complex64 input).  Same two-sided modal form; the I and Q components
+// share every coefficient, so all recurrences, scans and carries run on float2 (I, Q) pairs with fma.rn.f32x2
+// (SASS FFMA2), Kogge-Stone stages whose multiplier (p^R)^(2^s) is below 1e-9 are skipped, the lane powers of the
+// cross-warp carry come from a shared-memory table, and the 13 timing-phase power sums are taken from a
+// shared-memory copy of |y|^2 by 16 threads per phase (fixed order) instead of 13 warp reductions per warp.
+struct ChanFast32Params {
+    float p[2][2];
+    float ppow[6][2][2];           // (p^R)^(2^s)
+    float c0p;
+    float a2[2][2];                // 2 alpha_i
+    float aF2[CF_R][2][2];         // 2 alpha_i p^(r+1)
+    float aB2[CF_R][2][2];         // 2 alpha_i p^(R-r)
+    float lanepow[32][2][2];       // (p^R)^l
+    float ka[2][2], kM[2][2][2], kMc[2][2][2];
+    float pc[2][2];                // p^16
+    float p7[2][2], p15[2][2];
+    int nstage[2];                 // Kogge-Stone stages that matter for mode i
+};
+
+__global__ void __launch_bounds__(CF_W * 32, 4)
+chan_fast32_kernel(const float *__restrict__ x, long n, long in_stride, int tiles_per_chunk,
+                   const double *__restrict__ freq_off, double fs, ChanFast32Params K,
+                   double *__restrict__ filtered, long out_stride, double *__restrict__ phase_partial, int sps, int step)
+{
+    __shared__ cp carryF[CF_W][2];
+    __shared__ cp carryB[CF_W][2];
+    __shared__ cp kappa[2];
+    __shared__ cf lanepow[32][2];
+    __shared__ float pws[(CF_W - 2) * CF_P];
+    if (threadIdx.x < 64) lanepow[threadIdx.x >> 1][threadIdx.x & 1] = ld2(K.lanepow[threadIdx.x >> 1][threadIdx.x & 1]);
+    const int chunk = blockIdx.x / tiles_per_chunk;
+    const int tile = blockIdx.x - chunk * tiles_per_chunk;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float *xc = x + (long)chunk * in_stride * 2;
+    const double f = freq_off ? freq_off[chunk] : 0.0;
+    const double W = (f != 0.0) ? __dmul_rn(-6.283185307179586, f) : 0.0;
+    const bool last_tile = tile == tiles_per_chunk - 1;
+    const long mt0 = n - (long)(tiles_per_chunk - tile) * (CF_W - 2) * CF_P;      // first sample of the storing range
+    const long m0 = mt0 - CF_P + (long)w * CF_P + (long)lane * CF_R;
+    const bool do_F = (w < CF_W - 1) || last_tile, do_B = w > 0, store = w > 0 && w < CF_W - 1;
+    const bool edge_lane = last_tile && w == CF_W - 1 && lane == 1;              // owns ext[M-1] at r = 6
+
+    float2 xs[CF_R];
+    if (W == 0.0 && m0 >= 0 && m0 + CF_R <= n && ((reinterpret_cast<uintptr_t>(xc + 2 * m0) & 15) == 0)) {
+        const float4 *v4 = reinterpret_cast<const float4 *>(xc + 2 * m0);
+#pragma unroll
+        for (int r = 0; r < CF_R / 2; ++r) {
+            const float4 v = v4[r];
+            xs[2 * r] = make_float2(v.x, v.y);
+            xs[2 * r + 1] = make_float2(v.z, v.w);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) { cdd v = chan_padded<float>(xc, n, 15 + m0 + r, W, fs); xs[r] = make_float2((float)v.x, (float)v.y); }
+    }
+    float2 y[CF_R];
+#pragma unroll
+    for (int r = 0; r < CF_R; ++r) y[r] = make_float2(K.c0p * xs[r].x, K.c0p * xs[r].y);
+    const cf p0 = ld2(K.p[0]), p1 = ld2(K.p[1]), a0 = ld2(K.a2[0]), a1 = ld2(K.a2[1]);
+    const float2 zero2 = make_float2(0.f, 0.f);
+    cp Fe[2];
+    Fe[0].re = Fe[0].im = Fe[1].re = Fe[1].im = zero2;
+
+    if (do_F) {
+        cp s[2];
+        s[0].re = s[0].im = s[1].re = s[1].im = zero2;
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) {
+            cp in; in.re = xs[r]; in.im = zero2;
+            s[0] = cpfma(p0, s[0], in);
+            s[1] = cpfma(p1, s[1], in);
+            y[r] = re_acc(a0, s[0], re_acc(a1, s[1], y[r]));
+            if (r == 6) { Fe[0] = s[0]; Fe[1] = s[1]; }
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            cp a = s[m];
+#pragma unroll
+            for (int st = 0; st < 5; ++st) {
+                if (st < K.nstage[m]) {
+                    cp o; o.re = shfl2_up(a.re, 1 << st); o.im = shfl2_up(a.im, 1 << st);
+                    cf g = ld2(K.ppow[st][m]);
+                    if (lane < (1 << st)) g.x = g.y = 0.f;
+                    a = cpfma(g, o, a);
+                }
+            }
+            cp cin; cin.re = shfl2_up(a.re, 1); cin.im = shfl2_up(a.im, 1);
+            if (lane == 0) cin.re = cin.im = zero2;
+            if (lane == 31) carryF[w][m] = a;
+            if (edge_lane) Fe[m] = cpfma(ld2(K.p7[m]), cin, Fe[m]);
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) y[r] = re_acc(ld2(K.aF2[r][m]), cin, y[r]);
+        }
+    }
+    if (do_B) {
+        cp s[2];
+        s[0].re = s[0].im = s[1].re = s[1].im = zero2;
+#pragma unroll
+        for (int r = CF_R - 1; r >= 0; --r) {
+            cp in; in.re = xs[r]; in.im = zero2;
+            s[0] = cpfma(p0, s[0], in);
+            s[1] = cpfma(p1, s[1], in);
+            y[r] = re_acc(a0, s[0], re_acc(a1, s[1], y[r]));
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            cp a = s[m];
+#pragma unroll
+            for (int st = 0; st < 5; ++st) {
+                if (st < K.nstage[m]) {
+                    cp o; o.re = shfl2_down(a.re, 1 << st); o.im = shfl2_down(a.im, 1 << st);
+                    cf g = ld2(K.ppow[st][m]);
+                    if (lane + (1 << st) >= 32) g.x = g.y = 0.f;
+                    a = cpfma(g, o, a);
+                }
+            }
+            cp cin; cin.re = shfl2_down(a.re, 1); cin.im = shfl2_down(a.im, 1);
+            if (lane == 31) cin.re = cin.im = zero2;
+            if (lane == 0) carryB[w][m] = a;
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) y[r] = re_acc(ld2(K.aB2[r][m]), cin, y[r]);
+        }
+    }
+    __syncthreads();
+    if (last_tile) {
+        if (edge_lane) {
+            // F_j[M-1] = local + p^15 * (end state of the previous warp);  kappa_i = ka_i x_last + sum_j kM F_j + kMc conj F_j
+#pragma unroll
+            for (int m = 0; m < 2; ++m) Fe[m] = cpfma(ld2(K.p15[m]), carryF[w - 1][m], Fe[m]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                cp k;
+                k.re = make_float2(K.ka[i][0] * xs[6].x, K.ka[i][0] * xs[6].y);
+                k.im = make_float2(K.ka[i][1] * xs[6].x, K.ka[i][1] * xs[6].y);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    k = cpfma(ld2(K.kM[i][j]), Fe[j], k);
+                    cp cj; cj.re = Fe[j].re; cj.im = make_float2(-Fe[j].im.x, -Fe[j].im.y);
+                    k = cpfma(ld2(K.kMc[i][j]), cj, k);
+                }
+                kappa[i] = k;
+            }
+        }
+        __syncthreads();
+    }
+    if (store) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const cp gF = cpmul(lanepow[lane][m], carryF[w - 1][m]);
+            const cp gB = cpmul(lanepow[31 - lane][m], carryB[w + 1][m]);
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) y[r] = re_acc(ld2(K.aB2[r][m]), gB, re_acc(ld2(K.aF2[r][m]), gF, y[r]));
+        }
+        if (last_tile && n - 1 - m0 < CF_FIX + CF_R) {
+            // y[m] -= 2 Re sum_i kappa_i p_i^(16 + mm),  mm = n-1-m   (only the last CF_FIX samples matter)
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) {
+                const long mm = n - 1 - (m0 + r);
+                if (mm < 0 || mm >= CF_FIX) continue;
+                const int a = (int)(mm / CF_R), b = (int)(mm - (long)a * CF_R);
+                for (int m = 0; m < 2; ++m) {
+                    cf g = ld2(K.pc[m]);
+                    for (int sft = 0; sft < 6; ++sft) if (a & (1 << sft)) g = cmulf(g, ld2(K.ppow[sft][m]));
+                    const cf pm = ld2(K.p[m]);
+                    for (int i = 0; i < b; ++i) g = cmulf(g, pm);
+                    y[r] = re_acc(cf{-2.0f * g.x, -2.0f * g.y}, kappa[m], y[r]);
+                }
+            }
+        }
+        double2 *out = reinterpret_cast<double2 *>(filtered) + (long)chunk * out_stride;
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) {
+            const long m = m0 + r;
+            const bool ok = m >= 0 && m < n;
+            if (ok) out[m] = make_double2((double)y[r].x, (double)y[r].y);
+            if (phase_partial) pws[(w - 1) * CF_P + lane * CF_R + r] = ok ? y[r].x * y[r].x + y[r].y * y[r].y : 0.f;
+        }
+    }
+    // ---- per-phase power partial sums for the timing pick (extract_symbols, processor.py:196-210): 16 threads per
+    // phase walk the tile's |y|^2 in shared memory (fixed order), a 16-lane shuffle tree finishes the sum.
+    if (phase_partial) {
+        __syncthreads();
+        const int grp = threadIdx.x >> 4, seg = threadIdx.x & 15;
+        const int ph = grp * step;
+        double t = 0.0;
+        if (ph < sps) {
+            const int ni = (int)n, t0 = (int)mt0, lo = t0 > 0 ? t0 : 0, hi = t0 + (CF_W - 2) * CF_P;
+            const int first = lo + ((ph - lo % sps) % sps + sps) % sps;
+            const int kmax = (ni - ph) / sps;                       // symbols of this phase: k < kmax
+            for (int m = first + seg * sps; m < hi; m += 16 * sps)
+                if (m / sps < kmax) t += (double)pws[m - t0];
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (ph < sps && seg == 0) phase_partial[((long)chunk * tiles_per_chunk + tile) * TB200_MAX_PHASES + ph] = t;
+    }
+}
+
 // ---- host: modal constants from the Butterworth poles ---------------------------------------
 typedef std::complex<double> cd;
 static void putd(double dst[2], cd v) { dst[0] = v.real(); dst[1] = v.imag(); }
@@ -363,6 +564,37 @@ static int make_chan_params(double bandwidth, double fs, ChanFastParams &K)
     return TB200_OK;
 }
 
+static void putf(float dst[2], const double src[2]) { dst[0] = (float)src[0]; dst[1] = (float)src[1]; }
+
+static void make_chan32_params(const ChanFastParams &K, ChanFast32Params &F)
+{
+    memset(&F, 0, sizeof(F));
+    F.c0p = (float)K.c0p;
+    for (int j = 0; j < 2; ++j) {
+        putf(F.p[j], K.p[j]);
+        const cd pj(K.p[j][0], K.p[j][1]), al(K.a[j][0], K.a[j][1]);
+        F.a2[j][0] = (float)(2.0 * al.real()); F.a2[j][1] = (float)(2.0 * al.imag());
+        int ns = 0;
+        for (int s = 0; s < 6; ++s) {
+            putf(F.ppow[s][j], K.ppow[s][j]);
+            if (s < 5 && std::hypot(K.ppow[s][j][0], K.ppow[s][j][1]) >= 1e-9) ns = s + 1;
+        }
+        F.nstage[j] = ns;
+        for (int r = 0; r < CF_R; ++r) {
+            F.aF2[r][j][0] = (float)(2.0 * K.aF[r][j][0]); F.aF2[r][j][1] = (float)(2.0 * K.aF[r][j][1]);
+            F.aB2[r][j][0] = (float)(2.0 * K.aB[r][j][0]); F.aB2[r][j][1] = (float)(2.0 * K.aB[r][j][1]);
+        }
+        const cd pr = std::pow(pj, CF_R);
+        for (int l = 0; l < 32; ++l) { cd v = std::pow(pr, l); F.lanepow[l][j][0] = (float)v.real(); F.lanepow[l][j][1] = (float)v.imag(); }
+        putf(F.ka[j], K.ka[j]);
+        for (int i = 0; i < 2; ++i) { putf(F.kM[j][i], K.kM[j][i]); putf(F.kMc[j][i], K.kMc[j][i]); }
+        putf(F.pc[j], K.pc[j]);
+        cd v7 = std::pow(pj, 7), v15 = std::pow(pj, 15);
+        F.p7[j][0] = (float)v7.real(); F.p7[j][1] = (float)v7.imag();
+        F.p15[j][0] = (float)v15.real(); F.p15[j][1] = (float)v15.imag();
+    }
+}
+
 int chan_fast_tiles(long n)
 {
     const int per_tile = (CF_W - 2) * CF_P;
@@ -375,7 +607,12 @@ static int launch_t(tb200_handle h, const void *x, int n_chunks, long n, long in
                     double *phase_tail, int sps, int step, cudaStream_t st)
 {
     const int tiles = chan_fast_tiles(n);
-    if (h->chan_f32)
+    if (h->chan_f32 && sizeof(TI) == 4 && n < (1L << 30)) {
+        ChanFast32Params F;
+        make_chan32_params(K, F);
+        chan_fast32_kernel<<<n_chunks * tiles, CF_W * 32, 0, st>>>((const float *)x, n, in_stride, tiles, freq_off, fs, F, filtered,
+                                                                 out_stride, phase_partial, sps, step);
+    } else if (h->chan_f32)
         chan_fast_kernel<TI, float><<<n_chunks * tiles, CF_W * 32, 0, st>>>((const TI *)x, n, in_stride, tiles, freq_off, fs, K,
                                                                           filtered, out_stride, phase_partial, sps, step);
     else

@@ -25,12 +25,15 @@
 #include <complex>
 #include "common.h"
 #include "kernels.h"
+#include "packed.h"
 
 namespace tb200 {
 
 constexpr int FD_R = 3;              // outputs per lane
 constexpr int FD_P = 32 * FD_R;      // outputs per warp pass
-constexpr int FD_W = 8;              // warps per CTA: 1 left-halo + 6 storing + 1 right-halo
+constexpr int FD_W = 8;              // warps per CTA: warp 0 = both halo half-passes, warps 1..7 = storing passes
+constexpr int FD_NS = FD_W - 1;      // storing passes per CTA
+constexpr int FD_NP = FD_W + 1;      // passes staged per tile: left halo, FD_NS storing, right halo
 constexpr int FD_QMAX = 16;
 constexpr int FD_NM = 4;              // modes per FIR sweep (4 = one pass over the tile rows, 2 = two passes, fewer registers)
 constexpr int FD_EDGE_S = 42;        // right-edge term: samples per lane (32 x 42 = 1344; 0.982^1344 = 3e-11)
@@ -52,15 +55,9 @@ struct FastDecimParams {
     float pc[4][2];                  // p_i^(M - n_last)
     float pS[5][4][2];               // (p_i^S)^(2^s): lane-combine multipliers of the edge kernel
     float lanepow[32][4][2];         // lambda_i^(R lane): cross-pass carry weights
+    int nstage[4];                   // Kogge-Stone stages that matter for mode i
 };
 
-struct cf { float x, y; };
-__device__ __forceinline__ cf cmulf(cf a, cf b) { return cf{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
-__device__ __forceinline__ cf cfma(cf a, cf b, cf c) { return cf{fmaf(a.x, b.x, fmaf(-a.y, b.y, c.x)), fmaf(a.x, b.y, fmaf(a.y, b.x, c.y))}; }
-__device__ __forceinline__ cf cshfl_up(cf v, int d) { return cf{__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d)}; }
-__device__ __forceinline__ cf cshfl_down(cf v, int d) { return cf{__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d)}; }
-__device__ __forceinline__ cf cshfl(cf v, int l) { return cf{__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l)}; }
-__device__ __forceinline__ cf ld2(const float c[2]) { return cf{c[0], c[1]}; }
 
 // sample t of the padded signal (ext coordinates, scipy odd_ext with edge 27) continued by the
 // constants the steady-state initial conditions stand for: ext[0] to the left, ext[M-1] to the right
@@ -96,35 +93,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
                  "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(a), "r"(parity) : "memory");
 }
 
-// ---- packed float2 arithmetic: the I and Q components of a sample share every coefficient, so each
-// quantity is kept as a float2 (I, Q) and updated with ONE fma.rn.f32x2 (SASS FFMA2) instead of two FFMAs.
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
-{
-    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
-                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    return *reinterpret_cast<float2 *>(&rd);
-}
-__device__ __forceinline__ float2 splat(float s) { return make_float2(s, s); }
-// complex value per component: re = (re_I, re_Q), im = (im_I, im_Q)
-struct cp { float2 re, im; };
-// c + g * a  for a scalar complex g and packed complex a, c
-__device__ __forceinline__ cp cpfma(cf g, cp a, cp c)
-{
-    cp o;
-    o.re = ffma2(splat(g.x), a.re, ffma2(splat(-g.y), a.im, c.re));
-    o.im = ffma2(splat(g.x), a.im, ffma2(splat(g.y), a.re, c.im));
-    return o;
-}
-__device__ __forceinline__ cp cpmul(cf g, cp a)
-{
-    cp z; z.re = z.im = make_float2(0.f, 0.f);
-    return cpfma(g, a, z);
-}
-__device__ __forceinline__ float2 shfl2_up(float2 v, int d) { return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d)); }
-__device__ __forceinline__ float2 shfl2_down(float2 v, int d) { return make_float2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d)); }
-// y += Re(g * a)
-__device__ __forceinline__ float2 re_acc(cf g, cp a, float2 y) { return ffma2(splat(g.x), a.re, ffma2(splat(-g.y), a.im, y)); }
 
 // one direction (causal: row0.., taps reversed; anti-causal: next row, taps ascending) for two of the
 // four modes; accumulates Re(alpha * .) into y (I, Q packed) and leaves the pass-end state in `carry`.
@@ -164,11 +132,14 @@ __device__ __forceinline__ void fd_half(const float2 *__restrict__ tile, int row
         cp a = U[FWD ? FD_R - 1 : 0][mm];
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
+            if (s >= K.nstage[m]) continue;              // multiplier (lambda^R)^(2^s) below 1e-9: nothing to add in float32
             cp o;
             o.re = FWD ? shfl2_up(a.re, 1 << s) : shfl2_down(a.re, 1 << s);
             o.im = FWD ? shfl2_up(a.im, 1 << s) : shfl2_down(a.im, 1 << s);
             const bool take = FWD ? (lane >= (1 << s)) : (lane + (1 << s) < 32);
-            if (take) a = cpfma(ld2(K.lampow[s][m]), o, a);
+            cf g = ld2(K.lampow[s][m]);
+            if (!take) g.x = g.y = 0.f;                  // select on the multiplier, not on the 4-register result
+            a = cpfma(g, o, a);
         }
         cp cin;
         cin.re = FWD ? shfl2_up(a.re, 1) : shfl2_down(a.re, 1);
@@ -241,14 +212,14 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
     // apart (30 for q = 10: a 2-way bank conflict on the 8-byte loads, cheaper than a padded layout that
     // TMA cannot write).  One extra leading sample keeps the global source 16-byte aligned.
     constexpr int PITCH = Q;
-    constexpr int ROWS = FD_W * FD_P + 1;
+    constexpr int ROWS = FD_NP * FD_P + 1;
     constexpr int TILE = ROWS * Q;
     constexpr unsigned TMA_BYTES = (unsigned)(((TILE + 1) * 8 + 15) & ~15);
     extern __shared__ __align__(128) float2 fd_raw[];
     __shared__ __align__(8) uint64_t tile_bar;
     float2 *fd_tile = fd_raw + 1;
-    __shared__ cp carryF[FD_W][4];
-    __shared__ cp carryB[FD_W][4];
+    __shared__ cp carryF[FD_NP][4];
+    __shared__ cp carryB[FD_NP][4];
     __shared__ cf lanepow[32][4];
     __shared__ cp kappa[4];
     if (threadIdx.x < 128) lanepow[threadIdx.x >> 2][threadIdx.x & 3] = ld2(K.lanepow[threadIdx.x >> 2][threadIdx.x & 3]);
@@ -257,46 +228,58 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
     const int tile = blockIdx.x - chunk * tiles_per_chunk;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float2 *xc = x + (long)chunk * chunk_stride;
-    // first output of warp 0 (the left-halo pass) and the padded-signal position of tile row 0, col 0
-    // Tiles are aligned to the END of the chunk (the first one may be partial): the last (FD_W-2)*FD_P outputs and
+    // first output of pass 0 (the left halo) and the padded-signal position of tile row 0, col 0.
+    // Tiles are aligned to the END of the chunk (the first one may be partial): the last FD_NS*FD_P outputs and
     // the whole right extension then live in ONE tile, which also computes and applies the right-edge term.
     const bool last_tile = tile == tiles_per_chunk - 1;
-    const long k_tile0 = n_dec - (long)(tiles_per_chunk - tile) * (FD_W - 2) * FD_P - FD_P;
+    const long k_tile0 = n_dec - (long)(tiles_per_chunk - tile) * FD_NS * FD_P - FD_P;
     const long t0 = 27 + (long)Q * k_tile0 - (Q - 1);
 
-    // ---- stage the tile.  Interior tiles: ONE TMA bulk copy issued by thread 0, everybody waits on the
-    // mbarrier; tiles touching a chunk end synthesise the odd extension sample by sample.
-    const float2 *src = xc + (t0 - 28);                       // one sample early: 16-byte aligned (see above)
-    const bool interior = (t0 >= 28) && (t0 - 28 + (long)(TMA_BYTES / 8) <= n) &&
-                          ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    // ---- stage the tile with TMA bulk copies issued by thread 0 (everybody waits on the mbarrier).  Interior
+    // tiles: ONE copy.  Tiles touching a chunk end: the in-range, 16-byte aligned middle part by TMA, the odd
+    // extension / constant continuation sample by sample.  fd_raw[j] is padded-signal sample t0 - 1 + j, i.e.
+    // chunk sample g0 + j with g0 = t0 - 28 (one sample early: 16-byte aligned source for even t0).
+    const long g0 = t0 - 28;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(xc) & 15) == 0) && ((g0 & 1) == 0);
+    const bool interior = aligned && g0 >= 0 && (g0 + (long)(TMA_BYTES / 8) <= n);
     if (interior) {
         if (threadIdx.x == 0) {
             mbar_init(&tile_bar, 1);
-            tma_load_1d(fd_raw, src, TMA_BYTES, &tile_bar);
+            tma_load_1d(fd_raw, xc + g0, TMA_BYTES, &tile_bar);
         }
         __syncthreads();                                       // barrier initialised before anybody polls it
         mbar_wait(&tile_bar, 0);
     } else {
-        for (int s = threadIdx.x; s < TILE; s += blockDim.x) fd_tile[s] = padded_sample(xc, n, t0 + s);
+        long ja = g0 < 0 ? -g0 : 0, jb = (n - g0 < (long)(TILE + 1)) ? n - g0 : (long)(TILE + 1);
+        ja = (ja + 1) & ~1L;
+        jb = ja + ((jb - ja) & ~1L);
+        const bool bulk = aligned && jb - ja >= 64;
+        if (!bulk) ja = jb = 0;
+        if (bulk && threadIdx.x == 0) {
+            mbar_init(&tile_bar, 1);
+            tma_load_1d(fd_raw + ja, xc + g0 + ja, (unsigned)((jb - ja) * 8), &tile_bar);
+        }
+        for (int s = threadIdx.x; s < TILE + 1; s += blockDim.x)
+            if (s < ja || s >= jb) fd_raw[s] = padded_sample(xc, n, t0 - 1 + s);
         __syncthreads();
+        if (bulk) mbar_wait(&tile_bar, 0);
     }
 
-    const bool do_F = w < FD_W - 1, do_B = w > 0, store = w > 0 && w < FD_W - 1;
-    const int row0 = w * FD_P + lane * FD_R;
+    // warp 0 runs the two halo half-passes (causal over pass 0, anti-causal over pass FD_NP-1), warps 1..FD_NS one
+    // storing pass each (both directions): every warp does the same amount of work.
+    const bool store = w > 0;
+    const int passB = store ? w : FD_NP - 1;
+    const int row0 = w * FD_P + lane * FD_R, row0B = passB * FD_P + lane * FD_R;
     float2 y[FD_R];
 #pragma unroll
     for (int r = 0; r < FD_R; ++r) y[r] = make_float2(0.f, 0.f);
-    if (do_F) {
-        fd_half<Q, PITCH, true, FD_NM>(fd_tile, row0, lane, 0, K, y, carryF[w]);
-        if (FD_NM == 2) fd_half<Q, PITCH, true, FD_NM>(fd_tile, row0, lane, 2, K, y, carryF[w]);
-    }
-    if (do_B) {
-        fd_half<Q, PITCH, false, FD_NM>(fd_tile, row0, lane, 0, K, y, carryB[w]);
-        if (FD_NM == 2) fd_half<Q, PITCH, false, FD_NM>(fd_tile, row0, lane, 2, K, y, carryB[w]);
-    }
-    // Right-edge transient (see the header): the right-halo warp of the chunk's last tile, which has only
-    // half a pass of work, derives kappa_i from F_i[M-1] = sum_k p_i^k ext[M-1-k] over the tile in smem.
-    if (last_tile && w == FD_W - 1) fd_kappa(fd_tile, (int)((n + 53) - t0), lane, K, kappa);
+    fd_half<Q, PITCH, true, FD_NM>(fd_tile, row0, lane, 0, K, y, carryF[w]);
+    if (FD_NM == 2) fd_half<Q, PITCH, true, FD_NM>(fd_tile, row0, lane, 2, K, y, carryF[w]);
+    fd_half<Q, PITCH, false, FD_NM>(fd_tile, row0B, lane, 0, K, y, carryB[passB]);
+    if (FD_NM == 2) fd_half<Q, PITCH, false, FD_NM>(fd_tile, row0B, lane, 2, K, y, carryB[passB]);
+    // Right-edge transient (see the header): warp 0 of the chunk's last tile derives kappa_i from
+    // F_i[M-1] = sum_k p_i^k ext[M-1-k] over the tile in smem.
+    if (last_tile && w == 0) fd_kappa(fd_tile, (int)((n + 53) - t0), lane, K, kappa);
     __syncthreads();
     if (!store) return;
     // ---- carries from the neighbour passes: lambda^(lane R) cF on the left, lambda^((31-lane) R) cB on the right
@@ -371,7 +354,12 @@ static int make_fast_params(const DecimDesign &d, int q, long n, long n_dec, Fas
         for (int t = 0; t < q; ++t) { put(K.tap[t][j], pw); pw *= p8[j]; }
         put(K.lam[j], lam[j]);
         cd lr = std::pow(lam[j], FD_R);
-        for (int s = 0; s < 6; ++s) { put(K.lampow[s][j], lr); lr *= lr; }
+        K.nstage[j] = 0;
+        for (int s = 0; s < 6; ++s) {
+            put(K.lampow[s][j], lr);
+            if (s < 5 && std::abs(lr) >= 1e-9) K.nstage[j] = s + 1;
+            lr *= lr;
+        }
         put(K.a0[j], alpha[j]);
         put(K.ap[j], alpha[j] * p8[j]);
         for (int r = 0; r < FD_R; ++r) {
@@ -410,7 +398,7 @@ template <int Q>
 static int launch_q(tb200_handle h, const void *x, int n_chunks, long n, long chunk_stride, long n_dec,
                     const FastDecimParams &K, void *dec_out, cudaStream_t st)
 {
-    constexpr int ROWS = FD_W * FD_P + 1;
+    constexpr int ROWS = FD_NP * FD_P + 1;
     const size_t smem = ((size_t)(ROWS * Q + 1) * sizeof(float2) + 15 + 16) & ~(size_t)15;
     static bool attr_set = false;
     if (!attr_set) {
@@ -418,7 +406,7 @@ static int launch_q(tb200_handle h, const void *x, int n_chunks, long n, long ch
         if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(decim_fast): %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    const int per_tile = (FD_W - 2) * FD_P;
+    const int per_tile = FD_NS * FD_P;
     const int tiles = (int)((n_dec + per_tile - 1) / per_tile);
     decim_fast_kernel<Q><<<n_chunks * tiles, FD_W * 32, smem, st>>>((const float2 *)x, n, chunk_stride, tiles, n_dec, K,
                                                                   (float2 *)dec_out);
