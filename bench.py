@@ -2,7 +2,7 @@
 """bench.py — IQ Msamples/s (and CRC-pass bursts/s) of the IQ->bursts receive path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c3|c2]
-                    [--mode exact|fast]
+                    [--mode exact|fast|fast32]
 
 Workload c1 (default, BASELINE.json configs[0]): one synthetic TETRA-like downlink carrier, 10 s of
 complex64 IQ at 2.4 MS/s = 183 whole chunks of 131072 samples (the ragged 0.1-chunk tail is
@@ -223,6 +223,27 @@ def run_b200(args):
     sync_all()
     ms_e2e16 = t2.elapsed_time(t3)
 
+    # ---- the same device-resident loop with the float64 channel filter ('fast'), for comparison with the default
+    alt = None
+    if args.mode == "fast32" and world == 1 and not args.no_extras:
+        pipe64 = pipeline.ReceivePipeline(FS, CHUNK, max_chunks=n_chunks, mode="fast", device=local_rank, n_lanes=args.lanes)
+        for _ in range(3):
+            pipe64.run_device(dev)
+        sync_all()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k64 = min(args.steps, 50)
+        a0.record(stream)
+        for _ in range(k64):
+            pipe64.run_device(dev, join=False)
+        pipe64.join()
+        a1.record(stream)
+        sync_all()
+        ms64 = a0.elapsed_time(a1) / k64
+        alt = {"value": round(total_samples / (ms64 / 1e3) / 1e6, 3), "unit": "Msamples/s", "ms_per_step": round(ms64, 4),
+               "note": "mode 'fast': channel filter recurrences in float64 (1e-11 from scipy's filtfilt) instead of float32 (3e-6)"}
+        del pipe64
+        torch.cuda.empty_cache()
+
     # ---- per-stage device time for the roofline (separate pass so the events do not sit in `value`)
     # (single lane: the per-stage events of concurrent lanes would overlap and double count)
     pipe1 = pipe if args.lanes == 1 else pipeline.ReceivePipeline(FS, CHUNK, max_chunks=n_chunks, mode=args.mode, device=local_rank)
@@ -281,7 +302,11 @@ def run_b200(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "c1: single synthetic TETRA downlink carrier, 10 s complex64 IQ @2.4 MS/s, "
                                f"{n_chunks} chunks x 131072 samples per GPU, process+decode per chunk (reference mode, "
-                               f"decimator arithmetic '{args.mode}')",
+                               f"arithmetic '{args.mode}': " + {
+                                   "exact": "op-order-exact float32 decimator recurrence + float64 channel filter, bit-identical to the reference",
+                                   "fast": "time-parallel float32 decimator + float64 channel filter; dibits identical, soft symbols <= 1e-4 of full scale",
+                                   "fast32": "time-parallel float32 decimator and float32 channel filter; dibits identical on the parity cases, "
+                                             "soft symbols <= 1e-4 of full scale (tests/test_gpu_parity.py::test_fast_mode_within_tolerance)"}[args.mode] + ")",
                    "l2": "input 192 MB per step > 126 MB L2, no flush needed", "parallelism": f"capture segment per GPU x{world}",
                    "stream_lanes": args.lanes},
         "crc_pass_bursts_per_s": round(bursts_per_s, 1), "crc_pass_per_step": int(stats[1] // max(args.steps, 1)),
@@ -296,7 +321,7 @@ def run_b200(args):
                      "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
                      # dram__bytes_read.sum + dram__bytes_write.sum of decim_fast_kernel<10>, one launch, ncu --set full
                      # (profiles/r01_ncu_kernels_final.md); valid for the fast mode on this workload only
-                     "traffic": 208214272 if args.mode.startswith("fast") else None,
+                     "traffic": 206542592 if args.mode.startswith("fast") else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "ms_per_launch": round(dec_launch_ms, 4),
                      "path_achieved_gbs": round(path_bytes / (step_ms / 1e3) / 1e9, 2),
@@ -305,6 +330,8 @@ def run_b200(args):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if alt:
+        line["value_f64_channel_filter"] = alt
     if world == 1 and not args.no_extras:
         try:
             del dev, host
@@ -582,7 +609,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("TB200_BENCH_LANES", "2")),
                     help="sub-batches processed on concurrent streams (overlaps the latency-bound tail kernels)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("TB200_BENCH_MODE", "fast"), choices=["exact", "fast", "fast32"])
+    ap.add_argument("--mode", default=os.environ.get("TB200_BENCH_MODE", "fast32"), choices=["exact", "fast", "fast32"])
     ap.add_argument("--workload", default="c1", choices=["c1", "c5"], help="c1 = headline; c5 = multichannel archive replay")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the other-workload kernel figures")

@@ -25,7 +25,7 @@ int fast_decimator_supported(int q);
 int launch_channel_fast(tb200_handle h, const void *x, int dtype, int n_chunks, long n, long in_stride,
                         const double *freq_off, double fs, double bandwidth, double *filtered, long out_stride,
                         double *phase_partial, double *phase_tail, int sps, int step, cudaStream_t st);
-int chan_fast_tiles(long n);
+int chan_fast_tiles(tb200_handle h, int dtype, long n);
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -323,7 +323,7 @@ extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, 
     {
         StageTimer tm(h, TB_STAGE_CHAN, st);
         if (h->cfg.mode == TB200_MODE_FAST && P.filtered) {
-            int tiles = chan_fast_tiles(P.n_dec);
+            int tiles = chan_fast_tiles(h, (P.q > 1) ? cur_dtype : dtype, P.n_dec);
             if (P.sps > 1 && P.sps <= TB200_MAX_PHASES &&
                 (size_t)n_chunks * (tiles + 1) * TB200_MAX_PHASES * sizeof(double) <= h->phase_bytes) {
                 ph_partial = h->phase_pw;

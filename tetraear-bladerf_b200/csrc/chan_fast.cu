@@ -318,31 +318,57 @@ struct ChanFast32Params {
     int nstage[2];                 // Kogge-Stone stages that matter for mode i
 };
 
-__global__ void __launch_bounds__(CF_W * 32, 4)
-chan_fast32_kernel(const float *__restrict__ x, long n, long in_stride, int tiles_per_chunk,
-                   const double *__restrict__ freq_off, double fs, ChanFast32Params K,
-                   double *__restrict__ filtered, long out_stride, double *__restrict__ phase_partial, int sps, int step)
-{
-    __shared__ cp carryF[CF_W][2];
-    __shared__ cp carryB[CF_W][2];
-    __shared__ cp kappa[2];
-    __shared__ cf lanepow[32][2];
-    __shared__ float pws[(CF_W - 2) * CF_P];
-    if (threadIdx.x < 64) lanepow[threadIdx.x >> 1][threadIdx.x & 1] = ld2(K.lanepow[threadIdx.x >> 1][threadIdx.x & 1]);
-    const int chunk = blockIdx.x / tiles_per_chunk;
-    const int tile = blockIdx.x - chunk * tiles_per_chunk;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float *xc = x + (long)chunk * in_stride * 2;
-    const double f = freq_off ? freq_off[chunk] : 0.0;
-    const double W = (f != 0.0) ? __dmul_rn(-6.283185307179586, f) : 0.0;
-    const bool last_tile = tile == tiles_per_chunk - 1;
-    const long mt0 = n - (long)(tiles_per_chunk - tile) * (CF_W - 2) * CF_P;      // first sample of the storing range
-    const long m0 = mt0 - CF_P + (long)w * CF_P + (long)lane * CF_R;
-    const bool do_F = (w < CF_W - 1) || last_tile, do_B = w > 0, store = w > 0 && w < CF_W - 1;
-    const bool edge_lane = last_tile && w == CF_W - 1 && lane == 1;              // owns ext[M-1] at r = 6
+constexpr int C32_NS = CF_W - 1;      // storing passes per CTA (warps 1..7); warp 0 runs both halo half-passes
+constexpr int C32_NP = CF_W + 1;      // passes per tile: left halo, C32_NS storing, right halo
 
-    float2 xs[CF_R];
+// one direction over the lane's CF_R samples: zero-state recurrences, Kogge-Stone scan of the lane aggregates,
+// in-warp carry applied to y; the pass-end state goes to carry[0..1]
+template <bool FWD>
+__device__ __forceinline__ void c32_dir(const float2 (&xs)[CF_R], float2 (&y)[CF_R], int lane, const ChanFast32Params &K,
+                                        cp *carry, cp *Fe, bool edge_lane)
+{
+    const cf p0 = ld2(K.p[0]), p1 = ld2(K.p[1]), a0 = ld2(K.a2[0]), a1 = ld2(K.a2[1]);
+    const float2 zero2 = make_float2(0.f, 0.f);
+    cp s[2];
+    s[0].re = s[0].im = s[1].re = s[1].im = zero2;
+#pragma unroll
+    for (int i = 0; i < CF_R; ++i) {
+        const int r = FWD ? i : CF_R - 1 - i;
+        cp in; in.re = xs[r]; in.im = zero2;
+        s[0] = cpfma(p0, s[0], in);
+        s[1] = cpfma(p1, s[1], in);
+        y[r] = re_acc(a0, s[0], re_acc(a1, s[1], y[r]));
+        if (FWD && r == 6) { Fe[0] = s[0]; Fe[1] = s[1]; }           // zero-state F at r = 6 (edge lane)
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        cp a = s[m];
+#pragma unroll
+        for (int st = 0; st < 5; ++st) {
+            if (st < K.nstage[m]) {
+                cp o;
+                o.re = FWD ? shfl2_up(a.re, 1 << st) : shfl2_down(a.re, 1 << st);
+                o.im = FWD ? shfl2_up(a.im, 1 << st) : shfl2_down(a.im, 1 << st);
+                cf g = ld2(K.ppow[st][m]);
+                if (FWD ? (lane < (1 << st)) : (lane + (1 << st) >= 32)) g.x = g.y = 0.f;
+                a = cpfma(g, o, a);
+            }
+        }
+        cp cin;
+        cin.re = FWD ? shfl2_up(a.re, 1) : shfl2_down(a.re, 1);
+        cin.im = FWD ? shfl2_up(a.im, 1) : shfl2_down(a.im, 1);
+        if (lane == (FWD ? 0 : 31)) cin.re = cin.im = zero2;
+        if (lane == (FWD ? 31 : 0)) carry[m] = a;
+        if (FWD && edge_lane) Fe[m] = cpfma(ld2(K.p7[m]), cin, Fe[m]);   // + p^7 * (carry from lane 0 of this warp)
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) y[r] = re_acc(FWD ? ld2(K.aF2[r][m]) : ld2(K.aB2[r][m]), cin, y[r]);
+    }
+}
+
+__device__ __forceinline__ void c32_load(const float *__restrict__ xc, long n, long m0, double W, double fs, float2 (&xs)[CF_R])
+{
     if (W == 0.0 && m0 >= 0 && m0 + CF_R <= n && ((reinterpret_cast<uintptr_t>(xc + 2 * m0) & 15) == 0)) {
+        // interior lane, no NCO: 8 samples = 64 contiguous bytes = four 16-byte loads (tiles are end-aligned)
         const float4 *v4 = reinterpret_cast<const float4 *>(xc + 2 * m0);
 #pragma unroll
         for (int r = 0; r < CF_R / 2; ++r) {
@@ -354,80 +380,53 @@ chan_fast32_kernel(const float *__restrict__ x, long n, long in_stride, int tile
 #pragma unroll
         for (int r = 0; r < CF_R; ++r) { cdd v = chan_padded<float>(xc, n, 15 + m0 + r, W, fs); xs[r] = make_float2((float)v.x, (float)v.y); }
     }
-    float2 y[CF_R];
+}
+
+__global__ void __launch_bounds__(CF_W * 32, 4)
+chan_fast32_kernel(const float *__restrict__ x, long n, long in_stride, int tiles_per_chunk,
+                   const double *__restrict__ freq_off, double fs, ChanFast32Params K,
+                   double *__restrict__ filtered, long out_stride, double *__restrict__ phase_partial, int sps, int step)
+{
+    __shared__ cp carryF[C32_NP][2];
+    __shared__ cp carryB[C32_NP][2];
+    __shared__ cp kappa[2];
+    __shared__ cf lanepow[32][2];
+    __shared__ float pws[C32_NS * CF_P];
+    if (threadIdx.x < 64) lanepow[threadIdx.x >> 1][threadIdx.x & 1] = ld2(K.lanepow[threadIdx.x >> 1][threadIdx.x & 1]);
+    const int chunk = blockIdx.x / tiles_per_chunk;
+    const int tile = blockIdx.x - chunk * tiles_per_chunk;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float *xc = x + (long)chunk * in_stride * 2;
+    const double f = freq_off ? freq_off[chunk] : 0.0;
+    const double W = (f != 0.0) ? __dmul_rn(-6.283185307179586, f) : 0.0;
+    // tiles are aligned to the END of the chunk (the first may be partial): the last CF_FIX samples and the right
+    // extension belong to one tile, which also derives and applies the right-edge term
+    const bool last_tile = tile == tiles_per_chunk - 1;
+    const long mt0 = n - (long)(tiles_per_chunk - tile) * C32_NS * CF_P;          // first sample of the storing range
+    const bool store = w > 0;
+    const int passB = store ? w : C32_NP - 1;
+    const long m0 = mt0 - CF_P + (long)w * CF_P + (long)lane * CF_R;             // causal pass of this warp
+    const long m0B = mt0 - CF_P + (long)passB * CF_P + (long)lane * CF_R;        // anti-causal pass
+    // ext[M-1] is sample m = n + 14: lane 1, r = 6 of the right-halo pass of the last tile (run by warp 0)
+    const bool edge_lane = last_tile && w == 0 && lane == 1;
+
+    float2 xs[CF_R], y[CF_R];
+    cp Fe[2];
+    c32_load(xc, n, m0, W, fs, xs);
 #pragma unroll
     for (int r = 0; r < CF_R; ++r) y[r] = make_float2(K.c0p * xs[r].x, K.c0p * xs[r].y);
-    const cf p0 = ld2(K.p[0]), p1 = ld2(K.p[1]), a0 = ld2(K.a2[0]), a1 = ld2(K.a2[1]);
-    const float2 zero2 = make_float2(0.f, 0.f);
-    cp Fe[2];
-    Fe[0].re = Fe[0].im = Fe[1].re = Fe[1].im = zero2;
-
-    if (do_F) {
-        cp s[2];
-        s[0].re = s[0].im = s[1].re = s[1].im = zero2;
-#pragma unroll
-        for (int r = 0; r < CF_R; ++r) {
-            cp in; in.re = xs[r]; in.im = zero2;
-            s[0] = cpfma(p0, s[0], in);
-            s[1] = cpfma(p1, s[1], in);
-            y[r] = re_acc(a0, s[0], re_acc(a1, s[1], y[r]));
-            if (r == 6) { Fe[0] = s[0]; Fe[1] = s[1]; }
-        }
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            cp a = s[m];
-#pragma unroll
-            for (int st = 0; st < 5; ++st) {
-                if (st < K.nstage[m]) {
-                    cp o; o.re = shfl2_up(a.re, 1 << st); o.im = shfl2_up(a.im, 1 << st);
-                    cf g = ld2(K.ppow[st][m]);
-                    if (lane < (1 << st)) g.x = g.y = 0.f;
-                    a = cpfma(g, o, a);
-                }
-            }
-            cp cin; cin.re = shfl2_up(a.re, 1); cin.im = shfl2_up(a.im, 1);
-            if (lane == 0) cin.re = cin.im = zero2;
-            if (lane == 31) carryF[w][m] = a;
-            if (edge_lane) Fe[m] = cpfma(ld2(K.p7[m]), cin, Fe[m]);
-#pragma unroll
-            for (int r = 0; r < CF_R; ++r) y[r] = re_acc(ld2(K.aF2[r][m]), cin, y[r]);
-        }
+    c32_dir<true>(xs, y, lane, K, carryF[w], Fe, false);
+    if (!store) {
+        c32_load(xc, n, m0B, W, fs, xs);
+        if (last_tile) c32_dir<true>(xs, y, lane, K, carryF[C32_NP - 1], Fe, edge_lane);   // F[M-1] lives in the right halo
     }
-    if (do_B) {
-        cp s[2];
-        s[0].re = s[0].im = s[1].re = s[1].im = zero2;
-#pragma unroll
-        for (int r = CF_R - 1; r >= 0; --r) {
-            cp in; in.re = xs[r]; in.im = zero2;
-            s[0] = cpfma(p0, s[0], in);
-            s[1] = cpfma(p1, s[1], in);
-            y[r] = re_acc(a0, s[0], re_acc(a1, s[1], y[r]));
-        }
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            cp a = s[m];
-#pragma unroll
-            for (int st = 0; st < 5; ++st) {
-                if (st < K.nstage[m]) {
-                    cp o; o.re = shfl2_down(a.re, 1 << st); o.im = shfl2_down(a.im, 1 << st);
-                    cf g = ld2(K.ppow[st][m]);
-                    if (lane + (1 << st) >= 32) g.x = g.y = 0.f;
-                    a = cpfma(g, o, a);
-                }
-            }
-            cp cin; cin.re = shfl2_down(a.re, 1); cin.im = shfl2_down(a.im, 1);
-            if (lane == 31) cin.re = cin.im = zero2;
-            if (lane == 0) carryB[w][m] = a;
-#pragma unroll
-            for (int r = 0; r < CF_R; ++r) y[r] = re_acc(ld2(K.aB2[r][m]), cin, y[r]);
-        }
-    }
+    c32_dir<false>(xs, y, lane, K, carryB[passB], Fe, false);
     __syncthreads();
     if (last_tile) {
         if (edge_lane) {
-            // F_j[M-1] = local + p^15 * (end state of the previous warp);  kappa_i = ka_i x_last + sum_j kM F_j + kMc conj F_j
+            // F_j[M-1] = local + p^15 * (end state of the last storing pass);  kappa_i = ka_i x_last + sum_j kM F_j + kMc conj F_j
 #pragma unroll
-            for (int m = 0; m < 2; ++m) Fe[m] = cpfma(ld2(K.p15[m]), carryF[w - 1][m], Fe[m]);
+            for (int m = 0; m < 2; ++m) Fe[m] = cpfma(ld2(K.p15[m]), carryF[C32_NP - 2][m], Fe[m]);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 cp k;
@@ -485,11 +484,11 @@ chan_fast32_kernel(const float *__restrict__ x, long n, long in_stride, int tile
         const int ph = grp * step;
         double t = 0.0;
         if (ph < sps) {
-            const int ni = (int)n, t0 = (int)mt0, lo = t0 > 0 ? t0 : 0, hi = t0 + (CF_W - 2) * CF_P;
-            const int first = lo + ((ph - lo % sps) % sps + sps) % sps;
-            const int kmax = (ni - ph) / sps;                       // symbols of this phase: k < kmax
-            for (int m = first + seg * sps; m < hi; m += 16 * sps)
-                if (m / sps < kmax) t += (double)pws[m - t0];
+            const int ni = (int)n, t0 = (int)mt0, lo = t0 > 0 ? t0 : 0, hi = t0 + C32_NS * CF_P;
+            const int first = lo + ((ph - lo % sps) % sps + sps) % sps;      // first sample of this phase in the tile
+            const int kmax = (ni - ph) / sps;                                // symbols of this phase: k < kmax
+            int k = first / sps + seg;                                       // first = ph + sps * (first / sps)
+            for (int m = first + seg * sps; m < hi && k < kmax; m += 16 * sps, k += 16) t += (double)pws[m - t0];
         }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
@@ -595,9 +594,12 @@ static void make_chan32_params(const ChanFastParams &K, ChanFast32Params &F)
     }
 }
 
-int chan_fast_tiles(long n)
+static bool use_packed32(tb200_handle h, int dtype, long n) { return h->chan_f32 && dtype == TB200_DTYPE_C64 && n < (1L << 30); }
+
+// tiles per chunk of the kernel launch_channel_fast will pick for (handle options, input dtype, n)
+int chan_fast_tiles(tb200_handle h, int dtype, long n)
 {
-    const int per_tile = (CF_W - 2) * CF_P;
+    const int per_tile = (use_packed32(h, dtype, n) ? C32_NS : CF_W - 2) * CF_P;
     return (int)((n + per_tile - 1) / per_tile);
 }
 
@@ -606,8 +608,8 @@ static int launch_t(tb200_handle h, const void *x, int n_chunks, long n, long in
                     double fs, const ChanFastParams &K, double *filtered, long out_stride, double *phase_partial,
                     double *phase_tail, int sps, int step, cudaStream_t st)
 {
-    const int tiles = chan_fast_tiles(n);
-    if (h->chan_f32 && sizeof(TI) == 4 && n < (1L << 30)) {
+    const int tiles = chan_fast_tiles(h, sizeof(TI) == 4 ? TB200_DTYPE_C64 : TB200_DTYPE_C128, n);
+    if (use_packed32(h, sizeof(TI) == 4 ? TB200_DTYPE_C64 : TB200_DTYPE_C128, n)) {
         ChanFast32Params F;
         make_chan32_params(K, F);
         chan_fast32_kernel<<<n_chunks * tiles, CF_W * 32, 0, st>>>((const float *)x, n, in_stride, tiles, freq_off, fs, F, filtered,
