@@ -365,6 +365,13 @@ __device__ __forceinline__ void c32_dir(const float2 (&xs)[CF_R], float2 (&y)[CF
     }
 }
 
+// out-of-line: edge lanes and NCO'd chunks only; keeps the hot path's code small (instruction fetch)
+__device__ __noinline__ float2 c32_padded(const float *__restrict__ xc, long n, long t, double W, double fs)
+{
+    cdd v = chan_padded<float>(xc, n, t, W, fs);
+    return make_float2((float)v.x, (float)v.y);
+}
+
 __device__ __forceinline__ void c32_load(const float *__restrict__ xc, long n, long m0, double W, double fs, float2 (&xs)[CF_R])
 {
     if (W == 0.0 && m0 >= 0 && m0 + CF_R <= n && ((reinterpret_cast<uintptr_t>(xc + 2 * m0) & 15) == 0)) {
@@ -378,7 +385,7 @@ __device__ __forceinline__ void c32_load(const float *__restrict__ xc, long n, l
         }
     } else {
 #pragma unroll
-        for (int r = 0; r < CF_R; ++r) { cdd v = chan_padded<float>(xc, n, 15 + m0 + r, W, fs); xs[r] = make_float2((float)v.x, (float)v.y); }
+        for (int r = 0; r < CF_R; ++r) xs[r] = c32_padded(xc, n, 15 + m0 + r, W, fs);
     }
 }
 
