@@ -372,16 +372,39 @@ __device__ __noinline__ float2 c32_padded(const float *__restrict__ xc, long n, 
     return make_float2((float)v.x, (float)v.y);
 }
 
+// NCO of an interior lane (frequency_shift, processor.py:85-100): phase of the lane's first sample exactly as the
+// reference forms it (float64: fl(-2 pi f) * fl(i / fs)), then a float32 rotation by the per-sample step for the other
+// seven samples (error ~4e-7 of full scale; two double sincos per lane instead of eight).
+__device__ __noinline__ float4 c32_nco(long m0, double W, double fs)
+{
+    double s0, c0, sd, cdv;
+    sincos(__dmul_rn(W, (double)m0 / fs), &s0, &c0);
+    sincos(W / fs, &sd, &cdv);
+    return make_float4((float)c0, (float)s0, (float)cdv, (float)sd);
+}
+
 __device__ __forceinline__ void c32_load(const float *__restrict__ xc, long n, long m0, double W, double fs, float2 (&xs)[CF_R])
 {
-    if (W == 0.0 && m0 >= 0 && m0 + CF_R <= n && ((reinterpret_cast<uintptr_t>(xc + 2 * m0) & 15) == 0)) {
-        // interior lane, no NCO: 8 samples = 64 contiguous bytes = four 16-byte loads (tiles are end-aligned)
+    if (m0 >= 0 && m0 + CF_R <= n && ((reinterpret_cast<uintptr_t>(xc + 2 * m0) & 15) == 0)) {
+        // interior lane: 8 samples = 64 contiguous bytes = four 16-byte loads (tiles are end-aligned)
         const float4 *v4 = reinterpret_cast<const float4 *>(xc + 2 * m0);
 #pragma unroll
         for (int r = 0; r < CF_R / 2; ++r) {
             const float4 v = v4[r];
             xs[2 * r] = make_float2(v.x, v.y);
             xs[2 * r + 1] = make_float2(v.z, v.w);
+        }
+        if (W != 0.0) {
+            const float4 rot = c32_nco(m0, W, fs);
+            float c = rot.x, sn = rot.y;
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) {
+                const float xr = xs[r].x, xi = xs[r].y;
+                xs[r] = make_float2(xr * c - xi * sn, xr * sn + xi * c);
+                const float c2 = c * rot.z - sn * rot.w;
+                sn = sn * rot.z + c * rot.w;
+                c = c2;
+            }
         }
     } else {
 #pragma unroll
