@@ -122,6 +122,55 @@ __global__ void detect_finish_sums_kernel(const double *__restrict__ partial, lo
     }
 }
 
+
+// ---- decisions.  Exact form (any T): the reference's own sequence of operations.
+template <typename T>
+__device__ __noinline__ bool mod_match_exact(T re0, T im0, T re1, T im1)
+{
+    typedef wrapc<T> W;
+    const T a0 = angle_of<T>(re0, im0), a1 = angle_of<T>(re1, im1);
+    const double d = (double)wrap_step<T>(W::sub(a1, a0));
+    double best = 1e9;
+#pragma unroll
+    for (int k = -4; k <= 3; ++k) {
+        // np.array([-np.pi, -3*np.pi/4, -np.pi/2, -np.pi/4, 0, np.pi/4, np.pi/2, 3*np.pi/4])
+        const double e = (k == -4) ? -3.141592653589793 : (k == -3) ? -2.356194490192345 : (k == -2) ? -1.5707963267948966
+                       : (k == -1) ? -0.7853981633974483 : (k == 0) ? 0.0 : (k == 1) ? 0.7853981633974483
+                       : (k == 2) ? 1.5707963267948966 : 2.356194490192345;
+        best = fmin(best, fabs(e - d));
+    }
+    return best < 0.39269908169872414;
+}
+
+template <typename T>
+__device__ __noinline__ bool sync_bit_exact(T re0, T im0, T re1, T im1)
+{
+    typedef wrapc<T> W;
+    const T a0 = angle_of<T>(re0, im0), a1 = angle_of<T>(re1, im1);
+    const T d = wrap_step<T>(W::sub(a1, a0));
+    return W::rint_(W::div(d, W::qpi())) == T(0);
+}
+
+// float32 fast form: atan2f (<= 2 ulp) gives the phase step to ~2e-6; the decision is taken from it unless the
+// step sits within 2e-5 of a decision boundary (or of the +-pi wrap), where the exact form is evaluated instead —
+// so the result always equals the exact form's.
+__device__ __forceinline__ bool mod_match_fast(float a0, float a1, float re0, float im0, float re1, float im1)
+{
+    const float d = wrap_step<float>(__fsub_rn(a1, a0));
+    const float k = fminf(3.f, fmaxf(-4.f, rintf(d * 1.27323954473516f)));
+    const float best = fabsf(fmaf(-k, 0.785398163397448f, d));
+    if (fabsf(best - 0.392699081698724f) < 2e-5f || fabsf(d) > 3.14157f) return mod_match_exact<float>(re0, im0, re1, im1);
+    return best < 0.392699081698724f;
+}
+
+__device__ __forceinline__ bool sync_bit_fast(float re0, float im0, float re1, float im1)
+{
+    const float d = wrap_step<float>(__fsub_rn(atan2f(im1, re1), atan2f(im0, re0)));
+    const float q = d * 1.27323954473516f;
+    if (fabsf(fabsf(q) - 0.5f) < 2e-5f) return sync_bit_exact<float>(re0, im0, re1, im1);
+    return rintf(q) == 0.f;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 detect_steps_kernel(const T *__restrict__ x, long n, long stride, int sync_step, int do_mod,
@@ -138,24 +187,24 @@ detect_steps_kernel(const T *__restrict__ x, long n, long stride, int sync_step,
         constexpr int S = 8;
         int cnt = 0;
         for (long base = gtid * S; base < n - 1; base += gsz * S) {
-            T prev = angle_of<T>(W::mul(xc[2 * base], inv), W::mul(xc[2 * base + 1], inv));
+            T pre = W::mul(xc[2 * base], inv), pim = W::mul(xc[2 * base + 1], inv);
+            float pa = 0.f;
+            if (sizeof(T) == 4) pa = atan2f((float)pim, (float)pre);
 #pragma unroll
             for (int j = 1; j <= S; ++j) {
                 const long i = base + j;
                 if (i >= n) break;
-                const T cur = angle_of<T>(W::mul(xc[2 * i], inv), W::mul(xc[2 * i + 1], inv));
-                const double d = (double)wrap_step<T>(W::sub(cur, prev));
-                prev = cur;
-                double best = 1e9;
-#pragma unroll
-                for (int k = -4; k <= 3; ++k) {
-                    // np.array([-np.pi, -3*np.pi/4, -np.pi/2, -np.pi/4, 0, np.pi/4, np.pi/2, 3*np.pi/4])
-                    const double e = (k == -4) ? -3.141592653589793 : (k == -3) ? -2.356194490192345 : (k == -2) ? -1.5707963267948966
-                                   : (k == -1) ? -0.7853981633974483 : (k == 0) ? 0.0 : (k == 1) ? 0.7853981633974483
-                                   : (k == 2) ? 1.5707963267948966 : 2.356194490192345;
-                    best = fmin(best, fabs(e - d));
+                const T cre = W::mul(xc[2 * i], inv), cim = W::mul(xc[2 * i + 1], inv);
+                bool hit;
+                if (sizeof(T) == 4) {
+                    const float ca = atan2f((float)cim, (float)cre);
+                    hit = mod_match_fast(pa, ca, (float)pre, (float)pim, (float)cre, (float)cim);
+                    pa = ca;
+                } else {
+                    hit = mod_match_exact<T>(pre, pim, cre, cim);
                 }
-                cnt += best < 0.39269908169872414 ? 1 : 0;
+                pre = cre; pim = cim;
+                cnt += hit ? 1 : 0;
             }
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -171,9 +220,8 @@ detect_steps_kernel(const T *__restrict__ x, long n, long stride, int sync_step,
             bool bit = false;
             if (j < nbits) {
                 const long i0 = j * sync_step, i1 = i0 + sync_step;
-                const T a0 = angle_of<T>(xc[2 * i0], xc[2 * i0 + 1]), a1 = angle_of<T>(xc[2 * i1], xc[2 * i1 + 1]);
-                const T d = wrap_step<T>(W::sub(a1, a0));
-                bit = W::rint_(W::div(d, W::qpi())) == T(0);
+                if (sizeof(T) == 4) bit = sync_bit_fast((float)xc[2 * i0], (float)xc[2 * i0 + 1], (float)xc[2 * i1], (float)xc[2 * i1 + 1]);
+                else bit = sync_bit_exact<T>(xc[2 * i0], xc[2 * i0 + 1], xc[2 * i1], xc[2 * i1 + 1]);
             }
             const unsigned wv = __ballot_sync(0xffffffffu, bit);
             if ((threadIdx.x & 31) == 0) words[(long)dwell * words_stride + (j >> 5)] = wv;
