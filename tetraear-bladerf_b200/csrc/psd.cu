@@ -157,6 +157,153 @@ __global__ void psd_kernel(const float2 *__restrict__ iq, long frame_stride, int
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dense config mode, N = 4096, float32: three radix-16 passes with the 16 points of each small DFT in registers
+// (4096 = 16 x 16 x 16), two shared-memory exchanges, persistent CTAs that keep the twiddle tables in shared
+// memory and each thread's 16 window coefficients in registers.  With n = 256 a + b and k = c + 16 d:
+//   X[c + 16 d] = sum_b W256^(b d) [ W4096^(b c) sum_a W16^(a c) x[256 a + b] ]            (pass 1, thread b)
+// and the 256-point transforms over b = 16 e + f, d = g + 16 h split the same way:
+//   Z[c][g][f] = W256^(f g) sum_e W16^(e g) Y[c][16 e + f]   (pass 2, thread (c, f)),
+//   X[c + 16 g + 256 h] = sum_f W16^(f h) Z[c][g][f]         (pass 3, thread t = 16 g + c: k = t + 256 h, coalesced).
+constexpr int P4_PITCH = 17;                                  // Z rows of 16 padded to 17: conflict-free pass-3 reads
+constexpr int P4_BUF = 256 * P4_PITCH;
+
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// 4-point DFT in place: (a, b, c, d) <- (X0, X1, X2, X3)
+__device__ __forceinline__ void dft4(float2 &a, float2 &b, float2 &c, float2 &d)
+{
+    const float2 s0 = f2add(a, c), d0 = f2sub(a, c), s1 = f2add(b, d), d1 = f2sub(b, d);
+    const float2 mj = make_float2(d1.y, -d1.x);               // -j d1
+    a = f2add(s0, s1); c = f2sub(s0, s1);
+    b = f2add(d0, mj); d = f2sub(d0, mj);
+}
+// 16-point DFT of v[0..15] (natural order in); X[k] is left at position 4 (k & 3) + (k >> 2)
+__device__ __forceinline__ void dft16(float2 (&v)[16])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dft4(v[j], v[j + 4], v[j + 8], v[j + 12]);
+    const float c1 = 0.923879532511287f, s1 = 0.382683432365090f, r2 = 0.707106781186548f;
+    const float2 W1 = make_float2(c1, -s1), W2 = make_float2(r2, -r2), W3 = make_float2(s1, -c1), W6 = make_float2(-r2, -r2),
+                 W9 = make_float2(-c1, s1);
+    v[5] = f2mul(v[5], W1); v[6] = f2mul(v[6], W2); v[7] = f2mul(v[7], W3);
+    v[9] = f2mul(v[9], W2); v[10] = make_float2(v[10].y, -v[10].x); v[11] = f2mul(v[11], W6);
+    v[13] = f2mul(v[13], W3); v[14] = f2mul(v[14], W6); v[15] = f2mul(v[15], W9);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dft4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+__device__ __forceinline__ int dft16_index(int p) { return (p >> 2) + 4 * (p & 3); }
+
+__global__ void __launch_bounds__(256, 3)
+psd4096_f32_kernel(const float2 *__restrict__ iq, long frame_stride, long n_frames, const double *__restrict__ window,
+                   const double2 *__restrict__ tw, BandParams bp, float *__restrict__ power, double *__restrict__ stats)
+{
+    constexpr int N = 4096;
+    float2 *buf = reinterpret_cast<float2 *>(psd_smem_raw);   // pass exchange: Y[c][b] (pitch 256), then Z[t][f] (pitch 17)
+    float2 *T1 = buf + P4_BUF;                                // W4096^(b c), [c][b]
+    float2 *T2 = T1 + N;                                      // W256^(f g),  [g][f]
+    __shared__ double red[3][8];
+    __shared__ int redi[8];
+    const int t = threadIdx.x;
+    // the double table holds exp(-2 pi j i / N) for i <= 3N/4 only: use W^(i + N/2) = -W^i
+    for (int i = t; i < N; i += 256) {
+        const int e = ((i & 255) * (i >> 8)) & (N - 1);
+        const double2 w = tw[e & (N / 2 - 1)];
+        const float sg = e >= N / 2 ? -1.f : 1.f;
+        T1[i] = make_float2(sg * (float)w.x, sg * (float)w.y);
+    }
+    {
+        const int e = (16 * (t & 15) * (t >> 4)) & (N - 1);
+        const double2 w = tw[e & (N / 2 - 1)];
+        const float sg = e >= N / 2 ? -1.f : 1.f;
+        T2[t] = make_float2(sg * (float)w.x, sg * (float)w.y);
+    }
+    float win[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) win[a] = (float)window[256 * a + t];
+    __syncthreads();
+    const float invN = 1.0f / (float)N;
+    const int lane = t & 31, wp = t >> 5;
+    for (long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
+        const float2 *in = iq + frame * frame_stride;
+        float2 v[16];
+#pragma unroll
+        for (int a = 0; a < 16; ++a) { const float2 x = in[256 * a + t]; v[a] = make_float2(x.x * win[a], x.y * win[a]); }
+        dft16(v);
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            const int c = dft16_index(p);
+            buf[c * 256 + t] = c ? f2mul(v[p], T1[c * 256 + t]) : v[p];
+        }
+        __syncthreads();
+        {
+            const int c2 = t >> 4, f = t & 15;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = buf[c2 * 256 + 16 * e + f];
+            dft16(v);
+            __syncthreads();
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const int g = dft16_index(p);
+                buf[(g * 16 + c2) * P4_PITCH + f] = g ? f2mul(v[p], T2[g * 16 + f]) : v[p];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int f = 0; f < 16; ++f) v[f] = buf[t * P4_PITCH + f];
+        dft16(v);
+        // dBFS, fftshift, band statistics
+        double sig = 0.0, noise = 0.0, pk = -1e300;
+        int pki = 0x7fffffff;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            const int k = t + 256 * dft16_index(p);
+            const int j = (k + N / 2) & (N - 1);
+            const double pdb = (double)db20(mag2(v[p]) * invN);
+            if (power) power[frame * N + j] = (float)pdb;
+            if (j >= bp.start && j < bp.end) {
+                sig += pdb;
+                if (pdb > pk || (pdb == pk && j < pki)) { pk = pdb; pki = j; }
+            }
+            if (j < bp.n_lo || j >= bp.n_hi0) noise += pdb;
+        }
+        if (stats) {
+            for (int o = 16; o > 0; o >>= 1) {
+                sig += __shfl_down_sync(0xffffffffu, sig, o);
+                noise += __shfl_down_sync(0xffffffffu, noise, o);
+                const double opk = __shfl_down_sync(0xffffffffu, pk, o);
+                const int oi = __shfl_down_sync(0xffffffffu, pki, o);
+                if (opk > pk || (opk == pk && oi < pki)) { pk = opk; pki = oi; }
+            }
+            if (lane == 0) { red[0][wp] = sig; red[1][wp] = noise; red[2][wp] = pk; redi[wp] = pki; }
+            __syncthreads();
+            if (t == 0) {
+                sig = 0.0; noise = 0.0; pk = -1e300; pki = 0x7fffffff;
+                for (int ww = 0; ww < 8; ++ww) {
+                    sig += red[0][ww]; noise += red[1][ww];
+                    if (red[2][ww] > pk || (red[2][ww] == pk && redi[ww] < pki)) { pk = red[2][ww]; pki = redi[ww]; }
+                }
+                double *s = stats + frame * 8;
+                const int nband = bp.end - bp.start, nnoise = bp.n_lo + (N - bp.n_hi0);
+                if (nband <= 0) { for (int kk = 0; kk < 8; ++kk) s[kk] = 0.0; }
+                else {
+                    const double signal_power = sig / (double)nband;
+                    const double noise_floor = nnoise > 0 ? noise / (double)nnoise : -100.0;     // modern.py:1989-1992
+                    const double snr = signal_power - noise_floor;
+                    const double off = (double)(pki - N / 2) * bp.freq_step;                      // freqs[peak_idx]
+                    const bool present = (snr > 15.0) && (pk > -70.0) && ((pk - signal_power) > 3.0);   // :2006
+                    s[0] = signal_power; s[1] = pk; s[2] = (double)pki; s[3] = off; s[4] = noise_floor; s[5] = snr;
+                    s[6] = present ? 1.0 : 0.0;
+                    s[7] = (present && pk > -70.0) ? off : 0.0;                                   // :2028
+                }
+            }
+        }
+        __syncthreads();                                       // buf (and red) are reused by the next frame
+    }
+}
+
 // EMA across frames, dB domain: S = S (1 - a) + P a ; first frame S = P  (modern.py:929-935).
 // The recurrence forgets its past as (1-a)^k, so the frame axis is cut into groups of EMA_G frames and each
 // group re-runs the EMA_W frames before it as warm-up (exact when that reaches frame 0, otherwise the
@@ -215,6 +362,18 @@ int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_
     bp.n_lo = bp.start - 10 > 0 ? bp.start - 10 : 0;
     bp.n_hi0 = bp.end + 10 < n_fft ? bp.end + 10 : n_fft;
     bp.freq_step = 1.0 / ((double)n_fft * (1.0 / fs));
+    if (use_f32 && n_fft == 4096) {
+        const size_t sm4 = sizeof(float2) * (size_t)(P4_BUF + 4096 + 256);
+        static bool attr4 = false;
+        if (!attr4) {
+            cudaError_t e = cudaFuncSetAttribute(psd4096_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
+            if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(psd4096_f32_kernel): %s", cudaGetErrorString(e));
+            attr4 = true;
+        }
+        const long ctas = n_frames < 3 * 148 ? n_frames : 3 * 148;            // persistent: 3 CTAs per SM
+        psd4096_f32_kernel<<<(unsigned)ctas, 256, sm4, st>>>((const float2 *)iq, frame_stride, n_frames, window, tw, bp, power, stats);
+        TB_LAUNCH_CHECK(h);
+    } else {
     size_t smem = (use_f32 ? sizeof(float2) : sizeof(double2)) * (size_t)n_fft;
     if (smem > 48 * 1024) {
         cudaError_t e = use_f32 ? cudaFuncSetAttribute(psd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -229,6 +388,7 @@ int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_
         psd_kernel<double><<<(unsigned)n_frames, threads, smem, st>>>((const float2 *)iq, frame_stride, n_fft, log2n, window, tw, bp,
                                                                      power, stats);
     TB_LAUNCH_CHECK(h);
+    }
     if (smoothed) {
         // state_in and state_out may alias only when a single group runs; otherwise read a snapshot
         double *state_in = ema_state;
