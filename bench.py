@@ -148,6 +148,24 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def bind_to_gpu_numa(torch, local_rank):
+    """Pin this rank to the CPUs NVML lists as local to its GPU, so that the pinned staging buffer it allocates
+    next is first-touched on that NUMA node (matters for the end-to-end figure when several ranks copy at once)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        n = os.cpu_count()
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = [i for i in range(n) if (mask[i // 64] >> (i % 64)) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -164,6 +182,8 @@ def run_b200(args):
         dist.barrier()
     torch.cuda.set_device(local_rank)
     from tetraear_b200 import pipeline, _lib
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = bind_to_gpu_numa(torch, local_rank) if world > 1 else 0
 
     # every rank owns one independent 10 s capture (weak scaling: shard = capture segment per GPU)
     x = make_c1(seed=1234 + rank)
@@ -308,7 +328,7 @@ def run_b200(args):
                                    "fast32": "time-parallel float32 decimator and float32 channel filter; dibits identical on the parity cases, "
                                              "soft symbols <= 1e-4 of full scale (tests/test_gpu_parity.py::test_fast_mode_within_tolerance)"}[args.mode] + ")",
                    "l2": "input 192 MB per step > 126 MB L2, no flush needed", "parallelism": f"capture segment per GPU x{world}",
-                   "stream_lanes": args.lanes},
+                   "stream_lanes": args.lanes, "cpus_bound_per_rank": numa_cpus},
         "crc_pass_bursts_per_s": round(bursts_per_s, 1), "crc_pass_per_step": int(stats[1] // max(args.steps, 1)),
         "gpu_launches": int(launches),
         "e2e": {"value": round(e2e, 3), "unit": "Msamples/s", "h2d_bytes_per_step": pipe.h2d_bytes(n_chunks),
