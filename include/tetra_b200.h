@@ -230,6 +230,14 @@ int tb200_etsi_demod_batch(tb200_handle h, const void *d_iq_c64, int n_streams, 
 int tb200_etsi_find_bursts(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,
                            const int32_t *d_n_soft, double threshold, float *d_metric, int8_t *d_blocks,
                            int32_t *d_burst_pos, int32_t *d_n_bursts, int max_bursts, void *stream);
+/* synchronisation-burst search: normalised soft correlation with the 38-bit sync training sequence y at every symbol
+ * position (d_metric scratch as above); for every sync burst found the 120 SB1 soft bits go to d_sb1
+ * [n_streams][max_bursts][120] (input of tb200_etsi_decode_batch, channel 2 = BSCH, scrambling init 3: its 60 type-1
+ * bits carry colour code, MCC and MNC, i.e. the scrambling init of every other channel) and, if d_bkn2 != NULL, the 216
+ * BKN2 soft bits to d_bkn2 [n_streams][max_bursts][216]. */
+int tb200_etsi_find_sync_bursts(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,
+                                const int32_t *d_n_soft, double threshold, float *d_metric, int8_t *d_sb1, int8_t *d_bkn2,
+                                int32_t *d_burst_pos, int32_t *d_n_bursts, int max_bursts, void *stream);
 
 /* ---- waterfall PSD + AFC statistics (tetraear/ui/modern.py:1926-2029, :923-947) ---------
  * frame i = Hann(n_fft) * iq[i*frame_stride : +n_fft]; power = 20 log10(|fftshift FFT|/n_fft + 1e-20)

@@ -47,3 +47,53 @@ def test_receiver_round_trip(fs, t_off, sigma):
                 assert np.array_equal(b["blocks"], truth[s][idx]), (s, idx)
                 good += 1
         assert good >= n_bursts - 5, (s, good)
+
+
+def test_bsch_fields_round_trip_cpu():
+    f = dict(system_code=1, colour_code=17, timeslot=2, frame=11, multiframe=42, sharing_mode=1, ts_reserved_frames=3,
+             u_plane_dtx=1, frame18_extension=0, reserved=0, mcc=262, mnc=42, neighbour_cell_broadcast=2,
+             cell_service_level=1, late_entry=1)
+    b = etsi.bsch_pack(**f)
+    assert len(b) == 60 and etsi.bsch_unpack(b) == f
+    bits, t1, init = etsi.make_etsi_stream(9, seed=2, sync_every=4)
+    assert bits[214:252].tolist() == etsi.TS_Y.tolist() and bits[14:94].tolist() == etsi.FREQ_CORRECTION.tolist()
+    assert bits[510 + 244:510 + 266].tolist() == etsi.TS_N.tolist()
+    assert init == etsi.scrambling_init(262, 42, 17)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fs,sigma", [(72000.0, 0.0), (50000.0, 0.05)])
+def test_sync_burst_acquisition_bootstraps_the_scrambling_code(fs, sigma):
+    """No network code given: find the synchronisation bursts (38-bit sequence y), decode BSCH (init 3), read
+    MCC / MNC / colour code, derive the scrambling init and decode the normal bursts with it."""
+    import __graft_entry__ as entry
+    entry.build()
+    n_bursts, k = 26, 6
+    nets = [(262, 42, 17), (901, 16383, 63), (1, 0, 0)]
+    streams, truth = [], []
+    for s, net in enumerate(nets):
+        bits, t1, init = etsi.make_etsi_stream(n_bursts, seed=40 + s, sync_every=k, network=net)
+        streams.append(etsi.modulate_dqpsk(bits, fs, sigma=sigma, t_offset=0.15 * s, seed=s))
+        truth.append((t1, init))
+    n = min(len(v) for v in streams)
+    x = np.stack([v[:n] for v in streams])
+    rx = etsi.EtsiReceiver(fs, max_streams=3, max_samples=n)
+    acq = rx.acquire(x)
+    for s, net in enumerate(nets):
+        assert len(acq[s]) >= n_bursts // k - 1, (s, len(acq[s]))          # the first burst may precede timing lock
+        for a in acq[s]:
+            idx = int(round(a["start"] / 510.0))
+            assert abs(a["start"] - 510 * idx) <= 4 and idx % k == 0
+            f = a["fields"]
+            assert (f["mcc"], f["mnc"], f["colour_code"]) == net and f["timeslot"] == idx % 4
+            assert a["scrambling_init"] == truth[s][1]
+    # the derived code decodes the traffic of its own stream
+    for s in range(3):
+        res = rx.run(x[s:s + 1], acq[s][0]["scrambling_init"])[0]
+        good = 0
+        for b in res:
+            idx = int(round(b["start"] / 510.0))
+            if idx % k and b["crc_ok"].all() and 0 <= idx < n_bursts:
+                assert np.array_equal(b["blocks"], truth[s][0][idx])
+                good += 1
+        assert good >= (n_bursts - n_bursts // k) - 6, (s, good)

@@ -587,6 +587,17 @@ extern "C" int tb200_etsi_find_bursts(tb200_handle h, const float *d_soft, int n
                                    d_n_bursts, max_bursts, (cudaStream_t)stream);
 }
 
+extern "C" int tb200_etsi_find_sync_bursts(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,
+                                           const int32_t *d_n_soft, double threshold, float *d_metric, int8_t *d_sb1,
+                                           int8_t *d_bkn2, int32_t *d_burst_pos, int32_t *d_n_bursts, int max_bursts, void *stream)
+{
+    if (!h || n_streams < 0 || !d_soft || !d_n_soft || !d_metric || !d_sb1 || !d_burst_pos || !d_n_bursts || max_bursts <= 0)
+        return fail(TB200_E_ARG, "tb200_etsi_find_sync_bursts: bad argument");
+    StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
+    return launch_etsi_find_sync(h, d_soft, n_streams, soft_stride, d_n_soft, (float)threshold, d_metric, d_sb1, d_bkn2, d_burst_pos,
+                                 d_n_bursts, max_bursts, (cudaStream_t)stream);
+}
+
 extern "C" int tb200_channelize(tb200_handle h, const void *d_iq_c64, int64_t n_samples, int n_channels, void *d_out_c64,
                                 int64_t out_stride, int64_t n_frames, void *stream)
 {

@@ -184,6 +184,65 @@ __global__ void etsi_find_bursts_kernel(const float *__restrict__ soft, long sof
     if (lane == 0) n_bursts[s] = found;
 }
 
+
+// ---- synchronisation continuous downlink burst (EN 300 392-2 cl. 9.4.4.2.6): q(12) PA(2) frequency correction(80)
+// SB1(120) sync training sequence y(38) BB(30) BKN2(216) PB(2) q(10): y starts at bit 214, SB1 at 94, BKN2 at 282.
+__constant__ int8_t c_ts_y[38] = {1, 1, -1, -1, -1, -1, -1, 1, 1, -1, -1, 1, 1, 1, -1, -1, 1, 1, 1, -1, 1, -1, -1, 1, 1, 1, -1, -1, -1,
+                                  -1, -1, 1, 1, -1, -1, 1, 1, 1};
+
+__global__ void etsi_sync_corr_kernel(const float *__restrict__ soft, long soft_stride, const int32_t *__restrict__ n_soft,
+                                      float *__restrict__ metric)
+{
+    int s = blockIdx.y;
+    long nb = n_soft[s];
+    long p = 2 * (blockIdx.x * (long)blockDim.x + threadIdx.x);
+    if (p + 38 > nb) return;
+    const float *b = soft + (long)s * soft_stride + p;
+    float c = 0.f, en = 0.f;
+#pragma unroll
+    for (int i = 0; i < 38; ++i) { float v = fminf(fmaxf(b[i], -1.0f), 1.0f); c += v * c_ts_y[i]; en += fabsf(v); }
+    metric[(long)s * (soft_stride / 2) + p / 2] = c / (en + 1e-20f);
+}
+
+// one warp per stream: first position over threshold, local maximum of the next 4 symbol positions, emit SB1
+// (120 soft bits, input of the BSCH decoder) and BKN2 (216), skip ahead one burst.
+__global__ void etsi_find_sync_kernel(const float *__restrict__ soft, long soft_stride, const int32_t *__restrict__ n_soft,
+                                      const float *__restrict__ metric, int n_streams, float thr, int8_t *__restrict__ sb1,
+                                      int8_t *__restrict__ bkn2, int32_t *__restrict__ burst_pos, int32_t *__restrict__ n_bursts,
+                                      int max_bursts, float quant)
+{
+    const int lane = threadIdx.x & 31;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= n_streams) return;
+    const long nb = n_soft[s];
+    const long npos = (nb >= 38) ? (nb - 38) / 2 + 1 : 0;
+    const float *m = metric + (long)s * (soft_stride / 2);
+    const float *b = soft + (long)s * soft_stride;
+    int found = 0;
+    long i = 0;
+    while (i < npos && found < max_bursts) {
+        long p = i + lane;
+        float v = (p < npos) ? m[p] : 0.f;
+        unsigned ball = __ballot_sync(0xffffffffu, v >= thr);
+        if (!ball) { i += 32; continue; }
+        long first = i + (__ffs(ball) - 1);
+        long best = first;
+        float bv = m[first];
+        for (int d = 1; d < 4; ++d) if (first + d < npos && m[first + d] > bv) { bv = m[first + d]; best = first + d; }
+        long start = 2 * best - 214;
+        if (start >= 0 && start + 510 <= nb) {
+            int8_t *o1 = sb1 + ((long)s * max_bursts + found) * 120;
+            int8_t *o2 = bkn2 ? bkn2 + ((long)s * max_bursts + found) * 216 : nullptr;
+            for (int j = lane; j < 120; j += 32) o1[j] = (int8_t)fminf(fmaxf(rintf(b[start + 94 + j] * quant), -127.f), 127.f);
+            if (o2) for (int j = lane; j < 216; j += 32) o2[j] = (int8_t)fminf(fmaxf(rintf(b[start + 282 + j] * quant), -127.f), 127.f);
+            if (lane == 0) burst_pos[(long)s * max_bursts + found] = (int32_t)start;
+            ++found;
+        }
+        i = best + 200;
+    }
+    if (lane == 0) n_bursts[s] = found;
+}
+
 void make_mf_taps(double sps, float *taps)
 {
     const double alpha = 0.35;
@@ -234,6 +293,21 @@ int launch_etsi_find_bursts(tb200_handle h, const float *soft, int n_streams, lo
     int threads = 128, blocks_n = (n_streams * 32 + threads - 1) / threads;
     etsi_find_bursts_kernel<<<blocks_n, threads, 0, st>>>(soft, soft_stride, n_soft, metric, n_streams, thr, blocks, burst_pos,
                                                          n_bursts, max_bursts, 45.0f);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+int launch_etsi_find_sync(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft, float thr,
+                          float *metric, int8_t *sb1, int8_t *bkn2, int32_t *burst_pos, int32_t *n_bursts, int max_bursts,
+                          cudaStream_t st)
+{
+    if (n_streams <= 0) return TB200_OK;
+    dim3 grid((unsigned)((soft_stride / 2 + 255) / 256), (unsigned)n_streams);
+    etsi_sync_corr_kernel<<<grid, 256, 0, st>>>(soft, soft_stride, n_soft, metric);
+    TB_LAUNCH_CHECK(h);
+    int threads = 128, blocks_n = (n_streams * 32 + threads - 1) / threads;
+    etsi_find_sync_kernel<<<blocks_n, threads, 0, st>>>(soft, soft_stride, n_soft, metric, n_streams, thr, sb1, bkn2, burst_pos,
+                                                       n_bursts, max_bursts, 45.0f);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
 }

@@ -138,6 +138,15 @@ TS_Q = np.array([1, 0, 1, 1, 0, 1, 1, 1, 0, 0, 0, 0, 0, 1, 1, 0, 1, 0, 1, 1, 0, 
 # normal continuous downlink burst, bit offsets (EN 300 392-2 cl. 9.4.4.3.2)
 NDB = {"q_tail": (0, 12), "pa": (12, 14), "bkn1": (14, 230), "bb1": (230, 244), "ts": (244, 266),
        "bb2": (266, 282), "bkn2": (282, 498), "pb": (498, 500), "q_head": (500, 510)}
+# synchronisation continuous downlink burst (cl. 9.4.4.2.6): SB1 = the BSCH block, y = 38-bit sync training sequence
+TS_Y = np.array([int(c) for c in "11000001100111001110100111000001100111"], dtype=np.uint8)
+SDB = {"q_tail": (0, 12), "pa": (12, 14), "fc": (14, 94), "sb1": (94, 214), "ts": (214, 252), "bb": (252, 282),
+       "bkn2": (282, 498), "pb": (498, 500), "q_head": (500, 510)}
+FREQ_CORRECTION = np.concatenate([np.ones(8, np.uint8), np.zeros(64, np.uint8), np.ones(8, np.uint8)])
+# BSCH type-1 block: SYNC PDU (cl. 21.4.4.2) + D-MLE-SYNC (cl. 18.4.2.1), 60 bits
+BSCH_FIELDS = (("system_code", 4), ("colour_code", 6), ("timeslot", 2), ("frame", 5), ("multiframe", 6), ("sharing_mode", 2),
+               ("ts_reserved_frames", 3), ("u_plane_dtx", 1), ("frame18_extension", 1), ("reserved", 1),
+               ("mcc", 10), ("mnc", 14), ("neighbour_cell_broadcast", 2), ("cell_service_level", 2), ("late_entry", 1))
 # dibit (b1, b2) -> differential phase
 DQPSK_DPHI = {(0, 0): np.pi / 4, (0, 1): 3 * np.pi / 4, (1, 1): -3 * np.pi / 4, (1, 0): -np.pi / 4}
 
@@ -170,14 +179,54 @@ def build_normal_burst(bkn1, bkn2, rng=None, ts=TS_N):
     return b
 
 
-def make_etsi_stream(n_bursts, seed=0, scramb_init=None, ts=TS_N):
-    """Back-to-back normal bursts carrying random SCH/HD blocks.  Returns (bits, type1 [n,2,124])."""
+def bsch_pack(**fields):
+    """60 type-1 bits of a BSCH block from named fields (MSB first; missing fields = 0)."""
+    out = []
+    for name, width in BSCH_FIELDS:
+        v = int(fields.get(name, 0))
+        out += [(v >> (width - 1 - i)) & 1 for i in range(width)]
+    return np.array(out, dtype=np.uint8)
+
+
+def bsch_unpack(bits):
+    bits = np.asarray(bits).astype(np.int64)
+    out, pos = {}, 0
+    for name, width in BSCH_FIELDS:
+        out[name] = int(sum(int(b) << (width - 1 - i) for i, b in enumerate(bits[pos:pos + width])))
+        pos += width
+    return out
+
+
+def build_sync_burst(sb1, bkn2, rng=None):
+    """510-bit synchronisation continuous downlink burst around the 120-bit BSCH block and a 216-bit block."""
+    rng = np.random.default_rng(0) if rng is None else rng
+    b = rng.integers(0, 2, 510, dtype=np.uint8)
+    b[0:12] = TS_Q[10:22]
+    b[14:94] = FREQ_CORRECTION
+    b[94:214] = sb1
+    b[214:252] = TS_Y
+    b[282:498] = bkn2
+    b[500:510] = TS_Q[0:10]
+    return b
+
+
+def make_etsi_stream(n_bursts, seed=0, scramb_init=None, ts=TS_N, sync_every=0, network=(262, 42, 17)):
+    """Back-to-back downlink bursts carrying random SCH/HD blocks.  With sync_every = k > 0 every k-th burst is a
+    synchronisation burst whose BSCH block announces `network` = (MCC, MNC, colour code) and whose BKN2 is an SCH/HD
+    block (its first type-1 row of that burst is then unused).  Returns (bits, type1 [n,2,124], scrambling init)."""
     rng = np.random.default_rng(seed)
-    init = scrambling_init(262, 42, 17) if scramb_init is None else scramb_init
+    init = scrambling_init(*network) if scramb_init is None else scramb_init
     t1 = rng.integers(0, 2, (n_bursts, 2, 124), dtype=np.uint8)
     t5 = encode(t1.reshape(-1, 124), "SCH/HD", init).reshape(n_bursts, 2, 216)
-    bits = np.concatenate([build_normal_burst(t5[i, 0], t5[i, 1], rng, ts) for i in range(n_bursts)])
-    return bits, t1, init
+    out = []
+    for i in range(n_bursts):
+        if sync_every and i % sync_every == 0:
+            sb = bsch_pack(mcc=network[0], mnc=network[1], colour_code=network[2], timeslot=i % 4, frame=1 + (i // 4) % 18,
+                           multiframe=1 + (i // 72) % 60)
+            out.append(build_sync_burst(encode(sb[None, :], "BSCH", 3)[0], t5[i, 1], rng))
+        else:
+            out.append(build_normal_burst(t5[i, 0], t5[i, 1], rng, ts))
+    return np.concatenate(out), t1, init
 
 
 def modulate_dqpsk(bits, fs, symbol_rate=18000.0, sigma=0.0, freq=0.0, t_offset=0.0, amplitude=1.0, seed=0,
@@ -233,6 +282,57 @@ class EtsiReceiver:
         self.crc_ok = _dev.zeros((S * self.max_bursts * 2,), torch.uint8, device)
         self.path_metric = _dev.zeros((S * self.max_bursts * 2,), torch.int32, device)
         self.symbols = None
+        self.max_sync = self.max_bursts
+        self.sb1 = _dev.zeros((S, self.max_sync, 120), torch.int8, device)
+        self.sync_pos = _dev.zeros((S, self.max_sync), torch.int32, device)
+        self.n_sync = _dev.zeros((S,), torch.int32, device)
+        self.sync_bits = _dev.zeros((S * self.max_sync, 40), torch.uint8, device)
+        self.sync_crc = _dev.zeros((S * self.max_sync,), torch.uint8, device)
+        self.sync_metric = _dev.zeros((S * self.max_sync,), torch.int32, device)
+
+    def acquire_device(self, n_streams, threshold=0.8):
+        """After a demodulation (run_device*): search the soft bits of every stream for synchronisation bursts (38-bit
+        sequence y) and decode their BSCH blocks (scrambling init 3).  Asynchronous; see acquire() for the host view."""
+        from . import _dev
+        h, lib = self._h, self._h.lib
+        st = _dev.stream_ptr(self.device)
+        self.metric.zero_()
+        _lib.check(lib.tb200_etsi_find_sync_bursts(h.h, self.soft.data_ptr(), n_streams, self.soft_stride, self.n_soft.data_ptr(),
+                                                   float(threshold), self.metric.data_ptr(), self.sb1.data_ptr(), None,
+                                                   self.sync_pos.data_ptr(), self.n_sync.data_ptr(), self.max_sync, st))
+        _lib.check(lib.tb200_etsi_decode_batch(h.h, self.sb1.data_ptr(), n_streams * self.max_sync, CHANNEL_IDS["BSCH"], 3,
+                                               self.sync_bits.data_ptr(), self.sync_crc.data_ptr(), self.sync_metric.data_ptr(), st))
+
+    def acquire(self, iq, threshold=0.8):
+        """numpy complex64 [n_streams, n] -> per stream the list of CRC-clean BSCH blocks found:
+        dicts(start, fields (bsch_unpack), scrambling_init).  The bootstrap of `etsi` mode: no network code needed."""
+        from . import _dev
+        x = np.ascontiguousarray(iq, dtype=np.complex64)
+        if x.ndim == 1:
+            x = x[None, :]
+        d = _dev.to_dev(x.view(np.float32).reshape(x.shape[0], x.shape[1], 2), self.device)
+        h, lib = self._h, self._h.lib
+        _lib.check(lib.tb200_etsi_demod_batch(h.h, d.data_ptr(), x.shape[0], x.shape[1], x.shape[1], self.fs, None,
+                                              self.soft.data_ptr(), self.soft_stride, self.n_soft.data_ptr(),
+                                              _dev.stream_ptr(self.device)))
+        self.acquire_device(x.shape[0], threshold)
+        return self.sync_results(x.shape[0])
+
+    def sync_results(self, n_streams):
+        ns = self.n_sync.cpu().numpy()[:n_streams]
+        pos = self.sync_pos.cpu().numpy()[:n_streams]
+        bits = np.unpackbits(self.sync_bits.cpu().numpy(), axis=1)[:, :60].reshape(self.max_streams, self.max_sync, 60)
+        ok = self.sync_crc.cpu().numpy().reshape(self.max_streams, self.max_sync).astype(bool)
+        out = []
+        for s in range(n_streams):
+            rows = []
+            for i in range(int(ns[s])):
+                if ok[s, i]:
+                    f = bsch_unpack(bits[s, i])
+                    rows.append({"start": int(pos[s, i]), "fields": f,
+                                 "scrambling_init": scrambling_init(f["mcc"], f["mnc"], f["colour_code"])})
+            out.append(rows)
+        return out
 
     def run_device(self, iq, n_samples, scramb_init, threshold=0.8, keep_symbols=False):
         """iq: CUDA float32 tensor [n_streams, stride, 2].  Asynchronous; results stay on the device."""
