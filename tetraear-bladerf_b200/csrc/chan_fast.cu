@@ -11,6 +11,8 @@
 // warp Kogge-Stone scans give the in-pass carries and the neighbour warp's end state the
 // cross-pass carry (|p|max^256 < 1e-15).  All float64: agrees with scipy to ~1e-13.
 #include <complex>
+#include <mutex>
+#include <vector>
 #include "common.h"
 #include "kernels.h"
 #include "packed.h"
@@ -640,8 +642,18 @@ static int launch_t(tb200_handle h, const void *x, int n_chunks, long n, long in
 {
     const int tiles = chan_fast_tiles(h, sizeof(TI) == 4 ? TB200_DTYPE_C64 : TB200_DTYPE_C128, n);
     if (use_packed32(h, sizeof(TI) == 4 ? TB200_DTYPE_C64 : TB200_DTYPE_C128, n)) {
+        static std::mutex mu32;
+        static ChanFast32Params F32;
+        static double key[3] = {0, 0, 0};
         ChanFast32Params F;
-        make_chan32_params(K, F);
+        {
+            std::lock_guard<std::mutex> lk(mu32);
+            if (!(key[0] == K.p[0][0] && key[1] == K.p[0][1] && key[2] == K.c0p)) {
+                make_chan32_params(K, F32);
+                key[0] = K.p[0][0]; key[1] = K.p[0][1]; key[2] = K.c0p;
+            }
+            F = F32;
+        }
         chan_fast32_kernel<<<n_chunks * tiles, CF_W * 32, 0, st>>>((const float *)x, n, in_stride, tiles, freq_off, fs, F, filtered,
                                                                  out_stride, phase_partial, sps, step);
     } else if (h->chan_f32)
@@ -659,9 +671,23 @@ int launch_channel_fast(tb200_handle h, const void *x, int dtype, int n_chunks, 
                         const double *freq_off, double fs, double bandwidth, double *filtered, long out_stride,
                         double *phase_partial, double *phase_tail, int sps, int step, cudaStream_t st)
 {
+    // constants depend on (bandwidth, fs) only: cached (see launch_decimate_fast)
+    struct Cached { double bw, fs; ChanFastParams K; };
+    static std::mutex mu;
+    static std::vector<Cached> cache;
     ChanFastParams K;
-    int rc = make_chan_params(bandwidth, fs, K);
-    if (rc) return rc;
+    bool hit = false;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (const Cached &c : cache) if (c.bw == bandwidth && c.fs == fs) { K = c.K; hit = true; break; }
+    }
+    if (!hit) {
+        int rc0 = make_chan_params(bandwidth, fs, K);
+        if (rc0) return rc0;
+        std::lock_guard<std::mutex> lk(mu);
+        if (cache.size() >= 16) cache.erase(cache.begin());
+        cache.push_back(Cached{bandwidth, fs, K});
+    }
     if (sps > TB200_MAX_PHASES || sps <= 1) phase_partial = phase_tail = nullptr;
     if (dtype == TB200_DTYPE_C64)
         return launch_t<float>(h, x, n_chunks, n, in_stride, freq_off, fs, K, filtered, out_stride, phase_partial, phase_tail, sps, step, st);

@@ -23,6 +23,8 @@
 // planes, one row of q samples per output with an odd row pitch (q+1 for even q), so that the
 // 32 lanes of a warp — each owning R=3 consecutive rows — read conflict-free.
 #include <complex>
+#include <mutex>
+#include <vector>
 #include "common.h"
 #include "kernels.h"
 #include "packed.h"
@@ -418,9 +420,26 @@ int launch_decimate_fast(tb200_handle h, const void *x, int n_chunks, long n, lo
                          const DecimDesign &d, void *dec_out, long n_dec, cudaStream_t st)
 {
     if (!fast_decimator_supported(q)) return fail(TB200_E_ARG, "fast decimator: q=%d not instantiated", q);
+    // the modal constants depend on (design, q, n, n_dec) only: keep the last few sets instead of re-deriving them
+    // (dozens of complex pow) on every launch — the host must stay ahead of a ~50 us kernel
+    struct Cached { int q; long n, n_dec; float g; FastDecimParams K; };
+    static std::mutex mu;
+    static std::vector<Cached> cache;
     FastDecimParams K;
-    int rc = make_fast_params(d, q, n, n_dec, K);
-    if (rc) return rc;
+    bool hit = false;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (const Cached &c : cache)
+            if (c.q == q && c.n == n && c.n_dec == n_dec && c.g == d.sos32[0]) { K = c.K; hit = true; break; }
+    }
+    if (!hit) {
+        int rc0 = make_fast_params(d, q, n, n_dec, K);
+        if (rc0) return rc0;
+        std::lock_guard<std::mutex> lk(mu);
+        if (cache.size() >= 16) cache.erase(cache.begin());
+        cache.push_back(Cached{q, n, n_dec, d.sos32[0], K});
+    }
+    int rc = TB200_OK;
     if (q == 10) rc = launch_q<10>(h, x, n_chunks, n, chunk_stride, n_dec, K, dec_out, st);
     else if (q == 7) rc = launch_q<7>(h, x, n_chunks, n, chunk_stride, n_dec, K, dec_out, st);
     else rc = launch_q<8>(h, x, n_chunks, n, chunk_stride, n_dec, K, dec_out, st);

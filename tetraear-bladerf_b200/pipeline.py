@@ -37,13 +37,22 @@ class ReceivePipeline:
                 hh.set_option(_lib.OPT_CHAN_F32, 1)
         self.h = self.handles[0]
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.n_lanes)]
+        # the sync search / burst parse of a sub-batch is latency-bound (one small CTA per chunk): it runs on a
+        # HIGH-priority stream so that its CTAs take the SM slots the bulk kernels of the other lanes free up,
+        # instead of queueing behind them; the dibit rows are double-buffered so that the next batch's
+        # demodulation need not wait for this batch's decode
+        self.tail_streams = [torch.cuda.Stream(device=self.dev, priority=-1) for _ in range(self.n_lanes)]
         self._pending = []
+        self._dec_done = [[None, None] for _ in range(self.n_lanes)]
+        self._flip = 0
         C = self.max_chunks
         self.stride = int(self.plan.max_symbols) + 8
         self.max_frames = (2 * self.stride) // 250 + 2
-        self.dibits = torch.zeros((C, self.stride), dtype=torch.uint8, device=self.dev)
+        self._dibits2 = torch.zeros((2, C, self.stride), dtype=torch.uint8, device=self.dev)
+        self.dibits = self._dibits2[0]
         self.symbols = torch.zeros((C, self.stride, 2), dtype=torch.float64, device=self.dev) if keep_symbols else None
-        self.n_dibits = torch.zeros((C,), dtype=torch.int32, device=self.dev)
+        self._n_dibits2 = torch.zeros((2, C), dtype=torch.int32, device=self.dev)
+        self.n_dibits = self._n_dibits2[0]
         self.phase = torch.zeros((C,), dtype=torch.int32, device=self.dev)
         self.frames = torch.zeros((C, self.max_frames, _lib.FRAME_DTYPE.itemsize), dtype=torch.uint8, device=self.dev)
         self.n_frames = torch.zeros((C,), dtype=torch.int32, device=self.dev)
@@ -65,16 +74,33 @@ class ReceivePipeline:
         per = (n_chunks + self.n_lanes - 1) // self.n_lanes
         fork = torch.cuda.Event()
         fork.record(main)                       # the batch (input, previous consumers) is ready at this point of `main`
+        buf = self._flip
+        self._flip ^= 1
+        self.dibits, self.n_dibits = self._dibits2[buf], self._n_dibits2[buf]     # where this batch's rows go
         for li in range(self.n_lanes):
             lo, hi = li * per, min(n_chunks, (li + 1) * per)
             if lo >= hi:
                 break
             st = self.streams[li]
             st.wait_event(fork)
-            self._run_slice(self.handles[li], st.cuda_stream, iq, freq_off, lo, hi, decode)
+            if not decode:
+                self._run_slice(self.handles[li], st.cuda_stream, iq, freq_off, lo, hi, False)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                self._pending.append(ev)
+                continue
+            if self._dec_done[li][buf] is not None:
+                st.wait_event(self._dec_done[li][buf])          # the decode that last read this dibit buffer
+            self._run_slice(self.handles[li], st.cuda_stream, iq, freq_off, lo, hi, False)
             ev = torch.cuda.Event()
             ev.record(st)
-            self._pending.append(ev)
+            tl = self.tail_streams[li]
+            tl.wait_event(ev)
+            self._decode_slice(self.handles[li], tl.cuda_stream, lo, hi)
+            done = torch.cuda.Event()
+            done.record(tl)
+            self._dec_done[li][buf] = done
+            self._pending.append(done)
         if join:
             self.join()
         return n_chunks
@@ -97,11 +123,14 @@ class ReceivePipeline:
             freq_off.data_ptr() + lo * 8 if freq_off is not None else None, self.dibits.data_ptr() + lo * self.stride,
             sym_ptr, self.stride, self.n_dibits.data_ptr() + lo * 4, self.phase.data_ptr() + lo * 4, stream))
         if decode:
-            fsz = self.max_frames * _lib.FRAME_DTYPE.itemsize
-            _lib.check(lib.tb200_decode_batch(h, self.dibits.data_ptr() + lo * self.stride, n, self.stride,
-                                              self.n_dibits.data_ptr() + lo * 4, self.frames.data_ptr() + lo * fsz,
-                                              self.max_frames, self.n_frames.data_ptr() + lo * 4,
-                                              self.stats.data_ptr(), stream))
+            self._decode_slice(handle, stream, lo, hi)
+
+    def _decode_slice(self, handle, stream, lo, hi):
+        fsz = self.max_frames * _lib.FRAME_DTYPE.itemsize
+        _lib.check(handle.lib.tb200_decode_batch(handle.h, self.dibits.data_ptr() + lo * self.stride, hi - lo, self.stride,
+                                                 self.n_dibits.data_ptr() + lo * 4, self.frames.data_ptr() + lo * fsz,
+                                                 self.max_frames, self.n_frames.data_ptr() + lo * 4,
+                                                 self.stats.data_ptr(), stream))
 
     # ---------------------------------------------------------------- host-buffer path (end to end)
     def run_host(self, iq_host, freq_off=None, decode=True):
