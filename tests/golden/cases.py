@@ -32,6 +32,8 @@ def process_cases():
     cases.append(("wide_q83_afc", 20e6, 700.0, wide))
     cases.append(("rate_1p8M", 1.8e6, 0.0, synth.make_capture(98000, 98, seed=3)))
     cases.append(("rate_240k_nodecim", 240000.0, 0.0, synth.make_capture(20000, 13, seed=4)))
+    cases.append(("rate_2p0M_q8", 2.0e6, 0.0, synth.make_capture(90000, 111, seed=6)))
+    cases.append(("rate_2p0M_q8_afc", 2.0e6, -812.5, synth.make_capture(90000, 111, seed=6)))
     cases.append(("c128_input", 2.4e6, 0.0, cap[:40000].astype(np.complex128)))
     cases.append(("ragged_40001", 2.4e6, 250.0, cap[:40001]))
     for m in (1, 2, 16, 27, 28, 29, 100, 150, 160, 161, 290, 500):

@@ -80,12 +80,13 @@ def test_burst_batch_fuzz(mods):
     assert p.stats["crc_pass"] == int(o["crc_ok"].sum())
 
 
-@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("mode", ["exact", "fast", "fast32"])
 def test_process_fuzz(mods, mode):
     signal, core, synth = mods
     rng = np.random.default_rng(99)
-    for case in range(10):
-        fs, sps_total = [(2.4e6, 130), (2.4e6, 130), (1.8e6, 98), (240000.0, 13)][case % 4]
+    for case in range(15):
+        # q = 10, 10, 7, none, 8 (all three FAST instantiations + the undecimated path)
+        fs, sps_total = [(2.4e6, 130), (2.4e6, 130), (1.8e6, 98), (240000.0, 13), (2.0e6, 111)][case % 5]
         n = int(rng.integers(3000, 70000))
         f = float(rng.choice([0.0, 0.0, rng.uniform(-3000, 3000)]))
         iq = synth.make_capture(n, sps_total, seed=500 + case, sigma=0.03)
