@@ -347,14 +347,14 @@ __device__ __forceinline__ void c32_dir(const float2 (&xs)[CF_R], float2 (&y)[CF
         cp a = s[m];
 #pragma unroll
         for (int st = 0; st < 5; ++st) {
-            if (st < K.nstage[m]) {
-                cp o;
-                o.re = FWD ? shfl2_up(a.re, 1 << st) : shfl2_down(a.re, 1 << st);
-                o.im = FWD ? shfl2_up(a.im, 1 << st) : shfl2_down(a.im, 1 << st);
-                cf g = ld2(K.ppow[st][m]);
-                if (FWD ? (lane < (1 << st)) : (lane + (1 << st) >= 32)) g.x = g.y = 0.f;
-                a = cpfma(g, o, a);
-            }
+            // (a uniform test on K.nstage[m] would skip the last stages of the fast-decaying mode, but the branch
+            // costs more issue slots than the 10 instructions it saves)
+            cp o;
+            o.re = FWD ? shfl2_up(a.re, 1 << st) : shfl2_down(a.re, 1 << st);
+            o.im = FWD ? shfl2_up(a.im, 1 << st) : shfl2_down(a.im, 1 << st);
+            cf g = ld2(K.ppow[st][m]);
+            if (FWD ? (lane < (1 << st)) : (lane + (1 << st) >= 32)) g.x = g.y = 0.f;
+            a = cpfma(g, o, a);
         }
         cp cin;
         cin.re = FWD ? shfl2_up(a.re, 1) : shfl2_down(a.re, 1);
@@ -499,13 +499,22 @@ chan_fast32_kernel(const float *__restrict__ x, long n, long in_stride, int tile
                 }
             }
         }
-        double2 *out = reinterpret_cast<double2 *>(filtered) + (long)chunk * out_stride;
+        double2 *out = reinterpret_cast<double2 *>(filtered) + (long)chunk * out_stride + m0;
+        const int mi = (int)m0, ni = (int)n;                     // n < 2^30 (launch_t): 32-bit index tests
+        float *pw = pws + (w - 1) * CF_P + lane * CF_R;
+        if (mi >= 0 && mi + CF_R <= ni) {
 #pragma unroll
-        for (int r = 0; r < CF_R; ++r) {
-            const long m = m0 + r;
-            const bool ok = m >= 0 && m < n;
-            if (ok) out[m] = make_double2((double)y[r].x, (double)y[r].y);
-            if (phase_partial) pws[(w - 1) * CF_P + lane * CF_R + r] = ok ? y[r].x * y[r].x + y[r].y * y[r].y : 0.f;
+            for (int r = 0; r < CF_R; ++r) {
+                out[r] = make_double2((double)y[r].x, (double)y[r].y);
+                if (phase_partial) pw[r] = y[r].x * y[r].x + y[r].y * y[r].y;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) {
+                const bool ok = mi + r >= 0 && mi + r < ni;
+                if (ok) out[r] = make_double2((double)y[r].x, (double)y[r].y);
+                if (phase_partial) pw[r] = ok ? y[r].x * y[r].x + y[r].y * y[r].y : 0.f;
+            }
         }
     }
     // ---- per-phase power partial sums for the timing pick (extract_symbols, processor.py:196-210): 16 threads per
