@@ -119,7 +119,7 @@ int tb200_set_sample_rate(tb200_handle h, double sample_rate); /* attr is mutate
 /* options: TB200_OPT_CHAN_F32 = 1: in FAST mode evaluate the Butterworth channel filter's recurrences in
  * float32 instead of float64 (soft symbols then agree with the reference to ~1e-6 of full scale instead
  * of ~1e-13 for that stage; the 1e-4 budget of FAST mode is dominated by the reference's own float32
- * decimator either way).  Default 0. */
+ * decimator either way; the NCO of a lane's 8 samples is then one float64 sincos + a float32 rotation).  Default 0. */
 #define TB200_OPT_CHAN_F32 1
 /* TB200_OPT_PSD_F32 = 2: PSD frames with a float32 FFT and float32 dB conversion (amplitude error ~1e-7 of the
  * frame peak, i.e. far inside the 1e-4-of-full-scale budget; dB values of bins > 100 dB below the frame peak lose
