@@ -399,3 +399,18 @@ def find_peak_near(freqs_mhz, powers, freq_mhz, search_range_hz):
             step = float((x3 - x1) / 2.0) if x3 != x1 else float(x3 - x2)
             return float(x2 + delta * step)
     return float(freqs[pk])
+
+
+def afc_step(freqs_mhz, powers, freq_mhz):
+    """Auto-follow rule of ModernTetraGUI.on_spectrum, ui/modern.py:5223-5257."""
+    freqs = np.asarray(freqs_mhz)
+    powers = np.asarray(powers)
+    mask = np.abs(freqs - freq_mhz) < 0.010
+    if not np.any(mask):
+        return freq_mhz
+    win = np.where(mask)[0]
+    pk = win[np.argmax(powers[win])]
+    offset = freqs[pk] - freq_mhz
+    if powers[pk] > -60 and abs(offset) > 0.00005:
+        return freq_mhz + (offset * 0.1)
+    return freq_mhz

@@ -90,3 +90,17 @@ def voice_cases():
     pos = [0, 1, 2, 3, 300, 510, 1019, 2255, 2256, 2258, 2259, 3020, 5000]
     bits = [rng.integers(0, 2, m, dtype=np.uint8) for m in (510, 432, 431, 600, 0, 510)]
     return dibits, pos, bits
+
+
+def afc_cases(n=40, seed=12):
+    """(freqs_mhz, powers_db, tuned_mhz) triples for the auto-follow rule (ui/modern.py:5223-5257)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for case in range(n):
+        fc = 390.0 + rng.uniform(-1, 1)
+        freqs = fc + (np.arange(2048) - 1024) * (2.4 / 2048)
+        powers = rng.uniform(-110, -70, 2048)
+        if case % 4:
+            powers[1024 + int(rng.integers(-12, 12))] = rng.uniform(-65, -20)
+        out.append((freqs, powers, fc + rng.uniform(-0.004, 0.004)))
+    return out

@@ -26,7 +26,7 @@ logging.disable(logging.CRITICAL)
 
 from oracle import ref_bridge  # noqa: E402
 from tetraear_b200 import synth  # noqa: E402
-from tests.golden.cases import process_cases, psd_chunks, burst_batch, scanner_cases, voice_cases  # noqa: E402
+from tests.golden.cases import process_cases, psd_chunks, burst_batch, scanner_cases, voice_cases, afc_cases  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SP, TD, TP = ref_bridge.load()
@@ -220,6 +220,19 @@ def gen_voice():
     save("voice.npz", in_sha=np.array(sha(dibits)), blocks=blocks, valid=valid)
 
 
+def gen_afc():
+    """Auto-follow rule: lines 5227-5251 of ui/modern.py exec'd from the source text."""
+    modern = os.path.join(ref_bridge.REFERENCE_ROOT, "tetraear", "ui", "modern.py")
+    src = _lines(modern, 5227, 5251)
+    assert src.startswith("center_idx = np.abs(freqs - freq_mhz).argmin()") and "new_freq" in src
+    out = []
+    for freqs, powers, tuned in afc_cases():
+        ns = {"np": np, "freqs": freqs, "powers": powers, "freq_mhz": tuned}
+        exec(src, ns)
+        out.append(ns.get("new_freq", tuned))
+    save("afc.npz", new_freq=np.array(out, dtype=np.float64))
+
+
 if __name__ == "__main__":
     proc = gen_process()
     gen_decode(proc)
@@ -227,3 +240,4 @@ if __name__ == "__main__":
     gen_psd()
     gen_scanner()
     gen_voice()
+    gen_afc()

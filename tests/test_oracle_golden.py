@@ -144,3 +144,17 @@ def test_voice_blocks_match_reference():
             assert b[0] == 0x6B21 and np.count_nonzero(b) == 433 and set(np.unique(b[1:115])) <= {-127, 127}
             p = ov.from_params(r)
             assert p[0] == 0x6B21 and -500 <= p[1] <= 500 and 20 <= p[2] <= 220 and 0 <= p[3] <= 150
+
+
+def test_afc_rule_matches_reference():
+    import os
+    from tests.conftest import GOLDEN
+    from tests.golden.cases import afc_cases
+    from tetraear_b200.signal import afc_step
+    want = np.load(os.path.join(GOLDEN, "afc.npz"))["new_freq"]
+    moved = 0
+    for (freqs, powers, tuned), w in zip(afc_cases(), want):
+        assert oracle.afc_step(freqs, powers, tuned) == w
+        assert afc_step(freqs, powers, tuned) == w          # host helper (scalar GUI logic, no device work)
+        moved += w != tuned
+    assert 5 < moved < len(want)

@@ -96,3 +96,30 @@ def test_scanner_heuristics_live(ref):
         got = osc.analyze_signal(x, 2.4e6)
         for k in want:
             assert got[k] == want[k], (case, k, got[k], want[k])
+
+
+def test_afc_rule_live(ref):
+    """oracle.afc_step and the shipped host helper against the reference's own lines (ui/modern.py:5227-5251,
+    exec'd from the source text: the module needs PyQt6 and cannot be imported)."""
+    import os, textwrap
+    from tetraear_b200.signal import afc_step
+    path = os.path.join(ref_bridge.REFERENCE_ROOT, "tetraear", "ui", "modern.py")
+    with open(path) as f:
+        src = textwrap.dedent("".join(f.readlines()[5226:5251]))
+    assert src.startswith("center_idx = np.abs(freqs - freq_mhz).argmin()") and "new_freq" in src
+    rng = np.random.default_rng(12)
+    fired = 0
+    for case in range(40):
+        fc = 390.0 + rng.uniform(-1, 1)
+        freqs = fc + (np.arange(2048) - 1024) * (2.4 / 2048)
+        powers = rng.uniform(-110, -70, 2048)
+        if case % 4:
+            powers[1024 + int(rng.integers(-12, 12))] = rng.uniform(-65, -20)
+        tuned = fc + rng.uniform(-0.004, 0.004)
+        ns = {"np": np, "freqs": freqs, "powers": powers, "freq_mhz": tuned}
+        exec(src, ns)
+        want = ns.get("new_freq", tuned)
+        fired += "new_freq" in ns
+        assert oracle.afc_step(freqs, powers, tuned) == want, case
+        assert afc_step(freqs, powers, tuned) == want, case
+    assert 5 < fired < 40

@@ -132,3 +132,19 @@ def find_peak_near(freqs_mhz, powers, freq_mhz, search_range_hz):
             step = float((x3 - x1) / 2.0) if x3 != x1 else float(x3 - x2)
             return float(x2 + delta * step)
     return float(freqs[pk])
+
+
+def afc_step(freqs_mhz, powers, freq_mhz, window_mhz=0.010, min_power_db=-60.0, min_offset_mhz=0.00005, gain=0.1):
+    """The GUI's auto-follow rule (ModernTetraGUI.on_spectrum, modern.py:5223-5257): strongest bin within
+    +-10 kHz of the tuned frequency; if it is above -60 dB and more than 50 Hz away, move 10 % of the way.
+    Returns the new tuned frequency in MHz (unchanged when the rule does not fire).  Scalar host logic."""
+    freqs = np.asarray(freqs_mhz)
+    powers = np.asarray(powers)
+    idx = np.nonzero(np.abs(freqs - freq_mhz) < window_mhz)[0]
+    if len(idx) == 0:
+        return freq_mhz
+    pk = idx[np.argmax(powers[idx])]
+    offset = freqs[pk] - freq_mhz
+    if powers[pk] > min_power_db and abs(offset) > min_offset_mhz:
+        return freq_mhz + (offset * gain)
+    return freq_mhz
