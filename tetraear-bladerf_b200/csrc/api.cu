@@ -403,13 +403,20 @@ extern "C" int tb200_filter(tb200_handle h, const void *d_x, int dtype, int n, d
 {
     if (!h || !d_x || !d_out_c128) return fail(TB200_E_ARG, "tb200_filter: bad argument");
     if (n <= 15) return fail(TB200_E_ARG, "The length of the input vector x must be greater than padlen, which is 15.");
-    if ((size_t)2 * (n + 30) * sizeof(double) > h->chan_bytes) return fail(TB200_E_ARG, "tb200_filter: n exceeds the handle capacity");
-    if (h->cfg.mode == TB200_MODE_FAST)
+    if (h->cfg.mode == TB200_MODE_FAST)          // time-parallel form: no scratch
         return launch_channel_fast(h, d_x, dtype, 1, n, n, nullptr, fs, bandwidth, (double *)d_out_c128, n, nullptr, nullptr,
                                    0, 1, (cudaStream_t)stream);
+    // forward-pass scratch [time][lane]: the channel-filter workspace is sized for the DECIMATED chunk; a full-rate
+    // input (filter_signal called directly at the capture rate) borrows the decimator's forward scratch, idle here
+    const size_t need = (size_t)2 * (n + 30) * sizeof(double);
+    double *scratch = h->chan_fwd;
+    if (need > h->chan_bytes) {
+        if (need > h->fwd_bytes) return fail(TB200_E_ARG, "tb200_filter: n exceeds the handle capacity");
+        scratch = (double *)h->fwd;
+    }
     int rc = get_chan(h, bandwidth, fs);
     if (rc) return rc;
-    return launch_channel_exact(h, d_x, dtype, 1, n, n, nullptr, fs, h->chan, 1, h->chan_fwd, (double *)d_out_c128, n,
+    return launch_channel_exact(h, d_x, dtype, 1, n, n, nullptr, fs, h->chan, 1, scratch, (double *)d_out_c128, n,
                                 (cudaStream_t)stream);
 }
 
