@@ -104,3 +104,34 @@ def afc_cases(n=40, seed=12):
             powers[1024 + int(rng.integers(-12, 12))] = rng.uniform(-65, -20)
         out.append((freqs, powers, fc + rng.uniform(-0.004, 0.004)))
     return out
+
+
+def stage_edge_cases():
+    """Stage-level calls with awkward shapes / rates / dtypes: (method, kwargs, input).  Shared by the live
+    oracle-vs-reference check (CPU, build container) and the CUDA-vs-oracle check (GPU box)."""
+    rng = np.random.default_rng(77)
+
+    def c(n, dtype=np.complex128, scale=1.0):
+        return (scale * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(dtype)
+
+    cases = []
+    for n in (16, 17, 31, 100, 4999, 70001):
+        for fs in (240000.0, 1.0e6, 2.4e6):
+            cases.append(("filter_signal", {"bandwidth": 25000, "sample_rate": fs}, c(n)))
+    cases.append(("filter_signal", {"bandwidth": 50000, "sample_rate": 240000.0}, c(3000, np.complex64)))
+    cases.append(("filter_signal", {"bandwidth": 1.0, "sample_rate": 2.4e6}, c(2000)))             # cutoff clipped to 0.01
+    cases.append(("filter_signal", {"bandwidth": 1e9, "sample_rate": 2.4e6}, c(2000)))             # cutoff clipped to 0.99
+    cases.append(("filter_signal", {"bandwidth": 25000, "sample_rate": 240000.0}, c(15)))          # too short: returned as is
+    for n, f, fs in ((1, 100.0, 2.4e6), (1000, -12345.678, 2.4e6), (70001, 0.5, 240000.0), (257, 1e6, 20e6)):
+        cases.append(("frequency_shift", {"freq_offset": f, "sample_rate": fs}, c(n)))
+    cases.append(("frequency_shift", {"freq_offset": 1000.0, "sample_rate": 2.4e6}, c(500, np.complex64)))
+    cases.append(("frequency_shift", {"freq_offset": 1000.0, "sample_rate": 2.4e6}, rng.standard_normal(300)))   # real input
+    for n, fs in ((13, 240000.0), (14, 240000.0), (1000, 240000.0), (1000, 18000.0), (1000, 9000.0), (50, 2.4e6),
+                  (5000, 300000.0), (40000, 2.4e6)):
+        cases.append(("extract_symbols", {"sample_rate": fs}, c(n)))
+    for n in (2, 3, 1000):
+        cases.append(("demodulate_dqpsk", {}, c(n)))
+    cases.append(("demodulate_dqpsk", {}, np.zeros(10, complex)))
+    cases.append(("demodulate_dqpsk", {}, c(500, np.complex64, 1e-6)))
+    cases.append(("demodulate_dqpsk", {}, np.exp(1j * np.pi / 8 * np.arange(64) * 3)))              # steps exactly on 3 pi / 8
+    return cases

@@ -222,3 +222,36 @@ def test_decoding_and_statistics_scenarios(api):
     assert p.get_statistics()["total_bursts"] == 4
     p.fragment_buffer = bytearray(b"Hello " + b"World")
     assert len(p.fragment_buffer) == 11
+
+
+# ------------------------------------------------------------------------------------ awkward stage-level inputs
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_stage_edge_cases(api, mode):
+    """Shapes / rates / dtypes off the beaten path (tests/golden/cases.py::stage_edge_cases); the oracle is pinned to
+    the live reference on the same list by tests/test_oracle_vs_reference.py::test_stage_edge_cases_live."""
+    from tests.golden.cases import stage_edge_cases
+    sp = api[0].SignalProcessor(2.4e6, mode=mode)
+    for i, (method, kw, x) in enumerate(stage_edge_cases()):
+        fs = kw.get("sample_rate", 2.4e6)
+        got = getattr(sp, method)(x, **kw)
+        if method == "filter_signal":
+            want = oracle.filter_signal(x, kw["bandwidth"], fs)
+        elif method == "frequency_shift":
+            want = oracle.frequency_shift(x, kw["freq_offset"], fs)
+        elif method == "extract_symbols":
+            want = oracle.extract_symbols(x, fs)[0]
+        else:
+            want = oracle.demodulate_dqpsk(x)
+        assert len(got) == len(want), (i, method, kw, len(got), len(want))
+        if not len(want):
+            continue
+        if method == "demodulate_dqpsk":
+            bad = np.nonzero(np.asarray(got) != np.asarray(want))[0]
+            # identical except where a phase step sits on a slicer boundary to the last ulp (the crafted 3 pi / 8 case)
+            xs = np.asarray(x, dtype=np.complex128)
+            for k in bad:
+                ph = np.angle(xs[k + 1] * np.conj(xs[k]))
+                assert np.min(np.abs(np.abs(ph) - np.array([3, 5]) * np.pi / 8)) < 1e-9, (i, k)
+        else:
+            tol = 1e-9 if (mode == "exact" or method != "filter_signal") else 1e-9
+            assert np.abs(np.asarray(got) - np.asarray(want)).max() <= tol * max(1.0, np.abs(want).max()), (i, method, kw)

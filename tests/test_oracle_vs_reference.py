@@ -123,3 +123,29 @@ def test_afc_rule_live(ref):
         assert oracle.afc_step(freqs, powers, tuned) == want, case
         assert afc_step(freqs, powers, tuned) == want, case
     assert 5 < fired < 40
+
+
+def _oracle_stage(method, kw, x):
+    """The oracle's counterpart of a SignalProcessor stage call (reference defaults: sample_rate 2.4e6)."""
+    fs = kw.get("sample_rate", 2.4e6)
+    if method == "filter_signal":
+        return oracle.filter_signal(x, kw["bandwidth"], fs)
+    if method == "frequency_shift":
+        return oracle.frequency_shift(x, kw["freq_offset"], fs)
+    if method == "extract_symbols":
+        return oracle.extract_symbols(x, fs)[0]
+    return oracle.demodulate_dqpsk(x)
+
+
+def test_stage_edge_cases_live(ref):
+    """Pins the oracle on the awkward stage-level inputs the GPU test (tests/test_gpu_dropin_api.py) relies on."""
+    from tests.golden.cases import stage_edge_cases
+    SP = ref[0]
+    for i, (method, kw, x) in enumerate(stage_edge_cases()):
+        want = getattr(SP(2.4e6), method)(x, **kw)
+        got = _oracle_stage(method, kw, x)
+        assert len(got) == len(want), (i, method, kw)
+        if method == "demodulate_dqpsk":
+            assert np.array_equal(got, want), (i, method)
+        elif len(want):
+            assert np.abs(np.asarray(got) - np.asarray(want)).max() <= 1e-12 * max(1.0, np.abs(want).max()), (i, method, kw)

@@ -322,7 +322,7 @@ extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, 
     int ph_tiles = 0;
     {
         StageTimer tm(h, TB_STAGE_CHAN, st);
-        if (h->cfg.mode == TB200_MODE_FAST && P.filtered) {
+        if (h->cfg.mode == TB200_MODE_FAST && P.filtered && chan_fast_supported(25000.0, P.rate)) {
             int tiles = chan_fast_tiles(h, (P.q > 1) ? cur_dtype : dtype, P.n_dec);
             if (P.sps > 1 && P.sps <= TB200_MAX_PHASES &&
                 (size_t)n_chunks * (tiles + 1) * TB200_MAX_PHASES * sizeof(double) <= h->phase_bytes) {
@@ -403,7 +403,7 @@ extern "C" int tb200_filter(tb200_handle h, const void *d_x, int dtype, int n, d
 {
     if (!h || !d_x || !d_out_c128) return fail(TB200_E_ARG, "tb200_filter: bad argument");
     if (n <= 15) return fail(TB200_E_ARG, "The length of the input vector x must be greater than padlen, which is 15.");
-    if (h->cfg.mode == TB200_MODE_FAST)          // time-parallel form: no scratch
+    if (h->cfg.mode == TB200_MODE_FAST && chan_fast_supported(bandwidth, fs))          // time-parallel form: no scratch
         return launch_channel_fast(h, d_x, dtype, 1, n, n, nullptr, fs, bandwidth, (double *)d_out_c128, n, nullptr, nullptr,
                                    0, 1, (cudaStream_t)stream);
     // forward-pass scratch [time][lane]: the channel-filter workspace is sized for the DECIMATED chunk; a full-rate

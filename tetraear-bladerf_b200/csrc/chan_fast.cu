@@ -10,6 +10,7 @@
 // Each lane owns R = 8 consecutive samples, runs both one-pole recurrences from a zero state,
 // warp Kogge-Stone scans give the in-pass carries and the neighbour warp's end state the
 // cross-pass carry (|p|max^256 < 1e-15).  All float64: agrees with scipy to ~1e-13.
+#include <algorithm>
 #include <complex>
 #include <mutex>
 #include <vector>
@@ -674,6 +675,19 @@ static int launch_t(tb200_handle h, const void *x, int n_chunks, long n, long in
     TB_LAUNCH_CHECK(h);
     (void)phase_tail;
     return TB200_OK;
+}
+
+// The time-parallel form assumes that a pass forgets its past within one halo pass of CF_P samples.  That holds
+// for the rates process() runs the channel filter at (240..480 kHz: |p|^256 < 1e-7), not for a 25 kHz filter
+// applied directly at a multi-MHz rate (filter_signal as a stand-alone call): those go to the exact kernel.
+bool chan_fast_supported(double bandwidth, double fs)
+{
+    std::complex<double> pz[4];
+    double k;
+    if (channel_filter_poles(bandwidth, fs, pz, &k)) return false;
+    double r = 0.0;
+    for (int i = 0; i < 4; ++i) r = std::max(r, std::abs(pz[i]));
+    return std::pow(r, (double)CF_P) <= 1e-7;
 }
 
 int launch_channel_fast(tb200_handle h, const void *x, int dtype, int n_chunks, long n, long in_stride,

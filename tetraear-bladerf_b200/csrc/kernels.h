@@ -49,6 +49,7 @@ int launch_sc16_to_c64(tb200_handle h, const void *in, long n, void *out, cudaSt
 int launch_resample(tb200_handle h, const void *x, int dtype, long n, long num, void *y, double *scratch, size_t scratch_bytes,
                     cudaStream_t st);
 int launch_freq_shift(tb200_handle h, const void *x, int dtype, long n, double f, double fs, double *out, cudaStream_t st);
+bool chan_fast_supported(double bandwidth, double fs);
 int launch_detect(tb200_handle h, const void *x, int dtype, int n_dwells, long n, long stride, double fs, int num_windows,
                   tb200_detect_stats *out, void *scratch, size_t scratch_bytes, cudaStream_t st);
 int launch_voice_blocks(tb200_handle h, int mode, const void *src, long src_stride, const int32_t *n_src,
