@@ -135,3 +135,26 @@ def stage_edge_cases():
     cases.append(("demodulate_dqpsk", {}, c(500, np.complex64, 1e-6)))
     cases.append(("demodulate_dqpsk", {}, np.exp(1j * np.pi / 8 * np.arange(64) * 3)))              # steps exactly on 3 pi / 8
     return cases
+
+
+def process_edge_cases():
+    """process(samples, freq_offset) at unusual sample rates / lengths / dtypes: (fs, freq_offset, iq)."""
+    out = []
+    rates = [480001.0, 719999.0, 0.96e6, 1.2e6, 1.92e6, 2.16e6, 3.0e6, 200000.0, 100000.0, 30000.0, 15000.0, 2.4e6]
+    for i, fs in enumerate(rates):
+        sps = max(2, int(round(fs / 18000.0)))
+        n = [9000, 20011, 33333][i % 3] if fs >= 100000.0 else 4000
+        iq = synth.make_capture(n, sps, seed=700 + i, sigma=0.03)
+        f = [0.0, 321.0, -1500.5][i % 3]
+        if f:
+            iq = (iq * np.exp(2j * np.pi * f * np.arange(n) / fs)).astype(np.complex64)
+        out.append((fs, f, iq))
+    cap = synth.make_capture(30000, 130, seed=777, sigma=0.03)
+    out.append((2.4e6, 0.0, cap[:27]))
+    out.append((2.4e6, 0.0, cap[:28]))
+    out.append((2.4e6, 100.0, cap[:29]))
+    out.append((2.4e6, 0.0, cap[:159]))           # 16 decimated samples: the shortest input the channel filter accepts
+    out.append((2.4e6, 0.0, cap[:151]))           # 16 -> 15 decimated samples: filter skipped (returns input)
+    out.append((2.4e6, -700.0, cap.astype(np.complex128)))
+    out.append((1.8e6, 0.0, synth.make_capture(25000, 98, seed=778).astype(np.complex128)))
+    return out

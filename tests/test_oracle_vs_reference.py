@@ -149,3 +149,18 @@ def test_stage_edge_cases_live(ref):
             assert np.array_equal(got, want), (i, method)
         elif len(want):
             assert np.abs(np.asarray(got) - np.asarray(want)).max() <= 1e-12 * max(1.0, np.abs(want).max()), (i, method, kw)
+
+
+def test_process_edge_cases_live(ref):
+    """Pins oracle.process on the unusual rates / lengths / dtypes of tests/golden/cases.py::process_edge_cases."""
+    from tests.golden.cases import process_edge_cases
+    SP = ref[0]
+    for i, (fs, f, iq) in enumerate(process_edge_cases()):
+        sp = SP(fs)
+        want = sp.process(iq, f)
+        got, sym, _ = oracle.process(iq, fs, f)
+        assert np.array_equal(got, want), (i, fs, f, len(iq))
+        rs = np.asarray(sp.symbols)
+        assert len(sym) == len(rs), (i, fs)
+        if len(rs):
+            assert np.abs(sym - rs).max() <= 1e-12 * max(1.0, np.abs(rs).max()), (i, fs)
