@@ -280,3 +280,37 @@ def test_process_edge_cases(api, mode):
             for k in bad:                    # only decisions lying on a slicer boundary may differ
                 assert np.min(np.abs(np.abs(ph[k]) - np.array([3, 5]) * np.pi / 8)) < 1e-3, (i, fs, k)
             assert len(bad) <= 0.01 * max(len(want), 1) + 1, (i, fs, len(bad))
+
+
+@pytest.mark.parametrize("mode,chunk_len,n_chunks,lanes", [("exact", 50001, 5, 2), ("fast32", 50001, 5, 2), ("fast", 33000, 7, 3),
+                                                         ("fast32", 131072, 1, 2), ("fast32", 7000, 9, 4)])
+def test_pipeline_odd_geometries(api, mode, chunk_len, n_chunks, lanes):
+    """The batched pipeline with chunk lengths that are not multiples of q, fewer chunks than lanes, short chunks."""
+    from tetraear_b200 import pipeline, synth
+    cap = synth.make_capture(chunk_len * n_chunks, 130, seed=31 + n_chunks, mix=(0.7, 0.15, 0.15)).reshape(n_chunks, chunk_len)
+    pipe = pipeline.ReceivePipeline(2.4e6, chunk_len, max_chunks=n_chunks + 2, mode=mode, n_lanes=lanes)
+    nfr, frames, stats = pipe.run_host(cap)
+    ndib = pipe.n_dibits.cpu().numpy()
+    dib = pipe.dibits.cpu().numpy()
+    tot = [0, 0, 0]
+    for c in range(n_chunks):
+        od, _, _ = oracle.process(cap[c], 2.4e6, 0.0)
+        assert ndib[c] == len(od) and np.array_equal(dib[c, :ndib[c]], od), (mode, c)
+        ofr, ost = oracle.decode(od)
+        kept = [r for r in frames[c, :nfr[c]] if r["kept"]]
+        assert [(int(r["number"]), int(r["type"]), bool(r["crc_ok"])) for r in kept] == \
+               [(f["number"], f["type"], f["burst_crc"]) for f in ofr], (mode, c)
+        for k, key in enumerate(("total_bursts", "crc_pass", "crc_fail")):
+            tot[k] += ost[key]
+    assert list(stats) == tot
+    # device-resident entry point, twice (double-buffered dibit rows), then joined
+    import torch
+    dev = torch.from_numpy(cap.view(np.float32).reshape(n_chunks, chunk_len, 2)).cuda()
+    pipe.stats.zero_()
+    pipe.run_device(dev, join=False)
+    pipe.run_device(dev, join=False)
+    pipe.join()
+    torch.cuda.synchronize()
+    assert list(pipe.stats.cpu().numpy()) == [2 * t for t in tot]
+    assert np.array_equal(pipe.n_dibits.cpu().numpy()[:n_chunks], ndib[:n_chunks])
+    assert np.array_equal(pipe.dibits.cpu().numpy()[:n_chunks], dib[:n_chunks])
