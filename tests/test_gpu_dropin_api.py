@@ -314,3 +314,32 @@ def test_pipeline_odd_geometries(api, mode, chunk_len, n_chunks, lanes):
     assert list(pipe.stats.cpu().numpy()) == [2 * t for t in tot]
     assert np.array_equal(pipe.n_dibits.cpu().numpy()[:n_chunks], ndib[:n_chunks])
     assert np.array_equal(pipe.dibits.cpu().numpy()[:n_chunks], dib[:n_chunks])
+
+
+def test_integration_md_ctypes_binding(api):
+    """The reference-side ctypes stub printed in INTEGRATION.md (section B) is executed as written (only the library
+    path is substituted) and its two functions are compared with the oracle."""
+    import os
+    import re
+    from tests.conftest import ROOT
+    from tetraear_b200 import _lib, synth
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    sec = text[text.index("## B. Bind the C-ABI directly"):]
+    code = re.search(r"```python\n(.*?)```", sec, re.S).group(1)
+    assert 'C.CDLL("libtetra_b200.so")' in code
+    ns = {}
+    exec(code.replace('C.CDLL("libtetra_b200.so")', f'C.CDLL({_lib.LIB_PATH!r})'), ns)
+    iq = synth.make_capture(131072, 130, seed=1234)
+    d = ns["process"](iq)
+    want, _, _ = oracle.process(iq, 2.4e6, 0.0)
+    assert np.array_equal(d, want)                 # FAST mode handle: identical hard decisions on a signal chunk
+    shifted = (iq * np.exp(2j * np.pi * 800.0 * np.arange(len(iq)) / 2.4e6)).astype(np.complex64)
+    assert np.array_equal(ns["process"](shifted, 800.0), oracle.process(shifted, 2.4e6, 800.0)[0])
+    rows = synth.make_burst_batch(32, seed=5)
+    for row in rows:
+        r = ns["parse_burst"](row)
+        o = oracle.parse_bursts(row[None, :])
+        assert r["burst_type"] == int(o["burst_type"][0]) and r["crc_ok"] == bool(o["crc_ok"][0])
+        nd = int(o["n_data"][0])
+        if nd == 216:
+            assert np.array_equal(r["data_bits"][:216], o["data_bits"][0, :216])
