@@ -448,7 +448,7 @@ def other_workloads(device, peak):
     met = torch.empty((nb,), dtype=torch.int32, device=dev)
     ms = timed(lambda: dec.decode_device(soft_d, init, bits, ok, met))
     out["c3_etsi_viterbi_1M"] = {"blocks_per_s": round(nb / ms * 1e3, 0), "ms": round(ms, 4), "crc_pass": int(ok.sum().item()),
-                                 "achieved_gbs": round(nb * (216 + 45) / ms / 1e6, 1), "bound": "issue (shuffle ACS), not HBM"}
+                                 "achieved_gbs": round(nb * (216 + 45) / ms / 1e6, 1), "bound": "integer-ALU issue (one thread per block, 16 register ACS per step), not HBM"}
     del soft_d, bits, ok, met
 
     # ---- c4: 20 MS/s -> 800 x 25 kHz: channelizer + per-channel etsi receiver, 0.2 s of capture

@@ -1,25 +1,28 @@
-import sys, numpy as np, torch
-sys.path.insert(0, '.')  # run from the repo root
-from tetraear_b200 import etsi, _lib, _dev
-from tetraear_b200.replay import ArchiveReplay
-M, n = 800, 4_000_000
-dev = torch.device("cuda:0")
-wide = 0.02 * torch.randn((n, 2), device=dev, dtype=torch.float32)
-rp = ArchiveReplay(M, n)
-bits_s, _, init = etsi.make_etsi_stream(14, seed=3)
-rx = rp.rx
-def t(fn, reps=5):
-    fn(); torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(reps): fn()
-    b.record(); torch.cuda.synchronize()
-    return a.elapsed_time(b) / reps
-print("channelizer ms", t(lambda: rp.chan.run_device(wide, n, rp.rows)))
-h, lib = rx._h, rx._h.lib
-st = _dev.stream_ptr(0)
-print("demod ms", t(lambda: _lib.check(lib.tb200_etsi_demod_batch(h.h, rp.rows.data_ptr(), M, rp.nf, rp.nf, 50000.0, None, rx.soft.data_ptr(), rx.soft_stride, rx.n_soft.data_ptr(), st))))
-print("find ms", t(lambda: _lib.check(lib.tb200_etsi_find_bursts(h.h, rx.soft.data_ptr(), M, rx.soft_stride, rx.n_soft.data_ptr(), 0.8, rx.metric.data_ptr(), rx.blocks.data_ptr(), rx.burst_pos.data_ptr(), rx.n_bursts.data_ptr(), rx.max_bursts, st))))
-nblk = M * rx.max_bursts * 2
-print("decode ms", nblk, t(lambda: _lib.check(lib.tb200_etsi_decode_batch(h.h, rx.blocks.data_ptr(), nblk, 0, init, rx.bits.data_ptr(), rx.crc_ok.data_ptr(), rx.path_metric.data_ptr(), st))))
-print("metric zero ms", t(lambda: rx.metric.zero_()))
+"""Device-resident timing of the ETSI channel decoder (tb200_etsi_decode_batch) per logical channel, 1M blocks."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np, torch
+from tetraear_b200 import etsi
+
+nb, pool = 1_000_000, 4096
+rng = np.random.default_rng(7)
+for ch in ("SCH/HD", "SCH/F", "BSCH"):
+    K1, K2, K3, a = etsi.CHANNELS[ch]
+    init = 3 if ch == "BSCH" else etsi.scrambling_init(262, 42, 17)
+    t1 = rng.integers(0, 2, (pool, K1), dtype=np.uint8)
+    soft = etsi.to_soft(etsi.encode(t1, ch, init), 0.5, rng)
+    d = torch.from_numpy(soft).cuda().repeat(nb // pool + 1, 1)[:nb].contiguous()
+    dec = etsi.ChannelDecoder(ch)
+    bits = torch.empty((nb, 40), dtype=torch.uint8, device="cuda")
+    ok = torch.empty((nb,), dtype=torch.uint8, device="cuda")
+    met = torch.empty((nb,), dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        dec.decode_device(d, init, bits, ok, met)
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(5):
+        dec.decode_device(d, init, bits, ok, met)
+    a1.record(); torch.cuda.synchronize()
+    ms = a0.elapsed_time(a1) / 5
+    print(f"{ch:7s} {ms:.3f} ms per 1M blocks  {nb / ms / 1e3:.0f} M blocks/s  crc_ok {int(ok.sum())}")
