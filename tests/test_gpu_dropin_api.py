@@ -343,3 +343,20 @@ def test_integration_md_ctypes_binding(api):
         nd = int(o["n_data"][0])
         if nd == 216:
             assert np.array_equal(r["data_bits"][:216], o["data_bits"][0, :216])
+
+
+@pytest.mark.parametrize("alpha,n_fft", [(0.15, 512), (0.05, 512), (0.01, 256), (1.0, 256), (0.5, 1024)])
+def test_ema_smoothing_factors(api, alpha, n_fft):
+    """The dB-domain EMA (ui/modern.py:929-935) for smoothing factors other than the GUI's 0.15: the grouped kernel
+    sizes its warm-up from alpha (single exact group when the history would be too long), incl. a second call
+    that continues from the carried state."""
+    rng = np.random.default_rng(4)
+    nfr = 3000
+    x = (0.1 * (rng.standard_normal(nfr * n_fft) + 1j * rng.standard_normal(nfr * n_fft))).astype(np.complex64)
+    an = api[0].SpectrumAnalyzer(2.4e6, n_fft, ema_alpha=alpha)
+    r1 = an.run(x[: 2000 * n_fft], denoise=True)
+    r2 = an.run(x[2000 * n_fft:], denoise=True)
+    power = np.concatenate([r1["power"], r2["power"]]).astype(np.float64)
+    got = np.concatenate([r1["smoothed"], r2["smoothed"]]).astype(np.float64)
+    want = oracle.ema_denoise(power, alpha)
+    assert np.abs(got - want).max() <= 2e-4, (alpha, np.abs(got - want).max())

@@ -7,6 +7,7 @@
 // radix-4 (+ one radix-2 stage when log2 N is odd) decimation-in-time FFT with a twiddle
 // table, then turned into dBFS, fft-shifted, written as float32, and reduced to the 8
 // band statistics the AFC loop reads — all without leaving the SM.
+#include <cmath>
 #include "common.h"
 #include "kernels.h"
 
@@ -309,12 +310,12 @@ psd4096_f32_kernel(const float2 *__restrict__ iq, long frame_stride, long n_fram
 // group re-runs the EMA_W frames before it as warm-up (exact when that reaches frame 0, otherwise the
 // truncated history is below (1-a)^EMA_W of a dB difference: 9e-10 for a = 0.15).  Parallelism:
 // groups x bins threads instead of one thread per bin walking every frame.
-constexpr int EMA_G = 128;
-constexpr int EMA_W = 128;
+// Warm-up length = frames until (1-a)^W < 1e-9 (128 for a = 0.15); groups of 4 W frames read the input 1.25 times.
+// A smoothing factor so small that the warm-up would exceed 4096 frames runs as ONE group (exact, bins-parallel only).
 
 __global__ void psd_ema_kernel(const float *__restrict__ power, long n_frames, int n_fft, double alpha, int first,
                                const double *__restrict__ state_in, double *__restrict__ state_out,
-                               float *__restrict__ smoothed)
+                               float *__restrict__ smoothed, long EMA_G, long EMA_W)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_fft) return;
@@ -392,13 +393,17 @@ int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_
     if (smoothed) {
         // state_in and state_out may alias only when a single group runs; otherwise read a snapshot
         double *state_in = ema_state;
-        long groups = (n_frames + EMA_G - 1) / EMA_G;
+        long warm = 1;
+        if (alpha < 1.0 && alpha > 0.0) warm = (long)std::ceil(-20.72 / std::log1p(-alpha));     // (1-a)^warm < 1e-9
+        long group = 4 * warm;
+        if (!(alpha > 0.0) || warm > 4096 || group >= n_frames) { group = n_frames; warm = 0; }
+        long groups = (n_frames + group - 1) / group;
         if (groups > 1 && !first) {
             state_in = tables + n_fft + 2 * (n_fft / 2 + n_fft / 4 + 1);       // spare n_fft doubles behind the tables
             TB_CUDA(cudaMemcpyAsync(state_in, ema_state, sizeof(double) * n_fft, cudaMemcpyDeviceToDevice, st));
         }
         dim3 grid((n_fft + 127) / 128, (unsigned)groups);
-        psd_ema_kernel<<<grid, 128, 0, st>>>(power, n_frames, n_fft, alpha, first, state_in, ema_state, smoothed);
+        psd_ema_kernel<<<grid, 128, 0, st>>>(power, n_frames, n_fft, alpha, first, state_in, ema_state, smoothed, group, warm);
         TB_LAUNCH_CHECK(h);
     }
     return TB200_OK;
