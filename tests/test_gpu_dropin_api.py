@@ -360,3 +360,27 @@ def test_ema_smoothing_factors(api, alpha, n_fft):
     got = np.concatenate([r1["smoothed"], r2["smoothed"]]).astype(np.float64)
     want = oracle.ema_denoise(power, alpha)
     assert np.abs(got - want).max() <= 2e-4, (alpha, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("fs,n_fft", [(2.4e6, 2048), (1.8e6, 2048), (240000.0, 2048), (50000.0, 1024), (20e6, 4096),
+                                      (30000.0, 256), (2.4e6, 64)])
+def test_spectrum_band_statistics_at_other_rates(api, fs, n_fft):
+    """The band / noise window arithmetic of the spectrum block (ui/modern.py:1956-2010) away from 2.4 MS/s:
+    band wider than the FFT, no noise bins left (noise floor -100), band of zero bins."""
+    rng = np.random.default_rng(int(fs) % 1000 + n_fft)
+    n = n_fft * 3
+    x = (0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    x += (0.4 * np.exp(2j * np.pi * (fs / n_fft * 3.3) * np.arange(n) / fs)).astype(np.complex64)
+    an = api[0].SpectrumAnalyzer(fs, n_fft)
+    r = an.run(x, denoise=False)
+    for i in range(3):
+        _, want_p = oracle.psd_frame(x[i * n_fft:(i + 1) * n_fft], fs, n_fft)
+        m = want_p > -120
+        assert np.abs(r["power"][i].astype(np.float64) - want_p)[m].max() <= 1e-3
+        o = oracle.band_stats(want_p, fs)
+        st = r["stats"][i]
+        if o is None:                       # zero-width band: the reference block would divide by zero / skip
+            continue
+        assert st["peak_idx"] == o["peak_idx"] and st["signal_present"] == o["signal_present"], (fs, i)
+        for k in ("signal_power", "peak_power", "peak_freq_offset", "noise_floor", "snr", "afc_offset"):
+            assert abs(st[k] - o[k]) <= 2e-3, (fs, i, k, st[k], o[k])

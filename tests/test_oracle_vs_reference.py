@@ -164,3 +164,30 @@ def test_process_edge_cases_live(ref):
         assert len(sym) == len(rs), (i, fs)
         if len(rs):
             assert np.abs(sym - rs).max() <= 1e-12 * max(1.0, np.abs(rs).max()), (i, fs)
+
+
+def test_band_statistics_other_rates_live(ref):
+    """oracle.band_stats against the reference's inline block (ui/modern.py:1953-2010, exec'd from the source text)
+    at sample rates where the 25 kHz band is wider than the FFT or leaves no noise bins."""
+    import os, textwrap, types
+    path = os.path.join(ref_bridge.REFERENCE_ROOT, "tetraear", "ui", "modern.py")
+    with open(path) as f:
+        lines = f.readlines()
+    spec_src = textwrap.dedent("".join(lines[1927:1944]))
+    stat_src = textwrap.dedent("".join(lines[1952:2010]))
+    assert "np.hanning" in spec_src and "is_signal_strong" in stat_src
+    rng = np.random.default_rng(5)
+    for fs in (2.4e6, 1.8e6, 240000.0, 50000.0, 30000.0, 20e6):
+        x = (0.05 * (rng.standard_normal(2048) + 1j * rng.standard_normal(2048))).astype(np.complex64)
+        x += (0.4 * np.exp(2j * np.pi * (fs / 2048 * 3.3) * np.arange(2048) / fs)).astype(np.complex64)
+        ns = {"np": np, "samples": x, "current_time": 0.0,
+              "self": types.SimpleNamespace(sample_rate=fs, frequency=390e6, last_signal_time=0.0)}
+        exec(spec_src, ns)
+        exec(stat_src, ns)
+        _, p = oracle.psd_frame(x, fs, 2048)
+        assert np.array_equal(p, ns["power"])
+        o = oracle.band_stats(p, fs)
+        assert o["peak_idx"] == ns["peak_idx"] and o["signal_present"] == bool(ns["signal_present"]), fs
+        for k, ref_k in (("signal_power", "signal_power"), ("peak_power", "peak_power"), ("noise_floor", "noise_floor"),
+                         ("snr", "snr"), ("peak_freq_offset", "peak_freq_offset")):
+            assert o[k] == float(ns[ref_k]), (fs, k)
