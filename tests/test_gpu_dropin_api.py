@@ -384,3 +384,23 @@ def test_spectrum_band_statistics_at_other_rates(api, fs, n_fft):
         assert st["peak_idx"] == o["peak_idx"] and st["signal_present"] == o["signal_present"], (fs, i)
         for k in ("signal_power", "peak_power", "peak_freq_offset", "noise_floor", "snr", "afc_offset"):
             assert abs(st[k] - o[k]) <= 2e-3, (fs, i, k, st[k], o[k])
+
+
+def test_handles_on_two_devices_in_one_process(api):
+    """Several handles on different GPUs in one process: every entry point runs on its handle's device and leaves the
+    caller's current device alone (skipped on a single-GPU box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from tetraear_b200 import synth
+    iq = synth.make_capture(60000, 130, seed=5)
+    want, _, _ = oracle.process(iq, 2.4e6, 0.0)
+    before = torch.cuda.current_device()
+    for mode in ("exact", "fast32"):
+        sps = [api[0].SignalProcessor(2.4e6, mode=mode, device=d) for d in (0, 1)]
+        for _ in range(2):
+            for sp in sps:
+                assert np.array_equal(sp.process(iq), want)
+                assert torch.cuda.current_device() == before
+    dec = api[1].TetraDecoder(auto_decrypt=False, device=1)
+    assert len(dec.decode(want)) == len(oracle.decode(want)[0])

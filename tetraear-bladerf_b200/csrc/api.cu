@@ -18,6 +18,19 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
+// Entry points run on the handle's device whatever the caller's current device is (several handles on different
+// GPUs may live in one process); the caller's device is restored on exit.
+struct DevGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DevGuard(tb200_handle h)
+    {
+        if (!h) return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != h->cfg.device) switched = cudaSetDevice(h->cfg.device) == cudaSuccess;
+    }
+    ~DevGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 int ensure_crc_tables(int device);
 int launch_decimate_fast(tb200_handle h, const void *x, int n_chunks, long n, long chunk_stride, int q,
                          const DecimDesign &d, void *dec_out, long n_dec, cudaStream_t st);
@@ -143,6 +156,7 @@ using namespace tb200;
 
 extern "C" int tb200_profile_enable(tb200_handle h, int on)
 {
+    DevGuard dev_guard(h);
     if (!h) return fail(TB200_E_ARG, "tb200_profile_enable: null handle");
     if (!h->prof_ev) { h->prof_ev = new std::vector<cudaEvent_t>(); h->prof_stage = new std::vector<int>(); }
     h->profiling = on;
@@ -151,6 +165,7 @@ extern "C" int tb200_profile_enable(tb200_handle h, int on)
 
 extern "C" int tb200_profile_read(tb200_handle h, double ms[TB200_N_STAGES], int64_t calls[TB200_N_STAGES])
 {
+    DevGuard dev_guard(h);
     if (!h || !ms || !calls) return fail(TB200_E_ARG, "tb200_profile_read: bad argument");
     for (int i = 0; i < TB200_N_STAGES; ++i) { ms[i] = 0.0; calls[i] = 0; }
     if (!h->prof_ev) return TB200_OK;
@@ -185,6 +200,7 @@ extern "C" int tb200_create(const tb200_config *cfg, tb200_handle *out)
     int ndev = tb200_device_count();
     if (ndev <= 0) return fail(TB200_E_NODEV, "tb200_create: no CUDA device visible (there is no CPU fallback)");
     if (cfg->device < 0 || cfg->device >= ndev) return fail(TB200_E_ARG, "tb200_create: device %d of %d", cfg->device, ndev);
+    struct Restore { int prev = -1; Restore() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; } ~Restore() { if (prev >= 0) cudaSetDevice(prev); } } restore;
     TB_CUDA(cudaSetDevice(cfg->device));
     tb200_handle h = new (std::nothrow) tb200_handle_s();
     if (!h) return fail(TB200_E_ALLOC, "tb200_create: out of host memory");
@@ -218,7 +234,7 @@ extern "C" int tb200_create(const tb200_config *cfg, tb200_handle *out)
 extern "C" int tb200_destroy(tb200_handle h)
 {
     if (!h) return TB200_OK;
-    cudaSetDevice(h->cfg.device);
+    DevGuard dev_guard(h);
     if (h->ws) cudaFree(h->ws);
     if (h->prof_ev) {
         for (cudaEvent_t e : *h->prof_ev) cudaEventDestroy(e);
@@ -230,6 +246,7 @@ extern "C" int tb200_destroy(tb200_handle h)
 
 extern "C" int tb200_set_sample_rate(tb200_handle h, double sample_rate)
 {
+    DevGuard dev_guard(h);
     if (!h || !(sample_rate > 0)) return fail(TB200_E_ARG, "tb200_set_sample_rate: bad argument");
     tb200_handle_s probe = *h;
     probe.cfg.sample_rate = sample_rate;
@@ -246,6 +263,7 @@ extern "C" int tb200_set_sample_rate(tb200_handle h, double sample_rate)
 
 extern "C" int tb200_set_option(tb200_handle h, int option, int value)
 {
+    DevGuard dev_guard(h);
     if (!h) return fail(TB200_E_ARG, "tb200_set_option: null handle");
     switch (option) {
     case TB200_OPT_CHAN_F32: h->chan_f32 = value ? 1 : 0; return TB200_OK;
@@ -263,6 +281,7 @@ extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, 
                                    void *d_symbols, int out_stride, int32_t *d_n_dibits, int32_t *d_phase,
                                    void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || !d_n_dibits || n_chunks < 0 || chunk_len < 0) return fail(TB200_E_ARG, "tb200_process_batch: bad argument");
     if (dtype != TB200_DTYPE_C64 && dtype != TB200_DTYPE_C128 && dtype != TB200_DTYPE_SC16)
         return fail(TB200_E_ARG, "tb200_process_batch: dtype");
@@ -347,6 +366,7 @@ extern "C" int tb200_process_batch_host(tb200_handle h, const void *h_iq, int dt
                                         const double *h_freq_off, uint8_t *h_dibits, void *h_symbols, int out_stride,
                                         int32_t *h_n_dibits, int32_t *h_phase, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || !h_n_dibits) return fail(TB200_E_ARG, "tb200_process_batch_host: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_chunks <= 0) return TB200_OK;
@@ -379,6 +399,7 @@ extern "C" int tb200_process_batch_host(tb200_handle h, const void *h_iq, int dt
 // ------------------------------------------------------------------------- stage level
 extern "C" int tb200_decimate(tb200_handle h, const void *d_x, int dtype, int n, int q, void *d_out, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || !d_x || !d_out || q < 2) return fail(TB200_E_ARG, "tb200_decimate: bad argument");
     if (n <= 27) return fail(TB200_E_ARG, "The length of the input vector x must be greater than padlen, which is 27.");
     const size_t esz = dtype == TB200_DTYPE_C64 ? 4 : 8;
@@ -394,6 +415,7 @@ extern "C" int tb200_decimate(tb200_handle h, const void *d_x, int dtype, int n,
 extern "C" int tb200_freq_shift(tb200_handle h, const void *d_x, int dtype, int n, double freq_offset, double fs,
                                 void *d_out_c128, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n < 0 || (n && (!d_x || !d_out_c128))) return fail(TB200_E_ARG, "tb200_freq_shift: bad argument");
     return launch_freq_shift(h, d_x, dtype, n, freq_offset, fs, (double *)d_out_c128, (cudaStream_t)stream);
 }
@@ -401,6 +423,7 @@ extern "C" int tb200_freq_shift(tb200_handle h, const void *d_x, int dtype, int 
 extern "C" int tb200_filter(tb200_handle h, const void *d_x, int dtype, int n, double bandwidth, double fs,
                             void *d_out_c128, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || !d_x || !d_out_c128) return fail(TB200_E_ARG, "tb200_filter: bad argument");
     if (n <= 15) return fail(TB200_E_ARG, "The length of the input vector x must be greater than padlen, which is 15.");
     if (h->cfg.mode == TB200_MODE_FAST && chan_fast_supported(bandwidth, fs))          // time-parallel form: no scratch
@@ -422,6 +445,7 @@ extern "C" int tb200_filter(tb200_handle h, const void *d_x, int dtype, int n, d
 
 extern "C" int tb200_resample(tb200_handle h, const void *d_x, int dtype, int n, int num, void *d_out, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n < 0 || num < 0 || (n && num && (!d_x || !d_out))) return fail(TB200_E_ARG, "tb200_resample: bad argument");
     if (dtype != TB200_DTYPE_C64 && dtype != TB200_DTYPE_C128) return fail(TB200_E_ARG, "tb200_resample: dtype");
     // scratch: the decimator workspaces (forward scratch + decimated chunks, carved back to back) are idle here
@@ -433,6 +457,7 @@ extern "C" int tb200_resample(tb200_handle h, const void *d_x, int dtype, int n,
 extern "C" int tb200_extract_symbols(tb200_handle h, const void *d_x_c128, int n, double fs, void *d_out_c128,
                                      int32_t *d_n_out, int32_t *d_phase, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n < 0 || !d_n_out) return fail(TB200_E_ARG, "tb200_extract_symbols: bad argument");
     int sps = (int)(fs / 18000);
     int step = sps / 8 > 1 ? sps / 8 : 1;
@@ -443,6 +468,7 @@ extern "C" int tb200_extract_symbols(tb200_handle h, const void *d_x_c128, int n
 
 extern "C" int tb200_demod_dqpsk(tb200_handle h, const void *d_sym_c128, int n, uint8_t *d_dibits, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n < 0) return fail(TB200_E_ARG, "tb200_demod_dqpsk: bad argument");
     return launch_slicer(h, (const double *)d_sym_c128, n, d_dibits, (cudaStream_t)stream);
 }
@@ -451,6 +477,7 @@ extern "C" int tb200_demod_dqpsk(tb200_handle h, const void *d_sym_c128, int n, 
 extern "C" int tb200_symbols_to_bits(tb200_handle h, const uint8_t *d_symbols, int n, uint8_t *d_bits, uint8_t *d_mapped,
                                      void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n < 0 || (n && (!d_symbols || !d_bits))) return fail(TB200_E_ARG, "tb200_symbols_to_bits: bad argument");
     if (n == 0) return TB200_OK;
     // mapped is written at bits_stride/2 pitch: with one stream the pitch is irrelevant
@@ -460,6 +487,7 @@ extern "C" int tb200_symbols_to_bits(tb200_handle h, const uint8_t *d_symbols, i
 extern "C" int tb200_find_sync(tb200_handle h, const uint8_t *d_bits, int n_bits, double threshold, int32_t *d_pos,
                                int max_pos, int32_t *d_count, int32_t *d_max_match, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n_bits < 0 || !d_count || !d_max_match) return fail(TB200_E_ARG, "tb200_find_sync: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_bits < 22) {                                               // decoder.py:201-204
@@ -477,6 +505,7 @@ extern "C" int tb200_decode_batch(tb200_handle h, const uint8_t *d_dibits, int n
                                   const int32_t *d_n_dibits, tb200_frame *d_frames, int max_frames, int32_t *d_n_frames,
                                   int64_t *d_stats, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n_streams < 0 || stride < 0 || !d_n_dibits || !d_frames || !d_n_frames)
         return fail(TB200_E_ARG, "tb200_decode_batch: bad argument");
     if (n_streams == 0) return TB200_OK;
@@ -507,6 +536,7 @@ extern "C" int tb200_decode_batch(tb200_handle h, const uint8_t *d_dibits, int n
 extern "C" int tb200_burst_batch(tb200_handle h, const uint8_t *d_dibits, int64_t n, uint8_t *d_rec, uint8_t *d_full,
                                  int64_t *d_stats, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n < 0 || (n && (!d_dibits || !d_rec))) return fail(TB200_E_ARG, "tb200_burst_batch: bad argument");
     StageTimer tm(h, TB_STAGE_BURST, (cudaStream_t)stream);
     return launch_burst_batch(h, d_dibits, n, d_rec, d_full, d_stats, (cudaStream_t)stream);
@@ -515,6 +545,7 @@ extern "C" int tb200_burst_batch(tb200_handle h, const uint8_t *d_dibits, int64_
 extern "C" int tb200_burst_batch_host(tb200_handle h, const uint8_t *h_dibits, int64_t n, uint8_t *h_rec, uint8_t *h_full,
                                       int64_t *h_stats, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n < 0 || (n && (!h_dibits || !h_rec))) return fail(TB200_E_ARG, "tb200_burst_batch_host: bad argument");
     if (n > h->cfg.max_bursts) return fail(TB200_E_ARG, "tb200_burst_batch_host: %lld bursts exceed max_bursts %d", (long long)n, h->cfg.max_bursts);
     if (n == 0) return TB200_OK;
@@ -536,6 +567,7 @@ extern "C" int tb200_burst_batch_host(tb200_handle h, const uint8_t *h_dibits, i
 extern "C" int tb200_crc16_rows(tb200_handle h, const uint8_t *d_bits, int n_rows, int n_bits, int row_stride,
                                 uint16_t *d_crc, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n_rows < 0 || n_bits < 0 || !d_crc) return fail(TB200_E_ARG, "tb200_crc16_rows: bad argument");
     return launch_crc16_rows(h, d_bits, n_rows, n_bits, row_stride, d_crc, (cudaStream_t)stream);
 }
@@ -544,6 +576,7 @@ extern "C" int tb200_crc16_rows(tb200_handle h, const uint8_t *d_bits, int n_row
 extern "C" int tb200_detect_batch(tb200_handle h, const void *d_iq, int dtype, int n_dwells, int64_t n, int64_t stride, double fs,
                                   int num_windows, tb200_detect_stats *d_out, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n_dwells < 0 || n < 0 || stride < n || !(fs > 0) || (n_dwells && (!d_iq || !d_out)) ||
         (dtype != TB200_DTYPE_C64 && dtype != TB200_DTYPE_C128))
         return fail(TB200_E_ARG, "tb200_detect_batch: bad argument");
@@ -555,6 +588,7 @@ extern "C" int tb200_voice_blocks(tb200_handle h, int mode, const void *d_src, i
                                   const int32_t *d_frame_stream, const int32_t *d_frame_pos, int64_t n_frames, double scale,
                                   int16_t *d_blocks, uint8_t *d_valid, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n_frames < 0 || mode < TB200_VOICE_SYMBOLS || mode > TB200_VOICE_SOFT || src_stride < 0 ||
         (n_frames && (!d_src || !d_blocks)) || (n_frames && mode == TB200_VOICE_SYMBOLS && !d_frame_pos))
         return fail(TB200_E_ARG, "tb200_voice_blocks: bad argument");
@@ -566,6 +600,7 @@ extern "C" int tb200_voice_blocks(tb200_handle h, int mode, const void *d_src, i
 extern "C" int tb200_etsi_decode_batch(tb200_handle h, const int8_t *d_soft, int64_t n, int channel, uint32_t scramb_init,
                                        uint8_t *d_bits, uint8_t *d_crc_ok, int32_t *d_metric, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n < 0 || (n && (!d_soft || !d_bits || !d_crc_ok || !d_metric)))
         return fail(TB200_E_ARG, "tb200_etsi_decode_batch: bad argument");
     StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
@@ -576,6 +611,7 @@ extern "C" int tb200_etsi_demod_batch(tb200_handle h, const void *d_iq_c64, int 
                                       double fs, void *d_sym_c64, float *d_soft, int64_t soft_stride, int32_t *d_n_soft,
                                       void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n_streams < 0 || n_samples < 0 || !d_iq_c64 || !d_soft || !d_n_soft || soft_stride < 2)
         return fail(TB200_E_ARG, "tb200_etsi_demod_batch: bad argument");
     StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
@@ -587,6 +623,7 @@ extern "C" int tb200_etsi_find_bursts(tb200_handle h, const float *d_soft, int n
                                       const int32_t *d_n_soft, double threshold, float *d_metric, int8_t *d_blocks,
                                       int32_t *d_burst_pos, int32_t *d_n_bursts, int max_bursts, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n_streams < 0 || !d_soft || !d_n_soft || !d_metric || !d_blocks || !d_burst_pos || !d_n_bursts || max_bursts <= 0)
         return fail(TB200_E_ARG, "tb200_etsi_find_bursts: bad argument");
     StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
@@ -598,6 +635,7 @@ extern "C" int tb200_etsi_find_sync_bursts(tb200_handle h, const float *d_soft, 
                                            const int32_t *d_n_soft, double threshold, float *d_metric, int8_t *d_sb1,
                                            int8_t *d_bkn2, int32_t *d_burst_pos, int32_t *d_n_bursts, int max_bursts, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n_streams < 0 || !d_soft || !d_n_soft || !d_metric || !d_sb1 || !d_burst_pos || !d_n_bursts || max_bursts <= 0)
         return fail(TB200_E_ARG, "tb200_etsi_find_sync_bursts: bad argument");
     StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
@@ -608,6 +646,7 @@ extern "C" int tb200_etsi_find_sync_bursts(tb200_handle h, const float *d_soft, 
 extern "C" int tb200_channelize(tb200_handle h, const void *d_iq_c64, int64_t n_samples, int n_channels, void *d_out_c64,
                                 int64_t out_stride, int64_t n_frames, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || !d_iq_c64 || !d_out_c64 || n_samples < 0 || n_channels < 2 || (n_channels & 1) || n_channels > h->cfg.max_channels)
         return fail(TB200_E_ARG, "tb200_channelize: bad argument (n_channels must be even and <= the handle's max_channels)");
     if (n_frames < 0 || n_frames > out_stride) return fail(TB200_E_ARG, "tb200_channelize: n_frames exceeds out_stride");
@@ -621,6 +660,7 @@ extern "C" int tb200_psd_batch(tb200_handle h, const void *d_iq_c64, int64_t n_f
                                double sample_rate, double ema_alpha, int first, float *d_power, float *d_smoothed,
                                double *d_ema_state, double *d_stats, void *stream)
 {
+    DevGuard dev_guard(h);
     if (!h || n_frames < 0 || !d_iq_c64) return fail(TB200_E_ARG, "tb200_psd_batch: bad argument");
     if (n_fft < 16 || (n_fft & (n_fft - 1)) || n_fft > h->cfg.max_fft)
         return fail(TB200_E_ARG, "tb200_psd_batch: n_fft must be a power of two in [16, %d]", h->cfg.max_fft);
@@ -633,6 +673,7 @@ extern "C" int tb200_psd_batch(tb200_handle h, const void *d_iq_c64, int64_t n_f
 // ------------------------------------------------------------------------- debugging aid
 extern "C" int tb200_debug_read(tb200_handle h, int region, void *h_dst, size_t nbytes)
 {
+    DevGuard dev_guard(h);
     if (!h || !h_dst) return fail(TB200_E_ARG, "tb200_debug_read: bad argument");
     const void *src = nullptr;
     size_t cap = 0;

@@ -402,11 +402,12 @@ static int launch_q(tb200_handle h, const void *x, int n_chunks, long n, long ch
 {
     constexpr int ROWS = FD_NP * FD_P + 1;
     const size_t smem = ((size_t)(ROWS * Q + 1) * sizeof(float2) + 15 + 16) & ~(size_t)15;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};          // per device: the attribute belongs to the device's copy of the kernel
+    const int dv = h->cfg.device & 63;
+    if (!attr_set[dv]) {
         cudaError_t e = cudaFuncSetAttribute(decim_fast_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(decim_fast): %s", cudaGetErrorString(e));
-        attr_set = true;
+        attr_set[dv] = true;
     }
     const int per_tile = FD_NS * FD_P;
     const int tiles = (int)((n_dec + per_tile - 1) / per_tile);

@@ -365,7 +365,8 @@ int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_
     bp.freq_step = 1.0 / ((double)n_fft * (1.0 / fs));
     if (use_f32 && n_fft == 4096) {
         const size_t sm4 = sizeof(float2) * (size_t)(P4_BUF + 4096 + 256);
-        static bool attr4 = false;
+        static bool attr4_dev[64] = {false};     // per device
+        bool &attr4 = attr4_dev[h->cfg.device & 63];
         if (!attr4) {
             cudaError_t e = cudaFuncSetAttribute(psd4096_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
             if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(psd4096_f32_kernel): %s", cudaGetErrorString(e));
