@@ -22,7 +22,7 @@ namespace tb200 {
 
 constexpr int CF_R = 8;
 constexpr int CF_P = 32 * CF_R;
-constexpr int CF_W = 8;            // warps per CTA: halo + 6 storing + halo
+constexpr int CF_W = 8;            // warps per CTA: warp 0 = both halo half-passes, warps 1..7 = storing passes
 constexpr int CF_FIX = 320;        // samples that receive the right-edge term (0.88^320 ~ 2e-18)
 
 struct ChanFastParams {
@@ -81,37 +81,68 @@ __device__ __forceinline__ cdd chan_padded(const TI *__restrict__ x, long n, lon
     return cdd{__dsub_rn(__dmul_rn(2.0, e.x), v.x), __dsub_rn(__dmul_rn(2.0, e.y), v.y)};
 }
 
-template <typename TI, typename T>
-__global__ void __launch_bounds__(CF_W * 32)
-chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per_chunk,
-                 const double *__restrict__ freq_off, double fs, ChanFastParams K,
-                 double *__restrict__ filtered, long out_stride, double *__restrict__ phase_partial, int sps, int step)
+constexpr int CG_NS = CF_W - 1;       // storing passes per CTA (warps 1..7); warp 0 runs both halo half-passes
+constexpr int CG_NP = CF_W + 1;       // passes per tile: left halo, CG_NS storing, right halo
+
+// one direction over the lane's CF_R samples (both modes, I and Q): zero-state recurrences, Kogge-Stone scan of the
+// lane aggregates, in-warp carry applied to y; the pass-end state goes to carry[I/Q][mode]
+template <typename T, bool FWD>
+__device__ __forceinline__ void cg_dir(const cx<T> (&xs)[CF_R], T (&yI)[CF_R], T (&yQ)[CF_R], int lane, const ChanFastParams &K,
+                                       cx<T> (*carry)[2], cx<T> *FeI, cx<T> *FeQ, bool edge_lane)
 {
     typedef cx<T> C;
-    __shared__ C carryF[CF_W][2][2];
-    __shared__ C carryB[CF_W][2][2];
-    __shared__ C kappa[2][2];      // [I/Q][mode] right-edge transient amplitudes of this chunk (last tile only)
-    __shared__ double phacc[CF_W][TB200_MAX_PHASES];
-    const int chunk = blockIdx.x / tiles_per_chunk;
-    const int tile = blockIdx.x - chunk * tiles_per_chunk;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const TI *xc = x + (long)chunk * in_stride * 2;
-    const double f = freq_off ? freq_off[chunk] : 0.0;
-    const double W = (f != 0.0) ? __dmul_rn(-6.283185307179586, f) : 0.0;
-    // output index (0-based, un-padded) of this lane's first sample; ext position = 15 + m
-    // tiles are aligned to the END of the chunk (the first may be partial), so the last CF_FIX samples and the
-    // right extension belong to one tile, which also derives and applies the right-edge term
-    const bool last_tile = tile == tiles_per_chunk - 1;
-    const long m0 = n - (long)(tiles_per_chunk - tile) * (CF_W - 2) * CF_P - CF_P + (long)w * CF_P + (long)lane * CF_R;
-    const bool do_F = (w < CF_W - 1) || last_tile, do_B = w > 0, store = w > 0 && w < CF_W - 1;
-    // ext[M-1] is sample m = n + 14: lane 1, r = 6 of the right-halo warp of the last tile
-    const bool edge_lane = last_tile && w == CF_W - 1 && lane == 1;
-    C FeI[2], FeQ[2];
+    const C p0 = cxld<T>(K.p[0]), p1 = cxld<T>(K.p[1]), a0 = cxld<T>(K.a[0]), a1 = cxld<T>(K.a[1]);
+    C sI0 = C{T(0), T(0)}, sQ0 = sI0, sI1 = sI0, sQ1 = sI0;
+#pragma unroll
+    for (int i = 0; i < CF_R; ++i) {
+        const int r = FWD ? i : CF_R - 1 - i;
+        sI0 = cxmul<T>(p0, sI0); sI0.x += xs[r].x;
+        sQ0 = cxmul<T>(p0, sQ0); sQ0.x += xs[r].y;
+        sI1 = cxmul<T>(p1, sI1); sI1.x += xs[r].x;
+        sQ1 = cxmul<T>(p1, sQ1); sQ1.x += xs[r].y;
+        yI[r] += T(2) * (a0.x * sI0.x - a0.y * sI0.y + a1.x * sI1.x - a1.y * sI1.y);
+        yQ[r] += T(2) * (a0.x * sQ0.x - a0.y * sQ0.y + a1.x * sQ1.x - a1.y * sQ1.y);
+        if (FWD && r == 6) { FeI[0] = sI0; FeI[1] = sI1; FeQ[0] = sQ0; FeQ[1] = sQ1; }      // zero-state F at r = 6
+    }
+    C sI[2] = {sI0, sI1}, sQ[2] = {sQ0, sQ1};
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+        for (int st = 0; st < 5; ++st) {
+            C oI = FWD ? cxup<T>(sI[m], 1 << st) : cxdown<T>(sI[m], 1 << st);
+            C oQ = FWD ? cxup<T>(sQ[m], 1 << st) : cxdown<T>(sQ[m], 1 << st);
+            C g = cxld<T>(K.ppow[st][m]);
+            if (FWD ? (lane < (1 << st)) : (lane + (1 << st) >= 32)) g = C{T(0), T(0)};
+            sI[m] = cxfma<T>(g, oI, sI[m]);
+            sQ[m] = cxfma<T>(g, oQ, sQ[m]);
+        }
+        C cI = FWD ? cxup<T>(sI[m], 1) : cxdown<T>(sI[m], 1);
+        C cQ = FWD ? cxup<T>(sQ[m], 1) : cxdown<T>(sQ[m], 1);
+        if (lane == (FWD ? 0 : 31)) cI = cQ = C{T(0), T(0)};
+        if (lane == (FWD ? 31 : 0)) { carry[0][m] = sI[m]; carry[1][m] = sQ[m]; }
+        if (FWD && edge_lane) {                                   // + p^7 * (carry from lane 0 of this warp)
+            C p7 = cxld<T>(K.p[m]);
+            const C pm = p7;
+            for (int i = 0; i < 6; ++i) p7 = cxmul<T>(p7, pm);
+            FeI[m] = cxfma<T>(p7, cI, FeI[m]);
+            FeQ[m] = cxfma<T>(p7, cQ, FeQ[m]);
+        }
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) {
+            const C af = FWD ? cxld<T>(K.aF[r][m]) : cxld<T>(K.aB[r][m]);
+            yI[r] += T(2) * (af.x * cI.x - af.y * cI.y);
+            yQ[r] += T(2) * (af.x * cQ.x - af.y * cQ.y);
+        }
+    }
+}
 
-    C xs[CF_R];
+template <typename TI, typename T>
+__device__ __forceinline__ void cg_load(const TI *__restrict__ xc, long n, long m0, double W, double fs, cx<T> (&xs)[CF_R])
+{
+    typedef cx<T> C;
     if (sizeof(TI) == 4 && W == 0.0 && m0 >= 0 && m0 + CF_R <= n && ((reinterpret_cast<uintptr_t>(xc + 2 * m0) & 15) == 0)) {
-        // interior lane, complex64, no NCO: 8 samples = 64 contiguous bytes = four 16-byte loads
-        const float4 *v4 = reinterpret_cast<const float4 *>(xc + 2 * m0);     // alignment checked above (tiles are end-aligned)
+        // interior lane, complex64, no NCO: 8 samples = 64 contiguous bytes = four 16-byte loads (tiles are end-aligned)
+        const float4 *v4 = reinterpret_cast<const float4 *>(xc + 2 * m0);
 #pragma unroll
         for (int r = 0; r < CF_R / 2; ++r) {
             float4 v = v4[r];
@@ -122,91 +153,60 @@ chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per
 #pragma unroll
         for (int r = 0; r < CF_R; ++r) { cdd v = chan_padded<TI>(xc, n, 15 + m0 + r, W, fs); xs[r] = C{(T)v.x, (T)v.y}; }
     }
+}
+
+template <typename TI, typename T>
+__global__ void __launch_bounds__(CF_W * 32, 2)
+chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per_chunk,
+                 const double *__restrict__ freq_off, double fs, ChanFastParams K,
+                 double *__restrict__ filtered, long out_stride, double *__restrict__ phase_partial, int sps, int step)
+{
+    typedef cx<T> C;
+    __shared__ C carryF[CG_NP][2][2];         // [pass][I/Q][mode]
+    __shared__ C carryB[CG_NP][2][2];
+    __shared__ C kappa[2][2];                 // [I/Q][mode] right-edge transient amplitudes of this chunk (last tile only)
+    __shared__ T pws[CG_NS * CF_P];           // |y|^2 of the tile's storing range, for the timing-phase sums
+    const int chunk = blockIdx.x / tiles_per_chunk;
+    const int tile = blockIdx.x - chunk * tiles_per_chunk;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TI *xc = x + (long)chunk * in_stride * 2;
+    const double f = freq_off ? freq_off[chunk] : 0.0;
+    const double W = (f != 0.0) ? __dmul_rn(-6.283185307179586, f) : 0.0;
+    // tiles are aligned to the END of the chunk (the first may be partial), so the last CF_FIX samples and the right
+    // extension belong to one tile, which also derives and applies the right-edge term.  Warp 0 runs the two halo
+    // half-passes (causal over pass 0, anti-causal over pass CG_NP-1), warps 1..7 one storing pass each.
+    const bool last_tile = tile == tiles_per_chunk - 1;
+    const long mt0 = n - (long)(tiles_per_chunk - tile) * CG_NS * CF_P;          // first sample of the storing range
+    const bool store = w > 0;
+    const int passB = store ? w : CG_NP - 1;
+    const long m0 = mt0 - CF_P + (long)w * CF_P + (long)lane * CF_R;
+    const long m0B = mt0 - CF_P + (long)passB * CF_P + (long)lane * CF_R;
+    // ext[M-1] is sample m = n + 14: lane 1, r = 6 of the right-halo pass of the last tile (run by warp 0)
+    const bool edge_lane = last_tile && w == 0 && lane == 1;
+    C FeI[2], FeQ[2];
+
+    C xs[CF_R];
+    cg_load<TI, T>(xc, n, m0, W, fs, xs);
     T yI[CF_R], yQ[CF_R];
     const T c0p = (T)K.c0p;
 #pragma unroll
     for (int r = 0; r < CF_R; ++r) { yI[r] = c0p * xs[r].x; yQ[r] = c0p * xs[r].y; }
-
-    // both modes and both components advance together: four independent recurrences per direction
-    const C p0 = cxld<T>(K.p[0]), p1 = cxld<T>(K.p[1]), a0 = cxld<T>(K.a[0]), a1 = cxld<T>(K.a[1]);
-    if (do_F) {
-        C sI0 = C{T(0), T(0)}, sQ0 = sI0, sI1 = sI0, sQ1 = sI0;
-#pragma unroll
-        for (int r = 0; r < CF_R; ++r) {
-            sI0 = cxmul<T>(p0, sI0); sI0.x += xs[r].x;
-            sQ0 = cxmul<T>(p0, sQ0); sQ0.x += xs[r].y;
-            sI1 = cxmul<T>(p1, sI1); sI1.x += xs[r].x;
-            sQ1 = cxmul<T>(p1, sQ1); sQ1.x += xs[r].y;
-            yI[r] += T(2) * (a0.x * sI0.x - a0.y * sI0.y + a1.x * sI1.x - a1.y * sI1.y);
-            yQ[r] += T(2) * (a0.x * sQ0.x - a0.y * sQ0.y + a1.x * sQ1.x - a1.y * sQ1.y);
-            if (r == 6) { FeI[0] = sI0; FeI[1] = sI1; FeQ[0] = sQ0; FeQ[1] = sQ1; }      // zero-state F at r = 6
-        }
-        C sI[2] = {sI0, sI1}, sQ[2] = {sQ0, sQ1};
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-#pragma unroll
-            for (int s = 0; s < 5; ++s) {
-                C oI = cxup<T>(sI[m], 1 << s), oQ = cxup<T>(sQ[m], 1 << s);
-                if (lane >= (1 << s)) { C g = cxld<T>(K.ppow[s][m]); sI[m] = cxfma<T>(g, oI, sI[m]); sQ[m] = cxfma<T>(g, oQ, sQ[m]); }
-            }
-            C cI = cxup<T>(sI[m], 1), cQ = cxup<T>(sQ[m], 1);
-            if (lane == 0) cI = cQ = C{T(0), T(0)};
-            if (lane == 31) { carryF[w][0][m] = sI[m]; carryF[w][1][m] = sQ[m]; }
-            if (edge_lane) {                                   // + p^7 * (carry from lane 0 of this warp)
-                C p7 = cxld<T>(K.p[m]);
-                const C pm = p7;
-                for (int i = 0; i < 6; ++i) p7 = cxmul<T>(p7, pm);
-                FeI[m] = cxfma<T>(p7, cI, FeI[m]);
-                FeQ[m] = cxfma<T>(p7, cQ, FeQ[m]);
-            }
-#pragma unroll
-            for (int r = 0; r < CF_R; ++r) {
-                const C af = cxld<T>(K.aF[r][m]);
-                yI[r] += T(2) * (af.x * cI.x - af.y * cI.y);
-                yQ[r] += T(2) * (af.x * cQ.x - af.y * cQ.y);
-            }
-        }
+    cg_dir<T, true>(xs, yI, yQ, lane, K, carryF[w], FeI, FeQ, false);
+    if (!store) {
+        cg_load<TI, T>(xc, n, m0B, W, fs, xs);
+        if (last_tile) cg_dir<T, true>(xs, yI, yQ, lane, K, carryF[CG_NP - 1], FeI, FeQ, edge_lane);   // F[M-1] lives in the right halo
     }
-    if (do_B) {
-        C sI0 = C{T(0), T(0)}, sQ0 = sI0, sI1 = sI0, sQ1 = sI0;
-#pragma unroll
-        for (int r = CF_R - 1; r >= 0; --r) {
-            sI0 = cxmul<T>(p0, sI0); sI0.x += xs[r].x;
-            sQ0 = cxmul<T>(p0, sQ0); sQ0.x += xs[r].y;
-            sI1 = cxmul<T>(p1, sI1); sI1.x += xs[r].x;
-            sQ1 = cxmul<T>(p1, sQ1); sQ1.x += xs[r].y;
-            yI[r] += T(2) * (a0.x * sI0.x - a0.y * sI0.y + a1.x * sI1.x - a1.y * sI1.y);
-            yQ[r] += T(2) * (a0.x * sQ0.x - a0.y * sQ0.y + a1.x * sQ1.x - a1.y * sQ1.y);
-        }
-        C sI[2] = {sI0, sI1}, sQ[2] = {sQ0, sQ1};
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-#pragma unroll
-            for (int s = 0; s < 5; ++s) {
-                C oI = cxdown<T>(sI[m], 1 << s), oQ = cxdown<T>(sQ[m], 1 << s);
-                if (lane + (1 << s) < 32) { C g = cxld<T>(K.ppow[s][m]); sI[m] = cxfma<T>(g, oI, sI[m]); sQ[m] = cxfma<T>(g, oQ, sQ[m]); }
-            }
-            C cI = cxdown<T>(sI[m], 1), cQ = cxdown<T>(sQ[m], 1);
-            if (lane == 31) cI = cQ = C{T(0), T(0)};
-            if (lane == 0) { carryB[w][0][m] = sI[m]; carryB[w][1][m] = sQ[m]; }
-#pragma unroll
-            for (int r = 0; r < CF_R; ++r) {
-                const C ab = cxld<T>(K.aB[r][m]);
-                yI[r] += T(2) * (ab.x * cI.x - ab.y * cI.y);
-                yQ[r] += T(2) * (ab.x * cQ.x - ab.y * cQ.y);
-            }
-        }
-    }
+    cg_dir<T, false>(xs, yI, yQ, lane, K, carryB[passB], FeI, FeQ, false);
     __syncthreads();
     if (last_tile) {
         if (edge_lane) {
-            // F_j[M-1] = local + p^15 * (end state of the previous warp);  kappa_i = ka_i x_last + sum_j kM F_j + kMc conj F_j
+            // F_j[M-1] = local + p^15 * (end state of the last storing pass);  kappa_i = ka_i x_last + sum_j kM F_j + kMc conj F_j
             for (int m = 0; m < 2; ++m) {
                 C p15 = cxld<T>(K.p[m]);
                 const C pm = p15;
                 for (int i = 0; i < 14; ++i) p15 = cxmul<T>(p15, pm);
-                FeI[m] = cxfma<T>(p15, carryF[w - 1][0][m], FeI[m]);
-                FeQ[m] = cxfma<T>(p15, carryF[w - 1][1][m], FeQ[m]);
+                FeI[m] = cxfma<T>(p15, carryF[CG_NP - 2][0][m], FeI[m]);
+                FeQ[m] = cxfma<T>(p15, carryF[CG_NP - 2][1][m], FeQ[m]);
             }
             for (int i = 0; i < 2; ++i) {
                 C kI = C{(T)K.ka[i][0] * xs[6].x, (T)K.ka[i][1] * xs[6].x}, kQ = C{(T)K.ka[i][0] * xs[6].y, (T)K.ka[i][1] * xs[6].y};
@@ -223,83 +223,69 @@ chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per
     }
     if (store) {
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
-        C LF = C{T(1), T(0)}, LB = C{T(1), T(0)};
+        for (int m = 0; m < 2; ++m) {
+            C LF = C{T(1), T(0)}, LB = C{T(1), T(0)};
 #pragma unroll
-        for (int s = 0; s < 5; ++s) {
-            C g = cxld<T>(K.ppow[s][m]);
-            if (lane & (1 << s)) LF = cxmul<T>(LF, g);
-            if ((31 - lane) & (1 << s)) LB = cxmul<T>(LB, g);
-        }
-        C gFI = cxmul<T>(LF, carryF[w - 1][0][m]), gFQ = cxmul<T>(LF, carryF[w - 1][1][m]);
-        C gBI = cxmul<T>(LB, carryB[w + 1][0][m]), gBQ = cxmul<T>(LB, carryB[w + 1][1][m]);
-#pragma unroll
-        for (int r = 0; r < CF_R; ++r) {
-            const C af = cxld<T>(K.aF[r][m]), ab = cxld<T>(K.aB[r][m]);
-            yI[r] += T(2) * (af.x * gFI.x - af.y * gFI.y + ab.x * gBI.x - ab.y * gBI.y);
-            yQ[r] += T(2) * (af.x * gFQ.x - af.y * gFQ.y + ab.x * gBQ.x - ab.y * gBQ.y);
-        }
-    }
-    if (last_tile && n - 1 - m0 < CF_FIX + CF_R) {
-        // y[m] -= 2 Re sum_i kappa_i p_i^(16 + mm),  mm = n-1-m   (only the last CF_FIX samples matter)
-#pragma unroll
-        for (int r = 0; r < CF_R; ++r) {
-            const long mm = n - 1 - (m0 + r);
-            if (mm < 0 || mm >= CF_FIX) continue;
-            const int a = (int)(mm / CF_R), b = (int)(mm - (long)a * CF_R);
-            for (int m = 0; m < 2; ++m) {
-                C g = cxld<T>(K.pc[m]);
-                for (int sft = 0; sft < 6; ++sft) if (a & (1 << sft)) g = cxmul<T>(g, cxld<T>(K.ppow[sft][m]));
-                const C pm = cxld<T>(K.p[m]);
-                for (int i = 0; i < b; ++i) g = cxmul<T>(g, pm);
-                yI[r] -= T(2) * (kappa[0][m].x * g.x - kappa[0][m].y * g.y);
-                yQ[r] -= T(2) * (kappa[1][m].x * g.x - kappa[1][m].y * g.y);
+            for (int s = 0; s < 5; ++s) {
+                C g = cxld<T>(K.ppow[s][m]);
+                if (lane & (1 << s)) LF = cxmul<T>(LF, g);
+                if ((31 - lane) & (1 << s)) LB = cxmul<T>(LB, g);
             }
-        }
-    }
-    double2 *out = reinterpret_cast<double2 *>(filtered) + (long)chunk * out_stride;
-#pragma unroll
-    for (int r = 0; r < CF_R; ++r) {
-        long m = m0 + r;
-        if (m >= 0 && m < n) out[m] = make_double2((double)yI[r], (double)yQ[r]);
-    }
-    }
-    // ---- per-phase power partial sums for the timing pick (extract_symbols, processor.py:196-210):
-    // deterministic order — lanes by shuffle tree, warps then tiles in index order.
-    if (phase_partial) {
-        if (store) {
-            // phase class of each owned sample, -1 when it does not count (32-bit arithmetic, once per sample)
-            int phr[CF_R];
-            double pw[CF_R];
-            const int ni = (int)n;
+            C gFI = cxmul<T>(LF, carryF[w - 1][0][m]), gFQ = cxmul<T>(LF, carryF[w - 1][1][m]);
+            C gBI = cxmul<T>(LB, carryB[w + 1][0][m]), gBQ = cxmul<T>(LB, carryB[w + 1][1][m]);
 #pragma unroll
             for (int r = 0; r < CF_R; ++r) {
-                long m = m0 + r;
-                phr[r] = -1;
-                pw[r] = (double)yI[r] * (double)yI[r] + (double)yQ[r] * (double)yQ[r];
-                if (m >= 0 && m < n) {
-                    int mi = (int)m, k = mi / sps, ph = mi - k * sps;
-                    if ((ph % step) == 0 && k < (ni - ph) / sps) phr[r] = ph;
+                const C af = cxld<T>(K.aF[r][m]), ab = cxld<T>(K.aB[r][m]);
+                yI[r] += T(2) * (af.x * gFI.x - af.y * gFI.y + ab.x * gBI.x - ab.y * gBI.y);
+                yQ[r] += T(2) * (af.x * gFQ.x - af.y * gFQ.y + ab.x * gBQ.x - ab.y * gBQ.y);
+            }
+        }
+        if (last_tile && n - 1 - m0 < CF_FIX + CF_R) {
+            // y[m] -= 2 Re sum_i kappa_i p_i^(16 + mm),  mm = n-1-m   (only the last CF_FIX samples matter)
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) {
+                const long mm = n - 1 - (m0 + r);
+                if (mm < 0 || mm >= CF_FIX) continue;
+                const int a = (int)(mm / CF_R), b = (int)(mm - (long)a * CF_R);
+                for (int m = 0; m < 2; ++m) {
+                    C g = cxld<T>(K.pc[m]);
+                    for (int sft = 0; sft < 6; ++sft) if (a & (1 << sft)) g = cxmul<T>(g, cxld<T>(K.ppow[sft][m]));
+                    const C pm = cxld<T>(K.p[m]);
+                    for (int i = 0; i < b; ++i) g = cxmul<T>(g, pm);
+                    yI[r] -= T(2) * (kappa[0][m].x * g.x - kappa[0][m].y * g.y);
+                    yQ[r] -= T(2) * (kappa[1][m].x * g.x - kappa[1][m].y * g.y);
                 }
             }
-            for (int ph = 0; ph < sps; ph += step) {
-                double v = 0.0;
-#pragma unroll
-                for (int r = 0; r < CF_R; ++r) v += (phr[r] == ph) ? pw[r] : 0.0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) phacc[w][ph] = v;
-            }
         }
-        __syncthreads();
-        if (threadIdx.x < sps && (threadIdx.x % step) == 0) {
-            double t = 0.0;
-            for (int ww = 1; ww < CF_W - 1; ++ww) t += phacc[ww][threadIdx.x];
-            phase_partial[((long)chunk * tiles_per_chunk + tile) * TB200_MAX_PHASES + threadIdx.x] = t;
+        double2 *out = reinterpret_cast<double2 *>(filtered) + (long)chunk * out_stride;
+        T *pw = pws + (w - 1) * CF_P + lane * CF_R;
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) {
+            const long m = m0 + r;
+            const bool ok = m >= 0 && m < n;
+            if (ok) out[m] = make_double2((double)yI[r], (double)yQ[r]);
+            if (phase_partial) pw[r] = ok ? yI[r] * yI[r] + yQ[r] * yQ[r] : T(0);
         }
     }
+    // ---- per-phase power partial sums for the timing pick (extract_symbols, processor.py:196-210): 16 threads per
+    // phase walk the tile's |y|^2 in shared memory (fixed order), a 16-lane shuffle tree finishes the sum.
+    if (phase_partial) {
+        __syncthreads();
+        const int grp = threadIdx.x >> 4, seg = threadIdx.x & 15;
+        const int ph = grp * step;
+        double t = 0.0;
+        if (ph < sps) {
+            const long lo = mt0 > 0 ? mt0 : 0, hi = mt0 + (long)CG_NS * CF_P;
+            const long first = lo + ((ph - lo % sps) % sps + sps) % sps;     // first sample of this phase in the tile
+            const long kmax = (n - ph) / sps;                                // symbols of this phase: k < kmax
+            long k = first / sps + seg;
+            for (long m = first + (long)seg * sps; m < hi && k < kmax; m += 16L * sps, k += 16) t += (double)pws[m - mt0];
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (ph < sps && seg == 0) phase_partial[((long)chunk * tiles_per_chunk + tile) * TB200_MAX_PHASES + ph] = t;
+    }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------
 // float32 packed variant (TB200_OPT_CHAN_F32, complex64 input).  Same two-sided modal form; the I and Q components
@@ -321,8 +307,8 @@ struct ChanFast32Params {
     int nstage[2];                 // Kogge-Stone stages that matter for mode i
 };
 
-constexpr int C32_NS = CF_W - 1;      // storing passes per CTA (warps 1..7); warp 0 runs both halo half-passes
-constexpr int C32_NP = CF_W + 1;      // passes per tile: left halo, C32_NS storing, right halo
+constexpr int C32_NS = CG_NS;
+constexpr int C32_NP = CG_NP;
 
 // one direction over the lane's CF_R samples: zero-state recurrences, Kogge-Stone scan of the lane aggregates,
 // in-warp carry applied to y; the pass-end state goes to carry[0..1]
@@ -641,7 +627,8 @@ static bool use_packed32(tb200_handle h, int dtype, long n) { return h->chan_f32
 // tiles per chunk of the kernel launch_channel_fast will pick for (handle options, input dtype, n)
 int chan_fast_tiles(tb200_handle h, int dtype, long n)
 {
-    const int per_tile = (use_packed32(h, dtype, n) ? C32_NS : CF_W - 2) * CF_P;
+    (void)h; (void)dtype;
+    const int per_tile = CG_NS * CF_P;            // both kernels: 7 storing passes per CTA
     return (int)((n + per_tile - 1) / per_tile);
 }
 
