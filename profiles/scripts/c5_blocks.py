@@ -13,7 +13,7 @@ def t(fn, reps=5):
     for _ in range(reps): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
-for nb in (1, 2, 4, 8):
+for nb in (1, 4, 8, 16, 32):
     rp = ArchiveReplay(M, n, n_blocks=nb)
     rp.chan.run_device(wide, n, rp.rows)
     print("blocks", nb, rp.n_blocks, "receive ms", round(t(lambda: rp.receive_rows(rp.nf, init)), 3), "chan ms", round(t(lambda: rp.chan.run_device(wide, n, rp.rows)), 3))

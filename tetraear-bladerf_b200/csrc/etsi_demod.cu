@@ -8,9 +8,9 @@
 // regions and a hard-bit Hamming scan) — parity unpinned; validated end to end by
 // modulator -> demod -> TS search -> channel decoder round trips (tests/test_etsi_phy.py).
 //
-// One warp per stream: the feedback state (timing phase, loop integrator, power estimate) is
-// warp-uniform and register resident; the 32 lanes are the 32 taps of the interpolating matched
-// filter, reduced with shuffles, for the on-time and the half-symbol sample of every symbol.
+// Eight lanes per stream: the feedback state (timing phase, loop integrator, power estimate) is replicated in the
+// group's registers; each lane owns 4 of the 32 taps of the interpolating matched filter (reduced with 3 shuffle
+// stages) for the on-time and the half-symbol sample of every symbol.
 #include <cmath>
 #include "common.h"
 #include "kernels.h"
@@ -20,102 +20,103 @@ namespace tb200 {
 constexpr int ED_TAPS = 32;
 constexpr int ED_PH = 32;
 
-__device__ __forceinline__ float2 warp_sum2(float2 v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o); }
-    return v;
-}
+// Mapping: EIGHT lanes per stream, four streams per warp.  The loop is a chain of dependent steps per symbol
+// (timing phase -> two matched-filter outputs -> Gardner error -> loop filter -> next phase), so what counts is the
+// latency of that chain, not arithmetic: each lane owns 4 of the 32 taps (4 multiply-adds per output in registers,
+// then a 3-stage shuffle reduction instead of 5), the stream's samples sit in a shared-memory ring the group refills
+// 64 samples at a time well ahead of their use, and the tap table is read as one float4 per output.
+constexpr int ED_L = 8;                   // lanes per stream
+constexpr int ED_RING = 256;              // ring capacity per stream (samples)
+constexpr int ED_FILL = 64;               // refill granularity
 
-// Register-resident sliding window of the stream: lane l holds x[base + l] (cur), x[base + 32 + l] (nxt)
-// and the prefetched x[base + 64 + l] (pre); the matched filter reads its 32 taps with shuffles, so the
-// only global loads are coalesced 256-byte prefetches issued a whole window ahead of their use.
-struct Window {
-    float2 cur, nxt, pre;
-    long base;
-    __device__ __forceinline__ float2 ld(const float2 *__restrict__ x, long n, long i) const
-    {
-        return (i >= 0 && i < n) ? x[i] : make_float2(0.f, 0.f);
-    }
-    __device__ __forceinline__ void init(const float2 *__restrict__ x, long n, long b, int lane)
-    {
-        base = b;
-        cur = ld(x, n, b + lane); nxt = ld(x, n, b + 32 + lane); pre = ld(x, n, b + 64 + lane);
-    }
-    // make sure [first, first + 48) lies inside [base, base + 64)
-    __device__ __forceinline__ void advance_to(const float2 *__restrict__ x, long n, long first, int lane)
-    {
-        while (first >= base + 16) {
-            if (first >= base + 32) { cur = nxt; nxt = pre; base += 32; pre = ld(x, n, base + 64 + lane); }
-            else break;
-        }
-    }
-    __device__ __forceinline__ float2 at(long j) const       // j in [base, base + 64), per lane
-    {
-        int rel = (int)(j - base);
-        int src = rel & 31;
-        float cx = __shfl_sync(0xffffffffu, cur.x, src), cy = __shfl_sync(0xffffffffu, cur.y, src);
-        float nx = __shfl_sync(0xffffffffu, nxt.x, src), ny = __shfl_sync(0xffffffffu, nxt.y, src);
-        return (rel & 32) ? make_float2(nx, ny) : make_float2(cx, cy);
-    }
-};
-
-// matched-filter output at continuous sample time tau (window i-15 .. i+16 around i = floor(tau))
-__device__ __forceinline__ float2 mf_at(const Window &wdw, const float *__restrict__ taps, float tau, int lane)
+__global__ void __launch_bounds__(128)
+etsi_demod_kernel(const float2 *__restrict__ iq, int n_streams, long n, long stride, float sps, float kp,
+                  float ki, const float *__restrict__ taps_g, float2 *__restrict__ sym_out,
+                  float *__restrict__ soft_out, long soft_stride, int32_t *__restrict__ n_soft)
 {
-    float fl = floorf(tau);
-    long i = (long)fl;
-    int ph = (int)((tau - fl) * ED_PH);
-    ph = ph < 0 ? 0 : (ph >= ED_PH ? ED_PH - 1 : ph);
-    float2 v = wdw.at(i + lane - 15);
-    float g = taps[ph * ED_TAPS + lane];
-    return warp_sum2(make_float2(v.x * g, v.y * g));
-}
-
-__global__ void etsi_demod_kernel(const float2 *__restrict__ iq, int n_streams, long n, long stride, float sps, float kp,
-                                  float ki, const float *__restrict__ taps_g, float2 *__restrict__ sym_out,
-                                  float *__restrict__ soft_out, long soft_stride, int32_t *__restrict__ n_soft)
-{
-    __shared__ float taps[ED_PH * ED_TAPS];
+    __shared__ __align__(16) float taps[ED_PH * ED_TAPS];
+    __shared__ float2 ring[16][ED_RING];                       // 16 streams per CTA
     for (int i = threadIdx.x; i < ED_PH * ED_TAPS; i += blockDim.x) taps[i] = taps_g[i];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (s >= n_streams) return;
-    const float2 *x = iq + (long)s * stride;
-    float tau = 16.0f + sps;                 // first symbol instant with a full filter window
+    const int q = threadIdx.x & (ED_L - 1);                    // tap quad of this lane: taps 4q .. 4q+3
+    const int grp = threadIdx.x >> 3;                          // stream slot in the CTA
+    const int s = blockIdx.x * 16 + grp;
+    const bool live = s < n_streams;
+    const float2 *x = iq + (long)(live ? s : 0) * stride;
+    float2 *rb = ring[grp];
+    float tau = 16.0f + sps;                                   // first symbol instant with a full filter window
     float integ = 0.f, pavg = 0.f;
     float2 prev = make_float2(0.f, 0.f);
-    long k = 0;
-    const long max_sym = soft_stride / 2;
-    float2 *so = sym_out ? sym_out + (long)s * max_sym : nullptr;
-    float *sb = soft_out + (long)s * soft_stride;
-    Window wdw;
-    wdw.init(x, n, 0, lane);
-    while (tau + 17.0f < (float)n && k < max_sym) {
-        // earliest sample touched this symbol: the half-symbol point's window start
-        long first = (long)floorf(tau - 0.5f * sps) - 15;
-        wdw.advance_to(x, n, first < 0 ? 0 : first, lane);
-        float2 on = mf_at(wdw, taps, tau, lane);
-        float2 mid = mf_at(wdw, taps, tau - 0.5f * sps, lane);
-        float p = on.x * on.x + on.y * on.y;
-        pavg = (k == 0) ? p : 0.98f * pavg + 0.02f * p;
-        float inv = 1.0f / (pavg + 1e-20f);
-        // Gardner: e = Re{(y[k] - y[k-1]) conj(y[k-1/2])}; e > 0 <=> sampling late
-        float e = ((on.x - prev.x) * mid.x + (on.y - prev.y) * mid.y) * inv;
-        e = fminf(fmaxf(e, -1.0f), 1.0f);
-        // differential detection: d = y[k] conj(y[k-1]); b1 = [Im d < 0], b2 = [Re d < 0]; soft = -(.)/P
-        float dre = on.x * prev.x + on.y * prev.y, dim = on.y * prev.x - on.x * prev.y;
-        if (lane == 0) {
-            if (so) so[k] = on;
-            if (k > 0) { sb[2 * (k - 1)] = -dim * inv; sb[2 * (k - 1) + 1] = -dre * inv; }
+    int k = 0;
+    const int max_sym = (int)(soft_stride / 2);
+    const int ni = (int)n;                                     // n < 2^31 (launch check): 32-bit index arithmetic in the loop
+    const float nf_end = (float)n - 17.0f;
+    const float half = 0.5f * sps;
+    float2 *so = (sym_out && live) ? sym_out + (long)s * max_sym : nullptr;
+    float *sb = soft_out + (long)(live ? s : 0) * soft_stride;
+    int filled = 0;                                            // ring holds samples [filled - ED_RING, filled)
+    bool active = live && (tau < nf_end) && (k < max_sym);
+    while (__any_sync(0xffffffffu, active)) {
+        const float tmid = tau - half;
+        const float fl_on = floorf(tau), fl_mid = floorf(tmid);
+        const int i_on = (int)fl_on, i_mid = (int)fl_mid;
+        // keep [i_mid - 15, i_on + 16] inside the ring: refill ahead, 64 samples at a time
+#pragma unroll 1
+        while (active && filled < i_on + 17 + ED_FILL) {
+            const int g = filled + q * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int idx = g + j;
+                rb[idx & (ED_RING - 1)] = (idx < ni) ? x[idx] : make_float2(0.f, 0.f);
+            }
+            filled += ED_FILL;
         }
-        prev = on;
-        if (k > 0) { integ += ki * e; tau += sps - kp * e - integ; }
-        else tau += sps;
-        ++k;
+        __syncwarp();
+        int ph_on = (int)((tau - fl_on) * ED_PH), ph_mid = (int)((tmid - fl_mid) * ED_PH);
+        ph_on = min(max(ph_on, 0), ED_PH - 1);
+        ph_mid = min(max(ph_mid, 0), ED_PH - 1);
+        const float4 g_on = *reinterpret_cast<const float4 *>(&taps[ph_on * ED_TAPS + 4 * q]);
+        const float4 g_mid = *reinterpret_cast<const float4 *>(&taps[ph_mid * ED_TAPS + 4 * q]);
+        const int b_on = i_on - 15 + 4 * q, b_mid = i_mid - 15 + 4 * q;
+        float2 on = make_float2(0.f, 0.f), mid = make_float2(0.f, 0.f);
+        {
+            const float gw[4] = {g_on.x, g_on.y, g_on.z, g_on.w}, hw[4] = {g_mid.x, g_mid.y, g_mid.z, g_mid.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int a = b_on + j, c = b_mid + j;
+                const float2 va = (a >= 0) ? rb[a & (ED_RING - 1)] : make_float2(0.f, 0.f);
+                const float2 vc = (c >= 0) ? rb[c & (ED_RING - 1)] : make_float2(0.f, 0.f);
+                on.x = fmaf(va.x, gw[j], on.x); on.y = fmaf(va.y, gw[j], on.y);
+                mid.x = fmaf(vc.x, hw[j], mid.x); mid.y = fmaf(vc.y, hw[j], mid.y);
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < ED_L; o <<= 1) {
+            on.x += __shfl_xor_sync(0xffffffffu, on.x, o); on.y += __shfl_xor_sync(0xffffffffu, on.y, o);
+            mid.x += __shfl_xor_sync(0xffffffffu, mid.x, o); mid.y += __shfl_xor_sync(0xffffffffu, mid.y, o);
+        }
+        if (active) {
+            const float p = on.x * on.x + on.y * on.y;
+            pavg = (k == 0) ? p : 0.98f * pavg + 0.02f * p;
+            const float inv = __frcp_rn(pavg + 1e-20f);
+            // Gardner: e = Re{(y[k] - y[k-1]) conj(y[k-1/2])}; e > 0 <=> sampling late
+            float e = ((on.x - prev.x) * mid.x + (on.y - prev.y) * mid.y) * inv;
+            e = fminf(fmaxf(e, -1.0f), 1.0f);
+            // differential detection: d = y[k] conj(y[k-1]); b1 = [Im d < 0], b2 = [Re d < 0]; soft = -(.)/P
+            const float dre = on.x * prev.x + on.y * prev.y, dim = on.y * prev.x - on.x * prev.y;
+            if (q == 0) {
+                if (so) so[k] = on;
+                if (k > 0) *reinterpret_cast<float2 *>(sb + 2 * (k - 1)) = make_float2(-dim * inv, -dre * inv);
+            }
+            prev = on;
+            if (k > 0) { integ += ki * e; tau += sps - kp * e - integ; }
+            else tau += sps;
+            ++k;
+            active = (tau < nf_end) && (k < max_sym);
+        }
+        __syncwarp();                                           // ring reads of this symbol precede the next refill
     }
-    if (lane == 0) n_soft[s] = (int32_t)(k > 0 ? 2 * (k - 1) : 0);
+    if (live && q == 0) n_soft[s] = (int32_t)(k > 0 ? 2 * (k - 1) : 0);
 }
 
 // training sequences (EN 300 392-2 cl. 9.4.4.3): normal n, p, and the extended/tail q
@@ -268,6 +269,7 @@ int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, l
     if (n_streams <= 0) return TB200_OK;
     double sps = fs / 18000.0;
     if (sps < 2.0 || sps > 4.01) return fail(TB200_E_ARG, "tb200_etsi_demod_batch: %.3f samples/symbol outside [2, 4]", sps);
+    if (n >= (1L << 30) || (soft_stride & 1) || (reinterpret_cast<uintptr_t>(soft) & 7)) return fail(TB200_E_ARG, "tb200_etsi_demod_batch: n < 2^30, even soft_stride and 8-byte aligned d_soft required");
     if (h->etsi_taps_fs != fs) {                 // the tap table depends on fs only: upload once per handle
         float taps[ED_PH * ED_TAPS];
         make_mf_taps(sps, taps);
@@ -275,7 +277,7 @@ int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, l
         TB_CUDA(cudaStreamSynchronize(st));      // `taps` is a stack buffer
         h->etsi_taps_fs = fs;
     }
-    int threads = 128, blocks = (n_streams * 32 + threads - 1) / threads;
+    int threads = 128, blocks = (n_streams + 15) / 16;              // 8 lanes per stream, 16 streams per CTA
     etsi_demod_kernel<<<blocks, threads, 0, st>>>(iq, n_streams, n, stride, (float)sps, (float)(0.05 * sps), (float)(0.0005 * sps),
                                                   taps_dev, sym, soft, soft_stride, n_soft);
     TB_LAUNCH_CHECK(h);
