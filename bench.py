@@ -207,13 +207,18 @@ def run_b200(args):
     l0 = pipe.launches
     pipe.run_device(dev)
     launches_per_step = pipe.launches - l0
-    graphs = None
+    graphs, graph_error = None, None
     if args.graph:
         # one step = one CUDA graph launch; two captured pipelines (own workspaces / outputs) alternate on two
         # streams, so consecutive batches overlap exactly like the lanes of one batch do
-        pipe_b = pipeline.ReceivePipeline(FS, CHUNK, max_chunks=n_chunks, mode=args.mode, device=local_rank, n_lanes=args.lanes)
-        graphs = [pipe.capture(dev), pipe_b.capture(dev)]
-        gstreams = [torch.cuda.Stream(device=local_rank), torch.cuda.Stream(device=local_rank)]
+        try:
+            pipe_b = pipeline.ReceivePipeline(FS, CHUNK, max_chunks=n_chunks, mode=args.mode, device=local_rank, n_lanes=args.lanes)
+            graphs = [pipe.capture(dev), pipe_b.capture(dev)]
+            gstreams = [torch.cuda.Stream(device=local_rank), torch.cuda.Stream(device=local_rank)]
+        except Exception as e:                   # capture unsupported in this environment: drive the steps from Python
+            print(f"bench: CUDA graph capture failed ({e!r}); falling back to per-step launches", file=sys.stderr)
+            graphs, graph_error = None, repr(e)[:200]
+            torch.cuda.synchronize()
 
     def run_steps(k):
         if graphs is None:
@@ -243,7 +248,8 @@ def run_b200(args):
     ms = e0.elapsed_time(e1)
     launches = launches_per_step * args.steps
     stats = pipe.stats.cpu().numpy().copy()
-    if graphs is not None:
+    used_graphs = graphs is not None
+    if used_graphs:
         stats = stats + pipe_b.stats.cpu().numpy()
         del graphs, pipe_b
         torch.cuda.empty_cache()
@@ -358,7 +364,8 @@ def run_b200(args):
                                    "fast32": "time-parallel float32 decimator and float32 channel filter; dibits identical on the parity cases, "
                                              "soft symbols <= 1e-4 of full scale (tests/test_gpu_parity.py::test_fast_mode_within_tolerance)"}[args.mode] + ")",
                    "l2": "input 192 MB per step > 126 MB L2, no flush needed", "parallelism": f"capture segment per GPU x{world}",
-                   "stream_lanes": args.lanes, "cuda_graph": bool(args.graph), "cpus_bound_per_rank": numa_cpus},
+                   "stream_lanes": args.lanes, "cuda_graph": bool(args.graph) and graph_error is None,
+                   "cpus_bound_per_rank": numa_cpus},
         "crc_pass_bursts_per_s": round(bursts_per_s, 1), "crc_pass_per_step": int(stats[1] // max(args.steps, 1)),
         "gpu_launches": int(launches),
         "e2e": {"value": round(e2e, 3), "unit": "Msamples/s", "h2d_bytes_per_step": pipe.h2d_bytes(n_chunks),
