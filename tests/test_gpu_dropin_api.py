@@ -434,3 +434,29 @@ def test_cuda_graph_replay_equals_direct_launch(api, mode, lanes):
             for k, key in enumerate(("total_bursts", "crc_pass", "crc_fail")):
                 tot[k] += ost[key]
         assert list(pipe.stats.cpu().numpy()) == tot, rep
+
+
+def test_pipeline_records_to_frame_dicts(api):
+    """ReceivePipeline output -> TetraDecoder.frames_from_records == TetraDecoder.decode(dibits) chunk by chunk
+    (the streaming form documented in INTEGRATION.md section C)."""
+    from tetraear_b200 import pipeline, synth
+    core = api[1]
+    n_chunks, L = 4, 131072
+    cap = synth.make_capture(L * n_chunks, 130, seed=17, mix=(0.7, 0.15, 0.15)).reshape(n_chunks, L)
+    pipe = pipeline.ReceivePipeline(2.4e6, L, max_chunks=n_chunks, mode="fast32", n_lanes=2)
+    nfr, frames, _ = pipe.run_host(cap)
+    ndib, dib = pipe.n_dibits.cpu().numpy(), pipe.dibits.cpu().numpy()
+    total = 0
+    for c in range(n_chunks):
+        a = core.TetraDecoder(auto_decrypt=False).frames_from_records(frames[c, :nfr[c]])
+        b = core.TetraDecoder(auto_decrypt=False).decode(dib[c, :ndib[c]])
+        assert len(a) == len(b) > 0
+        for fa, fb in zip(a, b):
+            assert set(fa) == set(fb)
+            for k in fa:
+                if isinstance(fa[k], np.ndarray):
+                    assert np.array_equal(fa[k], fb[k]), k
+                else:
+                    assert fa[k] == fb[k], k
+        total += len(a)
+    assert total >= 8

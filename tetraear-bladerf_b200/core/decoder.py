@@ -146,10 +146,11 @@ class TetraDecoder:
         return frames.cpu().numpy().view(_lib.FRAME_DTYPE)[:k].copy()
 
     # ------------------------------------------------------------------ reference API
-    def decode(self, symbols):
-        """decoder.py:835-888."""
+    def frames_from_records(self, records):
+        """tb200_frame records (one chunk's row of ReceivePipeline.frames[:n_frames], or decode_records()) -> the
+        frame dicts decode() returns: the host half of decode() (MAC header walk, dict schema), in burst order."""
         frames = []
-        for rec in self.decode_records(symbols):
+        for rec in records:
             if not rec["kept"]:
                 continue
             frame = self._frame_dict(_unpack510(rec["bits"]), 0, int(rec["number"]), rec)
@@ -157,6 +158,10 @@ class TetraDecoder:
                 frames.append(frame)
                 logger.info(f"Decoded frame {frame['number']} (type: {frame['type']})")
         return frames
+
+    def decode(self, symbols):
+        """decoder.py:835-888."""
+        return self.frames_from_records(self.decode_records(symbols))
 
     def decode_frame(self, bits, start_pos, symbols=None, frame_number=0):
         """decoder.py:890-1119 (integer head + burst parse; no decryption)."""
