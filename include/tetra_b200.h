@@ -230,6 +230,11 @@ int tb200_etsi_demod_batch(tb200_handle h, const void *d_iq_c64, int n_streams, 
 int tb200_etsi_find_bursts(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,
                            const int32_t *d_n_soft, double threshold, float *d_metric, int8_t *d_blocks,
                            int32_t *d_burst_pos, int32_t *d_n_bursts, int max_bursts, void *stream);
+/* feed-forward carrier-offset correction of the soft bits in place: theta = (arg sum d^4 - pi) / 4 over each stream's
+ * differential symbols d (unambiguous for |df| < 2250 Hz), every soft pair rotated by -theta; d_theta [n_streams]
+ * (radians per symbol; df = theta * 18000 / 2 pi) or NULL.  Run between tb200_etsi_demod_batch and the searches. */
+int tb200_etsi_afc(tb200_handle h, float *d_soft, int n_streams, int64_t soft_stride, const int32_t *d_n_soft,
+                   float *d_theta, void *stream);
 /* synchronisation-burst search: normalised soft correlation with the 38-bit sync training sequence y at every symbol
  * position (d_metric scratch as above); for every sync burst found the 120 SB1 soft bits go to d_sb1
  * [n_streams][max_bursts][120] (input of tb200_etsi_decode_batch, channel 2 = BSCH, scrambling init 3: its 60 type-1

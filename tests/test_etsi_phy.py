@@ -97,3 +97,35 @@ def test_sync_burst_acquisition_bootstraps_the_scrambling_code(fs, sigma):
                 assert np.array_equal(b["blocks"], truth[s][0][idx])
                 good += 1
         assert good >= (n_bursts - n_bursts // k) - 6, (s, good)
+
+
+@pytest.mark.gpu
+def test_carrier_offset_correction():
+    """Feed-forward AFC (tb200_etsi_afc): carrier offsets up to +-2 kHz are estimated to a few Hz from sum d^4 and
+    removed before the searches."""
+    import __graft_entry__ as entry
+    entry.build()
+    fs, n_bursts = 50000.0, 20
+    offs = [-2000.0, -900.0, 0.0, 650.0, 1800.0]
+    streams, truth = [], []
+    for s, f in enumerate(offs):
+        bits, t1, init = etsi.make_etsi_stream(n_bursts, seed=70 + s)
+        streams.append(etsi.modulate_dqpsk(bits, fs, sigma=0.04, freq=f, t_offset=0.1 * s, seed=s))
+        truth.append(t1)
+    n = min(len(v) for v in streams)
+    x = np.stack([v[:n] for v in streams])
+    rx = etsi.EtsiReceiver(fs, max_streams=len(offs), max_samples=n)
+    res = rx.run(x, init)
+    est = rx.carrier_offsets_hz(len(offs))
+    with_afc = []
+    for s, f in enumerate(offs):
+        assert abs(est[s] - f) < 15.0, (f, est[s])
+        good = sum(1 for b in res[s] if b["crc_ok"].all() and np.array_equal(b["blocks"], truth[s][int(round(b["start"] / 510.0))]))
+        assert good >= n_bursts - 5, (f, good)
+        with_afc.append(good)
+    # the same capture without the correction: the rotated decisions cost bursts at +-2 kHz (40 degrees of the 45 available)
+    rx0 = etsi.EtsiReceiver(fs, max_streams=len(offs), max_samples=n, afc=False)
+    res0 = rx0.run(x, init)
+    without = [sum(1 for b in res0[s] if b["crc_ok"].all()) for s in range(len(offs))]
+    assert all(w <= a for w, a in zip(without, with_afc)), (without, with_afc)
+    assert without[0] < with_afc[0] or without[4] < with_afc[4], (without, with_afc)

@@ -631,6 +631,16 @@ extern "C" int tb200_etsi_find_bursts(tb200_handle h, const float *d_soft, int n
                                    d_n_bursts, max_bursts, (cudaStream_t)stream);
 }
 
+extern "C" int tb200_etsi_afc(tb200_handle h, float *d_soft, int n_streams, int64_t soft_stride, const int32_t *d_n_soft,
+                              float *d_theta, void *stream)
+{
+    DevGuard dev_guard(h);
+    if (!h || n_streams < 0 || !d_soft || !d_n_soft || (soft_stride & 1) || (reinterpret_cast<uintptr_t>(d_soft) & 7))
+        return fail(TB200_E_ARG, "tb200_etsi_afc: bad argument");
+    StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
+    return launch_etsi_afc(h, d_soft, n_streams, soft_stride, d_n_soft, d_theta, (cudaStream_t)stream);
+}
+
 extern "C" int tb200_etsi_find_sync_bursts(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,
                                            const int32_t *d_n_soft, double threshold, float *d_metric, int8_t *d_sb1,
                                            int8_t *d_bkn2, int32_t *d_burst_pos, int32_t *d_n_bursts, int max_bursts, void *stream)

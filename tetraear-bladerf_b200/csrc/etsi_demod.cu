@@ -244,6 +244,50 @@ __global__ void etsi_find_sync_kernel(const float *__restrict__ soft, long soft_
     if (lane == 0) n_bursts[s] = found;
 }
 
+
+// ---- feed-forward carrier-offset correction on the differential symbols.  The soft pair of symbol k is the
+// normalised d_k = y_k conj(y_(k-1)):  Re d = -soft[2k+1], Im d = -soft[2k].  For pi/4-DQPSK arg d is one of
+// +-pi/4, +-3pi/4 plus theta = 2 pi df T, so d^4 has phase pi + 4 theta whatever the data: theta = (arg sum d^4 - pi) / 4,
+// unambiguous for |df| < symbol rate / 8 = 2250 Hz.  One CTA per stream: sum, then rotate every pair by -theta in place.
+__global__ void __launch_bounds__(256)
+etsi_afc_kernel(float *__restrict__ soft, long soft_stride, const int32_t *__restrict__ n_soft, float *__restrict__ theta_out)
+{
+    __shared__ double red[2][8];
+    __shared__ float rot[2];
+    const int s = blockIdx.x;
+    float *b = soft + (long)s * soft_stride;
+    const int nsym = n_soft[s] / 2;
+    double sr = 0.0, si = 0.0;
+    for (int k = threadIdx.x; k < nsym; k += blockDim.x) {
+        const float2 p = *reinterpret_cast<const float2 *>(b + 2 * k);
+        float re = -p.y, im = -p.x;
+        const float m = fmaxf(sqrtf(re * re + im * im), 1e-12f);
+        re /= m; im /= m;                                   // unit modulus: every symbol one vote
+        const float r2 = re * re - im * im, i2 = 2.f * re * im;
+        sr += (double)(r2 * r2 - i2 * i2); si += (double)(2.f * r2 * i2);
+    }
+    for (int o = 16; o > 0; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sr; red[1][threadIdx.x >> 5] = si; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tr = 0.0, ti = 0.0;
+        for (int w = 0; w < 8; ++w) { tr += red[0][w]; ti += red[1][w]; }
+        // phase of -S4 is 4 theta
+        const float theta = (nsym > 0) ? 0.25f * atan2f((float)-ti, (float)-tr) : 0.f;
+        rot[0] = cosf(theta); rot[1] = sinf(theta);
+        if (theta_out) theta_out[s] = theta;
+    }
+    __syncthreads();
+    const float c = rot[0], sn = rot[1];
+    for (int k = threadIdx.x; k < nsym; k += blockDim.x) {
+        float2 p = *reinterpret_cast<float2 *>(b + 2 * k);
+        const float re = -p.y, im = -p.x;
+        const float r = re * c + im * sn, i = im * c - re * sn;     // d * exp(-j theta)
+        p.x = -i; p.y = -r;
+        *reinterpret_cast<float2 *>(b + 2 * k) = p;
+    }
+}
+
 void make_mf_taps(double sps, float *taps)
 {
     const double alpha = 0.35;
@@ -295,6 +339,14 @@ int launch_etsi_find_bursts(tb200_handle h, const float *soft, int n_streams, lo
     int threads = 128, blocks_n = (n_streams * 32 + threads - 1) / threads;
     etsi_find_bursts_kernel<<<blocks_n, threads, 0, st>>>(soft, soft_stride, n_soft, metric, n_streams, thr, blocks, burst_pos,
                                                          n_bursts, max_bursts, 45.0f);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+int launch_etsi_afc(tb200_handle h, float *soft, int n_streams, long soft_stride, const int32_t *n_soft, float *theta, cudaStream_t st)
+{
+    if (n_streams <= 0) return TB200_OK;
+    etsi_afc_kernel<<<n_streams, 256, 0, st>>>(soft, soft_stride, n_soft, theta);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
 }

@@ -40,6 +40,7 @@ int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, l
 int launch_etsi_find_bursts(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft,
                             float thr, float *metric, int8_t *blocks, int32_t *burst_pos, int32_t *n_bursts, int max_bursts,
                             cudaStream_t st);
+int launch_etsi_afc(tb200_handle h, float *soft, int n_streams, long soft_stride, const int32_t *n_soft, float *theta, cudaStream_t st);
 int launch_etsi_find_sync(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft, float thr,
                           float *metric, int8_t *sb1, int8_t *bkn2, int32_t *burst_pos, int32_t *n_bursts, int max_bursts,
                           cudaStream_t st);

@@ -260,7 +260,7 @@ class EtsiReceiver:
     training-sequence search + block extraction (tb200_etsi_find_bursts) ->
     descramble / de-interleave / Viterbi / CRC of both SCH/HD blocks (tb200_etsi_decode_batch)."""
 
-    def __init__(self, fs, max_streams, max_samples, device=0, max_bursts_per_stream=None):
+    def __init__(self, fs, max_streams, max_samples, device=0, max_bursts_per_stream=None, afc=True):
         import torch
         from . import _dev
         self.fs = float(fs)
@@ -282,6 +282,8 @@ class EtsiReceiver:
         self.crc_ok = _dev.zeros((S * self.max_bursts * 2,), torch.uint8, device)
         self.path_metric = _dev.zeros((S * self.max_bursts * 2,), torch.int32, device)
         self.symbols = None
+        self.afc = bool(afc)                      # feed-forward carrier-offset correction (tb200_etsi_afc), |df| < 2250 Hz
+        self.theta = _dev.zeros((S,), torch.float32, device)
         self.max_sync = self.max_bursts
         self.sb1 = _dev.zeros((S, self.max_sync, 120), torch.int8, device)
         self.sync_pos = _dev.zeros((S, self.max_sync), torch.int32, device)
@@ -315,8 +317,15 @@ class EtsiReceiver:
         _lib.check(lib.tb200_etsi_demod_batch(h.h, d.data_ptr(), x.shape[0], x.shape[1], x.shape[1], self.fs, None,
                                               self.soft.data_ptr(), self.soft_stride, self.n_soft.data_ptr(),
                                               _dev.stream_ptr(self.device)))
+        if self.afc:
+            _lib.check(lib.tb200_etsi_afc(h.h, self.soft.data_ptr(), x.shape[0], self.soft_stride, self.n_soft.data_ptr(),
+                                          self.theta.data_ptr(), _dev.stream_ptr(self.device)))
         self.acquire_device(x.shape[0], threshold)
         return self.sync_results(x.shape[0])
+
+    def carrier_offsets_hz(self, n_streams):
+        """Carrier offset estimated by the last run per stream (Hz)."""
+        return self.theta.cpu().numpy()[:n_streams].astype(np.float64) * 18000.0 / (2 * np.pi)
 
     def sync_results(self, n_streams):
         ns = self.n_sync.cpu().numpy()[:n_streams]
@@ -352,6 +361,9 @@ class EtsiReceiver:
         _lib.check(lib.tb200_etsi_demod_batch(h.h, int(iq_ptr), n_streams, int(n_samples), int(stride), self.fs,
                                               self.symbols.data_ptr() if keep_symbols else None, self.soft.data_ptr(),
                                               self.soft_stride, self.n_soft.data_ptr(), st))
+        if self.afc:
+            _lib.check(lib.tb200_etsi_afc(h.h, self.soft.data_ptr(), n_streams, self.soft_stride, self.n_soft.data_ptr(),
+                                          self.theta.data_ptr(), st))
         _lib.check(lib.tb200_etsi_find_bursts(h.h, self.soft.data_ptr(), n_streams, self.soft_stride, self.n_soft.data_ptr(),
                                               float(threshold), self.metric.data_ptr(), self.blocks.data_ptr(),
                                               self.burst_pos.data_ptr(), self.n_bursts.data_ptr(), self.max_bursts, st))
