@@ -96,6 +96,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 }
 
 
+// Kogge-Stone stages that matter per mode (multiplier >= 1e-9).  The design is a fixed function of q and for every
+// instantiated q (7, 8, 10) the counts are the same; make_fast_params checks them, so the test is resolved at compile time.
+__host__ __device__ constexpr int fd_nstage(int m) { return m == 0 ? 3 : (m == 3 ? 5 : 4); }
+
 // one direction (causal: row0.., taps reversed; anti-causal: next row, taps ascending) for two of the
 // four modes; accumulates Re(alpha * .) into y (I, Q packed) and leaves the pass-end state in `carry`.
 template <int Q, int PITCH, bool FWD, int NM>
@@ -134,7 +138,7 @@ __device__ __forceinline__ void fd_half(const float2 *__restrict__ tile, int row
         cp a = U[FWD ? FD_R - 1 : 0][mm];
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
-            if (s >= K.nstage[m]) continue;              // multiplier (lambda^R)^(2^s) below 1e-9: nothing to add in float32
+            if (s >= fd_nstage(m)) continue;             // multiplier (lambda^R)^(2^s) below 1e-9: nothing to add in float32 (compile time)
             cp o;
             o.re = FWD ? shfl2_up(a.re, 1 << s) : shfl2_down(a.re, 1 << s);
             o.im = FWD ? shfl2_up(a.im, 1 << s) : shfl2_down(a.im, 1 << s);
@@ -362,6 +366,8 @@ static int make_fast_params(const DecimDesign &d, int q, long n, long n_dec, Fas
             if (s < 5 && std::abs(lr) >= 1e-9) K.nstage[j] = s + 1;
             lr *= lr;
         }
+        if (K.nstage[j] > fd_nstage(j))
+            return fail(TB200_E_ARG, "fast decimator: mode %d of q=%d needs %d scan stages, kernel has %d", j, q, K.nstage[j], fd_nstage(j));
         put(K.a0[j], alpha[j]);
         put(K.ap[j], alpha[j] * p8[j]);
         for (int r = 0; r < FD_R; ++r) {
