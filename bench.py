@@ -378,7 +378,7 @@ def run_b200(args):
                      "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
                      # dram__bytes_read.sum + dram__bytes_write.sum of decim_fast_kernel<10>, one launch, ncu --set full
                      # (profiles/r01_ncu_kernels_final.md); valid for the fast mode on this workload only
-                     "traffic": 205659904 if args.mode.startswith("fast") else None,
+                     "traffic": 208479744 if args.mode.startswith("fast") else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "ms_per_launch": round(dec_launch_ms, 4),
                      "path_achieved_gbs": round(path_bytes / (step_ms / 1e3) / 1e9, 2),
