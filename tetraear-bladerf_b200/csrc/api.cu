@@ -142,6 +142,9 @@ struct StageTimer {
     StageTimer(tb200_handle h_, int stage, cudaStream_t st_) : h(h_), st(st_), on(h_->profiling != 0)
     {
         if (!on) return;
+        // events recorded into a graph capture cannot be read back with cudaEventElapsedTime: no timing while capturing
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); on = false; return; }
         cudaEvent_t a, b;
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { on = false; return; }
         h->prof_ev->push_back(a); h->prof_ev->push_back(b); h->prof_stage->push_back(stage);
@@ -255,7 +258,9 @@ extern "C" int tb200_set_sample_rate(tb200_handle h, double sample_rate)
     probe.bits_stride = h->bits_stride; probe.max_frames = h->max_frames; probe.max_streams = h->max_streams;
     if (probe.plan.max_symbols + 8 > h->bits_stride / 2 || carve(&probe, nullptr) > h->ws_bytes)
         return fail(TB200_E_ARG, "tb200_set_sample_rate: %g Hz needs a larger workspace; create a new handle", sample_rate);
-    probe.ws = h->ws; probe.ws_bytes = h->ws_bytes; probe.launches = h->launches; probe.psd_tables_n = 0;
+    probe.ws = h->ws; probe.ws_bytes = h->ws_bytes; probe.launches = h->launches;
+    // every table carved behind the plan-dependent regions moves with n_dec: forget what was uploaded into them
+    probe.psd_tables_n = 0; probe.etsi_taps_fs = 0.0; probe.chan_M = 0;
     carve(&probe, (char *)h->ws);
     *h = probe;
     return TB200_OK;
@@ -513,14 +518,14 @@ extern "C" int tb200_decode_batch(tb200_handle h, const uint8_t *d_dibits, int n
     long bstride = 2L * stride;
     if ((size_t)n_streams * bstride > (size_t)h->max_streams * h->bits_stride)
         return fail(TB200_E_ARG, "tb200_decode_batch: %d x %d dibits exceed the handle capacity", n_streams, stride);
-    if ((size_t)n_streams * max_frames > (size_t)h->max_streams * h->max_frames)
-        return fail(TB200_E_ARG, "tb200_decode_batch: max_frames too large for the handle");
     if (stride == 0) { TB_CUDA(cudaMemsetAsync(d_n_frames, 0, sizeof(int32_t) * n_streams, st)); return TB200_OK; }
     int rc;
     if (stride <= 6000 && max_frames <= 64) {          // one chunk's worth: fused single-launch path (42 KB smem)
-        StageTimer tm(h, TB_STAGE_DECODE, st);
+        StageTimer tm(h, TB_STAGE_DECODE, st);         // (keeps its sync positions in shared memory: no sync_pos capacity rule)
         return launch_decode_fused(h, d_dibits, n_streams, stride, d_n_dibits, d_frames, max_frames, d_n_frames, d_stats, st);
     }
+    if ((size_t)n_streams * max_frames > (size_t)h->max_streams * h->max_frames)
+        return fail(TB200_E_ARG, "tb200_decode_batch: max_frames too large for the handle");
     {
         StageTimer tm(h, TB_STAGE_BITS_SYNC, st);
         rc = launch_symbols_to_bits(h, d_dibits, n_streams, stride, d_n_dibits, 0, h->bits, h->mapped, bstride, st);

@@ -9,6 +9,7 @@
 // the 32-byte record is written.  The CRC-16 is linear over GF(2), so instead of a 200-step
 // serial shift register each lane XORs the precomputed contribution of its own 1-bits and
 // the warp XOR-reduces (5 shuffles) — forward and bit-reversed payload in the same pass.
+#include <mutex>
 #include "common.h"
 #include "kernels.h"
 
@@ -28,6 +29,7 @@ __device__ uint16_t g_crc_init[512];
 // direction (0 forward, 1 reversed): g_crc_nib[type][dir][nibble 0..127][value 0..15]
 __device__ uint16_t g_crc_nib[2][2][128][16];
 static bool g_crc_ready[64] = {false};
+static std::mutex g_crc_mu;                 // tb200_create may run concurrently for several devices
 
 static void build_crc_tables(uint16_t *tab, uint16_t *init)
 {
@@ -46,6 +48,7 @@ static void build_crc_tables(uint16_t *tab, uint16_t *init)
 int ensure_crc_tables(int device)
 {
     if (device < 0 || device >= 64) return fail(TB200_E_ARG, "device ordinal out of range");
+    std::lock_guard<std::mutex> lk(g_crc_mu);
     if (g_crc_ready[device]) return TB200_OK;
     uint16_t tab[512], init[512];
     build_crc_tables(tab, init);
@@ -79,6 +82,7 @@ __global__ void symbols_to_bits_kernel(const uint8_t *__restrict__ sym, long str
     __shared__ int s_max;
     int s = blockIdx.x;
     long n = n_sym ? n_sym[s] : n_fixed;
+    n = n < 0 ? 0 : (n > stride ? stride : n);          // the count lives on the device: never trust it past the row
     const uint8_t *in = sym + (long)s * stride;
     if (threadIdx.x == 0) s_max = 0;
     __syncthreads();
@@ -106,6 +110,7 @@ __global__ void sync_corr_kernel(const uint8_t *__restrict__ bits, long bits_str
 {
     int s = blockIdx.y;
     long nb = n_sym ? 2L * n_sym[s] : n_bits_fixed;
+    nb = nb < 0 ? 0 : (nb > bits_stride ? bits_stride : nb);
     long nwin = nb - 21;
     long pos = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (pos >= nwin) return;
@@ -552,7 +557,8 @@ __global__ void decode_kernel(const uint8_t *__restrict__ bits, const uint8_t *_
     int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s >= n_streams) return;
     decode_stream_warp(bits + (long)s * bits_stride, mapped + (long)s * (bits_stride / 2), m1 + (long)s * bits_stride,
-                       m2 + (long)s * bits_stride, n_sym[s], tab, initv, frames + (long)s * max_frames, max_frames,
+                       m2 + (long)s * bits_stride, min(max((long)n_sym[s], 0L), bits_stride / 2), tab, initv,
+                       frames + (long)s * max_frames, max_frames,
                        n_frames + s, stats, pos_scratch + (long)s * max_frames);
 }
 
@@ -569,7 +575,7 @@ decode_fused_kernel(const uint8_t *__restrict__ dibits, int n_streams, long stri
     __shared__ int s_max;
     __shared__ int32_t pos_sm[64];
     const int s = blockIdx.x;
-    const long n = n_sym[s];
+    const long n = min(max((long)n_sym[s], 0L), stride);      // clamp: the shared buffers hold `stride` dibits
     uint8_t *mp = dsm;                       // [stride]
     uint8_t *b = mp + stride;                // [2 stride]
     uint8_t *c1 = b + 2 * stride;            // [2 stride]

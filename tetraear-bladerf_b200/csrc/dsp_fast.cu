@@ -22,6 +22,7 @@
 // Data layout: a CTA stages its tile of the padded chunk in shared memory as separate I and Q
 // planes, one row of q samples per output with an odd row pitch (q+1 for even q), so that the
 // 32 lanes of a warp — each owning R=3 consecutive rows — read conflict-free.
+#include <atomic>
 #include <complex>
 #include <mutex>
 #include <vector>
@@ -408,7 +409,7 @@ static int launch_q(tb200_handle h, const void *x, int n_chunks, long n, long ch
 {
     constexpr int ROWS = FD_NP * FD_P + 1;
     const size_t smem = ((size_t)(ROWS * Q + 1) * sizeof(float2) + 15 + 16) & ~(size_t)15;
-    static bool attr_set[64] = {false};          // per device: the attribute belongs to the device's copy of the kernel
+    static std::atomic<bool> attr_set[64];       // per device: the attribute belongs to the device's copy of the kernel (setting it twice is harmless)
     const int dv = h->cfg.device & 63;
     if (!attr_set[dv]) {
         cudaError_t e = cudaFuncSetAttribute(decim_fast_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -429,7 +430,7 @@ int launch_decimate_fast(tb200_handle h, const void *x, int n_chunks, long n, lo
     if (!fast_decimator_supported(q)) return fail(TB200_E_ARG, "fast decimator: q=%d not instantiated", q);
     // the modal constants depend on (design, q, n, n_dec) only: keep the last few sets instead of re-deriving them
     // (dozens of complex pow) on every launch — the host must stay ahead of a ~50 us kernel
-    struct Cached { int q; long n, n_dec; float g; FastDecimParams K; };
+    struct Cached { int q; long n, n_dec; float sos[24]; FastDecimParams K; };
     static std::mutex mu;
     static std::vector<Cached> cache;
     FastDecimParams K;
@@ -437,14 +438,15 @@ int launch_decimate_fast(tb200_handle h, const void *x, int n_chunks, long n, lo
     {
         std::lock_guard<std::mutex> lk(mu);
         for (const Cached &c : cache)
-            if (c.q == q && c.n == n && c.n_dec == n_dec && c.g == d.sos32[0]) { K = c.K; hit = true; break; }
+            if (c.q == q && c.n == n && c.n_dec == n_dec && !memcmp(c.sos, d.sos32, sizeof(c.sos))) { K = c.K; hit = true; break; }
     }
     if (!hit) {
         int rc0 = make_fast_params(d, q, n, n_dec, K);
         if (rc0) return rc0;
         std::lock_guard<std::mutex> lk(mu);
         if (cache.size() >= 16) cache.erase(cache.begin());
-        cache.push_back(Cached{q, n, n_dec, d.sos32[0], K});
+        Cached c; c.q = q; c.n = n; c.n_dec = n_dec; memcpy(c.sos, d.sos32, sizeof(c.sos)); c.K = K;
+        cache.push_back(c);
     }
     int rc = TB200_OK;
     if (q == 10) rc = launch_q<10>(h, x, n_chunks, n, chunk_stride, n_dec, K, dec_out, st);

@@ -8,6 +8,7 @@
 // table, then turned into dBFS, fft-shifted, written as float32, and reduced to the 8
 // band statistics the AFC loop reads — all without leaving the SM.
 #include <cmath>
+#include <atomic>
 #include "common.h"
 #include "kernels.h"
 
@@ -365,8 +366,8 @@ int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_
     bp.freq_step = 1.0 / ((double)n_fft * (1.0 / fs));
     if (use_f32 && n_fft == 4096) {
         const size_t sm4 = sizeof(float2) * (size_t)(P4_BUF + 4096 + 256);
-        static bool attr4_dev[64] = {false};     // per device
-        bool &attr4 = attr4_dev[h->cfg.device & 63];
+        static std::atomic<bool> attr4_dev[64];  // per device
+        std::atomic<bool> &attr4 = attr4_dev[h->cfg.device & 63];
         if (!attr4) {
             cudaError_t e = cudaFuncSetAttribute(psd4096_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
             if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(psd4096_f32_kernel): %s", cudaGetErrorString(e));
