@@ -125,6 +125,11 @@ int tb200_set_sample_rate(tb200_handle h, double sample_rate); /* attr is mutate
  * frame peak, i.e. far inside the 1e-4-of-full-scale budget; dB values of bins > 100 dB below the frame peak lose
  * digits).  Default 0 = float64 like numpy. */
 #define TB200_OPT_PSD_F32 2
+/* TB200_OPT_DECIM_TC = 3: in FAST mode run the decimator's linear part (q-tap modal FIRs and the in-lane recurrences)
+ * as split-TF32 tcgen05 MMAs (dsp_tc.cu) when q is 8 or 10, the input is complex64, 16-byte aligned with an even chunk
+ * stride and a chunk holds at least 1536 outputs; other geometries use the FFMA2 kernel of dsp_fast.cu.  Same
+ * filter, same float32-level accuracy (<= 1e-4 of full scale vs the reference).  Default 1. */
+#define TB200_OPT_DECIM_TC 3
 int tb200_set_option(tb200_handle h, int option, int value);
 size_t tb200_workspace_bytes(tb200_handle h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
@@ -266,6 +271,12 @@ int tb200_profile_read(tb200_handle h, double ms[8], int64_t calls[8]);
 /* ---- debugging aid: synchronous copy of an internal workspace region to the host ---------
  * region 0 = decimated chunks, 1 = channel-filtered complex128, 2 / 3 = forward-pass scratches */
 int tb200_debug_read(tb200_handle h, int region, void *h_dst, size_t nbytes);
+/* host only (no device needed): the weight matrix of the tensor-core decimator for factor q as K x 48 doubles
+ * (row-major), its TF32 split in the shared-memory layout ([K/4][48][4] floats each) and the carry constants (flat
+ * floats: lampow[5][4][2], lanepow[32][4][2], cF[3][4][2], cB[3][4][2], initF[4][2], initB[4][2]); tests emulate the kernel
+ * with them on the CPU (tests/test_tc_design_cpu.py).  Any output pointer may be NULL. */
+int tb200_debug_tc_design(int q, double *B, int b_capacity, float *bhi, float *blo, int split_capacity, float *params,
+                          int params_capacity, int *K_out);
 
 /* ---- scanner heuristics, batched over dwells ----------------------------------------------
  * Replaces the per-sample Python loops of TetraSignalDetector.calculate_power / detect_tetra_modulation /

@@ -384,6 +384,11 @@ def find_peak_near(freqs_mhz, powers, freq_mhz, search_range_hz):
     """WaterfallWidget.find_peak_near, ui/modern.py:727-772 (parabolic sub-bin peak)."""
     freqs = np.asarray(freqs_mhz, dtype=np.float64)
     powers = np.asarray(powers, dtype=np.float64)
+    if len(freqs) == 0 or len(powers) == 0:                    # :729-735
+        return freq_mhz
+    if freqs.shape != powers.shape:                            # :745-748
+        n = min(len(freqs), len(powers))
+        freqs, powers = freqs[:n], powers[:n]
     half = search_range_hz / 1e6
     mask = (freqs >= float(freq_mhz) - half) & (freqs <= float(freq_mhz) + half)
     if not np.any(mask):

@@ -1,19 +1,23 @@
-"""Import the UNMODIFIED reference from /root/reference (build container only).
+"""Import the UNMODIFIED reference: from /root/reference in the build container, else from oracle/_ref/.
 
-TEST INFRASTRUCTURE.  The GPU box has no /root/reference, so nothing in the ``-m gpu``
-tests, ``smoke()`` or ``bench.py`` may import this module; it exists for
-``tests/golden/make_golden.py`` and for the container-only cross-checks in
-``tests/test_oracle_vs_reference.py`` (skipped when the tree is absent).
+TEST INFRASTRUCTURE.  The GPU box has no /root/reference; ``oracle/make_ref.py`` stages byte-identical copies of
+the seven modules of the path under the git-ignored ``oracle/_ref/`` (it travels with the snapshot like the built
+libraries), so that ``bench.py --impl reference`` / ``cpu_baseline`` time the reference's own code there and the
+cross-checks of ``tests/test_oracle_vs_reference.py`` run on both sides.  ``tests/golden/make_golden.py`` uses the
+full tree (it also reads ui/modern.py source lines).  The product never imports this module.
 """
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("TETRAEAR_REFERENCE", "/root/reference")
+_FULL = os.environ.get("TETRAEAR_REFERENCE", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+FULL_TREE = os.path.isdir(os.path.join(_FULL, "tetraear"))            # ui/modern.py etc. present (build container)
+REFERENCE_ROOT = _FULL if FULL_TREE else _STAGED
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "tetraear"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "tetraear", "signal", "processor.py"))
 
 
 def load():

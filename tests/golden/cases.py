@@ -106,6 +106,41 @@ def afc_cases(n=40, seed=12):
     return out
 
 
+def peak_cases(n=60, seed=21):
+    """(freqs_mhz, powers_db, click_mhz, search_range_hz) for WaterfallWidget.find_peak_near (ui/modern.py:727-772):
+    narrow spikes between bins, flat tops (zero denominator), peaks on the first / last bin, empty search windows,
+    unequal array lengths and a non-uniform frequency axis."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for case in range(n):
+        nb = 2048 if case % 5 else 257
+        fc = 390.0 + rng.uniform(-1, 1)
+        freqs = fc + (np.arange(nb) - nb // 2) * (2.4 / nb)
+        powers = rng.uniform(-110, -70, nb)
+        kind = case % 6
+        pk = int(rng.integers(3, nb - 3))
+        if kind == 0:
+            powers[pk] = -30.0; powers[pk - 1] = -36.0; powers[pk + 1] = -33.0
+        elif kind == 1:
+            powers[pk - 1:pk + 2] = -40.0                       # flat top: denominator 0
+        elif kind == 2:
+            pk = 0 if case % 2 else nb - 1
+            powers[pk] = -20.0                                   # edge bin: no interpolation
+        elif kind == 3:
+            freqs = freqs + np.cumsum(rng.uniform(0, 2e-4, nb))  # non-uniform axis
+            powers[pk] = -25.0; powers[pk + 1] = -26.0
+        elif kind == 4:
+            powers = powers[: nb - 7]                            # lengths differ: truncated to the shorter
+            pk = min(pk, nb - 12)
+            powers[pk] = -22.0
+        click = float(freqs[pk] + rng.uniform(-0.002, 0.002))
+        rng_hz = float(rng.choice([500.0, 5000.0, 25000.0, 200000.0]))
+        if kind == 5:
+            click, rng_hz = float(freqs[-1] + 1.0), 1000.0      # nothing in range: the click comes back
+        out.append((freqs, powers, click, rng_hz))
+    return out
+
+
 def stage_edge_cases():
     """Stage-level calls with awkward shapes / rates / dtypes: (method, kwargs, input).  Shared by the live
     oracle-vs-reference check (CPU, build container) and the CUDA-vs-oracle check (GPU box)."""

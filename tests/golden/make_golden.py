@@ -26,7 +26,7 @@ logging.disable(logging.CRITICAL)
 
 from oracle import ref_bridge  # noqa: E402
 from tetraear_b200 import synth  # noqa: E402
-from tests.golden.cases import process_cases, psd_chunks, burst_batch, scanner_cases, voice_cases, afc_cases  # noqa: E402
+from tests.golden.cases import process_cases, psd_chunks, burst_batch, scanner_cases, voice_cases, afc_cases, peak_cases  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SP, TD, TP = ref_bridge.load()
@@ -233,6 +233,20 @@ def gen_afc():
     save("afc.npz", new_freq=np.array(out, dtype=np.float64))
 
 
+def gen_peak():
+    """WaterfallWidget.find_peak_near: lines 727-772 of ui/modern.py exec'd as a plain function against a stub self."""
+    modern = os.path.join(ref_bridge.REFERENCE_ROOT, "tetraear", "ui", "modern.py")
+    src = _lines(modern, 727, 772)
+    assert src.startswith("def find_peak_near(self, freq, search_range_hz):") and "Sub-bin quadratic" in src
+    ns = {"np": np}
+    exec(src, ns)
+    out = []
+    for freqs, powers, click, rng_hz in peak_cases():
+        stub = types.SimpleNamespace(current_fft=powers, current_freqs=freqs)
+        out.append(ns["find_peak_near"](stub, click, rng_hz))
+    save("peak.npz", peak=np.array(out, dtype=np.float64))
+
+
 if __name__ == "__main__":
     proc = gen_process()
     gen_decode(proc)
@@ -241,3 +255,4 @@ if __name__ == "__main__":
     gen_scanner()
     gen_voice()
     gen_afc()
+    gen_peak()

@@ -146,6 +146,23 @@ def test_voice_blocks_match_reference():
             assert p[0] == 0x6B21 and -500 <= p[1] <= 500 and 20 <= p[2] <= 220 and 0 <= p[3] <= 150
 
 
+def test_find_peak_near_matches_reference():
+    """WaterfallWidget.find_peak_near (ui/modern.py:727-772): golden values from the reference's own source lines."""
+    import os
+    from tests.conftest import GOLDEN
+    from tests.golden.cases import peak_cases
+    from tetraear_b200.signal import find_peak_near
+    want = np.load(os.path.join(GOLDEN, "peak.npz"))["peak"]
+    cases = peak_cases()
+    assert len(want) == len(cases)
+    interpolated = 0
+    for (freqs, powers, click, rng_hz), w in zip(cases, want):
+        assert oracle.find_peak_near(freqs, powers, click, rng_hz) == w
+        assert find_peak_near(freqs, powers, click, rng_hz) == w      # host helper (scalar GUI logic, no device work)
+        interpolated += not np.any(np.asarray(freqs) == w) and w != click
+    assert interpolated >= 10
+
+
 def test_afc_rule_matches_reference():
     import os
     from tests.conftest import GOLDEN

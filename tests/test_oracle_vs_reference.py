@@ -9,6 +9,8 @@ from oracle import oracle, ref_bridge
 from tetraear_b200 import synth
 
 pytestmark = pytest.mark.skipif(not ref_bridge.available(), reason="reference tree not present")
+# tests that read ui/modern.py / signal/scanner.py need the full tree (build container); oracle/_ref stages only the path's modules
+needs_full = pytest.mark.skipif(not ref_bridge.FULL_TREE, reason="full reference tree not present")
 
 
 @pytest.fixture(scope="module")
@@ -79,6 +81,7 @@ def test_host_mac_header_walk_matches_reference(ref):
            {k: m.stats[k] for k in ("clear_mode_frames", "encrypted_frames")}
 
 
+@needs_full
 def test_scanner_heuristics_live(ref):
     """oracle/scanner.py against the live TetraSignalDetector on fresh seeds (scanner.py:42-289)."""
     from oracle import scanner as osc
@@ -98,6 +101,7 @@ def test_scanner_heuristics_live(ref):
             assert got[k] == want[k], (case, k, got[k], want[k])
 
 
+@needs_full
 def test_afc_rule_live(ref):
     """oracle.afc_step and the shipped host helper against the reference's own lines (ui/modern.py:5227-5251,
     exec'd from the source text: the module needs PyQt6 and cannot be imported)."""
@@ -123,6 +127,24 @@ def test_afc_rule_live(ref):
         assert oracle.afc_step(freqs, powers, tuned) == want, case
         assert afc_step(freqs, powers, tuned) == want, case
     assert 5 < fired < 40
+
+
+@needs_full
+def test_find_peak_near_live(ref):
+    """oracle.find_peak_near and the shipped helper against ui/modern.py:727-772 exec'd from the source text."""
+    import os, textwrap, types
+    from tests.golden.cases import peak_cases
+    from tetraear_b200.signal import find_peak_near
+    path = os.path.join(ref_bridge.REFERENCE_ROOT, "tetraear", "ui", "modern.py")
+    with open(path) as f:
+        src = textwrap.dedent("".join(f.readlines()[726:772]))
+    assert src.startswith("def find_peak_near(self, freq, search_range_hz):")
+    ns = {"np": np}
+    exec(src, ns)
+    for freqs, powers, click, rng_hz in peak_cases(n=90, seed=4):
+        want = ns["find_peak_near"](types.SimpleNamespace(current_fft=powers, current_freqs=freqs), click, rng_hz)
+        assert oracle.find_peak_near(freqs, powers, click, rng_hz) == want
+        assert find_peak_near(freqs, powers, click, rng_hz) == want
 
 
 def _oracle_stage(method, kw, x):
@@ -166,6 +188,7 @@ def test_process_edge_cases_live(ref):
             assert np.abs(sym - rs).max() <= 1e-12 * max(1.0, np.abs(rs).max()), (i, fs)
 
 
+@needs_full
 def test_band_statistics_other_rates_live(ref):
     """oracle.band_stats against the reference's inline block (ui/modern.py:1953-2010, exec'd from the source text)
     at sample rates where the 25 kHz band is wider than the FFT or leaves no noise bins."""

@@ -16,6 +16,7 @@ DTYPE_C64, DTYPE_C128, DTYPE_SC16 = 0, 1, 2
 MODE_EXACT, MODE_FAST = 0, 1
 OPT_CHAN_F32 = 1
 OPT_PSD_F32 = 2
+OPT_DECIM_TC = 3
 
 
 class Config(C.Structure):
@@ -77,6 +78,7 @@ _PROTOS = {
     "tb200_profile_enable": (_i, [_vp, _i]),
     "tb200_profile_read": (_i, [_vp, _vp, _vp]),
     "tb200_debug_read": (_i, [_vp, _i, _vp, C.c_size_t]),
+    "tb200_debug_tc_design": (_i, [_i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "tb200_psd_batch": (_i, [_vp, _vp, _i64, _i64, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "tb200_detect_batch": (_i, [_vp, _vp, _i, _i, _i64, _i64, _d, _i, _vp, _vp]),
     "tb200_voice_blocks": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _i64, _d, _vp, _vp, _vp]),

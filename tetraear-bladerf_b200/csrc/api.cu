@@ -35,6 +35,9 @@ int ensure_crc_tables(int device);
 int launch_decimate_fast(tb200_handle h, const void *x, int n_chunks, long n, long chunk_stride, int q,
                          const DecimDesign &d, void *dec_out, long n_dec, cudaStream_t st);
 int fast_decimator_supported(int q);
+bool tc_decimator_usable(const void *x, long n, long chunk_stride, int q);
+int launch_decimate_tc(tb200_handle h, const void *x, int n_chunks, long n, long chunk_stride, int q, const DecimDesign &d,
+                       void *dec_out, long n_dec, cudaStream_t st);
 int launch_channel_fast(tb200_handle h, const void *x, int dtype, int n_chunks, long n, long in_stride,
                         const double *freq_off, double fs, double bandwidth, double *filtered, long out_stride,
                         double *phase_partial, double *phase_tail, int sps, int step, cudaStream_t st);
@@ -89,6 +92,8 @@ static size_t carve(tb200_handle h, char *base)
     size_t nf = (size_t)cfg.max_fft;
     h->psd_tables = c.take<double>((2 * nf + 2 * (nf / 2 + nf / 4 + 1)) * sizeof(double));
     h->etsi_taps = c.take<float>(32 * 32 * sizeof(float));
+    h->tc_bmat_bytes = (C && L) ? 2 * 16 * 48 * 16 : 0;           // Bhi + Blo, up to 16 K-chunks x 48 columns x 16 bytes
+    h->tc_bmat = c.take<float>(h->tc_bmat_bytes);
     size_t MC = (size_t)cfg.max_channels;
     h->chan_proto = c.take<float>(MC * 6 * sizeof(float));
     h->chan_tw = c.take<float>((MC + 256) * 2 * sizeof(float));
@@ -220,6 +225,8 @@ extern "C" int tb200_create(const tb200_config *cfg, tb200_handle *out)
     h->max_frames = (int)(h->bits_stride / 250 + 2);
     h->psd_tables_n = 0;
     h->chan_M = 0;
+    h->decim_tc = 1;
+    h->tc_key_q = 0;
     h->ws_bytes = carve(h, nullptr);
     cudaError_t e = cudaMalloc(&h->ws, h->ws_bytes);
     if (e != cudaSuccess) {
@@ -260,7 +267,7 @@ extern "C" int tb200_set_sample_rate(tb200_handle h, double sample_rate)
         return fail(TB200_E_ARG, "tb200_set_sample_rate: %g Hz needs a larger workspace; create a new handle", sample_rate);
     probe.ws = h->ws; probe.ws_bytes = h->ws_bytes; probe.launches = h->launches;
     // every table carved behind the plan-dependent regions moves with n_dec: forget what was uploaded into them
-    probe.psd_tables_n = 0; probe.etsi_taps_fs = 0.0; probe.chan_M = 0;
+    probe.psd_tables_n = 0; probe.etsi_taps_fs = 0.0; probe.chan_M = 0; probe.tc_key_q = 0;
     carve(&probe, (char *)h->ws);
     *h = probe;
     return TB200_OK;
@@ -273,6 +280,7 @@ extern "C" int tb200_set_option(tb200_handle h, int option, int value)
     switch (option) {
     case TB200_OPT_CHAN_F32: h->chan_f32 = value ? 1 : 0; return TB200_OK;
     case TB200_OPT_PSD_F32: h->psd_f32 = value ? 1 : 0; return TB200_OK;
+    case TB200_OPT_DECIM_TC: h->decim_tc = value ? 1 : 0; return TB200_OK;
     default: return fail(TB200_E_ARG, "tb200_set_option: unknown option %d", option);
     }
 }
@@ -326,7 +334,10 @@ extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, 
         if ((size_t)n_chunks * P.n_dec * 2 * esz > h->dec_bytes)
             return fail(TB200_E_ARG, "tb200_process_batch: decimated batch exceeds workspace");
         StageTimer tm(h, TB_STAGE_DECIM, st);
-        if (h->cfg.mode == TB200_MODE_FAST && dtype == TB200_DTYPE_C64 && fast_decimator_supported(P.q)) {
+        if (h->cfg.mode == TB200_MODE_FAST && dtype == TB200_DTYPE_C64 && h->decim_tc &&
+            tc_decimator_usable(d_iq, chunk_len, (long)chunk_stride, P.q)) {
+            rc = launch_decimate_tc(h, d_iq, n_chunks, chunk_len, (long)chunk_stride, P.q, h->dec, h->dec_out, P.n_dec, st);
+        } else if (h->cfg.mode == TB200_MODE_FAST && dtype == TB200_DTYPE_C64 && fast_decimator_supported(P.q)) {
             rc = launch_decimate_fast(h, d_iq, n_chunks, chunk_len, (long)chunk_stride, P.q, h->dec, h->dec_out, P.n_dec, st);
         } else {
             if ((size_t)n_chunks * 2 * (chunk_len + 54) * esz > h->fwd_bytes)
@@ -412,6 +423,8 @@ extern "C" int tb200_decimate(tb200_handle h, const void *d_x, int dtype, int n,
     int rc = get_decim(h, q);
     if (rc) return rc;
     long n_dec = (n + q - 1) / q;
+    if (h->cfg.mode == TB200_MODE_FAST && dtype == TB200_DTYPE_C64 && h->decim_tc && tc_decimator_usable(d_x, n, n + (n & 1), q))
+        return launch_decimate_tc(h, d_x, 1, n, n + (n & 1), q, h->dec, d_out, n_dec, (cudaStream_t)stream);
     if (h->cfg.mode == TB200_MODE_FAST && dtype == TB200_DTYPE_C64 && fast_decimator_supported(q))
         return launch_decimate_fast(h, d_x, 1, n, n, q, h->dec, d_out, n_dec, (cudaStream_t)stream);
     return launch_decimate_exact(h, d_x, dtype, 1, n, n, q, h->dec, h->fwd, d_out, n_dec, (cudaStream_t)stream);

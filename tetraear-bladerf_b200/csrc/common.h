@@ -52,6 +52,7 @@ struct tb200_handle_s {
     // optional per-stage CUDA-event timing (tb200_profile_*): pairs recorded on the launching stream
     int psd_f32;                 // PSD: float32 FFT + dB (dense config mode) instead of float64
     int chan_f32;                // FAST mode: run the channel filter's recurrences in float32 (tb200_set_option)
+    int decim_tc;                // FAST mode: tensor-core decimator (dsp_tc.cu) where its geometry rules hold (default on)
     int profiling;
     std::vector<cudaEvent_t> *prof_ev;      // flat: start, stop, start, stop ...
     std::vector<int> *prof_stage;
@@ -79,6 +80,8 @@ struct tb200_handle_s {
     float *chan_proto, *chan_tw; int chan_M;   // channelizer prototype [6 M], twiddles, M they are for
     double etsi_taps_fs;                      // fs the tap table below was built for (0 = none)
     float *etsi_taps;                         // [32 phases][32 taps] interpolating matched filter
+    float *tc_bmat; size_t tc_bmat_bytes;     // tensor-core decimator weights (Bhi, Blo in the canonical layout)
+    int tc_key_q; float tc_key_sos[24];       // design the weights above were built for (q = 0: none)
     // staging for the *_host entry points
     void *stage_in;   size_t stage_in_bytes;
     void *stage_sc16;                         // int16 IQ staging of the host entry point

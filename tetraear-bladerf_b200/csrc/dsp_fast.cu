@@ -29,77 +29,9 @@
 #include "common.h"
 #include "kernels.h"
 #include "packed.h"
+#include "decim_common.h"
 
 namespace tb200 {
-
-constexpr int FD_R = 3;              // outputs per lane
-constexpr int FD_P = 32 * FD_R;      // outputs per warp pass
-constexpr int FD_W = 8;              // warps per CTA: warp 0 = both halo half-passes, warps 1..7 = storing passes
-constexpr int FD_NS = FD_W - 1;      // storing passes per CTA
-constexpr int FD_NP = FD_W + 1;      // passes staged per tile: left halo, FD_NS storing, right halo
-constexpr int FD_QMAX = 16;
-constexpr int FD_NM = 4;              // modes per FIR sweep (4 = one pass over the tile rows, 2 = two passes, fewer registers)
-constexpr int FD_EDGE_S = 42;        // right-edge term: samples per lane (32 x 42 = 1344; 0.982^1344 = 3e-11)
-
-struct FastDecimParams {
-    float tap[FD_QMAX][4][2];        // p_i^j
-    float lam[4][2];                 // lambda_i = p_i^q
-    float lampow[6][4][2];           // (lambda^R)^(2^s), Kogge-Stone multipliers (s = 5 only for the edge term)
-    float a0[4][2];                  // alpha_i
-    float ap[4][2];                  // alpha_i p_i
-    float aF[FD_R][4][2];            // alpha_i lambda^(r+1)
-    float aB[FD_R][4][2];            // alpha_i p_i lambda^(R-r)
-    // edge kernel (right-end transient), complex as (re, im)
-    float p[4][2];                   // p_i
-    float inv1mp[4][2];              // 1 / (1 - p_i)
-    float ka[4][2];                  // kappa_i = ka_i * xc + sum_j kM[i][j] F_j + kMc[i][j] conj(F_j)
-    float kM[4][4][2];
-    float kMc[4][4][2];
-    float pc[4][2];                  // p_i^(M - n_last)
-    float pS[5][4][2];               // (p_i^S)^(2^s): lane-combine multipliers of the edge kernel
-    float lanepow[32][4][2];         // lambda_i^(R lane): cross-pass carry weights
-    int nstage[4];                   // Kogge-Stone stages that matter for mode i
-};
-
-
-// sample t of the padded signal (ext coordinates, scipy odd_ext with edge 27) continued by the
-// constants the steady-state initial conditions stand for: ext[0] to the left, ext[M-1] to the right
-__device__ __forceinline__ float2 padded_sample(const float2 *__restrict__ x, long n, long t)
-{
-    const long edge = 27;
-    if (t >= edge && t < edge + n) return x[t - edge];
-    float2 e, v;
-    if (t < edge) { e = x[0]; v = x[t < 0 ? edge : edge - t]; }
-    else { long u = t - edge - n; e = x[n - 1]; v = x[u < edge ? n - 2 - u : n - 1 - edge]; }
-    return make_float2(__fsub_rn(__fmul_rn(2.0f, e.x), v.x), __fsub_rn(__fmul_rn(2.0f, e.y), v.y));
-}
-
-// ---- TMA (bulk async copy) of one contiguous tile: global -> shared, completion on an mbarrier ----
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
-{
-    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, unsigned bytes, uint64_t *bar)
-{
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem), ba = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(ba), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(sa), "l"(gmem), "r"(bytes), "r"(ba) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
-{
-    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(a), "r"(parity) : "memory");
-}
-
-
-// Kogge-Stone stages that matter per mode (multiplier >= 1e-9).  The design is a fixed function of q and for every
-// instantiated q (7, 8, 10) the counts are the same; make_fast_params checks them, so the test is resolved at compile time.
-__host__ __device__ constexpr int fd_nstage(int m) { return m == 0 ? 3 : (m == 3 ? 5 : 4); }
 
 // one direction (causal: row0.., taps reversed; anti-causal: next row, taps ascending) for two of the
 // four modes; accumulates Re(alpha * .) into y (I, Q packed) and leaves the pass-end state in `carry`.
@@ -162,7 +94,6 @@ __device__ __forceinline__ void fd_half(const float2 *__restrict__ tile, int row
     }
 }
 
-constexpr int FD_NFIX = 160;           // outputs that receive the right-edge term (0.982^1600 ~ 2e-13)
 
 // kappa_i (packed over I, Q) of one chunk from the staged tile; s_end = tile index of ext[M-1].  One warp.
 __device__ __forceinline__ void fd_kappa(const float2 *__restrict__ tile, int s_end, int lane, const FastDecimParams &K, cp *kappa)
@@ -329,7 +260,7 @@ typedef std::complex<double> cd;
 
 static void put(float dst[2], cd v) { dst[0] = (float)v.real(); dst[1] = (float)v.imag(); }
 
-static int make_fast_params(const DecimDesign &d, int q, long n, long n_dec, FastDecimParams &K)
+int make_fast_params(const DecimDesign &d, int q, long n, long n_dec, FastDecimParams &K)
 {
     cd p8[8], r8[8];
     const double g = (double)d.sos32[0];

@@ -1,0 +1,660 @@
+// dsp_tc.cu — tensor-core ("TC") form of the time-parallel zero-phase decimator of dsp_fast.cu, for
+// scipy.signal.decimate(x, q) as called by SignalProcessor.process
+// (/root/reference/tetraear/signal/processor.py:254).
+//
+// Same filter and the same two-sided modal form as dsp_fast.cu (see its header):
+//     y[k] = 2 Re sum_i alpha_i ( F_i[n_k] + p_i B_i[n_k + 1] ) - right-edge transient,   n_k = 27 + q k,
+// but everything that is a plain linear map of the input samples is one dense contraction on the 5th-generation
+// tensor cores.  A lane owns R = 3 consecutive outputs, i.e. 3 q consecutive input samples (its "slot").  For every
+// slot one tcgen05.mma row produces, from the slot's own samples only,
+//     * Y0[r]   the R outputs with zero state on both sides of the slot (weights h[|t - n_k|] = 2 sum Re alpha p^|d|),
+//     * AF_i    the causal lane aggregate   2 alpha_i     sum p_i^(n_last - t) x[t]    (complex, 4 modes),
+//     * AB_i    the anti-causal aggregate   2 alpha_i p_i sum p_i^(t - t_first) x[t]   (complex, 4 modes),
+// for I and Q at once: the A operand is the interleaved complex64 input exactly as it lies in HBM (one TMA bulk copy
+// per group of 128 slots; the threads re-lay it into the canonical K-major shared-memory layout, one 16-byte chunk
+// of every slot per core-matrix row), B holds the weights with zeros where I would meet Q.  float32 accuracy
+// comes from a split: x = hi + lo with hi, lo representable in TF32, B = Bhi + Blo, three MMAs per k-step
+// (hi*Bhi + lo*Bhi + hi*Blo) accumulated in TMEM (missing term ~2^-22).  What is left for the CUDA cores is the
+// part that is a recurrence: the Kogge-Stone scans of the aggregates over the 32 lanes of a pass (shuffles), the carry
+// of the neighbour pass, and three multiply-adds per output.
+//
+// A CTA streams over a contiguous range of 384-output groups (one MMA of M = 128 slots): the causal carry chains
+// from group to group, the anti-causal carry of a group's last pass arrives one group later (those 96 outputs are
+// held back in registers), chunk ends use the analytic steady state of scipy's constant continuation, so there is
+// no halo inside a range — only one extra group at a range end that falls inside a chunk.
+#include <atomic>
+#include <complex>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include "common.h"
+#include "kernels.h"
+#include "packed.h"
+#include "decim_common.h"
+
+namespace tb200 {
+
+constexpr int TC_R = FD_R;                 // outputs per lane slot
+constexpr int TC_PASS = 32 * TC_R;         // outputs per warp pass
+constexpr int TC_GP = 4;                   // passes per group = MMA rows / 32
+constexpr int TC_GROUP = TC_GP * TC_PASS;  // outputs per group
+constexpr int TC_N = 48;                   // MMA N: 6 zero-state outputs + 16 + 16 aggregate components (+ 10 unused)
+constexpr int TC_TMEM_COLS = 64;
+
+template <int Q> struct TcG {
+    static constexpr int KF = 2 + 2 * TC_R * Q;          // floats of a slot that carry weight positions: 1 pad sample in front
+    static constexpr int K = (KF + 7) / 8 * 8;           // contraction length (multiple of the TF32 MMA K = 8)
+    static constexpr int KC = K / 4;                     // 16-byte chunks per slot
+    static constexpr int A_BYTES = KC * 128 * 16;
+    static constexpr int B_BYTES = KC * TC_N * 16;
+    static constexpr int LEAD = 27 / Q;                  // the stream of a chunk starts LEAD rows before output 0
+    static constexpr int SLOT_FLOATS = 2 * TC_R * Q;     // distance of consecutive slots in the input
+};
+
+struct TcParams {
+    float lampow[5][4][2];        // (lambda^R)^(2^s): Kogge-Stone multipliers
+    float lanepow[32][4][2];      // (lambda^R)^l: cross-pass carry weights
+    float cF[TC_R][4][2];         // lambda^(r+1)
+    float cB[TC_R][4][2];         // lambda^(R-1-r)
+    float initF[4][2];            // 2 alpha / (1 - p): causal state of a constant signal
+    float initB[4][2];            // 2 alpha p / (1 - p)
+};
+
+// ---- PTX wrappers: tcgen05 (TMEM allocation, MMA, commit, load), TMA tensor copy ---------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, unsigned cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, unsigned cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes stored contiguously;
+// lbo = byte distance of the two 16-byte K chunks of one MMA, sbo = byte distance of consecutive 8-row groups
+__device__ __forceinline__ uint64_t umma_desc(unsigned saddr, unsigned lbo, unsigned sbo)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+           (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                   "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                   "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+__device__ __forceinline__ cp cpadd(cp a, cp b)
+{
+    cp o;
+    o.re = make_float2(a.re.x + b.re.x, a.re.y + b.re.y);
+    o.im = make_float2(a.im.x + b.im.x, a.im.y + b.im.y);
+    return o;
+}
+// packed complex (I, Q) state of a constant signal c: v * c for a complex scalar v
+__device__ __forceinline__ cp cp_const(cf v, float2 c)
+{
+    cp o;
+    o.re = make_float2(v.x * c.x, v.x * c.y);
+    o.im = make_float2(v.y * c.x, v.y * c.y);
+    return o;
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------------------
+template <int Q>
+__global__ void __launch_bounds__(TC_GP * 32, 2)
+decim_tc_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_chunks, long n_dec, int gpc, long total_floats,
+                TcParams P, const float *__restrict__ bmat, float2 *__restrict__ dec_out)
+{
+    using G = TcG<Q>;
+    extern __shared__ uint8_t tc_raw[];
+    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tc_raw) + 127) & ~(uintptr_t)127);
+    uint8_t *A_hi = sm, *A_lo = A_hi + G::A_BYTES, *B_hi = A_lo + G::A_BYTES, *B_lo = B_hi + G::B_BYTES;
+    __shared__ __align__(8) uint64_t full_bar, mma_bar, b_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ cp carryF_s[2][TC_GP][4];
+    __shared__ cp carryB_s[2][TC_GP][4];
+    __shared__ cf lanepow_s[32][4];
+
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const long NG = (long)n_chunks * gpc;
+    const long G0 = NG * blockIdx.x / gridDim.x, G1 = NG * (blockIdx.x + 1) / gridDim.x;
+    if (G0 >= G1) return;
+    const long gs = G0 - ((G0 % gpc) ? 1 : 0);       // a range that starts inside a chunk first runs the group before it (causal carry)
+    const long ge = G1 + ((G1 % gpc) ? 1 : 0);       // ... one that ends inside a chunk also the group after it (anti-causal carry)
+
+    lanepow_s[lane][w] = ld2(P.lanepow[lane][w]);
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        mbar_init(&mma_bar, 1);
+        mbar_init(&b_bar, 1);
+    }
+    if (w == 0) tmem_alloc(&tmem_base_s, TC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_s;
+
+    // float offset (from x) of slot (pass 0, lane 0) of group g (a multiple of 4: 16-byte aligned), and whether the whole
+    // raw run of the group lies inside the input so that one bulk copy may fetch it
+    constexpr long RAW_FLOATS = 127L * G::SLOT_FLOATS + G::K;
+    auto group_f0 = [&](long g) -> long {
+        const long c = g / gpc, gi = g - c * gpc;
+        return 2 * (c * chunk_stride + (long)Q * ((long)gi * TC_GROUP - G::LEAD - 1));
+    };
+    auto group_tma = [&](long g) -> bool {
+        const long f0 = group_f0(g);
+        return f0 >= 0 && f0 + RAW_FLOATS <= total_floats;
+    };
+    auto issue_load = [&](long g) {
+        tma_load_1d(A_hi, reinterpret_cast<const float *>(x) + group_f0(g), (unsigned)(RAW_FLOATS * 4), &full_bar);
+    };
+
+    if (tid == 0) {
+        tma_load_1d(B_hi, bmat, 2u * G::B_BYTES, &b_bar);          // weights: Bhi then Blo, already in the canonical layout
+        if (group_tma(gs)) issue_load(gs);
+    }
+
+    const int m = tid;                                              // slot = MMA row = TMEM lane
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    unsigned ph_full = 0, ph_mma = 0;
+    bool pend = false;
+    float2 ypend[TC_R];
+    long pend_k0 = 0, pend_chunk = 0;
+    ypend[0] = ypend[1] = ypend[2] = make_float2(0.f, 0.f);
+
+    for (long g = gs; g < ge; ++g) {
+        const int buf = (int)((g - gs) & 1);
+        const long chunk = g / gpc;
+        const int gi = (int)(g - chunk * gpc);
+        const bool store = g >= G0 && g < G1;
+        const float2 *xc = x + chunk * chunk_stride;
+        const long k0 = (long)gi * TC_GROUP - G::LEAD + (long)w * TC_PASS + (long)lane * TC_R;   // first output of this slot
+        const long i0 = 1 + (long)Q * (k0 - 1);                     // chunk sample under weight position 0 (slot float 2)
+        const bool via_tma = group_tma(g);
+
+        // ---- A operand.  The 128 slots of a group are one contiguous run of the input (slot m starts SLOT_FLOATS * m
+        // floats in, slots overlap by the pad floats): ONE bulk copy stages it raw in the A_hi region; every thread
+        // then takes its slot into registers, and after a barrier writes it back in the canonical K-major layout
+        // (16-byte chunk kc of slot m at kc * 2048 + m * 16), split into hi = x rounded to TF32 and lo = x - hi (exact).
+        if (via_tma) {
+            mbar_wait(&full_bar, ph_full);
+            ph_full ^= 1;
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < G::K / 2; ++j) {                     // range at an end of the whole input: plain loads
+                const long i = i0 - 1 + j;
+                const float2 v = (i >= 0 && i < n) ? xc[i] : padded_sample(xc, n, 27 + i);
+                *reinterpret_cast<float2 *>(A_hi + m * (G::SLOT_FLOATS * 4) + j * 8) = v;
+            }
+            __syncthreads();
+        }
+        float4 v[G::KC];
+#pragma unroll
+        for (int kc = 0; kc < G::KC; ++kc) v[kc] = *reinterpret_cast<const float4 *>(A_hi + m * (G::SLOT_FLOATS * 4) + kc * 16);
+        __syncthreads();                                             // everybody holds its slot: the raw bytes may be overwritten
+#pragma unroll
+        for (int kc = 0; kc < G::KC; ++kc) {
+            float4 hi, lo;
+            hi.x = __uint_as_float((__float_as_uint(v[kc].x) + 0x1000u) & 0xFFFFE000u);
+            hi.y = __uint_as_float((__float_as_uint(v[kc].y) + 0x1000u) & 0xFFFFE000u);
+            hi.z = __uint_as_float((__float_as_uint(v[kc].z) + 0x1000u) & 0xFFFFE000u);
+            hi.w = __uint_as_float((__float_as_uint(v[kc].w) + 0x1000u) & 0xFFFFE000u);
+            lo.x = v[kc].x - hi.x; lo.y = v[kc].y - hi.y; lo.z = v[kc].z - hi.z; lo.w = v[kc].w - hi.w;
+            *reinterpret_cast<float4 *>(A_hi + kc * 2048 + m * 16) = hi;
+            *reinterpret_cast<float4 *>(A_lo + kc * 2048 + m * 16) = lo;
+        }
+        if (via_tma && (i0 - 1 < 0 || i0 - 1 + G::K / 2 > n)) {     // slot reaches outside the chunk: scipy's padded signal there
+#pragma unroll 1
+            for (int j = 0; j < G::K / 2; ++j) {
+                const long i = i0 - 1 + j;
+                if (i >= 0 && i < n) continue;
+                const float2 e = padded_sample(xc, n, 27 + i);
+                float2 hi, lo;
+                hi.x = __uint_as_float((__float_as_uint(e.x) + 0x1000u) & 0xFFFFE000u);
+                hi.y = __uint_as_float((__float_as_uint(e.y) + 0x1000u) & 0xFFFFE000u);
+                lo.x = e.x - hi.x; lo.y = e.y - hi.y;
+                *reinterpret_cast<float2 *>(A_hi + (j >> 1) * 2048 + m * 16 + (j & 1) * 8) = hi;
+                *reinterpret_cast<float2 *>(A_lo + (j >> 1) * 2048 + m * 16 + (j & 1) * 8) = lo;
+            }
+        }
+        fence_async_smem();                                         // generic-proxy writes -> visible to the tensor core
+        __syncthreads();
+
+        // ---- one thread issues the MMAs of the group: D[128 x 48] = sum over k-steps of hi*Bhi + lo*Bhi + hi*Blo
+        if (tid == 0) {
+            if (g == gs) mbar_wait(&b_bar, 0);
+            tc_fence_after();
+            const unsigned a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b_hi = smem_u32(B_hi), b_lo = smem_u32(B_lo);
+#pragma unroll
+            for (int ks = 0; ks < G::K / 8; ++ks) {
+                const uint64_t dah = umma_desc(a_hi + ks * 4096, 2048, 128), dal = umma_desc(a_lo + ks * 4096, 2048, 128);
+                const uint64_t dbh = umma_desc(b_hi + ks * 2 * TC_N * 16, TC_N * 16, 128), dbl = umma_desc(b_lo + ks * 2 * TC_N * 16, TC_N * 16, 128);
+                umma_tf32(tmem_d, dah, dbh, idesc, ks > 0 ? 1u : 0u);
+                umma_tf32(tmem_d, dal, dbh, idesc, 1u);
+                umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+            }
+            umma_commit(&mma_bar);
+        }
+        mbar_wait(&mma_bar, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        if (tid == 0 && g + 1 < ge && group_tma(g + 1)) issue_load(g + 1);     // the MMAs are done with A_hi: prefetch the next group
+
+        // ---- accumulators of this slot: TMEM lane m, columns 0..39
+        uint32_t va[32], vb[8];
+        const uint32_t taddr = tmem_d + ((uint32_t)(w * 32) << 16);
+        tmem_ld32(taddr, va);
+        tmem_ld8(taddr + 32, vb);
+        tmem_ld_wait();
+        tc_fence_before();
+        float2 y[TC_R];
+        cp aF[4], aB[4];
+#pragma unroll
+        for (int r = 0; r < TC_R; ++r) y[r] = make_float2(__uint_as_float(va[2 * r]), __uint_as_float(va[2 * r + 1]));
+#pragma unroll
+        for (int mm = 0; mm < 4; ++mm) {
+            aF[mm].re = make_float2(__uint_as_float(va[6 + 4 * mm]), __uint_as_float(va[7 + 4 * mm]));
+            aF[mm].im = make_float2(__uint_as_float(va[8 + 4 * mm]), __uint_as_float(va[9 + 4 * mm]));
+        }
+#pragma unroll
+        for (int mm = 0; mm < 4; ++mm) {
+            const int c = 22 + 4 * mm;
+            auto col = [&](int cc) -> float { return __uint_as_float(cc < 32 ? va[cc < 32 ? cc : 0] : vb[cc >= 32 ? cc - 32 : 0]); };
+            aB[mm].re = make_float2(col(c), col(c + 1));
+            aB[mm].im = make_float2(col(c + 2), col(c + 3));
+        }
+
+        // ---- Kogge-Stone scans of the aggregates over the lanes of the pass (zero state at the pass ends)
+        cp tF[4], tB[4];
+        const float2 zero2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int mm = 0; mm < 4; ++mm) {
+            cp a = aF[mm], b = aB[mm];
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                if (s >= fd_nstage(mm)) continue;
+                cp oa, ob;
+                oa.re = shfl2_up(a.re, 1 << s); oa.im = shfl2_up(a.im, 1 << s);
+                ob.re = shfl2_down(b.re, 1 << s); ob.im = shfl2_down(b.im, 1 << s);
+                cf ga = ld2(P.lampow[s][mm]), gb = ga;
+                if (lane < (1 << s)) ga.x = ga.y = 0.f;
+                if (lane + (1 << s) >= 32) gb.x = gb.y = 0.f;
+                a = cpfma(ga, oa, a);
+                b = cpfma(gb, ob, b);
+            }
+            if (lane == 31) carryF_s[buf][w][mm] = a;
+            if (lane == 0) carryB_s[buf][w][mm] = b;
+            tF[mm].re = shfl2_up(a.re, 1); tF[mm].im = shfl2_up(a.im, 1);
+            tB[mm].re = shfl2_down(b.re, 1); tB[mm].im = shfl2_down(b.im, 1);
+            if (lane == 0) tF[mm].re = tF[mm].im = zero2;
+            if (lane == 31) tB[mm].re = tB[mm].im = zero2;
+        }
+        __syncthreads();
+
+        // ---- the pass held back from the previous group gets its anti-causal carry from this group's first pass
+        if (pend) {
+            float2 *out = dec_out + pend_chunk * n_dec;
+#pragma unroll
+            for (int mm = 0; mm < 4; ++mm) {
+                const cp gB = cpmul(lanepow_s[31 - lane][mm], carryB_s[buf][0][mm]);
+#pragma unroll
+                for (int r = 0; r < TC_R; ++r) ypend[r] = re_acc(ld2(P.cB[r][mm]), gB, ypend[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < TC_R; ++r) {
+                const long k = pend_k0 + r;
+                if (k >= 0 && k < n_dec) out[k] = ypend[r];
+            }
+            pend = false;
+        }
+
+        // ---- carries across passes: causal from the pass before (previous group / analytic at a chunk start),
+        // anti-causal from the pass after (analytic at a chunk end; the last pass of any other group waits one group)
+        const bool last_group = gi == gpc - 1;
+        const bool wait_b = (w == TC_GP - 1) && !last_group;
+        float2 c0 = zero2, cM = zero2;
+        if (w == 0 && gi == 0) c0 = padded_sample(xc, n, 0);
+        if (w == TC_GP - 1 && last_group) cM = padded_sample(xc, n, n + 53);
+#pragma unroll
+        for (int mm = 0; mm < 4; ++mm) {
+            cp inF, inB;
+            inF.re = inF.im = inB.re = inB.im = zero2;
+            if (w > 0) inF = carryF_s[buf][w - 1][mm];
+            else if (gi == 0) inF = cp_const(ld2(P.initF[mm]), c0);
+            else if (g > gs) inF = carryF_s[buf ^ 1][TC_GP - 1][mm];
+            if (w < TC_GP - 1) inB = carryB_s[buf][w + 1][mm];
+            else if (last_group) inB = cp_const(ld2(P.initB[mm]), cM);
+            const cp sF = cpadd(tF[mm], cpmul(lanepow_s[lane][mm], inF));
+            const cp sB = cpadd(tB[mm], cpmul(lanepow_s[31 - lane][mm], inB));
+#pragma unroll
+            for (int r = 0; r < TC_R; ++r) y[r] = re_acc(ld2(P.cB[r][mm]), sB, re_acc(ld2(P.cF[r][mm]), sF, y[r]));
+        }
+        if (store) {
+            if (wait_b) {
+                pend = true; pend_k0 = k0; pend_chunk = chunk;
+#pragma unroll
+                for (int r = 0; r < TC_R; ++r) ypend[r] = y[r];
+            } else {
+                float2 *out = dec_out + chunk * n_dec;
+#pragma unroll
+                for (int r = 0; r < TC_R; ++r) {
+                    const long k = k0 + r;
+                    if (k >= 0 && k < n_dec) out[k] = y[r];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (w == 0) tmem_dealloc(tmem_d, TC_TMEM_COLS);
+}
+
+// ---- right-edge transient of scipy's backward pass: y[k] -= 2 Re sum_i kappa_i pc_i lambda_i^(n_dec-1-k) on the last
+// FD_NFIX outputs of every chunk (dsp_fast.cu header); kappa_i from F_i[M-1] = sum_k p_i^k ext[M-1-k].  One warp per chunk.
+__global__ void __launch_bounds__(32)
+decim_tc_edge_kernel(const float2 *__restrict__ x, long n, long chunk_stride, long n_dec, FastDecimParams K, float2 *__restrict__ dec_out)
+{
+    const int lane = threadIdx.x;
+    const float2 *xc = x + (long)blockIdx.x * chunk_stride;
+    cp S[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S[j].re = S[j].im = make_float2(0.f, 0.f);
+    const long t_end = n + 53;
+    const long t0 = t_end - 32 * FD_EDGE_S + 1 + (long)lane * FD_EDGE_S;
+    for (int i = 0; i < FD_EDGE_S; ++i) {
+        const float2 e = padded_sample(xc, n, t0 + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cp nx = cpmul(ld2(K.p[j]), S[j]);
+            nx.re.x += e.x; nx.re.y += e.y;
+            S[j] = nx;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int st = 0; st < 5; ++st) {
+            cp o;
+            o.re = shfl2_up(S[j].re, 1 << st); o.im = shfl2_up(S[j].im, 1 << st);
+            if (lane >= (1 << st)) S[j] = cpfma(ld2(K.pS[st][j]), o, S[j]);
+        }
+    }
+    cp kappa[4];
+    {
+        const float2 xl = padded_sample(xc, n, t_end);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            cp k;
+            k.re = make_float2(K.ka[i][0] * xl.x, K.ka[i][0] * xl.y);
+            k.im = make_float2(K.ka[i][1] * xl.x, K.ka[i][1] * xl.y);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                k = cpfma(ld2(K.kM[i][j]), S[j], k);
+                cp cj; cj.re = S[j].re; cj.im = make_float2(-S[j].im.x, -S[j].im.y);
+                k = cpfma(ld2(K.kMc[i][j]), cj, k);
+            }
+            // lane 31 holds F_j[M-1]: broadcast its kappa
+            kappa[i].re = make_float2(__shfl_sync(0xffffffffu, k.re.x, 31), __shfl_sync(0xffffffffu, k.re.y, 31));
+            kappa[i].im = make_float2(__shfl_sync(0xffffffffu, k.im.x, 31), __shfl_sync(0xffffffffu, k.im.y, 31));
+        }
+    }
+    float2 *out = dec_out + (long)blockIdx.x * n_dec;
+    for (int mm = lane; mm < FD_NFIX; mm += 32) {
+        const long k = n_dec - 1 - mm;
+        if (k < 0) break;
+        const int a = mm / FD_R, b = mm - a * FD_R;
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            cf g = ld2(K.pc[m]);
+#pragma unroll
+            for (int sft = 0; sft < 6; ++sft) if (a & (1 << sft)) g = cmulf(g, ld2(K.lampow[sft][m]));
+            const cf lam = ld2(K.lam[m]);
+            for (int i = 0; i < b; ++i) g = cmulf(g, lam);
+            acc = re_acc(g, kappa[m], acc);
+        }
+        float2 v = out[k];
+        v.x -= 2.0f * acc.x; v.y -= 2.0f * acc.y;
+        out[k] = v;
+    }
+}
+
+// ---- host: weights and carry constants --------------------------------------------------------------------------
+typedef std::complex<double> cd;
+static void putc(float dst[2], cd v) { dst[0] = (float)v.real(); dst[1] = (float)v.imag(); }
+
+static float tf32_round(float v)
+{
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    memcpy(&v, &u, 4);
+    return v;
+}
+
+// modal constants (poles p_i, alpha_i of H(z)H(1/z)) of the float32-rounded design, as in make_fast_params
+static int tc_modes(const DecimDesign &d, cd p4[4], cd alpha[4])
+{
+    cd p8[8], r8[8];
+    const double g = (double)d.sos32[0];
+    for (int s = 0; s < 4; ++s) {
+        double a1 = (double)d.sos32[6 * s + 4], a2 = (double)d.sos32[6 * s + 5];
+        double disc = a1 * a1 - 4 * a2;
+        if (!(disc < 0)) return fail(TB200_E_ARG, "tc decimator: real pole pair in section %d", s);
+        p8[s] = cd(-a1 / 2, std::sqrt(-disc) / 2);
+        p8[s + 4] = std::conj(p8[s]);
+    }
+    cd prodp(1.0, 0.0);
+    for (int i = 0; i < 8; ++i) prodp *= p8[i];
+    const double dd = g / prodp.real();
+    for (int i = 0; i < 8; ++i) {
+        cd num = g * std::pow(1.0 + 1.0 / p8[i], 8), den(1.0, 0.0);
+        for (int j = 0; j < 8; ++j) if (j != i) den *= (1.0 - p8[j] / p8[i]);
+        r8[i] = num / den;
+    }
+    for (int j = 0; j < 4; ++j) {
+        cd acc(dd, 0.0);
+        for (int i = 0; i < 8; ++i) acc += r8[i] / (1.0 - p8[i] * p8[j]);
+        alpha[j] = r8[j] * acc;
+        p4[j] = p8[j];
+    }
+    return TB200_OK;
+}
+
+// B[k][n] in double (row-major, K x TC_N), the canonical-layout TF32 split (bhi, blo: [KC][TC_N][4] floats each) and the
+// carry constants for decimation factor q.  K_out = contraction length.
+static int tc_design(const DecimDesign &d, int q, std::vector<double> &B, std::vector<float> &bhi, std::vector<float> &blo,
+                     TcParams &P, int &K_out)
+{
+    cd p[4], alpha[4];
+    int rc = tc_modes(d, p, alpha);
+    if (rc) return rc;
+    const int KF = 2 + 2 * TC_R * q, K = (KF + 7) / 8 * 8, KC = K / 4;
+    K_out = K;
+    B.assign((size_t)K * TC_N, 0.0);
+    for (int f = 2; f < 2 + 2 * TC_R * q; ++f) {
+        const int j = f / 2 - 1, comp = f & 1, s = j / q, c = j % q;
+        double *row = &B[(size_t)f * TC_N];
+        for (int r = 0; r < TC_R; ++r) {                   // zero-state outputs: h[|t - n_k|]
+            const int delta = q * (s - r) - (q - 1) + c;
+            double hsum = 0.0;
+            for (int i = 0; i < 4; ++i) hsum += 2.0 * (alpha[i] * std::pow(p[i], std::abs(delta))).real();
+            row[2 * r + comp] = hsum;
+        }
+        for (int i = 0; i < 4; ++i) {
+            const cd vf = 2.0 * alpha[i] * std::pow(p[i], q * (TC_R - 1 - s) + (q - 1) - c);
+            const cd vb = 2.0 * alpha[i] * std::pow(p[i], q * s + c + 1);
+            row[6 + 4 * i + 0 + comp] = vf.real();
+            row[6 + 4 * i + 2 + comp] = vf.imag();
+            row[22 + 4 * i + 0 + comp] = vb.real();
+            row[22 + 4 * i + 2 + comp] = vb.imag();
+        }
+    }
+    bhi.assign((size_t)KC * TC_N * 4, 0.f);
+    blo.assign((size_t)KC * TC_N * 4, 0.f);
+    for (int k = 0; k < K; ++k)
+        for (int nn = 0; nn < TC_N; ++nn) {
+            const double v = B[(size_t)k * TC_N + nn];
+            const float hi = tf32_round((float)v);
+            const float lo = tf32_round((float)(v - (double)hi));
+            const size_t at = ((size_t)(k / 4) * TC_N + nn) * 4 + (k & 3);
+            bhi[at] = hi; blo[at] = lo;
+        }
+    memset(&P, 0, sizeof(P));
+    for (int i = 0; i < 4; ++i) {
+        const cd lam = std::pow(p[i], q), lr = std::pow(lam, TC_R);
+        cd v = lr;
+        int nst = 0;
+        for (int s = 0; s < 5; ++s) { putc(P.lampow[s][i], v); if (std::abs(v) >= 1e-9) nst = s + 1; v *= v; }
+        if (nst > fd_nstage(i)) return fail(TB200_E_ARG, "tc decimator: mode %d of q=%d needs %d scan stages, kernel has %d", i, q, nst, fd_nstage(i));
+        for (int l = 0; l < 32; ++l) putc(P.lanepow[l][i], std::pow(lr, l));
+        for (int r = 0; r < TC_R; ++r) { putc(P.cF[r][i], std::pow(lam, r + 1)); putc(P.cB[r][i], std::pow(lam, TC_R - 1 - r)); }
+        putc(P.initF[i], 2.0 * alpha[i] / (1.0 - p[i]));
+        putc(P.initB[i], 2.0 * alpha[i] * p[i] / (1.0 - p[i]));
+    }
+    return TB200_OK;
+}
+
+int tc_decimator_supported(int q) { return q == 10 || q == 8; }
+
+template <int Q>
+static int launch_tc_q(tb200_handle h, const void *x, int n_chunks, long n, long chunk_stride, long n_dec,
+                       long total_floats, const TcParams &P, const float *bmat, const FastDecimParams &KE, void *dec_out,
+                       cudaStream_t st)
+{
+    using G = TcG<Q>;
+    const size_t smem = 2 * (size_t)G::A_BYTES + 2 * (size_t)G::B_BYTES + 128;
+    static std::atomic<bool> attr_set[64];
+    static std::atomic<int> n_sm[64];
+    const int dv = h->cfg.device & 63;
+    if (!attr_set[dv]) {
+        cudaError_t e = cudaFuncSetAttribute(decim_tc_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(decim_tc): %s", cudaGetErrorString(e));
+        int sms = 0;
+        TB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+        n_sm[dv] = sms > 0 ? sms : 148;
+        attr_set[dv] = true;
+    }
+    const int gpc = (int)((n_dec + G::LEAD + 4 + TC_GROUP - 1) / TC_GROUP);
+    const long NG = (long)n_chunks * gpc;
+    long grid = 2L * n_sm[dv];                      // two resident CTAs per SM (88 KB of shared memory each), one range per CTA
+    if (grid > NG) grid = NG;
+    decim_tc_kernel<Q><<<(unsigned)grid, TC_GP * 32, smem, st>>>((const float2 *)x, n, chunk_stride, n_chunks, n_dec, gpc,
+                                                               total_floats, P, bmat, (float2 *)dec_out);
+    TB_LAUNCH_CHECK(h);
+    decim_tc_edge_kernel<<<n_chunks, 32, 0, st>>>((const float2 *)x, n, chunk_stride, n_dec, KE, (float2 *)dec_out);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+// eligibility beyond q: the streaming form needs a few groups per chunk and 16-byte aligned slots
+bool tc_decimator_usable(const void *x, long n, long chunk_stride, int q)
+{
+    return tc_decimator_supported(q) && n >= 4L * TC_GROUP * q && n < (1L << 28) && (chunk_stride & 1) == 0 &&
+           (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+}
+
+int launch_decimate_tc(tb200_handle h, const void *x, int n_chunks, long n, long chunk_stride, int q, const DecimDesign &d,
+                       void *dec_out, long n_dec, cudaStream_t st)
+{
+    if (!tc_decimator_usable(x, n, chunk_stride, q)) return fail(TB200_E_ARG, "tc decimator: unsupported geometry");
+    // constants depend on (design, q, n): cached; the weight matrices live in the handle's workspace
+    struct Cached { int q; long n, n_dec; float sos[24]; TcParams P; FastDecimParams KE; std::vector<float> bhi, blo; };
+    static std::mutex mu;
+    static std::vector<Cached> cache;
+    TcParams P;
+    FastDecimParams KE;
+    const Cached *hit = nullptr;
+    std::unique_lock<std::mutex> lk(mu);
+    for (const Cached &c : cache)
+        if (c.q == q && c.n == n && c.n_dec == n_dec && !memcmp(c.sos, d.sos32, sizeof(c.sos))) { hit = &c; break; }
+    if (!hit) {
+        Cached c;
+        c.q = q; c.n = n; c.n_dec = n_dec;
+        memcpy(c.sos, d.sos32, sizeof(c.sos));
+        std::vector<double> B;
+        int K = 0;
+        int rc = tc_design(d, q, B, c.bhi, c.blo, c.P, K);
+        if (rc) return rc;
+        rc = make_fast_params(d, q, n, n_dec, c.KE);
+        if (rc) return rc;
+        if (cache.size() >= 8) cache.erase(cache.begin());
+        cache.push_back(std::move(c));
+        hit = &cache.back();
+    }
+    P = hit->P; KE = hit->KE;
+    const size_t bbytes = hit->bhi.size() * sizeof(float);
+    if (2 * bbytes > h->tc_bmat_bytes) return fail(TB200_E_ARG, "tc decimator: weight matrices exceed the workspace");
+    if (!(h->tc_key_q == q && !memcmp(h->tc_key_sos, d.sos32, sizeof(h->tc_key_sos)))) {
+        // first use of this design on this handle: upload Bhi, Blo (synchronous copies from pageable memory)
+        TB_CUDA(cudaMemcpyAsync(h->tc_bmat, hit->bhi.data(), bbytes, cudaMemcpyHostToDevice, st));
+        TB_CUDA(cudaMemcpyAsync((char *)h->tc_bmat + bbytes, hit->blo.data(), bbytes, cudaMemcpyHostToDevice, st));
+        TB_CUDA(cudaStreamSynchronize(st));
+        h->tc_key_q = q;
+        memcpy(h->tc_key_sos, d.sos32, sizeof(h->tc_key_sos));
+    }
+    lk.unlock();
+    const long total_floats = 2 * ((long)(n_chunks - 1) * chunk_stride + n);
+    if (q == 10) return launch_tc_q<10>(h, x, n_chunks, n, chunk_stride, n_dec, total_floats, P, h->tc_bmat, KE, dec_out, st);
+    return launch_tc_q<8>(h, x, n_chunks, n, chunk_stride, n_dec, total_floats, P, h->tc_bmat, KE, dec_out, st);
+}
+
+}  // namespace tb200
+
+// Debugging / test aid: the weight matrix and constants of the tensor-core decimator for factor q (host only, no device
+// needed): B as K x 48 doubles (row-major), the TF32 split in the canonical layout, TcParams as 4-byte floats.
+extern "C" int tb200_debug_tc_design(int q, double *B, int b_capacity, float *bhi, float *blo, int split_capacity, float *params,
+                                     int params_capacity, int *K_out)
+{
+    using namespace tb200;
+    if (!tc_decimator_supported(q) || !K_out) return fail(TB200_E_ARG, "tb200_debug_tc_design: q=%d not supported", q);
+    DecimDesign d;
+    int rc = tb200_design_decimator(q, d.sos64, d.zi64, d.sos32, d.zi32);
+    if (rc) return rc;
+    std::vector<double> Bv;
+    std::vector<float> hi, lo;
+    TcParams P;
+    int K = 0;
+    rc = tc_design(d, q, Bv, hi, lo, P, K);
+    if (rc) return rc;
+    *K_out = K;
+    if (B) { if ((size_t)b_capacity < Bv.size()) return fail(TB200_E_ARG, "tb200_debug_tc_design: B capacity"); memcpy(B, Bv.data(), Bv.size() * sizeof(double)); }
+    if (bhi && blo) {
+        if ((size_t)split_capacity < hi.size()) return fail(TB200_E_ARG, "tb200_debug_tc_design: split capacity");
+        memcpy(bhi, hi.data(), hi.size() * sizeof(float));
+        memcpy(blo, lo.data(), lo.size() * sizeof(float));
+    }
+    if (params) {
+        if ((size_t)params_capacity * sizeof(float) < sizeof(P)) return fail(TB200_E_ARG, "tb200_debug_tc_design: params capacity");
+        memcpy(params, &P, sizeof(P));
+    }
+    return TB200_OK;
+}
