@@ -33,6 +33,7 @@ if ROOT not in sys.path:
 CHUNK = 131072
 FS = 2.4e6
 C1_CHUNKS = 183          # floor(24e6 / 131072)
+DECIM_TRAFFIC_BYTES = None   # filled from the ncu capture of the round's decimator kernel (profiles/)
 
 
 def host_cores():
@@ -73,20 +74,58 @@ def _cpu_worker(args):
     return n, crc, time.perf_counter() - t0
 
 
-def cpu_run(x, cores, reps=1):
-    """Oracle port over the chunks of x with `cores` worker processes.  Returns (Msamples/s, bursts/s, wall s)."""
+_REF = None
+
+
+def _ref_worker(args):
+    """process + decode of a list of chunks with the UNMODIFIED reference classes (oracle/_ref, staged by
+    oracle/make_ref.py); returns (samples, crc_pass, seconds)."""
+    global _REF
+    import logging
+    logging.disable(logging.CRITICAL)
+    if _REF is None:
+        from oracle import ref_bridge
+        _REF = ref_bridge.load()
+    SP, TD, _ = _REF
+    chunks, fs = args
+    t0 = time.perf_counter()
+    crc = 0
+    n = 0
+    for ch in chunks:
+        sp = SP(fs)
+        d = sp.process(ch, 0)
+        dec = TD(auto_decrypt=False)
+        if len(d) >= 255:                      # the receive loop's rule, ui/modern.py:2074-2077
+            dec.decode(d)
+        crc += dec.protocol_parser.stats["crc_pass"]
+        n += len(ch)
+    return n, crc, time.perf_counter() - t0
+
+
+def reference_available():
+    from oracle import ref_bridge
+    return ref_bridge.available()
+
+
+def cpu_run(x, cores, reps=1, kind="port"):
+    """The CPU implementation of the path over the chunks of x with `cores` worker processes: kind "reference" = the
+    unmodified reference classes, "port" = the oracle's C + numpy restatement.  Returns (Msamples/s, bursts/s, wall s)."""
     import multiprocessing as mp
-    from oracle import oracle
-    oracle.lib()                              # compile the C part before forking
+    worker = _cpu_worker
+    if kind == "reference":
+        worker = _ref_worker
+    else:
+        from oracle import oracle
+        oracle.lib()                          # compile the C part before forking
     parts = [list(x[i::cores]) for i in range(cores)]
     parts = [p for p in parts if p]
     best = None
     ctx = mp.get_context("fork")
     with ctx.Pool(len(parts)) as pool:
-        pool.map(_cpu_worker, [([p[0][:4096]], FS) for p in parts])      # warm the workers
+        pool.map(worker, [([p[0][:4096]], FS) for p in parts])      # warm the workers
         for _ in range(reps):
             t0 = time.perf_counter()
-            res = pool.map(_cpu_worker, [(p, FS) for p in parts])
+            res = pool.map(worker, [(p, FS) for p in parts])
             wall = time.perf_counter() - t0
             n = sum(r[0] for r in res)
             crc = sum(r[1] for r in res)
@@ -279,26 +318,70 @@ def run_b200(args):
     sync_all()
     ms_e2e16 = t2.elapsed_time(t3)
 
-    # ---- the same device-resident loop with the float64 channel filter ('fast'), for comparison with the default
+    # ---- the same device-resident loop in the other time-parallel arithmetic (float32 channel filter when the headline
+    # runs the float64 one, and vice versa), timed the same way (CUDA-graph replay on two streams)
     alt = None
-    if args.mode == "fast32" and world == 1 and not args.no_extras:
-        pipe64 = pipeline.ReceivePipeline(FS, CHUNK, max_chunks=n_chunks, mode="fast", device=local_rank, n_lanes=args.lanes)
-        for _ in range(3):
-            pipe64.run_device(dev)
+    alt_mode = {"fast": "fast32", "fast32": "fast", "fast-tc": "fast32-tc", "fast32-tc": "fast-tc"}.get(args.mode)
+    if alt_mode and world == 1 and not args.no_extras:
+        pa = pipeline.ReceivePipeline(FS, CHUNK, max_chunks=n_chunks, mode=alt_mode, device=local_rank, n_lanes=args.lanes)
+        pb = pipeline.ReceivePipeline(FS, CHUNK, max_chunks=n_chunks, mode=alt_mode, device=local_rank, n_lanes=args.lanes)
+        k_alt = min(args.steps, 200)
+        try:
+            ga = [pa.capture(dev), pb.capture(dev)]
+            gst = [torch.cuda.Stream(device=local_rank), torch.cuda.Stream(device=local_rank)]
+
+            def alt_steps(k):
+                for gs_ in gst:
+                    gs_.wait_stream(stream)
+                for i in range(k):
+                    with torch.cuda.stream(gst[i & 1]):
+                        ga[i & 1].replay()
+                for gs_ in gst:
+                    stream.wait_stream(gs_)
+        except Exception:
+            torch.cuda.synchronize()
+
+            def alt_steps(k):
+                for _ in range(k):
+                    pa.run_device(dev, join=False)
+                pa.join()
+        alt_steps(5)
         sync_all()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k64 = min(args.steps, 50)
         a0.record(stream)
-        for _ in range(k64):
-            pipe64.run_device(dev, join=False)
-        pipe64.join()
+        alt_steps(k_alt)
         a1.record(stream)
         sync_all()
-        ms64 = a0.elapsed_time(a1) / k64
-        alt = {"value": round(samples_per_step / (ms64 / 1e3) / 1e6, 3), "unit": "Msamples/s", "ms_per_step": round(ms64, 4),
-               "note": "mode 'fast': channel filter recurrences in float64 (1e-11 from scipy's filtfilt) instead of float32 (3e-6)"}
-        del pipe64
+        ms_alt = a0.elapsed_time(a1) / k_alt
+        alt = {"mode": alt_mode, "value": round(samples_per_step / (ms_alt / 1e3) / 1e6, 3), "unit": "Msamples/s",
+               "ms_per_step": round(ms_alt, 4),
+               "path_frac": round((samples_per_step * 8.0 + n_chunks * pipe.plan.max_symbols) / (ms_alt / 1e3) / 1e9 / measured_peaks()[0], 5),
+               "note": "fast32 = channel filter recurrences in float32 (3e-6 from scipy's filtfilt) instead of float64 (1e-11); same "
+                       "tensor-core float32 decimator; dibits / frames / CRC identical on all 183 chunks (tests/test_gpu_fullsize.py)"}
+        del pa, pb
         torch.cuda.empty_cache()
+
+    # ---- end to end through the mirrored CLASS API, one chunk per call like CaptureThread.run (ui/modern.py:1919-2077):
+    # SignalProcessor.process(numpy chunk) -> TetraDecoder.decode(dibits), host numpy in and out, H2D/D2H inside
+    class_api = None
+    if world == 1 and not args.no_extras:
+        from tetraear_b200.signal import SignalProcessor
+        from tetraear_b200.core import TetraDecoder
+        sp, dec = SignalProcessor(FS, mode=args.mode, device=local_rank), TetraDecoder(auto_decrypt=False, device=local_rank)
+        for c in range(3):
+            dec.decode(sp.process(x[c], 0.0))
+        torch.cuda.synchronize()
+        t_a = time.perf_counter()
+        nfr_class = 0
+        for c in range(n_chunks):
+            nfr_class += len(dec.decode(sp.process(x[c], 0.0)))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t_a
+        class_api = {"value": round(samples_per_step / dt / 1e6, 3), "unit": "Msamples/s", "ms_per_chunk": round(dt / n_chunks * 1e3, 4),
+                     "frames": nfr_class, "h2d_bytes_per_call": CHUNK * 8,
+                     "note": "per-chunk SignalProcessor.process + TetraDecoder.decode (the reference's own call pattern), wall clock, "
+                             "incl. the host MAC header walk per frame"}
+        del sp, dec
 
     # ---- per-stage device time for the roofline (separate pass so the events do not sit in `value`)
     # (single lane: the per-stage events of concurrent lanes would overlap and double count)
@@ -340,29 +423,46 @@ def run_b200(args):
     path_bytes = samples_per_step * 8.0 + n_chunks * (pipe.plan.max_symbols) * 1.0
     step_ms = ms / args.steps
 
-    # ---- CPU baseline: oracle port on a bounded sample, rank 0 only at N=1
+    # ---- CPU baseline: the unmodified reference (oracle/_ref) on a bounded sample, rank 0 only at N=1; the oracle's
+    # C + numpy port alongside
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = host_cores()
-        sample_chunks = n_chunks
-        one = cpu_run(x[:8], 1)
-        many = cpu_run(x[:sample_chunks], cores)
-        cpu = {"value": round(many[0], 3), "unit": "Msamples/s", "cores": cores, "kind": "port",
-               "sample": f"{sample_chunks} of {n_chunks} chunks (131072 samples each) of the same capture through "
-                         f"oracle.process + oracle.decode, {cores} worker processes; 1-core: {one[0]:.3f} Msamples/s over 8 chunks",
-               "one_core_value": round(one[0], 3), "bursts_per_s": round(many[1], 1)}
+        port_one = cpu_run(x[:8], 1)
+        port_many = cpu_run(x, cores)
+        if reference_available():
+            one = cpu_run(x[:4], 1, kind="reference")
+            many = cpu_run(x, cores, kind="reference")
+            cpu = {"value": round(many[0], 3), "unit": "Msamples/s", "cores": cores, "kind": "reference",
+                   "sample": f"all {n_chunks} chunks (131072 samples each) of the same capture, once, through the unmodified "
+                             f"tetraear SignalProcessor.process + TetraDecoder.decode (oracle/_ref), {cores} worker processes "
+                             f"({many[2]:.1f} s wall); 1-core: {one[0]:.3f} Msamples/s over 4 chunks",
+                   "one_core_value": round(one[0], 3), "bursts_per_s": round(many[1], 1),
+                   "port_value": round(port_many[0], 3), "port_one_core_value": round(port_one[0], 3),
+                   "port_note": "oracle.process + oracle.decode (C + numpy restatement), same chunks and worker count"}
+        else:
+            cpu = {"value": round(port_many[0], 3), "unit": "Msamples/s", "cores": cores, "kind": "port",
+                   "sample": f"all {n_chunks} chunks through oracle.process + oracle.decode, {cores} worker processes "
+                             "(oracle/_ref is absent: run oracle/make_ref.py where /root/reference exists)",
+                   "one_core_value": round(port_one[0], 3), "bursts_per_s": round(port_many[1], 1)}
 
     line = {
         "metric": "iq_msamples_per_s", "value": round(value, 3), "unit": "Msamples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.mode.startswith("fast32") else "f32 decimator / f64 channel filter",
+        "data": "synthetic",
         "config": {"workload": "c1: single synthetic TETRA downlink carrier, 10 s complex64 IQ @2.4 MS/s, "
                                f"{n_chunks} chunks x 131072 samples per GPU, process+decode per chunk (reference mode, "
                                f"arithmetic '{args.mode}': " + {
                                    "exact": "op-order-exact float32 decimator recurrence + float64 channel filter, bit-identical to the reference",
-                                   "fast": "time-parallel float32 decimator + float64 channel filter; dibits identical, soft symbols <= 1e-4 of full scale",
+                                   "fast": "time-parallel float32 decimator + float64 channel filter, the reference's own precision per stage; "
+                                           "dibits identical, soft symbols <= 1e-4 of full scale",
                                    "fast32": "time-parallel float32 decimator and float32 channel filter; dibits identical on the parity cases, "
-                                             "soft symbols <= 1e-4 of full scale (tests/test_gpu_parity.py::test_fast_mode_within_tolerance)"}[args.mode] + ")",
+                                             "soft symbols <= 1e-4 of full scale (tests/test_gpu_parity.py::test_fast_mode_within_tolerance)",
+                                   "fast-tc": "as 'fast' with the decimator's linear part on the tensor cores (split-TF32 tcgen05 MMAs)",
+                                   "fast32-tc": "as 'fast32' with the decimator's linear part on the tensor cores (split-TF32 tcgen05 MMAs)",
+                                   }[args.mode] + ")",
                    "l2": "input 192 MB per step > 126 MB L2, no flush needed", "parallelism": f"capture segment per GPU x{world}",
                    "stream_lanes": args.lanes, "cuda_graph": bool(args.graph) and graph_error is None,
                    "cpus_bound_per_rank": numa_cpus},
@@ -376,9 +476,9 @@ def run_b200(args):
                              "input quantised to int16, not part of the headline"},
         "roofline": {"bound": "hbm", "kernel": "decimator stage (cheby1 zero-phase IIR + ::q)", "achieved": round(achieved, 2),
                      "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
-                     # dram__bytes_read.sum + dram__bytes_write.sum of decim_fast_kernel<10>, one launch, ncu --set full
-                     # (profiles/r01_ncu_kernels_final.md); valid for the fast mode on this workload only
-                     "traffic": 208479744 if args.mode.startswith("fast") else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the decimator kernel, one launch, ncu --set full
+                     # (profiles/r02_ncu_decim_tc.md); valid for the fast modes on this workload only
+                     "traffic": DECIM_TRAFFIC_BYTES if args.mode.startswith("fast") else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "ms_per_launch": round(dec_launch_ms, 4),
                      "path_achieved_gbs": round(path_bytes / (step_ms / 1e3) / 1e9, 2),
@@ -388,7 +488,9 @@ def run_b200(args):
     if cpu:
         line["cpu_baseline"] = cpu
     if alt:
-        line["value_f64_channel_filter"] = alt
+        line["value_other_arithmetic"] = alt
+    if class_api:
+        line["e2e_class_api"] = class_api
     if world == 1 and not args.no_extras:
         try:
             del dev, host
@@ -643,18 +745,19 @@ def run_reference(args):
     from oracle import build as ob
     ob.build()
     cores = host_cores()
+    kind = "reference" if reference_available() else "port"
     x = make_c1(n_chunks=C1_CHUNKS)
     for _ in range(max(1, min(args.warmup, 1))):
-        cpu_run(x[:cores], cores)
+        cpu_run(x[:cores], cores, kind=kind)
     # bounded sample: the whole capture per step when K steps of it fit in ~90 s of wall clock, else its first chunks
-    _, _, t_full = cpu_run(x, cores)
+    _, _, t_full = cpu_run(x, cores, kind=kind)
     sample_chunks = C1_CHUNKS
     if t_full * args.steps > 90.0:
         sample_chunks = int(max(2 * cores, min(C1_CHUNKS, C1_CHUNKS * 90.0 / (t_full * args.steps))))
     x = x[:sample_chunks]
     walls, crcs = [], 0.0
     for _ in range(args.steps):
-        v, b, wall = cpu_run(x, cores)
+        v, b, wall = cpu_run(x, cores, kind=kind)
         walls.append(wall)
         crcs += b * wall
     total = sample_chunks * CHUNK * args.steps
@@ -663,13 +766,15 @@ def run_reference(args):
         "impl": "reference", "metric": "iq_msamples_per_s", "value": round(value, 3), "unit": "Msamples/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1e3 * sum(walls) / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32 decimator / f64 channel filter", "data": "synthetic",
         "config": {"workload": "c1: single synthetic TETRA downlink carrier @2.4 MS/s, process+decode per 131072-sample chunk",
                    "sample": f"{sample_chunks} of {C1_CHUNKS} chunks per step"},
         "crc_pass_bursts_per_s": round(crcs / sum(walls), 1),
-        "cpu_baseline": {"value": round(value, 3), "unit": "Msamples/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_chunks} chunks x 131072 samples per step, {cores} worker processes, "
-                                   "oracle.process + oracle.decode (C + numpy restatement of the Python reference)"},
+        "cpu_baseline": {"value": round(value, 3), "unit": "Msamples/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample_chunks} chunks x 131072 samples per step, {cores} worker processes, " +
+                                   ("the unmodified tetraear SignalProcessor.process + TetraDecoder.decode staged under oracle/_ref"
+                                    if kind == "reference" else
+                                    "oracle.process + oracle.decode (C + numpy restatement; oracle/_ref absent)")},
         "e2e": {"value": round(value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -685,7 +790,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("TB200_BENCH_LANES", "2")),
                     help="sub-batches processed on concurrent streams (overlaps the latency-bound tail kernels)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("TB200_BENCH_MODE", "fast32"), choices=["exact", "fast", "fast32"])
+    ap.add_argument("--mode", default=os.environ.get("TB200_BENCH_MODE", "fast"), choices=["exact", "fast", "fast32", "fast-tc", "fast32-tc"])
     ap.add_argument("--workload", default="c1", choices=["c1", "c5"], help="c1 = headline; c5 = multichannel archive replay")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the other-workload kernel figures")

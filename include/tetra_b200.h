@@ -128,7 +128,8 @@ int tb200_set_sample_rate(tb200_handle h, double sample_rate); /* attr is mutate
 /* TB200_OPT_DECIM_TC = 3: in FAST mode run the decimator's linear part (q-tap modal FIRs and the in-lane recurrences)
  * as split-TF32 tcgen05 MMAs (dsp_tc.cu) when q is 8 or 10, the input is complex64, 16-byte aligned with an even chunk
  * stride and a chunk holds at least 1536 outputs; other geometries use the FFMA2 kernel of dsp_fast.cu.  Same
- * filter, same float32-level accuracy (<= 1e-4 of full scale vs the reference).  Default 1. */
+ * filter, same float32-level accuracy (<= 1e-4 of full scale vs the reference; 7e-7 of full scale from the exact-arithmetic
+ * filter).  Default 0: on this round's B200 measurements the FFMA2 kernel is the faster of the two. */
 #define TB200_OPT_DECIM_TC 3
 int tb200_set_option(tb200_handle h, int option, int value);
 size_t tb200_workspace_bytes(tb200_handle h);
@@ -275,6 +276,9 @@ int tb200_debug_read(tb200_handle h, int region, void *h_dst, size_t nbytes);
  * (row-major), its TF32 split in the shared-memory layout ([K/4][48][4] floats each) and the carry constants (flat
  * floats: lampow[5][4][2], lanepow[32][4][2], cF[3][4][2], cB[3][4][2], initF[4][2], initB[4][2]); tests emulate the kernel
  * with them on the CPU (tests/test_tc_design_cpu.py).  Any output pointer may be NULL. */
+/* profiling aid: per-phase cycle counters of the tensor-core decimator (thread 0 of CTA 0); enable != 0 arms them for the
+ * following launches on this handle; out (may be NULL) receives and clears the 16 counters (see dsp_tc.cu) */
+int tb200_debug_tc_timing(tb200_handle h, int enable, int64_t out[16]);
 int tb200_debug_tc_design(int q, double *B, int b_capacity, float *bhi, float *blo, int split_capacity, float *params,
                           int params_capacity, int *K_out);
 

@@ -41,6 +41,17 @@ for tc in (0, 1):
     print(f"tc={tc}: max |y - exact| / full scale = {err.max() / scale:.3e} (body {err[:, :-200].max() / scale:.3e}, tail {err[:, -200:].max() / scale:.3e}, "
           f"head {err[:, :200].max() / scale:.3e}); vs scipy float32 {np.abs(out - sci).max() / scale:.3e}; worst chunk {err.max(axis=1).argmax()} at k={err.max(axis=0).argmax()}")
     res[tc] = (out, dib.cpu().numpy().copy(), cnt.cpu().numpy().copy())
+    import ctypes
+    tm = (ctypes.c_int64 * 16)()
+    if tc:
+        _lib.check(h.lib.tb200_debug_tc_timing(h.h, 1, None))
+        for _ in range(5):
+            run()
+        _lib.check(h.lib.tb200_debug_tc_timing(h.h, 0, tm))
+        t = list(tm)
+        names = ["top", "input wait", "slot read", "relayout+split", "mma issue", "mma wait", "tmem ld", "scans", "carries+store"]
+        g = max(t[15], 1)
+        print("   TC phases, cycles per group (CTA 0, thread 0):", {n: round(t[i] / g) for i, n in enumerate(names)}, "groups", t[15] // 5)
     h.profile(True)
     for _ in range(20):
         run()

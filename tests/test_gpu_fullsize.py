@@ -33,7 +33,7 @@ def c1_oracle(c1_capture):
     return out
 
 
-@pytest.mark.parametrize("mode", ["exact", "fast", "fast32"])
+@pytest.mark.parametrize("mode", ["exact", "fast", "fast32", "fast-tc", "fast32-tc"])
 def test_c1_full_capture(mods, c1_capture, c1_oracle, mode):
     """Every chunk of the 10 s capture: dibits bit-exact, kept frames (number, type, CRC flag, 510 bits) and the
     parser counters identical to the oracle — in all three arithmetic modes."""

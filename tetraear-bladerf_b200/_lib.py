@@ -78,6 +78,7 @@ _PROTOS = {
     "tb200_profile_enable": (_i, [_vp, _i]),
     "tb200_profile_read": (_i, [_vp, _vp, _vp]),
     "tb200_debug_read": (_i, [_vp, _i, _vp, C.c_size_t]),
+    "tb200_debug_tc_timing": (_i, [_vp, _i, _vp]),
     "tb200_debug_tc_design": (_i, [_i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "tb200_psd_batch": (_i, [_vp, _vp, _i64, _i64, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "tb200_detect_batch": (_i, [_vp, _vp, _i, _i, _i64, _i64, _d, _i, _vp, _vp]),

@@ -92,7 +92,7 @@ static size_t carve(tb200_handle h, char *base)
     size_t nf = (size_t)cfg.max_fft;
     h->psd_tables = c.take<double>((2 * nf + 2 * (nf / 2 + nf / 4 + 1)) * sizeof(double));
     h->etsi_taps = c.take<float>(32 * 32 * sizeof(float));
-    h->tc_bmat_bytes = (C && L) ? 2 * 16 * 48 * 16 : 0;           // Bhi + Blo, up to 16 K-chunks x 48 columns x 16 bytes
+    h->tc_bmat_bytes = (C && L) ? 2 * 16 * 48 * 16 + 128 : 0;     // Bhi + Blo, up to 16 K-chunks x 48 columns x 16 bytes (+ 16 phase counters)
     h->tc_bmat = c.take<float>(h->tc_bmat_bytes);
     size_t MC = (size_t)cfg.max_channels;
     h->chan_proto = c.take<float>(MC * 6 * sizeof(float));
@@ -225,7 +225,7 @@ extern "C" int tb200_create(const tb200_config *cfg, tb200_handle *out)
     h->max_frames = (int)(h->bits_stride / 250 + 2);
     h->psd_tables_n = 0;
     h->chan_M = 0;
-    h->decim_tc = 1;
+    h->decim_tc = 0;
     h->tc_key_q = 0;
     h->ws_bytes = carve(h, nullptr);
     cudaError_t e = cudaMalloc(&h->ws, h->ws_bytes);
@@ -267,7 +267,7 @@ extern "C" int tb200_set_sample_rate(tb200_handle h, double sample_rate)
         return fail(TB200_E_ARG, "tb200_set_sample_rate: %g Hz needs a larger workspace; create a new handle", sample_rate);
     probe.ws = h->ws; probe.ws_bytes = h->ws_bytes; probe.launches = h->launches;
     // every table carved behind the plan-dependent regions moves with n_dec: forget what was uploaded into them
-    probe.psd_tables_n = 0; probe.etsi_taps_fs = 0.0; probe.chan_M = 0; probe.tc_key_q = 0;
+    probe.psd_tables_n = 0; probe.etsi_taps_fs = 0.0; probe.chan_M = 0; probe.tc_key_q = 0; probe.tc_timing = nullptr;
     carve(&probe, (char *)h->ws);
     *h = probe;
     return TB200_OK;

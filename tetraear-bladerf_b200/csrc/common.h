@@ -82,6 +82,7 @@ struct tb200_handle_s {
     float *etsi_taps;                         // [32 phases][32 taps] interpolating matched filter
     float *tc_bmat; size_t tc_bmat_bytes;     // tensor-core decimator weights (Bhi, Blo in the canonical layout)
     int tc_key_q; float tc_key_sos[24];       // design the weights above were built for (q = 0: none)
+    long long *tc_timing;                     // phase counters of the tensor-core decimator (profiling aid) or null
     // staging for the *_host entry points
     void *stage_in;   size_t stage_in_bytes;
     void *stage_sc16;                         // int16 IQ staging of the host entry point

@@ -39,11 +39,10 @@ constexpr int TC_PASS = 32 * TC_R;         // outputs per warp pass
 constexpr int TC_GP = 4;                   // passes per group = MMA rows / 32
 constexpr int TC_GROUP = TC_GP * TC_PASS;  // outputs per group
 constexpr int TC_N = 48;                   // MMA N: 6 zero-state outputs + 16 + 16 aggregate components (+ 10 unused)
-constexpr int TC_TMEM_COLS = 64;
 
 template <int Q> struct TcG {
     static constexpr int KF = 2 + 2 * TC_R * Q;          // floats of a slot that carry weight positions: 1 pad sample in front
-    static constexpr int K = (KF + 7) / 8 * 8;           // contraction length (multiple of the TF32 MMA K = 8)
+    static constexpr int K = (KF + 15) / 16 * 16;        // contraction length (TF32 MMA K = 8; 16 so that lo goes to TMEM in 16-column stores)
     static constexpr int KC = K / 4;                     // 16-byte chunks per slot
     static constexpr int A_BYTES = KC * 128 * 16;
     static constexpr int B_BYTES = KC * TC_N * 16;
@@ -127,204 +126,248 @@ __device__ __forceinline__ cp cp_const(cf v, float2 c)
     return o;
 }
 
+// out of line: chunk ends only; keeps the group loop's code small
+__device__ __noinline__ float2 padded_sample_ool(const float2 *__restrict__ x, long n, long t) { return padded_sample(x, n, t); }
+
 // ---- the kernel ---------------------------------------------------------------------------------------------------
+// A CTA holds TC_TEAMS teams of 4 warps; every team streams over its own range of groups with its own buffers,
+// barriers and carries (the teams only share the weight matrices and the TMEM allocation), so that the latency of one
+// team's load / MMA / scan chain is covered by the others: 2 CTAs x 2 teams = 16 warps and 4 groups in flight per SM.
+constexpr int TC_TEAMS = 2;
+constexpr int TC_TEAM_COLS = 128;          // TMEM columns per team: accumulators at +0 (48 used), lo operand at +64 (K <= 64)
+
+// one lane of a fully active warp (warp-uniform control flow around the single-thread tcgen05 / TMA instructions)
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred)::"memory");
+    return pred != 0;
+}
+__device__ __forceinline__ void team_sync(int team)
+{
+    asm volatile("bar.sync %0, 128;\n" ::"r"(1 + team) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+                 "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand is read from tensor memory (row = TMEM lane, one TF32 element per column)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 template <int Q>
-__global__ void __launch_bounds__(TC_GP * 32, 2)
+__global__ void __launch_bounds__(TC_TEAMS * TC_GP * 32, 2)
 decim_tc_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_chunks, long n_dec, int gpc, long total_floats,
-                TcParams P, const float *__restrict__ bmat, float2 *__restrict__ dec_out)
+                TcParams P, const float *__restrict__ bmat, float2 *__restrict__ dec_out, long long *__restrict__ timing)
 {
     using G = TcG<Q>;
     extern __shared__ uint8_t tc_raw[];
-    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tc_raw) + 127) & ~(uintptr_t)127);
-    uint8_t *A_hi = sm, *A_lo = A_hi + G::A_BYTES, *B_hi = A_lo + G::A_BYTES, *B_lo = B_hi + G::B_BYTES;
-    __shared__ __align__(8) uint64_t full_bar, mma_bar, b_bar;
+    uint8_t *sm = tc_raw + ((128u - (smem_u32(tc_raw) & 127u)) & 127u);        // 128-byte aligned, still a shared-space pointer
+    uint8_t *B_hi = sm, *B_lo = B_hi + G::B_BYTES;
+    __shared__ __align__(8) uint64_t full_bar[TC_TEAMS], mma_bar[TC_TEAMS], b_bar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ cp carryF_s[2][TC_GP][4];
-    __shared__ cp carryB_s[2][TC_GP][4];
+    __shared__ cp carryF_s[TC_TEAMS][2][TC_GP][4];
+    __shared__ cp carryB_s[TC_TEAMS][2][TC_GP][4];
     __shared__ cf lanepow_s[32][4];
 
-    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    const long NG = (long)n_chunks * gpc;
-    const long G0 = NG * blockIdx.x / gridDim.x, G1 = NG * (blockIdx.x + 1) / gridDim.x;
-    if (G0 >= G1) return;
-    const long gs = G0 - ((G0 % gpc) ? 1 : 0);       // a range that starts inside a chunk first runs the group before it (causal carry)
-    const long ge = G1 + ((G1 % gpc) ? 1 : 0);       // ... one that ends inside a chunk also the group after it (anti-causal carry)
+    const int team = threadIdx.x >> 7, tid = threadIdx.x & 127, w = tid >> 5, lane = tid & 31;
+    uint8_t *A_hi = sm + 2 * G::B_BYTES + team * G::A_BYTES;                   // raw group, then the canonical hi operand
+    const int NG = n_chunks * gpc;                   // (the launcher keeps n_chunks * gpc below 2^30)
+    const int n_ranges = TC_TEAMS * gridDim.x, range = TC_TEAMS * blockIdx.x + team;
+    const int G0 = (int)((long)NG * range / n_ranges), G1 = (int)((long)NG * (range + 1) / n_ranges);
+    const int gs = G0 - ((G0 % gpc) ? 1 : 0);        // a range that starts inside a chunk first runs the group before it (causal carry)
+    const int ge = G1 + ((G1 % gpc) ? 1 : 0);        // ... one that ends inside a chunk also the group after it (anti-causal carry)
 
-    lanepow_s[lane][w] = ld2(P.lanepow[lane][w]);
-    if (tid == 0) {
-        mbar_init(&full_bar, 1);
-        mbar_init(&mma_bar, 1);
+    if (team == 0) lanepow_s[lane][w] = ld2(P.lanepow[lane][w]);
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < TC_TEAMS; ++t) { mbar_init(&full_bar[t], 1); mbar_init(&mma_bar[t], 1); }
         mbar_init(&b_bar, 1);
     }
-    if (w == 0) tmem_alloc(&tmem_base_s, TC_TMEM_COLS);
+    if (threadIdx.x < 32) tmem_alloc(&tmem_base_s, TC_TEAMS * TC_TEAM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = tmem_base_s;
+    const uint32_t tmem_d = tmem_base_s + team * TC_TEAM_COLS, tmem_a = tmem_d + 64;
 
     // float offset (from x) of slot (pass 0, lane 0) of group g (a multiple of 4: 16-byte aligned), and whether the whole
     // raw run of the group lies inside the input so that one bulk copy may fetch it
     constexpr long RAW_FLOATS = 127L * G::SLOT_FLOATS + G::K;
-    auto group_f0 = [&](long g) -> long {
-        const long c = g / gpc, gi = g - c * gpc;
-        return 2 * (c * chunk_stride + (long)Q * ((long)gi * TC_GROUP - G::LEAD - 1));
+    auto group_f0 = [&](int g) -> long {
+        const int c = g / gpc, gi = g - c * gpc;
+        return 2 * ((long)c * chunk_stride + (long)Q * (gi * TC_GROUP - G::LEAD - 1));
     };
-    auto group_tma = [&](long g) -> bool {
+    auto group_tma = [&](int g) -> bool {
         const long f0 = group_f0(g);
         return f0 >= 0 && f0 + RAW_FLOATS <= total_floats;
     };
-    auto issue_load = [&](long g) {
-        tma_load_1d(A_hi, reinterpret_cast<const float *>(x) + group_f0(g), (unsigned)(RAW_FLOATS * 4), &full_bar);
+    auto issue_load = [&](int g) {
+        tma_load_1d(A_hi, reinterpret_cast<const float *>(x) + group_f0(g), (unsigned)(RAW_FLOATS * 4), &full_bar[team]);
     };
 
-    if (tid == 0) {
-        tma_load_1d(B_hi, bmat, 2u * G::B_BYTES, &b_bar);          // weights: Bhi then Blo, already in the canonical layout
-        if (group_tma(gs)) issue_load(gs);
-    }
+    if (threadIdx.x < 32 && elect_one()) tma_load_1d(B_hi, bmat, 2u * G::B_BYTES, &b_bar);    // weights: Bhi then Blo, canonical layout
+    if (w == 0 && gs < ge && group_tma(gs) && elect_one()) issue_load(gs);
 
     const int m = tid;                                              // slot = MMA row = TMEM lane
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t lane_base = (uint32_t)(w * 32) << 16;
+    // matrix descriptors of k-step 0 (the start-address field advances by bytes >> 4 per k-step; no carry out of its 14 bits)
+    const uint64_t desc_a = umma_desc(smem_u32(A_hi), 2048, 128);
+    const uint64_t desc_bh = umma_desc(smem_u32(B_hi), TC_N * 16, 128), desc_bl = umma_desc(smem_u32(B_lo), TC_N * 16, 128);
     unsigned ph_full = 0, ph_mma = 0;
     bool pend = false;
     float2 ypend[TC_R];
-    long pend_k0 = 0, pend_chunk = 0;
+    long pend_k0 = 0;
+    int pend_chunk = 0;
     ypend[0] = ypend[1] = ypend[2] = make_float2(0.f, 0.f);
 
-    for (long g = gs; g < ge; ++g) {
-        const int buf = (int)((g - gs) & 1);
-        const long chunk = g / gpc;
-        const int gi = (int)(g - chunk * gpc);
+    // optional phase timing (profiling aid, tb200_debug_tc_timing): cycles of thread 0 of CTA 0 per phase, summed over its groups
+    const bool timed = timing != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long tprev = timed ? clock64() : 0;
+    auto tick = [&](int phase) { if (timed) { const long long t = clock64(); timing[phase] += t - tprev; tprev = t; } };
+    for (int g = gs; g < ge; ++g) {
+        tick(0);
+        const int buf = (g - gs) & 1;
+        const int chunk = g / gpc;
+        const int gi = g - chunk * gpc;
         const bool store = g >= G0 && g < G1;
-        const float2 *xc = x + chunk * chunk_stride;
+        const float2 *xc = x + (long)chunk * chunk_stride;
         const long k0 = (long)gi * TC_GROUP - G::LEAD + (long)w * TC_PASS + (long)lane * TC_R;   // first output of this slot
         const long i0 = 1 + (long)Q * (k0 - 1);                     // chunk sample under weight position 0 (slot float 2)
         const bool via_tma = group_tma(g);
 
         // ---- A operand.  The 128 slots of a group are one contiguous run of the input (slot m starts SLOT_FLOATS * m
         // floats in, slots overlap by the pad floats): ONE bulk copy stages it raw in the A_hi region; every thread
-        // then takes its slot into registers, and after a barrier writes it back in the canonical K-major layout
-        // (16-byte chunk kc of slot m at kc * 2048 + m * 16), split into hi = x rounded to TF32 and lo = x - hi (exact).
+        // then takes its slot into registers and, after a barrier, writes hi = x rounded to TF32 back in the canonical
+        // K-major layout (16-byte chunk kc of slot m at kc * 2048 + m * 16) and lo = x - hi (exact) into its lane of
+        // tensor memory, from where the second MMA term reads its A operand.
         if (via_tma) {
-            mbar_wait(&full_bar, ph_full);
+            mbar_wait(&full_bar[team], ph_full);
             ph_full ^= 1;
         } else {
 #pragma unroll 1
             for (int j = 0; j < G::K / 2; ++j) {                     // range at an end of the whole input: plain loads
                 const long i = i0 - 1 + j;
-                const float2 v = (i >= 0 && i < n) ? xc[i] : padded_sample(xc, n, 27 + i);
+                const float2 v = (i >= 0 && i < n) ? xc[i] : padded_sample_ool(xc, n, 27 + i);
                 *reinterpret_cast<float2 *>(A_hi + m * (G::SLOT_FLOATS * 4) + j * 8) = v;
             }
-            __syncthreads();
+            team_sync(team);
         }
+        tick(1);
         float4 v[G::KC];
 #pragma unroll
         for (int kc = 0; kc < G::KC; ++kc) v[kc] = *reinterpret_cast<const float4 *>(A_hi + m * (G::SLOT_FLOATS * 4) + kc * 16);
-        __syncthreads();                                             // everybody holds its slot: the raw bytes may be overwritten
-#pragma unroll
-        for (int kc = 0; kc < G::KC; ++kc) {
-            float4 hi, lo;
-            hi.x = __uint_as_float((__float_as_uint(v[kc].x) + 0x1000u) & 0xFFFFE000u);
-            hi.y = __uint_as_float((__float_as_uint(v[kc].y) + 0x1000u) & 0xFFFFE000u);
-            hi.z = __uint_as_float((__float_as_uint(v[kc].z) + 0x1000u) & 0xFFFFE000u);
-            hi.w = __uint_as_float((__float_as_uint(v[kc].w) + 0x1000u) & 0xFFFFE000u);
-            lo.x = v[kc].x - hi.x; lo.y = v[kc].y - hi.y; lo.z = v[kc].z - hi.z; lo.w = v[kc].w - hi.w;
-            *reinterpret_cast<float4 *>(A_hi + kc * 2048 + m * 16) = hi;
-            *reinterpret_cast<float4 *>(A_lo + kc * 2048 + m * 16) = lo;
-        }
         if (via_tma && (i0 - 1 < 0 || i0 - 1 + G::K / 2 > n)) {     // slot reaches outside the chunk: scipy's padded signal there
-#pragma unroll 1
-            for (int j = 0; j < G::K / 2; ++j) {
-                const long i = i0 - 1 + j;
-                if (i >= 0 && i < n) continue;
-                const float2 e = padded_sample(xc, n, 27 + i);
-                float2 hi, lo;
-                hi.x = __uint_as_float((__float_as_uint(e.x) + 0x1000u) & 0xFFFFE000u);
-                hi.y = __uint_as_float((__float_as_uint(e.y) + 0x1000u) & 0xFFFFE000u);
-                lo.x = e.x - hi.x; lo.y = e.y - hi.y;
-                *reinterpret_cast<float2 *>(A_hi + (j >> 1) * 2048 + m * 16 + (j & 1) * 8) = hi;
-                *reinterpret_cast<float2 *>(A_lo + (j >> 1) * 2048 + m * 16 + (j & 1) * 8) = lo;
+#pragma unroll
+            for (int kc = 0; kc < G::KC; ++kc) {
+                const long i = i0 - 1 + 2 * kc;
+                if (i < 0 || i >= n) { const float2 e = padded_sample_ool(xc, n, 27 + i); v[kc].x = e.x; v[kc].y = e.y; }
+                if (i + 1 < 0 || i + 1 >= n) { const float2 e = padded_sample_ool(xc, n, 28 + i); v[kc].z = e.x; v[kc].w = e.y; }
             }
         }
+        team_sync(team);                                             // everybody holds its slot: the raw bytes may be overwritten
+        tick(2);
+#pragma unroll
+        for (int q4 = 0; q4 < G::KC / 4; ++q4) {
+            float lo[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int kc = 4 * q4 + c;
+                float4 hi;
+                hi.x = __uint_as_float((__float_as_uint(v[kc].x) + 0x1000u) & 0xFFFFE000u);
+                hi.y = __uint_as_float((__float_as_uint(v[kc].y) + 0x1000u) & 0xFFFFE000u);
+                hi.z = __uint_as_float((__float_as_uint(v[kc].z) + 0x1000u) & 0xFFFFE000u);
+                hi.w = __uint_as_float((__float_as_uint(v[kc].w) + 0x1000u) & 0xFFFFE000u);
+                lo[4 * c + 0] = v[kc].x - hi.x; lo[4 * c + 1] = v[kc].y - hi.y;
+                lo[4 * c + 2] = v[kc].z - hi.z; lo[4 * c + 3] = v[kc].w - hi.w;
+                *reinterpret_cast<float4 *>(A_hi + kc * 2048 + m * 16) = hi;
+            }
+            tmem_st16(tmem_a + lane_base + 16 * q4, lo);
+        }
+        tmem_st_wait();
         fence_async_smem();                                         // generic-proxy writes -> visible to the tensor core
-        __syncthreads();
+        tc_fence_before();
+        team_sync(team);
+        tick(3);
 
         // ---- one thread issues the MMAs of the group: D[128 x 48] = sum over k-steps of hi*Bhi + lo*Bhi + hi*Blo
-        if (tid == 0) {
+        if (w == 0) {                                               // warp-uniform branch, one elected lane issues
             if (g == gs) mbar_wait(&b_bar, 0);
             tc_fence_after();
-            const unsigned a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b_hi = smem_u32(B_hi), b_lo = smem_u32(B_lo);
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < G::K / 8; ++ks) {
-                const uint64_t dah = umma_desc(a_hi + ks * 4096, 2048, 128), dal = umma_desc(a_lo + ks * 4096, 2048, 128);
-                const uint64_t dbh = umma_desc(b_hi + ks * 2 * TC_N * 16, TC_N * 16, 128), dbl = umma_desc(b_lo + ks * 2 * TC_N * 16, TC_N * 16, 128);
-                umma_tf32(tmem_d, dah, dbh, idesc, ks > 0 ? 1u : 0u);
-                umma_tf32(tmem_d, dal, dbh, idesc, 1u);
-                umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                for (int ks = 0; ks < G::K / 8; ++ks) {
+                    const uint64_t dah = desc_a + (uint64_t)(ks * (4096 >> 4));
+                    const uint64_t dbh = desc_bh + (uint64_t)(ks * ((2 * TC_N * 16) >> 4)), dbl = desc_bl + (uint64_t)(ks * ((2 * TC_N * 16) >> 4));
+                    umma_tf32(tmem_d, dah, dbh, idesc, ks > 0 ? 1u : 0u);
+                    umma_tf32_ts(tmem_d, tmem_a + 8 * ks, dbh, idesc, 1u);
+                    umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                }
+                umma_commit(&mma_bar[team]);
             }
-            umma_commit(&mma_bar);
+            __syncwarp();
         }
-        mbar_wait(&mma_bar, ph_mma);
+        tick(4);
+        mbar_wait(&mma_bar[team], ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        if (tid == 0 && g + 1 < ge && group_tma(g + 1)) issue_load(g + 1);     // the MMAs are done with A_hi: prefetch the next group
+        tick(5);
+        if (w == 0 && g + 1 < ge && group_tma(g + 1) && elect_one()) issue_load(g + 1);   // the MMAs are done with A_hi: prefetch the next group
 
         // ---- accumulators of this slot: TMEM lane m, columns 0..39
         uint32_t va[32], vb[8];
-        const uint32_t taddr = tmem_d + ((uint32_t)(w * 32) << 16);
-        tmem_ld32(taddr, va);
-        tmem_ld8(taddr + 32, vb);
+        tmem_ld32(tmem_d + lane_base, va);
+        tmem_ld8(tmem_d + lane_base + 32, vb);
         tmem_ld_wait();
         tc_fence_before();
+        tick(6);
         float2 y[TC_R];
-        cp aF[4], aB[4];
 #pragma unroll
         for (int r = 0; r < TC_R; ++r) y[r] = make_float2(__uint_as_float(va[2 * r]), __uint_as_float(va[2 * r + 1]));
-#pragma unroll
-        for (int mm = 0; mm < 4; ++mm) {
-            aF[mm].re = make_float2(__uint_as_float(va[6 + 4 * mm]), __uint_as_float(va[7 + 4 * mm]));
-            aF[mm].im = make_float2(__uint_as_float(va[8 + 4 * mm]), __uint_as_float(va[9 + 4 * mm]));
-        }
-#pragma unroll
-        for (int mm = 0; mm < 4; ++mm) {
-            const int c = 22 + 4 * mm;
-            auto col = [&](int cc) -> float { return __uint_as_float(cc < 32 ? va[cc < 32 ? cc : 0] : vb[cc >= 32 ? cc - 32 : 0]); };
-            aB[mm].re = make_float2(col(c), col(c + 1));
-            aB[mm].im = make_float2(col(c + 2), col(c + 3));
-        }
 
         // ---- Kogge-Stone scans of the aggregates over the lanes of the pass (zero state at the pass ends)
         cp tF[4], tB[4];
         const float2 zero2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int mm = 0; mm < 4; ++mm) {
-            cp a = aF[mm], b = aB[mm];
+            auto col = [&](int cc) -> float { return __uint_as_float(cc < 32 ? va[cc < 32 ? cc : 0] : vb[cc >= 32 ? cc - 32 : 0]); };
+            cp a, b;
+            a.re = make_float2(col(6 + 4 * mm), col(7 + 4 * mm));
+            a.im = make_float2(col(8 + 4 * mm), col(9 + 4 * mm));
+            b.re = make_float2(col(22 + 4 * mm), col(23 + 4 * mm));
+            b.im = make_float2(col(24 + 4 * mm), col(25 + 4 * mm));
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
                 if (s >= fd_nstage(mm)) continue;
                 cp oa, ob;
                 oa.re = shfl2_up(a.re, 1 << s); oa.im = shfl2_up(a.im, 1 << s);
                 ob.re = shfl2_down(b.re, 1 << s); ob.im = shfl2_down(b.im, 1 << s);
-                cf ga = ld2(P.lampow[s][mm]), gb = ga;
-                if (lane < (1 << s)) ga.x = ga.y = 0.f;
-                if (lane + (1 << s) >= 32) gb.x = gb.y = 0.f;
-                a = cpfma(ga, oa, a);
-                b = cpfma(gb, ob, b);
+                const cf gm = ld2(P.lampow[s][mm]);
+                if (lane >= (1 << s)) a = cpfma(gm, oa, a);
+                if (lane + (1 << s) < 32) b = cpfma(gm, ob, b);
             }
-            if (lane == 31) carryF_s[buf][w][mm] = a;
-            if (lane == 0) carryB_s[buf][w][mm] = b;
+            if (lane == 31) carryF_s[team][buf][w][mm] = a;
+            if (lane == 0) carryB_s[team][buf][w][mm] = b;
             tF[mm].re = shfl2_up(a.re, 1); tF[mm].im = shfl2_up(a.im, 1);
             tB[mm].re = shfl2_down(b.re, 1); tB[mm].im = shfl2_down(b.im, 1);
             if (lane == 0) tF[mm].re = tF[mm].im = zero2;
             if (lane == 31) tB[mm].re = tB[mm].im = zero2;
         }
-        __syncthreads();
+        team_sync(team);
+        tick(7);
 
         // ---- the pass held back from the previous group gets its anti-causal carry from this group's first pass
         if (pend) {
-            float2 *out = dec_out + pend_chunk * n_dec;
+            float2 *out = dec_out + (long)pend_chunk * n_dec;
 #pragma unroll
             for (int mm = 0; mm < 4; ++mm) {
-                const cp gB = cpmul(lanepow_s[31 - lane][mm], carryB_s[buf][0][mm]);
+                const cp gB = cpmul(lanepow_s[31 - lane][mm], carryB_s[team][buf][0][mm]);
 #pragma unroll
                 for (int r = 0; r < TC_R; ++r) ypend[r] = re_acc(ld2(P.cB[r][mm]), gB, ypend[r]);
             }
@@ -341,19 +384,19 @@ decim_tc_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_c
         const bool last_group = gi == gpc - 1;
         const bool wait_b = (w == TC_GP - 1) && !last_group;
         float2 c0 = zero2, cM = zero2;
-        if (w == 0 && gi == 0) c0 = padded_sample(xc, n, 0);
-        if (w == TC_GP - 1 && last_group) cM = padded_sample(xc, n, n + 53);
+        if (w == 0 && gi == 0) c0 = padded_sample_ool(xc, n, 0);
+        if (w == TC_GP - 1 && last_group) cM = padded_sample_ool(xc, n, n + 53);
 #pragma unroll
         for (int mm = 0; mm < 4; ++mm) {
             cp inF, inB;
             inF.re = inF.im = inB.re = inB.im = zero2;
-            if (w > 0) inF = carryF_s[buf][w - 1][mm];
+            if (w > 0) inF = carryF_s[team][buf][w - 1][mm];
             else if (gi == 0) inF = cp_const(ld2(P.initF[mm]), c0);
-            else if (g > gs) inF = carryF_s[buf ^ 1][TC_GP - 1][mm];
-            if (w < TC_GP - 1) inB = carryB_s[buf][w + 1][mm];
+            else if (g > gs) inF = carryF_s[team][buf ^ 1][TC_GP - 1][mm];
+            if (w < TC_GP - 1) inB = carryB_s[team][buf][w + 1][mm];
             else if (last_group) inB = cp_const(ld2(P.initB[mm]), cM);
-            const cp sF = cpadd(tF[mm], cpmul(lanepow_s[lane][mm], inF));
-            const cp sB = cpadd(tB[mm], cpmul(lanepow_s[31 - lane][mm], inB));
+            const cp sF = cpfma(lanepow_s[lane][mm], inF, tF[mm]);
+            const cp sB = cpfma(lanepow_s[31 - lane][mm], inB, tB[mm]);
 #pragma unroll
             for (int r = 0; r < TC_R; ++r) y[r] = re_acc(ld2(P.cB[r][mm]), sB, re_acc(ld2(P.cF[r][mm]), sF, y[r]));
         }
@@ -363,7 +406,7 @@ decim_tc_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_c
 #pragma unroll
                 for (int r = 0; r < TC_R; ++r) ypend[r] = y[r];
             } else {
-                float2 *out = dec_out + chunk * n_dec;
+                float2 *out = dec_out + (long)chunk * n_dec;
 #pragma unroll
                 for (int r = 0; r < TC_R; ++r) {
                     const long k = k0 + r;
@@ -372,9 +415,11 @@ decim_tc_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_c
             }
         }
     }
+    tick(8);
+    if (timed) timing[15] += ge - gs;
     tc_fence_before();
     __syncthreads();
-    if (w == 0) tmem_dealloc(tmem_d, TC_TMEM_COLS);
+    if (threadIdx.x < 32) tmem_dealloc(tmem_base_s, TC_TEAMS * TC_TEAM_COLS);
 }
 
 // ---- right-edge transient of scipy's backward pass: y[k] -= 2 Re sum_i kappa_i pc_i lambda_i^(n_dec-1-k) on the last
@@ -389,13 +434,20 @@ decim_tc_edge_kernel(const float2 *__restrict__ x, long n, long chunk_stride, lo
     for (int j = 0; j < 4; ++j) S[j].re = S[j].im = make_float2(0.f, 0.f);
     const long t_end = n + 53;
     const long t0 = t_end - 32 * FD_EDGE_S + 1 + (long)lane * FD_EDGE_S;
-    for (int i = 0; i < FD_EDGE_S; ++i) {
-        const float2 e = padded_sample(xc, n, t0 + i);
+    constexpr int EB = 14;                                  // samples fetched per batch: independent loads in flight
+    static_assert(FD_EDGE_S % EB == 0, "edge batch");
+    for (int i0 = 0; i0 < FD_EDGE_S; i0 += EB) {
+        float2 e[EB];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cp nx = cpmul(ld2(K.p[j]), S[j]);
-            nx.re.x += e.x; nx.re.y += e.y;
-            S[j] = nx;
+        for (int i = 0; i < EB; ++i) e[i] = padded_sample(xc, n, t0 + i0 + i);
+#pragma unroll
+        for (int i = 0; i < EB; ++i) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                cp nx = cpmul(ld2(K.p[j]), S[j]);
+                nx.re.x += e[i].x; nx.re.y += e[i].y;
+                S[j] = nx;
+            }
         }
     }
 #pragma unroll
@@ -497,7 +549,7 @@ static int tc_design(const DecimDesign &d, int q, std::vector<double> &B, std::v
     cd p[4], alpha[4];
     int rc = tc_modes(d, p, alpha);
     if (rc) return rc;
-    const int KF = 2 + 2 * TC_R * q, K = (KF + 7) / 8 * 8, KC = K / 4;
+    const int KF = 2 + 2 * TC_R * q, K = (KF + 15) / 16 * 16, KC = K / 4;
     K_out = K;
     B.assign((size_t)K * TC_N, 0.0);
     for (int f = 2; f < 2 + 2 * TC_R * q; ++f) {
@@ -551,7 +603,7 @@ static int launch_tc_q(tb200_handle h, const void *x, int n_chunks, long n, long
                        cudaStream_t st)
 {
     using G = TcG<Q>;
-    const size_t smem = 2 * (size_t)G::A_BYTES + 2 * (size_t)G::B_BYTES + 128;
+    const size_t smem = TC_TEAMS * (size_t)G::A_BYTES + 2 * (size_t)G::B_BYTES + 128;
     static std::atomic<bool> attr_set[64];
     static std::atomic<int> n_sm[64];
     const int dv = h->cfg.device & 63;
@@ -565,10 +617,11 @@ static int launch_tc_q(tb200_handle h, const void *x, int n_chunks, long n, long
     }
     const int gpc = (int)((n_dec + G::LEAD + 4 + TC_GROUP - 1) / TC_GROUP);
     const long NG = (long)n_chunks * gpc;
-    long grid = 2L * n_sm[dv];                      // two resident CTAs per SM (88 KB of shared memory each), one range per CTA
-    if (grid > NG) grid = NG;
-    decim_tc_kernel<Q><<<(unsigned)grid, TC_GP * 32, smem, st>>>((const float2 *)x, n, chunk_stride, n_chunks, n_dec, gpc,
-                                                               total_floats, P, bmat, (float2 *)dec_out);
+    if (NG >= (1L << 30)) return fail(TB200_E_ARG, "tc decimator: batch too large");
+    long grid = 2L * n_sm[dv];                      // two resident CTAs per SM (two teams each), one range of groups per team
+    if (grid * TC_TEAMS > NG) grid = NG / TC_TEAMS > 0 ? NG / TC_TEAMS : 1;
+    decim_tc_kernel<Q><<<(unsigned)grid, TC_TEAMS * TC_GP * 32, smem, st>>>((const float2 *)x, n, chunk_stride, n_chunks, n_dec, gpc,
+                                                               total_floats, P, bmat, (float2 *)dec_out, h->tc_timing);
     TB_LAUNCH_CHECK(h);
     decim_tc_edge_kernel<<<n_chunks, 32, 0, st>>>((const float2 *)x, n, chunk_stride, n_dec, KE, (float2 *)dec_out);
     TB_LAUNCH_CHECK(h);
@@ -612,7 +665,7 @@ int launch_decimate_tc(tb200_handle h, const void *x, int n_chunks, long n, long
     }
     P = hit->P; KE = hit->KE;
     const size_t bbytes = hit->bhi.size() * sizeof(float);
-    if (2 * bbytes > h->tc_bmat_bytes) return fail(TB200_E_ARG, "tc decimator: weight matrices exceed the workspace");
+    if (2 * bbytes + 128 > h->tc_bmat_bytes) return fail(TB200_E_ARG, "tc decimator: weight matrices exceed the workspace");
     if (!(h->tc_key_q == q && !memcmp(h->tc_key_sos, d.sos32, sizeof(h->tc_key_sos)))) {
         // first use of this design on this handle: upload Bhi, Blo (synchronous copies from pageable memory)
         TB_CUDA(cudaMemcpyAsync(h->tc_bmat, hit->bhi.data(), bbytes, cudaMemcpyHostToDevice, st));
@@ -656,5 +709,23 @@ extern "C" int tb200_debug_tc_design(int q, double *B, int b_capacity, float *bh
         if ((size_t)params_capacity * sizeof(float) < sizeof(P)) return fail(TB200_E_ARG, "tb200_debug_tc_design: params capacity");
         memcpy(params, &P, sizeof(P));
     }
+    return TB200_OK;
+}
+
+// Profiling aid: with a non-zero `enable` the tensor-core decimator of this handle accumulates, for thread 0 of CTA 0,
+// the cycles spent per phase (0 loop top, 1 input wait, 2 slot read, 3 re-layout + split, 4 MMA issue, 5 MMA wait,
+// 6 TMEM load, 7 scans, 8 carries + stores, 15 groups); reads and clears the counters.
+extern "C" int tb200_debug_tc_timing(tb200_handle h, int enable, int64_t out[16])
+{
+    using namespace tb200;
+    if (!h || !h->tc_bmat) return fail(TB200_E_ARG, "tb200_debug_tc_timing: handle has no process workspace");
+    long long *buf = reinterpret_cast<long long *>((char *)h->tc_bmat + h->tc_bmat_bytes - 16 * sizeof(long long));
+    TB_CUDA(cudaDeviceSynchronize());
+    if (out) {
+        if (h->tc_timing) TB_CUDA(cudaMemcpy(out, buf, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+        else memset(out, 0, 16 * sizeof(int64_t));
+    }
+    TB_CUDA(cudaMemset(buf, 0, 16 * sizeof(long long)));
+    h->tc_timing = enable ? buf : nullptr;
     return TB200_OK;
 }

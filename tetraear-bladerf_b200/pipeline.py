@@ -29,12 +29,15 @@ class ReceivePipeline:
         self.n_lanes = max(1, int(n_lanes))
         per = (self.max_chunks + self.n_lanes - 1) // self.n_lanes
         self.lane_chunks = per
-        m = {"exact": _lib.MODE_EXACT, "fast": _lib.MODE_FAST, "fast32": _lib.MODE_FAST}[mode]
+        m = {"exact": _lib.MODE_EXACT, "fast": _lib.MODE_FAST, "fast32": _lib.MODE_FAST, "fast-tc": _lib.MODE_FAST,
+             "fast32-tc": _lib.MODE_FAST}[mode]           # "-tc": tensor-core decimator (csrc/dsp_tc.cu)
         self.handles = [_lib.Handle(sample_rate=self.sample_rate, max_chunks=per, max_chunk_len=self.chunk_len, mode=m,
                                     device=device) for _ in range(self.n_lanes)]
-        if mode == "fast32":
-            for hh in self.handles:
+        for hh in self.handles:
+            if mode.startswith("fast32"):
                 hh.set_option(_lib.OPT_CHAN_F32, 1)
+            if mode.endswith("-tc"):
+                hh.set_option(_lib.OPT_DECIM_TC, 1)
         self.h = self.handles[0]
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.n_lanes)]
         # the sync search / burst parse of a sub-batch is latency-bound (one small CTA per chunk): it runs on a

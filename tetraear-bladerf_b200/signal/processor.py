@@ -15,7 +15,10 @@ from .. import _lib
 
 logger = logging.getLogger(__name__)
 
-_MODES = {"exact": _lib.MODE_EXACT, "fast": _lib.MODE_FAST, "fast32": _lib.MODE_FAST}
+# "fast" / "fast32": time-parallel float32 decimator + float64 / float32 channel filter; the "-tc" variants run the
+# decimator's linear part on the tensor cores (tcgen05, csrc/dsp_tc.cu) instead of packed FFMA2 (csrc/dsp_fast.cu)
+_MODES = {"exact": _lib.MODE_EXACT, "fast": _lib.MODE_FAST, "fast32": _lib.MODE_FAST, "fast-tc": _lib.MODE_FAST,
+          "fast32-tc": _lib.MODE_FAST}
 
 
 def _as_complex(samples):
@@ -51,8 +54,10 @@ class SignalProcessor:
             cap = max(2 * int(n) + 128, 1 << 16)
             self._h = _lib.Handle(sample_rate=fs, max_chunks=1, max_chunk_len=cap, mode=_MODES[self.mode],
                                   device=self.device)
-            if self.mode == "fast32":
+            if self.mode.startswith("fast32"):
                 self._h.set_option(_lib.OPT_CHAN_F32, 1)
+            if self.mode.endswith("-tc"):
+                self._h.set_option(_lib.OPT_DECIM_TC, 1)
             self._cap = ((cap - 128) // 2, fs)
         return self._h
 
