@@ -269,6 +269,18 @@ int tb200_psd_batch(tb200_handle h, const void *d_iq_c64, int64_t n_frames, int6
 int tb200_profile_enable(tb200_handle h, int on);
 int tb200_profile_read(tb200_handle h, double ms[8], int64_t calls[8]);
 
+/* ---- reference-mode channel bank (BASELINE configs[3]) ----------------------------------
+ * d_out[k][j], k = 0 .. n_channels-1, j = 0 .. ceil(n/q)-1  ==  scipy.signal.decimate(frequency_shift(x, f_k, fs), q)[j]
+ * with f_k = k fs / n_channels for k < n_channels/2, (k - n_channels) fs / n_channels above (DFT bin order), i.e. what
+ * SignalProcessor.frequency_shift + the decimation step of SignalProcessor.process compute for EVERY channel of a
+ * wideband chunk (tetraear/signal/processor.py:85-100, :245-257; complex128 in the reference, so the float64 design),
+ * with the input read once: polyphase fold of the zero-phase response + size-n_channels DFT, then scipy's chunk-end
+ * terms (odd extension, steady-state continuation, backward-pass transient) per channel in float64.  complex64 out,
+ * ~1e-6 of full scale from the reference.  Feed d_out to tb200_process_batch of a handle created for the decimated
+ * rate fs/q (no further decimation there) to get dibits / symbols per channel.  The handle needs max_channels >= n_channels. */
+int tb200_refchan_batch(tb200_handle h, const void *d_iq_c64, int64_t n_samples, int n_channels, int q, double fs,
+                        void *d_out_c64, int64_t out_stride, void *stream);
+
 /* ---- debugging aid: synchronous copy of an internal workspace region to the host ---------
  * region 0 = decimated chunks, 1 = channel-filtered complex128, 2 / 3 = forward-pass scratches */
 int tb200_debug_read(tb200_handle h, int region, void *h_dst, size_t nbytes);

@@ -50,8 +50,11 @@ def test_detector_matches_reference_golden(mods):
 
 
 def test_detector_counts_match_oracle(mods):
-    """The raw integers behind the ratios: modulation matches within 2 (float32 boundary cases), sync stream
-    best-match exact, on every golden dwell and on seeded noise at several lengths."""
+    """The raw integers behind the ratios: sync stream best-match exact; modulation matches equal to the reference's
+    count except for phase steps that sit within 4 float32 ulps of a decision boundary.  The reference's own count is
+    not reproducible there: numpy evaluates float32 arctan2 with its AVX-512 SVML kernel on this build machine (38 % of
+    its results differ from the correctly rounded value, which the CUDA kernel and any libm-based numpy produce), so
+    the bound below is the number of such borderline steps, counted per dwell — zero borderline steps => exact."""
     from oracle import scanner as osc
     signal, _, _lib = mods
     cases = list(scanner_cases())
@@ -63,7 +66,15 @@ def test_detector_counts_match_oracle(mods):
         rec, _ = det.stats_batch(x, 5)
         rec = rec[0]
         m, ns = osc.modulation_matches(x)
-        assert rec["n_steps"] == ns and abs(int(rec["matches"]) - m) <= 2, (name, rec["matches"], m)
+        assert rec["n_steps"] == ns
+        border = 0
+        if ns:
+            xn = x / (np.abs(x).max() + 1e-10)
+            d = osc._wrapped_steps(xn).astype(np.float64)
+            edges = np.arange(-7, 9, 2) * np.pi / 8                 # the open ends of the eight +-pi/8 windows
+            gap = np.abs(d[:, None] - edges[None, :]).min(axis=1)
+            border = int(np.count_nonzero(gap <= 4 * np.spacing(np.float32(np.pi))))
+        assert abs(int(rec["matches"]) - m) <= border, (name, rec["matches"], m, border)
         bits = osc.sync_bits(x, fs)
         if bits is None:
             assert rec["n_sync_bits"] == 0, name

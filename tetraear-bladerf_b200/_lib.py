@@ -75,6 +75,7 @@ _PROTOS = {
     "tb200_etsi_afc": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp]),
     "tb200_etsi_find_sync_bursts": (_i, [_vp, _vp, _i, _i64, _vp, _d, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "tb200_channelize": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _i64, _vp]),
+    "tb200_refchan_batch": (_i, [_vp, _vp, _i64, _i, _i, _d, _vp, _i64, _vp]),
     "tb200_profile_enable": (_i, [_vp, _i]),
     "tb200_profile_read": (_i, [_vp, _vp, _vp]),
     "tb200_debug_read": (_i, [_vp, _i, _vp, C.c_size_t]),

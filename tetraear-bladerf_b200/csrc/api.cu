@@ -97,6 +97,8 @@ static size_t carve(tb200_handle h, char *base)
     size_t MC = (size_t)cfg.max_channels;
     h->chan_proto = c.take<float>(MC * 6 * sizeof(float));
     h->chan_tw = c.take<float>((MC + 256) * 2 * sizeof(float));
+    h->rc_tab_bytes = MC ? MC * 32 * sizeof(float) + (MC + 512) * 2 * sizeof(float) + (MC * 16 + 64) * sizeof(double) + MC * sizeof(double) : 0;
+    h->rc_tab = MC ? c.take<char>(h->rc_tab_bytes) : nullptr;
     // staging for *_host
     h->stage_in_bytes = C * L * 8;
     h->stage_in = c.take<char>(h->stage_in_bytes);
@@ -226,6 +228,7 @@ extern "C" int tb200_create(const tb200_config *cfg, tb200_handle *out)
     h->psd_tables_n = 0;
     h->chan_M = 0;
     h->decim_tc = 0;
+    h->rc_M = 0;
     h->tc_key_q = 0;
     h->ws_bytes = carve(h, nullptr);
     cudaError_t e = cudaMalloc(&h->ws, h->ws_bytes);
@@ -267,7 +270,7 @@ extern "C" int tb200_set_sample_rate(tb200_handle h, double sample_rate)
         return fail(TB200_E_ARG, "tb200_set_sample_rate: %g Hz needs a larger workspace; create a new handle", sample_rate);
     probe.ws = h->ws; probe.ws_bytes = h->ws_bytes; probe.launches = h->launches;
     // every table carved behind the plan-dependent regions moves with n_dec: forget what was uploaded into them
-    probe.psd_tables_n = 0; probe.etsi_taps_fs = 0.0; probe.chan_M = 0; probe.tc_key_q = 0; probe.tc_timing = nullptr;
+    probe.psd_tables_n = 0; probe.etsi_taps_fs = 0.0; probe.chan_M = 0; probe.tc_key_q = 0; probe.tc_timing = nullptr; probe.rc_M = 0;
     carve(&probe, (char *)h->ws);
     *h = probe;
     return TB200_OK;
@@ -681,6 +684,20 @@ extern "C" int tb200_channelize(tb200_handle h, const void *d_iq_c64, int64_t n_
     StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
     return launch_channelizer(h, (const float2 *)d_iq_c64, n_samples, n_channels, h->chan_proto, (float2 *)h->chan_tw,
                               (float2 *)d_out_c64, out_stride, n_frames, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------- reference-mode channel bank
+extern "C" int tb200_refchan_batch(tb200_handle h, const void *d_iq_c64, int64_t n_samples, int n_channels, int q, double fs,
+                                   void *d_out_c64, int64_t out_stride, void *stream)
+{
+    DevGuard dev_guard(h);
+    if (!h || !d_iq_c64 || !d_out_c64 || n_samples <= 0 || n_channels < 2 || q < 2 || !(fs > 0))
+        return fail(TB200_E_ARG, "tb200_refchan_batch: bad argument");
+    int rc = get_decim(h, q);
+    if (rc) return rc;
+    StageTimer tm(h, TB_STAGE_DECIM, (cudaStream_t)stream);
+    return launch_refchan(h, (const float2 *)d_iq_c64, (long)n_samples, n_channels, q, fs, h->dec, (float2 *)d_out_c64, (long)out_stride,
+                          (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------- PSD

@@ -83,6 +83,8 @@ struct tb200_handle_s {
     float *tc_bmat; size_t tc_bmat_bytes;     // tensor-core decimator weights (Bhi, Blo in the canonical layout)
     int tc_key_q; float tc_key_sos[24];       // design the weights above were built for (q = 0: none)
     long long *tc_timing;                     // phase counters of the tensor-core decimator (profiling aid) or null
+    void *rc_tab; size_t rc_tab_bytes;        // reference-mode channel bank: folded prototype, twiddles, g, channel frequencies
+    int rc_M, rc_q; long rc_n; double rc_fs;  // what the tables above were built for (rc_M = 0: none)
     // staging for the *_host entry points
     void *stage_in;   size_t stage_in_bytes;
     void *stage_sc16;                         // int16 IQ staging of the host entry point

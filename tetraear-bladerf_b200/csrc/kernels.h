@@ -46,6 +46,8 @@ int launch_etsi_find_sync(tb200_handle h, const float *soft, int n_streams, long
                           cudaStream_t st);
 int launch_channelizer(tb200_handle h, const float2 *x, long n, int M, float *proto_dev, float2 *tw_dev, float2 *out,
                        long out_stride, long n_frames, cudaStream_t st);
+int launch_refchan(tb200_handle h, const float2 *x, long n, int M, int q, double fs, const DecimDesign &d, float2 *out,
+                   long out_stride, cudaStream_t st);
 int launch_sc16_to_c64(tb200_handle h, const void *in, long n, void *out, cudaStream_t st);
 int launch_resample(tb200_handle h, const void *x, int dtype, long n, long num, void *y, double *scratch, size_t scratch_bytes,
                     cudaStream_t st);

@@ -1,0 +1,369 @@
+// refchan.cu — reference-mode multichannel front end (BASELINE configs[3]).
+//
+// The reference reaches channel k of a wideband capture only as
+//     process(frequency_shift(x, f_k, fs))                    (/root/reference/tetraear/signal/processor.py:85-100, :245-262)
+// i.e. M passes over the input, each an NCO (complex128) followed by scipy.signal.decimate(., q) = zero-phase
+// cheby1(8) in float64.  The zero-phase response is g[d] = 2 Re sum_i alpha_i p_i^|d| (see dsp_fast.cu), so for every
+// channel at once
+//     y_k[j] = sum_t g[n_j - t] x[t] e^{-j w_k t}  =  e^{-j w_k n_j} sum_d g[d] e^{+j w_k d} x[n_j - d],   n_j = q j,
+// and with w_k = 2 pi k / M the inner sum is a polyphase filterbank: fold the window into M branches
+//     v_j[r] = sum_l g[|r + M l|] x[n_j - r - M l],   Y_j[k] = sum_r v_j[r] e^{+j 2 pi k r / M}   (size-M inverse DFT)
+// — the input is read once per frame for all M channels.  g is truncated where it has decayed to 1e-10 of its peak
+// (|d| < P/2 * M, P = 24 taps per branch for q = 83, M = 800).  What this leaves out is scipy's treatment of the chunk
+// ends, which depends on the channel because the reference shifts BEFORE it pads: the odd extension of the shifted
+// signal (27 samples), its constant continuation (steady-state initial conditions) and the right-edge transient of
+// the backward pass.  refchan_edge_kernel adds exactly those terms, in float64, to the ~P/2*M/q outputs at each end
+// of every channel.  Result: decimate(frequency_shift(x, f_k, fs), q) for all k to ~1e-6 of full scale.
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include "common.h"
+#include "kernels.h"
+
+namespace tb200 {
+
+constexpr int RC_PMAX = 32;          // prototype taps per polyphase branch (upper bound)
+constexpr int RC_EDGE = 27;          // scipy sosfiltfilt edge (3 * ntaps) of the order-8 decimator
+constexpr int RC_NFIX = 160;         // outputs that receive the right-edge transient
+
+struct RefChanEdge {
+    double p[4][2], lam[4][2];       // poles (upper half plane), lambda = p^q
+    double g_tail[4][2];             // 2 alpha_i / (1 - p_i): tail sum  Gt(D) = Re sum_i g_tail_i p_i^(D+1)
+    double ka[4][2], kM[4][4][2], kMc[4][4][2], pc[4][2];    // right-edge transient (dsp_fast.cu make_fast_params)
+    int L;                           // truncation length of g (multiple of M)
+};
+
+__global__ void __launch_bounds__(256)
+refchan_kernel(const float2 *__restrict__ x, long n, int M, int N1, int log2_n2, int F, int P, int hop, long n_frames,
+               const float *__restrict__ proto, const float2 *__restrict__ tw, float2 *__restrict__ out, long out_stride)
+{
+    extern __shared__ float2 rc_smem[];
+    const int N2 = 1 << log2_n2;
+    const int APITCH = N2 + 1;
+    float2 *v = rc_smem;                      // [F][M]
+    float2 *a = v + (long)F * M;              // [F][N1][APITCH]
+    float2 *w1 = a + (long)F * N1 * APITCH;   // [N1] exp(+j 2 pi i / N1)
+    float2 *w2 = w1 + N1;                     // [N2]
+    float2 *wm = w2 + N2;                     // [M]  exp(+j 2 pi i / M)
+    const long m0 = (long)blockIdx.x * F;
+    const int half = P / 2;
+    for (int i = threadIdx.x; i < N1 + N2 + M; i += blockDim.x) w1[i] = tw[i];
+    // ---- folded window: v[f][r] = sum_l g[|r + M l|] x[n_j - r - M l],  l = -P/2 .. P/2-1   (proto[(l + P/2) M + r])
+    for (int f = 0; f < F; ++f) {
+        const long j = m0 + f;
+        for (int r = threadIdx.x; r < M; r += blockDim.x) {
+            float2 acc = make_float2(0.f, 0.f);
+            if (j < n_frames) {
+                const long base = j * hop - r;
+                for (int l = -half; l < half; ++l) {
+                    const long idx = base - (long)l * M;
+                    if (idx >= 0 && idx < n) {
+                        const float2 s = x[idx];
+                        const float h = __ldg(proto + (l + half) * M + r);
+                        acc.x = fmaf(h, s.x, acc.x); acc.y = fmaf(h, s.y, acc.y);
+                    }
+                }
+            }
+            v[f * M + r] = acc;
+        }
+    }
+    __syncthreads();
+    // ---- stage A: for every r2, a size-N1 DFT over r1 (r = N2 r1 + r2), times exp(+j 2 pi k1 r2 / M)
+    for (int jj = threadIdx.x; jj < M; jj += blockDim.x) {
+        const int k1 = jj >> log2_n2, r2 = jj & (N2 - 1);
+        const float2 t = wm[(k1 * r2) % M];
+        for (int f = 0; f < F; ++f) {
+            const float2 *vf = v + (long)f * M + r2;
+            float2 acc = make_float2(0.f, 0.f);
+            int e = 0;                                        // (k1 r1) mod N1
+            for (int r1 = 0; r1 < N1; ++r1) {
+                float2 s = vf[r1 << log2_n2], w = w1[e];
+                acc.x = fmaf(s.x, w.x, fmaf(-s.y, w.y, acc.x)); acc.y = fmaf(s.x, w.y, fmaf(s.y, w.x, acc.y));
+                e += k1; if (e >= N1) e -= N1;
+            }
+            a[((long)f * N1 + k1) * APITCH + r2] = make_float2(acc.x * t.x - acc.y * t.y, acc.x * t.y + acc.y * t.x);
+        }
+    }
+    __syncthreads();
+    // ---- stage B: size-N2 DFT over r2; k = k1 + N1 k2; rotation e^{-j 2 pi k n_j / M}; store [k][m0 .. m0+F)
+    for (int k = threadIdx.x; k < M; k += blockDim.x) {
+        const int k2 = k / N1, k1 = k - k2 * N1;
+        float2 *o = out + (long)k * out_stride + m0;
+        const int kh = (int)(((long)k * hop) % M);
+        for (int f = 0; f < F; ++f) {
+            const long j = m0 + f;
+            if (j >= n_frames) break;
+            const float2 *af = a + ((long)f * N1 + k1) * APITCH;
+            float2 acc = make_float2(0.f, 0.f);
+            int e = 0;                                        // (k2 r2) mod N2
+            for (int r2 = 0; r2 < N2; ++r2) {
+                float2 s = af[r2], w = w2[e];
+                acc.x = fmaf(s.x, w.x, fmaf(-s.y, w.y, acc.x)); acc.y = fmaf(s.x, w.y, fmaf(s.y, w.x, acc.y));
+                e = (e + k2) & (N2 - 1);
+            }
+            const float2 rot = wm[(int)(((long)kh * (j % M)) % M)];     // e^{+j 2 pi (k hop j) / M}; conjugate applied
+            o[f] = make_float2(acc.x * rot.x + acc.y * rot.y, acc.y * rot.x - acc.x * rot.y);
+        }
+    }
+}
+
+struct cdd2 { double x, y; };
+__device__ __forceinline__ cdd2 zmul(cdd2 a, cdd2 b) { return cdd2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cdd2 zpow(cdd2 p, long e)
+{
+    cdd2 r = cdd2{1.0, 0.0};
+    while (e > 0) { if (e & 1) r = zmul(r, p); p = zmul(p, p); e >>= 1; }
+    return r;
+}
+// sample m of the frequency-shifted chunk, numpy's evaluation order: x[m] * exp(W * (m / fs)), W = fl(-2 pi f)
+__device__ __forceinline__ cdd2 shifted(const float2 *__restrict__ x, long m, double W, double fs)
+{
+    double s, c;
+    sincos(__dmul_rn(W, (double)m / fs), &s, &c);
+    const double xr = (double)x[m].x, xi = (double)x[m].y;
+    return cdd2{xr * c - xi * s, xr * s + xi * c};
+}
+
+// One CTA per channel: the terms of scipy's padded, zero-phase filtering that lie outside the chunk.
+__global__ void __launch_bounds__(128)
+refchan_edge_kernel(const float2 *__restrict__ x, long n, int q, double fs, const double *__restrict__ freq, long n_dec,
+                    const double *__restrict__ gfull, RefChanEdge E, float2 *__restrict__ out, long out_stride)
+{
+    __shared__ cdd2 extL[RC_EDGE + 1], extR[RC_EDGE + 1];      // ext[t], t = -1..-27 (index 1..27) / t = n..n+26 (index 0..26)
+    __shared__ cdd2 part[128][4][2];                            // per-thread partial one-pole sums [mode][I/Q]
+    __shared__ cdd2 kappa[4][2];
+    const int ch = blockIdx.x, tid = threadIdx.x;
+    const double f = freq[ch];
+    const double W = __dmul_rn(-6.283185307179586, f);
+    float2 *o = out + (long)ch * out_stride;
+    if (tid <= RC_EDGE && tid >= 1) {
+        const cdd2 e0 = shifted(x, 0, W, fs), v = shifted(x, tid, W, fs);
+        extL[tid] = cdd2{2.0 * e0.x - v.x, 2.0 * e0.y - v.y};
+    }
+    if (tid < RC_EDGE) {
+        const cdd2 e1 = shifted(x, n - 1, W, fs), v = shifted(x, n - 2 - tid, W, fs);
+        extR[tid] = cdd2{2.0 * e1.x - v.x, 2.0 * e1.y - v.y};
+    }
+    // ---- F_i[M-1] = sum_k p_i^k ext[M-1-k] over the last E.L samples of the padded, shifted signal (M-1 <-> t = n + 26)
+    __syncthreads();
+    {
+        const int per = (E.L + 127) / 128;
+        cdd2 S[4][2];
+        for (int i = 0; i < 4; ++i) S[i][0] = S[i][1] = cdd2{0.0, 0.0};
+        // thread tid covers k = tid*per .. tid*per+per-1, walked from the far end so that S = sum p^(k - k0) ext[..]
+        for (int u = per - 1; u >= 0; --u) {
+            const long k = (long)tid * per + u;
+            const long t = n + 26 - k;
+            cdd2 e;
+            if (t >= n) e = extR[t - n];
+            else if (t >= 0) e = shifted(x, t, W, fs);
+            else e = cdd2{0.0, 0.0};
+            for (int i = 0; i < 4; ++i) {
+                const cdd2 p = cdd2{E.p[i][0], E.p[i][1]};
+                cdd2 a = zmul(p, S[i][0]); a.x += e.x; S[i][0] = a;       // I component (real signal, complex state)
+                cdd2 b = zmul(p, S[i][1]); b.x += e.y; S[i][1] = b;       // Q component
+            }
+        }
+        for (int i = 0; i < 4; ++i) { part[tid][i][0] = S[i][0]; part[tid][i][1] = S[i][1]; }
+        __syncthreads();
+        if (tid < 8) {                                           // (mode, component) pairs: Horner over the 128 partials
+            const int i = tid >> 1, c = tid & 1;
+            const cdd2 pp = zpow(cdd2{E.p[i][0], E.p[i][1]}, per);
+            cdd2 Fv = cdd2{0.0, 0.0};
+            for (int t = 127; t >= 0; --t) { Fv = zmul(pp, Fv); Fv.x += part[t][i][c].x; Fv.y += part[t][i][c].y; }
+            part[0][i][c] = Fv;
+        }
+        __syncthreads();
+        if (tid < 8) {
+            const int i = tid >> 1, c = tid & 1;
+            const double xl = c ? extR[RC_EDGE - 1].y : extR[RC_EDGE - 1].x;
+            cdd2 k = cdd2{E.ka[i][0] * xl, E.ka[i][1] * xl};
+            for (int j = 0; j < 4; ++j) {
+                const cdd2 Fj = part[0][j][c];
+                const cdd2 t1 = zmul(cdd2{E.kM[i][j][0], E.kM[i][j][1]}, Fj);
+                const cdd2 t2 = zmul(cdd2{E.kMc[i][j][0], E.kMc[i][j][1]}, cdd2{Fj.x, -Fj.y});
+                k.x += t1.x + t2.x; k.y += t1.y + t2.y;
+            }
+            kappa[i][c] = k;
+        }
+        __syncthreads();
+    }
+    // tail sum of g beyond distance D: Gt(D) = sum_{d > D} g[d] = Re sum_i g_tail_i p_i^(D+1)
+    auto g_tail = [&](long D) -> double {
+        double s = 0.0;
+        for (int i = 0; i < 4; ++i) {
+            const cdd2 pw = zpow(cdd2{E.p[i][0], E.p[i][1]}, D + 1);
+            s += E.g_tail[i][0] * pw.x - E.g_tail[i][1] * pw.y;
+        }
+        return s;
+    };
+    const long n_edge = (long)E.L / q + 2;
+    // ---- left end: sum_{t<0} g[n_j - t] ext[t]  (27 extension samples + the constant continuation ext[-27])
+    for (long j = tid; j < n_edge && j < n_dec; j += blockDim.x) {
+        const long nj = j * q;
+        double ax = 0.0, ay = 0.0;
+        for (int u = 1; u <= RC_EDGE; ++u) {
+            const long d = nj + u;
+            if (d < E.L) { const double g = gfull[d]; ax += g * extL[u].x; ay += g * extL[u].y; }
+        }
+        const double gt = g_tail(nj + RC_EDGE);
+        ax += gt * extL[RC_EDGE].x; ay += gt * extL[RC_EDGE].y;
+        float2 v = o[j];
+        v.x += (float)ax; v.y += (float)ay;
+        o[j] = v;
+    }
+    __syncthreads();
+    // ---- right end: sum_{t>=n} g[t - n_j] ext[t] (+ constant continuation ext[n+26]) - transient of the backward pass
+    for (long jj = tid; jj < n_edge && jj < n_dec; jj += blockDim.x) {
+        const long j = n_dec - 1 - jj;
+        const long nj = j * q;
+        double ax = 0.0, ay = 0.0;
+        for (int u = 0; u < RC_EDGE; ++u) {
+            const long d = n + u - nj;
+            if (d < E.L) { const double g = gfull[d]; ax += g * extR[u].x; ay += g * extR[u].y; }
+        }
+        const double gt = g_tail(n + RC_EDGE - 1 - nj);
+        ax += gt * extR[RC_EDGE - 1].x; ay += gt * extR[RC_EDGE - 1].y;
+        if (jj < RC_NFIX) {
+            // y[k] -= 2 Re sum_i kappa_i pc_i lambda_i^(n_dec-1-k), I and Q separately (real filter, complex state)
+            for (int i = 0; i < 4; ++i) {
+                const cdd2 gl = zmul(cdd2{E.pc[i][0], E.pc[i][1]}, zpow(cdd2{E.lam[i][0], E.lam[i][1]}, jj));
+                ax -= 2.0 * (gl.x * kappa[i][0].x - gl.y * kappa[i][0].y);
+                ay -= 2.0 * (gl.x * kappa[i][1].x - gl.y * kappa[i][1].y);
+            }
+        }
+        float2 v = o[j];
+        v.x += (float)ax; v.y += (float)ay;
+        o[j] = v;
+    }
+}
+
+// ---- host: the zero-phase response of scipy.signal.decimate's float64 design for factor q ----------------------
+typedef std::complex<double> cd;
+static void putz(double dst[2], cd v) { dst[0] = v.real(); dst[1] = v.imag(); }
+
+int channelizer_factor(int M, int *N1, int *N2);
+
+static int refchan_design(const DecimDesign &d, int q, long n, long n_dec, int M, std::vector<double> &g, RefChanEdge &E)
+{
+    cd p8[8], r8[8];
+    const double gain = d.sos64[0];
+    for (int s = 0; s < 4; ++s) {
+        double a1 = d.sos64[6 * s + 4], a2 = d.sos64[6 * s + 5];
+        double disc = a1 * a1 - 4 * a2;
+        if (!(disc < 0)) return fail(TB200_E_ARG, "refchan: real pole pair in section %d", s);
+        p8[s] = cd(-a1 / 2, std::sqrt(-disc) / 2);
+        p8[s + 4] = std::conj(p8[s]);
+    }
+    cd prodp(1.0, 0.0);
+    for (int i = 0; i < 8; ++i) prodp *= p8[i];
+    const double dd = gain / prodp.real();
+    for (int i = 0; i < 8; ++i) {
+        cd num = gain * std::pow(1.0 + 1.0 / p8[i], 8), den(1.0, 0.0);
+        for (int j = 0; j < 8; ++j) if (j != i) den *= (1.0 - p8[j] / p8[i]);
+        r8[i] = num / den;
+    }
+    cd alpha[4];
+    double rmax = 0.0;
+    for (int j = 0; j < 4; ++j) {
+        cd acc(dd, 0.0);
+        for (int i = 0; i < 8; ++i) acc += r8[i] / (1.0 - p8[i] * p8[j]);
+        alpha[j] = r8[j] * acc;
+        rmax = std::max(rmax, std::abs(p8[j]));
+    }
+    // truncate g where the slowest mode has decayed to 1e-10: a whole number of M-blocks
+    long L = (long)std::ceil(std::log(1e-10) / std::log(rmax));
+    int half = (int)((L + M - 1) / M);
+    if (2 * half > RC_PMAX) return fail(TB200_E_ARG, "refchan: q=%d needs %d taps per branch (max %d)", q, 2 * half, RC_PMAX);
+    L = (long)half * M;
+    g.assign((size_t)L + 64, 0.0);
+    for (int j = 0; j < 4; ++j) {
+        cd pw(1.0, 0.0);
+        for (long k = 0; k < (long)g.size(); ++k) { g[k] += 2.0 * (alpha[j] * pw).real(); pw *= p8[j]; }
+    }
+    memset(&E, 0, sizeof(E));
+    E.L = (int)L;
+    for (int j = 0; j < 4; ++j) {
+        putz(E.p[j], p8[j]);
+        putz(E.lam[j], std::pow(p8[j], q));
+        putz(E.g_tail[j], 2.0 * alpha[j] / (1.0 - p8[j]));
+    }
+    // right-edge transient constants (same algebra as make_fast_params, kept in double)
+    cd H1(dd, 0.0);
+    for (int j = 0; j < 8; ++j) H1 += r8[j] / (1.0 - p8[j]);
+    const long Mx = n + 54, n_last = 27 + (long)q * (n_dec - 1);
+    for (int i = 0; i < 4; ++i) {
+        cd ka = (H1 - dd) / (1.0 - p8[i]);
+        cd kM[8];
+        for (int j = 0; j < 8; ++j) {
+            ka -= r8[j] * p8[j] / ((1.0 - p8[i] * p8[j]) * (1.0 - p8[j]));
+            kM[j] = -r8[j] / (1.0 - p8[i]) + r8[j] * p8[j] / (1.0 - p8[i] * p8[j]);
+        }
+        putz(E.ka[i], r8[i] * ka);
+        for (int j = 0; j < 4; ++j) { putz(E.kM[i][j], r8[i] * kM[j]); putz(E.kMc[i][j], r8[i] * kM[j + 4]); }
+        putz(E.pc[i], std::pow(p8[i], (double)(Mx - n_last)));
+    }
+    return TB200_OK;
+}
+
+// workspace layout of h->rc_tab: [proto: RC_PMAX * M floats][twiddles: (M + 512) float2][g: RC_PMAX * M / 2 + 64 doubles][freq: M doubles]
+int launch_refchan(tb200_handle h, const float2 *x, long n, int M, int q, double fs, const DecimDesign &d, float2 *out,
+                   long out_stride, cudaStream_t st)
+{
+    if (!h->rc_tab) return fail(TB200_E_ARG, "refchan: handle was created without max_channels");
+    if (M < 2 || M > h->cfg.max_channels) return fail(TB200_E_ARG, "refchan: n_channels %d exceeds the handle's max_channels", M);
+    if (n <= 2 * RC_EDGE + 2) return fail(TB200_E_ARG, "refchan: input too short");
+    int N1, N2;
+    int rc = channelizer_factor(M, &N1, &N2);
+    if (rc) return rc;
+    const long n_dec = (n + q - 1) / q;
+    if (out_stride < n_dec) return fail(TB200_E_ARG, "refchan: out_stride %ld < %ld outputs", out_stride, n_dec);
+    std::vector<double> g;
+    RefChanEdge E;
+    rc = refchan_design(d, q, n, n_dec, M, g, E);
+    if (rc) return rc;
+    const int P = 2 * (E.L / M);
+    float *proto = reinterpret_cast<float *>(h->rc_tab);
+    float2 *tw = reinterpret_cast<float2 *>(proto + (size_t)RC_PMAX * h->cfg.max_channels);
+    double *gdev = reinterpret_cast<double *>(tw + h->cfg.max_channels + 512);
+    double *fdev = gdev + (size_t)RC_PMAX * h->cfg.max_channels / 2 + 64;
+    if (!(h->rc_M == M && h->rc_q == q && h->rc_n == n && h->rc_fs == fs)) {
+        std::vector<float> hp((size_t)P * M);
+        for (int l = -P / 2; l < P / 2; ++l)
+            for (int r = 0; r < M; ++r) {
+                long dist = std::labs((long)r + (long)M * l);
+                hp[(size_t)(l + P / 2) * M + r] = dist < E.L ? (float)g[dist] : 0.f;
+            }
+        std::vector<float2> twv(N1 + N2 + M);
+        for (int i = 0; i < N1; ++i) twv[i] = make_float2((float)std::cos(2 * M_PI * i / N1), (float)std::sin(2 * M_PI * i / N1));
+        for (int i = 0; i < N2; ++i) twv[N1 + i] = make_float2((float)std::cos(2 * M_PI * i / N2), (float)std::sin(2 * M_PI * i / N2));
+        for (int i = 0; i < M; ++i) twv[N1 + N2 + i] = make_float2((float)std::cos(2 * M_PI * i / M), (float)std::sin(2 * M_PI * i / M));
+        std::vector<double> fr(M);
+        for (int k = 0; k < M; ++k) fr[k] = (k < M / 2 ? k : k - M) * (fs / M);      // centre frequency of DFT bin k
+        TB_CUDA(cudaMemcpyAsync(proto, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        TB_CUDA(cudaMemcpyAsync(tw, twv.data(), twv.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
+        TB_CUDA(cudaMemcpyAsync(gdev, g.data(), ((size_t)E.L + 32) * sizeof(double), cudaMemcpyHostToDevice, st));
+        TB_CUDA(cudaMemcpyAsync(fdev, fr.data(), fr.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        TB_CUDA(cudaStreamSynchronize(st));            // host vectors go out of scope
+        h->rc_M = M; h->rc_q = q; h->rc_n = n; h->rc_fs = fs;
+    }
+    int F = 8;
+    int log2_n2 = 0;
+    while ((1 << log2_n2) < N2) ++log2_n2;
+    auto need = [&](int f) { return sizeof(float2) * ((size_t)f * M + (size_t)f * N1 * (N2 + 1) + N1 + N2 + M); };
+    size_t smem = need(F);
+    while (smem > 100 * 1024 && F > 1) { F /= 2; smem = need(F); }
+    if (smem > 200 * 1024) return fail(TB200_E_ARG, "refchan: M=%d too large for shared memory", M);
+    cudaError_t e = cudaFuncSetAttribute(refchan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(refchan): %s", cudaGetErrorString(e));
+    unsigned blocks = (unsigned)((n_dec + F - 1) / F);
+    refchan_kernel<<<blocks, 256, smem, st>>>(x, n, M, N1, log2_n2, F, P, q, n_dec, proto, tw, out, out_stride);
+    TB_LAUNCH_CHECK(h);
+    refchan_edge_kernel<<<M, 128, 0, st>>>(x, n, q, fs, fdev, n_dec, gdev, E, out, out_stride);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+}  // namespace tb200

@@ -176,3 +176,19 @@ def make_burst_batch(n_bursts, seed=99, fractions=(0.5, 0.25, 0.25), sync_fracti
     out[:, 139:] = tail
     out[:, 127:139] = keep
     return out
+
+
+def make_wideband(n_samples, carriers, sample_rate=20e6, n_channels=800, samples_per_symbol=1079, seed=5,
+                  sigma=0.02, amplitude=0.05):
+    """C4 input: a wideband capture with independent reference-matched carriers.
+
+    ``carriers``: channel numbers k (centre k * sample_rate / n_channels, negative allowed), each modulated with its own
+    back-to-back bursts at ``samples_per_symbol`` = q * sps of the wideband rate (83 * 13 = 1079 at 20 MS/s), summed,
+    plus complex AWGN of ``sigma`` per component over the whole band.  complex64."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n_samples, dtype=np.float64)
+    x = sigma * (rng.standard_normal(n_samples) + 1j * rng.standard_normal(n_samples))
+    for i, k in enumerate(carriers):
+        base = make_capture(n_samples, samples_per_symbol, seed=seed * 1000 + i, sigma=0.0, amplitude=amplitude).astype(np.complex128)
+        x += base * np.exp(2j * np.pi * (k / n_channels) * t + 1j * rng.uniform(0, 2 * np.pi))
+    return x.astype(np.complex64)
