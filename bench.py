@@ -734,6 +734,182 @@ def run_c5(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------ c4: wideband, reference mode
+C4_FS, C4_M, C4_CHUNK, C4_RING = 20e6, 800, 1 << 20, 16
+C4_CARRIERS = [0, 1, -1, 7, -37, 120, 399, -400, 250, -333, 64, -199, 3, 311, -272, 158]
+
+
+def _ref_c4_worker(args):
+    """The reference's only way to a channel of a wideband chunk: frequency_shift + process + decode, per channel."""
+    global _REF
+    import logging
+    logging.disable(logging.CRITICAL)
+    if _REF is None:
+        from oracle import ref_bridge
+        _REF = ref_bridge.load()
+    SP, TD, _ = _REF
+    x, channels = args
+    t0 = time.perf_counter()
+    crc = 0
+    for ch in channels:
+        sp = SP(C4_FS)
+        d = sp.process(sp.frequency_shift(x, ch * C4_FS / C4_M), 0)
+        dec = TD(auto_decrypt=False)
+        if len(d) >= 255:
+            dec.decode(d)
+        crc += dec.protocol_parser.stats["crc_pass"]
+    return len(channels), crc, time.perf_counter() - t0
+
+
+def run_c4(args):
+    """BASELINE config 4 in REFERENCE mode: 20 MS/s wideband chunks of 2^20 samples, all 800 x 25 kHz channels of every
+    chunk demodulated to dibits and decoded exactly as process(frequency_shift(x, f_k)) + decode would per channel
+    (tests/test_gpu_multichannel.py).  A step = a ring of 16 different chunks (128 MB > L2).  Rank r owns its own ring
+    (weak scaling over capture segments, no collective)."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.set_device(local_rank)
+    from tetraear_b200 import synth
+    from tetraear_b200.multichannel import WidebandReceiver
+    dev = torch.device(f"cuda:{local_rank}")
+    base = synth.make_wideband(C4_CHUNK, C4_CARRIERS, C4_FS, C4_M, 1079, seed=5 + rank)
+    host = torch.from_numpy(base.view(np.float32).reshape(-1, 2)).pin_memory()
+    ring = torch.empty((C4_RING, C4_CHUNK, 2), dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev); g.manual_seed(40 + rank)
+    for i in range(C4_RING):                       # same carriers, fresh wideband noise per ring slot
+        ring[i].copy_(host, non_blocking=True)
+        ring[i] += 0.005 * torch.randn((C4_CHUNK, 2), generator=g, device=dev, dtype=torch.float32)
+    rx = WidebandReceiver(C4_FS, C4_M, C4_CHUNK, mode="fast32", device=local_rank, keep_symbols=False)
+    stream = torch.cuda.current_stream()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+
+    def step():
+        for i in range(C4_RING):
+            rx.run_device(ring[i])
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    l0 = rx.launches
+    step()
+    launches_per_step = rx.launches - l0
+    sync_all()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    rx.stats.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    stats = rx.stats.cpu().numpy().copy()
+    # end to end: pinned host chunk -> H2D -> kernels -> D2H of the per-channel frame counts and records
+    stage = torch.empty((C4_CHUNK, 2), dtype=torch.float32, device=dev)
+    h_nfr = torch.empty((C4_M,), dtype=torch.int32).pin_memory()
+    h_frames = torch.empty(rx.frames.shape, dtype=torch.uint8).pin_memory()
+
+    def step_host():
+        for _ in range(C4_RING):
+            stage.copy_(host, non_blocking=True)
+            rx.run_device(stage)
+            h_nfr.copy_(rx.n_frames, non_blocking=True)
+            h_frames.copy_(rx.frames, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    step_host()
+    sync_all()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_e2e = max(1, min(args.steps, 10))
+    t0.record(stream)
+    for _ in range(k_e2e):
+        step_host()
+    t1.record(stream)
+    sync_all()
+    ms_e2e = t0.elapsed_time(t1) / k_e2e
+    clk = clocks.stop() if clocks else None
+    # per-stage device time
+    for hh in (rx.bank, rx.rx):
+        hh.profile(True)
+    step()
+    torch.cuda.synchronize()
+    prof = {}
+    for hh in (rx.bank, rx.rx):
+        for k, (tms, calls) in hh.profile_read().items():
+            if calls:
+                prof[k] = round(prof.get(k, 0.0) + tms / C4_RING, 4)
+        hh.profile(False)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        c = torch.tensor(stats, dtype=torch.int64, device=dev); dist.all_reduce(c); stats = c.cpu().numpy()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    samples_per_step = C4_RING * C4_CHUNK
+    total = samples_per_step * world * args.steps
+    value = total / (ms / 1e3) / 1e6
+    step_ms = ms / args.steps
+    cpu = None
+    if world == 1 and not args.no_cpu and reference_available():
+        import multiprocessing as mp
+        cores = host_cores()
+        chans = C4_CARRIERS[:8]
+        parts = [chans[i::cores] for i in range(min(cores, len(chans)))]
+        with mp.get_context("fork").Pool(len(parts)) as pool:
+            pool.map(_ref_c4_worker, [(base[:65536], p[:1]) for p in parts])
+            w0 = time.perf_counter()
+            res = pool.map(_ref_c4_worker, [(base, p) for p in parts])
+            wall = time.perf_counter() - w0
+        per_channel_s = wall * len(parts) / len(chans)        # CPU seconds per (channel, chunk)
+        cpu = {"value": round(C4_CHUNK / (per_channel_s * C4_M / cores) / 1e6, 4), "unit": "Msamples/s", "cores": cores,
+               "kind": "reference",
+               "sample": f"8 of 800 channels of one 2^20-sample chunk through the unmodified frequency_shift + process + decode "
+                         f"({wall:.2f} s wall on {len(parts)} workers), scaled x100 to all 800 channels on {cores} cores",
+               "crc_pass_8_channels": int(sum(r[1] for r in res))}
+    alg = samples_per_step * 8.0 + C4_RING * C4_M * rx.stride * 1.0
+    line = {
+        "metric": "iq_msamples_per_s", "value": round(value, 3), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c4: wideband 20 MS/s capture, 800 x 25 kHz channels, reference mode (every channel == "
+                               "process(frequency_shift(x, f_k)) + decode), 16 chunks x 2^20 samples per step per GPU, 16 active carriers",
+                   "l2": "ring of 16 chunks = 128 MB per step > 126 MB L2", "parallelism": f"capture segment per GPU x{world}"},
+        "channel_msamples_per_s": round(value * C4_M, 1), "realtime_factor": round(value / 20.0, 1),
+        "crc_pass_bursts_per_s": round(float(stats[1]) / (ms / 1e3), 1), "gpu_launches": int(launches_per_step * args.steps),
+        "e2e": {"value": round(samples_per_step * world / (ms_e2e / 1e3) / 1e6, 3), "unit": "Msamples/s",
+                "h2d_bytes_per_step": samples_per_step * 8, "d2h_bytes_per_step": C4_RING * (C4_M * 4 + int(np.prod(rx.frames.shape))),
+                "ms_per_step": round(ms_e2e, 4)},
+        "roofline": {"bound": "hbm", "kernel": "whole c4 step (channel bank + channel filter + slicer + decode)",
+                     "achieved": round(alg / (step_ms / 1e3) / 1e9, 2), "peak": peak, "unit": "GB/s",
+                     "frac": round(alg / (step_ms / 1e3) / 1e9 / peak, 5), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg, "stage_ms_per_chunk": prof,
+                     "note": "8 B per wideband sample read once + 1 B per dibit (SURVEY 8(d)); the channel bank is a direct two-stage "
+                             "DFT (FP32-issue bound), not HBM bound"},
+        "clocks": clk,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     """The reference's CPU implementation of the path (oracle port: the reference is pure Python and
@@ -791,12 +967,15 @@ def main():
                     help="sub-batches processed on concurrent streams (overlaps the latency-bound tail kernels)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default=os.environ.get("TB200_BENCH_MODE", "fast"), choices=["exact", "fast", "fast32", "fast-tc", "fast32-tc"])
-    ap.add_argument("--workload", default="c1", choices=["c1", "c5"], help="c1 = headline; c5 = multichannel archive replay")
+    ap.add_argument("--workload", default="c1", choices=["c1", "c4", "c5"],
+                    help="c1 = headline; c4 = wideband 800-channel chunk in reference mode; c5 = multichannel archive replay (etsi mode)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the other-workload kernel figures")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c4":
+        run_c4(args)
     elif args.workload == "c5":
         run_c5(args)
     else:

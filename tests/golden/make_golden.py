@@ -217,7 +217,20 @@ def gen_voice():
             valid[i] = 1
     none_pos = fn(None, {}, dibits, 13)
     assert none_pos is None
-    save("voice.npz", in_sha=np.array(sha(dibits)), blocks=blocks, valid=valid)
+    # the inline bit-row builder of continuous_capture.py:103-124, exec'd from its source lines per frame
+    cc = os.path.join(ref_bridge.REFERENCE_ROOT, "continuous_capture.py")
+    bsrc = _lines(cc, 103, 124)
+    assert bsrc.startswith("soft_bits = [127 if int(b) else -127") and bsrc.rstrip().endswith("dtype=np.int16).tobytes()")
+    _, _, bit_rows = voice_cases()
+    bit_blocks = np.zeros((len(bit_rows), 690), np.int16)
+    bit_valid = np.zeros(len(bit_rows), np.uint8)
+    for i, bits in enumerate(bit_rows):
+        if bits is not None and len(bits) >= 432:              # the guard of continuous_capture.py:102
+            ns = {"np": np, "bits": bits}
+            exec(bsrc, ns)
+            bit_blocks[i] = np.frombuffer(ns["codec_input"], dtype="<i2")
+            bit_valid[i] = 1
+    save("voice.npz", in_sha=np.array(sha(dibits)), blocks=blocks, valid=valid, bit_blocks=bit_blocks, bit_valid=bit_valid)
 
 
 def gen_afc():

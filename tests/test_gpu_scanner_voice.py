@@ -113,11 +113,13 @@ def test_voice_blocks_match_reference_golden(mods):
         if got[i] is not None:
             assert len(got[i]) == 1380 and np.array_equal(np.frombuffer(got[i], "<i2"), g["blocks"][i]), p
     fb, fp = vb.from_bits(bit_rows), vb.from_params(bit_rows)
-    for r, b, p in zip(bit_rows, fb, fp):
+    for i, (r, b, p) in enumerate(zip(bit_rows, fb, fp)):
         want = ov.from_bits(r)
-        assert (b is None) == (want is None)
+        assert (b is None) == (want is None) == (not g["bit_valid"][i])
         if want is not None:
             assert np.array_equal(np.frombuffer(b, "<i2"), want)
+            # pinned: the reference's own lines (continuous_capture.py:103-124) exec'd by tests/golden/make_golden.py
+            assert np.array_equal(np.frombuffer(b, "<i2"), g["bit_blocks"][i]), i
             assert np.array_equal(np.frombuffer(p, "<i2"), ov.from_params(r))
     # every 6/7/3-bit field value of the parameter packing (int() truncation of float64 products)
     rows = []

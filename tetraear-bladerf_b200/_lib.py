@@ -109,9 +109,19 @@ def last_error():
     return load().tb200_last_error().decode("utf-8", "replace")
 
 
+class ComputeError(RuntimeError):
+    """A compute entry point refused its input (status code < 0).  Distinct from the RuntimeError raised when the
+    library or a CUDA device is missing: the class API turns THIS one into the reference's log-and-return-empty
+    behaviour (processor.py:81-83, :256-257), never the missing-backend one."""
+
+    def __init__(self, rc, msg):
+        super().__init__(f"libtetra_b200 error {rc}: {msg}")
+        self.rc = rc
+
+
 def check(rc):
     if rc != 0:
-        raise RuntimeError(f"libtetra_b200 error {rc}: {last_error()}")
+        raise ComputeError(rc, last_error())
 
 
 def require_device():

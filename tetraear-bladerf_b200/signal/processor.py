@@ -83,10 +83,21 @@ class SignalProcessor:
         return y if np.iscomplexobj(x_in) else y.real.astype(x_in.dtype if x_in.dtype.kind == "f" else np.float64)
 
     def process(self, samples, freq_offset=0):
-        """processor.py:221-273: decimate -> NCO -> Butterworth -> timing pick -> DQPSK slicer."""
+        """processor.py:221-273: decimate -> NCO -> Butterworth -> timing pick -> DQPSK slicer.
+        Like the reference (its stages log and carry on, processor.py:81-83, :256-257; callers rely on it,
+        ui/modern.py:2087-2089), an input the kernels refuse is logged and answered with an empty result instead of
+        an exception; a missing library / device still raises."""
         if len(samples) == 0:
             self.symbols = np.array([], dtype=complex)
             return np.array([], dtype=np.uint8)
+        try:
+            return self._process(samples, freq_offset)
+        except _lib.ComputeError as e:
+            logger.error(f"process failed: {e}")
+            self.symbols = np.array([], dtype=complex)
+            return np.array([], dtype=np.uint8)
+
+    def _process(self, samples, freq_offset):
         x, dt = _as_complex(samples)
         n = len(x)
         h = self._handle(n)
