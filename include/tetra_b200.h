@@ -131,6 +131,12 @@ int tb200_set_sample_rate(tb200_handle h, double sample_rate); /* attr is mutate
  * filter, same float32-level accuracy (<= 1e-4 of full scale vs the reference; 7e-7 of full scale from the exact-arithmetic
  * filter).  Default 0: on this round's B200 measurements the FFMA2 kernel is the faster of the two. */
 #define TB200_OPT_DECIM_TC 3
+/* TB200_OPT_PSD_AVG = 4: linear (Welch) averaging for tb200_psd_batch: value K >= 1; the n_frames input frames are taken
+ * K at a time and every OUTPUT frame (floor(n_frames / K) of them; power, smoothed and stats rows) is
+ * 20 log10( sqrt(mean_k (|X_k| / N)^2) + 1e-20 ), i.e. the reference's dBFS formula (ui/modern.py:1941) on the RMS of the K
+ * amplitude spectra; K = 1 (default) is the reference's per-frame spectrum.  The dB-domain EMA, if requested, runs over
+ * the averaged frames. */
+#define TB200_OPT_PSD_AVG 4
 int tb200_set_option(tb200_handle h, int option, int value);
 size_t tb200_workspace_bytes(tb200_handle h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */

@@ -340,6 +340,26 @@ def psd_frame(samples, sample_rate, n_fft=2048):
     return freqs, power
 
 
+def psd_welch(samples, sample_rate, n_fft=4096, average=8):
+    """BASELINE configs[1] "4096-pt windowed FFT w/ averaging": the reference's per-frame amplitude spectrum
+    (ui/modern.py:1932-1941: Hann window, fftshift(fft), |X|/N) averaged LINEARLY in power over `average` consecutive
+    dense frames, then the reference's dBFS formula on the RMS amplitude, 20 log10(rms + 1e-20).  average = 1 is
+    psd_frame.  The reference itself has no linear averaging (dB-domain EMA only) — parity unpinned, this is
+    the restatement the CUDA kernel is checked against.  Returns float64 [n_out, n_fft]."""
+    x = np.asarray(samples)
+    nfr = len(x) // n_fft
+    n_out = nfr // average
+    w = np.hanning(n_fft)
+    out = np.empty((n_out, n_fft))
+    for o in range(n_out):
+        acc = np.zeros(n_fft)
+        for k in range(average):
+            seg = x[(o * average + k) * n_fft:(o * average + k + 1) * n_fft]
+            acc += (np.abs(np.fft.fftshift(np.fft.fft(seg * w))) / n_fft) ** 2
+        out[o] = 20 * np.log10(np.sqrt(acc / average) + 1e-20)
+    return out
+
+
 def band_stats(power, sample_rate, n_fft=None):
     """ui/modern.py:1956-2010, :2028 -> dict(signal_power, peak_power, peak_idx,
     peak_freq_offset, noise_floor, snr, signal_present, afc_offset)."""

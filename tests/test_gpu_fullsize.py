@@ -109,3 +109,42 @@ def test_c2_sixty_seconds_psd(mods):
     assert torch.equal(smooth[0], power[0])
     err = (s64[1:] - (0.85 * s64[:-1] + 0.15 * p64[1:])).abs().max().item()
     assert err <= 2e-4, err          # float32 storage of S: 120 dB * 2^-24 * a few steps
+
+
+@pytest.mark.parametrize("precision,n_fft,avg", [("f64", 4096, 8), ("f32", 4096, 8), ("f32", 4096, 3), ("f64", 2048, 4), ("f32", 1024, 5)])
+def test_psd_linear_averaging_matches_oracle(mods, precision, n_fft, avg):
+    """BASELINE configs[1] "w/ averaging": K-frame linear (Welch) power average before the dB conversion, against
+    oracle.psd_welch (the reference's per-frame formula, ui/modern.py:1932-1941, averaged in power; parity unpinned — the
+    reference only has the dB-domain EMA) — abs <= 1e-3 dB where P > -120 dB, statistics from the averaged frame, and
+    K = 1 unchanged (bit-identical to the un-averaged call)."""
+    import torch
+    from tetraear_b200.signal import SpectrumAnalyzer
+    from tetraear_b200 import synth
+    fs = 2.4e6
+    nfr = 4 * avg + 2                                           # two input frames are left over and must be ignored
+    x = synth.make_capture(nfr * n_fft, 130, seed=9, amplitude=0.1)
+    x = (x + 0.03 * np.exp(2j * np.pi * 7300.0 / fs * np.arange(len(x)))).astype(np.complex64)
+    d = torch.from_numpy(x.view(np.float32).reshape(-1, 2)).cuda()
+    an = SpectrumAnalyzer(fs, n_fft, device=0, precision=precision, average=avg)
+    p, s, st = an.run_device(d, nfr, n_fft, denoise=True)
+    torch.cuda.synchronize()
+    assert p.shape[0] == nfr // avg == 4
+    want = oracle.psd_welch(x, fs, n_fft, avg)
+    got = p.cpu().numpy().astype(np.float64)
+    m = want > -120
+    assert np.abs(got[m] - want[m]).max() <= 1e-3
+    for k in range(4):
+        assert int(np.argmax(got[k])) == int(np.argmax(want[k]))
+        ws = oracle.band_stats(want[k], fs, n_fft)
+        row = st[k].cpu().numpy()
+        assert abs(row[0] - ws["signal_power"]) <= 1e-3 and int(row[2]) == ws["peak_idx"]
+    # EMA over the averaged frames
+    sm = s.cpu().numpy().astype(np.float64)
+    assert np.array_equal(sm[0], got[0].astype(np.float32).astype(np.float64))
+    assert np.abs(sm[1:] - (0.85 * sm[:-1] + 0.15 * got[1:])).max() <= 2e-4
+    # K = 1 is the plain spectrum
+    a1 = SpectrumAnalyzer(fs, n_fft, device=0, precision=precision, average=1)
+    a0 = SpectrumAnalyzer(fs, n_fft, device=0, precision=precision)
+    p1, _, _ = a1.run_device(d, nfr, n_fft)
+    p0, _, _ = a0.run_device(d, nfr, n_fft)
+    assert torch.equal(p1, p0)

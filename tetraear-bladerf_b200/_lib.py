@@ -17,6 +17,7 @@ MODE_EXACT, MODE_FAST = 0, 1
 OPT_CHAN_F32 = 1
 OPT_PSD_F32 = 2
 OPT_DECIM_TC = 3
+OPT_PSD_AVG = 4
 
 
 class Config(C.Structure):

@@ -284,6 +284,7 @@ extern "C" int tb200_set_option(tb200_handle h, int option, int value)
     case TB200_OPT_CHAN_F32: h->chan_f32 = value ? 1 : 0; return TB200_OK;
     case TB200_OPT_PSD_F32: h->psd_f32 = value ? 1 : 0; return TB200_OK;
     case TB200_OPT_DECIM_TC: h->decim_tc = value ? 1 : 0; return TB200_OK;
+    case TB200_OPT_PSD_AVG: h->psd_avg = value > 1 ? value : 1; return TB200_OK;
     default: return fail(TB200_E_ARG, "tb200_set_option: unknown option %d", option);
     }
 }
@@ -712,7 +713,7 @@ extern "C" int tb200_psd_batch(tb200_handle h, const void *d_iq_c64, int64_t n_f
     if (d_smoothed && (!d_power || !d_ema_state)) return fail(TB200_E_ARG, "tb200_psd_batch: smoothing needs d_power and d_ema_state");
     StageTimer tm(h, TB_STAGE_PSD, (cudaStream_t)stream);
     return launch_psd(h, (const float *)d_iq_c64, n_frames, frame_stride, n_fft, sample_rate, ema_alpha, first, d_power,
-                      d_smoothed, d_ema_state, d_stats, h->psd_tables, (cudaStream_t)stream, h->psd_f32);
+                      d_smoothed, d_ema_state, d_stats, h->psd_tables, (cudaStream_t)stream, h->psd_f32, h->psd_avg > 1 ? h->psd_avg : 1);
 }
 
 // ------------------------------------------------------------------------- debugging aid

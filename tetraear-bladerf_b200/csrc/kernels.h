@@ -32,7 +32,7 @@ int launch_crc16_rows(tb200_handle h, const uint8_t *bits, int n_rows, int n_bit
                       cudaStream_t st);
 int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_stride, int n_fft, double fs,
                double alpha, int first, float *power, float *smoothed, double *ema_state, double *stats,
-               double *scratch_db, cudaStream_t st, int use_f32 = 0);
+               double *scratch_db, cudaStream_t st, int use_f32 = 0, int avg = 1);
 int launch_etsi_decode(tb200_handle h, const int8_t *soft, long n, int channel, uint32_t scramb_init, uint8_t *bits,
                        uint8_t *crc_ok, int32_t *metric, cudaStream_t st);
 int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, long stride, double fs, float *taps_dev,

@@ -52,15 +52,20 @@ extern __shared__ __align__(16) unsigned char psd_smem_raw[];
 template <typename T>
 __global__ void psd_kernel(const float2 *__restrict__ iq, long frame_stride, int n_fft, int log2n,
                            const double *__restrict__ window, const double2 *__restrict__ tw, BandParams bp,
-                           float *__restrict__ power, double *__restrict__ stats)
+                           float *__restrict__ power, double *__restrict__ stats, int avg)
 {
     typedef typename V2<T>::type C;
     C *x = reinterpret_cast<C *>(psd_smem_raw);
     __shared__ double red[3][32];
     __shared__ int redi[32];
-    const long frame = blockIdx.x;
-    const float2 *in = iq + frame * frame_stride;
+    const long frame = blockIdx.x;                  // OUTPUT frame: the linear (Welch) average of `avg` input frames
     const int N = n_fft;
+    T acc[8];                                       // sum over the averaged frames of (|X| / N)^2 for this thread's bins
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = (T)0;
+    for (int ka = 0; ka < avg; ++ka) {
+    const float2 *in = iq + (frame * avg + ka) * frame_stride;
+    if (ka) __syncthreads();                        // the previous frame's bins have been read
     // load, window, bit-reverse (radix-2 ordering)
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         float2 v = in[i];
@@ -104,13 +109,25 @@ __global__ void psd_kernel(const float2 *__restrict__ iq, long frame_stride, int
         len = L4;
         __syncthreads();
     }
+    if (avg > 1) {
+        const T invNa = (T)1 / (T)N;
+        int i = 0;
+        for (int j = threadIdx.x; j < N; j += blockDim.x, ++i) {
+            const T mg = mag2(x[(j + N / 2) & (N - 1)]) * invNa;
+            acc[i & 7] += mg * mg;
+        }
+    }
+    }   // averaged frames
     // dBFS, fftshift, band statistics
     const T invN = (T)1 / (T)N;   // |X| / n_fft : power-of-two N, the product is exact
     double sig = 0.0, noise = 0.0, pk = -1e300;
     int pki = 0x7fffffff;
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    int ia = 0;
+    for (int j = threadIdx.x; j < N; j += blockDim.x, ++ia) {
         C v = x[(j + N / 2) & (N - 1)];
-        double p = (double)db20(mag2(v) * invN);
+        // avg == 1: the reference's formula 20 log10(|X|/N + 1e-20) (ui/modern.py:1941); avg > 1: the same with |X|/N
+        // replaced by its RMS over the averaged frames (linear power average, then dB)
+        double p = avg > 1 ? (double)db20((T)sqrt(acc[ia & 7] / (T)avg)) : (double)db20(mag2(v) * invN);
         if (power) power[frame * N + j] = (float)p;
         if (j >= bp.start && j < bp.end) {
             sig += p;
@@ -200,7 +217,7 @@ __device__ __forceinline__ int dft16_index(int p) { return (p >> 2) + 4 * (p & 3
 
 __global__ void __launch_bounds__(256, 3)
 psd4096_f32_kernel(const float2 *__restrict__ iq, long frame_stride, long n_frames, const double *__restrict__ window,
-                   const double2 *__restrict__ tw, BandParams bp, float *__restrict__ power, double *__restrict__ stats)
+                   const double2 *__restrict__ tw, BandParams bp, float *__restrict__ power, double *__restrict__ stats, int avg)
 {
     constexpr int N = 4096;
     float2 *buf = reinterpret_cast<float2 *>(psd_smem_raw);   // pass exchange: Y[c][b] (pitch 256), then Z[t][f] (pitch 17)
@@ -228,9 +245,14 @@ psd4096_f32_kernel(const float2 *__restrict__ iq, long frame_stride, long n_fram
     __syncthreads();
     const float invN = 1.0f / (float)N;
     const int lane = t & 31, wp = t >> 5;
-    for (long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
-        const float2 *in = iq + frame * frame_stride;
+    for (long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {      // OUTPUT frames (averages of `avg` input frames)
+        float acc[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) acc[p] = 0.f;
         float2 v[16];
+        for (int ka = 0; ka < avg; ++ka) {
+        const float2 *in = iq + (frame * avg + ka) * frame_stride;
+        if (ka) __syncthreads();                               // buf is reused
 #pragma unroll
         for (int a = 0; a < 16; ++a) { const float2 x = in[256 * a + t]; v[a] = make_float2(x.x * win[a], x.y * win[a]); }
         dft16(v);
@@ -256,6 +278,11 @@ psd4096_f32_kernel(const float2 *__restrict__ iq, long frame_stride, long n_fram
 #pragma unroll
         for (int f = 0; f < 16; ++f) v[f] = buf[t * P4_PITCH + f];
         dft16(v);
+        if (avg > 1) {
+#pragma unroll
+            for (int p = 0; p < 16; ++p) { const float mg = mag2(v[p]) * invN; acc[p] = fmaf(mg, mg, acc[p]); }
+        }
+        }   // averaged frames
         // dBFS, fftshift, band statistics
         double sig = 0.0, noise = 0.0, pk = -1e300;
         int pki = 0x7fffffff;
@@ -263,7 +290,7 @@ psd4096_f32_kernel(const float2 *__restrict__ iq, long frame_stride, long n_fram
         for (int p = 0; p < 16; ++p) {
             const int k = t + 256 * dft16_index(p);
             const int j = (k + N / 2) & (N - 1);
-            const double pdb = (double)db20(mag2(v[p]) * invN);
+            const double pdb = avg > 1 ? (double)db20(sqrtf(acc[p] / (float)avg)) : (double)db20(mag2(v[p]) * invN);
             if (power) power[frame * N + j] = (float)pdb;
             if (j >= bp.start && j < bp.end) {
                 sig += pdb;
@@ -343,8 +370,11 @@ __global__ void psd_ema_kernel(const float *__restrict__ power, long n_frames, i
 
 int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_stride, int n_fft, double fs,
                double alpha, int first, float *power, float *smoothed, double *ema_state, double *stats,
-               double *tables, cudaStream_t st, int use_f32)
+               double *tables, cudaStream_t st, int use_f32, int avg)
 {
+    // linear (Welch) averaging: every output frame is the power average of `avg` consecutive input frames
+    if (avg < 1) avg = 1;
+    n_frames /= avg;
     if (n_frames <= 0) return TB200_OK;
     int log2n = 0;
     while ((1 << log2n) < n_fft) ++log2n;
@@ -374,7 +404,7 @@ int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_
             attr4 = true;
         }
         const long ctas = n_frames < 3 * 148 ? n_frames : 3 * 148;            // persistent: 3 CTAs per SM
-        psd4096_f32_kernel<<<(unsigned)ctas, 256, sm4, st>>>((const float2 *)iq, frame_stride, n_frames, window, tw, bp, power, stats);
+        psd4096_f32_kernel<<<(unsigned)ctas, 256, sm4, st>>>((const float2 *)iq, frame_stride, n_frames, window, tw, bp, power, stats, avg);
         TB_LAUNCH_CHECK(h);
     } else {
     size_t smem = (use_f32 ? sizeof(float2) : sizeof(double2)) * (size_t)n_fft;
@@ -386,10 +416,10 @@ int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_
     int threads = n_fft >= 2048 ? 512 : (n_fft >= 512 ? 128 : 64);
     if (use_f32)
         psd_kernel<float><<<(unsigned)n_frames, threads, smem, st>>>((const float2 *)iq, frame_stride, n_fft, log2n, window, tw, bp,
-                                                                    power, stats);
+                                                                    power, stats, avg);
     else
         psd_kernel<double><<<(unsigned)n_frames, threads, smem, st>>>((const float2 *)iq, frame_stride, n_fft, log2n, window, tw, bp,
-                                                                     power, stats);
+                                                                     power, stats, avg);
     TB_LAUNCH_CHECK(h);
     }
     if (smoothed) {

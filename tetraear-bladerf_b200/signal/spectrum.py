@@ -28,7 +28,7 @@ class SpectrumAnalyzer:
     config mode    : any power-of-two n_fft (e.g. 4096), frame_stride = n_fft (dense).
     """
 
-    def __init__(self, sample_rate=2.4e6, n_fft=2048, ema_alpha=0.15, device=0, precision="f64"):
+    def __init__(self, sample_rate=2.4e6, n_fft=2048, ema_alpha=0.15, device=0, precision="f64", average=1):
         self.sample_rate = float(sample_rate)
         self.n_fft = int(n_fft)
         self.ema_alpha = float(ema_alpha)
@@ -38,6 +38,11 @@ class SpectrumAnalyzer:
         if precision == "f32":
             self._h.set_option(_lib.OPT_PSD_F32, 1)
         self.precision = precision
+        # linear (Welch) averaging: every output frame = power average of `average` consecutive input frames (then dB);
+        # 1 = the reference's per-frame spectrum.  The EMA ("denoise") then runs over the averaged frames.
+        self.average = max(1, int(average))
+        if self.average > 1:
+            self._h.set_option(_lib.OPT_PSD_AVG, self.average)
         self._state = None
         self._first = True
         self.freqs = _freq_axis(self.n_fft, self.sample_rate)
@@ -52,12 +57,13 @@ class SpectrumAnalyzer:
         import torch
         from .. import _dev
         dev = self.device
+        n_out = int(n_frames) // self.average            # rows written (== n_frames without averaging)
         if power is None:
-            power = _dev.empty((n_frames, self.n_fft), torch.float32, dev)
+            power = _dev.empty((n_out, self.n_fft), torch.float32, dev)
         if denoise and smoothed is None:
-            smoothed = _dev.empty((n_frames, self.n_fft), torch.float32, dev)
+            smoothed = _dev.empty((n_out, self.n_fft), torch.float32, dev)
         if want_stats and stats is None:
-            stats = _dev.empty((n_frames, 8), torch.float64, dev)
+            stats = _dev.empty((n_out, 8), torch.float64, dev)
         if self._state is None:
             self._state = _dev.zeros((self.n_fft,), torch.float64, dev)
         h = self._h
