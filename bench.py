@@ -102,6 +102,37 @@ def _ref_worker(args):
     return n, crc, time.perf_counter() - t0
 
 
+def _ref_burst_worker(rows):
+    """TetraProtocolParser.parse_burst of the unmodified reference over a block of 255-dibit rows."""
+    global _REF
+    import logging
+    logging.disable(logging.CRITICAL)
+    if _REF is None:
+        from oracle import ref_bridge
+        _REF = ref_bridge.load()
+    p = _REF[2]()
+    t0 = time.perf_counter()
+    ok = 0
+    for r in rows:
+        b = p.parse_burst(r)
+        ok += bool(b is not None and b.crc_ok)
+    return len(rows), ok, time.perf_counter() - t0
+
+
+def _psd_worker(args):
+    """The reference's per-frame spectrum block (ui/modern.py:1928-1941 restated in oracle.psd_frame: Hann window, fft,
+    fftshift, dB) + the GUI's dB-domain EMA (:929-935) over dense frames."""
+    from oracle import oracle
+    x, n_fft = args
+    t0 = time.perf_counter()
+    S = None
+    for k in range(len(x) // n_fft):
+        out = oracle.psd_frame(x[k * n_fft:(k + 1) * n_fft], FS, n_fft)
+        P = out[1] if isinstance(out, tuple) else out
+        S = P if S is None else S * 0.85 + P * 0.15
+    return len(x) // n_fft * n_fft, time.perf_counter() - t0
+
+
 def reference_available():
     from oracle import ref_bridge
     return ref_bridge.available()
@@ -187,9 +218,38 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def _cpulist(text):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out += list(range(int(a), int(b or a) + 1))
+    return out
+
+
 def bind_to_gpu_numa(torch, local_rank):
-    """Pin this rank to the CPUs NVML lists as local to its GPU, so that the pinned staging buffer it allocates
-    next is first-touched on that NUMA node (matters for the end-to-end figure when several ranks copy at once)."""
+    """Pin this rank to the CPUs of its GPU's NUMA node, so that the pinned staging buffer it allocates next is placed
+    on that node (matters for the end-to-end figure when several ranks copy at once).  The node comes from sysfs
+    (/sys/bus/pci/devices/<gpu>/numa_node + /sys/devices/system/node/nodeN/cpulist, intersected with the CPUs this
+    process may use); NVML's affinity mask, which inside a container is often just the container's CPU set, is the
+    fallback.  Returns (number of CPUs bound to, numa node or -1)."""
+    allowed = set(os.sched_getaffinity(0))
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus = sorted(set(_cpulist(f.read())) & allowed)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                return len(cpus), node
+    except Exception:
+        pass
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -197,12 +257,12 @@ def bind_to_gpu_numa(torch, local_rank):
         h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
         n = os.cpu_count()
         mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
-        cpus = [i for i in range(n) if (mask[i // 64] >> (i % 64)) & 1]
+        cpus = sorted({i for i in range(n) if (mask[i // 64] >> (i % 64)) & 1} & allowed)
         if cpus:
             os.sched_setaffinity(0, cpus)
-        return len(cpus)
+        return len(cpus), -1
     except Exception:
-        return 0
+        return 0, -1
 
 
 def run_b200(args):
@@ -222,9 +282,11 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     from tetraear_b200 import pipeline, _lib
     all_cpus = os.sched_getaffinity(0)
-    numa_cpus = bind_to_gpu_numa(torch, local_rank) if world > 1 else 0
+    numa_cpus, numa_node = bind_to_gpu_numa(torch, local_rank) if world > 1 else (0, -1)
 
-    # every rank owns one independent 10 s capture (weak scaling: shard = capture segment per GPU)
+    # weak scaling over capture segments: the job's capture is world x 10 s, rank r owns segment r (183 chunks); chunks
+    # are stateless (ui/modern.py:1915-1919), so the segments need no exchange — the only communication is the gather of
+    # the frame records on rank 0 (NCCL, inside the timed region, every step)
     x = make_c1(seed=1234 + rank)
     n_chunks = x.shape[0]
     samples_per_step = n_chunks * CHUNK
@@ -259,19 +321,43 @@ def run_b200(args):
             graphs, graph_error = None, repr(e)[:200]
             torch.cuda.synchronize()
 
+    gathered = None
+    if world > 1:
+        # final gather of every step: frame records + counts of all segments, to every rank's device (rank 0 reads them)
+        gathered = (torch.empty((world,) + tuple(pipe.frames.shape), dtype=torch.uint8, device=dev.device),
+                    torch.empty((world, n_chunks), dtype=torch.int32, device=dev.device))
+        gather_stream = torch.cuda.Stream(device=local_rank)
+
+    def gather_step(p, after):
+        """all-gather of pipeline p's records once the step on stream `after` is complete (NCCL, own stream)."""
+        gather_stream.wait_stream(after)
+        with torch.cuda.stream(gather_stream):
+            dist.all_gather_into_tensor(gathered[0], p.frames)
+            dist.all_gather_into_tensor(gathered[1], p.n_frames)
+
     def run_steps(k):
         if graphs is None:
             for _ in range(k):
                 pipe.run_device(dev, join=False)     # batches pipeline through the lane streams, each lane in order
+                if world > 1:
+                    pipe.join()
+                    gather_step(pipe, stream)
+                    stream.wait_stream(gather_stream)
             pipe.join()                              # ... and all of them are complete before the stop event
             return
         for gs in gstreams:
             gs.wait_stream(stream)
         for i in range(k):
             with torch.cuda.stream(gstreams[i & 1]):
+                if world > 1:
+                    gstreams[i & 1].wait_stream(gather_stream)      # the records of this pipeline's previous step are gathered
                 graphs[i & 1].replay()
+            if world > 1:
+                gather_step(pipe if (i & 1) == 0 else pipe_b, gstreams[i & 1])
         for gs in gstreams:
             stream.wait_stream(gs)
+        if world > 1:
+            stream.wait_stream(gather_stream)
 
     run_steps(args.warmup)
     sync_all()
@@ -287,6 +373,37 @@ def run_b200(args):
     ms = e0.elapsed_time(e1)
     launches = launches_per_step * args.steps
     stats = pipe.stats.cpu().numpy().copy()
+    # ---- untimed check of the gather: the merged record list must equal what ONE GPU finds in the same segments
+    shard_check = None
+    if world > 1:
+        last_pipe = pipe if ((args.steps - 1) & 1) == 0 or graphs is None else pipe_b
+        g_frames = gathered[0].cpu().numpy() if rank == 0 else None
+        g_counts = gathered[1].cpu().numpy() if rank == 0 else None
+        if rank == 0:
+            from tetraear_b200 import _lib as _l, shard as _shard
+            checked, n_merged = [], 0
+            merged = []
+            for r in range(world):
+                rec = g_frames[r].view(_l.FRAME_DTYPE).reshape(n_chunks, -1)
+                for c in range(n_chunks):
+                    for f in rec[c, :int(g_counts[r, c])]:
+                        if f["kept"]:
+                            merged.append((0, (r * n_chunks + c) * 8 + int(f["start_pos"]) // 510, (r, c, int(f["number"]), int(f["type"]),
+                                                                                                   bool(f["crc_ok"]), bytes(f["bits"]))))
+            merged = _shard.dedup_frames(sorted(merged, key=lambda t: (t[0], t[1])))
+            n_merged = len(merged)
+            solo = pipeline.ReceivePipeline(FS, CHUNK, max_chunks=n_chunks, mode=args.mode, device=local_rank, n_lanes=args.lanes)
+            for r in sorted({0, world - 1}):
+                xr = x if r == rank else make_c1(seed=1234 + r)
+                nfr1, fr1, _ = solo.run_host(xr)
+                want = [(r, c, int(f["number"]), int(f["type"]), bool(f["crc_ok"]), bytes(f["bits"]))
+                        for c in range(n_chunks) for f in fr1[c, :int(nfr1[c])] if f["kept"]]
+                got = [t[2] for t in merged if t[2][0] == r]
+                assert got == want, f"sharded gather differs from the single-GPU result on segment {r}"
+                checked.append(r)
+            del solo
+            shard_check = {"segments": world, "merged_frames": n_merged, "verified_against_single_gpu": checked, "ok": True}
+
     used_graphs = graphs is not None
     if used_graphs:
         stats = stats + pipe_b.stats.cpu().numpy()
@@ -465,7 +582,9 @@ def run_b200(args):
                                    }[args.mode] + ")",
                    "l2": "input 192 MB per step > 126 MB L2, no flush needed", "parallelism": f"capture segment per GPU x{world}",
                    "stream_lanes": args.lanes, "cuda_graph": bool(args.graph) and graph_error is None,
-                   "cpus_bound_per_rank": numa_cpus},
+                   "cpus_bound_per_rank": numa_cpus, "numa_node_rank0": numa_node,
+                   "gather": ("frame records of every segment all-gathered over NCCL inside the timed region, every step"
+                              if world > 1 else "single segment")},
         "crc_pass_bursts_per_s": round(bursts_per_s, 1), "crc_pass_per_step": int(stats[1] // max(args.steps, 1)),
         "gpu_launches": int(launches),
         "e2e": {"value": round(e2e, 3), "unit": "Msamples/s", "h2d_bytes_per_step": pipe.h2d_bytes(n_chunks),
@@ -491,6 +610,8 @@ def run_b200(args):
         line["value_other_arithmetic"] = alt
     if class_api:
         line["e2e_class_api"] = class_api
+    if shard_check:
+        line["shard_gather"] = shard_check
     if world == 1 and not args.no_extras:
         try:
             del dev, host
@@ -556,6 +677,33 @@ def other_workloads(device, peak):
     byts = n * 8 + nfr * 4096 * 4 * 3          # IQ read, power written, power re-read + smoothed written by the EMA pass
     out["c2_psd_4096_ema_60s_f32"] = {"msamples_per_s": round(n / ms / 1e3, 1), "ms": round(ms, 3), "frames": nfr,
                                   "achieved_gbs": round(byts / ms / 1e6, 1), "frac_of_hbm_peak": round(byts / ms / 1e6 / peak, 4)}
+    # same 60 s with linear (Welch) averaging of 8 frames before the dB conversion ("w/ averaging"): 1/8 of the output
+    an8 = SpectrumAnalyzer(FS, 4096, device=device, precision="f32", average=8)
+    p8 = torch.empty((nfr // 8, 4096), dtype=torch.float32, device=dev)
+    s8 = torch.empty((nfr // 8, 4096), dtype=torch.float32, device=dev)
+    st8 = torch.empty((nfr // 8, 8), dtype=torch.float64, device=dev)
+    ms8 = timed(lambda: an8.run_device(iq, nfr, 4096, denoise=True, power=p8, smoothed=s8, stats=st8), reps=3, warm=1)
+    byts8 = n * 8 + (nfr // 8) * 4096 * 4 * 3
+    out["c2_psd_4096_avg8_ema_60s_f32"] = {"msamples_per_s": round(n / ms8 / 1e3, 1), "ms": round(ms8, 3), "frames_out": nfr // 8,
+                                       "achieved_gbs": round(byts8 / ms8 / 1e6, 1),
+                                       "frac_of_hbm_peak": round(byts8 / ms8 / 1e6 / peak, 4)}
+    del an8, p8, s8, st8
+    # CPU side: the reference's per-frame block + EMA in numpy on the host cores, bounded sample
+    try:
+        import multiprocessing as mp
+        cores = host_cores()
+        xs = (0.1 * np.random.default_rng(1).standard_normal((cores, 2000 * 4096, 2))).astype(np.float32).view(np.complex64)[..., 0]
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_psd_worker, [(xs[i][:4096 * 8], 4096) for i in range(cores)])
+            w0 = time.perf_counter()
+            res = pool.map(_psd_worker, [(xs[i], 4096) for i in range(cores)])
+            wall = time.perf_counter() - w0
+        out["c2_psd_4096_ema_60s_f32"]["cpu_baseline"] = {
+            "value": round(sum(r[0] for r in res) / wall / 1e6, 2), "unit": "Msamples/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} x 2000 dense 4096-point frames (numpy restatement of ui/modern.py:1928-1941 + the EMA of :929-935), one worker per core"}
+        del xs
+    except Exception as e:
+        out["c2_psd_4096_ema_60s_f32"]["cpu_baseline"] = {"error": repr(e)[:200]}
     del iq, power, smooth, stats, an
     torch.cuda.empty_cache()
 
@@ -572,6 +720,21 @@ def other_workloads(device, peak):
     crc_pass = int(rec[:, 28].sum().item())
     out["c3_burst_batch_1M"] = {"bursts_per_s": round(nb / ms * 1e3, 0), "ms": round(ms, 4), "crc_pass": crc_pass,
                                 "achieved_gbs": round(byts / ms / 1e6, 1), "frac_of_hbm_peak": round(byts / ms / 1e6 / peak, 4)}
+    if reference_available():
+        try:
+            import multiprocessing as mp
+            cores = host_cores()
+            host_rows = rows[:cores * 1500].cpu().numpy()
+            with mp.get_context("fork").Pool(cores) as pool:
+                pool.map(_ref_burst_worker, [host_rows[:8]] * cores)
+                w0 = time.perf_counter()
+                res = pool.map(_ref_burst_worker, [host_rows[i::cores] for i in range(cores)])
+                wall = time.perf_counter() - w0
+            out["c3_burst_batch_1M"]["cpu_baseline"] = {
+                "value": round(sum(r[0] for r in res) / wall, 1), "unit": "bursts/s", "cores": cores, "kind": "reference",
+                "sample": f"first {len(host_rows)} of the 1M bursts through the unmodified TetraProtocolParser.parse_burst, {cores} workers"}
+        except Exception as e:
+            out["c3_burst_batch_1M"]["cpu_baseline"] = {"error": repr(e)[:200]}
     del rows, rec
 
     # ---- c3 (etsi mode): 1M SCH/HD blocks: descramble + de-interleave + RCPC Viterbi + CRC

@@ -80,7 +80,7 @@ typedef struct tb200_plan {
 } tb200_plan;
 
 /* one frame candidate of TetraDecoder.decode (core/decoder.py:861-888 + decode_frame :890-992) with the
- * fixed-offset MAC header fields of parse_mac_pdu — 152 bytes */
+ * fixed-offset MAC header fields of parse_mac_pdu and the payload statistics its callers test — 156 bytes */
 typedef struct tb200_frame {
     int32_t sync_pos;     /* bit position of the training sequence */
     int32_t start_pos;    /* sync_pos - 216 */
@@ -94,6 +94,9 @@ typedef struct tb200_frame {
     uint8_t mac_fill;     /* MAC header fill-bit indicator, data bit 4 (protocol.py:402, :454, :510) */
     uint8_t mac_length;   /* length field: data bits 29..34 (MAC-RESOURCE, :418-421) or 5..10 (MAC-END, :514-517), else 0 */
     uint32_t mac_address; /* 24-bit address, data bits 5..28, MAC-RESOURCE only (:410-413), else 0 */
+    uint8_t mac_data_bytes; /* len(MacPDU.data): the payload bits of protocol.py:423-443 / :456-462 / :496-501 / :519-537 packed to bytes */
+    uint8_t mac_unique;   /* len(set(MacPDU.data)): numerator of the entropy heuristic, decoder.py:1036-1053 */
+    uint8_t mac_b0, mac_b1; /* MacPDU.data[0], [1] (0 when absent): the SDS protocol-id pre-filters, protocol.py:820-900 */
     uint8_t bits[64];     /* the 510 frame bits (frame['bits']), MSB-first packed */
     uint8_t data[64];     /* TetraBurst.data_bits packed: 216 (normal) or 510 (sync) bits */
 } tb200_frame;

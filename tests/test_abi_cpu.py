@@ -33,7 +33,7 @@ def test_exports_match_header(lib):
 
 def test_struct_sizes():
     from tetraear_b200 import _lib
-    assert _lib.FRAME_DTYPE.itemsize == 152
+    assert _lib.FRAME_DTYPE.itemsize == 156
     assert ctypes.sizeof(_lib.Config) == 40       # 8 + 8 x int32
     assert ctypes.sizeof(_lib.Plan) == 32
     assert _lib.DETECT_DTYPE.itemsize == 112     # tb200_detect_stats

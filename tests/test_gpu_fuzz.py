@@ -52,6 +52,13 @@ def test_decode_fuzz(mods):
             # N1: the fixed-offset MAC header fields on the record equal the host header walk
             nd = 510 if int(r["burst_type"]) == 5 else 216
             pdu = host.parse_mac_pdu(np.unpackbits(r["data"])[:nd])
+            if pdu is not None:
+                # ... and the payload statistics (length, distinct bytes: the entropy heuristic; first bytes: SDS pre-filters)
+                assert int(r["mac_data_bytes"]) == len(pdu.data) and int(r["mac_unique"]) == len(set(pdu.data)), case
+                assert int(r["mac_b0"]) == (pdu.data[0] if len(pdu.data) > 0 else 0), case
+                assert int(r["mac_b1"]) == (pdu.data[1] if len(pdu.data) > 1 else 0), case
+            else:
+                assert int(r["mac_data_bytes"]) == 0 and int(r["mac_unique"]) == 0, case
             if pdu is not None and pdu.pdu_type.name in ("MAC_RESOURCE", "MAC_END"):
                 assert int(r["mac_length"]) == pdu.length and int(r["mac_fill"]) == pdu.fill_bits, case
                 if pdu.pdu_type.name == "MAC_RESOURCE":

@@ -34,8 +34,9 @@ class Plan(C.Structure):
 FRAME_DTYPE = np.dtype([("sync_pos", "<i4"), ("start_pos", "<i4"), ("number", "<i4"), ("type", "u1"),
                         ("enc_mode", "u1"), ("burst_type", "u1"), ("crc_ok", "u1"), ("mac_ok", "u1"),
                         ("kept", "u1"), ("mac_fill", "u1"), ("mac_length", "u1"), ("mac_address", "<u4"),
+                        ("mac_data_bytes", "u1"), ("mac_unique", "u1"), ("mac_b0", "u1"), ("mac_b1", "u1"),
                         ("bits", "u1", (64,)), ("data", "u1", (64,))])
-assert FRAME_DTYPE.itemsize == 152
+assert FRAME_DTYPE.itemsize == 156
 DETECT_DTYPE = np.dtype([("power_sum", "<f8"), ("window_sum", "<f8", (8,)), ("max_abs", "<f8"), ("n", "<i8"),
                          ("window_size", "<i4"), ("n_steps", "<i4"), ("matches", "<i4"), ("n_sync_bits", "<i4"),
                          ("sync_best", "<i4"), ("reserved", "<i4")])

@@ -218,7 +218,11 @@ class TetraDecoder:
                 frame['encryption_algorithm'] = 'TEA1'
         else:                                                      # entropy heuristic, decoder.py:1036-1053
             data = pdu.data
-            if len(data) > 0 and (len(set(data)) / max(len(data), 1)) > 0.7 and len(data) > 8:
+            if isinstance(rec, dict):
+                total, unique = len(data), len(set(data))
+            else:                                                  # counted on the device with the burst parse (N1)
+                total, unique = int(rec["mac_data_bytes"]), int(rec["mac_unique"])
+            if total > 0 and (unique / max(total, 1)) > 0.7 and total > 8:
                 frame['encrypted'] = True
             else:
                 frame['encrypted'] = False

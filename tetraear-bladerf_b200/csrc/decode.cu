@@ -316,6 +316,53 @@ __device__ void warp_parse_burst(unsigned w, const uint16_t *__restrict__ tab, c
     }
 }
 
+// Payload statistics of the MAC PDU parse_mac_pdu would build from the data bits (protocol.py:349-537): where
+// MacPDU.data starts and how many bits it takes per PDU type, its length in bytes (BitArray.tobytes pads the last byte
+// with zeros), the number of distinct byte values (the entropy heuristic of decoder.py:1036-1053 divides it by the
+// length) and its first two bytes (the protocol-id tests in front of parse_sds_data, protocol.py:820-900).
+// Every lane of the warp must call this.  w = burst word of the lane, o = the parsed header.
+struct MacPayload { uint32_t n_bytes, n_unique, b0, b1; };
+__device__ MacPayload warp_mac_payload(unsigned w, const BurstOut &o)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const bool is_sync = o.burst_type == 5;
+    const int n_data = is_sync ? 510 : 216;
+    const unsigned type = o.hdr >> 2;
+    int pos, nbits;
+    if (type == 0) { pos = 35; const int lb = 8 * (int)o.mac_length; nbits = (lb > 0 && pos + lb <= n_data) ? lb : n_data - pos; }
+    else if (type == 1) { pos = 5; nbits = n_data - pos; }
+    else if (type == 2) { pos = 4; nbits = n_data - pos; }
+    else { pos = 11; const int lb = 8 * (int)o.mac_length; nbits = (lb > 0 && pos + lb <= n_data) ? lb : n_data - pos; }
+    MacPayload r = {0u, 0u, 0u, 0u};
+    if (!o.mac_ok) nbits = 0;                                   // parse_mac_pdu returned None: no PDU, no data
+    r.n_bytes = (uint32_t)((nbits + 7) >> 3);
+    const int sh = pos & 7;
+    unsigned pres[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int j = lane + 32 * half;                         // payload byte index of this lane
+        const int a = (pos >> 3) + j;                           // aligned data byte that holds its first bit
+        const unsigned hi = data_byte(w, is_sync, a < 64 ? a : 63), lo = data_byte(w, is_sync, a + 1 < 64 ? a + 1 : 63);
+        unsigned v = ((((a < 64 ? hi : 0u) << 8) | (a + 1 < 64 ? lo : 0u)) >> (8 - sh)) & 0xFFu;
+        const int left = nbits - 8 * j;                         // payload bits from this byte on
+        const bool present = left > 0;
+        if (left < 8 && left > 0) v &= (0xFFu << (8 - left)) & 0xFFu;      // zero padding of the last byte
+        if (!present) v = 0u;
+        if (j == 0) r.b0 = v;
+        if (j == 1) r.b1 = v;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pres[k] |= (present && (int)(v >> 5) == k) ? (1u << (v & 31u)) : 0u;
+    }
+    unsigned uniq = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) uniq += __popc(__reduce_or_sync(FULL, pres[k]));
+    r.n_unique = uniq;
+    r.b0 = __shfl_sync(FULL, r.b0, 0);
+    r.b1 = __shfl_sync(FULL, r.b1, 1);
+    return r;
+}
+
 // lane's 16 bits of a burst given its 255 dibits (each dibit -> (s>>1)&1, s&1: protocol.py:211-214)
 __device__ __forceinline__ unsigned load_burst_word(const uint8_t *__restrict__ dib)
 {
@@ -499,6 +546,7 @@ __device__ void decode_stream_warp(const uint8_t *b, const uint8_t *mp, const ui
         bool ok = start_pos >= 0 && (start_sym + 255 <= nsym) && (start_pos + 510 <= nb);
         tb200_frame *fr = fo + f;
         BurstOut o = {0, 0, 0, 0, 0, 0, 0, 0};
+        MacPayload mp_stats = {0u, 0u, 0u, 0u};
         unsigned fw = 0;
         if (ok) {
             // frame bits come from the BIT stream at start_pos, burst symbols from the SYMBOL stream at
@@ -511,6 +559,7 @@ __device__ void decode_stream_warp(const uint8_t *b, const uint8_t *mp, const ui
             }
             unsigned w = load_burst_word(mp + start_sym);
             warp_parse_burst(w, tab, initv, nullptr, nullptr, o);
+            mp_stats = warp_mac_payload(w, o);
             // TetraBurst.data_bits packed into fr->data (216 or 510 bits)
             bool is_sync = o.burst_type == 5;
             for (int r = 0; r < 2; ++r) fr->data[r * 32 + lane] = (uint8_t)data_byte(w, is_sync, r * 32 + lane);
@@ -532,6 +581,10 @@ __device__ void decode_stream_warp(const uint8_t *b, const uint8_t *mp, const ui
             fr->mac_fill = (uint8_t)o.mac_fill;
             fr->mac_length = (uint8_t)o.mac_length;
             fr->mac_address = o.mac_address;
+            fr->mac_data_bytes = (uint8_t)mp_stats.n_bytes;
+            fr->mac_unique = (uint8_t)mp_stats.n_unique;
+            fr->mac_b0 = (uint8_t)mp_stats.b0;
+            fr->mac_b1 = (uint8_t)mp_stats.b1;
         }
     }
     if (lane == 0) {
