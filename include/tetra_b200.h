@@ -140,6 +140,10 @@ int tb200_set_sample_rate(tb200_handle h, double sample_rate); /* attr is mutate
  * amplitude spectra; K = 1 (default) is the reference's per-frame spectrum.  The dB-domain EMA, if requested, runs over
  * the averaged frames. */
 #define TB200_OPT_PSD_AVG 4
+/* TB200_OPT_ETSI_OPEN_LOOP = 5: tb200_etsi_demod_batch with both timing-loop gains zero: symbol k is taken at
+ * t = 16 + (k + 1) fs / 18000 samples exactly, so its matched-filter output can be checked against numpy.convolve with
+ * the same taps (tb200_debug_read region 4 returns the 32 x 32 interpolating RRC tap table).  Default 0. */
+#define TB200_OPT_ETSI_OPEN_LOOP 5
 int tb200_set_option(tb200_handle h, int option, int value);
 size_t tb200_workspace_bytes(tb200_handle h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
@@ -291,7 +295,8 @@ int tb200_refchan_batch(tb200_handle h, const void *d_iq_c64, int64_t n_samples,
                         void *d_out_c64, int64_t out_stride, void *stream);
 
 /* ---- debugging aid: synchronous copy of an internal workspace region to the host ---------
- * region 0 = decimated chunks, 1 = channel-filtered complex128, 2 / 3 = forward-pass scratches */
+ * region 0 = decimated chunks, 1 = channel-filtered complex128, 2 / 3 = forward-pass scratches,
+ * 4 = the etsi demodulator's tap table [32 fractional phases][32 taps] float32 (valid after the first demodulation) */
 int tb200_debug_read(tb200_handle h, int region, void *h_dst, size_t nbytes);
 /* host only (no device needed): the weight matrix of the tensor-core decimator for factor q as K x 48 doubles
  * (row-major), its TF32 split in the shared-memory layout ([K/4][48][4] floats each) and the carry constants (flat

@@ -18,6 +18,7 @@ OPT_CHAN_F32 = 1
 OPT_PSD_F32 = 2
 OPT_DECIM_TC = 3
 OPT_PSD_AVG = 4
+OPT_ETSI_OPEN_LOOP = 5
 
 
 class Config(C.Structure):

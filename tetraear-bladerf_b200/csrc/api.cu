@@ -285,6 +285,7 @@ extern "C" int tb200_set_option(tb200_handle h, int option, int value)
     case TB200_OPT_PSD_F32: h->psd_f32 = value ? 1 : 0; return TB200_OK;
     case TB200_OPT_DECIM_TC: h->decim_tc = value ? 1 : 0; return TB200_OK;
     case TB200_OPT_PSD_AVG: h->psd_avg = value > 1 ? value : 1; return TB200_OK;
+    case TB200_OPT_ETSI_OPEN_LOOP: h->etsi_open_loop = value ? 1 : 0; return TB200_OK;
     default: return fail(TB200_E_ARG, "tb200_set_option: unknown option %d", option);
     }
 }
@@ -728,6 +729,7 @@ extern "C" int tb200_debug_read(tb200_handle h, int region, void *h_dst, size_t 
     case 1: src = h->filtered; cap = h->filt_bytes; break;
     case 2: src = h->fwd; cap = h->fwd_bytes; break;
     case 3: src = h->chan_fwd; cap = h->chan_bytes; break;
+    case 4: src = h->etsi_taps; cap = 32 * 32 * sizeof(float); break;
     default: return fail(TB200_E_ARG, "tb200_debug_read: unknown region %d", region);
     }
     if (nbytes > cap) return fail(TB200_E_ARG, "tb200_debug_read: %zu bytes > region size %zu", nbytes, cap);

@@ -51,6 +51,7 @@ struct tb200_handle_s {
     int64_t launches;
     // optional per-stage CUDA-event timing (tb200_profile_*): pairs recorded on the launching stream
     int psd_f32;                 // PSD: float32 FFT + dB (dense config mode) instead of float64
+    int etsi_open_loop;          // etsi demodulator: timing loop gains 0 (fixed symbol period; validation of the matched filter)
     int psd_avg;                 // PSD: linear (Welch) average of this many consecutive frames per output frame (>= 1)
     int chan_f32;                // FAST mode: run the channel filter's recurrences in float32 (tb200_set_option)
     int decim_tc;                // FAST mode: tensor-core decimator (dsp_tc.cu) where its geometry rules hold (default on)

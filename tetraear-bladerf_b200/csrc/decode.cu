@@ -25,9 +25,10 @@ __constant__ uint8_t c_ts2[22] = {0,1,1,1,1,0,1,0,0,1,0,0,0,0,1,1,0,1,1,1,0,0}; 
 // folded in by the kernels (M^n * 0xFFFF) for the two payload lengths in use.
 __device__ uint16_t g_crc_tab[512];
 __device__ uint16_t g_crc_init[512];
-// CRC contribution of every 4-bit group of BURST bits, per burst type (0 normal, 1 sync) and payload
-// direction (0 forward, 1 reversed): g_crc_nib[type][dir][nibble 0..127][value 0..15]
-__device__ uint16_t g_crc_nib[2][2][128][16];
+// CRC contribution of every 4-bit group of BURST bits, per burst type (0 normal, 1 sync): forward-payload CRC in the low
+// half-word, reversed-payload CRC in the high one.  Indexed [type][nibble of the lane 0..3][value 0..15][lane]: the 32
+// lanes of a warp read 32 consecutive words — one shared-memory wavefront, no bank conflict (nibble j = 4 lane + q).
+__device__ uint32_t g_crc_nib[2][4][16][32];
 static bool g_crc_ready[64] = {false};
 static std::mutex g_crc_mu;                 // tb200_create may run concurrently for several devices
 
@@ -54,7 +55,7 @@ int ensure_crc_tables(int device)
     build_crc_tables(tab, init);
     TB_CUDA(cudaMemcpyToSymbol(g_crc_tab, tab, sizeof(tab)));
     TB_CUDA(cudaMemcpyToSymbol(g_crc_init, init, sizeof(init)));
-    static uint16_t nib[2][2][128][16];
+    static uint32_t nib[2][4][16][32];
     for (int type = 0; type < 2; ++type) {
         const int n_pay = type ? 494 : 200;
         for (int j = 0; j < 128; ++j)
@@ -66,7 +67,7 @@ int ensure_crc_tables(int device)
                     int d = type ? (bi < 510 ? bi : -1) : (bi < 108 ? bi : (bi >= 122 && bi < 230) ? bi - 14 : -1);
                     if (d >= 0 && d < n_pay) { f ^= tab[n_pay - d]; r ^= tab[d + 1]; }
                 }
-                nib[type][0][j][v] = f; nib[type][1][j][v] = r;
+                nib[type][j & 3][v][j >> 2] = (uint32_t)f | ((uint32_t)r << 16);
             }
     }
     TB_CUDA(cudaMemcpyToSymbol(g_crc_nib, nib, sizeof(nib)));
@@ -404,7 +405,7 @@ __device__ __forceinline__ unsigned load_burst_word_fast(const uint8_t *__restri
 }
 
 // Leaner burst parse for the batch kernel: nibble CRC tables, hardware warp reductions, direct shuffles.
-__device__ __forceinline__ void warp_parse_burst_v2(unsigned w, const uint16_t (*__restrict__ nibtab)[2][128][16],
+__device__ __forceinline__ void warp_parse_burst_v2(unsigned w, const uint32_t (*__restrict__ nibtab)[4][16][32],
                                                     const uint16_t *__restrict__ initv, uint8_t *__restrict__ rec,
                                                     uint8_t *__restrict__ full, BurstOut &out)
 {
@@ -436,8 +437,7 @@ __device__ __forceinline__ void warp_parse_burst_v2(unsigned w, const uint16_t (
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) {
         unsigned v = (w >> (12 - 4 * q4)) & 15u;
-        int j = lane * 4 + q4;
-        c ^= (unsigned)nibtab[type][0][j][v] | ((unsigned)nibtab[type][1][j][v] << 16);
+        c ^= nibtab[type][q4][v][lane];
     }
     c = __reduce_xor_sync(FULL, c);
     unsigned cf = (c & 0xFFFFu) ^ initv[n_pay], cr = (c >> 16) ^ initv[n_pay];
@@ -485,12 +485,12 @@ __global__ void __launch_bounds__(256)
 burst_batch_kernel(const uint8_t *__restrict__ dibits, long n, uint8_t *__restrict__ rec,
                    uint8_t *__restrict__ full, unsigned long long *__restrict__ stats)
 {
-    __shared__ uint16_t nibtab[2][2][128][16];
+    __shared__ uint32_t nibtab[2][4][16][32];
     __shared__ uint16_t initv[512];
     {
-        const uint16_t *src = &g_crc_nib[0][0][0][0];
-        uint16_t *dst = &nibtab[0][0][0][0];
-        for (int i = threadIdx.x; i < 2 * 2 * 128 * 16; i += blockDim.x) dst[i] = src[i];
+        const uint32_t *src = &g_crc_nib[0][0][0][0];
+        uint32_t *dst = &nibtab[0][0][0][0];
+        for (int i = threadIdx.x; i < 2 * 4 * 16 * 32; i += blockDim.x) dst[i] = src[i];
         for (int i = threadIdx.x; i < 512; i += blockDim.x) initv[i] = g_crc_init[i];
     }
     __syncthreads();

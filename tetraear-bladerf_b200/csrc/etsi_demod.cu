@@ -322,7 +322,8 @@ int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, l
         h->etsi_taps_fs = fs;
     }
     int threads = 128, blocks = (n_streams + 15) / 16;              // 8 lanes per stream, 16 streams per CTA
-    etsi_demod_kernel<<<blocks, threads, 0, st>>>(iq, n_streams, n, stride, (float)sps, (float)(0.05 * sps), (float)(0.0005 * sps),
+    const double loop = h->etsi_open_loop ? 0.0 : 1.0;
+    etsi_demod_kernel<<<blocks, threads, 0, st>>>(iq, n_streams, n, stride, (float)sps, (float)(loop * 0.05 * sps), (float)(loop * 0.0005 * sps),
                                                   taps_dev, sym, soft, soft_stride, n_soft);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
