@@ -24,7 +24,7 @@ xd = torch.from_numpy(x.view(np.float32).reshape(n_chunks, CH, 2)).to(dev)
 n_dec = (CH + q - 1) // q
 stride = n_dec + 8
 res = {}
-for tc in (0, 1):
+for tc in (0, 1, 2):
     h = _lib.Handle(sample_rate=2.4e6, max_chunks=n_chunks, max_chunk_len=CH, mode=_lib.MODE_FAST, device=0)
     h.set_option(_lib.OPT_DECIM_TC, tc)
     dib = torch.zeros((n_chunks, stride), dtype=torch.uint8, device=dev)
@@ -49,9 +49,15 @@ for tc in (0, 1):
             run()
         _lib.check(h.lib.tb200_debug_tc_timing(h.h, 0, tm))
         t = list(tm)
-        names = ["top", "input wait", "slot read", "relayout+split", "mma issue", "mma wait", "tmem ld", "scans", "carries+store"]
         g = max(t[15], 1)
-        print("   TC phases, cycles per group (CTA 0, thread 0):", {n: round(t[i] / g) for i, n in enumerate(names)}, "groups", t[15] // 5)
+        if tc == 1:
+            names = ["top", "input wait", "slot read", "relayout+split", "mma issue", "mma wait", "tmem ld", "scans", "carries+store"]
+            print("   TC phases, cycles per group (CTA 0, thread 0):", {n: round(t[i] / g) for i, n in enumerate(names)}, "groups", t[15] // 5)
+        else:
+            names = {0: "loader: wait raw free", 1: "relayout: wait raw full", 2: "relayout: wait A free", 3: "relayout: work", 4: "mma: wait A full / D free",
+                     5: "mma: issue", 7: "scan team 0: wait D full", 8: "scan: tmem ld", 9: "scan: KS + publish", 10: "scan: wait neighbours",
+                     11: "scan: carries + stores"}
+            print("   tc4 stages, cycles per group of CTA 0 (scan team 0 sees every 3rd group):", {n: round(t[i] / g) for i, n in names.items()}, "groups", t[15] // 5)
     h.profile(True)
     for _ in range(20):
         run()

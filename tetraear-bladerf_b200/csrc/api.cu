@@ -283,7 +283,7 @@ extern "C" int tb200_set_option(tb200_handle h, int option, int value)
     switch (option) {
     case TB200_OPT_CHAN_F32: h->chan_f32 = value ? 1 : 0; return TB200_OK;
     case TB200_OPT_PSD_F32: h->psd_f32 = value ? 1 : 0; return TB200_OK;
-    case TB200_OPT_DECIM_TC: h->decim_tc = value ? 1 : 0; return TB200_OK;
+    case TB200_OPT_DECIM_TC: h->decim_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return TB200_OK;
     case TB200_OPT_PSD_AVG: h->psd_avg = value > 1 ? value : 1; return TB200_OK;
     case TB200_OPT_ETSI_OPEN_LOOP: h->etsi_open_loop = value ? 1 : 0; return TB200_OK;
     default: return fail(TB200_E_ARG, "tb200_set_option: unknown option %d", option);

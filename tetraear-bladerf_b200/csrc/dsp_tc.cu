@@ -422,6 +422,344 @@ decim_tc_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_c
     if (threadIdx.x < 32) tmem_dealloc(tmem_base_s, TC_TEAMS * TC_TEAM_COLS);
 }
 
+// ====================================================================================================================
+// Warp-specialised form ("tc4"): ONE CTA per SM whose warps are the stages of a pipeline over the CTA's range of groups,
+//   warp 0        loader        one lane issues the TMA bulk copy of group g into a ring of 3 raw stages
+//   warps 2..5    re-layout     slot -> registers -> canonical hi (shared memory, 2 buffers) + lo (tensor memory, 2 buffers)
+//   warp 1        MMA issuer    one lane: 3 x K/8 tcgen05.mma into THREE accumulators (hi*Bhi, lo*Bhi, hi*Blo: three dependency
+//                               chains of K/8 instead of one of 3K/8), tcgen05.commit to "accumulators full" and "A free"
+//   warps 6..     scan teams    NS teams of 4 warps take alternate groups: TMEM load, sum of the three accumulators,
+//                               Kogge-Stone scans, carries, stores
+// connected by mbarriers (raw full/empty, A full/empty, D full/empty) and, between scan teams, a per-group "carries
+// published" barrier: the causal carry of group g-1 and the anti-causal carry of group g+1 come from another team.
+// Every wait is bounded: a stage that waits too long raises the CTA's abort flag and all stages drain and exit, so a
+// protocol error costs a wrong result (caught by the parity tests), never a hung GPU.
+constexpr int TC4_NS = 3;                       // scan teams
+constexpr int TC4_RAW = 3;                      // raw ring stages
+constexpr int TC4_WARPS = 6 + 4 * TC4_NS;
+constexpr int TC4_DCOLS = 144;                  // three 48-column accumulators per D buffer
+constexpr int TC4_ACOL0 = 2 * TC4_DCOLS;        // lo operand buffers behind the two D buffers (64 columns each)
+
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: false (and the abort flag set) if the phase did not complete in ~1 s
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, unsigned parity, volatile int *abort_flag)
+{
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        if (mbar_try(bar, parity)) return true;
+        if ((spin & 1023) == 1023 && *abort_flag) return false;
+    }
+    *abort_flag = 1;
+    return false;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int Q>
+__global__ void __launch_bounds__(TC4_WARPS * 32, 1)
+decim_tc4_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_chunks, long n_dec, int gpc, long total_floats,
+                 TcParams P, const float *__restrict__ bmat, float2 *__restrict__ dec_out, int *__restrict__ err_out,
+                 long long *__restrict__ timing)
+{
+    using G = TcG<Q>;
+    constexpr int RAW_BYTES = (int)(((127L * G::SLOT_FLOATS + G::K) * 4 + 127) & ~127L);
+    extern __shared__ uint8_t tc_raw[];
+    uint8_t *sm = tc_raw + ((128u - (smem_u32(tc_raw) & 127u)) & 127u);
+    uint8_t *B_hi = sm, *B_lo = B_hi + G::B_BYTES;
+    uint8_t *A_can = sm + 2 * G::B_BYTES;                         // 2 canonical hi buffers
+    uint8_t *raw = A_can + 2 * G::A_BYTES;                        // TC4_RAW raw stages
+    // d_full is per scan TEAM (the issuer commits group `it` to d_full[it % NS]): a team then waits consecutive phases of its
+    // own barrier — with a barrier per D buffer a team that skips groups could be two phases early and pass on parity alone
+    __shared__ __align__(8) uint64_t raw_full[TC4_RAW], raw_empty[TC4_RAW], a_full[2], a_empty[2], d_full[TC4_NS], d_empty[2], pub_bar[4], b_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ cp pubF[4][4], pubB[4][4];                         // per group slot (g & 3): causal carry of its last pass, anti-causal of its first
+    __shared__ cp carryF_s[TC4_NS][TC_GP][4], carryB_s[TC4_NS][TC_GP][4];
+    __shared__ cf lanepow_s[32][4];
+    __shared__ int abort_s;
+    volatile int *abort_flag = &abort_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NG = n_chunks * gpc;
+    const int G0 = (int)((long)NG * blockIdx.x / gridDim.x), G1 = (int)((long)NG * (blockIdx.x + 1) / gridDim.x);
+    const int gs = G0 - ((G0 % gpc) ? 1 : 0), ge = G1 + ((G1 % gpc) ? 1 : 0);
+
+    if (threadIdx.x < 128) lanepow_s[threadIdx.x & 31][threadIdx.x >> 5] = ld2(P.lanepow[threadIdx.x & 31][threadIdx.x >> 5]);
+    if (threadIdx.x == 0) {
+        abort_s = 0;
+        for (int i = 0; i < TC4_RAW; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&d_empty[i], 1); }
+        for (int i = 0; i < TC4_NS; ++i) mbar_init(&d_full[i], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&pub_bar[i], 1);
+        mbar_init(&b_bar, 1);
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem0 = tmem_base_s;
+    // profiling aid (tb200_debug_tc_timing): per-stage cycles of CTA 0 — one thread per role accumulates where it waits / works
+    const bool timed = timing != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6);
+    long long tprev = timed ? clock64() : 0;
+    long long tacc[12];                               // kept in registers (constant indices), written once at the end
+#pragma unroll
+    for (int i = 0; i < 12; ++i) tacc[i] = 0;
+    auto tick = [&](int c) { if (timed) { const long long t = clock64(); tacc[c] += t - tprev; tprev = t; } };
+
+    constexpr long RAW_FLOATS = 127L * G::SLOT_FLOATS + G::K;
+    auto group_f0 = [&](int g) -> long {
+        const int c = g / gpc, gi = g - c * gpc;
+        return 2 * ((long)c * chunk_stride + (long)Q * (gi * TC_GROUP - G::LEAD - 1));
+    };
+    auto group_tma = [&](int g) -> bool {
+        const long f0 = group_f0(g);
+        return f0 >= 0 && f0 + RAW_FLOATS <= total_floats;
+    };
+
+    if (warp == 0) {
+        // ================================================= loader
+        if (elect_one()) {
+            tma_load_1d(B_hi, bmat, 2u * G::B_BYTES, &b_bar);
+            for (int g = gs; g < ge && !*abort_flag; ++g) {
+                const int it = g - gs, st = it % TC4_RAW;
+                if (!mbar_wait_bounded(&raw_empty[st], ((it / TC4_RAW) & 1) ^ 1, abort_flag)) break;
+                tick(0);
+                if (group_tma(g))
+                    tma_load_1d(raw + st * RAW_BYTES, reinterpret_cast<const float *>(x) + group_f0(g), (unsigned)(RAW_FLOATS * 4), &raw_full[st]);
+                else
+                    mbar_arrive(&raw_full[st]);                    // the re-layout team fills this group with plain loads
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================================================= MMA issuer
+        if (elect_one()) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t desc_bh = umma_desc(smem_u32(B_hi), TC_N * 16, 128), desc_bl = umma_desc(smem_u32(B_lo), TC_N * 16, 128);
+            bool ok = mbar_wait_bounded(&b_bar, 0, abort_flag);
+            for (int g = gs; g < ge && ok && !*abort_flag; ++g) {
+                const int it = g - gs, b = it & 1;
+                ok = mbar_wait_bounded(&a_full[b], (it >> 1) & 1, abort_flag) && mbar_wait_bounded(&d_empty[b], ((it >> 1) & 1) ^ 1, abort_flag);
+                if (!ok) break;
+                tick(4);
+                tc_fence_after();
+                const uint64_t desc_a = umma_desc(smem_u32(A_can + b * G::A_BYTES), 2048, 128);
+                const uint32_t d0 = tmem0 + b * TC4_DCOLS, alo = tmem0 + TC4_ACOL0 + 64 * b;
+#pragma unroll
+                for (int ks = 0; ks < G::K / 8; ++ks) {
+                    const uint64_t dah = desc_a + (uint64_t)(ks * (4096 >> 4));
+                    const uint64_t dbh = desc_bh + (uint64_t)(ks * ((2 * TC_N * 16) >> 4)), dbl = desc_bl + (uint64_t)(ks * ((2 * TC_N * 16) >> 4));
+                    umma_tf32(d0, dah, dbh, idesc, ks > 0 ? 1u : 0u);
+                    umma_tf32_ts(d0 + 48, alo + 8 * ks, dbh, idesc, ks > 0 ? 1u : 0u);
+                    umma_tf32(d0 + 96, dah, dbl, idesc, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(&d_full[it % TC4_NS]);
+                umma_commit(&a_empty[b]);
+                tick(5);
+            }
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        // ================================================= re-layout team: 128 threads, slot m = 32 * (warp & 3) + lane
+        const int m = 32 * (warp & 3) + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        bool ok = true;
+        for (int g = gs; g < ge && ok; ++g) {
+            const int it = g - gs, st = it % TC4_RAW, b = it & 1;
+            const int chunk = g / gpc, gi = g - chunk * gpc;
+            const float2 *xc = x + (long)chunk * chunk_stride;
+            const long k0 = (long)gi * TC_GROUP - G::LEAD + (long)m * TC_R;
+            const long i0 = 1 + (long)Q * (k0 - 1);
+            const bool via_tma = group_tma(g);
+            uint8_t *rw = raw + st * RAW_BYTES;
+            ok = mbar_wait_bounded(&raw_full[st], (it / TC4_RAW) & 1, abort_flag);
+            if (!ok) break;
+            tick(1);
+            float4 v[G::KC];
+            if (via_tma) {
+#pragma unroll
+                for (int kc = 0; kc < G::KC; ++kc) v[kc] = *reinterpret_cast<const float4 *>(rw + m * (G::SLOT_FLOATS * 4) + kc * 16);
+                if (i0 - 1 < 0 || i0 - 1 + G::K / 2 > n) {
+#pragma unroll
+                    for (int kc = 0; kc < G::KC; ++kc) {
+                        const long i = i0 - 1 + 2 * kc;
+                        if (i < 0 || i >= n) { const float2 e = padded_sample_ool(xc, n, 27 + i); v[kc].x = e.x; v[kc].y = e.y; }
+                        if (i + 1 < 0 || i + 1 >= n) { const float2 e = padded_sample_ool(xc, n, 28 + i); v[kc].z = e.x; v[kc].w = e.y; }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int kc = 0; kc < G::KC; ++kc) {
+                    const long i = i0 - 1 + 2 * kc;
+                    const float2 e0 = (i >= 0 && i < n) ? xc[i] : padded_sample_ool(xc, n, 27 + i);
+                    const float2 e1 = (i + 1 >= 0 && i + 1 < n) ? xc[i + 1] : padded_sample_ool(xc, n, 28 + i);
+                    v[kc] = make_float4(e0.x, e0.y, e1.x, e1.y);
+                }
+            }
+            named_sync(1, 128);                                   // all slots are in registers: the raw stage is free
+            if (threadIdx.x == 64) mbar_arrive(&raw_empty[st]);
+            tick(3);
+            ok = mbar_wait_bounded(&a_empty[b], ((it >> 1) & 1) ^ 1, abort_flag);      // the MMAs of group g-2 are done with buffer b
+            if (!ok) break;
+            tick(2);
+            tc_fence_after();
+            uint8_t *Ah = A_can + b * G::A_BYTES;
+            const uint32_t alo = tmem0 + TC4_ACOL0 + 64 * b + lane_base;
+#pragma unroll
+            for (int q4 = 0; q4 < G::KC / 4; ++q4) {
+                float lo[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int kc = 4 * q4 + c;
+                    float4 hi;
+                    hi.x = __uint_as_float((__float_as_uint(v[kc].x) + 0x1000u) & 0xFFFFE000u);
+                    hi.y = __uint_as_float((__float_as_uint(v[kc].y) + 0x1000u) & 0xFFFFE000u);
+                    hi.z = __uint_as_float((__float_as_uint(v[kc].z) + 0x1000u) & 0xFFFFE000u);
+                    hi.w = __uint_as_float((__float_as_uint(v[kc].w) + 0x1000u) & 0xFFFFE000u);
+                    lo[4 * c + 0] = v[kc].x - hi.x; lo[4 * c + 1] = v[kc].y - hi.y;
+                    lo[4 * c + 2] = v[kc].z - hi.z; lo[4 * c + 3] = v[kc].w - hi.w;
+                    *reinterpret_cast<float4 *>(Ah + kc * 2048 + m * 16) = hi;
+                }
+                tmem_st16(alo + 16 * q4, lo);
+            }
+            tmem_st_wait();
+            fence_async_smem();
+            tc_fence_before();
+            named_sync(1, 128);
+            if (threadIdx.x == 64) mbar_arrive(&a_full[b]);
+            tick(3);
+        }
+    } else {
+        // ================================================= scan teams
+        const int team = (warp - 6) >> 2, w = warp & 3, tid = threadIdx.x - (6 + 4 * team) * 32;
+        (void)tid;
+        const uint32_t lane_base = (uint32_t)(w * 32) << 16;
+        const float2 zero2 = make_float2(0.f, 0.f);
+        bool ok = true;
+        for (int g = gs + team; g < ge && ok; g += TC4_NS) {
+            const int it = g - gs, b = it & 1, slot = it & 3;        // carry slots and their barrier phases count from the range start
+            const int chunk = g / gpc, gi = g - chunk * gpc;
+            const bool store = g >= G0 && g < G1;
+            const bool last_group = gi == gpc - 1;
+            const float2 *xc = x + (long)chunk * chunk_stride;
+            const long k0 = (long)gi * TC_GROUP - G::LEAD + (long)w * TC_PASS + (long)lane * TC_R;
+            tick(11);
+            ok = mbar_wait_bounded(&d_full[team], (it / TC4_NS) & 1, abort_flag);
+            if (!ok) break;
+            tick(7);
+            tc_fence_after();
+            // ---- accumulators of this slot: sum of the three partial products, columns 0..39
+            uint32_t va[32], vb[8];
+            {
+                const uint32_t d0 = tmem0 + b * TC4_DCOLS + lane_base;
+                uint32_t t1[32], t2[8];
+                tmem_ld32(d0, va); tmem_ld8(d0 + 32, vb);
+                tmem_ld32(d0 + 48, t1); tmem_ld8(d0 + 48 + 32, t2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) + __uint_as_float(t1[i]));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vb[i] = __float_as_uint(__uint_as_float(vb[i]) + __uint_as_float(t2[i]));
+                tmem_ld32(d0 + 96, t1); tmem_ld8(d0 + 96 + 32, t2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) + __uint_as_float(t1[i]));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vb[i] = __float_as_uint(__uint_as_float(vb[i]) + __uint_as_float(t2[i]));
+            }
+            tc_fence_before();
+            named_sync(2 + team, 128);
+            if (w == 0 && lane == 0) mbar_arrive(&d_empty[b]);     // the MMA issuer may overwrite this D buffer
+            tick(8);
+            float2 y[TC_R];
+#pragma unroll
+            for (int r = 0; r < TC_R; ++r) y[r] = make_float2(__uint_as_float(va[2 * r]), __uint_as_float(va[2 * r + 1]));
+            cp tF[4], tB[4];
+#pragma unroll
+            for (int mm = 0; mm < 4; ++mm) {
+                auto col = [&](int cc) -> float { return __uint_as_float(cc < 32 ? va[cc < 32 ? cc : 0] : vb[cc >= 32 ? cc - 32 : 0]); };
+                cp a, bb;
+                a.re = make_float2(col(6 + 4 * mm), col(7 + 4 * mm));
+                a.im = make_float2(col(8 + 4 * mm), col(9 + 4 * mm));
+                bb.re = make_float2(col(22 + 4 * mm), col(23 + 4 * mm));
+                bb.im = make_float2(col(24 + 4 * mm), col(25 + 4 * mm));
+#pragma unroll
+                for (int s = 0; s < 5; ++s) {
+                    if (s >= fd_nstage(mm)) continue;
+                    cp oa, ob;
+                    oa.re = shfl2_up(a.re, 1 << s); oa.im = shfl2_up(a.im, 1 << s);
+                    ob.re = shfl2_down(bb.re, 1 << s); ob.im = shfl2_down(bb.im, 1 << s);
+                    const cf gm = ld2(P.lampow[s][mm]);
+                    if (lane >= (1 << s)) a = cpfma(gm, oa, a);
+                    if (lane + (1 << s) < 32) bb = cpfma(gm, ob, bb);
+                }
+                if (lane == 31) { carryF_s[team][w][mm] = a; if (w == TC_GP - 1) pubF[slot][mm] = a; }
+                if (lane == 0) { carryB_s[team][w][mm] = bb; if (w == 0) pubB[slot][mm] = bb; }
+                tF[mm].re = shfl2_up(a.re, 1); tF[mm].im = shfl2_up(a.im, 1);
+                tB[mm].re = shfl2_down(bb.re, 1); tB[mm].im = shfl2_down(bb.im, 1);
+                if (lane == 0) tF[mm].re = tF[mm].im = zero2;
+                if (lane == 31) tB[mm].re = tB[mm].im = zero2;
+            }
+            named_sync(2 + team, 128);                             // this team's carries are in shared memory
+            if (w == 0 && lane == 0) mbar_arrive(&pub_bar[slot]);  // ... and published to the other teams
+            tick(9);
+            // ---- carries across passes
+            const bool need_prev = (w == 0) && gi != 0 && g > gs;
+            const bool need_next = (w == TC_GP - 1) && !last_group && (g + 1 < ge);
+            if (need_prev) ok = mbar_wait_bounded(&pub_bar[(it - 1) & 3], ((it - 1) >> 2) & 1, abort_flag);
+            if (need_next && ok) ok = mbar_wait_bounded(&pub_bar[(it + 1) & 3], ((it + 1) >> 2) & 1, abort_flag);
+            tick(10);
+            float2 c0 = zero2, cM = zero2;
+            if (w == 0 && gi == 0) c0 = padded_sample_ool(xc, n, 0);
+            if (w == TC_GP - 1 && last_group) cM = padded_sample_ool(xc, n, n + 53);
+#pragma unroll
+            for (int mm = 0; mm < 4; ++mm) {
+                cp inF, inB;
+                inF.re = inF.im = inB.re = inB.im = zero2;
+                if (w > 0) inF = carryF_s[team][w - 1][mm];
+                else if (gi == 0) inF = cp_const(ld2(P.initF[mm]), c0);
+                else if (g > gs) inF = pubF[(it - 1) & 3][mm];
+                if (w < TC_GP - 1) inB = carryB_s[team][w + 1][mm];
+                else if (last_group) inB = cp_const(ld2(P.initB[mm]), cM);
+                else if (g + 1 < ge) inB = pubB[(it + 1) & 3][mm];
+                const cp sF = cpfma(lanepow_s[lane][mm], inF, tF[mm]);
+                const cp sB = cpfma(lanepow_s[31 - lane][mm], inB, tB[mm]);
+#pragma unroll
+                for (int r = 0; r < TC_R; ++r) y[r] = re_acc(ld2(P.cB[r][mm]), sB, re_acc(ld2(P.cF[r][mm]), sF, y[r]));
+            }
+            if (store && ok) {
+                float2 *out = dec_out + (long)chunk * n_dec;
+#pragma unroll
+                for (int r = 0; r < TC_R; ++r) {
+                    const long k = k0 + r;
+                    if (k >= 0 && k < n_dec) out[k] = y[r];
+                }
+            }
+            named_sync(2 + team, 128);                             // carryF_s / carryB_s of this team are free again
+        }
+    }
+    if (timed) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) if (tacc[i]) timing[i] += tacc[i];
+        if (warp == 0) timing[15] += ge - gs;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && abort_s && err_out) atomicExch(err_out, 1);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem0, 512);
+}
+
 // ---- right-edge transient of scipy's backward pass: y[k] -= 2 Re sum_i kappa_i pc_i lambda_i^(n_dec-1-k) on the last
 // FD_NFIX outputs of every chunk (dsp_fast.cu header); kappa_i from F_i[M-1] = sum_k p_i^k ext[M-1-k].  One warp per chunk.
 __global__ void __launch_bounds__(32)
@@ -618,11 +956,29 @@ static int launch_tc_q(tb200_handle h, const void *x, int n_chunks, long n, long
     const int gpc = (int)((n_dec + G::LEAD + 4 + TC_GROUP - 1) / TC_GROUP);
     const long NG = (long)n_chunks * gpc;
     if (NG >= (1L << 30)) return fail(TB200_E_ARG, "tc decimator: batch too large");
+    if (h->decim_tc >= 2) {
+        // warp-specialised pipeline: one CTA per SM
+        constexpr int RAW_BYTES = (int)(((127L * G::SLOT_FLOATS + G::K) * 4 + 127) & ~127L);
+        const size_t smem4 = 2 * (size_t)G::B_BYTES + 2 * (size_t)G::A_BYTES + (size_t)TC4_RAW * RAW_BYTES + 128;
+        static std::atomic<bool> attr4_set[64];
+        if (!attr4_set[dv]) {
+            cudaError_t e = cudaFuncSetAttribute(decim_tc4_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+            if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(decim_tc4): %s", cudaGetErrorString(e));
+            attr4_set[dv] = true;
+        }
+        long grid4 = n_sm[dv];
+        if (grid4 > NG) grid4 = NG;
+        int *err = reinterpret_cast<int *>((char *)h->tc_bmat + h->tc_bmat_bytes - 16);      // counter slot 14 of the timing block
+        decim_tc4_kernel<Q><<<(unsigned)grid4, TC4_WARPS * 32, smem4, st>>>((const float2 *)x, n, chunk_stride, n_chunks, n_dec, gpc,
+                                                                          total_floats, P, bmat, (float2 *)dec_out, err, h->tc_timing);
+        TB_LAUNCH_CHECK(h);
+    } else {
     long grid = 2L * n_sm[dv];                      // two resident CTAs per SM (two teams each), one range of groups per team
     if (grid * TC_TEAMS > NG) grid = NG / TC_TEAMS > 0 ? NG / TC_TEAMS : 1;
     decim_tc_kernel<Q><<<(unsigned)grid, TC_TEAMS * TC_GP * 32, smem, st>>>((const float2 *)x, n, chunk_stride, n_chunks, n_dec, gpc,
                                                                total_floats, P, bmat, (float2 *)dec_out, h->tc_timing);
     TB_LAUNCH_CHECK(h);
+    }
     decim_tc_edge_kernel<<<n_chunks, 32, 0, st>>>((const float2 *)x, n, chunk_stride, n_dec, KE, (float2 *)dec_out);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;

@@ -46,6 +46,8 @@ int launch_etsi_find_sync(tb200_handle h, const float *soft, int n_streams, long
                           cudaStream_t st);
 int launch_channelizer(tb200_handle h, const float2 *x, long n, int M, float *proto_dev, float2 *tw_dev, float2 *out,
                        long out_stride, long n_frames, cudaStream_t st);
+int launch_polyphase_bank(tb200_handle h, const float2 *x, long n, int M, int N1, int N2, int P, int l0, int hop, long n_frames,
+                          const float *proto, const float2 *tw, float2 *out, long out_stride, cudaStream_t st);
 int launch_refchan(tb200_handle h, const float2 *x, long n, int M, int q, double fs, const DecimDesign &d, float2 *out,
                    long out_stride, cudaStream_t st);
 int launch_sc16_to_c64(tb200_handle h, const void *in, long n, void *out, cudaStream_t st);

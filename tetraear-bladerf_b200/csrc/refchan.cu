@@ -35,8 +35,73 @@ struct RefChanEdge {
     int L;                           // truncation length of g (multiple of M)
 };
 
+// twiddles of the in-register transforms: e^{+j 2 pi i / 32} (i < 16), e^{+j 2 pi i / 5} (i < 5), e^{+j 2 pi i / 25} (i < 25)
+__constant__ float2 c_w32[16];
+__constant__ float2 c_w5[5];
+__constant__ float2 c_w25[25];
+
+__device__ __forceinline__ float2 cmulf2(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 caddf2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csubf2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+__host__ __device__ constexpr int brev5(int i) { return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4); }
+// inverse (e^{+j}) 32-point DFT in registers: v[] holds the input in BIT-REVERSED order, the output in natural order
+template <int S>
+__device__ __forceinline__ void ifft32_stage(float2 (&v)[32])
+{
+    constexpr int m = 1 << S, hm = m >> 1, tstep = 32 >> S;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {                       // butterfly i: block i / hm, position i % hm
+        const int b = (i / hm) * m, j = i % hm;
+        const float2 t = j ? cmulf2(c_w32[j * tstep], v[b + j + hm]) : v[b + j + hm];
+        v[b + j + hm] = csubf2(v[b + j], t);
+        v[b + j] = caddf2(v[b + j], t);
+    }
+}
+__device__ __forceinline__ void ifft32_regs(float2 (&v)[32])
+{
+    ifft32_stage<1>(v); ifft32_stage<2>(v); ifft32_stage<3>(v); ifft32_stage<4>(v); ifft32_stage<5>(v);
+}
+// inverse 5-point DFT of (a0..a4), direct
+__device__ __forceinline__ void idft5(const float2 (&a)[5], float2 (&o)[5])
+{
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        float2 acc = a[0];
+#pragma unroll
+        for (int n = 1; n < 5; ++n) acc = caddf2(acc, cmulf2(a[n], c_w5[(k * n) % 5]));
+        o[k] = acc;
+    }
+}
+// inverse 25-point DFT in registers (5 x 5 Cooley-Tukey): in[r1], r1 = 5 a + b  ->  out[k1], k1 = c + 5 d
+__device__ __forceinline__ void idft25_regs(const float2 (&in)[25], float2 (&out)[25])
+{
+    float2 y[25];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {                     // over a: Y[b][c] = sum_a in[5 a + b] w5^(a c)
+        float2 col[5], o[5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) col[a] = in[5 * a + b];
+        idft5(col, o);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) y[5 * b + c] = (b && c) ? cmulf2(o[c], c_w25[(b * c) % 25]) : o[c];      // twiddle w25^(b c)
+    }
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {                     // over b: X[c + 5 d] = sum_b Y[b][c] w5^(b d)
+        float2 row[5], o[5];
+#pragma unroll
+        for (int b = 0; b < 5; ++b) row[b] = y[5 * b + c];
+        idft5(row, o);
+#pragma unroll
+        for (int d = 0; d < 5; ++d) out[c + 5 * d] = o[d];
+    }
+}
+
+// FFT = true: M = 25 x 32 (800 channels): both small DFTs run in registers (5 x 5 and radix-2), one thread per
+// (frame, r2) column resp. (frame, k1) row.  FFT = false: direct small DFTs from the twiddle tables, any M = N1 x 2^k.
+template <bool FFT>
 __global__ void __launch_bounds__(256)
-refchan_kernel(const float2 *__restrict__ x, long n, int M, int N1, int log2_n2, int F, int P, int hop, long n_frames,
+refchan_kernel(const float2 *__restrict__ x, long n, int M, int N1, int log2_n2, int F, int P, int l0, int hop, long n_frames,
                const float *__restrict__ proto, const float2 *__restrict__ tw, float2 *__restrict__ out, long out_stride)
 {
     extern __shared__ float2 rc_smem[];
@@ -48,28 +113,64 @@ refchan_kernel(const float2 *__restrict__ x, long n, int M, int N1, int log2_n2,
     float2 *w2 = w1 + N1;                     // [N2]
     float2 *wm = w2 + N2;                     // [M]  exp(+j 2 pi i / M)
     const long m0 = (long)blockIdx.x * F;
-    const int half = P / 2;
     for (int i = threadIdx.x; i < N1 + N2 + M; i += blockDim.x) w1[i] = tw[i];
-    // ---- folded window: v[f][r] = sum_l g[|r + M l|] x[n_j - r - M l],  l = -P/2 .. P/2-1   (proto[(l + P/2) M + r])
-    for (int f = 0; f < F; ++f) {
-        const long j = m0 + f;
-        for (int r = threadIdx.x; r < M; r += blockDim.x) {
-            float2 acc = make_float2(0.f, 0.f);
-            if (j < n_frames) {
-                const long base = j * hop - r;
-                for (int l = -half; l < half; ++l) {
-                    const long idx = base - (long)l * M;
-                    if (idx >= 0 && idx < n) {
-                        const float2 s = x[idx];
-                        const float h = __ldg(proto + (l + half) * M + r);
-                        acc.x = fmaf(h, s.x, acc.x); acc.y = fmaf(h, s.y, acc.y);
-                    }
+    // ---- folded window: v[f][r] = sum_l h[r + M l] x[n_j - r - M l],  l = l0 .. l0 + P - 1   (proto[(l - l0) M + r]);
+    // reference mode: h[d] = g[|d|], l0 = -P/2; the causal etsi prototype: l0 = 0.
+    // A thread keeps one r for all F frames: the tap is loaded once per F multiply-adds.
+    for (int r = threadIdx.x; r < M; r += blockDim.x) {
+        float2 acc[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) acc[f] = make_float2(0.f, 0.f);
+        for (int l = l0; l < l0 + P; ++l) {
+            const float h = __ldg(proto + (l - l0) * M + r);
+            const long base = m0 * hop - r - (long)l * M;
+#pragma unroll
+            for (int f = 0; f < 8; ++f) {
+                const long idx = base + (long)f * hop;
+                if (f < F && idx >= 0 && idx < n) {
+                    const float2 sv = x[idx];
+                    acc[f].x = fmaf(h, sv.x, acc[f].x); acc[f].y = fmaf(h, sv.y, acc[f].y);
                 }
             }
-            v[f * M + r] = acc;
         }
+#pragma unroll
+        for (int f = 0; f < 8; ++f) if (f < F) v[f * M + r] = (m0 + f < n_frames) ? acc[f] : make_float2(0.f, 0.f);
     }
     __syncthreads();
+    if (FFT) {
+        // ---- stage A: thread (f, r2): 25-point inverse DFT over r1 (r = 32 r1 + r2) in registers, times e^{+j 2 pi k1 r2 / M}
+        for (int c = threadIdx.x; c < F * 32; c += blockDim.x) {
+            const int f = c >> 5, r2 = c & 31;
+            float2 in[25], o[25];
+#pragma unroll
+            for (int r1 = 0; r1 < 25; ++r1) in[r1] = v[f * M + (r1 << 5) + r2];
+            idft25_regs(in, o);
+#pragma unroll
+            for (int k1 = 0; k1 < 25; ++k1) a[(f * 25 + k1) * APITCH + r2] = cmulf2(o[k1], wm[k1 * r2]);
+        }
+        __syncthreads();
+        // ---- stage B: thread (f, k1): 32-point inverse FFT over r2 in registers; k = k1 + 25 k2; rotation; store
+        for (int c = threadIdx.x; c < F * 25; c += blockDim.x) {
+            const int k1 = c / F, f = c - k1 * F;             // f fastest: the F outputs of a channel row are one 64-byte segment
+            const long j = m0 + f;
+            float2 vv[32];
+            const float2 *af = a + (f * 25 + k1) * APITCH;
+#pragma unroll
+            for (int r2 = 0; r2 < 32; ++r2) vv[brev5(r2)] = af[r2];
+            ifft32_regs(vv);
+            if (j < n_frames) {
+                const int jm = (int)(j % M);
+#pragma unroll
+                for (int k2 = 0; k2 < 32; ++k2) {
+                    const int k = k1 + 25 * k2;
+                    const int kh = (int)(((long)k * hop) % M);
+                    const float2 rot = wm[(kh * jm) % M];        // e^{+j 2 pi (k hop j) / M}; conjugate applied
+                    out[(long)k * out_stride + j] = make_float2(vv[k2].x * rot.x + vv[k2].y * rot.y, vv[k2].y * rot.x - vv[k2].x * rot.y);
+                }
+            }
+        }
+        return;
+    }
     // ---- stage A: for every r2, a size-N1 DFT over r1 (r = N2 r1 + r2), times exp(+j 2 pi k1 r2 / M)
     for (int jj = threadIdx.x; jj < M; jj += blockDim.x) {
         const int k1 = jj >> log2_n2, r2 = jj & (N2 - 1);
@@ -349,19 +450,49 @@ int launch_refchan(tb200_handle h, const float2 *x, long n, int M, int q, double
         TB_CUDA(cudaStreamSynchronize(st));            // host vectors go out of scope
         h->rc_M = M; h->rc_q = q; h->rc_n = n; h->rc_fs = fs;
     }
+    rc = launch_polyphase_bank(h, x, n, M, N1, N2, P, -P / 2, q, n_dec, proto, tw, out, out_stride, st);
+    if (rc) return rc;
+    refchan_edge_kernel<<<M, 128, 0, st>>>(x, n, q, fs, fdev, n_dec, gdev, E, out, out_stride);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+// The folded-window + size-M inverse DFT + rotation kernel for a prototype of P taps per branch starting at block l0,
+// frames `hop` samples apart: y_k[j] = e^{-j 2 pi k hop j / M} sum_r e^{+j 2 pi k r / M} sum_l h[r + M l] x[hop j - r - M l].
+// Shared by the reference-mode bank (above) and the etsi channelizer (channelizer.cu: hop = M / 2, l0 = 0).
+int launch_polyphase_bank(tb200_handle h, const float2 *x, long n, int M, int N1, int N2, int P, int l0, int hop, long n_frames,
+                          const float *proto, const float2 *tw, float2 *out, long out_stride, cudaStream_t st)
+{
     int F = 8;
     int log2_n2 = 0;
     while ((1 << log2_n2) < N2) ++log2_n2;
     auto need = [&](int f) { return sizeof(float2) * ((size_t)f * M + (size_t)f * N1 * (N2 + 1) + N1 + N2 + M); };
     size_t smem = need(F);
     while (smem > 100 * 1024 && F > 1) { F /= 2; smem = need(F); }
-    if (smem > 200 * 1024) return fail(TB200_E_ARG, "refchan: M=%d too large for shared memory", M);
-    cudaError_t e = cudaFuncSetAttribute(refchan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 200 * 1024) return fail(TB200_E_ARG, "polyphase bank: M=%d too large for shared memory", M);
+    const bool use_fft = (N1 == 25 && N2 == 32 && F == 8);
+    if (use_fft) {
+        static std::once_flag tw_once[64];
+        static cudaError_t tw_err[64];
+        const int dv = h->cfg.device & 63;
+        std::call_once(tw_once[dv], [&] {
+            float2 w32[16], w5[5], w25[25];
+            for (int i = 0; i < 16; ++i) w32[i] = make_float2((float)std::cos(2 * M_PI * i / 32), (float)std::sin(2 * M_PI * i / 32));
+            for (int i = 0; i < 5; ++i) w5[i] = make_float2((float)std::cos(2 * M_PI * i / 5), (float)std::sin(2 * M_PI * i / 5));
+            for (int i = 0; i < 25; ++i) w25[i] = make_float2((float)std::cos(2 * M_PI * i / 25), (float)std::sin(2 * M_PI * i / 25));
+            cudaError_t e1 = cudaMemcpyToSymbol(c_w32, w32, sizeof(w32));
+            cudaError_t e2 = cudaMemcpyToSymbol(c_w5, w5, sizeof(w5));
+            cudaError_t e3 = cudaMemcpyToSymbol(c_w25, w25, sizeof(w25));
+            tw_err[dv] = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+        });
+        if (tw_err[dv] != cudaSuccess) return fail(TB200_E_CUDA, "refchan: twiddle upload: %s", cudaGetErrorString(tw_err[dv]));
+    }
+    cudaError_t e = use_fft ? cudaFuncSetAttribute(refchan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(refchan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(refchan): %s", cudaGetErrorString(e));
-    unsigned blocks = (unsigned)((n_dec + F - 1) / F);
-    refchan_kernel<<<blocks, 256, smem, st>>>(x, n, M, N1, log2_n2, F, P, q, n_dec, proto, tw, out, out_stride);
-    TB_LAUNCH_CHECK(h);
-    refchan_edge_kernel<<<M, 128, 0, st>>>(x, n, q, fs, fdev, n_dec, gdev, E, out, out_stride);
+    unsigned blocks = (unsigned)((n_frames + F - 1) / F);
+    if (use_fft) refchan_kernel<true><<<blocks, 256, smem, st>>>(x, n, M, N1, log2_n2, F, P, l0, hop, n_frames, proto, tw, out, out_stride);
+    else refchan_kernel<false><<<blocks, 256, smem, st>>>(x, n, M, N1, log2_n2, F, P, l0, hop, n_frames, proto, tw, out, out_stride);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
 }

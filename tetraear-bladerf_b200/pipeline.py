@@ -30,14 +30,15 @@ class ReceivePipeline:
         per = (self.max_chunks + self.n_lanes - 1) // self.n_lanes
         self.lane_chunks = per
         m = {"exact": _lib.MODE_EXACT, "fast": _lib.MODE_FAST, "fast32": _lib.MODE_FAST, "fast-tc": _lib.MODE_FAST,
-             "fast32-tc": _lib.MODE_FAST}[mode]           # "-tc": tensor-core decimator (csrc/dsp_tc.cu)
+             "fast32-tc": _lib.MODE_FAST, "fast-tc4": _lib.MODE_FAST, "fast32-tc4": _lib.MODE_FAST}[mode]
+        # "-tc" / "-tc4": tensor-core decimator (csrc/dsp_tc.cu), streaming teams / warp-specialised pipeline
         self.handles = [_lib.Handle(sample_rate=self.sample_rate, max_chunks=per, max_chunk_len=self.chunk_len, mode=m,
                                     device=device) for _ in range(self.n_lanes)]
         for hh in self.handles:
             if mode.startswith("fast32"):
                 hh.set_option(_lib.OPT_CHAN_F32, 1)
-            if mode.endswith("-tc"):
-                hh.set_option(_lib.OPT_DECIM_TC, 1)
+            if mode.endswith("-tc") or mode.endswith("-tc4"):
+                hh.set_option(_lib.OPT_DECIM_TC, 2 if mode.endswith("4") else 1)
         self.h = self.handles[0]
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.n_lanes)]
         # the sync search / burst parse of a sub-batch is latency-bound (one small CTA per chunk): it runs on a
@@ -57,8 +58,12 @@ class ReceivePipeline:
         self._n_dibits2 = torch.zeros((2, C), dtype=torch.int32, device=self.dev)
         self.n_dibits = self._n_dibits2[0]
         self.phase = torch.zeros((C,), dtype=torch.int32, device=self.dev)
-        self.frames = torch.zeros((C, self.max_frames, _lib.FRAME_DTYPE.itemsize), dtype=torch.uint8, device=self.dev)
-        self.n_frames = torch.zeros((C,), dtype=torch.int32, device=self.dev)
+        # frame records and their per-chunk counts live in ONE allocation (`records`): a multi-GPU job gathers a step's
+        # results with a single collective on it
+        fbytes = C * self.max_frames * _lib.FRAME_DTYPE.itemsize
+        self.records = torch.zeros((fbytes + 4 * C,), dtype=torch.uint8, device=self.dev)
+        self.frames = self.records[:fbytes].view(C, self.max_frames, _lib.FRAME_DTYPE.itemsize)
+        self.n_frames = self.records[fbytes:].view(torch.int32)
         self.stats = torch.zeros((3,), dtype=torch.int64, device=self.dev)
         self._staging = None
 

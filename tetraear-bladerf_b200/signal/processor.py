@@ -18,7 +18,7 @@ logger = logging.getLogger(__name__)
 # "fast" / "fast32": time-parallel float32 decimator + float64 / float32 channel filter; the "-tc" variants run the
 # decimator's linear part on the tensor cores (tcgen05, csrc/dsp_tc.cu) instead of packed FFMA2 (csrc/dsp_fast.cu)
 _MODES = {"exact": _lib.MODE_EXACT, "fast": _lib.MODE_FAST, "fast32": _lib.MODE_FAST, "fast-tc": _lib.MODE_FAST,
-          "fast32-tc": _lib.MODE_FAST}
+          "fast32-tc": _lib.MODE_FAST, "fast-tc4": _lib.MODE_FAST, "fast32-tc4": _lib.MODE_FAST}
 
 
 def _as_complex(samples):
@@ -56,8 +56,8 @@ class SignalProcessor:
                                   device=self.device)
             if self.mode.startswith("fast32"):
                 self._h.set_option(_lib.OPT_CHAN_F32, 1)
-            if self.mode.endswith("-tc"):
-                self._h.set_option(_lib.OPT_DECIM_TC, 1)
+            if self.mode.endswith("-tc") or self.mode.endswith("-tc4"):
+                self._h.set_option(_lib.OPT_DECIM_TC, 2 if self.mode.endswith("4") else 1)
             self._cap = ((cap - 128) // 2, fs)
         return self._h
 
