@@ -35,6 +35,12 @@ struct ChanFastParams {
     double inv1mp[2][2];
     double ka[2][2], kM[2][2][2], kMc[2][2][2];
     double pc[2][2];               // p^16 : exponent of the last output (M - n_last)
+    double a2[2][2];               // 2 alpha_i
+    double aF2[CF_R][2][2];        // 2 alpha_i p^(r+1)
+    double aB2[CF_R][2][2];        // 2 alpha_i p^(R-r)
+    double p7[2][2], p15[2][2];
+    double lanepow[32][2][2];      // (p^R)^l: weight of the cross-pass carry at lane l
+    int nstage[2];                 // Kogge-Stone stages whose multiplier (p^R)^(2^s) is above 1e-17
 };
 
 struct cdd { double x, y; };
@@ -288,6 +294,197 @@ chan_fast_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// float64 kernel of the "fast" mode.  Same tiling as chan_fast_kernel<TI, double> above (which stays for float working
+// precision on complex128 input) with the instruction count roughly halved: every recurrence step and every output
+// update is a chain of DFMAs on pre-doubled weights, the halo warp carries no outputs, the in-pass (lane) carry and the
+// cross-pass (warp) carry are summed first and applied to the 8 outputs once, lane powers come from a shared-memory
+// table and the timing-phase sums index in 32 bits without divisions.
+__device__ __forceinline__ void d_step(cdd &s, const cdd p, const double x)          // s = p s + x
+{
+    const double re = fma(p.x, s.x, fma(-p.y, s.y, x));
+    const double im = fma(p.x, s.y, p.y * s.x);
+    s.x = re; s.y = im;
+}
+__device__ __forceinline__ double d_reacc(const cdd a, const cdd s, const double y) { return fma(a.x, s.x, fma(-a.y, s.y, y)); }   // y + Re(a s)
+
+// one direction over the lane's CF_R samples of ONE component: zero-state recurrences (+ the outputs' own-lane part when
+// STORE), Kogge-Stone scan of the lane aggregates; returns the lane's in-pass carry-in (exclusive), the pass-end state
+// goes to carry[mode]
+template <bool FWD, bool STORE, bool EDGE>
+__device__ __forceinline__ void c64_dir(const double (&xs)[CF_R], double (&y)[CF_R], int lane, const ChanFastParams &K,
+                                        cdd *carry, cdd (&cin)[2], cdd *Fe, bool edge_lane)
+{
+    const cdd p0 = ldd(K.p[0]), p1 = ldd(K.p[1]), a0 = ldd(K.a2[0]), a1 = ldd(K.a2[1]);
+    cdd s[2] = {cdd{0.0, 0.0}, cdd{0.0, 0.0}};
+#pragma unroll
+    for (int i = 0; i < CF_R; ++i) {
+        const int r = FWD ? i : CF_R - 1 - i;
+        d_step(s[0], p0, xs[r]);
+        d_step(s[1], p1, xs[r]);
+        if (STORE) y[r] = d_reacc(a0, s[0], d_reacc(a1, s[1], y[r]));
+        if (EDGE && r == 6) { Fe[0] = s[0]; Fe[1] = s[1]; }       // zero-state F at r = 6
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+        for (int st = 0; st < 5; ++st) {
+            const cdd o = FWD ? dshfl_up(s[m], 1 << st) : dshfl_down(s[m], 1 << st);
+            if (FWD ? (lane >= (1 << st)) : (lane + (1 << st) < 32)) s[m] = cfmad(ldd(K.ppow[st][m]), o, s[m]);
+        }
+        cin[m] = FWD ? dshfl_up(s[m], 1) : dshfl_down(s[m], 1);
+        if (lane == (FWD ? 0 : 31)) cin[m] = cdd{0.0, 0.0};
+        if (lane == (FWD ? 31 : 0)) carry[m] = s[m];
+        if (EDGE && edge_lane) Fe[m] = cfmad(ldd(K.p7[m]), cin[m], Fe[m]);     // + p^7 * (carry from lane 0 of this warp)
+    }
+}
+
+// component c (0 = I, 1 = Q) of the lane's CF_R samples
+template <typename TI>
+__device__ __noinline__ double c64_padded(const TI *__restrict__ xc, long n, long t, double W, double fs, int c)
+{
+    const cdd v = chan_padded<TI>(xc, n, t, W, fs);
+    return c ? v.y : v.x;
+}
+template <typename TI>
+__device__ __forceinline__ void c64_load(const TI *__restrict__ xc, long n, long m0, double W, double fs, int c, double (&xs)[CF_R])
+{
+    if (W == 0.0 && m0 >= 0 && m0 + CF_R <= n) {
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) xs[r] = (double)xc[2 * (m0 + r) + c];
+    } else {
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) xs[r] = c64_padded<TI>(xc, n, 15 + m0 + r, W, fs, c);
+    }
+}
+
+constexpr int C64_TILE = CG_NS * CF_P;                       // samples a CTA stores
+__host__ __device__ constexpr int c64_pad(int i) { return i + (i >> 4); }    // staging index: lane stride 8 doubles -> no bank conflicts
+
+// CTA = 16 warps: warp (pass, component).  I and Q never mix in the filter, so each warp carries one real signal: half
+// the registers of a (pass, I+Q) warp, twice the warps in flight for the same work — the kernel is bound by the latency
+// of dependent DFMAs, not by their count.  Results meet in shared memory: coalesced double2 stores and |y|^2.
+template <typename TI>
+__global__ void __launch_bounds__(2 * CF_W * 32, 2)
+chan_fast64_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_per_chunk,
+                   const double *__restrict__ freq_off, double fs, ChanFastParams K,
+                   double *__restrict__ filtered, long out_stride, double *__restrict__ phase_partial, int sps, int step)
+{
+    __shared__ cdd carryF[CG_NP][2][2];       // [pass][I/Q][mode]
+    __shared__ cdd carryB[CG_NP][2][2];
+    __shared__ cdd kappa[2][2];               // [I/Q][mode] right-edge transient amplitudes of this chunk (last tile only)
+    __shared__ cdd lanepow[32][2];
+    __shared__ double ys[2][c64_pad(C64_TILE) + 1];          // outputs of the tile per component, then |y|^2 in ys[0]
+    if (threadIdx.x < 64) lanepow[threadIdx.x >> 1][threadIdx.x & 1] = ldd(K.lanepow[threadIdx.x >> 1][threadIdx.x & 1]);
+    const int chunk = blockIdx.x / tiles_per_chunk;
+    const int tile = blockIdx.x - chunk * tiles_per_chunk;
+    const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = wi >> 1, c = wi & 1;        // pass, component
+    const TI *xc = x + (long)chunk * in_stride * 2;
+    const double f = freq_off ? freq_off[chunk] : 0.0;
+    const double W = (f != 0.0) ? __dmul_rn(-6.283185307179586, f) : 0.0;
+    // tiling: see chan_fast_kernel
+    const bool last_tile = tile == tiles_per_chunk - 1;
+    const long mt0 = n - (long)(tiles_per_chunk - tile) * C64_TILE;
+    const bool store = w > 0;
+    const int passB = store ? w : CG_NP - 1;
+    const long m0 = mt0 - CF_P + (long)w * CF_P + (long)lane * CF_R;
+    const long m0B = mt0 - CF_P + (long)passB * CF_P + (long)lane * CF_R;
+    const bool edge_lane = last_tile && w == 0 && lane == 1;
+    cdd Fe[2], cF[2], cB[2];
+
+    double xs[CF_R], y[CF_R];
+    c64_load<TI>(xc, n, m0, W, fs, c, xs);
+    if (store) {
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) y[r] = K.c0p * xs[r];
+        c64_dir<true, true, false>(xs, y, lane, K, carryF[w][c], cF, Fe, false);
+        c64_dir<false, true, false>(xs, y, lane, K, carryB[w][c], cB, Fe, false);
+    } else {
+        c64_dir<true, false, false>(xs, y, lane, K, carryF[0][c], cF, Fe, false);
+        c64_load<TI>(xc, n, m0B, W, fs, c, xs);
+        if (last_tile) c64_dir<true, false, true>(xs, y, lane, K, carryF[CG_NP - 1][c], cF, Fe, edge_lane);   // F[M-1] lives in the right halo
+        c64_dir<false, false, false>(xs, y, lane, K, carryB[CG_NP - 1][c], cB, Fe, false);
+    }
+    __syncthreads();
+    if (last_tile) {
+        if (edge_lane) {
+            // F_j[M-1] = local + p^15 * (end state of the last storing pass);  kappa_i = ka_i x_last + sum_j kM F_j + kMc conj F_j
+            for (int m = 0; m < 2; ++m) Fe[m] = cfmad(ldd(K.p15[m]), carryF[CG_NP - 2][c][m], Fe[m]);
+            for (int i = 0; i < 2; ++i) {
+                cdd k = cdd{K.ka[i][0] * xs[6], K.ka[i][1] * xs[6]};
+                for (int j = 0; j < 2; ++j) {
+                    k = cfmad(ldd(K.kM[i][j]), Fe[j], k);
+                    k = cfmad(ldd(K.kMc[i][j]), cdd{Fe[j].x, -Fe[j].y}, k);
+                }
+                kappa[c][i] = k;
+            }
+        }
+        __syncthreads();
+    }
+    if (store) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            // total carry into this lane: in-pass (from the scan) + lane power * end state of the neighbouring pass
+            const cdd gF = cfmad(lanepow[lane][m], carryF[w - 1][c][m], cF[m]);
+            const cdd gB = cfmad(lanepow[31 - lane][m], carryB[w + 1][c][m], cB[m]);
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) y[r] = d_reacc(ldd(K.aF2[r][m]), gF, d_reacc(ldd(K.aB2[r][m]), gB, y[r]));
+        }
+        const int mi = (int)m0, ni = (int)n;                     // n < 2^30 (launch_t): 32-bit index tests
+        if (last_tile && ni - 1 - mi < CF_FIX + CF_R) {
+            // y[m] -= 2 Re sum_i kappa_i p_i^(16 + mm),  mm = n-1-m   (only the last CF_FIX samples matter)
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) {
+                const int mm = ni - 1 - (mi + r);
+                if (mm < 0 || mm >= CF_FIX) continue;
+                const int a = mm / CF_R, b = mm - a * CF_R;
+                for (int m = 0; m < 2; ++m) {
+                    cdd g = ldd(K.pc[m]);
+                    for (int sft = 0; sft < 6; ++sft) if (a & (1 << sft)) g = cmuld(g, ldd(K.ppow[sft][m]));
+                    const cdd pm = ldd(K.p[m]);
+                    for (int i = 0; i < b; ++i) g = cmuld(g, pm);
+                    y[r] -= 2.0 * (kappa[c][m].x * g.x - kappa[c][m].y * g.y);
+                }
+            }
+        }
+        const int i0 = (w - 1) * CF_P + lane * CF_R;
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) ys[c][c64_pad(i0 + r)] = y[r];
+    }
+    __syncthreads();
+    // ---- coalesced complex128 stores; |y|^2 replaces the I component in shared memory
+    {
+        double2 *out = reinterpret_cast<double2 *>(filtered) + (long)chunk * out_stride;
+        const int ni = (int)n, t0 = (int)mt0;
+        for (int i = threadIdx.x; i < C64_TILE; i += 2 * CF_W * 32) {
+            const int m = t0 + i, ip = c64_pad(i);
+            const double yi = ys[0][ip], yq = ys[1][ip];
+            const bool ok = m >= 0 && m < ni;
+            if (ok) out[m] = make_double2(yi, yq);
+            if (phase_partial) ys[0][ip] = ok ? fma(yi, yi, yq * yq) : 0.0;
+        }
+    }
+    // ---- per-phase power partial sums for the timing pick (extract_symbols, processor.py:196-210): 16 threads per
+    // phase walk the tile's |y|^2 in shared memory (fixed order), a 16-lane shuffle tree finishes the sum.
+    if (phase_partial) {
+        __syncthreads();
+        const int grp = threadIdx.x >> 4, seg = threadIdx.x & 15;
+        const int ph = grp * step;
+        double t = 0.0;
+        if (ph < sps) {
+            const int ni = (int)n, t0 = (int)mt0, lo = t0 > 0 ? t0 : 0, hi = t0 + C64_TILE;
+            int d = ph - lo % sps;
+            if (d < 0) d += sps;                                             // first sample of this phase in the tile: lo + d
+            // symbols of this phase are k < (n - ph) / sps, i.e. samples m = ph + sps k with m + sps <= n
+            for (int m = lo + d + seg * sps; m < hi && m + sps <= ni; m += 16 * sps) t += ys[0][c64_pad(m - t0)];
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (ph < sps && seg == 0) phase_partial[((long)chunk * tiles_per_chunk + tile) * TB200_MAX_PHASES + ph] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // float32 packed variant (TB200_OPT_CHAN_F32, complex64 input).  Same two-sided modal form; the I and Q components
 // share every coefficient, so all recurrences, scans and carries run on float2 (I, Q) pairs with fma.rn.f32x2
 // (SASS FFMA2), Kogge-Stone stages whose multiplier (p^R)^(2^s) is below 1e-9 are skipped, the lane powers of the
@@ -410,7 +607,7 @@ chan_fast32_kernel(const float *__restrict__ x, long n, long in_stride, int tile
     __shared__ cp carryB[C32_NP][2];
     __shared__ cp kappa[2];
     __shared__ cf lanepow[32][2];
-    __shared__ float pws[C32_NS * CF_P];
+    __shared__ float pws[C32_NS * CF_P + C32_NS * CF_P / 32];      // index i + (i >> 5): lane stride 8 floats -> no bank conflicts
     if (threadIdx.x < 64) lanepow[threadIdx.x >> 1][threadIdx.x & 1] = ld2(K.lanepow[threadIdx.x >> 1][threadIdx.x & 1]);
     const int chunk = blockIdx.x / tiles_per_chunk;
     const int tile = blockIdx.x - chunk * tiles_per_chunk;
@@ -488,7 +685,7 @@ chan_fast32_kernel(const float *__restrict__ x, long n, long in_stride, int tile
         }
         double2 *out = reinterpret_cast<double2 *>(filtered) + (long)chunk * out_stride + m0;
         const int mi = (int)m0, ni = (int)n;                     // n < 2^30 (launch_t): 32-bit index tests
-        float *pw = pws + (w - 1) * CF_P + lane * CF_R;
+        float *pw = pws + (w - 1) * CF_P + lane * CF_R + (((w - 1) * CF_P + lane * CF_R) >> 5);     // 8 samples of a lane share i >> 5
         if (mi >= 0 && mi + CF_R <= ni) {
 #pragma unroll
             for (int r = 0; r < CF_R; ++r) {
@@ -513,10 +710,10 @@ chan_fast32_kernel(const float *__restrict__ x, long n, long in_stride, int tile
         double t = 0.0;
         if (ph < sps) {
             const int ni = (int)n, t0 = (int)mt0, lo = t0 > 0 ? t0 : 0, hi = t0 + C32_NS * CF_P;
-            const int first = lo + ((ph - lo % sps) % sps + sps) % sps;      // first sample of this phase in the tile
-            const int kmax = (ni - ph) / sps;                                // symbols of this phase: k < kmax
-            int k = first / sps + seg;                                       // first = ph + sps * (first / sps)
-            for (int m = first + seg * sps; m < hi && k < kmax; m += 16 * sps, k += 16) t += (double)pws[m - t0];
+            int d = ph - lo % sps;
+            if (d < 0) d += sps;                                             // first sample of this phase in the tile: lo + d
+            // symbols of this phase are k < (n - ph) / sps, i.e. samples m = ph + sps k with m + sps <= n
+            for (int m = lo + d + seg * sps; m < hi && m + sps <= ni; m += 16 * sps) { const int i = m - t0; t += (double)pws[i + (i >> 5)]; }
         }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
@@ -575,6 +772,18 @@ static int make_chan_params(double bandwidth, double fs, ChanFastParams &K)
         }
         putd(K.inv1mp[j], 1.0 / (1.0 - p4[j]));
         putd(K.pc[j], std::pow(p4[j], 16));
+        putd(K.a2[j], 2.0 * alpha[j]);
+        for (int r = 0; r < CF_R; ++r) {
+            putd(K.aF2[r][j], 2.0 * alpha[j] * std::pow(p4[j], r + 1));
+            putd(K.aB2[r][j], 2.0 * alpha[j] * std::pow(p4[j], CF_R - r));
+        }
+        putd(K.p7[j], std::pow(p4[j], 7));
+        putd(K.p15[j], std::pow(p4[j], 15));
+        const cd pr8 = std::pow(p4[j], CF_R);
+        for (int l = 0; l < 32; ++l) putd(K.lanepow[l][j], std::pow(pr8, l));
+        int ns = 0;
+        for (int s = 0; s < 5; ++s) if (std::hypot(K.ppow[s][j][0], K.ppow[s][j][1]) >= 1e-17) ns = s + 1;
+        K.nstage[j] = ns;
     }
     cd H1(dd, 0.0);
     for (int j = 0; j < 4; ++j) H1 += r4[j] / (1.0 - p4[j]);
@@ -656,6 +865,9 @@ static int launch_t(tb200_handle h, const void *x, int n_chunks, long n, long in
     } else if (h->chan_f32)
         chan_fast_kernel<TI, float><<<n_chunks * tiles, CF_W * 32, 0, st>>>((const TI *)x, n, in_stride, tiles, freq_off, fs, K,
                                                                           filtered, out_stride, phase_partial, sps, step);
+    else if (n < (1L << 30))
+        chan_fast64_kernel<TI><<<n_chunks * tiles, 2 * CF_W * 32, 0, st>>>((const TI *)x, n, in_stride, tiles, freq_off, fs, K,
+                                                                     filtered, out_stride, phase_partial, sps, step);
     else
         chan_fast_kernel<TI, double><<<n_chunks * tiles, CF_W * 32, 0, st>>>((const TI *)x, n, in_stride, tiles, freq_off, fs, K,
                                                                            filtered, out_stride, phase_partial, sps, step);
