@@ -21,6 +21,8 @@
 #include <vector>
 #include "common.h"
 #include "kernels.h"
+#include "packed.h"
+#include "decim_common.h"
 
 namespace tb200 {
 
@@ -35,8 +37,8 @@ struct RefChanEdge {
     int L;                           // truncation length of g (multiple of M)
 };
 
-// twiddles of the in-register transforms: e^{+j 2 pi i / 32} (i < 16), e^{+j 2 pi i / 5} (i < 5), e^{+j 2 pi i / 25} (i < 25)
-__constant__ float2 c_w32[16];
+// twiddles of the in-register transforms: e^{+j 2 pi i / 32} (i < 32), e^{+j 2 pi i / 5} (i < 5), e^{+j 2 pi i / 25} (i < 25)
+__constant__ float2 c_w32[32];
 __constant__ float2 c_w5[5];
 __constant__ float2 c_w25[25];
 
@@ -44,24 +46,6 @@ __device__ __forceinline__ float2 cmulf2(float2 a, float2 b) { return make_float
 __device__ __forceinline__ float2 caddf2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csubf2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
-__host__ __device__ constexpr int brev5(int i) { return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4); }
-// inverse (e^{+j}) 32-point DFT in registers: v[] holds the input in BIT-REVERSED order, the output in natural order
-template <int S>
-__device__ __forceinline__ void ifft32_stage(float2 (&v)[32])
-{
-    constexpr int m = 1 << S, hm = m >> 1, tstep = 32 >> S;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {                       // butterfly i: block i / hm, position i % hm
-        const int b = (i / hm) * m, j = i % hm;
-        const float2 t = j ? cmulf2(c_w32[j * tstep], v[b + j + hm]) : v[b + j + hm];
-        v[b + j + hm] = csubf2(v[b + j], t);
-        v[b + j] = caddf2(v[b + j], t);
-    }
-}
-__device__ __forceinline__ void ifft32_regs(float2 (&v)[32])
-{
-    ifft32_stage<1>(v); ifft32_stage<2>(v); ifft32_stage<3>(v); ifft32_stage<4>(v); ifft32_stage<5>(v);
-}
 // inverse 5-point DFT of (a0..a4), direct
 __device__ __forceinline__ void idft5(const float2 (&a)[5], float2 (&o)[5])
 {
@@ -73,33 +57,7 @@ __device__ __forceinline__ void idft5(const float2 (&a)[5], float2 (&o)[5])
         o[k] = acc;
     }
 }
-// inverse 25-point DFT in registers (5 x 5 Cooley-Tukey): in[r1], r1 = 5 a + b  ->  out[k1], k1 = c + 5 d
-__device__ __forceinline__ void idft25_regs(const float2 (&in)[25], float2 (&out)[25])
-{
-    float2 y[25];
-#pragma unroll
-    for (int b = 0; b < 5; ++b) {                     // over a: Y[b][c] = sum_a in[5 a + b] w5^(a c)
-        float2 col[5], o[5];
-#pragma unroll
-        for (int a = 0; a < 5; ++a) col[a] = in[5 * a + b];
-        idft5(col, o);
-#pragma unroll
-        for (int c = 0; c < 5; ++c) y[5 * b + c] = (b && c) ? cmulf2(o[c], c_w25[(b * c) % 25]) : o[c];      // twiddle w25^(b c)
-    }
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {                     // over b: X[c + 5 d] = sum_b Y[b][c] w5^(b d)
-        float2 row[5], o[5];
-#pragma unroll
-        for (int b = 0; b < 5; ++b) row[b] = y[5 * b + c];
-        idft5(row, o);
-#pragma unroll
-        for (int d = 0; d < 5; ++d) out[c + 5 * d] = o[d];
-    }
-}
-
-// FFT = true: M = 25 x 32 (800 channels): both small DFTs run in registers (5 x 5 and radix-2), one thread per
-// (frame, r2) column resp. (frame, k1) row.  FFT = false: direct small DFTs from the twiddle tables, any M = N1 x 2^k.
-template <bool FFT>
+// General form, any M = N1 x 2^k: direct small DFTs from the twiddle tables (M = 800 has its own kernel below).
 __global__ void __launch_bounds__(256)
 refchan_kernel(const float2 *__restrict__ x, long n, int M, int N1, int log2_n2, int F, int P, int l0, int hop, long n_frames,
                const float *__restrict__ proto, const float2 *__restrict__ tw, float2 *__restrict__ out, long out_stride)
@@ -137,40 +95,6 @@ refchan_kernel(const float2 *__restrict__ x, long n, int M, int N1, int log2_n2,
         for (int f = 0; f < 8; ++f) if (f < F) v[f * M + r] = (m0 + f < n_frames) ? acc[f] : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    if (FFT) {
-        // ---- stage A: thread (f, r2): 25-point inverse DFT over r1 (r = 32 r1 + r2) in registers, times e^{+j 2 pi k1 r2 / M}
-        for (int c = threadIdx.x; c < F * 32; c += blockDim.x) {
-            const int f = c >> 5, r2 = c & 31;
-            float2 in[25], o[25];
-#pragma unroll
-            for (int r1 = 0; r1 < 25; ++r1) in[r1] = v[f * M + (r1 << 5) + r2];
-            idft25_regs(in, o);
-#pragma unroll
-            for (int k1 = 0; k1 < 25; ++k1) a[(f * 25 + k1) * APITCH + r2] = cmulf2(o[k1], wm[k1 * r2]);
-        }
-        __syncthreads();
-        // ---- stage B: thread (f, k1): 32-point inverse FFT over r2 in registers; k = k1 + 25 k2; rotation; store
-        for (int c = threadIdx.x; c < F * 25; c += blockDim.x) {
-            const int k1 = c / F, f = c - k1 * F;             // f fastest: the F outputs of a channel row are one 64-byte segment
-            const long j = m0 + f;
-            float2 vv[32];
-            const float2 *af = a + (f * 25 + k1) * APITCH;
-#pragma unroll
-            for (int r2 = 0; r2 < 32; ++r2) vv[brev5(r2)] = af[r2];
-            ifft32_regs(vv);
-            if (j < n_frames) {
-                const int jm = (int)(j % M);
-#pragma unroll
-                for (int k2 = 0; k2 < 32; ++k2) {
-                    const int k = k1 + 25 * k2;
-                    const int kh = (int)(((long)k * hop) % M);
-                    const float2 rot = wm[(kh * jm) % M];        // e^{+j 2 pi (k hop j) / M}; conjugate applied
-                    out[(long)k * out_stride + j] = make_float2(vv[k2].x * rot.x + vv[k2].y * rot.y, vv[k2].y * rot.x - vv[k2].x * rot.y);
-                }
-            }
-        }
-        return;
-    }
     // ---- stage A: for every r2, a size-N1 DFT over r1 (r = N2 r1 + r2), times exp(+j 2 pi k1 r2 / M)
     for (int jj = threadIdx.x; jj < M; jj += blockDim.x) {
         const int k1 = jj >> log2_n2, r2 = jj & (N2 - 1);
@@ -206,6 +130,192 @@ refchan_kernel(const float2 *__restrict__ x, long n, int M, int N1, int log2_n2,
             }
             const float2 rot = wm[(int)(((long)kh * (j % M)) % M)];     // e^{+j 2 pi (k hop j) / M}; conjugate applied
             o[f] = make_float2(acc.x * rot.x + acc.y * rot.y, acc.y * rot.x - acc.x * rot.y);
+        }
+    }
+}
+
+// ---- M = 800 = 25 x 32 ---------------------------------------------------------------------------------------------
+// A CTA folds the windows of 8 consecutive frames and transforms them.  The window of a frame is P * 800 samples (150 KB
+// for P = 24) and the windows of the 8 frames overlap almost entirely, so the input is staged in shared memory one
+// prototype block l at a time: the samples that block needs for all 8 frames are the 800 + 7 hop contiguous samples
+//     x[hop m0 - 799 - 800 l  ..  hop (m0 + 7) - 800 l],
+// brought in by one TMA bulk copy per block into a three-deep ring, two blocks ahead of the one being accumulated.  The 800-point
+// inverse DFT runs in place on the folded windows V[r1][f][r2] (r = 32 r1 + r2, pitch 33) as four small-radix passes —
+// 5-point over a (r1 = 5a + b), 5-point over b, 8-point over i and 4-point over g (r2 = 4i + g) — each a thread per
+// (row, column) task, so no thread holds more than 8 points and all 416 threads have work.  Output k = k1 + 25 k2.
+constexpr int PB_M = 800, PB_F = 8, PB_PITCH = 33, PB_ROWS = 25 * PB_F, PB_THREADS = 416, PB_RS = 400, PB_RING = 3;
+
+// inverse 8-point DFT in registers, radix 2: v[] holds the input in bit-reversed order, the output in natural order
+__device__ __forceinline__ void ifft8_regs(float2 (&v)[8])
+{
+#pragma unroll
+    for (int S = 1; S <= 3; ++S) {
+        const int m = 1 << S, hm = m >> 1, tstep = 32 >> S;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = (i / hm) * m, j = i % hm;
+            const float2 t = j ? cmulf2(c_w32[j * tstep], v[b + j + hm]) : v[b + j + hm];
+            v[b + j + hm] = csubf2(v[b + j], t);
+            v[b + j] = caddf2(v[b + j], t);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PB_THREADS, 2)
+polybank800_kernel(const float2 *__restrict__ x, long n, int P, int l0, int hop, long n_frames,
+                   const float *__restrict__ proto, const float2 *__restrict__ wm_g, float2 *__restrict__ out, long out_stride)
+{
+    extern __shared__ float2 pb_smem[];
+    __shared__ __align__(8) uint64_t full[PB_RING];
+    float2 *V = pb_smem;                              // [r1 or rho][f][PB_PITCH]
+    float2 *wm = V + PB_ROWS * PB_PITCH;              // [800] exp(+j 2 pi i / 800)
+    float2 *seg = wm + PB_M;                          // [PB_RING][SEGP]
+    // block l of the prototype needs x[s0 .. s0 + SEG), s0 = hop m0 - 799 - 800 l: odd, so the staged range starts one
+    // sample earlier (16-byte aligned for the bulk copy) and is padded to an even length
+    const int SEG = PB_M + (PB_F - 1) * hop, SEGP = (SEG + 2) & ~1;
+    const int tid = threadIdx.x;
+    const long m0 = (long)blockIdx.x * PB_F;
+    const long s_base = (long)hop * m0 - PB_M;        // first staged sample of block l: s_base - 800 l
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    if (tid == 0) {
+        for (int i = 0; i < PB_RING; ++i) mbar_init(&full[i], 1);
+    }
+    __syncthreads();
+    auto bulk = [&](int l) -> bool {                  // the whole staged range of block l lies inside the chunk
+        const long s0 = s_base - (long)PB_M * l;
+        return aligned && s0 >= 0 && s0 + SEGP <= n;
+    };
+    // inside the chunk: ONE bulk copy (TMA) issued by thread 0, completion on the slot's mbarrier; at the chunk ends:
+    // plain loads with zeros outside [0, n), made visible by the loop's __syncthreads
+    auto stage = [&](int l, int buf) {
+        const long s0 = s_base - (long)PB_M * l;
+        float2 *dst = seg + buf * SEGP;
+        if (bulk(l)) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                tma_load_1d(dst, x + s0, (unsigned)SEGP * 8u, &full[buf]);
+            }
+        } else {
+            for (int i = tid; i < SEGP; i += PB_THREADS) {
+                const long t = s0 + i;
+                dst[i] = (t >= 0 && t < n) ? x[t] : make_float2(0.f, 0.f);
+            }
+        }
+    };
+    stage(l0, 0);
+    if (P > 1) stage(l0 + 1, 1);
+    for (int i = tid; i < PB_M; i += PB_THREADS) wm[i] = wm_g[i];
+    // ---- folded windows: v_f[r] = sum_l h[r + 800 l] x[hop (m0 + f) - r - 800 l]; sample (r, f) of block l is staged at
+    // index 800 - r + hop f.  Branches hop apart see the same samples one frame later, so a thread takes the pair
+    // (rA, rA + hop) and all 8 frames: 9 shared loads feed 16 packed multiply-adds.  (If hop * ceil(ceil(800 / hop) / 2)
+    // exceeds the CTA, a thread takes branches r and r + 400 instead: 16 loads.)
+    const int nI = (PB_M + hop - 1) / hop, groups = (nI + 1) / 2;
+    const bool toep = hop * groups <= PB_THREADS;
+    int rA, rB;
+    if (toep) { const int grp = tid / hop; rA = tid - grp * hop + 2 * grp * hop; rB = rA + hop; if (grp >= groups) rA = rB = PB_M; }
+    else { rA = tid < PB_RS ? tid : PB_M; rB = tid < PB_RS ? tid + PB_RS : PB_M; }
+    const bool vA = rA < PB_M, vB = rB < PB_M;
+    float2 acc[2][PB_F];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int f = 0; f < PB_F; ++f) acc[i][f] = make_float2(0.f, 0.f);
+    unsigned phase = 0;                               // bit b: parity the next bulk completion of slot b will have
+    float hA_n = vA ? __ldg(proto + rA) : 0.f, hB_n = vB ? __ldg(proto + rB) : 0.f;
+    for (int li = 0; li < P; ++li) {
+        const int slot = li % PB_RING;
+        const float hA = hA_n, hB = hB_n;             // taps are fetched one block ahead: their latency hides behind the wait
+        if (li + 1 < P) { hA_n = vA ? __ldg(proto + (li + 1) * PB_M + rA) : 0.f; hB_n = vB ? __ldg(proto + (li + 1) * PB_M + rB) : 0.f; }
+        if (bulk(l0 + li)) { mbar_wait(&full[slot], (phase >> slot) & 1u); phase ^= 1u << slot; }
+        __syncthreads();                              // block li is visible; everyone is done with the buffer of block li - 1
+        if (li + 2 < P) stage(l0 + li + 2, (li + 2) % PB_RING);
+        const float2 *sg = seg + slot * SEGP + PB_M;
+        if (toep) {
+            if (vA) {
+                float2 prev = vB ? sg[-rB] : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int f = 0; f < PB_F; ++f) {
+                    const float2 cur = sg[hop * f - rA];
+                    acc[0][f] = ffma2(splat(hA), cur, acc[0][f]);
+                    acc[1][f] = ffma2(splat(hB), prev, acc[1][f]);
+                    prev = cur;
+                }
+            }
+        } else if (vA) {
+#pragma unroll
+            for (int f = 0; f < PB_F; ++f) {
+                acc[0][f] = ffma2(splat(hA), sg[hop * f - rA], acc[0][f]);
+                acc[1][f] = ffma2(splat(hB), sg[hop * f - rB], acc[1][f]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int r = i ? rB : rA;
+        if (r < PB_M) {
+            const int r1 = r >> 5, r2 = r & 31;
+#pragma unroll
+            for (int f = 0; f < PB_F; ++f) V[(r1 * PB_F + f) * PB_PITCH + r2] = (m0 + f < n_frames) ? acc[i][f] : make_float2(0.f, 0.f);
+        }
+    }
+    __syncthreads();
+    // ---- pass 1 (in place): 5-point inverse DFT over a, r1 = 5a + b; result c goes to row 5c + b with the twiddle w25^(b c)
+    for (int c = tid; c < PB_F * 32 * 5; c += PB_THREADS) {
+        const int r2 = c & 31, b = (c >> 5) % 5, f = c / 160;
+        float2 *col = V + (b * PB_F + f) * PB_PITCH + r2;
+        float2 in[5], o[5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) in[a] = col[5 * a * PB_F * PB_PITCH];
+        idft5(in, o);
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc) col[5 * cc * PB_F * PB_PITCH] = cc ? cmulf2(o[cc], c_w25[b * cc]) : o[cc];
+    }
+    __syncthreads();
+    // ---- pass 2 (in place): 5-point inverse DFT over b of rows 5c + b; k1 = c + 5d goes to row 5c + d, times e^{+j 2 pi k1 r2 / 800}
+    for (int c = tid; c < PB_F * 32 * 5; c += PB_THREADS) {
+        const int r2 = c & 31, cc = (c >> 5) % 5, f = c / 160;
+        float2 *col = V + (5 * cc * PB_F + f) * PB_PITCH + r2;
+        float2 in[5], o[5];
+#pragma unroll
+        for (int b = 0; b < 5; ++b) in[b] = col[b * PB_F * PB_PITCH];
+        idft5(in, o);
+#pragma unroll
+        for (int d = 0; d < 5; ++d) col[d * PB_F * PB_PITCH] = cmulf2(o[d], wm[(cc + 5 * d) * r2]);
+    }
+    __syncthreads();
+    // ---- pass 3 (in place): 8-point inverse DFT over i, r2 = 4i + g; result u goes to column 4u + g with the twiddle w32^(g u)
+    for (int c = tid; c < PB_ROWS * 4; c += PB_THREADS) {
+        const int row = c % PB_ROWS, g = c / PB_ROWS;
+        float2 *rp = V + row * PB_PITCH + g;
+        float2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[((i & 1) << 2) | (i & 2) | ((i & 4) >> 2)] = rp[4 * i];
+        ifft8_regs(v);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rp[4 * u] = (g && u) ? cmulf2(v[u], c_w32[g * u]) : v[u];
+    }
+    __syncthreads();
+    // ---- pass 4: 4-point inverse DFT over g of columns 4u + g: k2 = u + 8v; channel k = k1 + 25 k2; rotation e^{-j 2 pi k hop j / 800}
+    for (int c = tid; c < PB_ROWS * 8; c += PB_THREADS) {
+        const int row = c % PB_ROWS, u = c / PB_ROWS;
+        const int f = row & (PB_F - 1), rho = row >> 3;
+        const long j = m0 + f;
+        if (j >= n_frames) continue;
+        const float2 *rp = V + row * PB_PITCH + 4 * u;
+        const float2 z0 = rp[0], z1 = rp[1], z2 = rp[2], z3 = rp[3];
+        const float2 s02 = caddf2(z0, z2), d02 = csubf2(z0, z2), s13 = caddf2(z1, z3), d13 = csubf2(z1, z3);
+        float2 X[4];
+        X[0] = caddf2(s02, s13);
+        X[1] = make_float2(d02.x - d13.y, d02.y + d13.x);          // d02 + j d13
+        X[2] = csubf2(s02, s13);
+        X[3] = make_float2(d02.x + d13.y, d02.y - d13.x);          // d02 - j d13
+        const int k1 = rho / 5 + 5 * (rho % 5);
+        const unsigned hj = (unsigned)(((long)hop * j) % PB_M);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int k = k1 + 25 * (u + 8 * v);
+            const float2 rot = wm[((unsigned)k * hj) % PB_M];         // conjugate applied
+            out[(long)k * out_stride + j] = make_float2(X[v].x * rot.x + X[v].y * rot.y, X[v].y * rot.x - X[v].x * rot.y);
         }
     }
 }
@@ -253,14 +363,26 @@ refchan_edge_kernel(const float2 *__restrict__ x, long n, int q, double fs, cons
         const int per = (E.L + 127) / 128;
         cdd2 S[4][2];
         for (int i = 0; i < 4; ++i) S[i][0] = S[i][1] = cdd2{0.0, 0.0};
-        // thread tid covers k = tid*per .. tid*per+per-1, walked from the far end so that S = sum p^(k - k0) ext[..]
+        // thread tid covers k = tid*per .. tid*per+per-1, walked from the far end so that S = sum p^(k - k0) ext[..].
+        // The NCO of this run of consecutive samples is one sincos and a rotation per step (the transient it feeds is
+        // ~1e-3 of the output and needs 1e-4 of that; `per` rotations lose ~1e-14).
+        cdd2 cur, rot;
+        {
+            const long t_first = n + 26 - ((long)tid * per + per - 1);
+            double sn, cs;
+            sincos(__dmul_rn(W, (double)t_first / fs), &sn, &cs);
+            cur = cdd2{cs, sn};
+            sincos(W / fs, &sn, &cs);
+            rot = cdd2{cs, sn};
+        }
         for (int u = per - 1; u >= 0; --u) {
             const long k = (long)tid * per + u;
             const long t = n + 26 - k;
             cdd2 e;
             if (t >= n) e = extR[t - n];
-            else if (t >= 0) e = shifted(x, t, W, fs);
+            else if (t >= 0) e = zmul(cdd2{(double)x[t].x, (double)x[t].y}, cur);
             else e = cdd2{0.0, 0.0};
+            cur = zmul(cur, rot);
             for (int i = 0; i < 4; ++i) {
                 const cdd2 p = cdd2{E.p[i][0], E.p[i][1]};
                 cdd2 a = zmul(p, S[i][0]); a.x += e.x; S[i][0] = a;       // I component (real signal, complex state)
@@ -463,6 +585,31 @@ int launch_refchan(tb200_handle h, const float2 *x, long n, int M, int q, double
 int launch_polyphase_bank(tb200_handle h, const float2 *x, long n, int M, int N1, int N2, int P, int l0, int hop, long n_frames,
                           const float *proto, const float2 *tw, float2 *out, long out_stride, cudaStream_t st)
 {
+    if (N1 == 25 && N2 == 32) {
+        const size_t smem = sizeof(float2) * ((size_t)PB_ROWS * PB_PITCH + PB_M + PB_RING * (size_t)((PB_M + (PB_F - 1) * hop + 2) & ~1));
+        if (smem <= 200 * 1024) {
+            static std::once_flag tw_once[64];
+            static cudaError_t tw_err[64];
+            const int dv = h->cfg.device & 63;
+            std::call_once(tw_once[dv], [&] {
+                float2 w32[32], w5[5], w25[25];
+                for (int i = 0; i < 32; ++i) w32[i] = make_float2((float)std::cos(2 * M_PI * i / 32), (float)std::sin(2 * M_PI * i / 32));
+                for (int i = 0; i < 5; ++i) w5[i] = make_float2((float)std::cos(2 * M_PI * i / 5), (float)std::sin(2 * M_PI * i / 5));
+                for (int i = 0; i < 25; ++i) w25[i] = make_float2((float)std::cos(2 * M_PI * i / 25), (float)std::sin(2 * M_PI * i / 25));
+                cudaError_t e1 = cudaMemcpyToSymbol(c_w32, w32, sizeof(w32));
+                cudaError_t e2 = cudaMemcpyToSymbol(c_w5, w5, sizeof(w5));
+                cudaError_t e3 = cudaMemcpyToSymbol(c_w25, w25, sizeof(w25));
+                tw_err[dv] = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+            });
+            if (tw_err[dv] != cudaSuccess) return fail(TB200_E_CUDA, "polyphase bank: twiddle upload: %s", cudaGetErrorString(tw_err[dv]));
+            cudaError_t e = cudaFuncSetAttribute(polybank800_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(polybank800): %s", cudaGetErrorString(e));
+            const unsigned blocks = (unsigned)((n_frames + PB_F - 1) / PB_F);
+            polybank800_kernel<<<blocks, PB_THREADS, smem, st>>>(x, n, P, l0, hop, n_frames, proto, tw + N1 + N2, out, out_stride);
+            TB_LAUNCH_CHECK(h);
+            return TB200_OK;
+        }
+    }
     int F = 8;
     int log2_n2 = 0;
     while ((1 << log2_n2) < N2) ++log2_n2;
@@ -470,29 +617,10 @@ int launch_polyphase_bank(tb200_handle h, const float2 *x, long n, int M, int N1
     size_t smem = need(F);
     while (smem > 100 * 1024 && F > 1) { F /= 2; smem = need(F); }
     if (smem > 200 * 1024) return fail(TB200_E_ARG, "polyphase bank: M=%d too large for shared memory", M);
-    const bool use_fft = (N1 == 25 && N2 == 32 && F == 8);
-    if (use_fft) {
-        static std::once_flag tw_once[64];
-        static cudaError_t tw_err[64];
-        const int dv = h->cfg.device & 63;
-        std::call_once(tw_once[dv], [&] {
-            float2 w32[16], w5[5], w25[25];
-            for (int i = 0; i < 16; ++i) w32[i] = make_float2((float)std::cos(2 * M_PI * i / 32), (float)std::sin(2 * M_PI * i / 32));
-            for (int i = 0; i < 5; ++i) w5[i] = make_float2((float)std::cos(2 * M_PI * i / 5), (float)std::sin(2 * M_PI * i / 5));
-            for (int i = 0; i < 25; ++i) w25[i] = make_float2((float)std::cos(2 * M_PI * i / 25), (float)std::sin(2 * M_PI * i / 25));
-            cudaError_t e1 = cudaMemcpyToSymbol(c_w32, w32, sizeof(w32));
-            cudaError_t e2 = cudaMemcpyToSymbol(c_w5, w5, sizeof(w5));
-            cudaError_t e3 = cudaMemcpyToSymbol(c_w25, w25, sizeof(w25));
-            tw_err[dv] = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
-        });
-        if (tw_err[dv] != cudaSuccess) return fail(TB200_E_CUDA, "refchan: twiddle upload: %s", cudaGetErrorString(tw_err[dv]));
-    }
-    cudaError_t e = use_fft ? cudaFuncSetAttribute(refchan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                            : cudaFuncSetAttribute(refchan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(refchan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(refchan): %s", cudaGetErrorString(e));
     unsigned blocks = (unsigned)((n_frames + F - 1) / F);
-    if (use_fft) refchan_kernel<true><<<blocks, 256, smem, st>>>(x, n, M, N1, log2_n2, F, P, l0, hop, n_frames, proto, tw, out, out_stride);
-    else refchan_kernel<false><<<blocks, 256, smem, st>>>(x, n, M, N1, log2_n2, F, P, l0, hop, n_frames, proto, tw, out, out_stride);
+    refchan_kernel<<<blocks, 256, smem, st>>>(x, n, M, N1, log2_n2, F, P, l0, hop, n_frames, proto, tw, out, out_stride);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
 }
