@@ -161,8 +161,9 @@ __device__ __forceinline__ void ifft8_regs(float2 (&v)[8])
     }
 }
 
+template <int HOP>                                   // frame spacing as a constant (83: reference mode at 20 MS/s, 400: etsi bank), 0 = run time
 __global__ void __launch_bounds__(PB_THREADS, 2)
-polybank800_kernel(const float2 *__restrict__ x, long n, int P, int l0, int hop, long n_frames,
+polybank800_kernel(const float2 *__restrict__ x, long n, int P, int l0, int hop_rt, long n_frames,
                    const float *__restrict__ proto, const float2 *__restrict__ wm_g, float2 *__restrict__ out, long out_stride)
 {
     extern __shared__ float2 pb_smem[];
@@ -172,6 +173,7 @@ polybank800_kernel(const float2 *__restrict__ x, long n, int P, int l0, int hop,
     float2 *seg = wm + PB_M;                          // [PB_RING][SEGP]
     // block l of the prototype needs x[s0 .. s0 + SEG), s0 = hop m0 - 799 - 800 l: odd, so the staged range starts one
     // sample earlier (16-byte aligned for the bulk copy) and is padded to an even length
+    const int hop = HOP ? HOP : hop_rt;
     const int SEG = PB_M + (PB_F - 1) * hop, SEGP = (SEG + 2) & ~1;
     const int tid = threadIdx.x;
     const long m0 = (long)blockIdx.x * PB_F;
@@ -181,10 +183,14 @@ polybank800_kernel(const float2 *__restrict__ x, long n, int P, int l0, int hop,
         for (int i = 0; i < PB_RING; ++i) mbar_init(&full[i], 1);
     }
     __syncthreads();
-    auto bulk = [&](int l) -> bool {                  // the whole staged range of block l lies inside the chunk
-        const long s0 = s_base - (long)PB_M * l;
-        return aligned && s0 >= 0 && s0 + SEGP <= n;
-    };
+    // blocks l whose whole staged range lies inside the chunk: lb_lo <= l <= lb_hi
+    int lb_lo = 1, lb_hi = 0;
+    if (aligned) {
+        auto fdiv = [](long a, long b) -> long { return a / b - ((a % b != 0) && (a < 0)); };
+        lb_hi = (int)max(min(fdiv(s_base, PB_M), 1L << 20), -(1L << 20));
+        lb_lo = (int)max(min(-fdiv(n - s_base - SEGP, PB_M), 1L << 20), -(1L << 20));
+    }
+    auto bulk = [&](int l) -> bool { return l >= lb_lo && l <= lb_hi; };
     // inside the chunk: ONE bulk copy (TMA) issued by thread 0, completion on the slot's mbarrier; at the chunk ends:
     // plain loads with zeros outside [0, n), made visible by the loop's __syncthreads
     auto stage = [&](int l, int buf) {
@@ -221,31 +227,38 @@ polybank800_kernel(const float2 *__restrict__ x, long n, int P, int l0, int hop,
 #pragma unroll
         for (int f = 0; f < PB_F; ++f) acc[i][f] = make_float2(0.f, 0.f);
     unsigned phase = 0;                               // bit b: parity the next bulk completion of slot b will have
-    float hA_n = vA ? __ldg(proto + rA) : 0.f, hB_n = vB ? __ldg(proto + rB) : 0.f;
-    for (int li = 0; li < P; ++li) {
-        const int slot = li % PB_RING;
-        const float hA = hA_n, hB = hB_n;             // taps are fetched one block ahead: their latency hides behind the wait
-        if (li + 1 < P) { hA_n = vA ? __ldg(proto + (li + 1) * PB_M + rA) : 0.f; hB_n = vB ? __ldg(proto + (li + 1) * PB_M + rB) : 0.f; }
-        if (bulk(l0 + li)) { mbar_wait(&full[slot], (phase >> slot) & 1u); phase ^= 1u << slot; }
-        __syncthreads();                              // block li is visible; everyone is done with the buffer of block li - 1
-        if (li + 2 < P) stage(l0 + li + 2, (li + 2) % PB_RING);
-        const float2 *sg = seg + slot * SEGP + PB_M;
-        if (toep) {
-            if (vA) {
-                float2 prev = vB ? sg[-rB] : make_float2(0.f, 0.f);
+    // taps are fetched one block ahead: their latency hides behind the wait.  Threads without a valid second branch
+    // read tap 0 and the word in front of the stage: their acc[1] is never stored.
+    const float *pA = proto + (vA ? rA : 0), *pB = proto + (vB ? rB : 0);
+    float hA_n = __ldg(pA), hB_n = __ldg(pB);
+    const int offA = PB_M - rA, offB = PB_M - rB;
+    for (int li0 = 0; li0 < P; li0 += PB_RING) {
+#pragma unroll
+        for (int slot = 0; slot < PB_RING; ++slot) {
+            const int li = li0 + slot;
+            if (li >= P) break;
+            const float hA = hA_n, hB = hB_n;
+            if (li + 1 < P) { pA += PB_M; pB += PB_M; hA_n = __ldg(pA); hB_n = __ldg(pB); }
+            if (bulk(l0 + li)) { mbar_wait(&full[slot], (phase >> slot) & 1u); phase ^= 1u << slot; }
+            __syncthreads();                          // block li is visible; everyone is done with the buffer of block li - 1
+            if (li + 2 < P) stage(l0 + li + 2, (slot + 2) % PB_RING);
+            if (!vA) continue;
+            const float2 *sg = seg + slot * SEGP;
+            if (toep) {
+                float2 prev = sg[offB];
 #pragma unroll
                 for (int f = 0; f < PB_F; ++f) {
-                    const float2 cur = sg[hop * f - rA];
+                    const float2 cur = sg[offA + hop * f];
                     acc[0][f] = ffma2(splat(hA), cur, acc[0][f]);
                     acc[1][f] = ffma2(splat(hB), prev, acc[1][f]);
                     prev = cur;
                 }
-            }
-        } else if (vA) {
+            } else {
 #pragma unroll
-            for (int f = 0; f < PB_F; ++f) {
-                acc[0][f] = ffma2(splat(hA), sg[hop * f - rA], acc[0][f]);
-                acc[1][f] = ffma2(splat(hB), sg[hop * f - rB], acc[1][f]);
+                for (int f = 0; f < PB_F; ++f) {
+                    acc[0][f] = ffma2(splat(hA), sg[offA + hop * f], acc[0][f]);
+                    acc[1][f] = ffma2(splat(hB), sg[offB + hop * f], acc[1][f]);
+                }
             }
         }
     }
@@ -602,10 +615,15 @@ int launch_polyphase_bank(tb200_handle h, const float2 *x, long n, int M, int N1
                 tw_err[dv] = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
             });
             if (tw_err[dv] != cudaSuccess) return fail(TB200_E_CUDA, "polyphase bank: twiddle upload: %s", cudaGetErrorString(tw_err[dv]));
-            cudaError_t e = cudaFuncSetAttribute(polybank800_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(polybank800): %s", cudaGetErrorString(e));
-            const unsigned blocks = (unsigned)((n_frames + PB_F - 1) / PB_F);
-            polybank800_kernel<<<blocks, PB_THREADS, smem, st>>>(x, n, P, l0, hop, n_frames, proto, tw + N1 + N2, out, out_stride);
+            auto go = [&](auto kern) -> int {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(polybank800): %s", cudaGetErrorString(e));
+                const unsigned blocks = (unsigned)((n_frames + PB_F - 1) / PB_F);
+                kern<<<blocks, PB_THREADS, smem, st>>>(x, n, P, l0, hop, n_frames, proto, tw + N1 + N2, out, out_stride);
+                return TB200_OK;
+            };
+            const int rc = hop == 83 ? go(polybank800_kernel<83>) : hop == 400 ? go(polybank800_kernel<400>) : go(polybank800_kernel<0>);
+            if (rc) return rc;
             TB_LAUNCH_CHECK(h);
             return TB200_OK;
         }
