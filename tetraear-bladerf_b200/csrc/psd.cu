@@ -215,6 +215,7 @@ __device__ __forceinline__ void dft16(float2 (&v)[16])
 }
 __device__ __forceinline__ int dft16_index(int p) { return (p >> 2) + 4 * (p & 3); }
 
+template <bool AVG>                                        // AVG = false: no accumulators (avg == 1)
 __global__ void __launch_bounds__(256, 3)
 psd4096_f32_kernel(const float2 *__restrict__ iq, long frame_stride, long n_frames, const double *__restrict__ window,
                    const double2 *__restrict__ tw, BandParams bp, float *__restrict__ power, double *__restrict__ stats, int avg)
@@ -246,12 +247,12 @@ psd4096_f32_kernel(const float2 *__restrict__ iq, long frame_stride, long n_fram
     const float invN = 1.0f / (float)N;
     const int lane = t & 31, wp = t >> 5;
     for (long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {      // OUTPUT frames (averages of `avg` input frames)
-        float acc[16];
+        float acc[AVG ? 16 : 1];
 #pragma unroll
-        for (int p = 0; p < 16; ++p) acc[p] = 0.f;
+        for (int p = 0; p < (AVG ? 16 : 1); ++p) acc[p] = 0.f;
         float2 v[16];
-        for (int ka = 0; ka < avg; ++ka) {
-        const float2 *in = iq + (frame * avg + ka) * frame_stride;
+        for (int ka = 0; ka < (AVG ? avg : 1); ++ka) {
+        const float2 *in = iq + (AVG ? frame * avg + ka : frame) * frame_stride;
         if (ka) __syncthreads();                               // buf is reused
 #pragma unroll
         for (int a = 0; a < 16; ++a) { const float2 x = in[256 * a + t]; v[a] = make_float2(x.x * win[a], x.y * win[a]); }
@@ -278,9 +279,9 @@ psd4096_f32_kernel(const float2 *__restrict__ iq, long frame_stride, long n_fram
 #pragma unroll
         for (int f = 0; f < 16; ++f) v[f] = buf[t * P4_PITCH + f];
         dft16(v);
-        if (avg > 1) {
+        if (AVG) {
 #pragma unroll
-            for (int p = 0; p < 16; ++p) { const float mg = mag2(v[p]) * invN; acc[p] = fmaf(mg, mg, acc[p]); }
+            for (int p = 0; p < 16; ++p) { const float mg = mag2(v[p]) * invN; acc[AVG ? p : 0] = fmaf(mg, mg, acc[AVG ? p : 0]); }
         }
         }   // averaged frames
         // dBFS, fftshift, band statistics
@@ -290,7 +291,7 @@ psd4096_f32_kernel(const float2 *__restrict__ iq, long frame_stride, long n_fram
         for (int p = 0; p < 16; ++p) {
             const int k = t + 256 * dft16_index(p);
             const int j = (k + N / 2) & (N - 1);
-            const double pdb = avg > 1 ? (double)db20(sqrtf(acc[p] / (float)avg)) : (double)db20(mag2(v[p]) * invN);
+            const double pdb = AVG ? (double)db20(sqrtf(acc[AVG ? p : 0] / (float)avg)) : (double)db20(mag2(v[p]) * invN);
             if (power) power[frame * N + j] = (float)pdb;
             if (j >= bp.start && j < bp.end) {
                 sig += pdb;
@@ -341,14 +342,15 @@ psd4096_f32_kernel(const float2 *__restrict__ iq, long frame_stride, long n_fram
 // Warm-up length = frames until (1-a)^W < 1e-9 (128 for a = 0.15); groups of 4 W frames read the input 1.25 times.
 // A smoothing factor so small that the warm-up would exceed 4096 frames runs as ONE group (exact, bins-parallel only).
 
+// One launch covers the output frames [f_begin, f_end) (a batch, see launch_psd); warm-up frames may lie before f_begin.
 __global__ void psd_ema_kernel(const float *__restrict__ power, long n_frames, int n_fft, double alpha, int first,
                                const double *__restrict__ state_in, double *__restrict__ state_out,
-                               float *__restrict__ smoothed, long EMA_G, long EMA_W)
+                               float *__restrict__ smoothed, long EMA_G, long EMA_W, long f_begin, long f_end)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_fft) return;
-    const long g0 = (long)blockIdx.y * EMA_G;
-    const long g1 = g0 + EMA_G < n_frames ? g0 + EMA_G : n_frames;
+    const long g0 = f_begin + (long)(gridDim.y - 1 - blockIdx.y) * EMA_G;      // last group first: see launch_psd
+    const long g1 = g0 + EMA_G < f_end ? g0 + EMA_G : f_end;
     long f = g0 - EMA_W;
     double S;
     if (f <= 0) {
@@ -394,17 +396,42 @@ int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_
     bp.n_lo = bp.start - 10 > 0 ? bp.start - 10 : 0;
     bp.n_hi0 = bp.end + 10 < n_fft ? bp.end + 10 : n_fft;
     bp.freq_step = 1.0 / ((double)n_fft * (1.0 / fs));
+    // EMA grouping (psd_ema_kernel): state_in and state_out may alias only when a single group runs; otherwise read a snapshot
+    double *state_in = ema_state;
+    long warm = 1, group = n_frames;
+    if (smoothed) {
+        if (alpha < 1.0 && alpha > 0.0) warm = (long)std::ceil(-20.72 / std::log1p(-alpha));     // (1-a)^warm < 1e-9
+        group = 4 * warm;
+        if (!(alpha > 0.0) || warm > 4096 || group >= n_frames) { group = n_frames; warm = 0; }
+        const long groups = (n_frames + group - 1) / group;
+        if (groups > 1 && !first) {
+            state_in = tables + n_fft + 2 * (n_fft / 2 + n_fft / 4 + 1);       // spare n_fft doubles behind the tables
+            TB_CUDA(cudaMemcpyAsync(state_in, ema_state, sizeof(double) * n_fft, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    // One batch: cutting the frame axis into L2-sized batches (FFT then smoothing per ~32 MB of spectra) was measured and
+    // lost — each launch then has too few CTAs (17 x 2 launches: 2.9 ms against 1.0 ms).  Instead the smoothing pass
+    // walks its groups from the LAST frame back, so that it starts on the spectra the FFT pass wrote most recently and
+    // that are still in the 126 MB L2.
+    const long batch = n_frames;
+    for (long f0 = 0; f0 < n_frames; f0 += batch) {
+    const long nb = f0 + batch < n_frames ? batch : n_frames - f0;
+    const float2 *iq_b = reinterpret_cast<const float2 *>(iq) + f0 * avg * frame_stride;
+    float *power_b = power + f0 * n_fft;
+    double *stats_b = stats ? stats + f0 * 8 : nullptr;
     if (use_f32 && n_fft == 4096) {
         const size_t sm4 = sizeof(float2) * (size_t)(P4_BUF + 4096 + 256);
         static std::atomic<bool> attr4_dev[64];  // per device
         std::atomic<bool> &attr4 = attr4_dev[h->cfg.device & 63];
         if (!attr4) {
-            cudaError_t e = cudaFuncSetAttribute(psd4096_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
+            cudaError_t e = cudaFuncSetAttribute(psd4096_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(psd4096_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
             if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(psd4096_f32_kernel): %s", cudaGetErrorString(e));
             attr4 = true;
         }
-        const long ctas = n_frames < 3 * 148 ? n_frames : 3 * 148;            // persistent: 3 CTAs per SM
-        psd4096_f32_kernel<<<(unsigned)ctas, 256, sm4, st>>>((const float2 *)iq, frame_stride, n_frames, window, tw, bp, power, stats, avg);
+        const long ctas = nb < 3 * 148 ? nb : 3 * 148;            // persistent: 3 CTAs per SM
+        if (avg > 1) psd4096_f32_kernel<true><<<(unsigned)ctas, 256, sm4, st>>>(iq_b, frame_stride, nb, window, tw, bp, power_b, stats_b, avg);
+        else psd4096_f32_kernel<false><<<(unsigned)ctas, 256, sm4, st>>>(iq_b, frame_stride, nb, window, tw, bp, power_b, stats_b, avg);
         TB_LAUNCH_CHECK(h);
     } else {
     size_t smem = (use_f32 ? sizeof(float2) : sizeof(double2)) * (size_t)n_fft;
@@ -415,29 +442,18 @@ int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_
     }
     int threads = n_fft >= 2048 ? 512 : (n_fft >= 512 ? 128 : 64);
     if (use_f32)
-        psd_kernel<float><<<(unsigned)n_frames, threads, smem, st>>>((const float2 *)iq, frame_stride, n_fft, log2n, window, tw, bp,
-                                                                    power, stats, avg);
+        psd_kernel<float><<<(unsigned)nb, threads, smem, st>>>(iq_b, frame_stride, n_fft, log2n, window, tw, bp, power_b, stats_b, avg);
     else
-        psd_kernel<double><<<(unsigned)n_frames, threads, smem, st>>>((const float2 *)iq, frame_stride, n_fft, log2n, window, tw, bp,
-                                                                     power, stats, avg);
+        psd_kernel<double><<<(unsigned)nb, threads, smem, st>>>(iq_b, frame_stride, n_fft, log2n, window, tw, bp, power_b, stats_b, avg);
     TB_LAUNCH_CHECK(h);
     }
     if (smoothed) {
-        // state_in and state_out may alias only when a single group runs; otherwise read a snapshot
-        double *state_in = ema_state;
-        long warm = 1;
-        if (alpha < 1.0 && alpha > 0.0) warm = (long)std::ceil(-20.72 / std::log1p(-alpha));     // (1-a)^warm < 1e-9
-        long group = 4 * warm;
-        if (!(alpha > 0.0) || warm > 4096 || group >= n_frames) { group = n_frames; warm = 0; }
-        long groups = (n_frames + group - 1) / group;
-        if (groups > 1 && !first) {
-            state_in = tables + n_fft + 2 * (n_fft / 2 + n_fft / 4 + 1);       // spare n_fft doubles behind the tables
-            TB_CUDA(cudaMemcpyAsync(state_in, ema_state, sizeof(double) * n_fft, cudaMemcpyDeviceToDevice, st));
-        }
-        dim3 grid((n_fft + 127) / 128, (unsigned)groups);
-        psd_ema_kernel<<<grid, 128, 0, st>>>(power, n_frames, n_fft, alpha, first, state_in, ema_state, smoothed, group, warm);
+        const long nb_groups = (nb + group - 1) / group;
+        dim3 grid((n_fft + 127) / 128, (unsigned)nb_groups);
+        psd_ema_kernel<<<grid, 128, 0, st>>>(power, n_frames, n_fft, alpha, first, state_in, ema_state, smoothed, group, warm, f0, f0 + nb);
         TB_LAUNCH_CHECK(h);
     }
+    }   // batches
     return TB200_OK;
 }
 
