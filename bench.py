@@ -858,7 +858,8 @@ def run_c5(args):
     dev = torch.device(f"cuda:{local_rank}")
     g = torch.Generator(device=dev); g.manual_seed(10 + rank)
     wide = 0.02 * torch.randn((n, 2), generator=g, device=dev, dtype=torch.float32)
-    rp = ArchiveReplay(M, n, device=local_rank, n_blocks=8)
+    n_blocks = int(os.environ.get("TB200_C5_BLOCKS", "2"))
+    rp = ArchiveReplay(M, n, device=local_rank, n_blocks=n_blocks)
     bits_s, _, init = etsi.make_etsi_stream(56, seed=3)
     inj = torch.from_numpy(etsi.modulate_dqpsk(bits_s, 50000.0).view(np.float32).reshape(-1, 2)).to(dev)
     L = min(inj.shape[0], rp.nf)
@@ -897,7 +898,7 @@ def run_c5(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "c5: multichannel archive replay, 20 MS/s -> 800 x 25 kHz etsi receive, looped 0.8 s "
-                                   "device-resident segment per rank, 8 concurrent time blocks, 16 carriers injected at the channelizer output",
+                                   f"device-resident segment per rank, {rp.n_blocks} concurrent time block(s) x time-parallel demodulator segments, 16 carriers injected at the channelizer output",
                        "parallelism": f"segment per GPU x{world}", "l2": "input 128 MB per step > 126 MB L2"},
             "crc_pass_blocks_per_s": round(ok_blocks * world / (ms / args.steps) * 1e3 / max(world, 1), 1),
             "realtime_factor": round(total / ms / 1e3 / 20.0, 1),

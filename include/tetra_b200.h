@@ -241,6 +241,17 @@ int tb200_channelize(tb200_handle h, const void *d_iq_c64, int64_t n_samples, in
 int tb200_etsi_demod_batch(tb200_handle h, const void *d_iq_c64, int n_streams, int64_t n_samples, int64_t stride,
                            double fs, void *d_sym_c64, float *d_soft, int64_t soft_stride, int32_t *d_n_soft,
                            void *stream);
+/* The same demodulator, time-parallel: every stream is cut into segments of >= 640 nominal symbols that run
+ * concurrently (each re-locks its timing loop over 160 warm-up symbols before its first output) and are joined symbol
+ * by symbol afterwards, so one long stream offers n_segments times the parallelism at 160/640 extra work.  Outputs as
+ * tb200_etsi_demod_batch; they agree with it wherever the loop is locked (same symbols, instants within the loop's
+ * jitter) and may differ in symbol count on a channel that carries only noise.  d_scratch: 16-byte aligned device
+ * memory of tb200_etsi_demod_scratch_bytes(...) bytes; with less (or a stream shorter than two segments) the call
+ * runs the sequential form. */
+int64_t tb200_etsi_demod_scratch_bytes(int n_streams, int64_t n_samples, double fs, int want_symbols);
+int tb200_etsi_demod_segmented(tb200_handle h, const void *d_iq_c64, int n_streams, int64_t n_samples, int64_t stride,
+                               double fs, void *d_sym_c64, float *d_soft, int64_t soft_stride, int32_t *d_n_soft,
+                               void *d_scratch, int64_t scratch_bytes, void *stream);
 /* normal-burst training-sequence search on the soft bits: d_metric [n_streams][soft_stride/2] scratch
  * (normalised correlation per symbol position, sign = which of the two normal sequences); for every
  * burst found the two 216-bit blocks BKN1 | BKN2 are quantised to int8 into d_blocks

@@ -129,3 +129,41 @@ def test_carrier_offset_correction():
     without = [sum(1 for b in res0[s] if b["crc_ok"].all()) for s in range(len(offs))]
     assert all(w <= a for w, a in zip(without, with_afc)), (without, with_afc)
     assert without[0] < with_afc[0] or without[4] < with_afc[4], (without, with_afc)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fs,sigma,rate_ppm", [(50000.0, 0.0, 0.0), (50000.0, 0.05, 0.0), (72000.0, 0.05, 60.0), (36000.0, 0.03, -40.0)])
+def test_segmented_demodulator_matches_the_sequential_loop(fs, sigma, rate_ppm):
+    """tb200_etsi_demod_segmented cuts every stream into concurrently running segments (warm-up, then symbol-exact
+    stitching): same number of symbols and the same decisions as the one sequential loop, also when the transmitter's
+    symbol clock is off (the segment boundaries are nominal instants, the loops track the real ones)."""
+    import __graft_entry__ as entry
+    entry.build()
+    n_bursts = 40                                                     # 10 200 symbols: 16 segments of 640
+    streams = []
+    for s in range(4):
+        bits, t1, init = etsi.make_etsi_stream(n_bursts, seed=90 + s)
+        streams.append(etsi.modulate_dqpsk(bits, fs, symbol_rate=18000.0 * (1 + rate_ppm * 1e-6), sigma=sigma, t_offset=0.13 * s + 0.2,
+                                           seed=s))
+    n = min(len(v) for v in streams)
+    x = np.stack([v[:n] for v in streams])
+    out = {}
+    for seg in (False, True):
+        rx = etsi.EtsiReceiver(fs, max_streams=4, max_samples=n, segmented=seg, afc=False)
+        res = rx.run(x, init)
+        out[seg] = (rx.n_soft.cpu().numpy().copy(), rx.soft.cpu().numpy().copy(), res)
+    assert rx._scratch is not None                                     # the segmented form did run
+    ns0, soft0, res0 = out[False]
+    ns1, soft1, res1 = out[True]
+    for s in range(4):
+        assert abs(int(ns0[s]) - int(ns1[s])) <= 2 * 2, (s, ns0[s], ns1[s])      # the last symbols may fall either side of the end
+        m = min(int(ns0[s]), int(ns1[s]))
+        assert m > 2 * 255 * (n_bursts - 1)
+        a, b = soft0[s, :m], soft1[s, :m]
+        # skip the first burst (both loops are still pulling in there, identically, but decisions on it are not the point)
+        agree = np.mean((a[510:] > 0) == (b[510:] > 0))
+        assert agree >= (1.0 if sigma == 0.0 else 0.9995), (s, agree)
+        assert np.max(np.abs(a[510:] - b[510:])) < (0.25 if sigma == 0.0 else 0.6)    # timing jitter of two loops, same decisions
+        good0 = sum(bool(v["crc_ok"].all()) for v in res0[s])
+        good1 = sum(bool(v["crc_ok"].all()) for v in res1[s])
+        assert good1 >= good0 - 1 and good1 >= n_bursts - 5, (s, good0, good1)

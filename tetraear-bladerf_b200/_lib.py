@@ -74,6 +74,8 @@ _PROTOS = {
     "tb200_crc16_rows": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "tb200_etsi_decode_batch": (_i, [_vp, _vp, _i64, _i, C.c_uint32, _vp, _vp, _vp, _vp]),
     "tb200_etsi_demod_batch": (_i, [_vp, _vp, _i, _i64, _i64, _d, _vp, _vp, _i64, _vp, _vp]),
+    "tb200_etsi_demod_scratch_bytes": (_i64, [_i, _i64, _d, _i]),
+    "tb200_etsi_demod_segmented": (_i, [_vp, _vp, _i, _i64, _i64, _d, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "tb200_etsi_find_bursts": (_i, [_vp, _vp, _i, _i64, _vp, _d, _vp, _vp, _vp, _vp, _i, _vp]),
     "tb200_etsi_afc": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp]),
     "tb200_etsi_find_sync_bursts": (_i, [_vp, _vp, _i, _i64, _vp, _d, _vp, _vp, _vp, _vp, _vp, _i, _vp]),

@@ -639,7 +639,25 @@ extern "C" int tb200_etsi_demod_batch(tb200_handle h, const void *d_iq_c64, int 
         return fail(TB200_E_ARG, "tb200_etsi_demod_batch: bad argument");
     StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
     return launch_etsi_demod(h, (const float2 *)d_iq_c64, n_streams, n_samples, stride, fs, h->etsi_taps, (float2 *)d_sym_c64,
-                             d_soft, soft_stride, d_n_soft, (cudaStream_t)stream);
+                             d_soft, soft_stride, d_n_soft, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int64_t tb200_etsi_demod_scratch_bytes(int n_streams, int64_t n_samples, double fs, int want_symbols)
+{
+    if (n_streams <= 0 || n_samples <= 0 || !(fs > 0.0)) return 0;
+    return etsi_demod_scratch_bytes(n_streams, n_samples, fs, want_symbols);
+}
+
+extern "C" int tb200_etsi_demod_segmented(tb200_handle h, const void *d_iq_c64, int n_streams, int64_t n_samples, int64_t stride,
+                                          double fs, void *d_sym_c64, float *d_soft, int64_t soft_stride, int32_t *d_n_soft,
+                                          void *d_scratch, int64_t scratch_bytes, void *stream)
+{
+    DevGuard dev_guard(h);
+    if (!h || n_streams < 0 || n_samples < 0 || !d_iq_c64 || !d_soft || !d_n_soft || soft_stride < 2 || scratch_bytes < 0)
+        return fail(TB200_E_ARG, "tb200_etsi_demod_segmented: bad argument");
+    StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
+    return launch_etsi_demod(h, (const float2 *)d_iq_c64, n_streams, n_samples, stride, fs, h->etsi_taps, (float2 *)d_sym_c64,
+                             d_soft, soft_stride, d_n_soft, d_scratch, (size_t)scratch_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int tb200_etsi_find_bursts(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,

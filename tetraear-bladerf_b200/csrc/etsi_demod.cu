@@ -8,7 +8,7 @@
 // regions and a hard-bit Hamming scan) — parity unpinned; validated end to end by
 // modulator -> demod -> TS search -> channel decoder round trips (tests/test_etsi_phy.py).
 //
-// Eight lanes per stream: the feedback state (timing phase, loop integrator, power estimate) is replicated in the
+// Eight lanes per stream (two in the time-parallel form): the feedback state (timing phase, loop integrator, power estimate) is replicated in the
 // group's registers; each lane owns 4 of the 32 taps of the interpolating matched filter (reduced with 3 shuffle
 // stages) for the on-time and the half-symbol sample of every symbol.
 #include <cmath>
@@ -25,98 +25,195 @@ constexpr int ED_PH = 32;
 // latency of that chain, not arithmetic: each lane owns 4 of the 32 taps (4 multiply-adds per output in registers,
 // then a 3-stage shuffle reduction instead of 5), the stream's samples sit in a shared-memory ring the group refills
 // 64 samples at a time well ahead of their use, and the tap table is read as one float4 per output.
-constexpr int ED_L = 8;                   // lanes per stream
-constexpr int ED_RING = 256;              // ring capacity per stream (samples)
-constexpr int ED_FILL = 64;               // refill granularity
+constexpr int ED_RING = 128;              // ring capacity per stream (samples): window 33 + two refills + a symbol
+constexpr int ED_FILL = 32;               // refill granularity
 
+// Time-parallel form (SEG = true).  The loop of a stream is sequential, but it forgets: after ~100 symbols its state
+// (timing phase, integrator, power estimate) no longer depends on where it started.  A stream is therefore cut at the
+// nominal symbol instants T_j = t_first + j * seg_syms * sps into segments that run concurrently, each in its own
+// 8-lane group: segment j > 0 starts ED_WARM symbols before T_j from the nominal state, keeps quiet until its timing
+// instant passes T_j, then writes its symbols (soft pair, instant) to a staging row, and runs 2 symbols past T_(j+1).
+// etsi_stitch_kernel joins the rows: segment j keeps the symbols that lie more than half a symbol before the first
+// symbol of segment j+1, so every symbol is taken exactly once even if two loops disagree about the instant by a
+// fraction of a symbol.  Work grows by ED_WARM / seg_syms; parallelism by the number of segments.
+constexpr int ED_WARM = 160;              // warm-up symbols of a segment (loop time constant ~15 symbols)
+constexpr int ED_SEG_MIN = 640;           // nominal symbols per segment (at least)
+constexpr int ED_SEG_MAX_N = 128;         // segments per stream (at most)
+constexpr int ED_SLACK = 16;              // staging slots beyond seg_syms
+
+struct EtsiSegMeta { int count; };
+
+// L lanes per group: the sequential form wants the shortest dependent chain per symbol (L = 8: 4 taps per lane, three
+// shuffle stages); the time-parallel form has groups to spare and wants the fewest instructions per symbol (L = 2: the
+// loop arithmetic, replicated in every lane of a group, is the larger part of the work at L = 8).
+template <bool SEG, int L>
 __global__ void __launch_bounds__(128)
 etsi_demod_kernel(const float2 *__restrict__ iq, int n_streams, long n, long stride, float sps, float kp,
                   float ki, const float *__restrict__ taps_g, float2 *__restrict__ sym_out,
-                  float *__restrict__ soft_out, long soft_stride, int32_t *__restrict__ n_soft)
+                  float *__restrict__ soft_out, long soft_stride, int32_t *__restrict__ n_soft,
+                  int n_seg, int seg_syms, float4 *__restrict__ stage, float2 *__restrict__ sym_stage, int32_t *__restrict__ seg_count)
 {
     __shared__ __align__(16) float taps[ED_PH * ED_TAPS];
-    __shared__ float2 ring[16][ED_RING];                       // 16 streams per CTA
+    constexpr int TPL = ED_TAPS / L, GPC = 128 / L;            // taps per lane, groups per CTA
+    extern __shared__ float2 ed_ring[];                        // [GPC][ED_RING]
     for (int i = threadIdx.x; i < ED_PH * ED_TAPS; i += blockDim.x) taps[i] = taps_g[i];
     __syncthreads();
-    const int q = threadIdx.x & (ED_L - 1);                    // tap quad of this lane: taps 4q .. 4q+3
-    const int grp = threadIdx.x >> 3;                          // stream slot in the CTA
-    const int s = blockIdx.x * 16 + grp;
+    const int q = threadIdx.x % L;                             // this lane owns taps TPL q .. TPL q + TPL - 1
+    const int grp = threadIdx.x / L;                           // group slot in the CTA
+    const int gid = blockIdx.x * GPC + grp;
+    const int s = SEG ? gid / n_seg : gid;
+    const int j = SEG ? gid - s * n_seg : 0;
     const bool live = s < n_streams;
     const float2 *x = iq + (long)(live ? s : 0) * stride;
-    float2 *rb = ring[grp];
-    float tau = 16.0f + sps;                                   // first symbol instant with a full filter window
-    float integ = 0.f, pavg = 0.f;
-    float2 prev = make_float2(0.f, 0.f);
-    int k = 0;
-    const int max_sym = (int)(soft_stride / 2);
-    const int ni = (int)n;                                     // n < 2^31 (launch check): 32-bit index arithmetic in the loop
+    float2 *rb = ed_ring + grp * ED_RING;
+    const float t_first = 16.0f + sps;                         // first symbol instant with a full filter window
+    const int ni = (int)n;                                     // n < 2^30 (launch check): 32-bit index arithmetic in the loop
     const float nf_end = (float)n - 17.0f;
     const float half = 0.5f * sps;
-    float2 *so = (sym_out && live) ? sym_out + (long)s * max_sym : nullptr;
+    float tau = t_first, emit_from = -1.0f, run_until = nf_end;
+    int slots = (int)(soft_stride / 2);
+    if (SEG) {
+        const float Tj = t_first + (float)j * (float)seg_syms * sps;
+        if (j > 0) { tau = Tj - (float)ED_WARM * sps; emit_from = Tj; }
+        if (j < n_seg - 1) run_until = fminf(nf_end, Tj + ((float)seg_syms + 2.0f) * sps);
+        slots = seg_syms + ED_SLACK;
+    }
+    float integ = 0.f, pavg = 0.f;
+    float2 prev = make_float2(0.f, 0.f);
+    int k = 0, it = 0;                                         // symbols written, loop iterations
+    float2 *so = nullptr;
     float *sb = soft_out + (long)(live ? s : 0) * soft_stride;
-    int filled = 0;                                            // ring holds samples [filled - ED_RING, filled)
-    bool active = live && (tau < nf_end) && (k < max_sym);
+    float4 *stg = nullptr;
+    if (SEG) {
+        const long row = ((long)(live ? s : 0) * n_seg + j) * slots;
+        stg = stage + row;
+        if (sym_stage && live) so = sym_stage + row;
+    } else if (sym_out && live) so = sym_out + (long)s * slots;
+    // the ring holds samples [filled - ED_RING, filled); a segment starts it just below its first filter window
+    int filled = 0;
+    if (SEG && j > 0) { const int lo = (int)floorf(tau - half) - 16; filled = lo > 0 ? (lo & ~(ED_FILL - 1)) : 0; }
+    float2 pre[ED_FILL / L];                                    // this lane's share of the next refill
+#pragma unroll
+    for (int jj = 0; jj < ED_FILL / L; ++jj) {
+        const int idx = filled + q * (ED_FILL / L) + jj;
+        pre[jj] = (live && idx < ni) ? x[idx] : make_float2(0.f, 0.f);
+    }
+    bool active = live && (tau < run_until) && (k < slots);
     while (__any_sync(0xffffffffu, active)) {
         const float tmid = tau - half;
         const float fl_on = floorf(tau), fl_mid = floorf(tmid);
         const int i_on = (int)fl_on, i_mid = (int)fl_mid;
-        // keep [i_mid - 15, i_on + 16] inside the ring: refill ahead, 64 samples at a time
+        // keep [i_mid - 15, i_on + 16] inside the ring: refill ahead, ED_FILL samples at a time.  The samples of the next
+        // refill are already in registers (loaded when the previous one was stored): no load latency in the loop.
 #pragma unroll 1
         while (active && filled < i_on + 17 + ED_FILL) {
-            const int g = filled + q * 8;
+            const int g = filled + q * (ED_FILL / L);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int idx = g + j;
-                rb[idx & (ED_RING - 1)] = (idx < ni) ? x[idx] : make_float2(0.f, 0.f);
-            }
+            for (int jj = 0; jj < ED_FILL / L; ++jj) rb[(g + jj) & (ED_RING - 1)] = pre[jj];
             filled += ED_FILL;
+#pragma unroll
+            for (int jj = 0; jj < ED_FILL / L; ++jj) {
+                const int idx = g + ED_FILL + jj;
+                pre[jj] = (idx < ni) ? x[idx] : make_float2(0.f, 0.f);
+            }
         }
         __syncwarp();
         int ph_on = (int)((tau - fl_on) * ED_PH), ph_mid = (int)((tmid - fl_mid) * ED_PH);
         ph_on = min(max(ph_on, 0), ED_PH - 1);
         ph_mid = min(max(ph_mid, 0), ED_PH - 1);
-        const float4 g_on = *reinterpret_cast<const float4 *>(&taps[ph_on * ED_TAPS + 4 * q]);
-        const float4 g_mid = *reinterpret_cast<const float4 *>(&taps[ph_mid * ED_TAPS + 4 * q]);
-        const int b_on = i_on - 15 + 4 * q, b_mid = i_mid - 15 + 4 * q;
+        const int b_on = i_on - 15 + TPL * q, b_mid = i_mid - 15 + TPL * q;
         float2 on = make_float2(0.f, 0.f), mid = make_float2(0.f, 0.f);
-        {
+#pragma unroll
+        for (int t4 = 0; t4 < TPL / 4; ++t4) {
+            const float4 g_on = *reinterpret_cast<const float4 *>(&taps[ph_on * ED_TAPS + TPL * q + 4 * t4]);
+            const float4 g_mid = *reinterpret_cast<const float4 *>(&taps[ph_mid * ED_TAPS + TPL * q + 4 * t4]);
             const float gw[4] = {g_on.x, g_on.y, g_on.z, g_on.w}, hw[4] = {g_mid.x, g_mid.y, g_mid.z, g_mid.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int a = b_on + j, c = b_mid + j;
-                const float2 va = (a >= 0) ? rb[a & (ED_RING - 1)] : make_float2(0.f, 0.f);
-                const float2 vc = (c >= 0) ? rb[c & (ED_RING - 1)] : make_float2(0.f, 0.f);
-                on.x = fmaf(va.x, gw[j], on.x); on.y = fmaf(va.y, gw[j], on.y);
-                mid.x = fmaf(vc.x, hw[j], mid.x); mid.y = fmaf(vc.y, hw[j], mid.y);
+            for (int jj = 0; jj < 4; ++jj) {
+                const int a = b_on + 4 * t4 + jj, c = b_mid + 4 * t4 + jj;
+                // a, c >= the ring's first sample: tau only moves forward from t_first (a >= 2) or from the segment start
+                const float2 va = rb[a & (ED_RING - 1)];
+                const float2 vc = rb[c & (ED_RING - 1)];
+                on.x = fmaf(va.x, gw[jj], on.x); on.y = fmaf(va.y, gw[jj], on.y);
+                mid.x = fmaf(vc.x, hw[jj], mid.x); mid.y = fmaf(vc.y, hw[jj], mid.y);
             }
         }
 #pragma unroll
-        for (int o = 1; o < ED_L; o <<= 1) {
+        for (int o = 1; o < L; o <<= 1) {
             on.x += __shfl_xor_sync(0xffffffffu, on.x, o); on.y += __shfl_xor_sync(0xffffffffu, on.y, o);
             mid.x += __shfl_xor_sync(0xffffffffu, mid.x, o); mid.y += __shfl_xor_sync(0xffffffffu, mid.y, o);
         }
         if (active) {
             const float p = on.x * on.x + on.y * on.y;
-            pavg = (k == 0) ? p : 0.98f * pavg + 0.02f * p;
-            const float inv = __frcp_rn(pavg + 1e-20f);
+            pavg = (it == 0) ? p : 0.98f * pavg + 0.02f * p;
+            const float inv = __fdividef(1.0f, pavg + 1e-20f);
             // Gardner: e = Re{(y[k] - y[k-1]) conj(y[k-1/2])}; e > 0 <=> sampling late
             float e = ((on.x - prev.x) * mid.x + (on.y - prev.y) * mid.y) * inv;
             e = fminf(fmaxf(e, -1.0f), 1.0f);
             // differential detection: d = y[k] conj(y[k-1]); b1 = [Im d < 0], b2 = [Re d < 0]; soft = -(.)/P
             const float dre = on.x * prev.x + on.y * prev.y, dim = on.y * prev.x - on.x * prev.y;
-            if (q == 0) {
-                if (so) so[k] = on;
-                if (k > 0) *reinterpret_cast<float2 *>(sb + 2 * (k - 1)) = make_float2(-dim * inv, -dre * inv);
+            if (!SEG || tau >= emit_from) {
+                if (q == 0) {
+                    if (so) so[k] = on;
+                    if (SEG) stg[k] = make_float4(-dim * inv, -dre * inv, tau, 0.f);
+                    else if (k > 0) *reinterpret_cast<float2 *>(sb + 2 * (k - 1)) = make_float2(-dim * inv, -dre * inv);
+                }
+                ++k;
             }
             prev = on;
-            if (k > 0) { integ += ki * e; tau += sps - kp * e - integ; }
+            if (it > 0) { integ += ki * e; tau += sps - kp * e - integ; }
             else tau += sps;
-            ++k;
-            active = (tau < nf_end) && (k < max_sym);
+            ++it;
+            active = (tau < run_until) && (k < slots);
         }
         __syncwarp();                                           // ring reads of this symbol precede the next refill
     }
-    if (live && q == 0) n_soft[s] = (int32_t)(k > 0 ? 2 * (k - 1) : 0);
+    if (live && q == 0) {
+        if (SEG) seg_count[(long)s * n_seg + j] = k;
+        else n_soft[s] = (int32_t)(k > 0 ? 2 * (k - 1) : 0);
+    }
+}
+
+// One CTA per stream: which symbols of every segment are kept, where they go, then the copy into the stream's
+// contiguous soft bits (pair k-1 belongs to symbol k >= 1, as in the sequential form) and symbols.
+__global__ void __launch_bounds__(128)
+etsi_stitch_kernel(int n_seg, int seg_syms, float sps, const float4 *__restrict__ stage, const float2 *__restrict__ sym_stage,
+                   const int32_t *__restrict__ seg_count, float2 *__restrict__ sym_out, float *__restrict__ soft_out,
+                   long soft_stride, int32_t *__restrict__ n_soft)
+{
+    __shared__ int keep[ED_SEG_MAX_N], base[ED_SEG_MAX_N + 1];
+    const int s = blockIdx.x, slots = seg_syms + ED_SLACK, max_sym = (int)(soft_stride / 2);
+    const float4 *st = stage + (long)s * n_seg * slots;
+    for (int j = threadIdx.x; j < n_seg; j += blockDim.x) {
+        int c = seg_count[(long)s * n_seg + j];
+        // the next segment that produced anything decides where this one ends
+        float thresh = 3.0e38f;
+        for (int jn = j + 1; jn < n_seg; ++jn)
+            if (seg_count[(long)s * n_seg + jn] > 0) { thresh = st[(long)jn * slots].z - 0.5f * sps; break; }
+        while (c > 0 && st[(long)j * slots + c - 1].z >= thresh) --c;
+        keep[j] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int j = 0; j < n_seg; ++j) { base[j] = acc; acc += keep[j]; }
+        base[n_seg] = acc;
+        const int total = acc < max_sym ? acc : max_sym;
+        n_soft[s] = total > 0 ? 2 * (total - 1) : 0;
+    }
+    __syncthreads();
+    float *sb = soft_out + (long)s * soft_stride;
+    float2 *so = sym_out ? sym_out + (long)s * max_sym : nullptr;
+    for (int j = 0; j < n_seg; ++j) {
+        const int b = base[j], c = keep[j];
+        for (int e = threadIdx.x; e < c; e += blockDim.x) {
+            const int k = b + e;
+            if (k >= max_sym) break;
+            const float4 v = st[(long)j * slots + e];
+            if (k > 0) *reinterpret_cast<float2 *>(sb + 2 * (k - 1)) = make_float2(v.x, v.y);
+            if (so) so[k] = sym_stage[((long)s * n_seg + j) * slots + e];
+        }
+    }
 }
 
 // training sequences (EN 300 392-2 cl. 9.4.4.3): normal n, p, and the extended/tail q
@@ -307,8 +404,28 @@ void make_mf_taps(double sps, float *taps)
     }
 }
 
+// segments per stream and symbols per segment the time-parallel form uses for n samples (n_seg < 2: sequential form)
+static void etsi_seg_plan(long n, double sps, int *n_seg, int *seg_syms)
+{
+    const long n_sym = (long)(((double)n - 33.0) / sps);
+    long seg = ED_SEG_MIN;
+    if (n_sym > seg * ED_SEG_MAX_N) seg = (n_sym + ED_SEG_MAX_N - 1) / ED_SEG_MAX_N;
+    long ns = n_sym > 0 ? (n_sym + seg - 1) / seg : 0;
+    *n_seg = (int)ns;
+    *seg_syms = (int)seg;
+}
+
+int64_t etsi_demod_scratch_bytes(int n_streams, long n, double fs, int want_symbols)
+{
+    int n_seg, seg_syms;
+    etsi_seg_plan(n, fs / 18000.0, &n_seg, &seg_syms);
+    if (n_seg < 2) return 0;
+    const size_t rows = (size_t)n_streams * n_seg;
+    return (int64_t)(rows * (seg_syms + ED_SLACK) * (sizeof(float4) + (want_symbols ? sizeof(float2) : 0)) + rows * sizeof(int32_t) + 256);
+}
+
 int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, long stride, double fs, float *taps_dev,
-                      float2 *sym, float *soft, long soft_stride, int32_t *n_soft, cudaStream_t st)
+                      float2 *sym, float *soft, long soft_stride, int32_t *n_soft, void *scratch, size_t scratch_bytes, cudaStream_t st)
 {
     if (n_streams <= 0) return TB200_OK;
     double sps = fs / 18000.0;
@@ -321,10 +438,32 @@ int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, l
         TB_CUDA(cudaStreamSynchronize(st));      // `taps` is a stack buffer
         h->etsi_taps_fs = fs;
     }
-    int threads = 128, blocks = (n_streams + 15) / 16;              // 8 lanes per stream, 16 streams per CTA
     const double loop = h->etsi_open_loop ? 0.0 : 1.0;
-    etsi_demod_kernel<<<blocks, threads, 0, st>>>(iq, n_streams, n, stride, (float)sps, (float)(loop * 0.05 * sps), (float)(loop * 0.0005 * sps),
-                                                  taps_dev, sym, soft, soft_stride, n_soft);
+    const float kp = (float)(loop * 0.05 * sps), ki = (float)(loop * 0.0005 * sps);
+    int n_seg = 0, seg_syms = 0;
+    etsi_seg_plan(n, sps, &n_seg, &seg_syms);
+    const int64_t need = etsi_demod_scratch_bytes(n_streams, n, fs, sym != nullptr);
+    if (scratch && n_seg >= 2 && need > 0 && (size_t)need <= scratch_bytes && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0) {
+        // time-parallel: n_streams * n_seg groups of LS lanes
+        const size_t rows = (size_t)n_streams * n_seg, slots = (size_t)seg_syms + ED_SLACK;
+        float4 *stage = reinterpret_cast<float4 *>(scratch);
+        float2 *sym_stage = sym ? reinterpret_cast<float2 *>(stage + rows * slots) : nullptr;
+        int32_t *seg_count = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(scratch) + rows * slots * (sizeof(float4) + (sym ? sizeof(float2) : 0)));
+        const long groups = (long)rows;
+        constexpr int LS = 8, GPC = 128 / LS;
+        constexpr int ring_bytes = GPC * ED_RING * (int)sizeof(float2);
+        cudaError_t e = cudaFuncSetAttribute(etsi_demod_kernel<true, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes);
+        if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(etsi_demod): %s", cudaGetErrorString(e));
+        etsi_demod_kernel<true, LS><<<(unsigned)((groups + GPC - 1) / GPC), 128, ring_bytes, st>>>(iq, n_streams, n, stride, (float)sps, kp, ki, taps_dev, sym, soft,
+                                                                            soft_stride, n_soft, n_seg, seg_syms, stage, sym_stage, seg_count);
+        TB_LAUNCH_CHECK(h);
+        etsi_stitch_kernel<<<n_streams, 128, 0, st>>>(n_seg, seg_syms, (float)sps, stage, sym_stage, seg_count, sym, soft, soft_stride, n_soft);
+        TB_LAUNCH_CHECK(h);
+        return TB200_OK;
+    }
+    int threads = 128, blocks = (n_streams + 15) / 16;              // 8 lanes per stream, 16 streams per CTA
+    etsi_demod_kernel<false, 8><<<blocks, threads, 16 * ED_RING * sizeof(float2), st>>>(iq, n_streams, n, stride, (float)sps, kp, ki, taps_dev, sym, soft, soft_stride, n_soft,
+                                                         1, 0, nullptr, nullptr, nullptr);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
 }

@@ -36,7 +36,8 @@ int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_
 int launch_etsi_decode(tb200_handle h, const int8_t *soft, long n, int channel, uint32_t scramb_init, uint8_t *bits,
                        uint8_t *crc_ok, int32_t *metric, cudaStream_t st);
 int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, long stride, double fs, float *taps_dev,
-                      float2 *sym, float *soft, long soft_stride, int32_t *n_soft, cudaStream_t st);
+                      float2 *sym, float *soft, long soft_stride, int32_t *n_soft, void *scratch, size_t scratch_bytes, cudaStream_t st);
+int64_t etsi_demod_scratch_bytes(int n_streams, long n, double fs, int want_symbols);
 int launch_etsi_find_bursts(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft,
                             float thr, float *metric, int8_t *blocks, int32_t *burst_pos, int32_t *n_bursts, int max_bursts,
                             cudaStream_t st);

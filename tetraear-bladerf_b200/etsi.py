@@ -260,7 +260,7 @@ class EtsiReceiver:
     training-sequence search + block extraction (tb200_etsi_find_bursts) ->
     descramble / de-interleave / Viterbi / CRC of both SCH/HD blocks (tb200_etsi_decode_batch)."""
 
-    def __init__(self, fs, max_streams, max_samples, device=0, max_bursts_per_stream=None, afc=True):
+    def __init__(self, fs, max_streams, max_samples, device=0, max_bursts_per_stream=None, afc=True, segmented=True):
         import torch
         from . import _dev
         self.fs = float(fs)
@@ -282,6 +282,10 @@ class EtsiReceiver:
         self.crc_ok = _dev.zeros((S * self.max_bursts * 2,), torch.uint8, device)
         self.path_metric = _dev.zeros((S * self.max_bursts * 2,), torch.int32, device)
         self.symbols = None
+        # time-parallel demodulator (tb200_etsi_demod_segmented): streams of two segments (1280 symbols) or more are cut
+        # into concurrently running segments; shorter ones, or segmented=False, run the sequential loop
+        self.segmented = bool(segmented)
+        self._scratch = None
         self.afc = bool(afc)                      # feed-forward carrier-offset correction (tb200_etsi_afc), |df| < 2250 Hz
         self.theta = _dev.zeros((S,), torch.float32, device)
         self.max_sync = self.max_bursts
@@ -291,6 +295,24 @@ class EtsiReceiver:
         self.sync_bits = _dev.zeros((S * self.max_sync, 40), torch.uint8, device)
         self.sync_crc = _dev.zeros((S * self.max_sync,), torch.uint8, device)
         self.sync_metric = _dev.zeros((S * self.max_sync,), torch.int32, device)
+
+    def _demod(self, iq_ptr, n_streams, n_samples, stride, sym_ptr, st):
+        """Matched filter + timing loop + soft bits of every stream (segmented when that pays, see __init__)."""
+        import torch
+        from . import _dev
+        h, lib = self._h, self._h.lib
+        need = 0
+        if self.segmented:
+            need = int(lib.tb200_etsi_demod_scratch_bytes(int(n_streams), int(n_samples), self.fs, 1 if sym_ptr else 0))
+        if need <= 0:
+            _lib.check(lib.tb200_etsi_demod_batch(h.h, int(iq_ptr), int(n_streams), int(n_samples), int(stride), self.fs, sym_ptr,
+                                                  self.soft.data_ptr(), self.soft_stride, self.n_soft.data_ptr(), st))
+            return
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = _dev.empty((need,), torch.uint8, self.device)
+        _lib.check(lib.tb200_etsi_demod_segmented(h.h, int(iq_ptr), int(n_streams), int(n_samples), int(stride), self.fs, sym_ptr,
+                                                  self.soft.data_ptr(), self.soft_stride, self.n_soft.data_ptr(),
+                                                  self._scratch.data_ptr(), int(self._scratch.numel()), st))
 
     def acquire_device(self, n_streams, threshold=0.8):
         """After a demodulation (run_device*): search the soft bits of every stream for synchronisation bursts (38-bit
@@ -314,9 +336,7 @@ class EtsiReceiver:
             x = x[None, :]
         d = _dev.to_dev(x.view(np.float32).reshape(x.shape[0], x.shape[1], 2), self.device)
         h, lib = self._h, self._h.lib
-        _lib.check(lib.tb200_etsi_demod_batch(h.h, d.data_ptr(), x.shape[0], x.shape[1], x.shape[1], self.fs, None,
-                                              self.soft.data_ptr(), self.soft_stride, self.n_soft.data_ptr(),
-                                              _dev.stream_ptr(self.device)))
+        self._demod(d.data_ptr(), x.shape[0], x.shape[1], x.shape[1], None, _dev.stream_ptr(self.device))
         if self.afc:
             _lib.check(lib.tb200_etsi_afc(h.h, self.soft.data_ptr(), x.shape[0], self.soft_stride, self.n_soft.data_ptr(),
                                           self.theta.data_ptr(), _dev.stream_ptr(self.device)))
@@ -358,9 +378,7 @@ class EtsiReceiver:
         if keep_symbols and self.symbols is None:
             self.symbols = _dev.zeros((self.max_streams, self.max_sym, 2), torch.float32, self.device)
         self.metric.zero_()
-        _lib.check(lib.tb200_etsi_demod_batch(h.h, int(iq_ptr), n_streams, int(n_samples), int(stride), self.fs,
-                                              self.symbols.data_ptr() if keep_symbols else None, self.soft.data_ptr(),
-                                              self.soft_stride, self.n_soft.data_ptr(), st))
+        self._demod(iq_ptr, n_streams, n_samples, stride, self.symbols.data_ptr() if keep_symbols else None, st)
         if self.afc:
             _lib.check(lib.tb200_etsi_afc(h.h, self.soft.data_ptr(), n_streams, self.soft_stride, self.n_soft.data_ptr(),
                                           self.theta.data_ptr(), st))
