@@ -56,9 +56,14 @@ etsi_demod_kernel(const float2 *__restrict__ iq, int n_streams, long n, long str
     __shared__ __align__(16) float taps[ED_PH * ED_TAPS];
     constexpr int TPL = ED_TAPS / L, GPC = 128 / L;            // taps per lane, groups per CTA
     extern __shared__ float2 ed_ring[];                        // [GPC][ED_RING]
-    for (int i = threadIdx.x; i < ED_PH * ED_TAPS; i += blockDim.x) taps[i] = taps_g[i];
+    // lane q owns taps q, q + L, q + 2L, ...: the lanes of a group read consecutive samples (one 64-byte run per tap
+    // index instead of 32-byte strides); the table is stored lane-major so that a lane's taps are one float4 run
+    for (int i = threadIdx.x; i < ED_PH * ED_TAPS; i += blockDim.x) {
+        const int ph = i / ED_TAPS, t = i % ED_TAPS;
+        taps[ph * ED_TAPS + (t % L) * TPL + t / L] = taps_g[i];
+    }
     __syncthreads();
-    const int q = threadIdx.x % L;                             // this lane owns taps TPL q .. TPL q + TPL - 1
+    const int q = threadIdx.x % L;
     const int grp = threadIdx.x / L;                           // group slot in the CTA
     const int gid = blockIdx.x * GPC + grp;
     const int s = SEG ? gid / n_seg : gid;
@@ -121,7 +126,7 @@ etsi_demod_kernel(const float2 *__restrict__ iq, int n_streams, long n, long str
         int ph_on = (int)((tau - fl_on) * ED_PH), ph_mid = (int)((tmid - fl_mid) * ED_PH);
         ph_on = min(max(ph_on, 0), ED_PH - 1);
         ph_mid = min(max(ph_mid, 0), ED_PH - 1);
-        const int b_on = i_on - 15 + TPL * q, b_mid = i_mid - 15 + TPL * q;
+        const int b_on = i_on - 15 + q, b_mid = i_mid - 15 + q;
         float2 on = make_float2(0.f, 0.f), mid = make_float2(0.f, 0.f);
 #pragma unroll
         for (int t4 = 0; t4 < TPL / 4; ++t4) {
@@ -130,7 +135,7 @@ etsi_demod_kernel(const float2 *__restrict__ iq, int n_streams, long n, long str
             const float gw[4] = {g_on.x, g_on.y, g_on.z, g_on.w}, hw[4] = {g_mid.x, g_mid.y, g_mid.z, g_mid.w};
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-                const int a = b_on + 4 * t4 + jj, c = b_mid + 4 * t4 + jj;
+                const int a = b_on + L * (4 * t4 + jj), c = b_mid + L * (4 * t4 + jj);
                 // a, c >= the ring's first sample: tau only moves forward from t_first (a >= 2) or from the segment start
                 const float2 va = rb[a & (ED_RING - 1)];
                 const float2 vc = rb[c & (ED_RING - 1)];
@@ -256,11 +261,17 @@ __global__ void etsi_find_bursts_kernel(const float *__restrict__ soft, long sof
     int found = 0;
     long i = 0;
     while (i < npos && found < max_bursts) {
-        long p = i + lane;
-        float v = (p < npos) ? fabsf(m[p]) : 0.f;
-        unsigned ball = __ballot_sync(0xffffffffu, v >= thr);
-        if (!ball) { i += 32; continue; }
-        long first = i + (__ffs(ball) - 1);
+        // 256 positions per step (about one burst period): eight independent loads in flight instead of one
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const long p = i + lane + 32 * u; v[u] = (p < npos) ? fabsf(m[p]) : 0.f; }
+        long first = -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const unsigned ball = __ballot_sync(0xffffffffu, v[u] >= thr);
+            if (ball && first < 0) first = i + 32 * u + (__ffs(ball) - 1);
+        }
+        if (first < 0) { i += 256; continue; }
         // local maximum over first .. first+3
         long best = first;
         float bv = fabsf(m[first]);
@@ -319,11 +330,16 @@ __global__ void etsi_find_sync_kernel(const float *__restrict__ soft, long soft_
     int found = 0;
     long i = 0;
     while (i < npos && found < max_bursts) {
-        long p = i + lane;
-        float v = (p < npos) ? m[p] : 0.f;
-        unsigned ball = __ballot_sync(0xffffffffu, v >= thr);
-        if (!ball) { i += 32; continue; }
-        long first = i + (__ffs(ball) - 1);
+        float v[8];                                   // 256 positions per step, as in etsi_find_bursts_kernel
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const long p = i + lane + 32 * u; v[u] = (p < npos) ? m[p] : 0.f; }
+        long first = -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const unsigned ball = __ballot_sync(0xffffffffu, v[u] >= thr);
+            if (ball && first < 0) first = i + 32 * u + (__ffs(ball) - 1);
+        }
+        if (first < 0) { i += 256; continue; }
         long best = first;
         float bv = m[first];
         for (int d = 1; d < 4; ++d) if (first + d < npos && m[first + d] > bv) { bv = m[first + d]; best = first + d; }
