@@ -57,7 +57,7 @@ for tc in (0, 1, 2):
             names = {0: "loader: wait raw free", 1: "relayout: wait raw full", 2: "relayout: wait A free", 3: "relayout: work", 4: "mma: wait A full / D free",
                      5: "mma: issue", 7: "scan team 0: wait D full", 8: "scan: tmem ld", 9: "scan: KS + publish", 10: "scan: wait neighbours",
                      11: "scan: carries + stores"}
-            print("   tc4 stages, cycles per group of CTA 0 (scan team 0 sees every 3rd group):", {n: round(t[i] / g) for i, n in names.items()}, "groups", t[15] // 5)
+            print("   tc4 stages, cycles per group of CTA 0 (scan team 0 sees every TC4_NS-th group):", {n: round(t[i] / g) for i, n in names.items()}, "groups", t[15] // 5)
     h.profile(True)
     for _ in range(20):
         run()

@@ -435,8 +435,12 @@ decim_tc_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_c
 // Every wait is bounded: a stage that waits too long raises the CTA's abort flag and all stages drain and exit, so a
 // protocol error costs a wrong result (caught by the parity tests), never a hung GPU.
 constexpr int TC4_NS = 3;                       // scan teams
+constexpr int TC4_NR = 1;                       // re-layout teams (2: team t owns operand buffer t; needs an even TC4_RAW so that a raw
+                                                // stage is always read by the same team.  Measured: no faster)
 constexpr int TC4_RAW = 3;                      // raw ring stages
-constexpr int TC4_WARPS = 6 + 4 * TC4_NS;
+constexpr int TC4_SCAN0 = 2 + 4 * TC4_NR;       // first scan warp
+constexpr int TC4_WARPS = TC4_SCAN0 + 4 * TC4_NS;
+static_assert(TC4_NR == 1 || (TC4_NR == 2 && TC4_RAW % 2 == 0), "two re-layout teams need an even raw ring");
 constexpr int TC4_DCOLS = 144;                  // three 48-column accumulators per D buffer
 constexpr int TC4_ACOL0 = 2 * TC4_DCOLS;        // lo operand buffers behind the two D buffers (64 columns each)
 
@@ -466,7 +470,7 @@ __device__ __forceinline__ void named_sync(int id, int threads)
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int Q>
+template <int Q, bool TIMED>
 __global__ void __launch_bounds__(TC4_WARPS * 32, 1)
 decim_tc4_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_chunks, long n_dec, int gpc, long total_floats,
                  TcParams P, const float *__restrict__ bmat, float2 *__restrict__ dec_out, int *__restrict__ err_out,
@@ -509,12 +513,12 @@ decim_tc4_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_
     tc_fence_after();
     const uint32_t tmem0 = tmem_base_s;
     // profiling aid (tb200_debug_tc_timing): per-stage cycles of CTA 0 — one thread per role accumulates where it waits / works
-    const bool timed = timing != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6);
+    const bool timed = TIMED && timing != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == TC4_SCAN0);
     long long tprev = timed ? clock64() : 0;
-    long long tacc[12];                               // kept in registers (constant indices), written once at the end
+    long long tacc[TIMED ? 12 : 1];                   // kept in registers (constant indices), written once at the end
 #pragma unroll
-    for (int i = 0; i < 12; ++i) tacc[i] = 0;
-    auto tick = [&](int c) { if (timed) { const long long t = clock64(); tacc[c] += t - tprev; tprev = t; } };
+    for (int i = 0; i < (TIMED ? 12 : 1); ++i) tacc[i] = 0;
+    auto tick = [&](int c) { if (TIMED && timed) { const long long t = clock64(); tacc[TIMED ? c : 0] += t - tprev; tprev = t; } };
 
     constexpr long RAW_FLOATS = 127L * G::SLOT_FLOATS + G::K;
     auto group_f0 = [&](int g) -> long {
@@ -569,12 +573,14 @@ decim_tc4_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_
             }
         }
         __syncwarp();
-    } else if (warp < 6) {
-        // ================================================= re-layout team: 128 threads, slot m = 32 * (warp & 3) + lane
+    } else if (warp < TC4_SCAN0) {
+        // ================================================= re-layout teams: 128 threads each, slot m = 32 * (warp & 3) + lane;
+        // team t takes the groups of parity t, i.e. always operand buffer t and the raw stages of parity t
+        const int rteam = (warp - 2) >> 2;
         const int m = 32 * (warp & 3) + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         bool ok = true;
-        for (int g = gs; g < ge && ok; ++g) {
+        for (int g = gs + rteam; g < ge && ok; g += TC4_NR) {
             const int it = g - gs, st = it % TC4_RAW, b = it & 1;
             const int chunk = g / gpc, gi = g - chunk * gpc;
             const float2 *xc = x + (long)chunk * chunk_stride;
@@ -606,8 +612,8 @@ decim_tc4_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_
                     v[kc] = make_float4(e0.x, e0.y, e1.x, e1.y);
                 }
             }
-            named_sync(1, 128);                                   // all slots are in registers: the raw stage is free
-            if (threadIdx.x == 64) mbar_arrive(&raw_empty[st]);
+            named_sync(1 + rteam, 128);                           // all slots are in registers: the raw stage is free
+            if ((warp & 3) == 0 && lane == 0) mbar_arrive(&raw_empty[st]);
             tick(3);
             ok = mbar_wait_bounded(&a_empty[b], ((it >> 1) & 1) ^ 1, abort_flag);      // the MMAs of group g-2 are done with buffer b
             if (!ok) break;
@@ -635,14 +641,13 @@ decim_tc4_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_
             tmem_st_wait();
             fence_async_smem();
             tc_fence_before();
-            named_sync(1, 128);
-            if (threadIdx.x == 64) mbar_arrive(&a_full[b]);
+            named_sync(1 + rteam, 128);
+            if ((warp & 3) == 0 && lane == 0) mbar_arrive(&a_full[b]);
             tick(3);
         }
     } else {
         // ================================================= scan teams
-        const int team = (warp - 6) >> 2, w = warp & 3, tid = threadIdx.x - (6 + 4 * team) * 32;
-        (void)tid;
+        const int team = (warp - TC4_SCAN0) >> 2, w = warp & 3;
         const uint32_t lane_base = (uint32_t)(w * 32) << 16;
         const float2 zero2 = make_float2(0.f, 0.f);
         bool ok = true;
@@ -678,7 +683,7 @@ decim_tc4_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_
                 for (int i = 0; i < 8; ++i) vb[i] = __float_as_uint(__uint_as_float(vb[i]) + __uint_as_float(t2[i]));
             }
             tc_fence_before();
-            named_sync(2 + team, 128);
+            named_sync(1 + TC4_NR + team, 128);
             if (w == 0 && lane == 0) mbar_arrive(&d_empty[b]);     // the MMA issuer may overwrite this D buffer
             tick(8);
             float2 y[TC_R];
@@ -710,7 +715,7 @@ decim_tc4_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_
                 if (lane == 0) tF[mm].re = tF[mm].im = zero2;
                 if (lane == 31) tB[mm].re = tB[mm].im = zero2;
             }
-            named_sync(2 + team, 128);                             // this team's carries are in shared memory
+            named_sync(1 + TC4_NR + team, 128);                             // this team's carries are in shared memory
             if (w == 0 && lane == 0) mbar_arrive(&pub_bar[slot]);  // ... and published to the other teams
             tick(9);
             // ---- carries across passes
@@ -745,12 +750,12 @@ decim_tc4_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int n_
                     if (k >= 0 && k < n_dec) out[k] = y[r];
                 }
             }
-            named_sync(2 + team, 128);                             // carryF_s / carryB_s of this team are free again
+            named_sync(1 + TC4_NR + team, 128);                             // carryF_s / carryB_s of this team are free again
         }
     }
-    if (timed) {
+    if (TIMED && timed) {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) if (tacc[i]) timing[i] += tacc[i];
+        for (int i = 0; i < (TIMED ? 12 : 1); ++i) if (tacc[i]) timing[i] += tacc[i];
         if (warp == 0) timing[15] += ge - gs;
     }
     __syncthreads();
@@ -962,15 +967,20 @@ static int launch_tc_q(tb200_handle h, const void *x, int n_chunks, long n, long
         const size_t smem4 = 2 * (size_t)G::B_BYTES + 2 * (size_t)G::A_BYTES + (size_t)TC4_RAW * RAW_BYTES + 128;
         static std::atomic<bool> attr4_set[64];
         if (!attr4_set[dv]) {
-            cudaError_t e = cudaFuncSetAttribute(decim_tc4_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+            cudaError_t e = cudaFuncSetAttribute(decim_tc4_kernel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(decim_tc4_kernel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
             if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(decim_tc4): %s", cudaGetErrorString(e));
             attr4_set[dv] = true;
         }
         long grid4 = n_sm[dv];
         if (grid4 > NG) grid4 = NG;
         int *err = reinterpret_cast<int *>((char *)h->tc_bmat + h->tc_bmat_bytes - 16);      // counter slot 14 of the timing block
-        decim_tc4_kernel<Q><<<(unsigned)grid4, TC4_WARPS * 32, smem4, st>>>((const float2 *)x, n, chunk_stride, n_chunks, n_dec, gpc,
-                                                                          total_floats, P, bmat, (float2 *)dec_out, err, h->tc_timing);
+        if (h->tc_timing)
+            decim_tc4_kernel<Q, true><<<(unsigned)grid4, TC4_WARPS * 32, smem4, st>>>((const float2 *)x, n, chunk_stride, n_chunks, n_dec, gpc,
+                                                                                    total_floats, P, bmat, (float2 *)dec_out, err, h->tc_timing);
+        else
+            decim_tc4_kernel<Q, false><<<(unsigned)grid4, TC4_WARPS * 32, smem4, st>>>((const float2 *)x, n, chunk_stride, n_chunks, n_dec, gpc,
+                                                                                     total_floats, P, bmat, (float2 *)dec_out, err, nullptr);
         TB_LAUNCH_CHECK(h);
     } else {
     long grid = 2L * n_sm[dv];                      // two resident CTAs per SM (two teams each), one range of groups per team
