@@ -2,7 +2,7 @@
 """bench.py — IQ Msamples/s (and CRC-pass bursts/s) of the IQ->bursts receive path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c3|c2]
-                    [--mode exact|fast|fast32]
+                    [--mode exact|fast|fast32|fast-tc|fast32-tc|fast-tc4|fast32-tc4]
 
 Workload c1 (default, BASELINE.json configs[0]): one synthetic TETRA-like downlink carrier, 10 s of
 complex64 IQ at 2.4 MS/s = 183 whole chunks of 131072 samples (the ragged 0.1-chunk tail is
@@ -485,7 +485,7 @@ def run_b200(args):
                "ms_per_step": round(ms_alt, 4),
                "path_frac": round((samples_per_step * 8.0 + n_chunks * pipe.plan.max_symbols) / (ms_alt / 1e3) / 1e9 / measured_peaks()[0], 5),
                "note": "fast32 = channel filter recurrences in float32 (3e-6 from scipy's filtfilt) instead of float64 (1e-11); same "
-                       "tensor-core float32 decimator; dibits / frames / CRC identical on all 183 chunks (tests/test_gpu_fullsize.py)"}
+                       "float32 time-parallel decimator; dibits / frames / CRC identical on all 183 chunks (tests/test_gpu_fullsize.py)"}
         del pa, pb
         torch.cuda.empty_cache()
 
@@ -1141,7 +1141,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("TB200_BENCH_LANES", "2")),
                     help="sub-batches processed on concurrent streams (overlaps the latency-bound tail kernels)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("TB200_BENCH_MODE", "fast"), choices=["exact", "fast", "fast32", "fast-tc", "fast32-tc"])
+    ap.add_argument("--mode", default=os.environ.get("TB200_BENCH_MODE", "fast"), choices=["exact", "fast", "fast32", "fast-tc", "fast32-tc", "fast-tc4", "fast32-tc4"])
     ap.add_argument("--workload", default="c1", choices=["c1", "c4", "c5"],
                     help="c1 = headline; c4 = wideband 800-channel chunk in reference mode; c5 = multichannel archive replay (etsi mode)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -97,7 +97,7 @@ static size_t carve(tb200_handle h, char *base)
     size_t MC = (size_t)cfg.max_channels;
     h->chan_proto = c.take<float>(MC * 6 * sizeof(float));
     h->chan_tw = c.take<float>((MC + 256) * 2 * sizeof(float));
-    h->rc_tab_bytes = MC ? MC * 32 * sizeof(float) + (MC + 512) * 2 * sizeof(float) + (MC * 16 + 64) * sizeof(double) + MC * sizeof(double) : 0;
+    h->rc_tab_bytes = MC ? MC * 32 * sizeof(float) + (MC + 512) * 2 * sizeof(float) + (MC * 16 + 64) * sizeof(double) + MC * sizeof(double) + 16 * MC * 2 * sizeof(double) : 0;
     h->rc_tab = MC ? c.take<char>(h->rc_tab_bytes) : nullptr;
     // staging for *_host
     h->stage_in_bytes = C * L * 8;

@@ -29,11 +29,13 @@ namespace tb200 {
 constexpr int RC_PMAX = 32;          // prototype taps per polyphase branch (upper bound)
 constexpr int RC_EDGE = 27;          // scipy sosfiltfilt edge (3 * ntaps) of the order-8 decimator
 constexpr int RC_NFIX = 160;         // outputs that receive the right-edge transient
+constexpr int RC_LT = 192;           // table of lambda^j in the edge kernel (>= RC_NFIX and the ~L/q + 2 edge outputs)
 
 struct RefChanEdge {
     double p[4][2], lam[4][2];       // poles (upper half plane), lambda = p^q
     double g_tail[4][2];             // 2 alpha_i / (1 - p_i): tail sum  Gt(D) = Re sum_i g_tail_i p_i^(D+1)
     double ka[4][2], kM[4][4][2], kMc[4][4][2], pc[4][2];    // right-edge transient (dsp_fast.cu make_fast_params)
+    double gL[4][2], gR[4][2];       // g_tail_i p_i^(RC_EDGE + 1)  and  g_tail_i p_i^(n + RC_EDGE - q (n_dec - 1)): tail sums at output 0 / n_dec - 1
     int L;                           // truncation length of g (multiple of M)
 };
 
@@ -350,14 +352,86 @@ __device__ __forceinline__ cdd2 shifted(const float2 *__restrict__ x, long m, do
     return cdd2{xr * c - xi * s, xr * s + xi * c};
 }
 
-// One CTA per channel: the terms of scipy's padded, zero-phase filtering that lie outside the chunk.
+// ---- G_P[k] = sum over the chunk's last K samples of P^(n + 26 - t) x[t] e^{-j 2 pi k t / M}, for the 8 poles P (the four
+// upper-half-plane poles of the decimator and their conjugates) and all M channels at once.  It is what the right-edge
+// transient of the backward pass needs per channel (F_i[M-1] of the frequency-shifted, padded chunk = the 27 extension
+// samples + this sum) and, taken channel by channel as the reference's arithmetic would, it was 70 % of the edge kernel:
+// M x K complex multiply-adds with a sincos each.  For all channels together it is again a fold and a DFT:
+//     v_P[r] = sum_{t = r mod M} P^(n + 26 - t) x[t],   G_P[k] = sum_r v_P[r] e^{-j 2 pi k r / M}      (8 M-point DFTs).
+// Two small kernels, float64 throughout: the fold (thread = (pole, r), up to K / M independent loads) and the DFTs
+// (8 lanes per output bin, 100 terms each, shuffle tree).
 __global__ void __launch_bounds__(128)
+refchan_fold_kernel(const float2 *__restrict__ x, long n, int M, int K, RefChanEdge E, cdd2 *__restrict__ V)
+{
+    const int pole = blockIdx.x, i = pole & 3;
+    const int r = blockIdx.y * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    const cdd2 P = cdd2{E.p[i][0], pole < 4 ? E.p[i][1] : -E.p[i][1]};
+    const cdd2 PM = zpow(P, M);
+    const long t_lo = n + 26 - (long)(K - 1) > 0 ? n + 26 - (long)(K - 1) : 0;
+    long t = (n - 1) - ((n - 1 - r) % M);                      // largest t <= n - 1 with t = r (mod M)
+    if (r > n - 1) t = -1;                                      // chunk shorter than M: no such sample
+    cdd2 pw = zpow(P, n + 26 - t), acc = cdd2{0.0, 0.0};
+    while (t >= t_lo) {
+        float2 s[4];                                            // four loads in flight per round
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const long tu = t - (long)u * M; s[u] = tu >= t_lo ? x[tu] : make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const cdd2 term = zmul(pw, cdd2{(double)s[u].x, (double)s[u].y});
+            acc.x += term.x; acc.y += term.y;
+            pw = zmul(pw, PM);
+        }
+        t -= 4L * M;
+    }
+    V[(long)pole * M + r] = acc;
+}
+
+__global__ void __launch_bounds__(128)
+refchan_gdft_kernel(int M, const cdd2 *__restrict__ V, cdd2 *__restrict__ G)
+{
+    extern __shared__ cdd2 ts_smem[];
+    cdd2 *v = ts_smem;                 // [M]
+    cdd2 *w = v + M;                   // [M] exp(-j 2 pi i / M)
+    const int pole = blockIdx.x;
+    for (int r = threadIdx.x; r < M; r += blockDim.x) {
+        v[r] = V[(long)pole * M + r];
+        double sn, cs;
+        sincospi(-2.0 * (double)r / (double)M, &sn, &cs);
+        w[r] = cdd2{cs, sn};
+    }
+    __syncthreads();
+    const int j = threadIdx.x & 7;                             // lane of the bin's group: terms r = j, j + 8, ...
+    const int k = blockIdx.y * 16 + (threadIdx.x >> 3);
+    cdd2 acc = cdd2{0.0, 0.0};
+    if (k < M) {
+        int e = (int)(((long)k * j) % M);                      // (k r) mod M
+        const int de = (int)(((long)k * 8) % M);
+        for (int r = j; r < M; r += 8) {
+            const cdd2 a = v[r], b = w[e];
+            acc.x = fma(a.x, b.x, fma(-a.y, b.y, acc.x));
+            acc.y = fma(a.x, b.y, fma(a.y, b.x, acc.y));
+            e += de; if (e >= M) e -= M;
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    }
+    if (k < M && j == 0) G[(long)pole * M + k] = acc;
+}
+
+// One CTA per channel: the terms of scipy's padded, zero-phase filtering that lie outside the chunk.
+__global__ void __launch_bounds__(128, 4)
 refchan_edge_kernel(const float2 *__restrict__ x, long n, int q, double fs, const double *__restrict__ freq, long n_dec,
-                    const double *__restrict__ gfull, RefChanEdge E, float2 *__restrict__ out, long out_stride)
+                    const double *__restrict__ gfull, RefChanEdge E, const cdd2 *__restrict__ Gsum, int n_ch,
+                    float2 *__restrict__ out, long out_stride)
 {
     __shared__ cdd2 extL[RC_EDGE + 1], extR[RC_EDGE + 1];      // ext[t], t = -1..-27 (index 1..27) / t = n..n+26 (index 0..26)
-    __shared__ cdd2 part[128][4][2];                            // per-thread partial one-pole sums [mode][I/Q]
+    __shared__ cdd2 part[4][2];                                 // F_i[M-1] [mode][I/Q]
     __shared__ cdd2 kappa[4][2];
+    __shared__ cdd2 lamp[4][RC_LT];
     const int ch = blockIdx.x, tid = threadIdx.x;
     const double f = freq[ch];
     const double W = __dmul_rn(-6.283185307179586, f);
@@ -370,70 +444,52 @@ refchan_edge_kernel(const float2 *__restrict__ x, long n, int q, double fs, cons
         const cdd2 e1 = shifted(x, n - 1, W, fs), v = shifted(x, n - 2 - tid, W, fs);
         extR[tid] = cdd2{2.0 * e1.x - v.x, 2.0 * e1.y - v.y};
     }
-    // ---- F_i[M-1] = sum_k p_i^k ext[M-1-k] over the last E.L samples of the padded, shifted signal (M-1 <-> t = n + 26)
+    // ---- F_i[M-1] = sum_k p_i^k ext[M-1-k] (M-1 <-> t = n + 26): the 27 extension samples here, the chunk's own samples
+    // from refchan_gdft_kernel: with A = G_{p_i}[ch], B = conj(G_{conj p_i}[ch]) the I part is (A + B) / 2, the Q part (A - B) / 2j
     __syncthreads();
-    {
-        const int per = (E.L + 127) / 128;
-        cdd2 S[4][2];
-        for (int i = 0; i < 4; ++i) S[i][0] = S[i][1] = cdd2{0.0, 0.0};
-        // thread tid covers k = tid*per .. tid*per+per-1, walked from the far end so that S = sum p^(k - k0) ext[..].
-        // The NCO of this run of consecutive samples is one sincos and a rotation per step (the transient it feeds is
-        // ~1e-3 of the output and needs 1e-4 of that; `per` rotations lose ~1e-14).
-        cdd2 cur, rot;
-        {
-            const long t_first = n + 26 - ((long)tid * per + per - 1);
-            double sn, cs;
-            sincos(__dmul_rn(W, (double)t_first / fs), &sn, &cs);
-            cur = cdd2{cs, sn};
-            sincos(W / fs, &sn, &cs);
-            rot = cdd2{cs, sn};
+    if (tid < 8) {
+        const int i = tid >> 1, c = tid & 1;
+        const cdd2 p = cdd2{E.p[i][0], E.p[i][1]};
+        cdd2 Fv = cdd2{0.0, 0.0};
+        for (int k = RC_EDGE - 1; k >= 0; --k) {                 // Horner over ext[n + 26 - k], k = 26 .. 0
+            Fv = zmul(p, Fv);
+            Fv.x += c ? extR[RC_EDGE - 1 - k].y : extR[RC_EDGE - 1 - k].x;        // ext[n + 26 - k]
         }
-        for (int u = per - 1; u >= 0; --u) {
-            const long k = (long)tid * per + u;
-            const long t = n + 26 - k;
-            cdd2 e;
-            if (t >= n) e = extR[t - n];
-            else if (t >= 0) e = zmul(cdd2{(double)x[t].x, (double)x[t].y}, cur);
-            else e = cdd2{0.0, 0.0};
-            cur = zmul(cur, rot);
-            for (int i = 0; i < 4; ++i) {
-                const cdd2 p = cdd2{E.p[i][0], E.p[i][1]};
-                cdd2 a = zmul(p, S[i][0]); a.x += e.x; S[i][0] = a;       // I component (real signal, complex state)
-                cdd2 b = zmul(p, S[i][1]); b.x += e.y; S[i][1] = b;       // Q component
-            }
-        }
-        for (int i = 0; i < 4; ++i) { part[tid][i][0] = S[i][0]; part[tid][i][1] = S[i][1]; }
-        __syncthreads();
-        if (tid < 8) {                                           // (mode, component) pairs: Horner over the 128 partials
-            const int i = tid >> 1, c = tid & 1;
-            const cdd2 pp = zpow(cdd2{E.p[i][0], E.p[i][1]}, per);
-            cdd2 Fv = cdd2{0.0, 0.0};
-            for (int t = 127; t >= 0; --t) { Fv = zmul(pp, Fv); Fv.x += part[t][i][c].x; Fv.y += part[t][i][c].y; }
-            part[0][i][c] = Fv;
-        }
-        __syncthreads();
-        if (tid < 8) {
-            const int i = tid >> 1, c = tid & 1;
-            const double xl = c ? extR[RC_EDGE - 1].y : extR[RC_EDGE - 1].x;
-            cdd2 k = cdd2{E.ka[i][0] * xl, E.ka[i][1] * xl};
-            for (int j = 0; j < 4; ++j) {
-                const cdd2 Fj = part[0][j][c];
-                const cdd2 t1 = zmul(cdd2{E.kM[i][j][0], E.kM[i][j][1]}, Fj);
-                const cdd2 t2 = zmul(cdd2{E.kMc[i][j][0], E.kMc[i][j][1]}, cdd2{Fj.x, -Fj.y});
-                k.x += t1.x + t2.x; k.y += t1.y + t2.y;
-            }
-            kappa[i][c] = k;
-        }
-        __syncthreads();
+        const cdd2 A = Gsum[(long)i * n_ch + ch], Bc = Gsum[(long)(i + 4) * n_ch + ch];
+        const cdd2 B = cdd2{Bc.x, -Bc.y};
+        if (c == 0) { Fv.x += 0.5 * (A.x + B.x); Fv.y += 0.5 * (A.y + B.y); }
+        else        { Fv.x += 0.5 * (A.y - B.y); Fv.y -= 0.5 * (A.x - B.x); }
+        part[i][c] = Fv;
     }
-    // tail sum of g beyond distance D: Gt(D) = sum_{d > D} g[d] = Re sum_i g_tail_i p_i^(D+1)
-    auto g_tail = [&](long D) -> double {
-        double s = 0.0;
-        for (int i = 0; i < 4; ++i) {
-            const cdd2 pw = zpow(cdd2{E.p[i][0], E.p[i][1]}, D + 1);
-            s += E.g_tail[i][0] * pw.x - E.g_tail[i][1] * pw.y;
+    __syncthreads();
+    if (tid < 8) {
+        const int i = tid >> 1, c = tid & 1;
+        const double xl = c ? extR[RC_EDGE - 1].y : extR[RC_EDGE - 1].x;
+        cdd2 k = cdd2{E.ka[i][0] * xl, E.ka[i][1] * xl};
+        for (int j = 0; j < 4; ++j) {
+            const cdd2 Fj = part[j][c];
+            const cdd2 t1 = zmul(cdd2{E.kM[i][j][0], E.kM[i][j][1]}, Fj);
+            const cdd2 t2 = zmul(cdd2{E.kMc[i][j][0], E.kMc[i][j][1]}, cdd2{Fj.x, -Fj.y});
+            k.x += t1.x + t2.x; k.y += t1.y + t2.y;
         }
-        return s;
+        kappa[i][c] = k;
+    }
+    __syncthreads();
+    // lambda_i^j, j < RC_LT: every power the two ends need is a host constant times one of these — the tail sum of g
+    // beyond distance D, Gt(D) = sum_{d > D} g[d] = Re sum_i g_tail_i p_i^(D+1), has D + 1 = RC_EDGE + 1 + q j at the left end
+    // and n + RC_EDGE - q (n_dec - 1) + q jj at the right end; the transient decays as lambda^jj
+    for (int e = tid; e < 4 * RC_LT; e += blockDim.x) {
+        const int i = e / RC_LT, j = e - i * RC_LT;
+        lamp[i][j] = zpow(cdd2{E.lam[i][0], E.lam[i][1]}, j);
+    }
+    __syncthreads();
+    auto g_tail = [&](const double (*g0)[2], long j) -> double {
+        double sacc = 0.0;
+        for (int i = 0; i < 4; ++i) {
+            const cdd2 pw = j < RC_LT ? lamp[i][j] : zpow(cdd2{E.lam[i][0], E.lam[i][1]}, j);
+            sacc += (g0[i][0] * pw.x - g0[i][1] * pw.y);
+        }
+        return sacc;
     };
     const long n_edge = (long)E.L / q + 2;
     // ---- left end: sum_{t<0} g[n_j - t] ext[t]  (27 extension samples + the constant continuation ext[-27])
@@ -444,7 +500,7 @@ refchan_edge_kernel(const float2 *__restrict__ x, long n, int q, double fs, cons
             const long d = nj + u;
             if (d < E.L) { const double g = gfull[d]; ax += g * extL[u].x; ay += g * extL[u].y; }
         }
-        const double gt = g_tail(nj + RC_EDGE);
+        const double gt = g_tail(E.gL, j);
         ax += gt * extL[RC_EDGE].x; ay += gt * extL[RC_EDGE].y;
         float2 v = o[j];
         v.x += (float)ax; v.y += (float)ay;
@@ -460,12 +516,12 @@ refchan_edge_kernel(const float2 *__restrict__ x, long n, int q, double fs, cons
             const long d = n + u - nj;
             if (d < E.L) { const double g = gfull[d]; ax += g * extR[u].x; ay += g * extR[u].y; }
         }
-        const double gt = g_tail(n + RC_EDGE - 1 - nj);
+        const double gt = g_tail(E.gR, jj);
         ax += gt * extR[RC_EDGE - 1].x; ay += gt * extR[RC_EDGE - 1].y;
         if (jj < RC_NFIX) {
             // y[k] -= 2 Re sum_i kappa_i pc_i lambda_i^(n_dec-1-k), I and Q separately (real filter, complex state)
             for (int i = 0; i < 4; ++i) {
-                const cdd2 gl = zmul(cdd2{E.pc[i][0], E.pc[i][1]}, zpow(cdd2{E.lam[i][0], E.lam[i][1]}, jj));
+                const cdd2 gl = zmul(cdd2{E.pc[i][0], E.pc[i][1]}, lamp[i][jj]);
                 ax -= 2.0 * (gl.x * kappa[i][0].x - gl.y * kappa[i][0].y);
                 ay -= 2.0 * (gl.x * kappa[i][1].x - gl.y * kappa[i][1].y);
             }
@@ -525,6 +581,9 @@ static int refchan_design(const DecimDesign &d, int q, long n, long n_dec, int M
         putz(E.p[j], p8[j]);
         putz(E.lam[j], std::pow(p8[j], q));
         putz(E.g_tail[j], 2.0 * alpha[j] / (1.0 - p8[j]));
+        const cd gt = 2.0 * alpha[j] / (1.0 - p8[j]);
+        putz(E.gL[j], gt * std::pow(p8[j], (double)(RC_EDGE + 1)));
+        putz(E.gR[j], gt * std::pow(p8[j], (double)(n + RC_EDGE - (long)q * (n_dec - 1))));
     }
     // right-edge transient constants (same algebra as make_fast_params, kept in double)
     cd H1(dd, 0.0);
@@ -545,6 +604,7 @@ static int refchan_design(const DecimDesign &d, int q, long n, long n_dec, int M
 }
 
 // workspace layout of h->rc_tab: [proto: RC_PMAX * M floats][twiddles: (M + 512) float2][g: RC_PMAX * M / 2 + 64 doubles][freq: M doubles]
+// [G: 8 * M complex128][V: 8 * M complex128] (refchan_fold_kernel / refchan_gdft_kernel)
 int launch_refchan(tb200_handle h, const float2 *x, long n, int M, int q, double fs, const DecimDesign &d, float2 *out,
                    long out_stride, cudaStream_t st)
 {
@@ -587,7 +647,21 @@ int launch_refchan(tb200_handle h, const float2 *x, long n, int M, int q, double
     }
     rc = launch_polyphase_bank(h, x, n, M, N1, N2, P, -P / 2, q, n_dec, proto, tw, out, out_stride, st);
     if (rc) return rc;
-    refchan_edge_kernel<<<M, 128, 0, st>>>(x, n, q, fs, fdev, n_dec, gdev, E, out, out_stride);
+    cdd2 *Gsum = reinterpret_cast<cdd2 *>(fdev + h->cfg.max_channels);
+    {
+        const int K = 128 * ((E.L + 127) / 128);                       // samples of the padded signal the transient looks back on
+        cdd2 *Vfold = Gsum + 8 * (size_t)h->cfg.max_channels;
+        refchan_fold_kernel<<<dim3(8, (M + 127) / 128), 128, 0, st>>>(x, n, M, K, E, Vfold);
+        TB_LAUNCH_CHECK(h);
+        const size_t smem = 2 * (size_t)M * sizeof(cdd2);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(refchan_gdft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(refchan_gdft): %s", cudaGetErrorString(e));
+        }
+        refchan_gdft_kernel<<<dim3(8, (M + 15) / 16), 128, smem, st>>>(M, Vfold, Gsum);
+        TB_LAUNCH_CHECK(h);
+    }
+    refchan_edge_kernel<<<M, 128, 0, st>>>(x, n, q, fs, fdev, n_dec, gdev, E, Gsum, M, out, out_stride);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
 }
