@@ -261,17 +261,17 @@ __global__ void etsi_find_bursts_kernel(const float *__restrict__ soft, long sof
     int found = 0;
     long i = 0;
     while (i < npos && found < max_bursts) {
-        // 256 positions per step (about one burst period): eight independent loads in flight instead of one
-        float v[8];
+        // 512 positions per step (two burst periods): sixteen independent loads in flight instead of one
+        float v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const long p = i + lane + 32 * u; v[u] = (p < npos) ? fabsf(m[p]) : 0.f; }
+        for (int u = 0; u < 16; ++u) { const long p = i + lane + 32 * u; v[u] = (p < npos) ? fabsf(m[p]) : 0.f; }
         long first = -1;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 16; ++u) {
             const unsigned ball = __ballot_sync(0xffffffffu, v[u] >= thr);
             if (ball && first < 0) first = i + 32 * u + (__ffs(ball) - 1);
         }
-        if (first < 0) { i += 256; continue; }
+        if (first < 0) { i += 512; continue; }
         // local maximum over first .. first+3
         long best = first;
         float bv = fabsf(m[first]);
