@@ -33,7 +33,8 @@ if ROOT not in sys.path:
 CHUNK = 131072
 FS = 2.4e6
 C1_CHUNKS = 183          # floor(24e6 / 131072)
-DECIM_TRAFFIC_BYTES = None   # filled from the ncu capture of the round's decimator kernel (profiles/)
+DECIM_TRAFFIC_BYTES = 207979008   # dram__bytes_read.sum + dram__bytes_write.sum of decim_fast_kernel<10>, one 183-chunk launch,
+                                   # ncu --set full (profiles/r02_ncu_c1.md: 191.96 MB + 16.02 MB); the -tc modes report null
 
 
 def host_cores():
@@ -618,8 +619,8 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "kernel": "decimator stage (cheby1 zero-phase IIR + ::q)", "achieved": round(achieved, 2),
                      "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
                      # dram__bytes_read.sum + dram__bytes_write.sum of the decimator kernel, one launch, ncu --set full
-                     # (profiles/r02_ncu_decim_tc.md); valid for the fast modes on this workload only
-                     "traffic": DECIM_TRAFFIC_BYTES if args.mode.startswith("fast") else None,
+                     # (profiles/r02_ncu_c1.md); valid for the FFMA2 decimator of the fast modes on this workload only
+                     "traffic": DECIM_TRAFFIC_BYTES if args.mode in ("fast", "fast32") else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "ms_per_launch": round(dec_launch_ms, 4),
                      "path_achieved_gbs": round(path_bytes / (step_ms / 1e3) / 1e9, 2),
