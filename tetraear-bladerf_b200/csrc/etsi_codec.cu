@@ -61,6 +61,14 @@ etsi_decode_kernel(const int8_t *__restrict__ soft, long n, EtsiParams P, uint8_
     const int tid = threadIdx.x;
     const long blk0 = (long)blockIdx.x * THREADS;
     const int nb = (int)((n - blk0 < THREADS) ? (n - blk0) : THREADS);
+    // the de-interleaver table and the scrambling words live in the kernel's parameter block: indexed per lane they are
+    // 32 serialised constant-bank reads per warp instruction (52 % of this kernel's stall samples in round 1's form),
+    // so a CTA copies them to shared memory once
+    __shared__ uint16_t inv_s[K3];
+    __shared__ uint32_t scr_s[14];
+    for (int i = tid; i < K3; i += THREADS) inv_s[i] = P.inv[i];
+    if (tid < 14) scr_s[tid] = P.scr[tid];
+    __syncthreads();
     // ---- coalesced load of nb * K3 contiguous bytes; descramble (sign flip where p(k) = 1) and de-interleave
     {
         const int8_t *src = soft + blk0 * K3;
@@ -69,8 +77,8 @@ etsi_decode_kernel(const int8_t *__restrict__ soft, long n, EtsiParams P, uint8_
         constexpr int DR = THREADS / K3, DK = THREADS - DR * K3;
         for (int idx = tid; idx < tot; idx += THREADS) {
             const int v = src[idx];
-            const int pk = (P.scr[k >> 5] >> (k & 31)) & 1;
-            T[(int)P.inv[k] * PITCH + r] = (int8_t)(pk ? -v : v);
+            const int pk = (scr_s[k >> 5] >> (k & 31)) & 1;
+            T[(int)inv_s[k] * PITCH + r] = (int8_t)(pk ? -v : v);
             r += DR; k += DK;
             if (k >= K3) { k -= K3; ++r; }
         }
