@@ -255,7 +255,7 @@ __device__ void warp_parse_burst(unsigned w, const uint16_t *__restrict__ tab, c
     unsigned win = (burst_field(w, 255, 11) << 11) | burst_field(w, 266, 11);
     int mc = 22 - __popc(win ^ SYNC_CONT_W), md = 22 - __popc(win ^ SYNC_DISC_W);
     int mx = max(mc, md);
-    bool is_sync = ((double)mx / 22.0) > 0.8;
+    bool is_sync = mx >= 18;                          // max(match) / 22 > 0.8 (protocol.py:252): 18/22 = 0.818, 17/22 = 0.773
     // per-lane view of the data bits: normal = [0,108) ++ [122,230), sync = all 510
     int ones = 0;
     unsigned cf = 0, cr = 0;           // forward / reversed-payload CRC contributions
@@ -397,11 +397,11 @@ __device__ __forceinline__ unsigned load_burst_word_fast(const uint8_t *__restri
     }
     if (lane == 31) v &= 0x00FFFFFFFFFFFFFFull;                            // dibit 255 does not exist
     v &= 0x0303030303030303ull;
-    // byte k (dibit k) -> bits 15-2k..14-2k
-    unsigned w = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) w |= (unsigned)((v >> (8 * k)) & 3ull) << (14 - 2 * k);
-    return w;
+    // byte k (dibit k) -> bits 15-2k..14-2k: reverse the bytes (dibit 0 on top), then gather the eight 2-bit fields of
+    // each 32-bit half by folding (|, >> 6) and (|, >> 12)
+    const unsigned hi = __byte_perm((unsigned)v, 0, 0x0123), lo = __byte_perm((unsigned)(v >> 32), 0, 0x0123);
+    auto gather4 = [](unsigned z) -> unsigned { const unsigned t = (z | (z >> 6)) & 0x000F000Fu; return (t | (t >> 12)) & 0xFFu; };
+    return (gather4(hi) << 8) | gather4(lo);
 }
 
 // Leaner burst parse for the batch kernel: nibble CRC tables, hardware warp reductions, direct shuffles.
@@ -415,7 +415,7 @@ __device__ __forceinline__ void warp_parse_burst_v2(unsigned w, const uint32_t (
     unsigned w15 = __shfl_sync(FULL, w, 15), w16 = __shfl_sync(FULL, w, 16), w17 = __shfl_sync(FULL, w, 17);
     unsigned win = ((w15 & 1u) << 21) | (w16 << 5) | (w17 >> 11);
     int mx = max(22 - __popc(win ^ SYNC_CONT_W), 22 - __popc(win ^ SYNC_DISC_W));
-    const bool is_sync = ((double)mx / 22.0) > 0.8;
+    const bool is_sync = mx >= 18;                    // max(match) / 22 > 0.8 (protocol.py:252): 18/22 = 0.818, 17/22 = 0.773
     const int type = is_sync ? 1 : 0;
     const int n_data = is_sync ? 510 : 216, n_pay = n_data - 16;
     // data-bit mask of this lane's 16 burst bits (normal: [0,108) ++ [122,230); sync: [0,510))
