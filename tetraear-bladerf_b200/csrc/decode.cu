@@ -514,6 +514,160 @@ burst_batch_kernel(const uint8_t *__restrict__ dibits, long n, uint8_t *__restri
     }
 }
 
+// ------------------------------------------------------------------ burst batch, one THREAD per burst
+// The warp-per-burst form above spends ~85 % of its instructions on scalars every lane recomputes (type, CRC compare,
+// header fields, record assembly) and on the shuffles / reductions that hand them round.  Here a CTA takes 128 bursts:
+//   phase 1 (cooperative): the 128 x 255 bytes are read in 8-byte pieces (two aligned 64-bit loads + funnel shift, as
+//     above) and packed 2 bits per dibit into shared memory, 16 words per burst, [word][burst] with pitch 129;
+//   phase 2: thread t owns burst t — its 510 bits in 16 registers, everything else is plain per-thread code: the
+//     22-bit sync window, the data-bit popcount, both CRCs from the position-dependent nibble table (re-laid
+//     [type][position][value] so that the 32 lanes of a warp, same position / different value, hit different banks),
+//     header fields, the 32-byte record as two 16-byte stores (a warp writes 1 KB contiguous).
+// Bit-identical to the warp form (tests/test_gpu_parity.py, test_gpu_fuzz.py, the 1M-burst test).
+constexpr int BT_THREADS = 128;
+constexpr int BT_PITCH = BT_THREADS + 1;
+
+__device__ __forceinline__ unsigned pack8_dibits(unsigned long long v)
+{
+    v &= 0x0303030303030303ull;
+    const unsigned hi = __byte_perm((unsigned)v, 0, 0x0123), lo = __byte_perm((unsigned)(v >> 32), 0, 0x0123);
+    auto gather4 = [](unsigned z) -> unsigned { const unsigned t = (z | (z >> 6)) & 0x000F000Fu; return (t | (t >> 12)) & 0xFFu; };
+    return (gather4(hi) << 8) | gather4(lo);
+}
+
+// bits [start, start + len) of the burst (bit 0 = MSB of W[0]), len <= 32, as the low `len` bits
+__device__ __forceinline__ unsigned burst_bits(const unsigned (&W)[16], int start, int len)
+{
+    const int q = start >> 5, sh = start & 31;
+    const unsigned hi = W[q], lo = (q + 1 < 16) ? W[q + 1] : 0u;
+    const unsigned x = __funnelshift_l(lo, hi, sh);              // bits start .. start+31
+    return len == 32 ? x : (x >> (32 - len));
+}
+
+__global__ void __launch_bounds__(BT_THREADS)
+burst_batch_tpb_kernel(const uint8_t *__restrict__ dibits, long n, uint8_t *__restrict__ rec,
+                       uint8_t *__restrict__ full, unsigned long long *__restrict__ stats)
+{
+    __shared__ uint32_t nib2[2][128][16];            // [type][16-bit lane * 4 + q4][value]: (forward | reversed << 16) CRC contribution
+    __shared__ uint16_t initv[512];
+    __shared__ __align__(4) uint16_t Wsm[16 * 2 * BT_PITCH];     // halfword g of burst t at (g >> 1) * 2 * PITCH + 2 t + (1 - (g & 1))  (word q = hi:lo)
+    {
+        for (int i = threadIdx.x; i < 2 * 128 * 16; i += blockDim.x) {
+            const int v = i & 15, pos = (i >> 4) & 127, type = i >> 11;
+            nib2[type][pos][v] = g_crc_nib[type][pos & 3][v][pos >> 2];
+        }
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) initv[i] = g_crc_init[i];
+    }
+    const long total_bytes = n * 255;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dibits) & 7) == 0);
+    unsigned pass = 0, total = 0;
+    for (long blk0 = (long)blockIdx.x * BT_THREADS; blk0 < n; blk0 += (long)gridDim.x * BT_THREADS) {
+        __syncthreads();                              // tables ready / previous tile consumed
+        const int nb = (int)((n - blk0 < BT_THREADS) ? (n - blk0) : BT_THREADS);
+        // ---- phase 1: pack
+        for (int task = threadIdx.x; task < nb * 32; task += BT_THREADS) {
+            const int t = task >> 5, g = task & 31;
+            const long a = (blk0 + t) * 255 + g * 8;
+            unsigned long long v;
+            const long a0 = a & ~7L;
+            if (aligned && a0 + 16 <= total_bytes) {
+                const unsigned long long *p = reinterpret_cast<const unsigned long long *>(dibits + a0);
+                const unsigned long long lo = p[0], hi = p[1];
+                const int sh = (int)(a & 7) * 8;
+                v = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+            } else {
+                v = 0;
+                for (int k = 0; k < 8; ++k) if (a + k < total_bytes) v |= (unsigned long long)dibits[a + k] << (8 * k);
+            }
+            if (g == 31) v &= 0x00FFFFFFFFFFFFFFull;  // dibit 255 does not exist
+            Wsm[(g >> 1) * 2 * BT_PITCH + 2 * t + (1 - (g & 1))] = (uint16_t)pack8_dibits(v);
+        }
+        __syncthreads();
+        // ---- phase 2: one burst per thread
+        const int t = threadIdx.x;
+        if (t < nb) {
+            unsigned W[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) W[q] = reinterpret_cast<const uint32_t *>(Wsm)[q * BT_PITCH + t];
+            // bits 255..276 against the two sync patterns (protocol.py:246-265)
+            const unsigned win = ((W[7] & 1u) << 21) | (W[8] >> 11);
+            const int mx = max(22 - __popc(win ^ SYNC_CONT_W), 22 - __popc(win ^ SYNC_DISC_W));
+            const bool is_sync = mx >= 18;
+            const int type = is_sync ? 1 : 0;
+            const int n_data = is_sync ? 510 : 216, n_pay = n_data - 16;
+            // data bits: normal [0,108) ++ [122,230); sync [0,510)
+            int ones;
+            if (is_sync) {
+                ones = __popc(W[15] & 0xFFFFFFFCu);
+#pragma unroll
+                for (int q = 0; q < 15; ++q) ones += __popc(W[q]);
+            } else {
+                ones = __popc(W[0]) + __popc(W[1]) + __popc(W[2]) + __popc(W[3] & 0xFFF0003Fu) + __popc(W[4]) + __popc(W[5]) +
+                       __popc(W[6]) + __popc(W[7] & 0xFC000000u);
+            }
+            // CRC-16 of the payload, forward and over the reversed payload, from per-position nibble contributions
+            unsigned c = 0;
+            const uint32_t (*nt)[16] = nib2[type];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                if (q >= 8 && !is_sync) break;         // normal: nibbles beyond bit 255 contribute nothing
+                const unsigned w = W[q];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) c ^= nt[8 * q + k][(w >> (28 - 4 * k)) & 15u];
+            }
+            const unsigned cf = (c & 0xFFFFu) ^ initv[n_pay], cr = (c >> 16) ^ initv[n_pay];
+            const unsigned rx = is_sync ? ((W[15] >> 2) & 0xFFFFu) : (((W[6] & 0x3FFu) << 6) | (W[7] >> 26));
+            bool crc_ok = false;
+            if (ones != 0 && ones != n_data) crc_ok = (__popc(cf ^ rx) <= 2) || (__popc(cr ^ rx) <= 2);
+            const unsigned long long head = ((unsigned long long)W[0] << 16) | (W[1] >> 16);
+            auto fld = [&](int lo, int nbits) -> unsigned { return (unsigned)((head >> (48 - lo - nbits)) & ((1ull << nbits) - 1ull)); };
+            const unsigned type2 = fld(0, 2), enc = fld(2, 2);
+            bool mac_ok;
+            if (type2 == 0) mac_ok = !((int)(fld(29, 6) * 8) > n_data - 35 + 16);
+            else if (type2 == 1) mac_ok = true;
+            else if (type2 == 2) { mac_ok = true; if (enc == 0) { unsigned mcc = fld(4, 10), mnc = fld(14, 14); mac_ok = !(mcc < 200 || mcc > 799 || mnc > 999); } }
+            else mac_ok = !((int)(fld(5, 6) * 8) > n_data - 11 + 16);
+            // record: 27 packed data bytes (data bits 0..215) + burst type, crc_ok, mac_ok, header, sync match
+            unsigned R[8];
+            if (is_sync) {
+#pragma unroll
+                for (int q = 0; q < 7; ++q) R[q] = W[q];
+            } else {
+                R[0] = W[0]; R[1] = W[1]; R[2] = W[2];
+                // data bits 96..107 = burst bits 96..107, data bits 108.. = burst bits 122..
+                R[3] = (W[3] & 0xFFF00000u) | burst_bits(W, 122, 20);
+#pragma unroll
+                for (int q = 4; q < 7; ++q) R[q] = burst_bits(W, 32 * q + 14, 32);
+            }
+            // bytes 24..26 = data bits 192..215 (top 24 bits of R[6]); bytes 27..31 = flags
+            const unsigned btype = is_sync ? 5u : 2u, hdr = (type2 << 2) | enc;
+            R[6] = (R[6] & 0xFFFFFF00u) | btype;
+            R[7] = ((crc_ok ? 1u : 0u) << 24) | ((mac_ok ? 1u : 0u) << 16) | (hdr << 8) | (unsigned)mx;
+            uint4 *ro = reinterpret_cast<uint4 *>(rec + (blk0 + t) * 32);
+            ro[0] = make_uint4(__byte_perm(R[0], 0, 0x0123), __byte_perm(R[1], 0, 0x0123), __byte_perm(R[2], 0, 0x0123), __byte_perm(R[3], 0, 0x0123));
+            ro[1] = make_uint4(__byte_perm(R[4], 0, 0x0123), __byte_perm(R[5], 0, 0x0123), __byte_perm(R[6], 0, 0x0123), __byte_perm(R[7], 0, 0x0123));
+            if (full) {
+                uint4 *fo = reinterpret_cast<uint4 *>(full + (blk0 + t) * 64);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                    fo[q4] = make_uint4(__byte_perm(W[4 * q4], 0, 0x0123), __byte_perm(W[4 * q4 + 1], 0, 0x0123),
+                                        __byte_perm(W[4 * q4 + 2], 0, 0x0123), __byte_perm(W[4 * q4 + 3], 0, 0x0123));
+            }
+            ++total;
+            pass += crc_ok ? 1u : 0u;
+        }
+    }
+    if (stats) {
+        total = __reduce_add_sync(0xffffffffu, total);
+        pass = __reduce_add_sync(0xffffffffu, pass);
+        if ((threadIdx.x & 31) == 0 && total) {
+            atomicAdd(&stats[0], (unsigned long long)total);
+            atomicAdd(&stats[1], (unsigned long long)pass);
+            atomicAdd(&stats[2], (unsigned long long)(total - pass));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ TetraDecoder.decode, one warp per stream
 // decode() of ONE stream by one full warp: b = bit row, mp = mapped symbols, c1/c2 = match counts
 // (global or shared memory), pos = scratch for max_frames sync positions.
@@ -764,6 +918,14 @@ int launch_burst_batch(tb200_handle h, const uint8_t *dibits, int64_t n, uint8_t
     long blocks = (warps_needed * 32 + threads - 1) / threads;
     long cap = 148L * 8 * 4;                  // persistent-ish: 8 CTAs/SM x 4 waves
     if (blocks > cap) blocks = cap;
+    // thread-per-burst form: needs 16-byte aligned outputs (two / four 16-byte stores per record)
+    if (((reinterpret_cast<uintptr_t>(rec) & 15) == 0) && (!full || (reinterpret_cast<uintptr_t>(full) & 15) == 0)) {
+        long tiles = (n + BT_THREADS - 1) / BT_THREADS;
+        long grid = tiles < 148L * 8 ? tiles : 148L * 8;
+        burst_batch_tpb_kernel<<<(unsigned)grid, BT_THREADS, 0, st>>>(dibits, n, rec, full, (unsigned long long *)stats);
+        TB_LAUNCH_CHECK(h);
+        return TB200_OK;
+    }
     burst_batch_kernel<<<(unsigned)blocks, threads, 0, st>>>(dibits, n, rec, full, (unsigned long long *)stats);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
