@@ -517,8 +517,9 @@ burst_batch_kernel(const uint8_t *__restrict__ dibits, long n, uint8_t *__restri
 // ------------------------------------------------------------------ burst batch, one THREAD per burst
 // The warp-per-burst form above spends ~85 % of its instructions on scalars every lane recomputes (type, CRC compare,
 // header fields, record assembly) and on the shuffles / reductions that hand them round.  Here a CTA takes 128 bursts:
-//   phase 1 (cooperative): the 128 x 255 bytes are read in 8-byte pieces (two aligned 64-bit loads + funnel shift, as
-//     above) and packed 2 bits per dibit into shared memory, 16 words per burst, [word][burst] with pitch 129;
+//   phase 1 (cooperative): the tile's 128 x 255 contiguous bytes come in with 16-byte loads (16 in flight per thread), are
+//     cut into 8-byte pieces (two aligned 64-bit shared loads + funnel shift) and packed 2 bits per dibit into shared
+//     memory, 16 words per burst, [word][burst] with pitch 129;
 //   phase 2: thread t owns burst t — its 510 bits in 16 registers, everything else is plain per-thread code: the
 //     22-bit sync window, the data-bit popcount, both CRCs from the position-dependent nibble table (re-laid
 //     [type][position][value] so that the 32 lanes of a warp, same position / different value, hit different banks),
@@ -550,6 +551,7 @@ burst_batch_tpb_kernel(const uint8_t *__restrict__ dibits, long n, uint8_t *__re
 {
     __shared__ uint32_t nib2[2][128][16];            // [type][16-bit lane * 4 + q4][value]: (forward | reversed << 16) CRC contribution
     __shared__ uint16_t initv[512];
+    extern __shared__ __align__(16) uint8_t raw[];               // [BT_THREADS * 255 + 32] the tile's dibits as they lie in memory
     __shared__ __align__(4) uint16_t Wsm[16 * 2 * BT_PITCH];     // halfword g of burst t at (g >> 1) * 2 * PITCH + 2 t + (1 - (g & 1))  (word q = hi:lo)
     {
         for (int i = threadIdx.x; i < 2 * 128 * 16; i += blockDim.x) {
@@ -558,27 +560,41 @@ burst_batch_tpb_kernel(const uint8_t *__restrict__ dibits, long n, uint8_t *__re
         }
         for (int i = threadIdx.x; i < 512; i += blockDim.x) initv[i] = g_crc_init[i];
     }
-    const long total_bytes = n * 255;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(dibits) & 7) == 0);
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(dibits) & 15) == 0);
     unsigned pass = 0, total = 0;
     for (long blk0 = (long)blockIdx.x * BT_THREADS; blk0 < n; blk0 += (long)gridDim.x * BT_THREADS) {
         __syncthreads();                              // tables ready / previous tile consumed
         const int nb = (int)((n - blk0 < BT_THREADS) ? (n - blk0) : BT_THREADS);
-        // ---- phase 1: pack
+        // ---- phase 1a: the tile's bytes (contiguous: bursts are 255-byte rows) into shared memory, 16 bytes per load, all of a
+        // thread's loads in flight before the first store
+        const long tile_byte0 = blk0 * 255;
+        const int tile_bytes = nb * 255;
+        if (aligned16) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(dibits + tile_byte0);
+            uint4 *dst = reinterpret_cast<uint4 *>(raw);
+            const int n16 = tile_bytes >> 4;
+            constexpr int PER = (BT_THREADS * 255 / 16 + BT_THREADS - 1) / BT_THREADS;     // 16, in two rounds of 8
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint4 tmp[PER / 2];
+#pragma unroll
+                for (int i = 0; i < PER / 2; ++i) { const int j = threadIdx.x + (h * (PER / 2) + i) * BT_THREADS; if (j < n16) tmp[i] = src[j]; }
+#pragma unroll
+                for (int i = 0; i < PER / 2; ++i) { const int j = threadIdx.x + (h * (PER / 2) + i) * BT_THREADS; if (j < n16) dst[j] = tmp[i]; }
+            }
+            for (int j = (n16 << 4) + threadIdx.x; j < tile_bytes; j += BT_THREADS) raw[j] = dibits[tile_byte0 + j];
+        } else {
+            for (int j = threadIdx.x; j < tile_bytes; j += BT_THREADS) raw[j] = dibits[tile_byte0 + j];
+        }
+        for (int j = tile_bytes + threadIdx.x; j < tile_bytes + 16; j += BT_THREADS) raw[j] = 0;      // the last piece reads past the tile
+        __syncthreads();
+        // ---- phase 1b: pack 8 dibits -> 16 bits (two aligned 64-bit shared loads + funnel shift per piece)
         for (int task = threadIdx.x; task < nb * 32; task += BT_THREADS) {
             const int t = task >> 5, g = task & 31;
-            const long a = (blk0 + t) * 255 + g * 8;
-            unsigned long long v;
-            const long a0 = a & ~7L;
-            if (aligned && a0 + 16 <= total_bytes) {
-                const unsigned long long *p = reinterpret_cast<const unsigned long long *>(dibits + a0);
-                const unsigned long long lo = p[0], hi = p[1];
-                const int sh = (int)(a & 7) * 8;
-                v = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
-            } else {
-                v = 0;
-                for (int k = 0; k < 8; ++k) if (a + k < total_bytes) v |= (unsigned long long)dibits[a + k] << (8 * k);
-            }
+            const int a = t * 255 + g * 8, a0 = a & ~7, sh = (a & 7) * 8;
+            const unsigned long long lo = *reinterpret_cast<const unsigned long long *>(raw + a0);
+            const unsigned long long hi = *reinterpret_cast<const unsigned long long *>(raw + a0 + 8);
+            unsigned long long v = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
             if (g == 31) v &= 0x00FFFFFFFFFFFFFFull;  // dibit 255 does not exist
             Wsm[(g >> 1) * 2 * BT_PITCH + 2 * t + (1 - (g & 1))] = (uint16_t)pack8_dibits(v);
         }
@@ -922,7 +938,10 @@ int launch_burst_batch(tb200_handle h, const uint8_t *dibits, int64_t n, uint8_t
     if (((reinterpret_cast<uintptr_t>(rec) & 15) == 0) && (!full || (reinterpret_cast<uintptr_t>(full) & 15) == 0)) {
         long tiles = (n + BT_THREADS - 1) / BT_THREADS;
         long grid = tiles < 148L * 8 ? tiles : 148L * 8;
-        burst_batch_tpb_kernel<<<(unsigned)grid, BT_THREADS, 0, st>>>(dibits, n, rec, full, (unsigned long long *)stats);
+        const size_t smem_bt = BT_THREADS * 255 + 32;          // + 25 KB static: above the 48 KB default, opt in
+        cudaError_t e = cudaFuncSetAttribute(burst_batch_tpb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(burst_batch): %s", cudaGetErrorString(e));
+        burst_batch_tpb_kernel<<<(unsigned)grid, BT_THREADS, smem_bt, st>>>(dibits, n, rec, full, (unsigned long long *)stats);
         TB_LAUNCH_CHECK(h);
         return TB200_OK;
     }
