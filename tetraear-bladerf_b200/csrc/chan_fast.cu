@@ -540,29 +540,53 @@ struct ChanFast32Params {
     float pc[2][2];                // p^16
     float p7[2][2], p15[2][2];
     int nstage[2];                 // Kogge-Stone stages that matter for mode i
+    float G[CF_R];                 // y[r] = sum_j G[|r - j|] x[j]: zero-state response inside a lane (G[0] includes c0p)
+    float PW[2][CF_R][2];          // p_i^k, k < R
 };
 
 constexpr int C32_NS = CG_NS;
 constexpr int C32_NP = CG_NP;
 
-// one direction over the lane's CF_R samples: zero-state recurrences, Kogge-Stone scan of the lane aggregates,
-// in-warp carry applied to y; the pass-end state goes to carry[0..1]
-template <bool FWD>
+// in-lane work as constant-weight sums (see c64_outputs): outputs' zero-state response and the lane aggregates
+__device__ __forceinline__ void c32_outputs(const float2 (&xs)[CF_R], float2 (&y)[CF_R], const ChanFast32Params &K)
+{
+#pragma unroll
+    for (int r = 0; r < CF_R; ++r) {
+        float2 acc = make_float2(K.G[0] * xs[r].x, K.G[0] * xs[r].y);
+#pragma unroll
+        for (int j = 0; j < CF_R; ++j) if (j != r) acc = ffma2(splat(K.G[j > r ? j - r : r - j]), xs[j], acc);
+        y[r] = acc;
+    }
+}
+template <bool FWD, int NT>
+__device__ __forceinline__ void c32_aggregate(const float2 (&xs)[CF_R], const ChanFast32Params &K, cp (&s)[2])
+{
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        float2 re = make_float2(0.f, 0.f), im = re;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int k = FWD ? NT - 1 - j : j;
+            re = ffma2(splat(K.PW[m][k][0]), xs[j], re);
+            im = ffma2(splat(K.PW[m][k][1]), xs[j], im);
+        }
+        s[m].re = re; s[m].im = im;
+    }
+}
+
+// one direction: Kogge-Stone scan of the lane aggregates, in-warp carry applied to y; the pass-end state goes to
+// carry[0..1].  EDGE: Fe = zero-state F at r = 6 of this lane + p^7 * carry-in (right-halo pass of the last tile).
+template <bool FWD, bool EDGE>
 __device__ __forceinline__ void c32_dir(const float2 (&xs)[CF_R], float2 (&y)[CF_R], int lane, const ChanFast32Params &K,
                                         cp *carry, cp *Fe, bool edge_lane)
 {
-    const cf p0 = ld2(K.p[0]), p1 = ld2(K.p[1]), a0 = ld2(K.a2[0]), a1 = ld2(K.a2[1]);
     const float2 zero2 = make_float2(0.f, 0.f);
     cp s[2];
-    s[0].re = s[0].im = s[1].re = s[1].im = zero2;
-#pragma unroll
-    for (int i = 0; i < CF_R; ++i) {
-        const int r = FWD ? i : CF_R - 1 - i;
-        cp in; in.re = xs[r]; in.im = zero2;
-        s[0] = cpfma(p0, s[0], in);
-        s[1] = cpfma(p1, s[1], in);
-        y[r] = re_acc(a0, s[0], re_acc(a1, s[1], y[r]));
-        if (FWD && r == 6) { Fe[0] = s[0]; Fe[1] = s[1]; }           // zero-state F at r = 6 (edge lane)
+    c32_aggregate<FWD, CF_R>(xs, K, s);
+    if (EDGE) {
+        cp f6[2];
+        c32_aggregate<true, CF_R - 1>(xs, K, f6);
+        Fe[0] = f6[0]; Fe[1] = f6[1];
     }
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
@@ -583,7 +607,7 @@ __device__ __forceinline__ void c32_dir(const float2 (&xs)[CF_R], float2 (&y)[CF
         cin.im = FWD ? shfl2_up(a.im, 1) : shfl2_down(a.im, 1);
         if (lane == (FWD ? 0 : 31)) cin.re = cin.im = zero2;
         if (lane == (FWD ? 31 : 0)) carry[m] = a;
-        if (FWD && edge_lane) Fe[m] = cpfma(ld2(K.p7[m]), cin, Fe[m]);   // + p^7 * (carry from lane 0 of this warp)
+        if (EDGE && edge_lane) Fe[m] = cpfma(ld2(K.p7[m]), cin, Fe[m]);   // + p^7 * (carry from lane 0 of this warp)
 #pragma unroll
         for (int r = 0; r < CF_R; ++r) y[r] = re_acc(FWD ? ld2(K.aF2[r][m]) : ld2(K.aB2[r][m]), cin, y[r]);
     }
@@ -667,14 +691,17 @@ chan_fast32_kernel(const float *__restrict__ x, long n, long in_stride, int tile
     float2 xs[CF_R], y[CF_R];
     cp Fe[2];
     c32_load(xc, n, m0, W, fs, xs);
+    if (store) c32_outputs(xs, y, K);
+    else {
 #pragma unroll
-    for (int r = 0; r < CF_R; ++r) y[r] = make_float2(K.c0p * xs[r].x, K.c0p * xs[r].y);
-    c32_dir<true>(xs, y, lane, K, carryF[w], Fe, false);
+        for (int r = 0; r < CF_R; ++r) y[r] = make_float2(0.f, 0.f);            // the halo warp stores nothing
+    }
+    c32_dir<true, false>(xs, y, lane, K, carryF[w], Fe, false);
     if (!store) {
         c32_load(xc, n, m0B, W, fs, xs);
-        if (last_tile) c32_dir<true>(xs, y, lane, K, carryF[C32_NP - 1], Fe, edge_lane);   // F[M-1] lives in the right halo
+        if (last_tile) c32_dir<true, true>(xs, y, lane, K, carryF[C32_NP - 1], Fe, edge_lane);   // F[M-1] lives in the right halo
     }
-    c32_dir<false>(xs, y, lane, K, carryB[passB], Fe, false);
+    c32_dir<false, false>(xs, y, lane, K, carryB[passB], Fe, false);
     __syncthreads();
     if (last_tile) {
         if (edge_lane) {
@@ -850,6 +877,7 @@ static void make_chan32_params(const ChanFastParams &K, ChanFast32Params &F)
 {
     memset(&F, 0, sizeof(F));
     F.c0p = (float)K.c0p;
+    for (int d = 0; d < CF_R; ++d) F.G[d] = (float)K.G[d];
     for (int j = 0; j < 2; ++j) {
         putf(F.p[j], K.p[j]);
         const cd pj(K.p[j][0], K.p[j][1]), al(K.a[j][0], K.a[j][1]);
@@ -869,6 +897,7 @@ static void make_chan32_params(const ChanFastParams &K, ChanFast32Params &F)
         putf(F.ka[j], K.ka[j]);
         for (int i = 0; i < 2; ++i) { putf(F.kM[j][i], K.kM[j][i]); putf(F.kMc[j][i], K.kMc[j][i]); }
         putf(F.pc[j], K.pc[j]);
+        for (int k = 0; k < CF_R; ++k) { F.PW[j][k][0] = (float)K.PW[j][k][0]; F.PW[j][k][1] = (float)K.PW[j][k][1]; }
         cd v7 = std::pow(pj, 7), v15 = std::pow(pj, 15);
         F.p7[j][0] = (float)v7.real(); F.p7[j][1] = (float)v7.imag();
         F.p15[j][0] = (float)v15.real(); F.p15[j][1] = (float)v15.imag();
