@@ -68,6 +68,15 @@ detect_sums_kernel(const T *__restrict__ x, long n, long stride, int num_windows
     double acc[DT_NW], tot = 0.0, mx = 0.0;
 #pragma unroll
     for (int k = 0; k < DT_NW; ++k) acc[k] = 0.0;
+    // a thread's samples come in increasing order, so its window index never decreases: one running sum for the current
+    // window, handed to acc[] when the window changes (same additions in the same order as adding every sample to acc[w])
+    int cur_w = -1;
+    long w_end = lo;                                   // first sample index beyond the current window
+    double accw = 0.0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int k = 0; k < DT_NW; ++k) if (k == cur_w && k < num_windows) acc[k] = accw;
+    };
     for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         const double re = (double)xc[2 * i], im = (double)xc[2 * i + 1];
         double p;
@@ -75,10 +84,17 @@ detect_sums_kernel(const T *__restrict__ x, long n, long stride, int num_windows
         else { double a = hypot(re, im); p = a * a; }
         tot += p;
         mx = fmax(mx, re * re + im * im);
-        const int w = ws > 0 ? (int)(i / ws) : DT_NW;
-#pragma unroll
-        for (int k = 0; k < DT_NW; ++k) acc[k] += (w == k && k < num_windows) ? p : 0.0;
+        if (ws > 0) {
+            if (i >= w_end) {                          // new window (a block's range rarely spans more than two)
+                flush();
+                cur_w = (int)(i / ws);
+                w_end = (long)(cur_w + 1) * ws;
+                accw = 0.0;
+            }
+            accw += p;
+        }
     }
+    flush();
     __shared__ double red[8][DT_PART];
     const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double v[DT_PART];

@@ -402,6 +402,9 @@ int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_
     if (smoothed) {
         if (alpha < 1.0 && alpha > 0.0) warm = (long)std::ceil(-20.72 / std::log1p(-alpha));     // (1-a)^warm < 1e-9
         group = 4 * warm;
+        // short runs (e.g. averaged spectra): smaller groups, down to one warm-up length, until the launch has ~1000 CTAs
+        while (group > warm && warm > 0 && ((n_frames + group - 1) / group) * ((n_fft + 127) / 128) < 1024) group /= 2;
+        if (group < warm) group = warm;
         if (!(alpha > 0.0) || warm > 4096 || group >= n_frames) { group = n_frames; warm = 0; }
         const long groups = (n_frames + group - 1) / group;
         if (groups > 1 && !first) {
