@@ -423,18 +423,34 @@ chan_fast64_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_p
     const bool edge_lane = last_tile && w == 0 && lane == 1;
     cdd Fe[2], cF[2], cB[2];
 
+    // A causal pass that lies entirely left of the odd extension (sample index < -15) sees the constant continuation
+    // only: its end state is the steady state c / (1 - p) and nothing of it is stored — the first, partial tile of a
+    // chunk skips those passes (tiles are aligned to the END of the chunk: 13108 samples = 3.2 of the first tile's 7).
+    const bool const_pass = mt0 - CF_P + (long)w * CF_P + CF_P - 1 < -15;
     double xs[CF_R], y[CF_R];
-    c64_load<TI>(xc, n, m0, W, fs, c, xs);
+    if (const_pass) {
+        if (lane == 31) {
+            const double c0 = c64_padded<TI>(xc, n, -1, W, fs, c);
+            carryF[w][c][0] = cdd{K.inv1mp[0][0] * c0, K.inv1mp[0][1] * c0};
+            carryF[w][c][1] = cdd{K.inv1mp[1][0] * c0, K.inv1mp[1][1] * c0};
+        }
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) { xs[r] = 0.0; y[r] = 0.0; }
+    } else c64_load<TI>(xc, n, m0, W, fs, c, xs);
     cdd sF[2], sB[2];
-    if (store) {
+    if (store && const_pass) {
+        cF[0] = cF[1] = cB[0] = cB[1] = cdd{0.0, 0.0};
+    } else if (store) {
         c64_outputs(xs, y, K);
         c64_aggregate<true>(xs, K, sF);
         c64_aggregate<false>(xs, K, sB);
         c64_scan<true, false>(xs, sF, lane, K, carryF[w][c], cF, Fe, false);
         c64_scan<false, false>(xs, sB, lane, K, carryB[w][c], cB, Fe, false);
     } else {
-        c64_aggregate<true>(xs, K, sF);
-        c64_scan<true, false>(xs, sF, lane, K, carryF[0][c], cF, Fe, false);
+        if (!const_pass) {
+            c64_aggregate<true>(xs, K, sF);
+            c64_scan<true, false>(xs, sF, lane, K, carryF[0][c], cF, Fe, false);
+        }
         c64_load<TI>(xc, n, m0B, W, fs, c, xs);
         if (last_tile) {                               // F[M-1] lives in the right halo
             c64_aggregate<true>(xs, K, sF);
@@ -459,7 +475,7 @@ chan_fast64_kernel(const TI *__restrict__ x, long n, long in_stride, int tiles_p
         }
         __syncthreads();
     }
-    if (store) {
+    if (store && !const_pass) {
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             // total carry into this lane: in-pass (from the scan) + lane power * end state of the neighbouring pass
@@ -541,6 +557,7 @@ struct ChanFast32Params {
     float p7[2][2], p15[2][2];
     int nstage[2];                 // Kogge-Stone stages that matter for mode i
     float G[CF_R];                 // y[r] = sum_j G[|r - j|] x[j]: zero-state response inside a lane (G[0] includes c0p)
+    float inv1mp[2][2];            // 1 / (1 - p_i): steady state of a constant input
     float PW[2][CF_R][2];          // p_i^k, k < R
 };
 
@@ -688,20 +705,35 @@ chan_fast32_kernel(const float *__restrict__ x, long n, long in_stride, int tile
     // ext[M-1] is sample m = n + 14: lane 1, r = 6 of the right-halo pass of the last tile (run by warp 0)
     const bool edge_lane = last_tile && w == 0 && lane == 1;
 
+    // a causal pass entirely left of the odd extension sees the constant continuation only (see chan_fast64_kernel)
+    const bool const_pass = mt0 - CF_P + (long)w * CF_P + CF_P - 1 < -15;
     float2 xs[CF_R], y[CF_R];
     cp Fe[2];
-    c32_load(xc, n, m0, W, fs, xs);
-    if (store) c32_outputs(xs, y, K);
-    else {
+    if (const_pass) {
+        if (lane == 31) {
+            const float2 c0 = c32_padded(xc, n, -1, W, fs);
 #pragma unroll
-        for (int r = 0; r < CF_R; ++r) y[r] = make_float2(0.f, 0.f);            // the halo warp stores nothing
+            for (int m = 0; m < 2; ++m) {
+                carryF[w][m].re = make_float2(K.inv1mp[m][0] * c0.x, K.inv1mp[m][0] * c0.y);
+                carryF[w][m].im = make_float2(K.inv1mp[m][1] * c0.x, K.inv1mp[m][1] * c0.y);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < CF_R; ++r) { xs[r] = make_float2(0.f, 0.f); y[r] = make_float2(0.f, 0.f); }
+    } else {
+        c32_load(xc, n, m0, W, fs, xs);
+        if (store) c32_outputs(xs, y, K);
+        else {
+#pragma unroll
+            for (int r = 0; r < CF_R; ++r) y[r] = make_float2(0.f, 0.f);        // the halo warp stores nothing
+        }
+        c32_dir<true, false>(xs, y, lane, K, carryF[w], Fe, false);
     }
-    c32_dir<true, false>(xs, y, lane, K, carryF[w], Fe, false);
     if (!store) {
         c32_load(xc, n, m0B, W, fs, xs);
         if (last_tile) c32_dir<true, true>(xs, y, lane, K, carryF[C32_NP - 1], Fe, edge_lane);   // F[M-1] lives in the right halo
     }
-    c32_dir<false, false>(xs, y, lane, K, carryB[passB], Fe, false);
+    if (!(store && const_pass)) c32_dir<false, false>(xs, y, lane, K, carryB[passB], Fe, false);
     __syncthreads();
     if (last_tile) {
         if (edge_lane) {
@@ -724,7 +756,7 @@ chan_fast32_kernel(const float *__restrict__ x, long n, long in_stride, int tile
         }
         __syncthreads();
     }
-    if (store) {
+    if (store && !const_pass) {                        // (a constant pass covers only negative sample indices: nothing to store or sum)
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             const cp gF = cpmul(lanepow[lane][m], carryF[w - 1][m]);
@@ -898,6 +930,7 @@ static void make_chan32_params(const ChanFastParams &K, ChanFast32Params &F)
         for (int i = 0; i < 2; ++i) { putf(F.kM[j][i], K.kM[j][i]); putf(F.kMc[j][i], K.kMc[j][i]); }
         putf(F.pc[j], K.pc[j]);
         for (int k = 0; k < CF_R; ++k) { F.PW[j][k][0] = (float)K.PW[j][k][0]; F.PW[j][k][1] = (float)K.PW[j][k][1]; }
+        F.inv1mp[j][0] = (float)K.inv1mp[j][0]; F.inv1mp[j][1] = (float)K.inv1mp[j][1];
         cd v7 = std::pow(pj, 7), v15 = std::pow(pj, 15);
         F.p7[j][0] = (float)v7.real(); F.p7[j][1] = (float)v7.imag();
         F.p15[j][0] = (float)v15.real(); F.p15[j][1] = (float)v15.imag();
