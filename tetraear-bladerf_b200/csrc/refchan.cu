@@ -141,11 +141,12 @@ refchan_kernel(const float2 *__restrict__ x, long n, int M, int N1, int log2_n2,
 // for P = 24) and the windows of the 8 frames overlap almost entirely, so the input is staged in shared memory one
 // prototype block l at a time: the samples that block needs for all 8 frames are the 800 + 7 hop contiguous samples
 //     x[hop m0 - 799 - 800 l  ..  hop (m0 + 7) - 800 l],
-// brought in by one TMA bulk copy per block into a three-deep ring, two blocks ahead of the one being accumulated.  The 800-point
+// brought in by one TMA bulk copy per PAIR of blocks (their ranges overlap: 800 + 800 + 7 hop samples) into a double buffer,
+// one pair ahead of the one being accumulated.  The 800-point
 // inverse DFT runs in place on the folded windows V[r1][f][r2] (r = 32 r1 + r2, pitch 33) as four small-radix passes —
 // 5-point over a (r1 = 5a + b), 5-point over b, 8-point over i and 4-point over g (r2 = 4i + g) — each a thread per
 // (row, column) task, so no thread holds more than 8 points and all 416 threads have work.  Output k = k1 + 25 k2.
-constexpr int PB_M = 800, PB_F = 8, PB_PITCH = 33, PB_ROWS = 25 * PB_F, PB_THREADS = 416, PB_RS = 400, PB_RING = 3;
+constexpr int PB_M = 800, PB_F = 8, PB_PITCH = 33, PB_ROWS = 25 * PB_F, PB_THREADS = 416, PB_RS = 400;
 
 // inverse 8-point DFT in registers, radix 2: v[] holds the input in bit-reversed order, the output in natural order
 __device__ __forceinline__ void ifft8_regs(float2 (&v)[8])
@@ -169,10 +170,10 @@ polybank800_kernel(const float2 *__restrict__ x, long n, int P, int l0, int hop_
                    const float *__restrict__ proto, const float2 *__restrict__ wm_g, float2 *__restrict__ out, long out_stride)
 {
     extern __shared__ float2 pb_smem[];
-    __shared__ __align__(8) uint64_t full[PB_RING];
+    __shared__ __align__(8) uint64_t full[2];
     float2 *V = pb_smem;                              // [r1 or rho][f][PB_PITCH]
     float2 *wm = V + PB_ROWS * PB_PITCH;              // [800] exp(+j 2 pi i / 800)
-    float2 *seg = wm + PB_M;                          // [PB_RING][SEGP]
+    float2 *seg = wm + PB_M;                          // [2][SEGP + 800]: two block pairs
     // block l of the prototype needs x[s0 .. s0 + SEG), s0 = hop m0 - 799 - 800 l: odd, so the staged range starts one
     // sample earlier (16-byte aligned for the bulk copy) and is padded to an even length
     const int hop = HOP ? HOP : hop_rt;
@@ -182,41 +183,44 @@ polybank800_kernel(const float2 *__restrict__ x, long n, int P, int l0, int hop_
     const long s_base = (long)hop * m0 - PB_M;        // first staged sample of block l: s_base - 800 l
     const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     if (tid == 0) {
-        for (int i = 0; i < PB_RING; ++i) mbar_init(&full[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&full[i], 1);
     }
     __syncthreads();
-    // blocks l whose whole staged range lies inside the chunk: lb_lo <= l <= lb_hi
-    int lb_lo = 1, lb_hi = 0;
+    // Blocks are staged in PAIRS: the ranges of blocks l and l + 1 are 800 samples apart and overlap, so the pair is the
+    // contiguous run of SEGP + 800 samples starting at s_base - 800 (l + 1) — one bulk copy and one __syncthreads per two
+    // blocks.  Pairs pi whose whole run lies inside the chunk (pb_lo <= pi <= pb_hi) come by TMA, the others by plain
+    // loads with zeros outside [0, n).
+    const int SEGQ = SEGP + PB_M;                     // samples per pair
+    const int n_pairs = P >> 1;                       // P is even (launch check)
+    const long s_pair0 = s_base - (long)PB_M * (l0 + 1);        // first sample of pair 0; pair pi starts 1600 pi earlier
+    int pb_lo = 1, pb_hi = 0;
     if (aligned) {
         auto fdiv = [](long a, long b) -> long { return a / b - ((a % b != 0) && (a < 0)); };
-        lb_hi = (int)max(min(fdiv(s_base, PB_M), 1L << 20), -(1L << 20));
-        lb_lo = (int)max(min(-fdiv(n - s_base - SEGP, PB_M), 1L << 20), -(1L << 20));
+        pb_hi = (int)max(min(fdiv(s_pair0, 2 * PB_M), 1L << 20), -(1L << 20));
+        pb_lo = (int)max(min(-fdiv(n - s_pair0 - SEGQ, 2 * PB_M), 1L << 20), -(1L << 20));
     }
-    auto bulk = [&](int l) -> bool { return l >= lb_lo && l <= lb_hi; };
-    // inside the chunk: ONE bulk copy (TMA) issued by thread 0, completion on the slot's mbarrier; at the chunk ends:
-    // plain loads with zeros outside [0, n), made visible by the loop's __syncthreads
-    auto stage = [&](int l, int buf) {
-        const long s0 = s_base - (long)PB_M * l;
-        float2 *dst = seg + buf * SEGP;
-        if (bulk(l)) {
+    auto bulk = [&](int pi) -> bool { return pi >= pb_lo && pi <= pb_hi; };
+    auto stage = [&](int pi, int buf) {
+        const long s0 = s_pair0 - 2L * PB_M * pi;
+        float2 *dst = seg + buf * SEGQ;
+        if (bulk(pi)) {
             if (tid == 0) {
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                tma_load_1d(dst, x + s0, (unsigned)SEGP * 8u, &full[buf]);
+                tma_load_1d(dst, x + s0, (unsigned)SEGQ * 8u, &full[buf]);
             }
         } else {
-            for (int i = tid; i < SEGP; i += PB_THREADS) {
+            for (int i = tid; i < SEGQ; i += PB_THREADS) {
                 const long t = s0 + i;
                 dst[i] = (t >= 0 && t < n) ? x[t] : make_float2(0.f, 0.f);
             }
         }
     };
-    stage(l0, 0);
-    if (P > 1) stage(l0 + 1, 1);
+    stage(0, 0);
     for (int i = tid; i < PB_M; i += PB_THREADS) wm[i] = wm_g[i];
     // ---- folded windows: v_f[r] = sum_l h[r + 800 l] x[hop (m0 + f) - r - 800 l]; sample (r, f) of block l is staged at
-    // index 800 - r + hop f.  Branches hop apart see the same samples one frame later, so a thread takes the pair
-    // (rA, rA + hop) and all 8 frames: 9 shared loads feed 16 packed multiply-adds.  (If hop * ceil(ceil(800 / hop) / 2)
-    // exceeds the CTA, a thread takes branches r and r + 400 instead: 16 loads.)
+    // index 800 - r + hop f of the block's range.  Branches hop apart see the same samples one frame later, so a thread
+    // takes the pair (rA, rA + hop) and all 8 frames: 9 shared loads feed 16 packed multiply-adds.  (If
+    // hop * ceil(ceil(800 / hop) / 2) exceeds the CTA, a thread takes branches r and r + 400 instead: 16 loads.)
     const int nI = (PB_M + hop - 1) / hop, groups = (nI + 1) / 2;
     const bool toep = hop * groups <= PB_THREADS;
     int rA, rB;
@@ -228,38 +232,40 @@ polybank800_kernel(const float2 *__restrict__ x, long n, int P, int l0, int hop_
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int f = 0; f < PB_F; ++f) acc[i][f] = make_float2(0.f, 0.f);
-    unsigned phase = 0;                               // bit b: parity the next bulk completion of slot b will have
-    // taps are fetched one block ahead: their latency hides behind the wait.  Threads without a valid second branch
+    unsigned phase = 0;                               // bit b: parity the next bulk completion of buffer b will have
+    // taps are fetched one pair ahead: their latency hides behind the wait.  Threads without a valid second branch
     // read tap 0 and the word in front of the stage: their acc[1] is never stored.
     const float *pA = proto + (vA ? rA : 0), *pB = proto + (vB ? rB : 0);
-    float hA_n = __ldg(pA), hB_n = __ldg(pB);
+    float hA_n[2] = {__ldg(pA), __ldg(pA + PB_M)}, hB_n[2] = {__ldg(pB), __ldg(pB + PB_M)};
     const int offA = PB_M - rA, offB = PB_M - rB;
-    for (int li0 = 0; li0 < P; li0 += PB_RING) {
+    for (int pi = 0; pi < n_pairs; ++pi) {
+        const int buf = pi & 1;
+        const float hA[2] = {hA_n[0], hA_n[1]}, hB[2] = {hB_n[0], hB_n[1]};
+        if (pi + 1 < n_pairs) {
+            pA += 2 * PB_M; pB += 2 * PB_M;
+            hA_n[0] = __ldg(pA); hA_n[1] = __ldg(pA + PB_M); hB_n[0] = __ldg(pB); hB_n[1] = __ldg(pB + PB_M);
+        }
+        if (bulk(pi)) { mbar_wait(&full[buf], (phase >> buf) & 1u); phase ^= 1u << buf; }
+        __syncthreads();                              // pair pi is visible; everyone is done with the other buffer
+        if (pi + 1 < n_pairs) stage(pi + 1, buf ^ 1);
+        if (!vA) continue;
 #pragma unroll
-        for (int slot = 0; slot < PB_RING; ++slot) {
-            const int li = li0 + slot;
-            if (li >= P) break;
-            const float hA = hA_n, hB = hB_n;
-            if (li + 1 < P) { pA += PB_M; pB += PB_M; hA_n = __ldg(pA); hB_n = __ldg(pB); }
-            if (bulk(l0 + li)) { mbar_wait(&full[slot], (phase >> slot) & 1u); phase ^= 1u << slot; }
-            __syncthreads();                          // block li is visible; everyone is done with the buffer of block li - 1
-            if (li + 2 < P) stage(l0 + li + 2, (slot + 2) % PB_RING);
-            if (!vA) continue;
-            const float2 *sg = seg + slot * SEGP;
+        for (int half = 0; half < 2; ++half) {        // block l0 + 2 pi + half lies 800 (1 - half) samples into the pair
+            const float2 *sg = seg + buf * SEGQ + (half ? 0 : PB_M);
             if (toep) {
                 float2 prev = sg[offB];
 #pragma unroll
                 for (int f = 0; f < PB_F; ++f) {
                     const float2 cur = sg[offA + hop * f];
-                    acc[0][f] = ffma2(splat(hA), cur, acc[0][f]);
-                    acc[1][f] = ffma2(splat(hB), prev, acc[1][f]);
+                    acc[0][f] = ffma2(splat(hA[half]), cur, acc[0][f]);
+                    acc[1][f] = ffma2(splat(hB[half]), prev, acc[1][f]);
                     prev = cur;
                 }
             } else {
 #pragma unroll
                 for (int f = 0; f < PB_F; ++f) {
-                    acc[0][f] = ffma2(splat(hA), sg[offA + hop * f], acc[0][f]);
-                    acc[1][f] = ffma2(splat(hB), sg[offB + hop * f], acc[1][f]);
+                    acc[0][f] = ffma2(splat(hA[half]), sg[offA + hop * f], acc[0][f]);
+                    acc[1][f] = ffma2(splat(hB[half]), sg[offB + hop * f], acc[1][f]);
                 }
             }
         }
@@ -672,8 +678,8 @@ int launch_refchan(tb200_handle h, const float2 *x, long n, int M, int q, double
 int launch_polyphase_bank(tb200_handle h, const float2 *x, long n, int M, int N1, int N2, int P, int l0, int hop, long n_frames,
                           const float *proto, const float2 *tw, float2 *out, long out_stride, cudaStream_t st)
 {
-    if (N1 == 25 && N2 == 32) {
-        const size_t smem = sizeof(float2) * ((size_t)PB_ROWS * PB_PITCH + PB_M + PB_RING * (size_t)((PB_M + (PB_F - 1) * hop + 2) & ~1));
+    if (N1 == 25 && N2 == 32 && (P & 1) == 0) {
+        const size_t smem = sizeof(float2) * ((size_t)PB_ROWS * PB_PITCH + PB_M + 2 * ((size_t)((PB_M + (PB_F - 1) * hop + 2) & ~1) + PB_M));
         if (smem <= 200 * 1024) {
             static std::once_flag tw_once[64];
             static cudaError_t tw_err[64];
