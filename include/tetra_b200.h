@@ -160,6 +160,16 @@ int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, int n_chunk
                         int64_t chunk_stride, const double *d_freq_off, uint8_t *d_dibits,
                         void *d_symbols, int out_stride, int32_t *d_n_dibits, int32_t *d_phase,
                         void *stream);
+/* process() followed by TetraDecoder.decode() of every chunk (decoder.py:835-888) — what CaptureThread.run does per
+ * chunk (ui/modern.py:2032-2044) — as one call: the outputs of tb200_process_batch plus those of tb200_decode_batch
+ * (d_frames [n_chunks][max_frames], d_n_frames [n_chunks], d_stats [3] or NULL).  Where a chunk's dibits fit the
+ * one-launch decoder (out_stride <= 6000, max_frames <= 64) the timing pick, slicer, sync search and frame records are
+ * ONE kernel launch per batch; otherwise the two calls run back to back.  Same results either way. */
+int tb200_process_decode_batch(tb200_handle h, const void *d_iq, int dtype, int n_chunks, int chunk_len,
+                               int64_t chunk_stride, const double *d_freq_off, uint8_t *d_dibits,
+                               void *d_symbols, int out_stride, int32_t *d_n_dibits, int32_t *d_phase,
+                               tb200_frame *d_frames, int max_frames, int32_t *d_n_frames, int64_t *d_stats,
+                               void *stream);
 /* same, HOST buffers in and out: H2D of the IQ, the kernels, D2H of dibits / counts / symbols,
  * all on `stream`, synchronised before return. */
 int tb200_process_batch_host(tb200_handle h, const void *h_iq, int dtype, int n_chunks, int chunk_len,

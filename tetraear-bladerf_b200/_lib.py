@@ -59,6 +59,7 @@ _PROTOS = {
     "tb200_workspace_bytes": (C.c_size_t, [_vp]),
     "tb200_launch_count": (_i64, [_vp]),
     "tb200_process_batch": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "tb200_process_decode_batch": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "tb200_process_batch_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "tb200_resample": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "tb200_decimate": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),

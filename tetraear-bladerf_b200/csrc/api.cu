@@ -294,10 +294,12 @@ extern "C" size_t tb200_workspace_bytes(tb200_handle h) { return h ? h->ws_bytes
 extern "C" int64_t tb200_launch_count(tb200_handle h) { return h ? h->launches : 0; }
 
 // ------------------------------------------------------------------------- process
-extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, int n_chunks, int chunk_len,
-                                   int64_t chunk_stride, const double *d_freq_off, uint8_t *d_dibits,
-                                   void *d_symbols, int out_stride, int32_t *d_n_dibits, int32_t *d_phase,
-                                   void *stream)
+// process() of a batch; with d_frames the decode() of every chunk follows: fused into the last launch where the chunk
+// fits the one-launch decoder (tb200_process_decode_batch), otherwise as the separate decode path
+static int process_impl(tb200_handle h, const void *d_iq, int dtype, int n_chunks, int chunk_len,
+                        int64_t chunk_stride, const double *d_freq_off, uint8_t *d_dibits,
+                        void *d_symbols, int out_stride, int32_t *d_n_dibits, int32_t *d_phase,
+                        tb200_frame *d_frames, int max_frames, int32_t *d_n_frames, int64_t *d_stats, void *stream)
 {
     DevGuard dev_guard(h);
     if (!h || !d_n_dibits || n_chunks < 0 || chunk_len < 0) return fail(TB200_E_ARG, "tb200_process_batch: bad argument");
@@ -378,9 +380,43 @@ extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, 
                                       h->chan_fwd, h->filtered, P.n_dec, st);
     }
     if (rc) return rc;
-    StageTimer tm(h, TB_STAGE_SYMBOLS, st);
-    return launch_symbols(h, h->filtered, n_chunks, P.n_dec, P.n_dec, P.sps, P.phase_step, (double *)d_symbols, d_dibits,
-                          out_stride, d_n_dibits, nullptr, d_phase, st, ph_partial, ph_tail, ph_tiles);
+    if (d_frames && out_stride <= 6000 && max_frames <= 64) {
+        StageTimer tm(h, TB_STAGE_SYMBOLS, st);            // timing pick + slicer + decode in one launch
+        return launch_tail_fused(h, h->filtered, n_chunks, P.n_dec, P.n_dec, P.sps, P.phase_step, (double *)d_symbols, d_dibits,
+                                 out_stride, d_n_dibits, d_phase, ph_partial, ph_tail, ph_tiles, d_frames, max_frames, d_n_frames,
+                                 d_stats, st);
+    }
+    {
+        StageTimer tm(h, TB_STAGE_SYMBOLS, st);
+        rc = launch_symbols(h, h->filtered, n_chunks, P.n_dec, P.n_dec, P.sps, P.phase_step, (double *)d_symbols, d_dibits,
+                            out_stride, d_n_dibits, nullptr, d_phase, st, ph_partial, ph_tail, ph_tiles);
+    }
+    if (rc || !d_frames) return rc;
+    return tb200_decode_batch(h, d_dibits, n_chunks, out_stride, d_n_dibits, d_frames, max_frames, d_n_frames, d_stats, stream);
+}
+
+extern "C" int tb200_process_batch(tb200_handle h, const void *d_iq, int dtype, int n_chunks, int chunk_len,
+                                   int64_t chunk_stride, const double *d_freq_off, uint8_t *d_dibits,
+                                   void *d_symbols, int out_stride, int32_t *d_n_dibits, int32_t *d_phase,
+                                   void *stream)
+{
+    return process_impl(h, d_iq, dtype, n_chunks, chunk_len, chunk_stride, d_freq_off, d_dibits, d_symbols, out_stride, d_n_dibits,
+                        d_phase, nullptr, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int tb200_process_decode_batch(tb200_handle h, const void *d_iq, int dtype, int n_chunks, int chunk_len,
+                                          int64_t chunk_stride, const double *d_freq_off, uint8_t *d_dibits,
+                                          void *d_symbols, int out_stride, int32_t *d_n_dibits, int32_t *d_phase,
+                                          tb200_frame *d_frames, int max_frames, int32_t *d_n_frames, int64_t *d_stats,
+                                          void *stream)
+{
+    if (!d_frames || !d_n_frames || max_frames <= 0) return fail(TB200_E_ARG, "tb200_process_decode_batch: bad argument");
+    if (n_chunks > 0 && chunk_len == 0) {
+        cudaError_t e = cudaMemsetAsync(d_n_frames, 0, sizeof(int32_t) * n_chunks, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(TB200_E_CUDA, "tb200_process_decode_batch: %s", cudaGetErrorString(e));
+    }
+    return process_impl(h, d_iq, dtype, n_chunks, chunk_len, chunk_stride, d_freq_off, d_dibits, d_symbols, out_stride, d_n_dibits,
+                        d_phase, d_frames, max_frames, d_n_frames, d_stats, stream);
 }
 
 extern "C" int tb200_process_batch_host(tb200_handle h, const void *h_iq, int dtype, int n_chunks, int chunk_len,

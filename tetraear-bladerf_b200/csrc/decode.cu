@@ -12,6 +12,7 @@
 #include <mutex>
 #include "common.h"
 #include "kernels.h"
+#include "symbols_dev.h"
 
 namespace tb200 {
 
@@ -787,18 +788,16 @@ __global__ void decode_kernel(const uint8_t *__restrict__ bits, const uint8_t *_
 
 // Fused variant for short streams (one chunk of process() output): symbols_to_bits, both 22-bit
 // correlations and decode() in ONE launch, every intermediate in shared memory.  One CTA per stream.
-__global__ void __launch_bounds__(128)
-decode_fused_kernel(const uint8_t *__restrict__ dibits, int n_streams, long stride, const int32_t *__restrict__ n_sym,
-                    tb200_frame *__restrict__ frames, int max_frames, int32_t *__restrict__ n_frames,
-                    unsigned long long *__restrict__ stats)
+__device__ __forceinline__ void decode_fused_body(int s, const uint8_t *__restrict__ dibits, long stride, int n_sym_s,
+                                                  tb200_frame *__restrict__ frames, int max_frames, int32_t *__restrict__ n_frames,
+                                                  unsigned long long *__restrict__ stats)
 {
     extern __shared__ uint8_t dsm[];
     __shared__ uint16_t tab[512];
     __shared__ uint16_t initv[512];
     __shared__ int s_max;
     __shared__ int32_t pos_sm[64];
-    const int s = blockIdx.x;
-    const long n = min(max((long)n_sym[s], 0L), stride);      // clamp: the shared buffers hold `stride` dibits
+    const long n = min(max((long)n_sym_s, 0L), stride);       // clamp: the shared buffers hold `stride` dibits
     uint8_t *mp = dsm;                       // [stride]
     uint8_t *b = mp + stride;                // [2 stride]
     uint8_t *c1 = b + 2 * stride;            // [2 stride]
@@ -850,6 +849,32 @@ decode_fused_kernel(const uint8_t *__restrict__ dibits, int n_streams, long stri
     if (threadIdx.x < 32)
         decode_stream_warp(b, mp, c1, c2, n, tab, initv, frames + (long)s * max_frames, max_frames < 64 ? max_frames : 64,
                            n_frames + s, stats, pos_sm);
+}
+
+__global__ void __launch_bounds__(128)
+decode_fused_kernel(const uint8_t *__restrict__ dibits, int n_streams, long stride, const int32_t *__restrict__ n_sym,
+                    tb200_frame *__restrict__ frames, int max_frames, int32_t *__restrict__ n_frames,
+                    unsigned long long *__restrict__ stats)
+{
+    (void)n_streams;
+    decode_fused_body(blockIdx.x, dibits, stride, n_sym[blockIdx.x], frames, max_frames, n_frames, stats);
+}
+
+// The whole tail of process() + decode() for one chunk in ONE launch: timing pick, symbols and
+// dibits (symbols_dev.h), then — same CTA, the dibits it just wrote — bits, both correlations, find_sync cascade and
+// the frame records.  One CTA of 256 threads per chunk.
+__global__ void __launch_bounds__(256)
+tail_fused_kernel(const double *__restrict__ filtered, long n, long in_stride, int sps, int step, double *__restrict__ symbols,
+                  uint8_t *__restrict__ dibits, long out_stride, int32_t *__restrict__ n_dibits, int32_t *__restrict__ phase_out,
+                  const double *__restrict__ phase_partial, const double *__restrict__ phase_tail, int n_tiles,
+                  tb200_frame *__restrict__ frames, int max_frames, int32_t *__restrict__ n_frames,
+                  unsigned long long *__restrict__ stats)
+{
+    const int chunk = blockIdx.x;
+    symbols_body(chunk, filtered, n, in_stride, sps, step, symbols, dibits, out_stride, n_dibits, nullptr, phase_out,
+                 phase_partial, phase_tail, n_tiles);
+    __syncthreads();                                   // the chunk's dibits and their count were written by this CTA
+    decode_fused_body(chunk, dibits, out_stride, n_dibits[chunk], frames, max_frames, n_frames, stats);
 }
 
 // _calculate_crc16 of bit rows (one byte per bit), one warp per row
@@ -921,6 +946,20 @@ int launch_decode_fused(tb200_handle h, const uint8_t *dibits, int n_streams, lo
     size_t smem = ((7 * (size_t)stride + 3) & ~(size_t)3) + 4 * ((2 * (size_t)stride + 31) / 32 + 2);      // + packed bits
     decode_fused_kernel<<<n_streams, 128, smem, st>>>(dibits, n_streams, stride, n_sym, frames, max_frames, n_frames,
                                                      (unsigned long long *)stats);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+int launch_tail_fused(tb200_handle h, const double *filtered, int n_chunks, long n, long in_stride, int sps, int phase_step,
+                      double *symbols, uint8_t *dibits, long out_stride, int32_t *n_dibits, int32_t *phase,
+                      const double *phase_partial, const double *phase_tail, int n_tiles, tb200_frame *frames, int max_frames,
+                      int32_t *n_frames, int64_t *stats, cudaStream_t st)
+{
+    if (n_chunks <= 0) return TB200_OK;
+    size_t smem = ((7 * (size_t)out_stride + 3) & ~(size_t)3) + 4 * ((2 * (size_t)out_stride + 31) / 32 + 2);
+    tail_fused_kernel<<<n_chunks, 256, smem, st>>>(filtered, n, in_stride, sps, phase_step, symbols, dibits, out_stride, n_dibits,
+                                                   phase, phase_partial, phase_tail, n_tiles, frames, max_frames, n_frames,
+                                                   (unsigned long long *)stats);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
 }

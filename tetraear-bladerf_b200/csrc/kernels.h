@@ -24,6 +24,10 @@ int launch_find_sync(tb200_handle h, const uint8_t *m1, const uint8_t *m2, int n
 int launch_decode(tb200_handle h, const uint8_t *bits, const uint8_t *mapped, const uint8_t *m1, const uint8_t *m2,
                   int n_streams, long bits_stride, const int32_t *n_sym, tb200_frame *frames, int max_frames,
                   int32_t *n_frames, int64_t *stats, cudaStream_t st);
+int launch_tail_fused(tb200_handle h, const double *filtered, int n_chunks, long n, long in_stride, int sps, int phase_step,
+                      double *symbols, uint8_t *dibits, long out_stride, int32_t *n_dibits, int32_t *phase,
+                      const double *phase_partial, const double *phase_tail, int n_tiles, tb200_frame *frames, int max_frames,
+                      int32_t *n_frames, int64_t *stats, cudaStream_t st);
 int launch_decode_fused(tb200_handle h, const uint8_t *dibits, int n_streams, long stride, const int32_t *n_sym,
                         tb200_frame *frames, int max_frames, int32_t *n_frames, int64_t *stats, cudaStream_t st);
 int launch_burst_batch(tb200_handle h, const uint8_t *dibits, int64_t n, uint8_t *rec, uint8_t *full,

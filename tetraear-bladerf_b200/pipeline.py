@@ -145,12 +145,20 @@ class ReceivePipeline:
         sc16 = iq.dtype == torch.int16
         esz = self.chunk_len * (4 if sc16 else 8)
         sym_ptr = self.symbols.data_ptr() + lo * self.stride * 16 if self.symbols is not None else None
+        if decode:
+            # process + decode as one call: the tail (timing pick, slicer, sync search, frame records) is one launch
+            fsz = self.max_frames * _lib.FRAME_DTYPE.itemsize
+            _lib.check(lib.tb200_process_decode_batch(
+                h, iq.data_ptr() + lo * esz, _lib.DTYPE_SC16 if sc16 else _lib.DTYPE_C64, n, self.chunk_len, self.chunk_len,
+                freq_off.data_ptr() + lo * 8 if freq_off is not None else None, self.dibits.data_ptr() + lo * self.stride,
+                sym_ptr, self.stride, self.n_dibits.data_ptr() + lo * 4, self.phase.data_ptr() + lo * 4,
+                self.frames.data_ptr() + lo * fsz, self.max_frames, self.n_frames.data_ptr() + lo * 4,
+                self.stats.data_ptr(), stream))
+            return
         _lib.check(lib.tb200_process_batch(
             h, iq.data_ptr() + lo * esz, _lib.DTYPE_SC16 if sc16 else _lib.DTYPE_C64, n, self.chunk_len, self.chunk_len,
             freq_off.data_ptr() + lo * 8 if freq_off is not None else None, self.dibits.data_ptr() + lo * self.stride,
             sym_ptr, self.stride, self.n_dibits.data_ptr() + lo * 4, self.phase.data_ptr() + lo * 4, stream))
-        if decode:
-            self._decode_slice(handle, stream, lo, hi)
 
     def _decode_slice(self, handle, stream, lo, hi):
         fsz = self.max_frames * _lib.FRAME_DTYPE.itemsize
