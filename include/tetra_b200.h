@@ -231,10 +231,30 @@ int tb200_crc16_rows(tb200_handle h, const uint8_t *d_bits, int n_rows, int n_bi
  * NOT in the reference (core/protocol.py:300 "we do not do full channel decoding"): parity unpinned,
  * validated by encode -> decode round trips (tests/test_etsi_*.py).
  * d_soft [n][K3] int8 soft type-5 bits (+ = 1); channel 0 SCH/HD (124->216), 1 SCH/F (268->432),
- * 2 BSCH (60->120); scramb_init = ((colour | mnc<<6 | mcc<<20) << 2) | 3.
- * d_bits [n][40]: decoded type-1 bits packed MSB-first; d_crc_ok [n]; d_metric [n] final path metric. */
+ * 2 BSCH (60->120), 3 SCH/HU (92->168), all RCPC rate 2/3 with the 16-bit CRC; 4 TCH/4.8 (288->432, rate 292/432),
+ * 5 TCH/2.4 (144->432, rate 148/432), both without a block code and with interleaving over N = 1 block;
+ * scramb_init = ((colour | mnc<<6 | mcc<<20) << 2) | 3.
+ * d_bits [n][40]: decoded type-1 bits packed MSB-first; d_crc_ok [n] (1 pass, 0 fail, 2 = the channel has no CRC);
+ * d_metric [n] final path metric. */
 int tb200_etsi_decode_batch(tb200_handle h, const int8_t *d_soft, int64_t n, int channel, uint32_t scramb_init,
                             uint8_t *d_bits, uint8_t *d_crc_ok, int32_t *d_metric, void *stream);
+
+/* AACH (cl. 8.2.3.2): soft maximum-likelihood decoding of a (30, 14) block code over all 16 384 codewords.
+ * d_soft [n][30] int8 soft type-5 bits; gen_rows: HOST array of the 14 generator rows, code bit j (first sent = 0) in word
+ * bit 29 - j, row k belongs to information bit k + 1; d_bits [n] uint16: the 14 information bits, bit 1 = MSB (bit 13);
+ * d_metric [n] the winning correlation, d_margin [n] (or NULL) its distance to the runner-up.  Ties go to the smaller
+ * information word.  The standard's own generator matrix is NOT reproduced in this repository (no copy of EN 300 392-2
+ * is available to it): tetraear_b200.etsi.rm3014_generator() builds a systematic shortened RM(2,5) of the same
+ * parameters (30, 14, d = 8); pass the matrix of cl. 8.2.3.2 here for on-air signals. */
+int tb200_etsi_aach_decode(tb200_handle h, const int8_t *d_soft, int64_t n, const uint32_t *gen_rows, uint32_t scramb_init,
+                           uint16_t *d_bits, int32_t *d_metric, int32_t *d_margin, void *stream);
+
+/* The same decoder for any block geometry: k2 = k1 + (crc ? 16 : 0) + 4 tail bits, k3 <= 432 type-3 bits, block
+ * interleaver (k3, a), k2 <= 320; rate 0 = 2/3, 1 = 1/3, 2 = 292/432, 3 = 148/432 (EN 300 392-2 cl. 8.2.3.1.3-8.2.3.1.6:
+ * type-3 bit j is mother bit 8 ((i-1) div t) + P(i - t ((i-1) div t)), i = j + (j-1) div {65, 35} for the last two). */
+int tb200_etsi_decode_custom(tb200_handle h, const int8_t *d_soft, int64_t n, int k1, int k2, int k3, int a, int rate,
+                             int crc, uint32_t scramb_init, uint8_t *d_bits, uint8_t *d_crc_ok, int32_t *d_metric,
+                             void *stream);
 
 /* `etsi` mode polyphase FIR channelizer (parity unpinned, SURVEY.md G1/G9: the reference has none):
  * wideband complex64 at fs = n_channels x 25 kHz -> n_channels rows at 50 kHz (2x oversampled);
@@ -270,6 +290,16 @@ int tb200_etsi_demod_segmented(tb200_handle h, const void *d_iq_c64, int n_strea
 int tb200_etsi_find_bursts(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,
                            const int32_t *d_n_soft, double threshold, float *d_metric, int8_t *d_blocks,
                            int32_t *d_burst_pos, int32_t *d_n_bursts, int max_bursts, void *stream);
+/* Search for any training sequence of EN 300 392-2 cl. 9.4.4.3 in the demodulator's soft bits: sequence 0 = normal n,
+ * 1 = normal p, 2 = tail q (22 bits; in a continuous downlink q(1..10) closes a burst and q(11..22) opens the next: a hit
+ * at bit p puts the slot boundary at p + 10), 3 = extended x (30 bits, uplink control bursts), 4 = synchronisation y (38).
+ * Metric = clipped soft correlation / sum |soft| at every symbol position (d_metric [n_streams][soft_stride / 2],
+ * scratch + output); a hit is the first position >= threshold refined to the maximum of the next 4 positions, after which
+ * min_gap_symbols positions are skipped.  d_pos / d_corr [n_streams][max_hits]: bit offset and metric of each hit. */
+int tb200_etsi_find_sequence(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,
+                             const int32_t *d_n_soft, int sequence, double threshold, int min_gap_symbols,
+                             float *d_metric, int32_t *d_pos, float *d_corr, int32_t *d_n_hits, int max_hits, void *stream);
+
 /* feed-forward carrier-offset correction of the soft bits in place: theta = (arg sum d^4 - pi) / 4 over each stream's
  * differential symbols d (unambiguous for |df| < 2250 Hz), every soft pair rotated by -theta; d_theta [n_streams]
  * (radians per symbol; df = theta * 18000 / 2 pi) or NULL.  Run between tb200_etsi_demod_batch and the searches. */

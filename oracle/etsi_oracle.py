@@ -1,7 +1,7 @@
 """CPU restatement of the ETSI EN 300 392-2 clause-8 channel DEcoder (TEST INFRASTRUCTURE).
 
 PARITY UNPINNED: the reference implements none of this (core/protocol.py:300); the algorithm is
-the published one (descrambling LFSR, block de-interleaver (K, a), RCPC rate-2/3 de-puncturing
+the published one (descrambling LFSR, block de-interleaver (K, a), RCPC de-puncturing (rates 2/3, 1/3, 292/432, 148/432)
 of the 16-state rate-1/4 mother code, Viterbi, CRC-16 with complemented parity).  This file pins
 the CUDA decoder bit for bit (integer metrics, same tie rule: keep the lower predecessor unless
 the upper one is strictly better) and is itself validated by encode -> decode round trips against
@@ -9,7 +9,13 @@ the encoder in tetraear_b200.etsi.
 """
 import numpy as np
 
-CHANNELS = {"SCH/HD": (124, 144, 216, 101), "SCH/F": (268, 288, 432, 103), "BSCH": (60, 80, 120, 11)}
+# logical channel -> (K1 type-1 bits, K2 type-2 bits, K3 type-3 bits, interleaver a, RCPC rate, 16-bit CRC present)
+CHANNELS = {"SCH/HD": (124, 144, 216, 101, "2/3", True), "SCH/F": (268, 288, 432, 103, "2/3", True),
+            "BSCH": (60, 80, 120, 11, "2/3", True), "SCH/HU": (92, 112, 168, 13, "2/3", True),
+            "TCH/4.8": (288, 292, 432, 103, "292/432", False), "TCH/2.4": (144, 148, 432, 103, "148/432", False)}
+# RCPC puncturing (EN 300 392-2 cl. 8.2.3.1.3-8.2.3.1.6): rate -> (P(1..t), t, divisor of the i(j) = j + (j-1) div d rule)
+PUNCTURERS = {"2/3": ((1, 2, 5), 3, 0), "1/3": ((1, 2, 3, 5, 6, 7), 6, 0),
+              "292/432": ((1, 2, 5), 3, 65), "148/432": ((1, 2, 3, 5, 6, 7), 6, 35)}
 GENERATORS = ((1, 1, 0, 0, 1), (1, 0, 1, 1, 1), (1, 1, 1, 0, 1), (1, 1, 0, 1, 1))
 
 
@@ -37,20 +43,36 @@ def _branch_outputs():
     return out
 
 
+def puncture_map(rate, K3):
+    """0-based index into the mother-code output V(1..4 K2) of the type-3 bit j = 1..K3 (cl. 8.2.3.1.2):
+    k = 8 ((i-1) div t) + P(i - t ((i-1) div t)), i = j for rates 2/3 and 1/3, i = j + (j-1) div 65 for
+    rate 292/432 and i = j + (j-1) div 35 for rate 148/432."""
+    P, t, div = PUNCTURERS[rate]
+    j = np.arange(1, K3 + 1)
+    i = j + (j - 1) // div if div else j
+    blk = (i - 1) // t
+    return 8 * blk + np.asarray(P)[i - t * blk - 1] - 1
+
+
 def decode(soft, channel="SCH/HD", scramb_init=3):
     """int8 soft type-5 values [n, K3] (+ = 1) -> (type-1 bits [n, K1], crc_ok [n], metric [n])."""
-    K1, K2, K3, a = CHANNELS[channel]
+    return decode_custom(soft, *CHANNELS[channel], scramb_init=scramb_init)
+
+
+def decode_custom(soft, K1, K2, K3, a, rate="2/3", crc=True, scramb_init=3):
+    """The same for any block geometry: K2 = K1 (+ 16 CRC bits) + 4 tail bits, K3 type-3 bits of the given rate."""
     s = np.asarray(soft, dtype=np.int32).reshape(-1, K3)
     n = s.shape[0]
     sign = 1 - 2 * scrambling_sequence(scramb_init, K3).astype(np.int32)
     t4 = s * sign[None, :]
     k_of_i = (a * np.arange(1, K3 + 1)) % K3
     t3 = t4[:, k_of_i]
-    # de-puncture: step 2m gets (g1, g2) = t3[3m], t3[3m+1]; step 2m+1 gets g1 = t3[3m+2]
-    mother = np.zeros((n, K2, 4), np.int32)
-    mother[:, 0::2, 0] = t3[:, 0::3]
-    mother[:, 0::2, 1] = t3[:, 1::3]
-    mother[:, 1::2, 0] = t3[:, 2::3]
+    # de-puncture: punctured mother bits count as erasures (0)
+    kidx = puncture_map(rate, K3)
+    assert kidx.max() < 4 * K2 and len(set(kidx.tolist())) == K3
+    flat = np.zeros((n, K2 * 4), np.int32)
+    flat[:, kidx] = t3
+    mother = flat.reshape(n, K2, 4)
     outs = 2 * _branch_outputs() - 1                                          # +-1
     NEG = -(1 << 28)
     pm = np.full((n, 16), NEG, np.int64)
@@ -77,6 +99,8 @@ def decode(soft, channel="SCH/HD", scramb_init=3):
         d = dec[rows, t, state]
         state = (state >> 1) | (d.astype(np.int64) << 3)
     t1 = bits[:, :K1]
+    if not crc:
+        return t1, np.ones(n, bool), metric
     crc = np.full(n, 0xFFFF, np.uint32)
     for i in range(K1):
         fb = (t1[:, i].astype(np.uint32) ^ (crc >> 15)) & 1
@@ -86,3 +110,18 @@ def decode(soft, channel="SCH/HD", scramb_init=3):
     for i in range(16):
         rx = (rx << 1) | bits[:, K1 + i]
     return t1, (crc == rx), metric
+
+
+def aach_decode(soft, generator, scramb_init=3):
+    """Brute-force soft ML decoding of a (30, 14) block code (AACH, cl. 8.2.3.2): int8 [n, 30] -> (bits [n, 14],
+    correlation [n], margin to the runner-up [n]).  Ties go to the smaller information word (bit 1 = MSB).  The
+    generator [14, 30] is a parameter — see tetraear_b200.etsi.rm3014_generator for what the tests use."""
+    G = np.asarray(generator, np.int64).reshape(14, 30)
+    s = np.asarray(soft, np.int64).reshape(-1, 30) * (1 - 2 * scrambling_sequence(scramb_init, 30).astype(np.int64))[None, :]
+    c = np.arange(1 << 14)
+    info = (c[:, None] >> np.arange(13, -1, -1)[None, :]) & 1
+    pm = 2 * ((info @ G) & 1) - 1                                              # [16384, 30] +-1
+    corr = s @ pm.T
+    best = corr.argmax(axis=1)                                                 # first maximum = smallest word
+    top2 = np.partition(corr, -2, axis=1)[:, -2:]
+    return info[best].astype(np.uint8), top2[:, 1].astype(np.int32), (top2[:, 1] - top2[:, 0]).astype(np.int32)

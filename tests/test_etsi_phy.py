@@ -167,3 +167,48 @@ def test_segmented_demodulator_matches_the_sequential_loop(fs, sigma, rate_ppm):
         good0 = sum(bool(v["crc_ok"].all()) for v in res0[s])
         good1 = sum(bool(v["crc_ok"].all()) for v in res1[s])
         assert good1 >= good0 - 1 and good1 >= n_bursts - 5, (s, good0, good1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fs,sigma", [(72000.0, 0.0), (50000.0, 0.08)])
+def test_training_sequence_search_all_sequences(fs, sigma):
+    """tb200_etsi_find_sequence: every training sequence of cl. 9.4.4.3 is found where the modulator put it — the tail
+    sequence q across every slot boundary (q(1..10) of one burst + q(11..22) of the next), normal n / p in the middle of
+    their bursts (bit 244), the sync sequence y (bit 214) and an extended sequence x planted in one block."""
+    import __graft_entry__ as entry
+    entry.build()
+    n_bursts = 20
+    bits, t1, init = etsi.make_etsi_stream(n_bursts, seed=5, sync_every=7)
+    bits_p, _, _ = etsi.make_etsi_stream(n_bursts, seed=6, ts=etsi.TS_P)
+    x_at = 510 * 9 + 60                                              # inside BKN1 of burst 9, on a symbol boundary
+    bits_p = bits_p.copy()
+    bits_p[x_at:x_at + 30] = etsi.TS_X
+    xs = [etsi.modulate_dqpsk(b, fs, sigma=sigma, t_offset=0.2 * i, seed=i) for i, b in enumerate((bits, bits_p))]
+    n = min(len(v) for v in xs)
+    rx = etsi.EtsiReceiver(fs, max_streams=2, max_samples=n)
+    rx.run(np.stack([v[:n] for v in xs]), init)                     # demodulates; soft bits stay on the device
+    lock = 2 * 510                                                   # the timing loop may need a burst or two
+
+    def near(hits, want, tol=4):
+        got = np.array([p for p, c in hits])
+        return [w for w in want if len(got) and np.abs(got - w).min() <= tol]
+
+    q_hits = rx.find_sequence(2, "q", threshold=0.8)
+    for s in range(2):
+        want = [510 * k - 10 for k in range(1, n_bursts) if 510 * k > lock]
+        assert len(near(q_hits[s], want)) >= len(want) - 1, (s, q_hits[s])
+        assert all(c <= 1.0 + 1e-5 for p, c in q_hits[s])
+    n_hits = rx.find_sequence(2, "n", threshold=0.8)
+    want_n = [510 * k + 244 for k in range(n_bursts) if k % 7 and 510 * k > lock]
+    assert len(near(n_hits[0], want_n)) >= len(want_n) - 1
+    assert not near(n_hits[1], [510 * k + 244 for k in range(n_bursts)])          # stream 1 carries p, not n
+    p_hits = rx.find_sequence(2, "p", threshold=0.8)
+    want_p = [510 * k + 244 for k in range(n_bursts) if 510 * k > lock]
+    assert len(near(p_hits[1], want_p)) >= len(want_p) - 1 and not near(p_hits[0], want_n)
+    y_hits = rx.find_sequence(2, "y", threshold=0.8)
+    want_y = [510 * k + 214 for k in range(0, n_bursts, 7) if 510 * k > lock]
+    assert near(y_hits[0], want_y) == want_y and len(y_hits[1]) == 0
+    x_hits = rx.find_sequence(2, "x", threshold=0.85, min_gap_symbols=20)
+    assert near(x_hits[1], [x_at]) == [x_at]
+    # x = n(12..22) n(1..19): it also lights up at every normal sequence n, 11 bits early, with partial correlation only
+    assert all(c < 0.85 or abs(p - x_at) <= 4 for p, c in x_hits[1])

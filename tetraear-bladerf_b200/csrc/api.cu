@@ -666,6 +666,28 @@ extern "C" int tb200_etsi_decode_batch(tb200_handle h, const int8_t *d_soft, int
     return launch_etsi_decode(h, d_soft, n, channel, scramb_init, d_bits, d_crc_ok, d_metric, (cudaStream_t)stream);
 }
 
+extern "C" int tb200_etsi_aach_decode(tb200_handle h, const int8_t *d_soft, int64_t n, const uint32_t *gen_rows, uint32_t scramb_init,
+                                      uint16_t *d_bits, int32_t *d_metric, int32_t *d_margin, void *stream)
+{
+    DevGuard dev_guard(h);
+    if (!h || n < 0 || !gen_rows || (n && (!d_soft || !d_bits || !d_metric)))
+        return fail(TB200_E_ARG, "tb200_etsi_aach_decode: bad argument");
+    StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
+    return launch_etsi_aach(h, d_soft, n, gen_rows, scramb_init, d_bits, d_metric, d_margin, (cudaStream_t)stream);
+}
+
+extern "C" int tb200_etsi_decode_custom(tb200_handle h, const int8_t *d_soft, int64_t n, int k1, int k2, int k3, int a, int rate,
+                                        int crc, uint32_t scramb_init, uint8_t *d_bits, uint8_t *d_crc_ok, int32_t *d_metric,
+                                        void *stream)
+{
+    DevGuard dev_guard(h);
+    if (!h || n < 0 || (n && (!d_soft || !d_bits || !d_crc_ok || !d_metric)))
+        return fail(TB200_E_ARG, "tb200_etsi_decode_custom: bad argument");
+    StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
+    return launch_etsi_decode_custom(h, d_soft, n, k1, k2, k3, a, rate, crc, scramb_init, d_bits, d_crc_ok, d_metric,
+                                     (cudaStream_t)stream);
+}
+
 extern "C" int tb200_etsi_demod_batch(tb200_handle h, const void *d_iq_c64, int n_streams, int64_t n_samples, int64_t stride,
                                       double fs, void *d_sym_c64, float *d_soft, int64_t soft_stride, int32_t *d_n_soft,
                                       void *stream)
@@ -706,6 +728,20 @@ extern "C" int tb200_etsi_find_bursts(tb200_handle h, const float *d_soft, int n
     StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
     return launch_etsi_find_bursts(h, d_soft, n_streams, soft_stride, d_n_soft, (float)threshold, d_metric, d_blocks, d_burst_pos,
                                    d_n_bursts, max_bursts, (cudaStream_t)stream);
+}
+
+extern "C" int tb200_etsi_find_sequence(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,
+                                        const int32_t *d_n_soft, int sequence, double threshold, int min_gap_symbols,
+                                        float *d_metric, int32_t *d_pos, float *d_corr, int32_t *d_n_hits, int max_hits,
+                                        void *stream)
+{
+    DevGuard dev_guard(h);
+    if (!h || n_streams < 0 || !d_soft || !d_n_soft || !d_metric || !d_pos || !d_corr || !d_n_hits || max_hits <= 0 ||
+        sequence < 0 || sequence > 4 || soft_stride < 2)
+        return fail(TB200_E_ARG, "tb200_etsi_find_sequence: bad argument");
+    StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
+    return launch_etsi_find_sequence(h, d_soft, n_streams, soft_stride, d_n_soft, sequence, (float)threshold, min_gap_symbols,
+                                     d_metric, d_pos, d_corr, d_n_hits, max_hits, (cudaStream_t)stream);
 }
 
 extern "C" int tb200_etsi_afc(tb200_handle h, float *d_soft, int n_streams, int64_t soft_stride, const int32_t *d_n_soft,

@@ -1,5 +1,5 @@
 // etsi_codec.cu — `etsi` mode channel decoder over batches of bursts: descrambling, block
-// de-interleaving (K, a), RCPC rate-2/3 de-puncturing, 16-state Viterbi, CRC-16
+// de-interleaving (K, a), RCPC de-puncturing (rate 2/3 specialised; 1/3, 292/432, 148/432 general), 16-state Viterbi, CRC-16
 // (ETSI EN 300 392-2 clause 8).  The reference has no implementation of this stage
 // (/root/reference/tetraear/core/protocol.py:300: "we do not do full channel decoding"), so
 // parity is unpinned; the kernel is checked bit for bit against oracle/etsi_oracle.py and by
@@ -13,6 +13,7 @@
 // DE-INTERLEAVED ([position][thread], pitch THREADS+4 bytes: conflict-free both ways), and keeps the survivor
 // decisions there as one uint16 per (step, thread).  No shuffles, no inter-thread traffic: ~110 instructions per
 // trellis step per block instead of ~320 lane-instructions with the former 16-lanes-per-block mapping.
+#include <vector>
 #include "common.h"
 #include "kernels.h"
 
@@ -147,6 +148,133 @@ etsi_decode_kernel(const int8_t *__restrict__ soft, long n, EtsiParams P, uint8_
     metric[burst] = final_metric;
 }
 
+
+// ---- general form: any RCPC rate of cl. 8.2.3.1 (1/3, 292/432, 148/432 — and 2/3 for block sizes without a
+// specialised instantiation).  None of the standard's puncturing tables ever keeps the fourth mother bit, so a trellis
+// step has three inputs (g1, g2, g3); punctured positions are erasures (0), which the load phase leaves in the
+// zero-filled array.  Otherwise the same mapping: one thread per block, metrics in registers, inputs and survivor
+// words in shared memory.
+struct EtsiGenParams {
+    uint32_t scr[14];      // scrambling sequence bits
+    uint16_t slot[432];    // received position k -> trellis input slot 3 * step + g
+    int K1, K2, K3, crc;
+};
+
+__host__ __device__ constexpr int etsi_c3(int ns) { return ((ns & 1) ^ ((ns >> 1) & 1) ^ ((ns >> 2) & 1) ^ ((ns >> 4) & 1)) ? 1 : -1; }
+
+__device__ __forceinline__ uint32_t acs_step3(int (&pm)[16], int v1, int v2, int v3)
+{
+    const int a = v1 + v2, b = v1 - v2;
+    const int s0 = a + v3, s1 = a - v3, s2 = b + v3, s3 = b - v3;       // v1 + c2 v2 + c3 v3 for (c2, c3) = ++, +-, -+, --
+    int np[16];
+    uint32_t word = 0;
+#pragma unroll
+    for (int ns = 0; ns < 16; ++ns) {
+        const int c1 = etsi_c1(ns), c2 = etsi_c2(ns) * c1, c3 = etsi_c3(ns) * c1;     // relative to c1
+        const int mag = (c2 > 0) ? (c3 > 0 ? s0 : s1) : (c3 > 0 ? s2 : s3);
+        const int bm = (c1 > 0) ? mag : -mag;
+        const int m0 = pm[ns >> 1] + bm, m1 = pm[(ns >> 1) | 8] - bm;
+        const bool take1 = m1 > m0;
+        np[ns] = take1 ? m1 : m0;
+        word |= (take1 ? 1u : 0u) << ns;
+    }
+#pragma unroll
+    for (int ns = 0; ns < 16; ++ns) pm[ns] = np[ns];
+    return word;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+etsi_decode_gen_kernel(const int8_t *__restrict__ soft, long n, EtsiGenParams P, uint8_t *__restrict__ bits_out,
+                       uint8_t *__restrict__ crc_ok, int32_t *__restrict__ metric)
+{
+    constexpr int PITCH = THREADS + 4;
+    extern __shared__ __align__(16) unsigned char etsi_sm[];
+    const int K1 = P.K1, K2 = P.K2, K3 = P.K3;
+    int8_t *T = reinterpret_cast<int8_t *>(etsi_sm);                                    // [3 K2][PITCH]
+    uint16_t *D = reinterpret_cast<uint16_t *>(etsi_sm + ((3 * K2 * PITCH + 15) & ~15));   // [K2][THREADS]
+    __shared__ uint16_t slot_s[432];
+    __shared__ uint32_t scr_s[14];
+    const int tid = threadIdx.x;
+    const long blk0 = (long)blockIdx.x * THREADS;
+    const int nb = (int)((n - blk0 < THREADS) ? (n - blk0) : THREADS);
+    for (int i = tid; i < K3; i += THREADS) slot_s[i] = P.slot[i];
+    if (tid < 14) scr_s[tid] = P.scr[tid];
+    {
+        uint32_t *Tz = reinterpret_cast<uint32_t *>(T);
+        const int nz = (3 * K2 * PITCH + 3) / 4;
+        for (int i = tid; i < nz; i += THREADS) Tz[i] = 0u;
+    }
+    __syncthreads();
+    {
+        const int8_t *src = soft + blk0 * K3;
+        const int tot = nb * K3;
+        int r = tid / K3, k = tid - r * K3;
+        const int DR = THREADS / K3, DK = THREADS - DR * K3;
+        for (int idx = tid; idx < tot; idx += THREADS) {
+            const int v = src[idx];
+            const int pk = (scr_s[k >> 5] >> (k & 31)) & 1;
+            T[(int)slot_s[k] * PITCH + r] = (int8_t)(pk ? -v : v);
+            r += DR; k += DK;
+            if (k >= K3) { k -= K3; ++r; }
+        }
+    }
+    __syncthreads();
+    const long burst = blk0 + tid;
+    if (tid >= nb) return;
+    int pm[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pm[i] = (i == 0) ? 0 : -(1 << 28);
+    const int8_t *tp = T + tid;
+    for (int t = 0; t < K2; ++t) {
+        const int v1 = tp[0], v2 = tp[PITCH], v3 = tp[2 * PITCH];
+        tp += 3 * PITCH;
+        D[t * THREADS + tid] = (uint16_t)acs_step3(pm, v1, v2, v3);
+    }
+    const int final_metric = pm[0];
+    // traceback: decoded bit t = the newest register bit of the state after step t; packed MSB first
+    uint32_t outw[10];
+#pragma unroll
+    for (int w = 0; w < 10; ++w) outw[w] = 0u;
+    int state = 0;
+    for (int t = K2 - 1; t >= 0; --t) {
+        const uint32_t bit = (uint32_t)(state & 1) << (31 - (t & 31));
+        const int w = t >> 5;
+#pragma unroll
+        for (int u = 0; u < 10; ++u) if (u == w) outw[u] |= bit;
+        const int dbit = (D[t * THREADS + tid] >> state) & 1;
+        state = (state >> 1) | (dbit << 3);
+    }
+    uint32_t crc = 0xFFFF, rx = 0;
+    if (P.crc) {
+#pragma unroll
+        for (int w = 0; w < 10; ++w) {
+            for (int j = 0; j < 32; ++j) {
+                const int t = w * 32 + j;
+                if (t >= K1 + 16) break;
+                const uint32_t bit = (outw[w] >> (31 - j)) & 1u;
+                if (t < K1) {
+                    const uint32_t fb = (bit ^ (crc >> 15)) & 1u;
+                    crc = ((crc << 1) & 0xFFFF) ^ (fb ? 0x1021u : 0u);
+                } else {
+                    rx = (rx << 1) | bit;
+                }
+            }
+        }
+        crc = (~crc) & 0xFFFF;
+    }
+    uint32_t *ob = reinterpret_cast<uint32_t *>(bits_out + burst * 40);
+#pragma unroll
+    for (int w = 0; w < 10; ++w) {
+        uint32_t v = outw[w];
+        const int lo = w * 32;
+        if (lo + 32 > K1) v &= (lo >= K1) ? 0u : (0xFFFFFFFFu << (lo + 32 - K1));
+        ob[w] = __byte_perm(v, 0, 0x0123);
+    }
+    crc_ok[burst] = P.crc ? (uint8_t)(crc == rx) : (uint8_t)2;          // 2: the channel has no block code to check
+    metric[burst] = final_metric;
+}
+
 static void scramble_words(uint32_t init, int n, uint32_t *words)
 {
     static const int taps[14] = {32, 26, 23, 22, 16, 12, 11, 10, 8, 7, 5, 4, 2, 1};
@@ -160,11 +288,146 @@ static void scramble_words(uint32_t init, int n, uint32_t *words)
     }
 }
 
+// ---- AACH: (30, 14) shortened second-order Reed-Muller block code (cl. 8.2.3.2), soft maximum-likelihood decoding.
+// One warp per block: lane L correlates the 512 codewords whose five leading information bits spell L, walking the
+// other nine in Gray-code order (one generator row XORed per step — the row index is the same for all lanes, so it is
+// a uniform constant-bank read); the correlation of a codeword is S - 2 * (sum of the soft values where it has a 1),
+// taken from four byte-indexed tables of partial sums the warp builds for its block in shared memory.  The generator is
+// a parameter (14 rows, code bit j in word bit 29 - j): any (30, 14) linear code decodes the same way.
+struct AachParams {
+    uint32_t gen[14];      // gen[k]: row of information bit k + 1 (MSB of the 14-bit result first)
+    uint32_t scr;          // scrambling bits of the 30 positions, bit j = p(j + 1)
+};
+
+__global__ void __launch_bounds__(128)
+etsi_aach_kernel(const int8_t *__restrict__ soft, long n, AachParams P, uint16_t *__restrict__ bits_out,
+                 int32_t *__restrict__ metric, int32_t *__restrict__ margin)
+{
+    __shared__ int16_t W[4][4][256];
+    __shared__ int16_t S[4][32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long blk = (long)blockIdx.x * 4 + w;
+    if (blk >= n) return;
+    int v = 0;
+    if (lane < 30) {
+        v = soft[blk * 30 + lane];
+        if ((P.scr >> lane) & 1u) v = -v;
+    }
+    S[w][lane] = (int16_t)v;                   // S[w][j] = descrambled soft value of code bit j (+ = 1)
+    int tot = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    __syncwarp();
+    for (int e = lane; e < 1024; e += 32) {
+        const int g = e >> 8, val = e & 255;
+        int acc = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int wb = 8 * g + u;          // word bit -> code bit 29 - wb
+            if (wb < 30 && ((val >> u) & 1)) acc += S[w][29 - wb];
+        }
+        W[w][g][val] = (int16_t)acc;
+    }
+    __syncwarp();
+    // lane's base codeword: information bits 1..5 = lane (MSB first) -> rows 0..4
+    uint32_t cw = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) if ((lane >> (4 - k)) & 1) cw ^= P.gen[k];
+    int best = -(1 << 30), second = -(1 << 30), best_c = 0;
+    uint32_t gray = 0;
+    for (int i = 0; i < 512; ++i) {
+        if (i) {
+            const int b = __ffs(i) - 1;        // Gray code: bit b of the low nine flips; low bit b <-> information bit 14 - b
+            gray ^= 1u << b;
+            cw ^= P.gen[13 - b];
+        }
+        // +1 expected where the codeword has a 1: correlation = (sum over ones) - (sum over zeros) = 2 * ones - total
+        const int ones = W[w][0][cw & 255] + W[w][1][(cw >> 8) & 255] + W[w][2][(cw >> 16) & 255] + W[w][3][cw >> 24];
+        const int corr = 2 * ones - tot;
+        const int c = (lane << 9) | (int)gray;
+        if (corr > best || (corr == best && c < best_c)) { second = best; best = corr; best_c = c; }
+        else if (corr > second) second = corr;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o), oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+        const int os = __shfl_xor_sync(0xffffffffu, second, o);
+        if (ob > best || (ob == best && oc < best_c)) { second = max(best, os); best = ob; best_c = oc; }
+        else second = max(second, ob);
+    }
+    if (lane == 0) {
+        bits_out[blk] = (uint16_t)best_c;
+        metric[blk] = best;
+        if (margin) margin[blk] = best - second;
+    }
+}
+
+int launch_etsi_aach(tb200_handle h, const int8_t *soft, long n, const uint32_t *gen_rows, uint32_t scramb_init, uint16_t *bits,
+                     int32_t *metric, int32_t *margin, cudaStream_t st)
+{
+    if (n <= 0) return TB200_OK;
+    AachParams P;
+    uint32_t seen = 0;
+    for (int k = 0; k < 14; ++k) {
+        P.gen[k] = gen_rows[k] & 0x3FFFFFFFu;
+        if (!P.gen[k]) return fail(TB200_E_ARG, "tb200_etsi_aach_decode: generator row %d is zero", k);
+        seen |= P.gen[k];
+    }
+    (void)seen;
+    uint32_t words[14];
+    scramble_words(scramb_init, 30, words);
+    P.scr = words[0] & 0x3FFFFFFFu;
+    etsi_aach_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(soft, n, P, bits, metric, margin);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+// any (K1, K2, K3, a) block with one of the four RCPC rates of cl. 8.2.3.1: rate 0 = 2/3, 1 = 1/3, 2 = 292/432, 3 = 148/432
+int launch_etsi_decode_custom(tb200_handle h, const int8_t *soft, long n, int K1, int K2, int K3, int a, int rate, int crc,
+                              uint32_t scramb_init, uint8_t *bits, uint8_t *crc_ok, int32_t *metric, cudaStream_t st)
+{
+    static const int P23[3] = {1, 2, 5}, P13[6] = {1, 2, 3, 5, 6, 7};
+    if (rate < 0 || rate > 3) return fail(TB200_E_ARG, "tb200_etsi_decode_custom: unknown RCPC rate id %d", rate);
+    if (K1 < 1 || K2 > 320 || K3 < 1 || K3 > 432 || a < 1 || K2 != K1 + (crc ? 16 : 0) + 4)
+        return fail(TB200_E_ARG, "tb200_etsi_decode_custom: unsupported block geometry K1 = %d, K2 = %d, K3 = %d", K1, K2, K3);
+    const int *Pt = (rate == 0 || rate == 2) ? P23 : P13;
+    const int t = (rate == 0 || rate == 2) ? 3 : 6;
+    const int div = rate == 2 ? 65 : rate == 3 ? 35 : 0;
+    EtsiGenParams P;
+    P.K1 = K1; P.K2 = K2; P.K3 = K3; P.crc = crc ? 1 : 0;
+    scramble_words(scramb_init, K3, P.scr);
+    // type-3 bit j (1-based) is mother bit k = 8 ((i-1) div t) + P(i - t ((i-1) div t)), i = j + (j-1) div d;
+    // it was sent at type-4 position 1 + (a j mod K3)
+    std::vector<char> seen((size_t)K3, 0);
+    for (int j = 1; j <= K3; ++j) {
+        const int i = div ? j + (j - 1) / div : j;
+        const int blk = (i - 1) / t;
+        const int k = 8 * blk + Pt[i - t * blk - 1];                     // 1-based mother bit
+        const int step = (k - 1) / 4, g = (k - 1) % 4;
+        if (step >= K2 || g > 2) return fail(TB200_E_ARG, "tb200_etsi_decode_custom: K3 = %d type-3 bits do not fit rate id %d with K2 = %d", K3, rate, K2);
+        const int pos = (int)(((long)a * j) % K3);
+        if (seen[pos]) return fail(TB200_E_ARG, "tb200_etsi_decode_custom: interleaver (%d, %d) is not a permutation", K3, a);
+        seen[pos] = 1;
+        P.slot[pos] = (uint16_t)(3 * step + g);
+    }
+    if ((reinterpret_cast<uintptr_t>(bits) & 3) != 0) return fail(TB200_E_ARG, "tb200_etsi_decode_custom: d_bits must be 4-byte aligned");
+    if (n <= 0) return TB200_OK;
+    constexpr int T = 64;
+    const size_t sm = (size_t)(((3 * K2 * (T + 4) + 15) & ~15) + K2 * T * 2);
+    cudaError_t e = cudaFuncSetAttribute(etsi_decode_gen_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(etsi_decode_gen_kernel): %s", cudaGetErrorString(e));
+    etsi_decode_gen_kernel<T><<<(unsigned)((n + T - 1) / T), T, sm, st>>>(soft, n, P, bits, crc_ok, metric);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
 int launch_etsi_decode(tb200_handle h, const int8_t *soft, long n, int channel, uint32_t scramb_init, uint8_t *bits,
                        uint8_t *crc_ok, int32_t *metric, cudaStream_t st)
 {
-    static const int tab[3][4] = {{124, 144, 216, 101}, {268, 288, 432, 103}, {60, 80, 120, 11}};
-    if (channel < 0 || channel > 2) return fail(TB200_E_ARG, "tb200_etsi_decode_batch: unknown logical channel %d", channel);
+    static const int tab[4][4] = {{124, 144, 216, 101}, {268, 288, 432, 103}, {60, 80, 120, 11}, {92, 112, 168, 13}};
+    if (channel == 4) return launch_etsi_decode_custom(h, soft, n, 288, 292, 432, 103, 2, 0, scramb_init, bits, crc_ok, metric, st);
+    if (channel == 5) return launch_etsi_decode_custom(h, soft, n, 144, 148, 432, 103, 3, 0, scramb_init, bits, crc_ok, metric, st);
+    if (channel < 0 || channel > 5) return fail(TB200_E_ARG, "tb200_etsi_decode_batch: unknown logical channel %d", channel);
     if (n <= 0) return TB200_OK;
     EtsiParams P;
     P.K1 = tab[channel][0]; P.K2 = tab[channel][1]; P.K3 = tab[channel][2]; P.a = tab[channel][3];
@@ -183,6 +446,11 @@ int launch_etsi_decode(tb200_handle h, const int8_t *soft, long n, int channel, 
         const size_t sm = smem_of(288, 432, T);
         e = cudaFuncSetAttribute(etsi_decode_kernel<288, 432, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e == cudaSuccess) etsi_decode_kernel<288, 432, T><<<(unsigned)((n + T - 1) / T), T, sm, st>>>(soft, n, P, bits, crc_ok, metric);
+    } else if (channel == 3) {
+        constexpr int T = 128;
+        const size_t sm = smem_of(112, 168, T);
+        e = cudaFuncSetAttribute(etsi_decode_kernel<112, 168, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e == cudaSuccess) etsi_decode_kernel<112, 168, T><<<(unsigned)((n + T - 1) / T), T, sm, st>>>(soft, n, P, bits, crc_ok, metric);
     } else {
         constexpr int T = 128;
         const size_t sm = smem_of(80, 120, T);

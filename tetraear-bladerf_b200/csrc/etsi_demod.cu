@@ -358,6 +358,70 @@ __global__ void etsi_find_sync_kernel(const float *__restrict__ soft, long soft_
 }
 
 
+// ---- generic training-sequence search (EN 300 392-2 cl. 9.4.4.3): the clipped, normalised soft correlation of the
+// kernels above for ANY of the standard's sequences — normal n and p (22 bits), the tail sequence q (22 bits: a
+// continuous downlink ends every burst with q(1..10) and opens the next with q(11..22), so q marks the slot boundary),
+// the extended sequence x (30 bits, uplink control bursts) and the synchronisation sequence y (38) — returning hit
+// positions instead of extracted blocks.
+__constant__ int8_t c_seq_len[5] = {22, 22, 22, 30, 38};
+__constant__ int8_t c_seq_pm[5][38] = {
+    {1, 1, -1, 1, -1, -1, -1, -1, 1, 1, 1, -1, 1, -1, -1, 1, 1, 1, -1, 1, -1, -1},
+    {-1, 1, 1, 1, 1, -1, 1, -1, -1, 1, -1, -1, -1, -1, 1, 1, -1, 1, 1, 1, 1, -1},
+    {1, -1, 1, 1, -1, 1, 1, 1, -1, -1, -1, -1, -1, 1, 1, -1, 1, -1, 1, 1, -1, 1},
+    {1, -1, -1, 1, 1, 1, -1, 1, -1, -1, -1, -1, 1, 1, 1, -1, 1, -1, -1, 1, 1, 1, -1, 1, -1, -1, -1, -1, 1, 1},
+    {1, 1, -1, -1, -1, -1, -1, 1, 1, -1, -1, 1, 1, 1, -1, -1, 1, 1, 1, -1, 1, -1, -1, 1, 1, 1, -1, -1, -1,
+     -1, -1, 1, 1, -1, -1, 1, 1, 1}};
+
+__global__ void etsi_seq_corr_kernel(const float *__restrict__ soft, long soft_stride, const int32_t *__restrict__ n_soft,
+                                     int seq, float *__restrict__ metric)
+{
+    const int s = blockIdx.y;
+    const long nb = n_soft[s];
+    const int L = c_seq_len[seq];
+    const long p = 2 * (blockIdx.x * (long)blockDim.x + threadIdx.x);
+    if (p + L > nb) return;
+    const float *b = soft + (long)s * soft_stride + p;
+    float c = 0.f, en = 0.f;
+    for (int i = 0; i < L; ++i) { const float v = fminf(fmaxf(b[i], -1.0f), 1.0f); c += v * c_seq_pm[seq][i]; en += fabsf(v); }
+    metric[(long)s * (soft_stride / 2) + p / 2] = c / (en + 1e-20f);
+}
+
+// one warp per stream: first position at or over the threshold, refined to the maximum of the next 4 symbol positions
+// (first wins ties), then `gap` symbols are skipped.  Positions are bit offsets into the stream's soft bits.
+__global__ void etsi_find_seq_kernel(const int32_t *__restrict__ n_soft, const float *__restrict__ metric, long metric_stride,
+                                     int n_streams, int L, float thr, int gap, int32_t *__restrict__ pos, float *__restrict__ corr,
+                                     int32_t *__restrict__ n_hits, int max_hits)
+{
+    const int lane = threadIdx.x & 31;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= n_streams) return;
+    const long nb = n_soft[s];
+    const long npos = (nb >= L) ? (nb - L) / 2 + 1 : 0;
+    const float *m = metric + (long)s * metric_stride;
+    int found = 0;
+    long i = 0;
+    while (i < npos && found < max_hits) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const long p = i + lane + 32 * u; v[u] = (p < npos) ? m[p] : -2.f; }
+        long first = -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const unsigned ball = __ballot_sync(0xffffffffu, v[u] >= thr);
+            if (ball && first < 0) first = i + 32 * u + (__ffs(ball) - 1);
+        }
+        if (first < 0) { i += 256; continue; }
+        long best = first;
+        float bv = m[first];
+        for (int d = 1; d < 4; ++d) if (first + d < npos && m[first + d] > bv) { bv = m[first + d]; best = first + d; }
+        if (lane == 0) { pos[(long)s * max_hits + found] = (int32_t)(2 * best); corr[(long)s * max_hits + found] = bv; }
+        ++found;
+        i = best + (gap > 0 ? gap : 1);
+    }
+    if (lane == 0) n_hits[s] = found;
+}
+
+
 // ---- feed-forward carrier-offset correction on the differential symbols.  The soft pair of symbol k is the
 // normalised d_k = y_k conj(y_(k-1)):  Re d = -soft[2k+1], Im d = -soft[2k].  For pi/4-DQPSK arg d is one of
 // +-pi/4, +-3pi/4 plus theta = 2 pi df T, so d^4 has phase pi + 4 theta whatever the data: theta = (arg sum d^4 - pi) / 4,
@@ -495,6 +559,22 @@ int launch_etsi_find_bursts(tb200_handle h, const float *soft, int n_streams, lo
     int threads = 128, blocks_n = (n_streams * 32 + threads - 1) / threads;
     etsi_find_bursts_kernel<<<blocks_n, threads, 0, st>>>(soft, soft_stride, n_soft, metric, n_streams, thr, blocks, burst_pos,
                                                          n_bursts, max_bursts, 45.0f);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+int launch_etsi_find_sequence(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft, int seq,
+                              float thr, int gap, float *metric, int32_t *pos, float *corr, int32_t *n_hits, int max_hits,
+                              cudaStream_t st)
+{
+    static const int len[5] = {22, 22, 22, 30, 38};
+    if (n_streams <= 0) return TB200_OK;
+    dim3 grid((unsigned)((soft_stride / 2 + 255) / 256), (unsigned)n_streams);
+    etsi_seq_corr_kernel<<<grid, 256, 0, st>>>(soft, soft_stride, n_soft, seq, metric);
+    TB_LAUNCH_CHECK(h);
+    int threads = 128, blocks_n = (n_streams * 32 + threads - 1) / threads;
+    etsi_find_seq_kernel<<<blocks_n, threads, 0, st>>>(n_soft, metric, soft_stride / 2, n_streams, len[seq], thr, gap, pos, corr,
+                                                      n_hits, max_hits);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
 }

@@ -37,6 +37,10 @@ int launch_crc16_rows(tb200_handle h, const uint8_t *bits, int n_rows, int n_bit
 int launch_psd(tb200_handle h, const float *iq, int64_t n_frames, int64_t frame_stride, int n_fft, double fs,
                double alpha, int first, float *power, float *smoothed, double *ema_state, double *stats,
                double *scratch_db, cudaStream_t st, int use_f32 = 0, int avg = 1);
+int launch_etsi_aach(tb200_handle h, const int8_t *soft, long n, const uint32_t *gen_rows, uint32_t scramb_init, uint16_t *bits,
+                     int32_t *metric, int32_t *margin, cudaStream_t st);
+int launch_etsi_decode_custom(tb200_handle h, const int8_t *soft, long n, int K1, int K2, int K3, int a, int rate, int crc,
+                              uint32_t scramb_init, uint8_t *bits, uint8_t *crc_ok, int32_t *metric, cudaStream_t st);
 int launch_etsi_decode(tb200_handle h, const int8_t *soft, long n, int channel, uint32_t scramb_init, uint8_t *bits,
                        uint8_t *crc_ok, int32_t *metric, cudaStream_t st);
 int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, long stride, double fs, float *taps_dev,
@@ -45,6 +49,9 @@ int64_t etsi_demod_scratch_bytes(int n_streams, long n, double fs, int want_symb
 int launch_etsi_find_bursts(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft,
                             float thr, float *metric, int8_t *blocks, int32_t *burst_pos, int32_t *n_bursts, int max_bursts,
                             cudaStream_t st);
+int launch_etsi_find_sequence(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft, int seq,
+                              float thr, int gap, float *metric, int32_t *pos, float *corr, int32_t *n_hits, int max_hits,
+                              cudaStream_t st);
 int launch_etsi_afc(tb200_handle h, float *soft, int n_streams, long soft_stride, const int32_t *n_soft, float *theta, cudaStream_t st);
 int launch_etsi_find_sync(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft, float thr,
                           float *metric, int8_t *sb1, int8_t *bkn2, int32_t *burst_pos, int32_t *n_bursts, int max_bursts,

@@ -13,12 +13,29 @@ import numpy as np
 
 from . import _lib
 
-# logical channels: (K1 type-1 bits, K2 = K1 + 16 CRC + 4 tail, K3 = 3/2 K2, interleaver a)
-CHANNELS = {"SCH/HD": (124, 144, 216, 101), "SCH/F": (268, 288, 432, 103), "BSCH": (60, 80, 120, 11)}
-CHANNEL_IDS = {"SCH/HD": 0, "SCH/F": 1, "BSCH": 2}
+# logical channels: (K1 type-1 bits, K2 = K1 (+ 16 CRC) + 4 tail, K3 type-3 bits, interleaver a)
+CHANNELS = {"SCH/HD": (124, 144, 216, 101), "SCH/F": (268, 288, 432, 103), "BSCH": (60, 80, 120, 11),
+            "SCH/HU": (92, 112, 168, 13), "TCH/4.8": (288, 292, 432, 103), "TCH/2.4": (144, 148, 432, 103)}
+CHANNEL_IDS = {"SCH/HD": 0, "SCH/F": 1, "BSCH": 2, "SCH/HU": 3, "TCH/4.8": 4, "TCH/2.4": 5}
+# (RCPC rate, 16-bit CRC present): the traffic channels carry no block code (cl. 8.3.1), only the 4 tail bits;
+# their interleaving over N blocks is taken with N = 1 (block interleaver (432, 103) only)
+CHANNEL_CODING = {"SCH/HD": ("2/3", True), "SCH/F": ("2/3", True), "BSCH": ("2/3", True), "SCH/HU": ("2/3", True),
+                  "TCH/4.8": ("292/432", False), "TCH/2.4": ("148/432", False)}
+RATE_IDS = {"2/3": 0, "1/3": 1, "292/432": 2, "148/432": 3}
+# RCPC puncturing, cl. 8.2.3.1.3-8.2.3.1.6: rate -> (P(1..t), t, d of i(j) = j + (j-1) div d; 0: i = j)
+PUNCTURERS = {"2/3": ((1, 2, 5), 3, 0), "1/3": ((1, 2, 3, 5, 6, 7), 6, 0),
+              "292/432": ((1, 2, 5), 3, 65), "148/432": ((1, 2, 3, 5, 6, 7), 6, 35)}
 # rate-1/4 mother code, constraint length 5: taps on (x[n], x[n-1], x[n-2], x[n-3], x[n-4])
 GENERATORS = ((1, 1, 0, 0, 1), (1, 0, 1, 1, 1), (1, 1, 1, 0, 1), (1, 1, 0, 1, 1))
-PUNCT_2_3 = (1, 2, 5)          # kept positions (1-based) of every 8 mother bits, t = 3
+
+
+def puncture_index(rate, K3):
+    """0-based position in the mother-code output V(1..4 K2) of type-3 bit j = 1..K3 (cl. 8.2.3.1.2)."""
+    P, t, div = PUNCTURERS[rate]
+    j = np.arange(1, K3 + 1)
+    i = j + (j - 1) // div if div else j
+    blk = (i - 1) // t
+    return 8 * blk + np.asarray(P)[i - t * blk - 1] - 1
 
 
 def scrambling_init(mcc=0, mnc=0, colour=0):
@@ -60,10 +77,14 @@ def interleave_index(K, a):
 
 def encode(type1, channel="SCH/HD", scramb_init=3):
     """[n, K1] type-1 bits -> [n, K3] type-5 bits."""
-    K1, K2, K3, a = CHANNELS[channel]
+    return encode_custom(type1, *CHANNELS[channel], *CHANNEL_CODING[channel], scramb_init=scramb_init)
+
+
+def encode_custom(type1, K1, K2, K3, a, rate="2/3", crc=True, scramb_init=3):
+    """The same for any block geometry (K2 = K1 + 16 crc + 4, K3 the number of type-3 bits the rate leaves)."""
     t1 = np.asarray(type1, dtype=np.uint8).reshape(-1, K1)
     n = t1.shape[0]
-    t2 = np.concatenate([t1, crc16_block(t1), np.zeros((n, 4), np.uint8)], axis=1)
+    t2 = np.concatenate([t1] + ([crc16_block(t1)] if crc else []) + [np.zeros((n, 4), np.uint8)], axis=1)
     assert t2.shape[1] == K2
     pad = np.concatenate([np.zeros((n, 4), np.uint8), t2], axis=1)         # x[n-4..n]
     mother = np.zeros((n, K2, 4), np.uint8)
@@ -74,9 +95,7 @@ def encode(type1, channel="SCH/HD", scramb_init=3):
                 acc ^= pad[:, 4 - d:4 - d + K2]
         mother[:, :, g] = acc
     flat = mother.reshape(n, K2 * 4)                                      # V(1..4 K2)
-    j = np.arange(K3)
-    idx = 8 * (j // 3) + np.asarray(PUNCT_2_3)[j % 3] - 1
-    t3 = flat[:, idx]
+    t3 = flat[:, puncture_index(rate, K3)]
     t4 = np.empty_like(t3)
     t4[:, interleave_index(K3, a)] = t3
     return t4 ^ scrambling_sequence(scramb_init, K3)[None, :]
@@ -92,11 +111,16 @@ def to_soft(bits, sigma=0.0, rng=None, scale=32.0):
 
 
 class ChannelDecoder:
-    """Batched descramble + de-interleave + RCPC (rate 2/3) Viterbi + CRC on the GPU."""
+    """Batched descramble + de-interleave + RCPC Viterbi (+ CRC) on the GPU.  `channel` is a logical channel name
+    or a tuple (K1, K2, K3, a, rate, crc) for any other block geometry (K2 <= 320; tb200_etsi_decode_custom)."""
 
     def __init__(self, channel="SCH/HD", device=0):
         self.channel = channel
-        self.K1, self.K2, self.K3, self.a = CHANNELS[channel]
+        if isinstance(channel, str):
+            self.K1, self.K2, self.K3, self.a = CHANNELS[channel]
+            self.rate, self.crc = CHANNEL_CODING[channel]
+        else:
+            self.K1, self.K2, self.K3, self.a, self.rate, self.crc = channel
         self.device = device
         self._h = _lib.Handle(max_chunks=0, max_chunk_len=0, device=device)
 
@@ -113,9 +137,15 @@ class ChannelDecoder:
         if metric is None:
             metric = _dev.empty((n,), torch.int32, self.device)
         h = self._h
-        _lib.check(h.lib.tb200_etsi_decode_batch(h.h, soft.data_ptr(), n, CHANNEL_IDS[self.channel],
-                                                 int(scramb_init) & 0xFFFFFFFF, bits.data_ptr(), crc_ok.data_ptr(),
-                                                 metric.data_ptr(), _dev.stream_ptr(self.device)))
+        if isinstance(self.channel, str):
+            _lib.check(h.lib.tb200_etsi_decode_batch(h.h, soft.data_ptr(), n, CHANNEL_IDS[self.channel],
+                                                     int(scramb_init) & 0xFFFFFFFF, bits.data_ptr(), crc_ok.data_ptr(),
+                                                     metric.data_ptr(), _dev.stream_ptr(self.device)))
+        else:
+            _lib.check(h.lib.tb200_etsi_decode_custom(h.h, soft.data_ptr(), n, self.K1, self.K2, self.K3, self.a,
+                                                      RATE_IDS[self.rate], int(bool(self.crc)),
+                                                      int(scramb_init) & 0xFFFFFFFF, bits.data_ptr(), crc_ok.data_ptr(),
+                                                      metric.data_ptr(), _dev.stream_ptr(self.device)))
         return bits, crc_ok, metric
 
     def decode(self, soft, scramb_init=3):
@@ -128,6 +158,87 @@ class ChannelDecoder:
         return b, ok.cpu().numpy().astype(bool), met.cpu().numpy()
 
 
+# ---- AACH: (30, 14) shortened Reed-Muller code (cl. 8.2.3.2)
+def rm3014_generator():
+    """A systematic generator [I14 | P] of a (30, 14, d = 8) shortened second-order Reed-Muller code: RM(2, 5) (the 16
+    monomials of degree <= 2 evaluated at the 32 points of GF(2)^5), restricted to the codewords that vanish at the
+    points 00000 and 11111, those two positions deleted, reduced to systematic form.  This is the CODE FAMILY of
+    cl. 8.2.3.2; the standard's own matrix (a particular basis and bit order) is not reproduced here — pass it as
+    `generator` to aach_encode / AachDecoder for on-air signals.  uint8 [14, 30]."""
+    import itertools
+    pts = np.array([[(v >> (4 - i)) & 1 for i in range(5)] for v in range(32)], np.uint8)
+    rows = [np.ones(32, np.uint8)] + [pts[:, i] for i in range(5)]
+    rows += [pts[:, i] & pts[:, j] for i, j in itertools.combinations(range(5), 2)]
+    G = np.array(rows, np.uint8)
+
+    def rref(M):
+        M = M.copy()
+        r, piv = 0, []
+        for c in range(M.shape[1]):
+            p = [i for i in range(r, M.shape[0]) if M[i, c]]
+            if not p:
+                continue
+            M[[r, p[0]]] = M[[p[0], r]]
+            for i in range(M.shape[0]):
+                if i != r and M[i, c]:
+                    M[i] ^= M[r]
+            piv.append(c)
+            r += 1
+            if r == M.shape[0]:
+                break
+        return M[:r], piv
+
+    R, _ = rref(G[:, [0, 31] + list(range(1, 31))])
+    S, piv = rref(R[2:, 2:])
+    return S[:, piv + [c for c in range(30) if c not in piv]]
+
+
+def generator_words(generator):
+    """[14, 30] 0/1 matrix -> the 14 uint32 row words of tb200_etsi_aach_decode (code bit j in word bit 29 - j)."""
+    g = np.asarray(generator, dtype=np.uint64).reshape(14, 30)
+    return (g << np.arange(29, -1, -1, dtype=np.uint64)[None, :]).sum(axis=1).astype(np.uint32)
+
+
+def aach_encode(info, scramb_init=3, generator=None):
+    """[n, 14] information bits -> [n, 30] scrambled type-5 bits."""
+    G = rm3014_generator() if generator is None else np.asarray(generator, np.uint8)
+    b = np.asarray(info, dtype=np.uint8).reshape(-1, 14)
+    return ((b.astype(np.int64) @ G.astype(np.int64)) & 1).astype(np.uint8) ^ scrambling_sequence(scramb_init, 30)[None, :]
+
+
+class AachDecoder:
+    """Batched soft ML decoder of the AACH block code on the GPU (tb200_etsi_aach_decode)."""
+
+    def __init__(self, generator=None, device=0):
+        self.generator = rm3014_generator() if generator is None else np.asarray(generator, np.uint8).reshape(14, 30)
+        self._rows = np.ascontiguousarray(generator_words(self.generator))
+        self.device = device
+        self._h = _lib.Handle(max_chunks=0, max_chunk_len=0, device=device)
+
+    def decode_device(self, soft, scramb_init=3):
+        """soft: CUDA int8 [n, 30] -> (uint16 [n] information word, bit 1 = MSB of 14; int32 [n] correlation; int32 [n]
+        margin to the runner-up) CUDA tensors (int16 view for the words)."""
+        import torch
+        from . import _dev
+        n = soft.shape[0]
+        bits = _dev.empty((n,), torch.int16, self.device)
+        metric = _dev.empty((n,), torch.int32, self.device)
+        margin = _dev.empty((n,), torch.int32, self.device)
+        h = self._h
+        _lib.check(h.lib.tb200_etsi_aach_decode(h.h, soft.data_ptr(), n, self._rows.ctypes.data, int(scramb_init) & 0xFFFFFFFF,
+                                                bits.data_ptr(), metric.data_ptr(), margin.data_ptr(),
+                                                _dev.stream_ptr(self.device)))
+        return bits, metric, margin
+
+    def decode(self, soft, scramb_init=3):
+        """numpy int8 [n, 30] -> (bits uint8 [n, 14], metric int32 [n], margin int32 [n])."""
+        from . import _dev
+        s = np.ascontiguousarray(soft, dtype=np.int8).reshape(-1, 30)
+        w, m, g = self.decode_device(_dev.to_dev(s, self.device), scramb_init)
+        w = w.cpu().numpy().view(np.uint16).astype(np.int64)
+        return ((w[:, None] >> np.arange(13, -1, -1)[None, :]) & 1).astype(np.uint8), m.cpu().numpy(), g.cpu().numpy()
+
+
 # ======================================================================================
 # ETSI physical layer: burst building + pi/4-DQPSK RRC modulator (workload generator) and the
 # host API of the CUDA demodulator (RRC matched filter, closed-loop timing, soft bits, TS search)
@@ -135,6 +246,8 @@ class ChannelDecoder:
 TS_N = np.array([1, 1, 0, 1, 0, 0, 0, 0, 1, 1, 1, 0, 1, 0, 0, 1, 1, 1, 0, 1, 0, 0], dtype=np.uint8)   # normal 1
 TS_P = np.array([0, 1, 1, 1, 1, 0, 1, 0, 0, 1, 0, 0, 0, 0, 1, 1, 0, 1, 1, 1, 1, 0], dtype=np.uint8)   # normal 2
 TS_Q = np.array([1, 0, 1, 1, 0, 1, 1, 1, 0, 0, 0, 0, 0, 1, 1, 0, 1, 0, 1, 1, 0, 1], dtype=np.uint8)   # tail/extended
+TS_X = np.array([int(c) for c in "100111010000111010011101000011"], dtype=np.uint8)                    # extended (uplink control)
+SEQUENCE_IDS = {"n": 0, "p": 1, "q": 2, "x": 3, "y": 4}
 # normal continuous downlink burst, bit offsets (EN 300 392-2 cl. 9.4.4.3.2)
 NDB = {"q_tail": (0, 12), "pa": (12, 14), "bkn1": (14, 230), "bb1": (230, 244), "ts": (244, 266),
        "bb2": (266, 282), "bkn2": (282, 498), "pb": (498, 500), "q_head": (500, 510)}
@@ -342,6 +455,25 @@ class EtsiReceiver:
                                           self.theta.data_ptr(), _dev.stream_ptr(self.device)))
         self.acquire_device(x.shape[0], threshold)
         return self.sync_results(x.shape[0])
+
+    def find_sequence(self, n_streams, sequence="q", threshold=0.8, min_gap_symbols=200, max_hits=None):
+        """Positions (bit offsets into the soft bits of the last demodulation) where training sequence `sequence` —
+        'n', 'p', 'q' (tail: slot boundary = position + 10), 'x' (extended, 30 bits) or 'y' (sync, 38 bits) — correlates
+        at or above `threshold` (tb200_etsi_find_sequence).  Returns a list per stream of (position, correlation)."""
+        import torch
+        from . import _dev
+        h, lib = self._h, self._h.lib
+        mh = int(max_hits or self.max_bursts)
+        pos = _dev.zeros((self.max_streams, mh), torch.int32, self.device)
+        corr = _dev.zeros((self.max_streams, mh), torch.float32, self.device)
+        nh = _dev.zeros((self.max_streams,), torch.int32, self.device)
+        self.metric.zero_()
+        _lib.check(lib.tb200_etsi_find_sequence(h.h, self.soft.data_ptr(), int(n_streams), self.soft_stride,
+                                                self.n_soft.data_ptr(), SEQUENCE_IDS[sequence], float(threshold),
+                                                int(min_gap_symbols), self.metric.data_ptr(), pos.data_ptr(), corr.data_ptr(),
+                                                nh.data_ptr(), mh, _dev.stream_ptr(self.device)))
+        pos, corr, nh = pos.cpu().numpy(), corr.cpu().numpy(), nh.cpu().numpy()
+        return [[(int(pos[s, i]), float(corr[s, i])) for i in range(int(nh[s]))] for s in range(int(n_streams))]
 
     def carrier_offsets_hz(self, n_streams):
         """Carrier offset estimated by the last run per stream (Hz)."""
