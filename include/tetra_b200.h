@@ -290,6 +290,14 @@ int tb200_etsi_demod_segmented(tb200_handle h, const void *d_iq_c64, int n_strea
 int tb200_etsi_find_bursts(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,
                            const int32_t *d_n_soft, double threshold, float *d_metric, int8_t *d_blocks,
                            int32_t *d_burst_pos, int32_t *d_n_bursts, int max_bursts, void *stream);
+/* Two bit ranges [off_a, off_a + len_a) + [off_b, off_b + len_b) of every burst found by tb200_etsi_find_bursts /
+ * tb200_etsi_find_sync_bursts, as int8 soft values (the blocks' scale): d_out [n_streams][max_bursts][len_a + len_b],
+ * zero beyond a stream's burst count.  (230, 14) + (266, 16) is the broadcast block of a normal downlink burst = the 30
+ * AACH bits, input of tb200_etsi_aach_decode. */
+int tb200_etsi_extract_bits(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,
+                            const int32_t *d_n_soft, const int32_t *d_burst_pos, const int32_t *d_n_bursts, int max_bursts,
+                            int off_a, int len_a, int off_b, int len_b, int8_t *d_out, void *stream);
+
 /* Search for any training sequence of EN 300 392-2 cl. 9.4.4.3 in the demodulator's soft bits: sequence 0 = normal n,
  * 1 = normal p, 2 = tail q (22 bits; in a continuous downlink q(1..10) closes a burst and q(11..22) opens the next: a hit
  * at bit p puts the slot boundary at p + 10), 3 = extended x (30 bits, uplink control bursts), 4 = synchronisation y (38).

@@ -212,3 +212,25 @@ def test_training_sequence_search_all_sequences(fs, sigma):
     assert near(x_hits[1], [x_at]) == [x_at]
     # x = n(12..22) n(1..19): it also lights up at every normal sequence n, 11 bits early, with partial correlation only
     assert all(c < 0.85 or abs(p - x_at) <= 4 for p, c in x_hits[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fs,sigma", [(72000.0, 0.0), (50000.0, 0.1)])
+def test_aach_through_the_receive_chain(fs, sigma):
+    """Broadcast block of every normal burst: modulator -> demodulator -> burst search -> tb200_etsi_extract_bits ->
+    (30, 14) soft ML decoder == the access-assignment word that was sent."""
+    import __graft_entry__ as entry
+    entry.build()
+    n_bursts = 24
+    bits, t1, init, words = etsi.make_etsi_stream(n_bursts, seed=21, aach=True)
+    x = etsi.modulate_dqpsk(bits, fs, sigma=sigma, t_offset=0.3, seed=2)
+    rx = etsi.EtsiReceiver(fs, max_streams=1, max_samples=len(x))
+    res = rx.run(x[None, :], init, aach=True)[0]
+    assert len(res) >= n_bursts - 4
+    good = 0
+    for b in res:
+        idx = int(round(b["start"] / 510.0))
+        if 0 <= idx < n_bursts and b["crc_ok"].all():
+            assert np.array_equal(b["aach"], words[idx]) and b["aach_margin"] > 0, idx
+            good += 1
+    assert good >= n_bursts - 5

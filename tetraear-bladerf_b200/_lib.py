@@ -74,6 +74,7 @@ _PROTOS = {
     "tb200_burst_batch_host": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "tb200_crc16_rows": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "tb200_etsi_decode_batch": (_i, [_vp, _vp, _i64, _i, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "tb200_etsi_extract_bits": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tb200_etsi_find_sequence": (_i, [_vp, _vp, _i, _i64, _vp, _i, C.c_double, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "tb200_etsi_aach_decode": (_i, [_vp, _vp, _i64, _vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "tb200_etsi_decode_custom": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _i, C.c_uint32, _vp, _vp, _vp, _vp]),

@@ -744,6 +744,19 @@ extern "C" int tb200_etsi_find_sequence(tb200_handle h, const float *d_soft, int
                                      d_metric, d_pos, d_corr, d_n_hits, max_hits, (cudaStream_t)stream);
 }
 
+extern "C" int tb200_etsi_extract_bits(tb200_handle h, const float *d_soft, int n_streams, int64_t soft_stride,
+                                       const int32_t *d_n_soft, const int32_t *d_burst_pos, const int32_t *d_n_bursts,
+                                       int max_bursts, int off_a, int len_a, int off_b, int len_b, int8_t *d_out, void *stream)
+{
+    DevGuard dev_guard(h);
+    if (!h || n_streams < 0 || !d_soft || !d_n_soft || !d_burst_pos || !d_n_bursts || !d_out || max_bursts <= 0 || len_a < 0 ||
+        len_b < 0 || len_a + len_b <= 0 || off_a < 0 || off_b < 0 || off_a + len_a > 510 || off_b + len_b > 510)
+        return fail(TB200_E_ARG, "tb200_etsi_extract_bits: bad argument");
+    StageTimer tm(h, TB_STAGE_ETSI, (cudaStream_t)stream);
+    return launch_etsi_extract(h, d_soft, n_streams, soft_stride, d_n_soft, d_burst_pos, d_n_bursts, max_bursts, off_a, len_a,
+                               off_b, len_b, d_out, (cudaStream_t)stream);
+}
+
 extern "C" int tb200_etsi_afc(tb200_handle h, float *d_soft, int n_streams, int64_t soft_stride, const int32_t *d_n_soft,
                               float *d_theta, void *stream)
 {

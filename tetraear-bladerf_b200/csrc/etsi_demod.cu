@@ -279,12 +279,8 @@ __global__ void etsi_find_bursts_kernel(const float *__restrict__ soft, long sof
         long ts_bit = 2 * best;
         long start = ts_bit - 244;
         if (start >= 0 && start + 510 <= nb) {
-            int8_t *o = blocks + ((long)s * max_bursts + found) * 432;
-            for (int j = lane; j < 432; j += 32) {
-                long src = start + (j < 216 ? 14 + j : 282 + (j - 216));
-                float q = rintf(b[src] * quant);
-                o[j] = (int8_t)fminf(fmaxf(q, -127.f), 127.f);
-            }
+            // the two blocks are cut out by etsi_extract_kernel afterwards, in parallel over (stream, burst, bit): doing it
+            // here put 14 dependent load -> store rounds of ONE warp between two hits (the search is a serial chain)
             if (lane == 0) burst_pos[(long)s * max_bursts + found] = (int32_t)start;
             ++found;
         }
@@ -421,6 +417,25 @@ __global__ void etsi_find_seq_kernel(const int32_t *__restrict__ n_soft, const f
     if (lane == 0) n_hits[s] = found;
 }
 
+
+// ---- extraction of two bit ranges of every found burst (e.g. the broadcast block BB = bits 230..243 + 266..281 of a
+// normal downlink burst, the 30 AACH bits; bits 252..281 of a synchronisation burst), quantised like the blocks
+__global__ void etsi_extract_kernel(const float *__restrict__ soft, long soft_stride, const int32_t *__restrict__ n_soft,
+                                    const int32_t *__restrict__ burst_pos, const int32_t *__restrict__ n_bursts, int max_bursts,
+                                    int off_a, int len_a, int off_b, int len_b, int8_t *__restrict__ out, float quant)
+{
+    const int s = blockIdx.y;
+    const int L = len_a + len_b;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;        // (burst, bit)
+    const int bi = idx / L, j = idx - bi * L;
+    if (bi >= max_bursts) return;
+    int8_t v = 0;
+    if (bi < n_bursts[s]) {
+        const long src = (long)burst_pos[(long)s * max_bursts + bi] + (j < len_a ? off_a + j : off_b + (j - len_a));
+        if (src >= 0 && src < n_soft[s]) v = (int8_t)fminf(fmaxf(rintf(soft[(long)s * soft_stride + src] * quant), -127.f), 127.f);
+    }
+    out[((long)s * max_bursts + bi) * L + j] = v;
+}
 
 // ---- feed-forward carrier-offset correction on the differential symbols.  The soft pair of symbol k is the
 // normalised d_k = y_k conj(y_(k-1)):  Re d = -soft[2k+1], Im d = -soft[2k].  For pi/4-DQPSK arg d is one of
@@ -560,7 +575,7 @@ int launch_etsi_find_bursts(tb200_handle h, const float *soft, int n_streams, lo
     etsi_find_bursts_kernel<<<blocks_n, threads, 0, st>>>(soft, soft_stride, n_soft, metric, n_streams, thr, blocks, burst_pos,
                                                          n_bursts, max_bursts, 45.0f);
     TB_LAUNCH_CHECK(h);
-    return TB200_OK;
+    return launch_etsi_extract(h, soft, n_streams, soft_stride, n_soft, burst_pos, n_bursts, max_bursts, 14, 216, 282, 216, blocks, st);
 }
 
 int launch_etsi_find_sequence(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft, int seq,
@@ -575,6 +590,19 @@ int launch_etsi_find_sequence(tb200_handle h, const float *soft, int n_streams, 
     int threads = 128, blocks_n = (n_streams * 32 + threads - 1) / threads;
     etsi_find_seq_kernel<<<blocks_n, threads, 0, st>>>(n_soft, metric, soft_stride / 2, n_streams, len[seq], thr, gap, pos, corr,
                                                       n_hits, max_hits);
+    TB_LAUNCH_CHECK(h);
+    return TB200_OK;
+}
+
+int launch_etsi_extract(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft,
+                        const int32_t *burst_pos, const int32_t *n_bursts, int max_bursts, int off_a, int len_a, int off_b, int len_b,
+                        int8_t *out, cudaStream_t st)
+{
+    if (n_streams <= 0) return TB200_OK;
+    const int tot = max_bursts * (len_a + len_b);
+    dim3 grid((unsigned)((tot + 127) / 128), (unsigned)n_streams);
+    etsi_extract_kernel<<<grid, 128, 0, st>>>(soft, soft_stride, n_soft, burst_pos, n_bursts, max_bursts, off_a, len_a, off_b, len_b,
+                                             out, 45.0f);
     TB_LAUNCH_CHECK(h);
     return TB200_OK;
 }

@@ -52,6 +52,9 @@ int launch_etsi_find_bursts(tb200_handle h, const float *soft, int n_streams, lo
 int launch_etsi_find_sequence(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft, int seq,
                               float thr, int gap, float *metric, int32_t *pos, float *corr, int32_t *n_hits, int max_hits,
                               cudaStream_t st);
+int launch_etsi_extract(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft,
+                        const int32_t *burst_pos, const int32_t *n_bursts, int max_bursts, int off_a, int len_a, int off_b, int len_b,
+                        int8_t *out, cudaStream_t st);
 int launch_etsi_afc(tb200_handle h, float *soft, int n_streams, long soft_stride, const int32_t *n_soft, float *theta, cudaStream_t st);
 int launch_etsi_find_sync(tb200_handle h, const float *soft, int n_streams, long soft_stride, const int32_t *n_soft, float thr,
                           float *metric, int8_t *sb1, int8_t *bkn2, int32_t *burst_pos, int32_t *n_bursts, int max_bursts,

@@ -280,10 +280,14 @@ def rrc_pulse(t, alpha=0.35):
     return out
 
 
-def build_normal_burst(bkn1, bkn2, rng=None, ts=TS_N):
-    """510-bit normal continuous downlink burst around two 216-bit (type-5) blocks."""
+def build_normal_burst(bkn1, bkn2, rng=None, ts=TS_N, bb=None):
+    """510-bit normal continuous downlink burst around two 216-bit (type-5) blocks; bb = the 30 broadcast-block bits
+    (the AACH block, 14 before and 16 behind the training sequence) or None for random bits."""
     rng = np.random.default_rng(0) if rng is None else rng
     b = rng.integers(0, 2, 510, dtype=np.uint8)
+    if bb is not None:
+        b[230:244] = bb[:14]
+        b[266:282] = bb[14:30]
     b[0:12] = TS_Q[10:22]
     b[14:230] = bkn1
     b[244:266] = ts
@@ -323,12 +327,16 @@ def build_sync_burst(sb1, bkn2, rng=None):
     return b
 
 
-def make_etsi_stream(n_bursts, seed=0, scramb_init=None, ts=TS_N, sync_every=0, network=(262, 42, 17)):
+def make_etsi_stream(n_bursts, seed=0, scramb_init=None, ts=TS_N, sync_every=0, network=(262, 42, 17), aach=False):
     """Back-to-back downlink bursts carrying random SCH/HD blocks.  With sync_every = k > 0 every k-th burst is a
     synchronisation burst whose BSCH block announces `network` = (MCC, MNC, colour code) and whose BKN2 is an SCH/HD
-    block (its first type-1 row of that burst is then unused).  Returns (bits, type1 [n,2,124], scrambling init)."""
+    block (its first type-1 row of that burst is then unused).  Returns (bits, type1 [n,2,124], scrambling init);
+    with aach=True the broadcast block of every normal burst carries a random 14-bit access-assignment word through
+    the (30, 14) code of rm3014_generator(), and the words [n, 14] are returned as a fourth item."""
     rng = np.random.default_rng(seed)
     init = scrambling_init(*network) if scramb_init is None else scramb_init
+    aach_bits = np.random.default_rng(seed + 100003).integers(0, 2, (n_bursts, 14), dtype=np.uint8) if aach else None
+    bb = aach_encode(aach_bits, init) if aach else None
     t1 = rng.integers(0, 2, (n_bursts, 2, 124), dtype=np.uint8)
     t5 = encode(t1.reshape(-1, 124), "SCH/HD", init).reshape(n_bursts, 2, 216)
     out = []
@@ -338,7 +346,9 @@ def make_etsi_stream(n_bursts, seed=0, scramb_init=None, ts=TS_N, sync_every=0, 
                            multiframe=1 + (i // 72) % 60)
             out.append(build_sync_burst(encode(sb[None, :], "BSCH", 3)[0], t5[i, 1], rng))
         else:
-            out.append(build_normal_burst(t5[i, 0], t5[i, 1], rng, ts))
+            out.append(build_normal_burst(t5[i, 0], t5[i, 1], rng, ts, None if bb is None else bb[i]))
+    if aach:
+        return np.concatenate(out), t1, init, aach_bits
     return np.concatenate(out), t1, init
 
 
@@ -401,6 +411,9 @@ class EtsiReceiver:
         self._scratch = None
         self.afc = bool(afc)                      # feed-forward carrier-offset correction (tb200_etsi_afc), |df| < 2250 Hz
         self.theta = _dev.zeros((S,), torch.float32, device)
+        self.aach = None                          # AachDecoder, created by run(..., aach=True)
+        self.bb = _dev.zeros((S, self.max_bursts, 30), torch.int8, device)
+        self.aach_words = self.aach_metric = self.aach_margin = None
         self.max_sync = self.max_bursts
         self.sb1 = _dev.zeros((S, self.max_sync, 120), torch.int8, device)
         self.sync_pos = _dev.zeros((S, self.max_sync), torch.int32, device)
@@ -522,21 +535,45 @@ class EtsiReceiver:
                                                self.bits.data_ptr(), self.crc_ok.data_ptr(), self.path_metric.data_ptr(), st))
         return n_streams
 
-    def run(self, iq, scramb_init, threshold=0.8):
-        """numpy complex64 [n_streams, n] -> list per stream of dicts(start, blocks [2,124] bits, crc_ok [2])."""
+    def decode_aach_device(self, n_streams, scramb_init, generator=None):
+        """After run_device: the broadcast block (bits 230..243 + 266..281) of every found burst through the (30, 14)
+        soft ML decoder (tb200_etsi_extract_bits + tb200_etsi_aach_decode).  Results stay on the device in
+        aach_words (int16 [S * max_bursts]), aach_metric, aach_margin."""
+        from . import _dev
+        h, lib = self._h, self._h.lib
+        if self.aach is None or generator is not None:
+            self.aach = AachDecoder(generator, self.device)
+        _lib.check(lib.tb200_etsi_extract_bits(h.h, self.soft.data_ptr(), int(n_streams), self.soft_stride, self.n_soft.data_ptr(),
+                                               self.burst_pos.data_ptr(), self.n_bursts.data_ptr(), self.max_bursts,
+                                               230, 14, 266, 16, self.bb.data_ptr(), _dev.stream_ptr(self.device)))
+        self.aach_words, self.aach_metric, self.aach_margin = self.aach.decode_device(
+            self.bb.view(-1, 30)[:int(n_streams) * self.max_bursts], scramb_init)
+
+    def run(self, iq, scramb_init, threshold=0.8, aach=False):
+        """numpy complex64 [n_streams, n] -> list per stream of dicts(start, blocks [2,124] bits, crc_ok [2]); with
+        aach=True also "aach" (the 14 access-assignment bits) and "aach_margin" per burst."""
         from . import _dev
         x = np.ascontiguousarray(iq, dtype=np.complex64)
         if x.ndim == 1:
             x = x[None, :]
         d = _dev.to_dev(x.view(np.float32).reshape(x.shape[0], x.shape[1], 2), self.device)
         S = self.run_device(d, x.shape[1], scramb_init, threshold)
+        if aach:
+            self.decode_aach_device(S, scramb_init)
+            w = self.aach_words.cpu().numpy().view(np.uint16).astype(np.int64).reshape(S, self.max_bursts)
+            ab = ((w[:, :, None] >> np.arange(13, -1, -1)[None, None, :]) & 1).astype(np.uint8)
+            am = self.aach_margin.cpu().numpy().reshape(S, self.max_bursts)
         nb = self.n_bursts.cpu().numpy()[:S]
         pos = self.burst_pos.cpu().numpy()[:S]
         bits = np.unpackbits(self.bits.cpu().numpy(), axis=1)[:, :124].reshape(self.max_streams, self.max_bursts, 2, 124)
         ok = self.crc_ok.cpu().numpy().reshape(self.max_streams, self.max_bursts, 2).astype(bool)
         out = []
         for s in range(S):
-            out.append([{"start": int(pos[s, i]), "blocks": bits[s, i], "crc_ok": ok[s, i]} for i in range(int(nb[s]))])
+            rows = [{"start": int(pos[s, i]), "blocks": bits[s, i], "crc_ok": ok[s, i]} for i in range(int(nb[s]))]
+            if aach:
+                for i, r in enumerate(rows):
+                    r["aach"], r["aach_margin"] = ab[s, i], int(am[s, i])
+            out.append(rows)
         return out
 
 
