@@ -13,6 +13,7 @@
 // DE-INTERLEAVED ([position][thread], pitch THREADS+4 bytes: conflict-free both ways), and keeps the survivor
 // decisions there as one uint16 per (step, thread).  No shuffles, no inter-thread traffic: ~110 instructions per
 // trellis step per block instead of ~320 lane-instructions with the former 16-lanes-per-block mapping.
+#include <climits>
 #include <vector>
 #include "common.h"
 #include "kernels.h"
@@ -290,10 +291,14 @@ static void scramble_words(uint32_t init, int n, uint32_t *words)
 
 // ---- AACH: (30, 14) shortened second-order Reed-Muller block code (cl. 8.2.3.2), soft maximum-likelihood decoding.
 // One warp per block: lane L correlates the 512 codewords whose five leading information bits spell L, walking the
-// other nine in Gray-code order (one generator row XORed per step — the row index is the same for all lanes, so it is
-// a uniform constant-bank read); the correlation of a codeword is S - 2 * (sum of the soft values where it has a 1),
-// taken from four byte-indexed tables of partial sums the warp builds for its block in shared memory.  The generator is
-// a parameter (14 rows, code bit j in word bit 29 - j): any (30, 14) linear code decodes the same way.
+// other nine in Gray-code order (one generator row XORed per step; the three fastest bits are unrolled, their rows sit in
+// registers).  The correlation of a codeword is 2 * (sum of the soft values where it has a 1) - (sum of all), and the
+// sum over its ones is taken five code bits at a time from six 32-entry tables of partial sums that live ONE ENTRY PER
+// LANE in six registers and are read with warp shuffles (index = five bits of the codeword): no shared memory, no bank
+// conflicts (a first version with byte-indexed tables in shared memory spent its time on 32-way-random 16-bit reads:
+// 1.0 G bank conflicts and 70 instructions per codeword, 32 ms per 1 M blocks).  Winner and runner-up are tracked as
+// one integer key = correlation * 2^14 + (16383 - word): max = best correlation, ties to the smaller word.
+// The generator is a parameter (14 rows, code bit j in word bit 29 - j): any (30, 14) linear code decodes the same way.
 struct AachParams {
     uint32_t gen[14];      // gen[k]: row of information bit k + 1 (MSB of the 14-bit result first)
     uint32_t scr;          // scrambling bits of the 30 positions, bit j = p(j + 1)
@@ -303,62 +308,72 @@ __global__ void __launch_bounds__(128)
 etsi_aach_kernel(const int8_t *__restrict__ soft, long n, AachParams P, uint16_t *__restrict__ bits_out,
                  int32_t *__restrict__ metric, int32_t *__restrict__ margin)
 {
-    __shared__ int16_t W[4][4][256];
-    __shared__ int16_t S[4][32];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long blk = (long)blockIdx.x * 4 + w;
+    const int lane = threadIdx.x & 31;
+    const long blk = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (blk >= n) return;
+    // lane w < 30 holds the descrambled soft value of WORD bit w = code bit 29 - w
     int v = 0;
     if (lane < 30) {
-        v = soft[blk * 30 + lane];
-        if ((P.scr >> lane) & 1u) v = -v;
+        const int j = 29 - lane;
+        v = soft[blk * 30 + j];
+        if ((P.scr >> j) & 1u) v = -v;
     }
-    S[w][lane] = (int16_t)v;                   // S[w][j] = descrambled soft value of code bit j (+ = 1)
     int tot = v;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    __syncwarp();
-    for (int e = lane; e < 1024; e += 32) {
-        const int g = e >> 8, val = e & 255;
+    // T[g] on lane L = sum of the soft values of word bits 5g + u over the set bits u of L
+    int T[6];
+#pragma unroll
+    for (int g = 0; g < 6; ++g) {
         int acc = 0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int wb = 8 * g + u;          // word bit -> code bit 29 - wb
-            if (wb < 30 && ((val >> u) & 1)) acc += S[w][29 - wb];
+        for (int u = 0; u < 5; ++u) {
+            const int sv = __shfl_sync(0xffffffffu, v, 5 * g + u);
+            if ((lane >> u) & 1) acc += sv;
         }
-        W[w][g][val] = (int16_t)acc;
+        T[g] = acc;
     }
-    __syncwarp();
-    // lane's base codeword: information bits 1..5 = lane (MSB first) -> rows 0..4
     uint32_t cw = 0;
 #pragma unroll
     for (int k = 0; k < 5; ++k) if ((lane >> (4 - k)) & 1) cw ^= P.gen[k];
-    int best = -(1 << 30), second = -(1 << 30), best_c = 0;
-    uint32_t gray = 0;
-    for (int i = 0; i < 512; ++i) {
-        if (i) {
-            const int b = __ffs(i) - 1;        // Gray code: bit b of the low nine flips; low bit b <-> information bit 14 - b
-            gray ^= 1u << b;
+    const uint32_t r0 = P.gen[13], r1 = P.gen[12], r2 = P.gen[11];
+    // key = corr * 16384 + 16383 - word = ones * 32768 + (16383 - tot * 16384 - (lane << 9)) - gray
+    const int k0 = 16383 - tot * 16384 - (lane << 9);
+    int best = INT_MIN, second = INT_MIN;
+    int gray = 0;
+    auto eval = [&](uint32_t c, int gr) {
+        int ones = __shfl_sync(0xffffffffu, T[0], (int)c);
+#pragma unroll
+        for (int g = 1; g < 6; ++g) ones += __shfl_sync(0xffffffffu, T[g], (int)(c >> (5 * g)));     // source lane is taken mod 32
+        const int key = ones * 32768 + k0 - gr;
+        second = max(second, min(best, key));
+        best = max(best, key);
+    };
+    for (int hi = 0; hi < 64; ++hi) {
+        if (hi) {
+            const int b = __ffs(hi) + 2;                  // Gray code over bits 3..8 of the low nine
+            gray ^= 1 << b;
             cw ^= P.gen[13 - b];
         }
-        // +1 expected where the codeword has a 1: correlation = (sum over ones) - (sum over zeros) = 2 * ones - total
-        const int ones = W[w][0][cw & 255] + W[w][1][(cw >> 8) & 255] + W[w][2][(cw >> 16) & 255] + W[w][3][cw >> 24];
-        const int corr = 2 * ones - tot;
-        const int c = (lane << 9) | (int)gray;
-        if (corr > best || (corr == best && c < best_c)) { second = best; best = corr; best_c = c; }
-        else if (corr > second) second = corr;
+        eval(cw, gray);
+        cw ^= r0; gray ^= 1; eval(cw, gray);
+        cw ^= r1; gray ^= 2; eval(cw, gray);
+        cw ^= r0; gray ^= 1; eval(cw, gray);
+        cw ^= r2; gray ^= 4; eval(cw, gray);
+        cw ^= r0; gray ^= 1; eval(cw, gray);
+        cw ^= r1; gray ^= 2; eval(cw, gray);
+        cw ^= r0; gray ^= 1; eval(cw, gray);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const int ob = __shfl_xor_sync(0xffffffffu, best, o), oc = __shfl_xor_sync(0xffffffffu, best_c, o);
-        const int os = __shfl_xor_sync(0xffffffffu, second, o);
-        if (ob > best || (ob == best && oc < best_c)) { second = max(best, os); best = ob; best_c = oc; }
-        else second = max(second, ob);
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
+        second = max(max(second, os), min(best, ob));
+        best = max(best, ob);
     }
     if (lane == 0) {
-        bits_out[blk] = (uint16_t)best_c;
-        metric[blk] = best;
-        if (margin) margin[blk] = best - second;
+        bits_out[blk] = (uint16_t)(16383 - (best & 16383));
+        metric[blk] = best >> 14;                         // arithmetic shift = floor: the low 14 bits are non-negative
+        if (margin) margin[blk] = (best >> 14) - (second >> 14);
     }
 }
 
