@@ -223,6 +223,22 @@ int tb200_burst_batch(tb200_handle h, const uint8_t *d_dibits, int64_t n, uint8_
                       uint8_t *d_full, int64_t *d_stats, void *stream);
 int tb200_burst_batch_host(tb200_handle h, const uint8_t *h_dibits, int64_t n, uint8_t *h_rec,
                            uint8_t *h_full, int64_t *h_stats, void *stream);
+/* The class API's per-chunk pattern in ONE call (ui/modern.py:1919-2077: processor.process(samples), then
+ * decoder.decode(demodulated)): host IQ in; dibits, soft symbols (or NULL), counts, timing phases, frame records,
+ * frame counts and the three decode statistics out.  One upload, the kernels of tb200_process_decode_batch, ONE download
+ * through a pinned mirror inside the handle, one synchronisation.  For the small batches of that pattern only: the
+ * result region is limited to 1 MiB (n_chunks x (out_stride x 17 + max_frames x 156)), max_frames <= 64. */
+int tb200_process_decode_host(tb200_handle h, const void *h_iq, int dtype, int n_chunks, int chunk_len,
+                              const double *h_freq_off, uint8_t *h_dibits, void *h_symbols, int out_stride,
+                              int32_t *h_n_dibits, int32_t *h_phase, tb200_frame *h_frames, int max_frames,
+                              int32_t *h_n_frames, int64_t *h_stats, void *stream);
+/* 1 when a call of that geometry fits the handle's result region (n chunks / streams; out_stride 0 for the decoder call) */
+int tb200_host_oneshot_fits(tb200_handle h, int n, int out_stride, int max_frames, int want_symbols);
+/* TetraDecoder.decode (core/decoder.py:835-888) of host dibit rows [n_streams][stride]: upload, tb200_decode_batch,
+ * one download, one synchronisation; h_stats[3] = total bursts, CRC pass, CRC fail of THIS call.  Same size limits. */
+int tb200_decode_batch_host(tb200_handle h, const uint8_t *h_dibits, int n_streams, int stride, const int32_t *h_n_dibits,
+                            tb200_frame *h_frames, int max_frames, int32_t *h_n_frames, int64_t *h_stats, void *stream);
+
 /* _calculate_crc16 (protocol.py:331-347) of n_rows bit rows of n_bits each -> uint16 */
 int tb200_crc16_rows(tb200_handle h, const uint8_t *d_bits, int n_rows, int n_bits, int row_stride,
                      uint16_t *d_crc, void *stream);

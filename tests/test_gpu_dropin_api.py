@@ -460,3 +460,81 @@ def test_pipeline_records_to_frame_dicts(api):
                     assert fa[k] == fb[k], k
         total += len(a)
     assert total >= 8
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast", "fast32"])
+def test_process_to_decode_hand_over_changes_nothing(api, mode):
+    """process() runs the decoder's device part in its own launch sequence (tb200_process_decode_host) and decode() of
+    the dibits it returned takes the records from there (_spec): frames, statistics, dibits and symbols must equal the
+    two-call path, a modified copy of the dibits must NOT hit the hand-over, and the result equals the oracle's."""
+    from tetraear_b200 import synth, _spec
+    signal, core = api
+    L = 131072
+    cap = synth.make_capture(L * 3, 130, seed=23, mix=(0.6, 0.2, 0.2)).reshape(3, L)
+    assert _spec.enabled
+
+    def run(spec):
+        _spec.enabled = spec
+        try:
+            sp, dec = signal.SignalProcessor(2.4e6, mode=mode), core.TetraDecoder(auto_decrypt=False)
+            out = []
+            for c in range(3):
+                d = sp.process(cap[c])
+                out.append((d, sp.symbols.copy(), dec.decode(d)))
+            return out, dict(dec.protocol_parser.stats)
+        finally:
+            _spec.enabled = True
+
+    a, sa = run(True)
+    b, sb = run(False)
+    assert sa == sb and sa["total_bursts"] >= 3
+    n_frames = 0
+    for (da, ya, fa), (db, yb, fb) in zip(a, b):
+        assert np.array_equal(da, db) and np.array_equal(ya, yb) and len(fa) == len(fb)
+        for x, y in zip(fa, fb):
+            assert set(x) == set(y)
+            for k in x:
+                assert np.array_equal(x[k], y[k]) if isinstance(x[k], np.ndarray) else x[k] == y[k], k
+        n_frames += len(fa)
+    assert n_frames >= 6
+    # oracle: same dibits -> same frame positions / CRC verdicts
+    ofr, ostats = oracle.decode(a[0][0])
+    assert [(f["number"], f["burst_crc"]) for f in a[0][2]] == [(f["number"], bool(f["burst_crc"])) for f in ofr]
+    # a different array never hits the hand-over: flip one dibit and compare with a fresh two-call decode
+    d2 = a[0][0].copy()
+    d2[300] ^= 1
+    assert _spec.lookup(d2) is None and _spec.lookup(a[2][0]) is not None
+    f_spec = core.TetraDecoder(auto_decrypt=False).decode(d2)
+    _spec.enabled = False
+    try:
+        f_plain = core.TetraDecoder(auto_decrypt=False).decode(d2)
+    finally:
+        _spec.enabled = True
+    assert len(f_spec) == len(f_plain) and all(x["number"] == y["number"] and x.get("burst_crc") == y.get("burst_crc")
+                                               for x, y in zip(f_spec, f_plain))
+
+
+def test_decode_host_entry_point_equals_device_entry_point(api):
+    """tb200_decode_batch_host (one call) vs tb200_decode_batch on device tensors, through decode_records."""
+    import torch
+    from tetraear_b200 import synth, _lib, _spec, _dev
+    signal, core = api
+    x = synth.make_capture(131072, 130, seed=31)
+    _spec.enabled = False
+    try:
+        d = signal.SignalProcessor(2.4e6, mode="fast").process(x)
+        dec = core.TetraDecoder(auto_decrypt=False)
+        rec = dec.decode_records(d)                       # host entry point
+    finally:
+        _spec.enabled = True
+    h = dec._handle(len(d))
+    dd = _dev.to_dev(d, 0)
+    cnt = _dev.to_dev(np.array([len(d)], np.int32), 0)
+    mf = (2 * len(d)) // 250 + 2
+    frames = _dev.zeros((mf * _lib.FRAME_DTYPE.itemsize,), torch.uint8, 0)
+    nfr, stats = _dev.zeros((1,), torch.int32, 0), _dev.zeros((3,), torch.int64, 0)
+    _lib.check(h.lib.tb200_decode_batch(h.h, dd.data_ptr(), 1, len(d), cnt.data_ptr(), frames.data_ptr(), mf, nfr.data_ptr(),
+                                        stats.data_ptr(), _dev.stream_ptr(0)))
+    k = int(nfr.cpu()[0])
+    ref = frames.cpu().numpy().view(_lib.FRAME_DTYPE)[:k]
+    assert k == len(rec) > 0 and rec.tobytes() == ref.tobytes()

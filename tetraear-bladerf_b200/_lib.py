@@ -60,6 +60,9 @@ _PROTOS = {
     "tb200_launch_count": (_i64, [_vp]),
     "tb200_process_batch": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "tb200_process_decode_batch": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "tb200_process_decode_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "tb200_host_oneshot_fits": (_i, [_vp, _i, _i, _i, _i]),
+    "tb200_decode_batch_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "tb200_process_batch_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "tb200_resample": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "tb200_decimate": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),

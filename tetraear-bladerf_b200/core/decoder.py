@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-from .. import _lib
+from .. import _lib, _spec
 from .protocol import TetraProtocolParser, BurstType
 
 logger = logging.getLogger(__name__)
@@ -126,12 +126,33 @@ class TetraDecoder:
         n = len(s)
         if n == 0:
             return np.zeros(0, _lib.FRAME_DTYPE)
+        ps = self.protocol_parser.stats
+        hit = _spec.lookup(s)
+        if hit is not None:                   # SignalProcessor.process decoded exactly these dibits in its own launch
+            rec, st = hit
+            ps['total_bursts'] += int(st[0])
+            ps['crc_pass'] += int(st[1])
+            ps['crc_fail'] += int(st[2])
+            return rec.copy()
+        h = self._handle(n)
+        d = np.ascontiguousarray(np.clip(s.astype(np.int64), 0, 255).astype(np.uint8))
+        max_frames = (2 * n) // 250 + 2
+        if n <= 6000 and h.lib.tb200_host_oneshot_fits(h.h, 1, 0, max_frames, 0):
+            # one C-ABI call: upload, fused decode launch, one download, one synchronisation
+            rec = np.zeros(max_frames, dtype=_lib.FRAME_DTYPE)
+            nfr = np.zeros(1, dtype=np.int32)
+            st = np.zeros(3, dtype=np.int64)
+            cnt = np.array([n], np.int32)
+            _lib.check(h.lib.tb200_decode_batch_host(h.h, d.ctypes.data, 1, n, cnt.ctypes.data, rec.ctypes.data, max_frames,
+                                                     nfr.ctypes.data, st.ctypes.data, None))
+            ps['total_bursts'] += int(st[0])
+            ps['crc_pass'] += int(st[1])
+            ps['crc_fail'] += int(st[2])
+            return rec[:int(nfr[0])].copy()
         import torch
         from .. import _dev
-        h = self._handle(n)
-        d = _dev.to_dev(np.clip(s.astype(np.int64), 0, 255).astype(np.uint8), self.device)
+        d = _dev.to_dev(d, self.device)
         cnt = _dev.to_dev(np.array([n], np.int32), self.device)
-        max_frames = (2 * n) // 250 + 2
         frames = _dev.zeros((max_frames * _lib.FRAME_DTYPE.itemsize,), torch.uint8, self.device)
         nfr = _dev.zeros((1,), torch.int32, self.device)
         stats = _dev.zeros((3,), torch.int64, self.device)
@@ -139,7 +160,6 @@ class TetraDecoder:
                                             nfr.data_ptr(), stats.data_ptr(), _dev.stream_ptr(self.device)))
         k = int(nfr.cpu().numpy()[0])
         st = stats.cpu().numpy()
-        ps = self.protocol_parser.stats
         ps['total_bursts'] += int(st[0])
         ps['crc_pass'] += int(st[1])
         ps['crc_fail'] += int(st[2])

@@ -113,6 +113,21 @@ static size_t carve(tb200_handle h, char *base)
     h->stage_burst_rec = c.take<uint8_t>(NB * 32);
     h->stage_burst_full = c.take<uint8_t>(NB * 64);
     h->stage_stats = c.take<int64_t>(64);
+    // one-shot result region (small batches only: the class API works chunk by chunk)
+    {
+        const size_t SS = C ? C : S;
+        const size_t stride = C ? h->stage_out_stride : B / 2;
+        const size_t MF = 64 < (size_t)h->max_frames ? 64 : (size_t)h->max_frames;
+        const size_t bytes = 256 + SS * 16 + SS * stride + 64 + SS * MF * sizeof(tb200_frame) + 64 + (C ? SS * stride * 16 : 0);
+        if (bytes <= (1u << 20)) {
+            h->oshot_bytes = bytes; h->oshot_streams = SS; h->oshot_stride = stride; h->oshot_frames = MF;
+            h->oshot = c.take<char>(bytes);
+        } else {
+            h->oshot_bytes = 0; h->oshot = nullptr; h->oshot_streams = h->oshot_stride = h->oshot_frames = 0;
+        }
+        h->stage_dec_in = c.take<uint8_t>(S * (B / 2));
+        h->stage_dec_cnt = c.take<int32_t>(S * sizeof(int32_t) + 64);
+    }
     return c.off;
 }
 
@@ -240,6 +255,10 @@ extern "C" int tb200_create(const tb200_config *cfg, tb200_handle *out)
     carve(h, (char *)h->ws);
     rc = ensure_crc_tables(cfg->device);
     if (rc) { cudaFree(h->ws); delete h; return rc; }
+    if (h->oshot_bytes) {                                   // pinned mirror of the one-shot result region
+        if (cudaHostAlloc((void **)&h->pin, h->oshot_bytes, cudaHostAllocDefault) == cudaSuccess) h->pin_bytes = h->oshot_bytes;
+        else { cudaGetLastError(); h->pin = nullptr; h->pin_bytes = 0; }
+    }
     *out = h;
     return TB200_OK;
 }
@@ -249,6 +268,7 @@ extern "C" int tb200_destroy(tb200_handle h)
     if (!h) return TB200_OK;
     DevGuard dev_guard(h);
     if (h->ws) cudaFree(h->ws);
+    if (h->pin) cudaFreeHost(h->pin);
     if (h->prof_ev) {
         for (cudaEvent_t e : *h->prof_ev) cudaEventDestroy(e);
         delete h->prof_ev; delete h->prof_stage;
@@ -450,6 +470,119 @@ extern "C" int tb200_process_batch_host(tb200_handle h, const void *h_iq, int dt
     TB_CUDA(cudaMemcpyAsync(h_n_dibits, d_cnt, sizeof(int32_t) * n_chunks, cudaMemcpyDeviceToHost, st));
     if (h_phase) TB_CUDA(cudaMemcpyAsync(h_phase, d_ph, sizeof(int32_t) * n_chunks, cudaMemcpyDeviceToHost, st));
     TB_CUDA(cudaStreamSynchronize(st));
+    return TB200_OK;
+}
+
+// Layout of the one-shot result region for (n streams, stride, max_frames): offsets of its parts
+struct OneShot { size_t cnt, phase, nfr, stats, dibits, frames, symbols, end_no_sym, end; };
+static OneShot oneshot_layout(size_t n, size_t stride, size_t mf, bool with_symbols)
+{
+    OneShot o;
+    o.cnt = 0; o.phase = n * 4; o.nfr = 2 * n * 4; o.stats = (3 * n * 4 + 15) & ~(size_t)15;
+    o.dibits = o.stats + 32;
+    o.frames = (o.dibits + n * stride + 15) & ~(size_t)15;
+    o.end_no_sym = o.frames + n * mf * sizeof(tb200_frame);
+    o.symbols = (o.end_no_sym + 15) & ~(size_t)15;
+    o.end = with_symbols ? o.symbols + n * stride * 16 : o.end_no_sym;
+    return o;
+}
+
+// 1 if a tb200_process_decode_host / tb200_decode_batch_host call of this geometry fits the handle's one-shot result region
+extern "C" int tb200_host_oneshot_fits(tb200_handle h, int n, int out_stride, int max_frames, int want_symbols)
+{
+    if (!h || !h->oshot || !h->pin || n <= 0 || out_stride < 0 || max_frames <= 0 || max_frames > 64) return 0;
+    const OneShot o = oneshot_layout((size_t)n, (size_t)out_stride, (size_t)max_frames, want_symbols != 0);
+    return (o.end <= h->oshot_bytes && o.end <= h->pin_bytes) ? 1 : 0;
+}
+
+// process() + decode() of host chunks in ONE call: the class API's per-chunk pattern (ui/modern.py:1919-2077:
+// processor.process(samples) then decoder.decode(demodulated)) costs one upload, one kernel sequence with the fused
+// tail, ONE download of every result through a pinned mirror and one synchronisation.
+extern "C" int tb200_process_decode_host(tb200_handle h, const void *h_iq, int dtype, int n_chunks, int chunk_len,
+                                         const double *h_freq_off, uint8_t *h_dibits, void *h_symbols, int out_stride,
+                                         int32_t *h_n_dibits, int32_t *h_phase, tb200_frame *h_frames, int max_frames,
+                                         int32_t *h_n_frames, int64_t *h_stats, void *stream)
+{
+    DevGuard dev_guard(h);
+    if (!h || !h_n_dibits || !h_frames || !h_n_frames || max_frames <= 0)
+        return fail(TB200_E_ARG, "tb200_process_decode_host: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_chunks <= 0) return TB200_OK;
+    if (n_chunks > h->cfg.max_chunks || chunk_len > h->cfg.max_chunk_len)
+        return fail(TB200_E_ARG, "tb200_process_decode_host: exceeds the handle capacity");
+    const size_t esz = dtype == TB200_DTYPE_C64 ? 8 : (dtype == TB200_DTYPE_SC16 ? 4 : 16);
+    const size_t in_bytes = (size_t)n_chunks * chunk_len * esz;
+    void *stage = dtype == TB200_DTYPE_SC16 ? h->stage_sc16 : h->stage_in;
+    if (in_bytes > (dtype == TB200_DTYPE_SC16 ? h->stage_in_bytes / 2 : h->stage_in_bytes))
+        return fail(TB200_E_ARG, "tb200_process_decode_host: input exceeds staging (complex128 needs 2x)");
+    const OneShot o = oneshot_layout((size_t)n_chunks, (size_t)out_stride, (size_t)max_frames, h_symbols != nullptr);
+    if (!h->oshot || !h->pin || o.end > h->oshot_bytes || o.end > h->pin_bytes || (size_t)out_stride > h->stage_out_stride)
+        return fail(TB200_E_ARG, "tb200_process_decode_host: %d chunks x stride %d x %d frames exceed the one-shot result region "
+                                 "(this entry point serves the chunk-by-chunk class API; batches use tb200_process_decode_batch)",
+                    n_chunks, out_stride, max_frames);
+    if (in_bytes) TB_CUDA(cudaMemcpyAsync(stage, h_iq, in_bytes, cudaMemcpyHostToDevice, st));
+    double *d_f = nullptr;
+    if (h_freq_off) {
+        TB_CUDA(cudaMemcpyAsync(h->stage_freq, h_freq_off, sizeof(double) * n_chunks, cudaMemcpyHostToDevice, st));
+        d_f = h->stage_freq;
+    }
+    char *r = h->oshot;
+    TB_CUDA(cudaMemsetAsync(r + o.nfr, 0, o.dibits - o.nfr, st));                 // frame counts and stats start at zero
+    int rc = tb200_process_decode_batch(h, stage, dtype, n_chunks, chunk_len, chunk_len, d_f, (uint8_t *)(r + o.dibits),
+                                        h_symbols ? (void *)(r + o.symbols) : nullptr, out_stride, (int32_t *)(r + o.cnt),
+                                        (int32_t *)(r + o.phase), (tb200_frame *)(r + o.frames), max_frames,
+                                        (int32_t *)(r + o.nfr), (int64_t *)(r + o.stats), stream);
+    if (rc) return rc;
+    TB_CUDA(cudaMemcpyAsync(h->pin, r, o.end, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    const char *p = h->pin;
+    memcpy(h_n_dibits, p + o.cnt, sizeof(int32_t) * n_chunks);
+    if (h_phase) memcpy(h_phase, p + o.phase, sizeof(int32_t) * n_chunks);
+    memcpy(h_n_frames, p + o.nfr, sizeof(int32_t) * n_chunks);
+    if (h_stats) memcpy(h_stats, p + o.stats, 3 * sizeof(int64_t));
+    if (h_dibits) memcpy(h_dibits, p + o.dibits, (size_t)n_chunks * out_stride);
+    for (int c = 0; c < n_chunks; ++c) {                                          // only the frames that exist
+        int k = ((const int32_t *)(p + o.nfr))[c];
+        if (k > max_frames) k = max_frames;
+        if (k > 0) memcpy(h_frames + (size_t)c * max_frames, p + o.frames + (size_t)c * max_frames * sizeof(tb200_frame), (size_t)k * sizeof(tb200_frame));
+    }
+    if (h_symbols) memcpy(h_symbols, p + o.symbols, (size_t)n_chunks * out_stride * 16);
+    return TB200_OK;
+}
+
+// decode() of host dibit rows in one call (upload, fused decode launch, one download, one synchronisation)
+extern "C" int tb200_decode_batch_host(tb200_handle h, const uint8_t *h_dibits, int n_streams, int stride, const int32_t *h_n_dibits,
+                                       tb200_frame *h_frames, int max_frames, int32_t *h_n_frames, int64_t *h_stats, void *stream)
+{
+    DevGuard dev_guard(h);
+    if (!h || n_streams < 0 || stride < 0 || !h_n_dibits || !h_frames || !h_n_frames || max_frames <= 0 || (stride && !h_dibits))
+        return fail(TB200_E_ARG, "tb200_decode_batch_host: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_streams == 0) return TB200_OK;
+    if (h_stats) h_stats[0] = h_stats[1] = h_stats[2] = 0;
+    if (stride == 0) { memset(h_n_frames, 0, sizeof(int32_t) * n_streams); return TB200_OK; }
+    const OneShot o = oneshot_layout((size_t)n_streams, 0, (size_t)max_frames, false);
+    if ((size_t)n_streams * stride > (size_t)h->max_streams * (h->bits_stride / 2) || n_streams > h->max_streams)
+        return fail(TB200_E_ARG, "tb200_decode_batch_host: %d x %d dibits exceed the handle capacity", n_streams, stride);
+    if (!h->oshot || !h->pin || o.end > h->oshot_bytes || o.end > h->pin_bytes)
+        return fail(TB200_E_ARG, "tb200_decode_batch_host: %d streams x %d frames exceed the one-shot result region", n_streams, max_frames);
+    TB_CUDA(cudaMemcpyAsync(h->stage_dec_in, h_dibits, (size_t)n_streams * stride, cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaMemcpyAsync(h->stage_dec_cnt, h_n_dibits, sizeof(int32_t) * n_streams, cudaMemcpyHostToDevice, st));
+    char *r = h->oshot;
+    TB_CUDA(cudaMemsetAsync(r + o.nfr, 0, o.dibits - o.nfr, st));
+    int rc = tb200_decode_batch(h, h->stage_dec_in, n_streams, stride, h->stage_dec_cnt, (tb200_frame *)(r + o.frames), max_frames,
+                                (int32_t *)(r + o.nfr), (int64_t *)(r + o.stats), stream);
+    if (rc) return rc;
+    TB_CUDA(cudaMemcpyAsync(h->pin, r, o.end, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    const char *p = h->pin;
+    memcpy(h_n_frames, p + o.nfr, sizeof(int32_t) * n_streams);
+    if (h_stats) memcpy(h_stats, p + o.stats, 3 * sizeof(int64_t));
+    for (int c = 0; c < n_streams; ++c) {
+        int k = h_n_frames[c];
+        if (k > max_frames) k = max_frames;
+        if (k > 0) memcpy(h_frames + (size_t)c * max_frames, p + o.frames + (size_t)c * max_frames * sizeof(tb200_frame), (size_t)k * sizeof(tb200_frame));
+    }
     return TB200_OK;
 }
 

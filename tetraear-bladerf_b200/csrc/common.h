@@ -93,4 +93,10 @@ struct tb200_handle_s {
     uint8_t *stage_dibits; void *stage_symbols; int32_t *stage_counts; double *stage_freq;
     size_t stage_out_stride;
     uint8_t *stage_burst_in, *stage_burst_rec, *stage_burst_full; int64_t *stage_stats;
+    // one-shot result region of tb200_process_decode_host / tb200_decode_batch_host: [header: n_dibits[C], phase[C],
+    // n_frames[C], stats[3]] [dibits C x stride] [frames C x max_frames x 156] [symbols C x stride x 16], copied to the
+    // pinned mirror `pin` with ONE device-to-host copy (0 bytes: batch too large, piecewise copies instead)
+    char *oshot; size_t oshot_bytes; size_t oshot_streams, oshot_stride, oshot_frames;
+    uint8_t *stage_dec_in; int32_t *stage_dec_cnt;
+    char *pin; size_t pin_bytes;
 };

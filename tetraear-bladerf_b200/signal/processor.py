@@ -11,7 +11,7 @@ import logging
 
 import numpy as np
 
-from .. import _lib
+from .. import _lib, _spec
 
 logger = logging.getLogger(__name__)
 
@@ -108,14 +108,25 @@ class SignalProcessor:
         cnt = np.zeros(1, dtype=np.int32)
         phase = np.zeros(1, dtype=np.int32)
         f = np.array([float(freq_offset)], dtype=np.float64)
-        rc = h.lib.tb200_process_batch_host(h.h, x.ctypes.data, dt, 1, n, f.ctypes.data, dibits.ctypes.data,
-                                            symbols.ctypes.data, stride, cnt.ctypes.data, phase.ctypes.data, None)
-        _lib.check(rc)
-        nd = int(cnt[0])
+        max_frames = (2 * stride) // 250 + 2
+        if _spec.enabled and stride <= 6000 and h.lib.tb200_host_oneshot_fits(h.h, 1, stride, max_frames, 1):
+            # process + the decoder's device part in one call; decode() of these dibits finds its records in _spec
+            rec = np.zeros(max_frames, dtype=_lib.FRAME_DTYPE)
+            nfr = np.zeros(1, dtype=np.int32)
+            stats = np.zeros(3, dtype=np.int64)
+            _lib.check(h.lib.tb200_process_decode_host(h.h, x.ctypes.data, dt, 1, n, f.ctypes.data, dibits.ctypes.data,
+                                                       symbols.ctypes.data, stride, cnt.ctypes.data, phase.ctypes.data,
+                                                       rec.ctypes.data, max_frames, nfr.ctypes.data, stats.ctypes.data, None))
+            out = dibits[:int(cnt[0])].copy()
+            _spec.publish(out.copy(), rec[:int(nfr[0])].copy(), stats)
+        else:
+            _lib.check(h.lib.tb200_process_batch_host(h.h, x.ctypes.data, dt, 1, n, f.ctypes.data, dibits.ctypes.data,
+                                                      symbols.ctypes.data, stride, cnt.ctypes.data, phase.ctypes.data, None))
+            out = dibits[:int(cnt[0])].copy()
         nsym = self._n_symbols(p, int(phase[0]))
         self.symbols = symbols[:nsym].copy()
         self.best_phase = int(phase[0])
-        return dibits[:nd].copy()
+        return out
 
     def process_sc16(self, iq_int16, freq_offset=0):
         """process() for the bladeRF's native SC16Q11 buffer (interleaved int16 I, Q): the conversion
