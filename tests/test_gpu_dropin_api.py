@@ -538,3 +538,18 @@ def test_decode_host_entry_point_equals_device_entry_point(api):
     k = int(nfr.cpu()[0])
     ref = frames.cpu().numpy().view(_lib.FRAME_DTYPE)[:k]
     assert k == len(rec) > 0 and rec.tobytes() == ref.tobytes()
+
+
+def test_symbols_to_bits_out_of_range_values_follow_the_reference(api):
+    """decoder.py:149-166: with max <= 3 every symbol goes through int(s) & 3 (-1 -> 3, -6 -> 2); with max > 3 the 8-PSK
+    table applies and anything outside 0..7 (negative, 9, 300) maps to 0."""
+    dec = api[1].TetraDecoder(auto_decrypt=False)
+    for sym in (np.array([-1, 0, 3, -6, 2, 1, -4]), np.array([-1, 9, 5, 300, 7, 3, 0, -20, 4]), np.array([-3, -2, -1])):
+        bits, mapped = dec.symbols_to_bits(sym)
+        ob, om = oracle.symbols_to_bits(sym)
+        assert np.array_equal(bits, ob) and np.array_equal(mapped, om), sym
+    rng = np.random.default_rng(4)
+    s = rng.integers(-4, 4, 1200)
+    a = dec.decode(s)
+    b = dec.decode((s & 3).astype(np.uint8))
+    assert len(a) == len(b)

@@ -28,6 +28,17 @@ def _unpack510(packed):
     return np.unpackbits(np.asarray(packed, dtype=np.uint8))[:510]
 
 
+def _symbol_bytes(s):
+    """Integer symbols -> the uint8 row the device takes, keeping the reference's treatment of out-of-range values
+    (decoder.py:149-166): when max(symbols) <= 3 every value goes through ``int(s) & 3`` (so -1 reads as 3); otherwise
+    the 8-PSK table applies and anything outside 0..7 maps to 0 — sent as 255, which the device maps to 0 too and which
+    keeps max > 3."""
+    v = np.asarray(s).astype(np.int64)
+    if len(v) == 0 or v.max() <= 3:
+        return (v & 3).astype(np.uint8)
+    return np.where((v < 0) | (v > 255), 255, v).astype(np.uint8)
+
+
 class TetraDecoder:
     """Decodes TETRA frames from demodulated symbols (B200 implementation)."""
 
@@ -93,7 +104,7 @@ class TetraDecoder:
         from .. import _dev
         h = self._handle(n)
         # values above 255 cannot occur for demodulated symbols; saturate so max()>3 still selects the 8-PSK map
-        d = _dev.to_dev(np.clip(s.astype(np.int64), 0, 255).astype(np.uint8), self.device)
+        d = _dev.to_dev(_symbol_bytes(s), self.device)
         bits = _dev.empty((2 * n,), torch.uint8, self.device)
         mapped = _dev.empty((n,), torch.uint8, self.device)
         _lib.check(h.lib.tb200_symbols_to_bits(h.h, d.data_ptr(), n, bits.data_ptr(), mapped.data_ptr(),
@@ -135,7 +146,7 @@ class TetraDecoder:
             ps['crc_fail'] += int(st[2])
             return rec.copy()
         h = self._handle(n)
-        d = np.ascontiguousarray(np.clip(s.astype(np.int64), 0, 255).astype(np.uint8))
+        d = np.ascontiguousarray(_symbol_bytes(s))
         max_frames = (2 * n) // 250 + 2
         if n <= 6000 and h.lib.tb200_host_oneshot_fits(h.h, 1, 0, max_frames, 0):
             # one C-ABI call: upload, fused decode launch, one download, one synchronisation
