@@ -553,3 +553,24 @@ def test_symbols_to_bits_out_of_range_values_follow_the_reference(api):
     a = dec.decode(s)
     b = dec.decode((s & 3).astype(np.uint8))
     assert len(a) == len(b)
+
+
+def test_pipeline_as_many_chunks_as_lanes(api):
+    """max_chunks == n_lanes == n_chunks: every lane's handle holds ONE chunk, so the batch must be split across the
+    lanes (round-1 advice: the single-lane shortcut overran handle 0); varying n_chunks between unjoined calls."""
+    import torch
+    from tetraear_b200 import pipeline, synth
+    L = 20000
+    cap = synth.make_capture(L * 4, 130, seed=5).reshape(4, L)
+    pipe = pipeline.ReceivePipeline(2.4e6, L, max_chunks=4, mode="fast32", n_lanes=4)
+    nfr, frames, stats = pipe.run_host(cap)
+    ndib, dib = pipe.n_dibits.cpu().numpy(), pipe.dibits.cpu().numpy()
+    for c in range(4):
+        od, _, _ = oracle.process(cap[c], 2.4e6, 0.0)
+        assert ndib[c] == len(od) and np.array_equal(dib[c, :ndib[c]], od)
+    dev = torch.from_numpy(cap.view(np.float32).reshape(4, L, 2)).cuda()
+    for n in (4, 3, 2, 4, 1, 4):
+        pipe.run_device(dev[:n].contiguous(), join=False)
+    pipe.join()
+    torch.cuda.synchronize()
+    assert np.array_equal(pipe.n_dibits.cpu().numpy()[:4], ndib[:4])

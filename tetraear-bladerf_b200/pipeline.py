@@ -76,7 +76,7 @@ class ReceivePipeline:
         n_chunks = iq.shape[0]
         assert iq.is_cuda and iq.dtype in (torch.float32, torch.int16) and iq.shape[1] == self.chunk_len and iq.is_contiguous()
         main = torch.cuda.current_stream(self.dev)
-        if self.n_lanes == 1 or n_chunks <= self.n_lanes:
+        if self.n_lanes == 1 or n_chunks <= min(self.n_lanes, self.lane_chunks):
             self._run_slice(self.handles[0], main.cuda_stream, iq, freq_off, 0, n_chunks, decode)
             return n_chunks
         per = (n_chunks + self.n_lanes - 1) // self.n_lanes
@@ -97,8 +97,9 @@ class ReceivePipeline:
                 ev.record(st)
                 self._pending.append(ev)
                 continue
-            if self._dec_done[li][buf] is not None:
-                st.wait_event(self._dec_done[li][buf])          # the decode that last read this dibit buffer
+            for done_prev in self._dec_done:                    # every decode that last read this dibit buffer (the
+                if done_prev[buf] is not None:                  # rows of a lane move when n_chunks changes between calls)
+                    st.wait_event(done_prev[buf])
             self._run_slice(self.handles[li], st.cuda_stream, iq, freq_off, lo, hi, False)
             ev = torch.cuda.Event()
             ev.record(st)
@@ -190,7 +191,7 @@ class ReceivePipeline:
             f = torch.as_tensor(np.asarray(freq_off, dtype=np.float64)).to(self.dev, non_blocking=True)
         self.stats.zero_()
         main = torch.cuda.current_stream(self.dev)
-        lanes = self.n_lanes if n_chunks > self.n_lanes else 1
+        lanes = 1 if n_chunks <= min(self.n_lanes, self.lane_chunks) else self.n_lanes
         per = (n_chunks + lanes - 1) // lanes
         fork = torch.cuda.Event()
         fork.record(main)
