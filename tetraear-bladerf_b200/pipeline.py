@@ -77,6 +77,7 @@ class ReceivePipeline:
         assert iq.is_cuda and iq.dtype in (torch.float32, torch.int16) and iq.shape[1] == self.chunk_len and iq.is_contiguous()
         main = torch.cuda.current_stream(self.dev)
         if self.n_lanes == 1 or n_chunks <= min(self.n_lanes, self.lane_chunks):
+            self.join()                         # handle 0 and the output rows may still be in use by unjoined lane work
             self._run_slice(self.handles[0], main.cuda_stream, iq, freq_off, 0, n_chunks, decode)
             return n_chunks
         per = (n_chunks + self.n_lanes - 1) // self.n_lanes
