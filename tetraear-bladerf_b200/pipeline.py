@@ -86,6 +86,7 @@ class ReceivePipeline:
         buf = self._flip
         self._flip ^= 1
         self.dibits, self.n_dibits = self._dibits2[buf], self._n_dibits2[buf]     # where this batch's rows go
+        prev_done = [d[buf] for d in self._dec_done]            # decodes of EARLIER calls (not the ones launched below)
         for li in range(self.n_lanes):
             lo, hi = li * per, min(n_chunks, (li + 1) * per)
             if lo >= hi:
@@ -98,9 +99,9 @@ class ReceivePipeline:
                 ev.record(st)
                 self._pending.append(ev)
                 continue
-            for done_prev in self._dec_done:                    # every decode that last read this dibit buffer (the
-                if done_prev[buf] is not None:                  # rows of a lane move when n_chunks changes between calls)
-                    st.wait_event(done_prev[buf])
+            for done_prev in prev_done:                         # every decode that last read this dibit buffer (the
+                if done_prev is not None:                       # rows of a lane move when n_chunks changes between calls)
+                    st.wait_event(done_prev)
             self._run_slice(self.handles[li], st.cuda_stream, iq, freq_off, lo, hi, False)
             ev = torch.cuda.Event()
             ev.record(st)
