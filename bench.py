@@ -697,7 +697,8 @@ def other_workloads(device, peak):
     smooth = torch.empty((nfr, 4096), dtype=torch.float32, device=dev)
     stats = torch.empty((nfr, 8), dtype=torch.float64, device=dev)
     ms = timed(lambda: an.run_device(iq, nfr, 4096, denoise=True, power=power, smoothed=smooth, stats=stats), reps=3, warm=1)
-    byts = n * 8 + nfr * 4096 * 4 * 3          # IQ read, power written, power re-read + smoothed written by the EMA pass
+    byts = n * 8 + nfr * 4096 * 4 * 2          # ALGORITHMIC bytes: IQ read, power written, smoothed written;
+    #                                            the EMA pass's re-read of the power array is traffic, not useful bytes
     out["c2_psd_4096_ema_60s_f32"] = {"msamples_per_s": round(n / ms / 1e3, 1), "ms": round(ms, 3), "frames": nfr,
                                   "achieved_gbs": round(byts / ms / 1e6, 1), "frac_of_hbm_peak": round(byts / ms / 1e6 / peak, 4)}
     # same 60 s with linear (Welch) averaging of 8 frames before the dB conversion ("w/ averaging"): 1/8 of the output
@@ -706,7 +707,7 @@ def other_workloads(device, peak):
     s8 = torch.empty((nfr // 8, 4096), dtype=torch.float32, device=dev)
     st8 = torch.empty((nfr // 8, 8), dtype=torch.float64, device=dev)
     ms8 = timed(lambda: an8.run_device(iq, nfr, 4096, denoise=True, power=p8, smoothed=s8, stats=st8), reps=3, warm=1)
-    byts8 = n * 8 + (nfr // 8) * 4096 * 4 * 3
+    byts8 = n * 8 + (nfr // 8) * 4096 * 4 * 2
     out["c2_psd_4096_avg8_ema_60s_f32"] = {"msamples_per_s": round(n / ms8 / 1e3, 1), "ms": round(ms8, 3), "frames_out": nfr // 8,
                                        "achieved_gbs": round(byts8 / ms8 / 1e6, 1),
                                        "frac_of_hbm_peak": round(byts8 / ms8 / 1e6 / peak, 4)}
