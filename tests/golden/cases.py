@@ -193,3 +193,37 @@ def process_edge_cases():
     out.append((2.4e6, -700.0, cap.astype(np.complex128)))
     out.append((1.8e6, 0.0, synth.make_capture(25000, 98, seed=778).astype(np.complex128)))
     return out
+
+
+def spike_cases(n=48, seed=33):
+    """(freqs_mhz, powers_db, click_mhz, search_range_hz, noise_floor_db) for WaterfallWidget.find_spike_band_near
+    (ui/modern.py:774-857): carriers of 1 ... 40 bins on a noise floor, spikes touching the window edge, two spikes in
+    one window, flat windows (threshold above everything but the peak), empty windows, unequal array lengths."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for case in range(n):
+        nb = 2048 if case % 4 else 512
+        fc = 392.0 + rng.uniform(-1, 1)
+        freqs = fc + (np.arange(nb) - nb // 2) * (2.4 / nb)
+        floor = float(rng.uniform(-105, -85))
+        powers = floor + rng.uniform(-3, 3, nb)
+        kind = case % 6
+        pk = int(rng.integers(60, nb - 60))
+        width = int(rng.choice([1, 2, 5, 11, 21, 40]))
+        if kind in (0, 1, 2):
+            powers[pk - width // 2: pk - width // 2 + width] = -40.0 + rng.uniform(-2, 2, width)
+        if kind == 1:
+            powers[pk + width + 3: pk + width + 6] = -38.0      # a second, stronger spike nearby
+        if kind == 2:
+            powers = powers[: nb - 9]
+            pk = min(pk, nb - 80)
+        rng_hz = float(rng.choice([3000.0, 12500.0, 25000.0, 100000.0]))
+        click = float(freqs[pk] + rng.uniform(-0.003, 0.003))
+        if kind == 3:                                           # spike cut by the window edge
+            powers[pk: pk + 30] = -45.0
+            click, rng_hz = float(freqs[pk + 29]), 12500.0
+        if kind == 4:
+            click, rng_hz = float(freqs[-1] + 1.0), 1000.0      # empty window
+        noise = floor if case % 3 else -100.0
+        out.append((freqs, powers, click, rng_hz, noise))
+    return out

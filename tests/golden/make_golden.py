@@ -26,7 +26,7 @@ logging.disable(logging.CRITICAL)
 
 from oracle import ref_bridge  # noqa: E402
 from tetraear_b200 import synth  # noqa: E402
-from tests.golden.cases import process_cases, psd_chunks, burst_batch, scanner_cases, voice_cases, afc_cases, peak_cases  # noqa: E402
+from tests.golden.cases import process_cases, psd_chunks, burst_batch, scanner_cases, voice_cases, afc_cases, peak_cases, spike_cases  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SP, TD, TP = ref_bridge.load()
@@ -260,6 +260,21 @@ def gen_peak():
     save("peak.npz", peak=np.array(out, dtype=np.float64))
 
 
+def gen_spike():
+    """WaterfallWidget.find_spike_band_near: lines 774-857 of ui/modern.py exec'd as a plain function against a stub self."""
+    modern = os.path.join(ref_bridge.REFERENCE_ROOT, "tetraear", "ui", "modern.py")
+    src = _lines(modern, 774, 857)
+    assert src.startswith("def find_spike_band_near(self, freq_mhz: float, search_range_hz: float)") and "bandwidth_hz" in src
+    ns = {"np": np}
+    exec(src, ns)
+    out = []
+    for freqs, powers, click, rng_hz, noise in spike_cases():
+        stub = types.SimpleNamespace(current_fft=powers, current_freqs=freqs, noise_floor=noise, bandwidth=25000.0)
+        r = ns["find_spike_band_near"](stub, click, rng_hz)
+        out.append([r["center_mhz"], r["left_mhz"], r["right_mhz"], r["bandwidth_hz"]])
+    save("spike.npz", spike=np.array(out, dtype=np.float64))
+
+
 if __name__ == "__main__":
     proc = gen_process()
     gen_decode(proc)
@@ -269,3 +284,4 @@ if __name__ == "__main__":
     gen_voice()
     gen_afc()
     gen_peak()
+    gen_spike()

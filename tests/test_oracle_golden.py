@@ -175,3 +175,21 @@ def test_afc_rule_matches_reference():
         assert afc_step(freqs, powers, tuned) == w          # host helper (scalar GUI logic, no device work)
         moved += w != tuned
     assert 5 < moved < len(want)
+
+
+def test_find_spike_band_near_matches_reference():
+    """WaterfallWidget.find_spike_band_near (ui/modern.py:774-857): centre, edges and clamped bandwidth equal to the golden
+    values produced by the reference's own source lines (tests/golden/make_golden.py::gen_spike)."""
+    import os
+    from tests.conftest import GOLDEN
+    from tests.golden.cases import spike_cases
+    from tetraear_b200.signal import find_spike_band_near
+    want = np.load(os.path.join(GOLDEN, "spike.npz"))["spike"]
+    cases = spike_cases()
+    assert len(want) == len(cases)
+    for (freqs, powers, click, rng_hz, noise), w in zip(cases, want):
+        d = find_spike_band_near(freqs, powers, click, rng_hz, noise_floor=noise, bandwidth=25000.0)
+        assert [d["center_mhz"], d["left_mhz"], d["right_mhz"], d["bandwidth_hz"]] == list(w)
+    assert len(set(want[:, 3])) >= 6 and (want[:, 3] == 1000.0).any() and (want[:, 3] == 25000.0).any()
+    none = find_spike_band_near(None, None, 390.0, 1000.0, bandwidth=12500.0)
+    assert none == {"center_mhz": 390.0, "left_mhz": 390.0, "right_mhz": 390.0, "bandwidth_hz": 12500.0}

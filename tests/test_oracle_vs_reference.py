@@ -147,6 +147,24 @@ def test_find_peak_near_live(ref):
         assert find_peak_near(freqs, powers, click, rng_hz) == want
 
 
+@needs_full
+def test_find_spike_band_near_live(ref):
+    """The shipped helper against ui/modern.py:774-857 exec'd from the source text, on fresh cases."""
+    import os, textwrap, types
+    from tests.golden.cases import spike_cases
+    from tetraear_b200.signal import find_spike_band_near
+    path = os.path.join(ref_bridge.REFERENCE_ROOT, "tetraear", "ui", "modern.py")
+    with open(path) as f:
+        src = textwrap.dedent("".join(f.readlines()[773:857]))
+    assert src.startswith("def find_spike_band_near(self, freq_mhz: float, search_range_hz: float)")
+    ns = {"np": np}
+    exec(src, ns)
+    for freqs, powers, click, rng_hz, noise in spike_cases(n=72, seed=9):
+        stub = types.SimpleNamespace(current_fft=powers, current_freqs=freqs, noise_floor=noise, bandwidth=20000.0)
+        assert find_spike_band_near(freqs, powers, click, rng_hz, noise_floor=noise, bandwidth=20000.0) == \
+               ns["find_spike_band_near"](stub, click, rng_hz)
+
+
 def _oracle_stage(method, kw, x):
     """The oracle's counterpart of a SignalProcessor stage call (reference defaults: sample_rate 2.4e6)."""
     fs = kw.get("sample_rate", 2.4e6)

@@ -140,6 +140,42 @@ def find_peak_near(freqs_mhz, powers, freq_mhz, search_range_hz):
     return float(freqs[pk])
 
 
+def find_spike_band_near(freqs_mhz, powers, freq_mhz, search_range_hz, noise_floor=-100.0, bandwidth=25000.0):
+    """WaterfallWidget.find_spike_band_near (modern.py:774-857): the strongest bin within the range and the contiguous
+    run around it that stays above max(peak - 6 dB, 20th percentile of the window + 6 dB, noise_floor + 3 dB); returns
+    centre / edges (MHz) and the bandwidth clamped to 1 kHz ... 250 kHz.  `noise_floor` and `bandwidth` are the widget
+    attributes the reference reads.  Scalar GUI helper, host side like find_peak_near."""
+    nothing = {"center_mhz": float(freq_mhz), "left_mhz": float(freq_mhz), "right_mhz": float(freq_mhz),
+               "bandwidth_hz": float(bandwidth)}
+    if freqs_mhz is None or powers is None or len(freqs_mhz) == 0 or len(powers) == 0:
+        return nothing
+    freqs = np.asarray(freqs_mhz, dtype=np.float64)
+    pw = np.asarray(powers, dtype=np.float64)
+    n = min(len(freqs), len(pw))
+    freqs, pw = freqs[:n], pw[:n]
+    half = float(search_range_hz) / 1e6
+    idx = np.nonzero((freqs >= float(freq_mhz) - half) & (freqs <= float(freq_mhz) + half))[0]
+    if len(idx) == 0:
+        return nothing
+    pk = int(idx[np.argmax(pw[idx])])
+    thr = max(float(pw[pk]) - 6.0, float(np.percentile(pw[idx], 20)) + 6.0, float(noise_floor) + 3.0)
+    left = pk
+    while left > idx[0] and pw[left] >= thr:
+        left -= 1
+    if pw[left] < thr and left < pk:
+        left += 1
+    right = pk
+    while right < idx[-1] and pw[right] >= thr:
+        right += 1
+    if pw[right] < thr and right > pk:
+        right -= 1
+    lo, hi = float(freqs[left]), float(freqs[right])
+    if hi < lo:
+        lo, hi = hi, lo
+    return {"center_mhz": (lo + hi) / 2.0, "left_mhz": lo, "right_mhz": hi,
+            "bandwidth_hz": float(max(1000.0, min(250000.0, (hi - lo) * 1e6)))}
+
+
 def afc_step(freqs_mhz, powers, freq_mhz, window_mhz=0.010, min_power_db=-60.0, min_offset_mhz=0.00005, gain=0.1):
     """The GUI's auto-follow rule (ModernTetraGUI.on_spectrum, modern.py:5223-5257): strongest bin within
     +-10 kHz of the tuned frequency; if it is above -60 dB and more than 50 Hz away, move 10 % of the way.
