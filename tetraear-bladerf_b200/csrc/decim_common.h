@@ -65,6 +65,17 @@ __device__ __forceinline__ void tma_load_1d(void *smem, const void *gmem, unsign
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  ::"r"(sa), "l"(gmem), "r"(bytes), "r"(ba) : "memory");
 }
+// the same with an L2 evict-first policy: a capture streams through once (192 MB against 126 MB of L2) and must not push
+// out the decimated / filtered intermediates the next kernels of the step re-read
+__device__ __forceinline__ void tma_load_1d_stream(void *smem, const void *gmem, unsigned bytes, uint64_t *bar)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem), ba = (unsigned)__cvta_generic_to_shared(bar);
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(ba), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
+                 ::"r"(sa), "l"(gmem), "r"(bytes), "r"(ba), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 {
     unsigned a = (unsigned)__cvta_generic_to_shared(bar);

@@ -183,7 +183,7 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
     if (interior) {
         if (threadIdx.x == 0) {
             mbar_init(&tile_bar, 1);
-            tma_load_1d(fd_raw, xc + g0, TMA_BYTES, &tile_bar);
+            tma_load_1d_stream(fd_raw, xc + g0, TMA_BYTES, &tile_bar);
         }
         __syncthreads();                                       // barrier initialised before anybody polls it
         mbar_wait(&tile_bar, 0);
@@ -195,7 +195,7 @@ decim_fast_kernel(const float2 *__restrict__ x, long n, long chunk_stride, int t
         if (!bulk) ja = jb = 0;
         if (bulk && threadIdx.x == 0) {
             mbar_init(&tile_bar, 1);
-            tma_load_1d(fd_raw + ja, xc + g0 + ja, (unsigned)((jb - ja) * 8), &tile_bar);
+            tma_load_1d_stream(fd_raw + ja, xc + g0 + ja, (unsigned)((jb - ja) * 8), &tile_bar);
         }
         for (int s = threadIdx.x; s < TILE + 1; s += blockDim.x)
             if (s < ja || s >= jb) fd_raw[s] = padded_sample(xc, n, t0 - 1 + s);
