@@ -55,6 +55,11 @@ class TetraDecoder:
             'TS2': np.array([0, 1, 1, 1, 1, 0, 1, 0, 0, 1, 0, 0, 0, 0, 1, 1, 0, 1, 1, 1, 0, 0]),
         }
         self.post_frame_hook = None
+        if key_manager is not None:
+            # accepted for signature compatibility; the brute-force decryptor (decoder.py:576-833) is host-side GUI work
+            # outside this path (behavioural notes): say so once instead of silently ignoring the keys
+            logger.warning("TetraDecoder: key_manager is accepted but frames are not decrypted on this path; chain the "
+                           "reference's own decryptor / parser through post_frame_hook (INTEGRATION.md section A)")
         self._setup_common_keys()
         self._h = None
         self._cap = 0
