@@ -157,7 +157,8 @@ etsi_decode_kernel(const int8_t *__restrict__ soft, long n, EtsiParams P, uint8_
 // words in shared memory.
 struct EtsiGenParams {
     uint32_t scr[14];      // scrambling sequence bits
-    uint16_t slot[432];    // received position k -> trellis input slot 3 * step + g
+    uint16_t row[432];     // received position k -> row of the de-interleaved array (= type-3 index j - 1)
+    uint16_t step[960];    // [K2][3]: rows feeding g1, g2, g3 of every trellis step (K3 = the zero row: punctured)
     int K1, K2, K3, crc;
 };
 
@@ -184,28 +185,30 @@ __device__ __forceinline__ uint32_t acs_step3(int (&pm)[16], int v1, int v2, int
     return word;
 }
 
+// Shared memory per CTA: the K3 received values per block ([K3 + 1][PITCH] int8, row K3 = zeros = "punctured"), the
+// survivor words ([K2][THREADS] uint16) and a per-step descriptor (three row numbers, the same for every thread:
+// broadcast reads).  The first form kept a [3 K2][PITCH] input array with the erasures stored: 1.5 KB per block at
+// K2 = 292, two CTAs of 64 threads per SM.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
-etsi_decode_gen_kernel(const int8_t *__restrict__ soft, long n, EtsiGenParams P, uint8_t *__restrict__ bits_out,
-                       uint8_t *__restrict__ crc_ok, int32_t *__restrict__ metric)
+etsi_decode_gen_kernel(const int8_t *__restrict__ soft, long n, const __grid_constant__ EtsiGenParams P,
+                       uint8_t *__restrict__ bits_out, uint8_t *__restrict__ crc_ok, int32_t *__restrict__ metric)
 {
     constexpr int PITCH = THREADS + 4;
     extern __shared__ __align__(16) unsigned char etsi_sm[];
     const int K1 = P.K1, K2 = P.K2, K3 = P.K3;
-    int8_t *T = reinterpret_cast<int8_t *>(etsi_sm);                                    // [3 K2][PITCH]
-    uint16_t *D = reinterpret_cast<uint16_t *>(etsi_sm + ((3 * K2 * PITCH + 15) & ~15));   // [K2][THREADS]
-    __shared__ uint16_t slot_s[432];
+    int8_t *T = reinterpret_cast<int8_t *>(etsi_sm);                                        // [K3 + 1][PITCH]
+    uint16_t *D = reinterpret_cast<uint16_t *>(etsi_sm + (((K3 + 1) * PITCH + 15) & ~15));   // [K2][THREADS]
+    uint16_t *desc = D + K2 * THREADS;                                                      // [K2][3] row numbers
+    __shared__ uint16_t row_s[432];
     __shared__ uint32_t scr_s[14];
     const int tid = threadIdx.x;
     const long blk0 = (long)blockIdx.x * THREADS;
     const int nb = (int)((n - blk0 < THREADS) ? (n - blk0) : THREADS);
-    for (int i = tid; i < K3; i += THREADS) slot_s[i] = P.slot[i];
+    for (int i = tid; i < K3; i += THREADS) row_s[i] = P.row[i];
     if (tid < 14) scr_s[tid] = P.scr[tid];
-    {
-        uint32_t *Tz = reinterpret_cast<uint32_t *>(T);
-        const int nz = (3 * K2 * PITCH + 3) / 4;
-        for (int i = tid; i < nz; i += THREADS) Tz[i] = 0u;
-    }
+    for (int i = tid; i < 3 * K2; i += THREADS) desc[i] = P.step[i];
+    for (int i = tid; i < PITCH; i += THREADS) T[K3 * PITCH + i] = 0;
     __syncthreads();
     {
         const int8_t *src = soft + blk0 * K3;
@@ -215,7 +218,7 @@ etsi_decode_gen_kernel(const int8_t *__restrict__ soft, long n, EtsiGenParams P,
         for (int idx = tid; idx < tot; idx += THREADS) {
             const int v = src[idx];
             const int pk = (scr_s[k >> 5] >> (k & 31)) & 1;
-            T[(int)slot_s[k] * PITCH + r] = (int8_t)(pk ? -v : v);
+            T[(int)row_s[k] * PITCH + r] = (int8_t)(pk ? -v : v);
             r += DR; k += DK;
             if (k >= K3) { k -= K3; ++r; }
         }
@@ -228,8 +231,8 @@ etsi_decode_gen_kernel(const int8_t *__restrict__ soft, long n, EtsiGenParams P,
     for (int i = 0; i < 16; ++i) pm[i] = (i == 0) ? 0 : -(1 << 28);
     const int8_t *tp = T + tid;
     for (int t = 0; t < K2; ++t) {
-        const int v1 = tp[0], v2 = tp[PITCH], v3 = tp[2 * PITCH];
-        tp += 3 * PITCH;
+        const int r1 = desc[3 * t], r2 = desc[3 * t + 1], r3 = desc[3 * t + 2];
+        const int v1 = tp[r1 * PITCH], v2 = tp[r2 * PITCH], v3 = tp[r3 * PITCH];
         D[t * THREADS + tid] = (uint16_t)acs_step3(pm, v1, v2, v3);
     }
     const int final_metric = pm[0];
@@ -414,6 +417,7 @@ int launch_etsi_decode_custom(tb200_handle h, const int8_t *soft, long n, int K1
     // type-3 bit j (1-based) is mother bit k = 8 ((i-1) div t) + P(i - t ((i-1) div t)), i = j + (j-1) div d;
     // it was sent at type-4 position 1 + (a j mod K3)
     std::vector<char> seen((size_t)K3, 0);
+    for (int i = 0; i < 3 * K2; ++i) P.step[i] = (uint16_t)K3;
     for (int j = 1; j <= K3; ++j) {
         const int i = div ? j + (j - 1) / div : j;
         const int blk = (i - 1) / t;
@@ -423,12 +427,13 @@ int launch_etsi_decode_custom(tb200_handle h, const int8_t *soft, long n, int K1
         const int pos = (int)(((long)a * j) % K3);
         if (seen[pos]) return fail(TB200_E_ARG, "tb200_etsi_decode_custom: interleaver (%d, %d) is not a permutation", K3, a);
         seen[pos] = 1;
-        P.slot[pos] = (uint16_t)(3 * step + g);
+        P.row[pos] = (uint16_t)(j - 1);
+        P.step[3 * step + g] = (uint16_t)(j - 1);
     }
     if ((reinterpret_cast<uintptr_t>(bits) & 3) != 0) return fail(TB200_E_ARG, "tb200_etsi_decode_custom: d_bits must be 4-byte aligned");
     if (n <= 0) return TB200_OK;
     constexpr int T = 64;
-    const size_t sm = (size_t)(((3 * K2 * (T + 4) + 15) & ~15) + K2 * T * 2);
+    const size_t sm = (size_t)((((K3 + 1) * (T + 4) + 15) & ~15) + K2 * T * 2 + 3 * K2 * 2);
     cudaError_t e = cudaFuncSetAttribute(etsi_decode_gen_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return fail(TB200_E_CUDA, "cudaFuncSetAttribute(etsi_decode_gen_kernel): %s", cudaGetErrorString(e));
     etsi_decode_gen_kernel<T><<<(unsigned)((n + T - 1) / T), T, sm, st>>>(soft, n, P, bits, crc_ok, metric);
