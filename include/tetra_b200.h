@@ -144,6 +144,10 @@ int tb200_set_sample_rate(tb200_handle h, double sample_rate); /* attr is mutate
  * t = 16 + (k + 1) fs / 18000 samples exactly, so its matched-filter output can be checked against numpy.convolve with
  * the same taps (tb200_debug_read region 4 returns the 32 x 32 interpolating RRC tap table).  Default 0. */
 #define TB200_OPT_ETSI_OPEN_LOOP 5
+/* TB200_OPT_ETSI_SEG_LANES = 6: form of tb200_etsi_demod_segmented.  0 (default): two stages — the RRC matched filter once
+ * per input sample for all streams, then one thread per (stream, segment) running the timing loop on 8-tap interpolations
+ * of its output; 8: eight lanes per segment with the 32-tap interpolating matched filter inside the loop. */
+#define TB200_OPT_ETSI_SEG_LANES 6
 int tb200_set_option(tb200_handle h, int option, int value);
 size_t tb200_workspace_bytes(tb200_handle h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */

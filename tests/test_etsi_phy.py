@@ -148,25 +148,26 @@ def test_segmented_demodulator_matches_the_sequential_loop(fs, sigma, rate_ppm):
     n = min(len(v) for v in streams)
     x = np.stack([v[:n] for v in streams])
     out = {}
-    for seg in (False, True):
-        rx = etsi.EtsiReceiver(fs, max_streams=4, max_samples=n, segmented=seg, afc=False)
+    for seg in (False, True, 8):                                       # sequential, two-stage (default), eight-lane
+        rx = etsi.EtsiReceiver(fs, max_streams=4, max_samples=n, segmented=bool(seg), afc=False, seg_lanes=8 if seg == 8 else 0)
         res = rx.run(x, init)
         out[seg] = (rx.n_soft.cpu().numpy().copy(), rx.soft.cpu().numpy().copy(), res)
-    assert rx._scratch is not None                                     # the segmented form did run
+        assert (rx._scratch is not None) == bool(seg)                  # the segmented forms did run
     ns0, soft0, res0 = out[False]
-    ns1, soft1, res1 = out[True]
-    for s in range(4):
-        assert abs(int(ns0[s]) - int(ns1[s])) <= 2 * 2, (s, ns0[s], ns1[s])      # the last symbols may fall either side of the end
-        m = min(int(ns0[s]), int(ns1[s]))
-        assert m > 2 * 255 * (n_bursts - 1)
-        a, b = soft0[s, :m], soft1[s, :m]
-        # skip the first burst (both loops are still pulling in there, identically, but decisions on it are not the point)
-        agree = np.mean((a[510:] > 0) == (b[510:] > 0))
-        assert agree >= (1.0 if sigma == 0.0 else 0.9995), (s, agree)
-        assert np.max(np.abs(a[510:] - b[510:])) < (0.25 if sigma == 0.0 else 0.6)    # timing jitter of two loops, same decisions
-        good0 = sum(bool(v["crc_ok"].all()) for v in res0[s])
-        good1 = sum(bool(v["crc_ok"].all()) for v in res1[s])
-        assert good1 >= good0 - 1 and good1 >= n_bursts - 5, (s, good0, good1)
+    for form in (True, 8):
+      ns1, soft1, res1 = out[form]
+      for s in range(4):
+          assert abs(int(ns0[s]) - int(ns1[s])) <= 2 * 2, (s, ns0[s], ns1[s])      # the last symbols may fall either side of the end
+          m = min(int(ns0[s]), int(ns1[s]))
+          assert m > 2 * 255 * (n_bursts - 1)
+          a, b = soft0[s, :m], soft1[s, :m]
+          # skip the first burst (both loops are still pulling in there, identically, but decisions on it are not the point)
+          agree = np.mean((a[510:] > 0) == (b[510:] > 0))
+          assert agree >= (1.0 if sigma == 0.0 else 0.9995), (s, agree)
+          assert np.max(np.abs(a[510:] - b[510:])) < (0.25 if sigma == 0.0 else 0.6)    # timing jitter of two loops, same decisions
+          good0 = sum(bool(v["crc_ok"].all()) for v in res0[s])
+          good1 = sum(bool(v["crc_ok"].all()) for v in res1[s])
+          assert good1 >= good0 - 1 and good1 >= n_bursts - 5, (s, good0, good1)
 
 
 @pytest.mark.gpu

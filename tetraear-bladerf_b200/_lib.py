@@ -19,6 +19,7 @@ OPT_PSD_F32 = 2
 OPT_DECIM_TC = 3
 OPT_PSD_AVG = 4
 OPT_ETSI_OPEN_LOOP = 5
+OPT_ETSI_SEG_LANES = 6
 
 
 class Config(C.Structure):

@@ -92,6 +92,7 @@ static size_t carve(tb200_handle h, char *base)
     size_t nf = (size_t)cfg.max_fft;
     h->psd_tables = c.take<double>((2 * nf + 2 * (nf / 2 + nf / 4 + 1)) * sizeof(double));
     h->etsi_taps = c.take<float>(32 * 32 * sizeof(float));
+    h->etsi_itab = c.take<float>(32 * 8 * sizeof(float));
     h->tc_bmat_bytes = (C && L) ? 2 * 16 * 48 * 16 + 128 : 0;     // Bhi + Blo, up to 16 K-chunks x 48 columns x 16 bytes (+ 16 phase counters)
     h->tc_bmat = c.take<float>(h->tc_bmat_bytes);
     size_t MC = (size_t)cfg.max_channels;
@@ -306,6 +307,7 @@ extern "C" int tb200_set_option(tb200_handle h, int option, int value)
     case TB200_OPT_DECIM_TC: h->decim_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return TB200_OK;
     case TB200_OPT_PSD_AVG: h->psd_avg = value > 1 ? value : 1; return TB200_OK;
     case TB200_OPT_ETSI_OPEN_LOOP: h->etsi_open_loop = value ? 1 : 0; return TB200_OK;
+    case TB200_OPT_ETSI_SEG_LANES: h->etsi_seg_lanes = value == 8 ? 8 : 0; return TB200_OK;
     default: return fail(TB200_E_ARG, "tb200_set_option: unknown option %d", option);
     }
 }

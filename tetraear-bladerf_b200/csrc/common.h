@@ -51,6 +51,7 @@ struct tb200_handle_s {
     int64_t launches;
     // optional per-stage CUDA-event timing (tb200_profile_*): pairs recorded on the launching stream
     int psd_f32;                 // PSD: float32 FFT + dB (dense config mode) instead of float64
+    int etsi_seg_lanes;          // tb200_etsi_demod_segmented: 0 = two-stage form (default), 8 = eight-lane kernel
     int etsi_open_loop;          // etsi demodulator: timing loop gains 0 (fixed symbol period; validation of the matched filter)
     int psd_avg;                 // PSD: linear (Welch) average of this many consecutive frames per output frame (>= 1)
     int chan_f32;                // FAST mode: run the channel filter's recurrences in float32 (tb200_set_option)
@@ -82,6 +83,7 @@ struct tb200_handle_s {
     float *chan_proto, *chan_tw; int chan_M;   // channelizer prototype [6 M], twiddles, M they are for
     double etsi_taps_fs;                      // fs the tap table below was built for (0 = none)
     float *etsi_taps;                         // [32 phases][32 taps] interpolating matched filter
+    float *etsi_itab;                         // [32 phases][8 taps] fractional-delay interpolator of the two-stage demodulator
     float *tc_bmat; size_t tc_bmat_bytes;     // tensor-core decimator weights (Bhi, Blo in the canonical layout)
     int tc_key_q; float tc_key_sos[24];       // design the weights above were built for (q = 0: none)
     long long *tc_timing;                     // phase counters of the tensor-core decimator (profiling aid) or null

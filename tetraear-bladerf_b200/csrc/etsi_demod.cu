@@ -14,6 +14,7 @@
 #include <cmath>
 #include "common.h"
 #include "kernels.h"
+#include "packed.h"
 
 namespace tb200 {
 
@@ -179,9 +180,164 @@ etsi_demod_kernel(const float2 *__restrict__ iq, int n_streams, long n, long str
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two-stage time-parallel form (default of tb200_etsi_demod_segmented).  The eight-lane kernel above evaluates the
+// 32-tap matched filter INSIDE the sequential loop, twice per symbol at the loop's current timing phase: ~210 warp
+// instructions per symbol and the kernel is issue-bound (757 M instructions per 800 x 10 000 samples).  But the matched
+// filter does not depend on the loop: stage 1 runs it ONCE per input sample for all streams in parallel
+// (etsi_mf_kernel, y[i] = sum_t h0[t] x[i - 15 + t]: the phase-0 row of the same tap table), and the loop of stage 2
+// only INTERPOLATES y at its timing instants with an 8-tap fractional-delay kernel (Kaiser-windowed sinc, beta = 6,
+// 32 phases: 1e-3 rms of full scale on a raised-cosine signal at 2 ... 4 samples per symbol, below the 1/32-sample
+// phase quantisation both forms share) — 16 multiply-adds per sample instead of 64, by ONE THREAD per segment, so a warp
+// advances 32 segments per instruction and the segments can be short (160 symbols + 160 of warm-up).  Same loop
+// equations, same staging rows, same stitch kernel.
+constexpr int EI_TAPS = 8;
+constexpr int ETS_SEG_MIN = 160;
+
+__global__ void __launch_bounds__(256)
+etsi_mf_kernel(const float2 *__restrict__ iq, long n, long stride, const float *__restrict__ taps_g, float2 *__restrict__ y, long ypitch)
+{
+    // 1024 outputs per CTA, FOUR CONSECUTIVE outputs per thread from a 35-sample register window: 8.75 shared loads per
+    // output instead of 32 (the first form, one load per tap and output, was shared-memory bound: 311 us per 32 M outputs).
+    // The tile is stored [e & 3][e >> 2] so that lane L's element 4 L + c is word L + (c >> 2) of row c & 3: conflict-free.
+    constexpr int OUT = 1024, COLS = OUT / 4 + 9;
+    __shared__ float h0[ED_TAPS];
+    __shared__ float2 xs[4][COLS];
+    const int s = blockIdx.y;
+    const long i0 = (long)blockIdx.x * OUT;
+    const float2 *x = iq + (long)s * stride;
+    if (threadIdx.x < ED_TAPS) h0[threadIdx.x] = taps_g[threadIdx.x];          // phase 0 row of the table
+    for (int e = threadIdx.x; e < OUT + ED_TAPS + 3; e += 256) {
+        const long t = i0 - 15 + e;
+        xs[e & 3][e >> 2] = (t >= 0 && t < n) ? x[t] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    float2 w[ED_TAPS + 3];
+#pragma unroll
+    for (int c = 0; c < ED_TAPS + 3; ++c) w[c] = xs[c & 3][threadIdx.x + (c >> 2)];
+    float2 acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        acc[u] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < ED_TAPS; ++t) acc[u] = ffma2(splat(h0[t]), w[u + t], acc[u]);
+    }
+    const long o = i0 + 4 * threadIdx.x;
+    float2 *ys = y + (long)s * ypitch + o;                                       // ypitch even, o multiple of 4: 16-byte aligned
+    if (o + 3 < n) {
+        *reinterpret_cast<float4 *>(ys) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+        *reinterpret_cast<float4 *>(ys + 2) = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (o + u < n) ys[u] = acc[u];
+    }
+}
+
+// both interpolations of a symbol — Y(tau - half) and Y(tau) — from ONE aligned 12-sample window: six 16-byte loads per
+// symbol instead of sixteen 8-byte ones.  (The threads of a warp walk 32 different segments, so every load instruction
+// costs 32 L1 wavefronts whatever its width: the first form of this loop was bound by exactly that, 639 us per 0.8 s.)
+__device__ __forceinline__ void etsi_interp2(const float2 *__restrict__ ys, const float *__restrict__ itab, float tau, float half,
+                                             float2 &on, float2 &mid)
+{
+    const float tm = tau - half;
+    const float fl_on = floorf(tau), fl_mid = floorf(tm);
+    const int i_on = (int)fl_on, i_mid = (int)fl_mid;
+    int ph_on = (int)((tau - fl_on) * ED_PH), ph_mid = (int)((tm - fl_mid) * ED_PH);
+    ph_on = min(max(ph_on, 0), ED_PH - 1);
+    ph_mid = min(max(ph_mid, 0), ED_PH - 1);
+    const int lo = i_mid - (EI_TAPS / 2 - 1), base = lo & ~1;
+    int D = i_on - i_mid;                                     // 1, 2 (or 3 at 4 samples per symbol): how far the on-time window is ahead
+    D = min(max(D, 1), 3);
+    float2 w[12];
+    const float4 *p = reinterpret_cast<const float4 *>(ys + base);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { const float4 v = __ldg(p + q); w[2 * q] = make_float2(v.x, v.y); w[2 * q + 1] = make_float2(v.z, v.w); }
+    if (lo & 1) {
+#pragma unroll
+        for (int i = 0; i < 11; ++i) w[i] = w[i + 1];
+    }
+    const float *cm = itab + ph_mid * EI_TAPS, *co = itab + ph_on * EI_TAPS;
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+#pragma unroll
+    for (int m = 0; m < EI_TAPS; m += 2) {
+        a0 = ffma2(splat(cm[m]), w[m], a0);
+        a1 = ffma2(splat(cm[m + 1]), w[m + 1], a1);
+        const float2 v0 = D == 1 ? w[m + 1] : (D == 2 ? w[m + 2] : w[m + 3]);
+        const float2 v1 = D == 1 ? w[m + 2] : (D == 2 ? w[m + 3] : w[m + 4]);
+        b0 = ffma2(splat(co[m]), v0, b0);
+        b1 = ffma2(splat(co[m + 1]), v1, b1);
+    }
+    mid = make_float2(a0.x + a1.x, a0.y + a1.y);
+    on = make_float2(b0.x + b1.x, b0.y + b1.y);
+}
+
+__global__ void __launch_bounds__(128)
+etsi_loop_kernel(const float2 *__restrict__ y, long ypitch, int n_streams, long n, float sps, float kp, float ki,
+                 const float *__restrict__ itab_g, int n_seg, int seg_syms, float4 *__restrict__ stage,
+                 float2 *__restrict__ sym_stage, int32_t *__restrict__ seg_count)
+{
+    __shared__ float itab[ED_PH * EI_TAPS];
+    for (int i = threadIdx.x; i < ED_PH * EI_TAPS; i += blockDim.x) itab[i] = itab_g[i];
+    __syncthreads();
+    const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = (int)(gid / n_seg), j = (int)(gid - (long)s * n_seg);
+    if (s >= n_streams) return;
+    const float2 *ys = y + (long)s * ypitch;
+    const float t_first = 16.0f + sps, nf_end = (float)n - 17.0f, half = 0.5f * sps;
+    const float Tj = t_first + (float)j * (float)seg_syms * sps;
+    float tau = t_first, emit_from = -1.0f, run_until = nf_end;
+    if (j > 0) { tau = Tj - (float)ED_WARM * sps; emit_from = Tj; }
+    if (j < n_seg - 1) run_until = fminf(nf_end, Tj + ((float)seg_syms + 2.0f) * sps);
+    const int slots = seg_syms + ED_SLACK;
+    const long row = ((long)s * n_seg + j) * slots;
+    float4 *stg = stage + row;
+    float2 *so = sym_stage ? sym_stage + row : nullptr;
+    float integ = 0.f, pavg = 0.f;
+    float2 prev = make_float2(0.f, 0.f);
+    int k = 0, it = 0;
+    while (tau < run_until && k < slots) {
+        float2 on, mid;
+        etsi_interp2(ys, itab, tau, half, on, mid);
+        const float p = on.x * on.x + on.y * on.y;
+        pavg = (it == 0) ? p : 0.98f * pavg + 0.02f * p;
+        const float inv = __fdividef(1.0f, pavg + 1e-20f);
+        float e = ((on.x - prev.x) * mid.x + (on.y - prev.y) * mid.y) * inv;       // Gardner, as in etsi_demod_kernel
+        e = fminf(fmaxf(e, -1.0f), 1.0f);
+        const float dre = on.x * prev.x + on.y * prev.y, dim = on.y * prev.x - on.x * prev.y;
+        if (tau >= emit_from) {
+            if (so) so[k] = on;
+            stg[k] = make_float4(-dim * inv, -dre * inv, tau, 0.f);
+            ++k;
+        }
+        prev = on;
+        if (it > 0) { integ += ki * e; tau += sps - kp * e - integ; }
+        else tau += sps;
+        ++it;
+    }
+    seg_count[(long)s * n_seg + j] = k;
+}
+
+// 8-tap fractional-delay kernels: c[ph][m] weights y[floor(t) - 3 + m] for t = floor(t) + ph / 32
+static void make_interp_table(float *tab)
+{
+    auto bessel_i0 = [](double x) { double s = 1.0, term = 1.0; for (int k = 1; k < 40; ++k) { term *= (x / (2.0 * k)) * (x / (2.0 * k)); s += term; } return s; };
+    const double beta = 6.0, hw = EI_TAPS / 2;
+    for (int ph = 0; ph < ED_PH; ++ph) {
+        double c[EI_TAPS], sum = 0.0;
+        for (int m = 0; m < EI_TAPS; ++m) {
+            const double u = (double)(m - (EI_TAPS / 2 - 1)) - (double)ph / ED_PH;
+            const double r = 1.0 - (u / hw) * (u / hw);
+            const double w = r > 0.0 ? bessel_i0(beta * std::sqrt(r)) / bessel_i0(beta) : 0.0;
+            const double sc = std::fabs(u) < 1e-12 ? 1.0 : std::sin(M_PI * u) / (M_PI * u);
+            c[m] = sc * w; sum += c[m];
+        }
+        for (int m = 0; m < EI_TAPS; ++m) tab[ph * EI_TAPS + m] = (float)(c[m] / sum);
+    }
+}
+
 // One CTA per stream: which symbols of every segment are kept, where they go, then the copy into the stream's
 // contiguous soft bits (pair k-1 belongs to symbol k >= 1, as in the sequential form) and symbols.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 etsi_stitch_kernel(int n_seg, int seg_syms, float sps, const float4 *__restrict__ stage, const float2 *__restrict__ sym_stage,
                    const int32_t *__restrict__ seg_count, float2 *__restrict__ sym_out, float *__restrict__ soft_out,
                    long soft_stride, int32_t *__restrict__ n_soft)
@@ -209,15 +365,17 @@ etsi_stitch_kernel(int n_seg, int seg_syms, float sps, const float4 *__restrict_
     __syncthreads();
     float *sb = soft_out + (long)s * soft_stride;
     float2 *so = sym_out ? sym_out + (long)s * max_sym : nullptr;
-    for (int j = 0; j < n_seg; ++j) {
-        const int b = base[j], c = keep[j];
-        for (int e = threadIdx.x; e < c; e += blockDim.x) {
-            const int k = b + e;
-            if (k >= max_sym) break;
-            const float4 v = st[(long)j * slots + e];
-            if (k > 0) *reinterpret_cast<float2 *>(sb + 2 * (k - 1)) = make_float2(v.x, v.y);
-            if (so) so[k] = sym_stage[((long)s * n_seg + j) * slots + e];
-        }
+    // one flat loop over the output symbols (segment of symbol k by binary search in base[]): every iteration is
+    // independent, so the loads of many symbols are in flight (a loop over the segments with an inner loop over their
+    // symbols serialised ~2 dependent round trips per segment: 122 us per 800 streams x 90 segments)
+    const int total = base[n_seg] < max_sym ? base[n_seg] : max_sym;
+    for (int k = threadIdx.x; k < total; k += blockDim.x) {
+        int lo = 0, hi = n_seg - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (base[mid] <= k) lo = mid; else hi = mid - 1; }
+        const int e = k - base[lo];
+        const float4 v = st[(long)lo * slots + e];
+        if (k > 0) *reinterpret_cast<float2 *>(sb + 2 * (k - 1)) = make_float2(v.x, v.y);
+        if (so) so[k] = sym_stage[((long)s * n_seg + lo) * slots + e];
     }
 }
 
@@ -499,24 +657,36 @@ void make_mf_taps(double sps, float *taps)
     }
 }
 
-// segments per stream and symbols per segment the time-parallel form uses for n samples (n_seg < 2: sequential form)
-static void etsi_seg_plan(long n, double sps, int *n_seg, int *seg_syms)
+// segments per stream and symbols per segment the time-parallel forms use for n samples (n_seg < 2: sequential form);
+// seg_min = ED_SEG_MIN for the eight-lane kernel, ETS_SEG_MIN for the two-stage form
+static void etsi_seg_plan(long n, double sps, int seg_min, int *n_seg, int *seg_syms)
 {
     const long n_sym = (long)(((double)n - 33.0) / sps);
-    long seg = ED_SEG_MIN;
+    long seg = seg_min;
     if (n_sym > seg * ED_SEG_MAX_N) seg = (n_sym + ED_SEG_MAX_N - 1) / ED_SEG_MAX_N;
     long ns = n_sym > 0 ? (n_sym + seg - 1) / seg : 0;
     *n_seg = (int)ns;
     *seg_syms = (int)seg;
 }
 
+static size_t etsi_stage_bytes(int n_streams, int n_seg, int seg_syms, int want_symbols)
+{
+    const size_t rows = (size_t)n_streams * n_seg;
+    return rows * (seg_syms + ED_SLACK) * (sizeof(float4) + (want_symbols ? sizeof(float2) : 0)) + rows * sizeof(int32_t) + 256;
+}
+
+// enough for either form: the eight-lane kernel's staging rows, or the two-stage form's rows + the matched-filter output
+// y [n_streams][n] complex64 + its interpolation table
 int64_t etsi_demod_scratch_bytes(int n_streams, long n, double fs, int want_symbols)
 {
-    int n_seg, seg_syms;
-    etsi_seg_plan(n, fs / 18000.0, &n_seg, &seg_syms);
+    int n_seg, seg_syms, n_seg2, seg_syms2;
+    etsi_seg_plan(n, fs / 18000.0, ED_SEG_MIN, &n_seg, &seg_syms);
+    etsi_seg_plan(n, fs / 18000.0, ETS_SEG_MIN, &n_seg2, &seg_syms2);
     if (n_seg < 2) return 0;
-    const size_t rows = (size_t)n_streams * n_seg;
-    return (int64_t)(rows * (seg_syms + ED_SLACK) * (sizeof(float4) + (want_symbols ? sizeof(float2) : 0)) + rows * sizeof(int32_t) + 256);
+    const size_t a = etsi_stage_bytes(n_streams, n_seg, seg_syms, want_symbols);
+    const size_t b = ((etsi_stage_bytes(n_streams, n_seg2, seg_syms2, want_symbols) + 255) & ~(size_t)255) +
+                     (size_t)n_streams * (size_t)((n + 1) & ~1L) * sizeof(float2) + 256;
+    return (int64_t)(a > b ? a : b);
 }
 
 int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, long stride, double fs, float *taps_dev,
@@ -527,19 +697,43 @@ int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, l
     if (sps < 2.0 || sps > 4.01) return fail(TB200_E_ARG, "tb200_etsi_demod_batch: %.3f samples/symbol outside [2, 4]", sps);
     if (n >= (1L << 30) || (soft_stride & 1) || (reinterpret_cast<uintptr_t>(soft) & 7)) return fail(TB200_E_ARG, "tb200_etsi_demod_batch: n < 2^30, even soft_stride and 8-byte aligned d_soft required");
     if (h->etsi_taps_fs != fs) {                 // the tap table depends on fs only: upload once per handle
-        float taps[ED_PH * ED_TAPS];
+        float taps[ED_PH * ED_TAPS], itab[ED_PH * EI_TAPS];
         make_mf_taps(sps, taps);
+        make_interp_table(itab);
         TB_CUDA(cudaMemcpyAsync(taps_dev, taps, sizeof(taps), cudaMemcpyHostToDevice, st));
-        TB_CUDA(cudaStreamSynchronize(st));      // `taps` is a stack buffer
+        TB_CUDA(cudaMemcpyAsync(h->etsi_itab, itab, sizeof(itab), cudaMemcpyHostToDevice, st));
+        TB_CUDA(cudaStreamSynchronize(st));      // stack buffers
         h->etsi_taps_fs = fs;
     }
     const double loop = h->etsi_open_loop ? 0.0 : 1.0;
     const float kp = (float)(loop * 0.05 * sps), ki = (float)(loop * 0.0005 * sps);
     int n_seg = 0, seg_syms = 0;
-    etsi_seg_plan(n, sps, &n_seg, &seg_syms);
+    etsi_seg_plan(n, sps, ED_SEG_MIN, &n_seg, &seg_syms);
     const int64_t need = etsi_demod_scratch_bytes(n_streams, n, fs, sym != nullptr);
-    if (scratch && n_seg >= 2 && need > 0 && (size_t)need <= scratch_bytes && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0) {
-        // time-parallel: n_streams * n_seg groups of LS lanes
+    const bool seg_ok = scratch && n_seg >= 2 && need > 0 && (size_t)need <= scratch_bytes && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0;
+    if (seg_ok && !h->etsi_seg_lanes) {
+        // two-stage form: matched filter once per sample, then one thread per (stream, segment) interpolating it
+        etsi_seg_plan(n, sps, ETS_SEG_MIN, &n_seg, &seg_syms);
+        const size_t rows = (size_t)n_streams * n_seg, slots = (size_t)seg_syms + ED_SLACK;
+        float4 *stage = reinterpret_cast<float4 *>(scratch);
+        float2 *sym_stage = sym ? reinterpret_cast<float2 *>(stage + rows * slots) : nullptr;
+        int32_t *seg_count = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(scratch) + rows * slots * (sizeof(float4) + (sym ? sizeof(float2) : 0)));
+        char *after = reinterpret_cast<char *>(scratch) + ((etsi_stage_bytes(n_streams, n_seg, seg_syms, sym != nullptr) + 255) & ~(size_t)255);
+        float2 *y = reinterpret_cast<float2 *>(after);
+        const float *itab = h->etsi_itab;
+        dim3 gmf((unsigned)((n + 1023) / 1024), (unsigned)n_streams);
+        const long ypitch = (n + 1) & ~1L;                     // even: every row of y starts 16-byte aligned
+        etsi_mf_kernel<<<gmf, 256, 0, st>>>(iq, n, stride, taps_dev, y, ypitch);
+        TB_LAUNCH_CHECK(h);
+        etsi_loop_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(y, ypitch, n_streams, n, (float)sps, kp, ki, itab, n_seg, seg_syms,
+                                                                         stage, sym_stage, seg_count);
+        TB_LAUNCH_CHECK(h);
+        etsi_stitch_kernel<<<n_streams, 256, 0, st>>>(n_seg, seg_syms, (float)sps, stage, sym_stage, seg_count, sym, soft, soft_stride, n_soft);
+        TB_LAUNCH_CHECK(h);
+        return TB200_OK;
+    }
+    if (seg_ok) {
+        // time-parallel, eight lanes per segment (TB200_OPT_ETSI_SEG_LANES = 8): the matched filter inside the loop
         const size_t rows = (size_t)n_streams * n_seg, slots = (size_t)seg_syms + ED_SLACK;
         float4 *stage = reinterpret_cast<float4 *>(scratch);
         float2 *sym_stage = sym ? reinterpret_cast<float2 *>(stage + rows * slots) : nullptr;
@@ -552,7 +746,7 @@ int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, l
         etsi_demod_kernel<true, LS><<<(unsigned)((groups + GPC - 1) / GPC), 128, ring_bytes, st>>>(iq, n_streams, n, stride, (float)sps, kp, ki, taps_dev, sym, soft,
                                                                             soft_stride, n_soft, n_seg, seg_syms, stage, sym_stage, seg_count);
         TB_LAUNCH_CHECK(h);
-        etsi_stitch_kernel<<<n_streams, 128, 0, st>>>(n_seg, seg_syms, (float)sps, stage, sym_stage, seg_count, sym, soft, soft_stride, n_soft);
+        etsi_stitch_kernel<<<n_streams, 256, 0, st>>>(n_seg, seg_syms, (float)sps, stage, sym_stage, seg_count, sym, soft, soft_stride, n_soft);
         TB_LAUNCH_CHECK(h);
         return TB200_OK;
     }

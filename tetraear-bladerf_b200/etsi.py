@@ -383,7 +383,7 @@ class EtsiReceiver:
     training-sequence search + block extraction (tb200_etsi_find_bursts) ->
     descramble / de-interleave / Viterbi / CRC of both SCH/HD blocks (tb200_etsi_decode_batch)."""
 
-    def __init__(self, fs, max_streams, max_samples, device=0, max_bursts_per_stream=None, afc=True, segmented=True):
+    def __init__(self, fs, max_streams, max_samples, device=0, max_bursts_per_stream=None, afc=True, segmented=True, seg_lanes=0):
         import torch
         from . import _dev
         self.fs = float(fs)
@@ -408,6 +408,12 @@ class EtsiReceiver:
         # time-parallel demodulator (tb200_etsi_demod_segmented): streams of two segments (1280 symbols) or more are cut
         # into concurrently running segments; shorter ones, or segmented=False, run the sequential loop
         self.segmented = bool(segmented)
+        # form of the time-parallel demodulator: 0 = two stages (matched filter once per sample, then one thread per
+        # segment interpolating its output), 8 = eight lanes per segment with the matched filter inside the loop
+        import os
+        seg_lanes = int(seg_lanes or os.environ.get("TB200_ETSI_SEG_LANES", "0"))     # the environment variable is for A/B timing
+        if seg_lanes:
+            self._h.set_option(_lib.OPT_ETSI_SEG_LANES, seg_lanes)
         self._scratch = None
         self.afc = bool(afc)                      # feed-forward carrier-offset correction (tb200_etsi_afc), |df| < 2250 Hz
         self.theta = _dev.zeros((S,), torch.float32, device)
