@@ -711,7 +711,7 @@ int launch_etsi_demod(tb200_handle h, const float2 *iq, int n_streams, long n, l
     etsi_seg_plan(n, sps, ED_SEG_MIN, &n_seg, &seg_syms);
     const int64_t need = etsi_demod_scratch_bytes(n_streams, n, fs, sym != nullptr);
     const bool seg_ok = scratch && n_seg >= 2 && need > 0 && (size_t)need <= scratch_bytes && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0;
-    if (seg_ok && !h->etsi_seg_lanes) {
+    if (seg_ok && h->etsi_seg_lanes != 8) {
         // two-stage form: matched filter once per sample, then one thread per (stream, segment) interpolating it
         etsi_seg_plan(n, sps, ETS_SEG_MIN, &n_seg, &seg_syms);
         const size_t rows = (size_t)n_streams * n_seg, slots = (size_t)seg_syms + ED_SLACK;
